@@ -1,0 +1,2 @@
+/* handbrake/ports.h -- part of the shim; everything lives in handbrake.h */
+#include "handbrake/handbrake.h"

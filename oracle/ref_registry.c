@@ -1,0 +1,46 @@
+/* oracle/ref_registry.c -- TEST INFRASTRUCTURE.
+ * The part of libhb/common.c:5331-5537 (hb_filter_get / hb_filter_init /
+ * hb_filter_close) that mt_frame_filter.c needs, restricted to the filters the
+ * reference build in oracle/_ref contains. */
+#include "handbrake/handbrake.h"
+
+hb_filter_object_t *hb_filter_get(int filter_id)
+{
+    switch (filter_id)
+    {
+        case HB_FILTER_NLMEANS:     return &hb_filter_nlmeans;
+        case HB_FILTER_COMB_DETECT: return &hb_filter_comb_detect;
+        case HB_FILTER_DECOMB:      return &hb_filter_decomb;
+        case HB_FILTER_LAPSHARP:    return &hb_filter_lapsharp;
+        case HB_FILTER_MT_FRAME:    return &hb_filter_mt_frame;
+        default:                    return NULL;
+    }
+}
+
+/* common.c:5497-5517: lapsharp/unsharp/chroma_smooth are wrapped in mt_frame */
+hb_filter_object_t *hb_filter_init(int filter_id)
+{
+    hb_filter_object_t *src = hb_filter_get(filter_id);
+    if (src == NULL) return NULL;
+    hb_filter_object_t *f = malloc(sizeof(*f));
+    memcpy(f, src, sizeof(*f));
+    if (filter_id == HB_FILTER_LAPSHARP)
+    {
+        hb_filter_object_t *wrapper = malloc(sizeof(*wrapper));
+        memcpy(wrapper, &hb_filter_mt_frame, sizeof(*wrapper));
+        wrapper->sub_filter = f;
+        wrapper->id = filter_id;   /* wrapper takes the wrapped filter's id */
+        return wrapper;
+    }
+    return f;
+}
+
+void hb_filter_close(hb_filter_object_t **pf)
+{
+    if (pf == NULL || *pf == NULL) return;
+    hb_filter_object_t *f = *pf;
+    if (f->sub_filter != NULL) hb_filter_close(&f->sub_filter);
+    if (f->settings != NULL) hb_dict_free(&f->settings);
+    free(f);
+    *pf = NULL;
+}
