@@ -1,0 +1,93 @@
+"""Builds the native pieces in-tree (no JIT cache: the .so files travel with the repo).
+
+  lib/libhbcu.so          CUDA kernels + C-ABI (include/hbcu.h), nvcc, sm_100a only
+  lib/libhbcu_filters.so  libhb-style filter objects in C (gcc) + shim runtime + harness,
+                          linked against libhbcu.so
+
+`python -m handbrake_b200.build` or `build_all()`.
+"""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+REPO = ROOT.parent
+LIB = ROOT / "lib"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                  # the reference is built without FMA contraction
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+CU_SOURCES = ["hbcu_core.cu", "nlmeans.cu"]
+C_SOURCES = ["hb_runtime.c", "hb_harness.c", "hbcu_registry.c", "nlmeans_cuda.c"]
+CFLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wno-unused-function", "-D__LIBHB__", "-pthread"]
+
+
+def _newer(target, deps):
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(str(c) for c in cmd), flush=True)
+    r = subprocess.run([str(c) for c in cmd], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build step failed: " + " ".join(str(c) for c in cmd))
+    if verbose and r.stderr.strip():
+        print(r.stderr)
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def build_cuda(force=False, verbose=False):
+    LIB.mkdir(exist_ok=True)
+    obj_dir = LIB / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    csrc = ROOT / "csrc"
+    headers = list(csrc.glob("*.h")) + list(csrc.glob("*.cuh")) + [REPO / "include" / "hbcu.h"]
+    objs = []
+    for name in CU_SOURCES:
+        src = csrc / name
+        obj = obj_dir / (name + ".o")
+        if force or _newer(obj, [src] + headers):
+            _run([nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", src, "-o", obj], verbose)
+        objs.append(obj)
+    out = LIB / "libhbcu.so"
+    if force or _newer(out, objs):
+        _run([nvcc_path(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xlinker", "--exclude-libs=ALL"], verbose)
+    return out
+
+
+def build_filters(force=False, verbose=False):
+    LIB.mkdir(exist_ok=True)
+    libhb = ROOT / "libhb"
+    srcs = [libhb / s for s in C_SOURCES]
+    headers = list(libhb.glob("**/*.h")) + [REPO / "include" / "hbcu.h"]
+    out = LIB / "libhbcu_filters.so"
+    if force or _newer(out, srcs + headers + [LIB / "libhbcu.so"]):
+        _run(["gcc"] + CFLAGS + ["-shared", "-o", out] + srcs +
+             ["-I", libhb, "-I", REPO / "include", "-L", LIB, "-lhbcu", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"], verbose)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return build_cuda(force, verbose), build_filters(force, verbose)
+
+
+if __name__ == "__main__":
+    a, b = build_all(force="--force" in sys.argv, verbose=True)
+    print("built", a, b)

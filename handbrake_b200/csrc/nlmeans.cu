@@ -1,0 +1,959 @@
+// nlmeans.cu -- NLMeans denoise for sm_100a behind the C-ABI of include/hbcu.h.
+//
+// Replaces (reference /root/reference/libhb):
+//   nlmeans_alloc / nlmeans_border      templates/nlmeans_template.c:20-101   -> pad_mirror_kernel
+//   build_integral_scalar / _sse2       templates/nlmeans_template.c:545-591, nlmeans_x86.c:20-149
+//   nlmeans_plane                       templates/nlmeans_template.c:593-717  -> nlmeans_tiled_kernel
+//   taskset fork/join per frame         nlmeans.c:546-597                      -> stream/event ordering
+//
+// Numeric contract: patch distances are exact integers
+// (the reference's u32 integral image gives the exact n x n sum of squared
+// differences); weights come from the host-computed 128-entry table; the fp32
+// accumulation runs in the reference's displacement order with separate
+// multiply and add (no FMA); the origin term is added in double; the result is
+// truncated and a zero result falls back to the source pixel.  The output is
+// therefore bit-identical to the reference C code.
+//
+// Kernel shape.  The reference materialises a whole-plane integral image per
+// displacement (33 MB at 4K) and streams it through DRAM 17 times.  Here a CTA
+// owns a 128 x TH tile: TMA brings the current and the compare tile (with an
+// 8 pixel halo, mirror border already real data) into shared memory once; each
+// thread marches down a 4-pixel-wide column strip keeping, per displacement,
+// the vertical running sum of horizontal patch-row sums in registers (the
+// n-row history lives in registers too), three horizontal displacements per
+// pass; weight/pixel accumulators live in shared memory.  HBM traffic is the
+// algorithmic minimum: every input tile is read once per output tile.
+#include "hbcu_common.h"
+#include "../../include/hbcu.h"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using hbcu::set_error;
+
+constexpr int kBorder    = 16;    // ((n+2)/2+15)/16*16 for every preset (nlmeans.c:529)
+constexpr int kMaxFrames = 32;    // NLMEANS_FRAMES_MAX
+constexpr int kTileW     = 128;
+constexpr int kHalo      = 8;     // vertical halo of the shared-memory tiles (>= n/2 + r/2)
+// Horizontal halo.  Measured on B200 (tools/tma_test.cu): cp.async.bulk.tensor raises
+// "illegal instruction" unless the box's first byte in global memory is 16-byte aligned,
+// so the tile starts at bordered column X0 (a multiple of 128), i.e. the halo is the
+// whole 16-pixel mirror border.
+constexpr int kHaloX     = kBorder;
+constexpr int kTilePW    = kTileW + 2 * kHaloX;  // 160 elements per tile row
+constexpr int kThreads   = 256;
+constexpr int kGroup     = 3;     // horizontal displacements handled per pass
+
+constexpr int kMaxTiledFrames = 8; // temporal depth the tiled kernel takes (tensor maps travel as kernel parameters)
+
+struct KernelParams
+{
+    const void *planes[kMaxFrames];   // bordered plane base pointers, frame f = current + f
+    int   nf;
+    int   w, h;                       // plane size
+    int   bpitch;                     // bordered plane pitch in elements
+    void *dst;
+    int   dpitch;                     // output pitch in elements
+    int   n_half, r_half;
+    float wfact;
+    int   diff_max;
+    double origin_tune;
+    const float *exptable;            // 128 floats in global memory
+};
+
+// ---------------------------------------------------------------------------
+// pad_mirror_kernel: unbordered plane -> bordered plane with the reference's
+// mirror (img[-1-x] = img[x], img[w+x] = img[w-1-x], then rows mirrored the
+// same way; templates/nlmeans_template.c:20-43).
+// ---------------------------------------------------------------------------
+template <typename PIX>
+__global__ void pad_mirror_kernel(const PIX *__restrict__ src, int spitch, int w, int h,
+                                  PIX *__restrict__ dst, int bpitch, int border)
+{
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y * blockDim.y + threadIdx.y;
+    const int bw = w + 2 * border, bh = h + 2 * border;
+    if (bx >= bw || by >= bh) return;
+    int x = bx - border, y = by - border;
+    if (x < 0) x = -1 - x; else if (x >= w) x = 2 * w - 1 - x;
+    if (y < 0) y = -1 - y; else if (y >= h) y = 2 * h - 1 - y;
+    x = min(max(x, 0), w - 1);   // only reachable when w < border; the reference reads out of bounds there
+    y = min(max(y, 0), h - 1);
+    dst[(size_t)by * bpitch + bx] = src[(size_t)y * spitch + x];
+}
+
+template <typename PIX>
+__global__ void copy_plane_kernel(const PIX *__restrict__ src, int spitch, int w, int h,
+                                  PIX *__restrict__ dst, int dpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w && y < h) dst[(size_t)y * dpitch + x] = src[(size_t)y * spitch + x];
+}
+
+// ---------------------------------------------------------------------------
+// shared numeric pieces
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void add_origin(float &ws, float &ps, double ot, int src)
+{
+    // tmp.weight_sum += origin_tune; tmp.pixel_sum += origin_tune * src   (template :649-650)
+    ws = (float)__dadd_rn((double)ws, ot);
+    ps = (float)__dadd_rn((double)ps, __dmul_rn(ot, (double)src));
+}
+
+__device__ __forceinline__ void add_weighted(float &ws, float &ps, int diff, int diff_max, float wfact,
+                                             const float *lut, int lut_stride, int lut_off, int pix)
+{
+    // if (diff < diff_max) { idx = diff * wfact; w = exptable[idx]; ...}   (template :685-694)
+    if (diff < diff_max)
+    {
+        const int idx = __float2int_rz(__fmul_rn(__int2float_rn(diff), wfact));
+        const float wgt = lut[idx * lut_stride + lut_off];
+        ws = __fadd_rn(ws, wgt);
+        ps = __fadd_rn(ps, __fmul_rn(wgt, __int2float_rn(pix)));
+    }
+}
+
+template <typename PIX>
+__device__ __forceinline__ PIX finish_pixel(float ws, float ps, PIX src)
+{
+    // result = (pixel)(pixel_sum / weight_sum); dst = result ? result : src   (template :706-713)
+    const int v = __float2int_rz(__fdiv_rn(ps, ws));
+    const PIX r = (PIX)v;
+    return r ? r : src;
+}
+
+// ---------------------------------------------------------------------------
+// Generic kernel: one thread per output pixel, reads the bordered planes
+// through L1/L2.  Any patch size / range; used when the tiled kernel's halo
+// (n/2 + r/2 <= 8) does not fit, and as an independent on-device cross check.
+// ---------------------------------------------------------------------------
+template <typename PIX>
+__global__ void nlmeans_generic_kernel(KernelParams p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= p.w || y >= p.h) return;
+    const int bp = p.bpitch;
+    const size_t org = (size_t)kBorder * bp + kBorder;
+    const PIX *src = (const PIX *)p.planes[0] + org;
+    float ws = 0.f, ps = 0.f;
+    for (int f = 0; f < p.nf; f++)
+    {
+        const PIX *cmp = (const PIX *)p.planes[f] + org;
+        for (int dy = -p.r_half; dy <= p.r_half; dy++)
+        {
+            for (int dx = -p.r_half; dx <= p.r_half; dx++)
+            {
+                if (f == 0 && dx == 0 && dy == 0)
+                {
+                    add_origin(ws, ps, p.origin_tune, (int)src[(size_t)y * bp + x]);
+                    continue;
+                }
+                unsigned ssd = 0;
+                for (int j = -p.n_half; j <= p.n_half; j++)
+                {
+                    const PIX *a = src + (ptrdiff_t)(y + j) * bp + x;
+                    const PIX *b = cmp + (ptrdiff_t)(y + j + dy) * bp + x + dx;
+                    for (int k = -p.n_half; k <= p.n_half; k++)
+                    {
+                        const int d = (int)a[k] - (int)b[k];
+                        ssd += (unsigned)(d * d);
+                    }
+                }
+                add_weighted(ws, ps, (int)ssd, p.diff_max, p.wfact, p.exptable, 1, 0,
+                             (int)cmp[(ptrdiff_t)(y + dy) * bp + x + dx]);
+            }
+        }
+    }
+    ((PIX *)p.dst)[(size_t)y * p.dpitch + x] = finish_pixel<PIX>(ws, ps, src[(size_t)y * bp + x]);
+}
+
+// ---------------------------------------------------------------------------
+// TMA / mbarrier helpers (sm_90+ PTX)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Tiled kernel.  CTA = 256 threads = 8 warps; tile = 128 x TH output pixels;
+// warp w owns rows [w*TH/8, (w+1)*TH/8), lane l owns columns [4l, 4l+4).
+// ---------------------------------------------------------------------------
+template <typename PIX, int TH>
+struct TileLayout
+{
+    static constexpr int kRows      = TH + 2 * kHalo;
+    static constexpr int kTileBytes = kRows * kTilePW * (int)sizeof(PIX);
+    static constexpr int kAccBytes  = TH * kTileW * (int)sizeof(float);
+    static constexpr int kLutBytes  = HBCU_NLMEANS_EXPSIZE * 32 * (int)sizeof(float);
+    static constexpr int kOffCur    = 0;
+    static constexpr int kOffCmp    = kOffCur + kTileBytes;
+    static constexpr int kOffWs     = kOffCmp + kTileBytes;
+    static constexpr int kOffPs     = kOffWs + kAccBytes;
+    static constexpr int kOffLut    = kOffPs + kAccBytes;
+    static constexpr int kOffBar    = kOffLut + kLutBytes;
+    static constexpr int kTotal     = kOffBar + 64;
+    static_assert(kTileBytes % 128 == 0, "TMA destination must stay 128-byte aligned");
+};
+
+template <typename PIX, int NH, int TH>
+__device__ __forceinline__ void nlm_group(const PIX *__restrict__ cur, const PIX *__restrict__ cmp,
+                                          float *__restrict__ acc_ws, float *__restrict__ acc_ps,
+                                          const float *__restrict__ lut, const KernelParams &p,
+                                          int seg_y0, int x, int lane, int dy, int dx0, int ng, int origin_g)
+{
+    constexpr int N  = 2 * NH + 1;
+    constexpr int RS = TH / 8;
+    constexpr int NA = 4 + 2 * NH;            // source values a thread needs per row
+    constexpr int NB = NA + kGroup - 1;       // compare values per row (all displacements of the group)
+
+    unsigned V[kGroup][4];
+    unsigned hist[N][kGroup][4];
+#pragma unroll
+    for (int g = 0; g < kGroup; g++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            V[g][i] = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) hist[k][g][i] = 0;
+        }
+
+#pragma unroll 1
+    for (int base = -NH; base < RS + NH; base += N)
+    {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+        {
+            const int yy = base + k;            // row being added, relative to the segment
+            if (yy < RS + NH)
+            {
+                const int ty = seg_y0 + yy + kHalo;
+                const PIX *arow = cur + ty * kTilePW + (x + kHaloX - NH);
+                const PIX *brow = cmp + (ty + dy) * kTilePW + (x + kHaloX - NH + dx0);
+                int a[NA], b[NB];
+#pragma unroll
+                for (int j = 0; j < NA; j++) a[j] = (int)arow[j];
+#pragma unroll
+                for (int j = 0; j < NB; j++) b[j] = (int)brow[j];
+#pragma unroll
+                for (int g = 0; g < kGroup; g++)
+                {
+                    if (g < ng)
+                    {
+                        unsigned c[NA + 1];
+                        c[0] = 0;
+#pragma unroll
+                        for (int j = 0; j < NA; j++)
+                        {
+                            const int d = a[j] - b[j + g];
+                            c[j + 1] = c[j] + (unsigned)(d * d);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                        {
+                            const unsigned hsum = c[i + N] - c[i];
+                            V[g][i] += hsum - hist[k][g][i];
+                            hist[k][g][i] = hsum;
+                        }
+                    }
+                }
+                if (yy >= NH)
+                {
+                    const int oy = seg_y0 + yy - NH;                 // finished output row (tile relative)
+                    float4 ws4 = *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + x);
+                    float4 ps4 = *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + x);
+                    float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+                    float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+                    const PIX *prow = cmp + (oy + kHalo + dy) * kTilePW + (x + kHaloX + dx0);
+#pragma unroll
+                    for (int g = 0; g < kGroup; g++)
+                    {
+                        if (g < ng)
+                        {
+                            if (g == origin_g)
+                            {
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    add_origin(ws[i], ps[i], p.origin_tune, (int)cur[(oy + kHalo) * kTilePW + x + kHaloX + i]);
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    add_weighted(ws[i], ps[i], (int)V[g][i], p.diff_max, p.wfact, lut, 32, lane, (int)prow[g + i]);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + x) = make_float4(ws[0], ws[1], ws[2], ws[3]);
+                    *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + x) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+                }
+            }
+        }
+    }
+}
+
+struct TiledParams
+{
+    KernelParams k;
+    CUtensorMap  maps[kMaxTiledFrames];   // one TMA descriptor per frame of the temporal window
+};
+
+template <typename PIX, int NH, int TH>
+__global__ void __launch_bounds__(kThreads, 1) nlmeans_tiled_kernel(const __grid_constant__ TiledParams tp)
+{
+    const KernelParams &p = tp.k;
+    using L = TileLayout<PIX, TH>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    PIX *cur      = reinterpret_cast<PIX *>(smem + L::kOffCur);
+    PIX *cmp      = reinterpret_cast<PIX *>(smem + L::kOffCmp);
+    float *acc_ws = reinterpret_cast<float *>(smem + L::kOffWs);
+    float *acc_ps = reinterpret_cast<float *>(smem + L::kOffPs);
+    float *lut    = reinterpret_cast<float *>(smem + L::kOffLut);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * kTileW, Y0 = blockIdx.y * TH;
+    // tile element (0,0) is bordered-plane element (X0 + border - haloX, Y0 + border - halo)
+    const int gx = X0 + kBorder - kHaloX, gy = Y0 + kBorder - kHalo;
+
+    if (tid == 0)
+    {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    if (tid == 0)
+    {
+        mbar_expect_tx(bar, L::kTileBytes);
+        tma_load_2d(cur, &tp.maps[0], gx, gy, bar);
+    }
+    // while the tile is in flight: replicate the weight table per bank, clear the accumulators
+    for (int i = tid; i < HBCU_NLMEANS_EXPSIZE * 32; i += kThreads) lut[i] = p.exptable[i >> 5];
+    for (int i = tid; i < TH * kTileW; i += kThreads)
+    {
+        acc_ws[i] = 0.f;
+        acc_ps[i] = 0.f;
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    __syncthreads();
+
+    const int seg_y0 = warp * (TH / 8);
+    const int x = lane * 4;
+    for (int f = 0; f < p.nf; f++)
+    {
+        const PIX *B = cur;
+        if (f > 0)
+        {
+            __syncthreads();            // every warp is done with the previous compare tile
+            if (tid == 0)
+            {
+                fence_proxy_async();
+                mbar_expect_tx(bar, L::kTileBytes);
+                tma_load_2d(cmp, &tp.maps[f], gx, gy, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            B = cmp;
+        }
+        for (int dy = -p.r_half; dy <= p.r_half; dy++)
+        {
+            for (int dx0 = -p.r_half; dx0 <= p.r_half; dx0 += kGroup)
+            {
+                const int ng = min(kGroup, p.r_half - dx0 + 1);
+                const int origin_g = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : -1;
+                nlm_group<PIX, NH, TH>(cur, B, acc_ws, acc_ps, lut, p, seg_y0, x, lane, dy, dx0, ng, origin_g);
+            }
+        }
+    }
+
+    // each warp finishes the rows it owns
+    PIX *dst = reinterpret_cast<PIX *>(p.dst);
+    for (int r = 0; r < TH / 8; r++)
+    {
+        const int oy = seg_y0 + r;
+        const int y = Y0 + oy;
+        if (y >= p.h) break;
+        const float4 ws4 = *reinterpret_cast<const float4 *>(acc_ws + oy * kTileW + x);
+        const float4 ps4 = *reinterpret_cast<const float4 *>(acc_ps + oy * kTileW + x);
+        const float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+        const float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+        PIX o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            o[i] = finish_pixel<PIX>(ws[i], ps[i], cur[(oy + kHalo) * kTilePW + x + kHaloX + i]);
+        PIX *drow = dst + (size_t)y * p.dpitch + X0 + x;
+        if (X0 + x + 3 < p.w)
+        {
+            if (sizeof(PIX) == 1)
+                *reinterpret_cast<uchar4 *>(drow) = make_uchar4(o[0], o[1], o[2], o[3]);
+            else
+                *reinterpret_cast<ushort4 *>(drow) = make_ushort4(o[0], o[1], o[2], o[3]);
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (X0 + x + i < p.w) drow[i] = o[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct PlaneGeom
+{
+    int w, h;            // plane size
+    int bw, bh;          // bordered size
+    int bpitch;          // bordered pitch, elements
+    size_t bbytes;       // bordered plane bytes
+    int rpitch;          // raw staging / output pitch, elements
+    size_t rbytes;
+};
+
+}  // namespace
+
+struct hbcu_nlmeans_s
+{
+    hbcu_nlmeans_config_t cfg;
+    int bps;
+    int impl;
+    PlaneGeom g[3];
+    int ring, out_slots;
+    std::vector<uint8_t *> ring_mem;      // [slot*3+plane] bordered planes
+    std::vector<uint8_t *> raw_mem;       // [slot*3+plane] unbordered staging (H2D target)
+    std::vector<uint8_t *> out_mem;       // [oslot*3+plane]
+    std::vector<int64_t>   ring_index;    // frame index held by each slot
+    std::vector<CUtensorMap> maps;        // [slot*3+plane] TMA descriptors of the bordered planes
+    float *d_exptable;                    // 3 x 128
+    cudaStream_t s_h2d, s_compute, s_d2h;
+    std::vector<cudaEvent_t> ev_upload;   // per ring slot: bordered planes ready
+    std::vector<cudaEvent_t> ev_readers;  // per ring slot: last kernel reading it is done
+    std::vector<cudaEvent_t> ev_kernel;   // per out slot
+    std::vector<cudaEvent_t> ev_d2h;      // per out slot
+    std::vector<int64_t>     out_index;
+    cudaEvent_t ev_mark[2];
+    std::vector<cudaEvent_t> ev_pool;     // event pairs around the main kernels (kernel-only timing)
+    int pool_used;                        // pairs recorded since mark 0
+    int kernel_launches;                  // main-kernel launches since mark 0
+};
+
+namespace {
+
+template <typename PIX, int NH, int TH>
+int launch_tiled(const TiledParams &kp, cudaStream_t st)
+{
+    using L = TileLayout<PIX, TH>;
+    static bool configured = false;
+    if (!configured)
+    {
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_tiled_kernel<PIX, NH, TH>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    dim3 grid((kp.k.w + kTileW - 1) / kTileW, (kp.k.h + TH - 1) / TH);
+    nlmeans_tiled_kernel<PIX, NH, TH><<<grid, kThreads, L::kTotal, st>>>(kp);
+    hbcu::count_launch();
+    return 0;
+}
+
+template <typename PIX, int TH>
+int launch_tiled_nh(const TiledParams &kp, cudaStream_t st)
+{
+    switch (kp.k.n_half)
+    {
+        case 1: return launch_tiled<PIX, 1, TH>(kp, st);
+        case 2: return launch_tiled<PIX, 2, TH>(kp, st);
+        case 3: return launch_tiled<PIX, 3, TH>(kp, st);
+        case 4: return launch_tiled<PIX, 4, TH>(kp, st);
+        default: return 1;
+    }
+}
+
+bool tiled_supported(const KernelParams &kp)
+{
+    return kp.n_half >= 1 && kp.n_half <= 4 && kp.n_half + kp.r_half <= kHalo && kp.nf <= kMaxTiledFrames;
+}
+
+int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, int plane)
+{
+    const bool want_tiled = h->impl != 1 && tiled_supported(kp);
+    if (h->impl == 2 && !want_tiled)
+    {
+        set_error("nlmeans: tiled kernel does not support n=%d r=%d", 2 * kp.n_half + 1, 2 * kp.r_half + 1);
+        return -1;
+    }
+    if (want_tiled)
+    {
+        TiledParams tp;
+        tp.k = kp;
+        for (int f = 0; f < kp.nf; f++) tp.maps[f] = h->maps[slots[f] * 3 + plane];
+        int rc = h->bps == 1 ? launch_tiled_nh<uint8_t, 128>(tp, h->s_compute)
+                             : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
+        if (rc < 0) return rc;
+        if (rc == 0)
+        {
+            HBCU_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
+    dim3 blk(32, 8), grid((kp.w + 31) / 32, (kp.h + 7) / 8);
+    if (h->bps == 1) nlmeans_generic_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(kp);
+    else             nlmeans_generic_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>(kp);
+    hbcu::count_launch();
+    HBCU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int pad_plane(hbcu_nlmeans_s *h, int slot, int pl, const void *src, int spitch_elems, cudaStream_t st)
+{
+    const PlaneGeom &g = h->g[pl];
+    dim3 blk(64, 4), grid((g.bw + 63) / 64, (g.bh + 3) / 4);
+    uint8_t *dst = h->ring_mem[slot * 3 + pl];
+    if (h->bps == 1)
+        pad_mirror_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder);
+    else
+        pad_mirror_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder);
+    hbcu::count_launch();
+    HBCU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot)
+{
+    if (navail < 1)
+    {
+        set_error("nlmeans: navail must be >= 1");
+        return -1;
+    }
+    int max_nf = 1;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const int nf = h->cfg.plane[pl].bypass ? 1 : (navail < h->cfg.plane[pl].nframes ? navail : h->cfg.plane[pl].nframes);
+        if (nf > max_nf) max_nf = nf;
+    }
+    for (int f = 0; f < max_nf; f++)
+    {
+        const int slot = (int)((index + f) % h->ring);
+        if (h->ring_index[slot] != index + f)
+        {
+            set_error("nlmeans: frame %lld is not resident (slot %d holds %lld)", (long long)(index + f), slot,
+                      (long long)h->ring_index[slot]);
+            return -1;
+        }
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_upload[slot], 0));
+    }
+    // the output slot must have been drained by its previous download
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_d2h[oslot], 0));
+
+    const int pair = h->pool_used < (int)h->ev_pool.size() / 2 ? h->pool_used : -1;
+    if (pair >= 0) HBCU_CHECK(cudaEventRecord(h->ev_pool[2 * pair], h->s_compute));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const hbcu_nlmeans_plane_t &pp = h->cfg.plane[pl];
+        const PlaneGeom &g = h->g[pl];
+        uint8_t *dst = h->out_mem[oslot * 3 + pl];
+        const int slot0 = (int)(index % h->ring);
+        if (pp.bypass)
+        {
+            // nlmeans_deborder (template :45-67): plane passes through untouched
+            dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
+            const uint8_t *src = h->ring_mem[slot0 * 3 + pl] + ((size_t)kBorder * g.bpitch + kBorder) * h->bps;
+            if (h->bps == 1) copy_plane_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(src, g.bpitch, g.w, g.h, dst, g.rpitch);
+            else copy_plane_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.bpitch, g.w, g.h, (uint16_t *)dst, g.rpitch);
+            hbcu::count_launch();
+            HBCU_CHECK(cudaGetLastError());
+            continue;
+        }
+        KernelParams kp;
+        memset(&kp, 0, sizeof(kp));
+        int slots[kMaxFrames];
+        kp.nf    = navail < pp.nframes ? navail : pp.nframes;
+        for (int f = 0; f < kp.nf; f++)
+        {
+            const int slot = (int)((index + f) % h->ring);
+            slots[f]     = slot;
+            kp.planes[f] = h->ring_mem[slot * 3 + pl];
+        }
+        kp.w = g.w;
+        kp.h = g.h;
+        kp.bpitch = g.bpitch;
+        kp.dst = dst;
+        kp.dpitch = g.rpitch;
+        kp.n_half = (pp.patch_size - 1) / 2;
+        kp.r_half = (pp.range - 1) / 2;
+        kp.wfact = pp.weight_fact;
+        kp.diff_max = pp.diff_max;
+        kp.origin_tune = pp.origin_tune;
+        kp.exptable = h->d_exptable + pl * HBCU_NLMEANS_EXPSIZE;
+        if (launch_plane(h, kp, slots, pl) != 0) return -1;
+        h->kernel_launches++;
+    }
+    if (pair >= 0)
+    {
+        HBCU_CHECK(cudaEventRecord(h->ev_pool[2 * pair + 1], h->s_compute));
+        h->pool_used++;
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_kernel[oslot], h->s_compute));
+    // frame `index` is read last by this very launch: its slot may be overwritten afterwards
+    HBCU_CHECK(cudaEventRecord(h->ev_readers[(int)(index % h->ring)], h->s_compute));
+    h->out_index[oslot] = index;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
+{
+    if (out == nullptr || cfg == nullptr)
+    {
+        set_error("nlmeans_create: null argument");
+        return -1;
+    }
+    *out = nullptr;
+    if (cfg->width < kBorder || cfg->height < kBorder || cfg->depth < 8 || cfg->depth > 16)
+    {
+        set_error("nlmeans_create: unsupported geometry %dx%d depth %d", cfg->width, cfg->height, cfg->depth);
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+    {
+        cudaGetLastError();
+        set_error("nlmeans_create: CUDA device %d not available (%d devices); there is no CPU fallback", cfg->device, ndev);
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    HBCU_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10)
+    {
+        set_error("nlmeans_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        return -1;
+    }
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const hbcu_nlmeans_plane_t &pp = cfg->plane[pl];
+        if (pp.bypass) continue;
+        if (pp.patch_size < 1 || !(pp.patch_size & 1) || pp.range < 1 || !(pp.range & 1) ||
+            pp.nframes < 1 || pp.nframes > kMaxFrames)
+        {
+            set_error("nlmeans_create: plane %d has invalid patch/range/frames %d/%d/%d", pl, pp.patch_size, pp.range, pp.nframes);
+            return -1;
+        }
+        if (pp.patch_size / 2 + pp.range / 2 > kBorder)
+        {
+            // the reference reads outside its 16-pixel border here (undefined behaviour); refuse instead
+            set_error("nlmeans_create: patch/2 + range/2 = %d exceeds the %d pixel border", pp.patch_size / 2 + pp.range / 2, kBorder);
+            return -1;
+        }
+    }
+
+    hbcu_nlmeans_s *h = new (std::nothrow) hbcu_nlmeans_s();
+    if (h == nullptr)
+    {
+        set_error("nlmeans_create: out of memory");
+        return -1;
+    }
+    h->cfg = *cfg;
+    h->bps = cfg->depth > 8 ? 2 : 1;
+    h->impl = 0;
+    h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
+    h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
+    h->d_exptable = nullptr;
+    h->pool_used = 0;
+    h->kernel_launches = 0;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        PlaneGeom &g = h->g[pl];
+        g.w = pl == 0 ? cfg->width : -((-cfg->width) >> cfg->chroma_shift_w);
+        g.h = pl == 0 ? cfg->height : -((-cfg->height) >> cfg->chroma_shift_h);
+        g.bw = g.w + 2 * kBorder;
+        g.bh = g.h + 2 * kBorder;
+        g.bpitch = (g.bw + 127) / 128 * 128;
+        g.bbytes = (size_t)g.bpitch * g.bh * h->bps;
+        g.rpitch = (g.w + 127) / 128 * 128;
+        g.rbytes = (size_t)g.rpitch * g.h * h->bps;
+    }
+#define CK(expr)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                                    \
+            hbcu_nlmeans_destroy(h);                                                                      \
+            return -1;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    h->ring_mem.assign(h->ring * 3, nullptr);
+    h->raw_mem.assign(h->ring * 3, nullptr);
+    h->out_mem.assign(h->out_slots * 3, nullptr);
+    h->ring_index.assign(h->ring, -1);
+    h->out_index.assign(h->out_slots, -1);
+    h->ev_upload.assign(h->ring, nullptr);
+    h->ev_readers.assign(h->ring, nullptr);
+    h->ev_kernel.assign(h->out_slots, nullptr);
+    h->ev_d2h.assign(h->out_slots, nullptr);
+    h->maps.resize(h->ring * 3);
+    for (int s = 0; s < h->ring; s++)
+    {
+        CK(cudaEventCreateWithFlags(&h->ev_upload[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_readers[s], cudaEventDisableTiming));
+        for (int pl = 0; pl < 3; pl++)
+        {
+            CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
+            CK(cudaMalloc(&h->raw_mem[s * 3 + pl], h->g[pl].rbytes));
+            const int th = h->bps == 1 ? 128 : 96;
+            if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
+                                           (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
+                                           th + 2 * kHalo) != 0)
+            {
+                hbcu_nlmeans_destroy(h);
+                return -1;
+            }
+        }
+    }
+    for (int s = 0; s < h->out_slots; s++)
+    {
+        CK(cudaEventCreateWithFlags(&h->ev_kernel[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_d2h[s], cudaEventDisableTiming));
+        for (int pl = 0; pl < 3; pl++) CK(cudaMalloc(&h->out_mem[s * 3 + pl], h->g[pl].rbytes));
+    }
+    CK(cudaEventCreate(&h->ev_mark[0]));
+    CK(cudaEventCreate(&h->ev_mark[1]));
+    h->ev_pool.assign(2 * 256, nullptr);
+    for (auto &e : h->ev_pool) CK(cudaEventCreate(&e));
+    CK(cudaMalloc(&h->d_exptable, 3 * HBCU_NLMEANS_EXPSIZE * sizeof(float)));
+    for (int pl = 0; pl < 3; pl++)
+        CK(cudaMemcpy(h->d_exptable + pl * HBCU_NLMEANS_EXPSIZE, cfg->plane[pl].exptable,
+                      HBCU_NLMEANS_EXPSIZE * sizeof(float), cudaMemcpyHostToDevice));
+#undef CK
+    *out = h;
+    return 0;
+}
+
+void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
+{
+    if (h == nullptr) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto p : h->ring_mem) if (p) cudaFree(p);
+    for (auto p : h->raw_mem) if (p) cudaFree(p);
+    for (auto p : h->out_mem) if (p) cudaFree(p);
+    for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_readers) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_kernel) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_d2h) if (e) cudaEventDestroy(e);
+    if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
+    if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
+    for (auto e : h->ev_pool) if (e) cudaEventDestroy(e);
+    if (h->d_exptable) cudaFree(h->d_exptable);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const planes[3], const int strides[3], bool from_device)
+{
+    if (h == nullptr || planes == nullptr || strides == nullptr || index < 0)
+    {
+        set_error("nlmeans_upload: bad argument");
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int slot = (int)(index % h->ring);
+    // do not overwrite a slot a queued kernel still reads
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_readers[slot], 0));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const PlaneGeom &g = h->g[pl];
+        if (from_device)
+        {
+            if (pad_plane(h, slot, pl, planes[pl], strides[pl] / h->bps, h->s_h2d) != 0) return -1;
+        }
+        else
+        {
+            HBCU_CHECK(cudaMemcpy2DAsync(h->raw_mem[slot * 3 + pl], (size_t)g.rpitch * h->bps, planes[pl], (size_t)strides[pl],
+                                         (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
+            if (pad_plane(h, slot, pl, h->raw_mem[slot * 3 + pl], g.rpitch, h->s_h2d) != 0) return -1;
+        }
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_upload[slot], h->s_h2d));
+    h->ring_index[slot] = index;
+    return 0;
+}
+
+int hbcu_nlmeans_upload(hbcu_nlmeans_t *h, int64_t index, const void *const planes[3], const int strides[3])
+{
+    return upload_common(h, index, planes, strides, false);
+}
+
+int hbcu_nlmeans_upload_device(hbcu_nlmeans_t *h, int64_t index, const void *const dplanes[3], const int strides[3])
+{
+    return upload_common(h, index, dplanes, strides, true);
+}
+
+int hbcu_nlmeans_wait_upload(hbcu_nlmeans_t *h, int64_t index)
+{
+    if (h == nullptr || index < 0) { set_error("nlmeans_wait_upload: bad argument"); return -1; }
+    const int slot = (int)(index % h->ring);
+    if (h->ring_index[slot] != index) { set_error("nlmeans_wait_upload: frame %lld not resident", (long long)index); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_upload[slot]));
+    return 0;
+}
+
+int hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, void *const planes[3], const int strides[3])
+{
+    if (h == nullptr || planes == nullptr || strides == nullptr || index < 0)
+    {
+        set_error("nlmeans_filter: bad argument");
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = (int)(index % h->out_slots);
+    if (run_filter(h, index, navail, oslot) != 0) return -1;
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_kernel[oslot], 0));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const PlaneGeom &g = h->g[pl];
+        HBCU_CHECK(cudaMemcpy2DAsync(planes[pl], (size_t)strides[pl], h->out_mem[oslot * 3 + pl], (size_t)g.rpitch * h->bps,
+                                     (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_d2h));
+    return 0;
+}
+
+int hbcu_nlmeans_wait(hbcu_nlmeans_t *h, int64_t index)
+{
+    if (h == nullptr || index < 0) { set_error("nlmeans_wait: bad argument"); return -1; }
+    const int oslot = (int)(index % h->out_slots);
+    if (h->out_index[oslot] != index) { set_error("nlmeans_wait: frame %lld is not in flight", (long long)index); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_d2h[oslot]));
+    return 0;
+}
+
+int hbcu_nlmeans_poll(hbcu_nlmeans_t *h, int64_t index)
+{
+    if (h == nullptr || index < 0) { set_error("nlmeans_poll: bad argument"); return -1; }
+    const int oslot = (int)(index % h->out_slots);
+    if (h->out_index[oslot] != index) { set_error("nlmeans_poll: frame %lld is not in flight", (long long)index); return -1; }
+    cudaError_t e = cudaEventQuery(h->ev_d2h[oslot]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    set_error("nlmeans_poll: %s", cudaGetErrorString(e));
+    return -1;
+}
+
+int hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail, void *out_planes[3], int out_strides[3])
+{
+    if (h == nullptr || index < 0) { set_error("nlmeans_filter_device: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = (int)(index % h->out_slots);
+    if (run_filter(h, index, navail, oslot) != 0) return -1;
+    // no download: the slot is free again as soon as the kernel is done
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_compute));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (out_planes) out_planes[pl] = h->out_mem[oslot * 3 + pl];
+        if (out_strides) out_strides[pl] = h->g[pl].rpitch * h->bps;
+    }
+    return 0;
+}
+
+int hbcu_nlmeans_sync(hbcu_nlmeans_t *h)
+{
+    if (h == nullptr) { set_error("nlmeans_sync: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
+    return 0;
+}
+
+int hbcu_nlmeans_set_impl(hbcu_nlmeans_t *h, int impl)
+{
+    if (h == nullptr || impl < 0 || impl > 2) { set_error("nlmeans_set_impl: bad argument"); return -1; }
+    h->impl = impl;
+    return 0;
+}
+
+int hbcu_nlmeans_mark(hbcu_nlmeans_t *h, int which)
+{
+    if (h == nullptr || which < 0 || which > 1) { set_error("nlmeans_mark: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    if (which == 0)
+    {
+        h->pool_used = 0;
+        h->kernel_launches = 0;
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_mark[which], h->s_compute));
+    return 0;
+}
+
+int hbcu_nlmeans_elapsed_ms(hbcu_nlmeans_t *h, float *ms)
+{
+    if (h == nullptr || ms == nullptr) { set_error("nlmeans_elapsed_ms: bad argument"); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_mark[1]));
+    HBCU_CHECK(cudaEventElapsedTime(ms, h->ev_mark[0], h->ev_mark[1]));
+    return 0;
+}
+
+int hbcu_nlmeans_kernel_ms(hbcu_nlmeans_t *h, float *ms, int *launches)
+{
+    if (h == nullptr) { set_error("nlmeans_kernel_ms: null handle"); return -1; }
+    // sums the event pairs recorded around the main kernels since mark 0 (at most 256 filter calls)
+    float total = 0.f;
+    for (int i = 0; i < h->pool_used; i++)
+    {
+        float t = 0.f;
+        HBCU_CHECK(cudaEventSynchronize(h->ev_pool[2 * i + 1]));
+        HBCU_CHECK(cudaEventElapsedTime(&t, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (launches) *launches = h->pool_used;   // filter calls timed (3 plane launches each)
+    return 0;
+}
+
+}  // extern "C"

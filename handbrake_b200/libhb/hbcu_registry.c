@@ -1,0 +1,38 @@
+/* hbcu_registry.c -- how the CUDA filter objects are substituted for the CPU
+ * ones: hb_filter_get() (libhb/common.c:5331-5495) returns the *_cuda object
+ * for the ids this library implements, i.e. exactly the pointer swap a libhb
+ * maintainer would make (cf. replace_filter, platform/macosx/vt_common.c:486-535).
+ */
+#include "handbrake/handbrake.h"
+
+extern hb_filter_object_t hb_filter_nlmeans_cuda;
+
+hb_filter_object_t *hb_filter_get(int filter_id)
+{
+    switch (filter_id)
+    {
+        case HB_FILTER_NLMEANS: return &hb_filter_nlmeans_cuda;
+        default:                return NULL;
+    }
+}
+
+/* common.c:5497-5517 */
+hb_filter_object_t *hb_filter_init(int filter_id)
+{
+    hb_filter_object_t *src = hb_filter_get(filter_id);
+    if (src == NULL) return NULL;
+    hb_filter_object_t *f = malloc(sizeof(*f));
+    if (f == NULL) return NULL;
+    memcpy(f, src, sizeof(*f));
+    return f;
+}
+
+void hb_filter_close(hb_filter_object_t **pf)
+{
+    if (pf == NULL || *pf == NULL) return;
+    hb_filter_object_t *f = *pf;
+    if (f->sub_filter != NULL) hb_filter_close(&f->sub_filter);
+    if (f->settings != NULL) hb_dict_free(&f->settings);
+    free(f);
+    *pf = NULL;
+}

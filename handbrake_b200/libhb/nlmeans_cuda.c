@@ -1,0 +1,415 @@
+/* nlmeans_cuda.c -- hb_filter_nlmeans_cuda: drop-in for hb_filter_nlmeans
+ * (reference libhb/nlmeans.c:202-213) whose per-pixel work runs on a B200
+ * through the C-ABI in include/hbcu.h.  Host side stays C, as in libhb.
+ *
+ * Same plugin surface as the reference: same settings_template and keys, same
+ * cascade / defaults / sanitising of the 19 settings (nlmeans.c:279-343), the
+ * same exp table (nlmeans.c:346-358, computed here on the host with the very
+ * same C expressions and uploaded, never recomputed on the device), same
+ * look-AHEAD temporal window (output t uses inputs t .. t+nframes-1), same
+ * shrinking window at EOF (nlmeans.c:636-640), same output order and props.
+ *
+ * What changes: the taskset of `threads` CPU workers (nlmeans.c:546-597)
+ * becomes CUDA stream dispatch -- frame t is enqueued as soon as frame
+ * t+max_frames-1 has been uploaded, up to `depth` outputs are in flight, and
+ * finished frames are handed downstream in order.  Burst sizes therefore
+ * differ from the reference (which emits `threads` frames at a time); output
+ * order and content do not.  The `threads` setting is accepted and sizes the
+ * number of frames kept in flight.  Prefilter modes (nlmeans.c:72-83) are not
+ * implemented yet: init() fails for prefilter != 0, so libhb drops the filter
+ * instead of silently producing different pictures.
+ */
+#include "handbrake/handbrake.h"
+#include "hbcu.h"
+
+#define NLMEANS_STRENGTH_DEFAULT    6
+#define NLMEANS_ORIGIN_TUNE_DEFAULT 1
+#define NLMEANS_PATCH_SIZE_DEFAULT  7
+#define NLMEANS_RANGE_DEFAULT       3
+#define NLMEANS_FRAMES_DEFAULT      2
+#define NLMEANS_PREFILTER_DEFAULT   0
+#define NLMEANS_FRAMES_MAX          32
+#define NLMEANS_EXPSIZE             HBCU_NLMEANS_EXPSIZE
+
+#define NLM_MAX_INFLIGHT 16
+
+typedef struct
+{
+    int64_t      index;
+    hb_buffer_t *in;      /* input buffer we took ownership of (source of the async upload) */
+    hb_buffer_t *out;     /* output buffer, NULL until the frame has been enqueued */
+} nlm_pending_t;
+
+struct hb_filter_private_s
+{
+    int depth;
+    int bps;
+
+    double strength[3];
+    double origin_tune[3];
+    int    patch_size[3];
+    int    range[3];
+    int    nframes[3];
+    int    prefilter[3];
+    int    threads;
+    int    max_frames;
+
+    hbcu_nlmeans_t *gpu;
+    int             inflight_max;   /* outputs in flight on the device */
+    int             ring;
+
+    /* frames received but not yet emitted, oldest first: [head, head+count) modulo cap */
+    nlm_pending_t  *pending;
+    int             cap, head, count;
+    int64_t         next_in;        /* index of the next input frame  */
+    int64_t         next_enqueue;   /* next frame to hand to the GPU */
+
+    hb_filter_init_t input;
+    hb_filter_init_t output;
+};
+
+static int  nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init);
+static int  nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, hb_buffer_t **buf_out);
+static void nlmeans_cuda_close(hb_filter_object_t *filter);
+
+static const char nlmeans_template[] =
+    "y-strength=^"HB_FLOAT_REG"$:y-origin-tune=^"HB_FLOAT_REG"$:"
+    "y-patch-size=^"HB_INT_REG"$:y-range=^"HB_INT_REG"$:"
+    "y-frame-count=^"HB_INT_REG"$:y-prefilter=^"HB_INT_REG"$:"
+    "cb-strength=^"HB_FLOAT_REG"$:cb-origin-tune=^"HB_FLOAT_REG"$:"
+    "cb-patch-size=^"HB_INT_REG"$:cb-range=^"HB_INT_REG"$:"
+    "cb-frame-count=^"HB_INT_REG"$:cb-prefilter=^"HB_INT_REG"$:"
+    "cr-strength=^"HB_FLOAT_REG"$:cr-origin-tune=^"HB_FLOAT_REG"$:"
+    "cr-patch-size=^"HB_INT_REG"$:cr-range=^"HB_INT_REG"$:"
+    "cr-frame-count=^"HB_INT_REG"$:cr-prefilter=^"HB_INT_REG"$:"
+    "threads=^"HB_INT_REG"$";
+
+hb_filter_object_t hb_filter_nlmeans_cuda =
+{
+    .id                = HB_FILTER_NLMEANS,
+    .enforce_order     = 1,
+    .name              = "Denoise (nlmeans, CUDA sm_100a)",
+    .short_name        = "nlmeans",
+    .settings          = NULL,
+    .init              = nlmeans_cuda_init,
+    .work              = nlmeans_cuda_work,
+    .close             = nlmeans_cuda_close,
+    .settings_template = nlmeans_template,
+};
+
+static nlm_pending_t *pending_at(hb_filter_private_t *pv, int i)
+{
+    return &pv->pending[(pv->head + i) % pv->cap];
+}
+
+static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
+{
+    static const char *const prefix[3] = { "y", "cb", "cr" };
+    hb_filter_private_t *pv = calloc(1, sizeof(*pv));
+    if (pv == NULL)
+    {
+        hb_error("nlmeans(cuda): calloc failed");
+        return -1;
+    }
+    filter->private_data = pv;
+    pv->input = *init;
+
+    const AVPixFmtDescriptor *desc = av_pix_fmt_desc_get(init->pix_fmt);
+    if (desc == NULL || desc->nb_components < 3)
+    {
+        hb_error("nlmeans(cuda): unsupported pixel format %d", init->pix_fmt);
+        goto fail;
+    }
+    pv->depth = desc->comp[0].depth;
+    pv->bps   = pv->depth > 8 ? 2 : 1;
+
+    for (int c = 0; c < 3; c++)
+    {
+        pv->strength[c] = pv->origin_tune[c] = -1;
+        pv->patch_size[c] = pv->range[c] = pv->nframes[c] = pv->prefilter[c] = -1;
+    }
+    pv->threads = -1;
+
+    if (filter->settings != NULL)
+    {
+        hb_dict_t *dict = filter->settings;
+        char key[32];
+        for (int c = 0; c < 3; c++)
+        {
+            snprintf(key, sizeof(key), "%s-strength", prefix[c]);    hb_dict_extract_double(&pv->strength[c], dict, key);
+            snprintf(key, sizeof(key), "%s-origin-tune", prefix[c]); hb_dict_extract_double(&pv->origin_tune[c], dict, key);
+            snprintf(key, sizeof(key), "%s-patch-size", prefix[c]);  hb_dict_extract_int(&pv->patch_size[c], dict, key);
+            snprintf(key, sizeof(key), "%s-range", prefix[c]);       hb_dict_extract_int(&pv->range[c], dict, key);
+            snprintf(key, sizeof(key), "%s-frame-count", prefix[c]); hb_dict_extract_int(&pv->nframes[c], dict, key);
+            snprintf(key, sizeof(key), "%s-prefilter", prefix[c]);   hb_dict_extract_int(&pv->prefilter[c], dict, key);
+        }
+        hb_dict_extract_int(&pv->threads, dict, "threads");
+    }
+
+    /* Cr inherits Cb, Cb inherits Y, Y takes the defaults (nlmeans.c:306-326) */
+    for (int c = 1; c < 3; c++)
+    {
+        if (pv->strength[c]    == -1) pv->strength[c]    = pv->strength[c-1];
+        if (pv->origin_tune[c] == -1) pv->origin_tune[c] = pv->origin_tune[c-1];
+        if (pv->patch_size[c]  == -1) pv->patch_size[c]  = pv->patch_size[c-1];
+        if (pv->range[c]       == -1) pv->range[c]       = pv->range[c-1];
+        if (pv->nframes[c]     == -1) pv->nframes[c]     = pv->nframes[c-1];
+        if (pv->prefilter[c]   == -1) pv->prefilter[c]   = pv->prefilter[c-1];
+    }
+
+    hbcu_nlmeans_config_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    for (int c = 0; c < 3; c++)
+    {
+        if (pv->strength[c]    == -1) pv->strength[c]    = NLMEANS_STRENGTH_DEFAULT;
+        if (pv->origin_tune[c] == -1) pv->origin_tune[c] = NLMEANS_ORIGIN_TUNE_DEFAULT;
+        if (pv->patch_size[c]  == -1) pv->patch_size[c]  = NLMEANS_PATCH_SIZE_DEFAULT;
+        if (pv->range[c]       == -1) pv->range[c]       = NLMEANS_RANGE_DEFAULT;
+        if (pv->nframes[c]     == -1) pv->nframes[c]     = NLMEANS_FRAMES_DEFAULT;
+        if (pv->prefilter[c]   == -1) pv->prefilter[c]   = NLMEANS_PREFILTER_DEFAULT;
+
+        /* sanitise (nlmeans.c:328-338) */
+        if (pv->strength[c] < 0)        pv->strength[c] = 0;
+        if (pv->origin_tune[c] < 0.01)  pv->origin_tune[c] = 0.01;
+        if (pv->origin_tune[c] > 1)     pv->origin_tune[c] = 1;
+        if (pv->patch_size[c] % 2 == 0) pv->patch_size[c]--;
+        if (pv->patch_size[c] < 1)      pv->patch_size[c] = 1;
+        if (pv->range[c] % 2 == 0)      pv->range[c]--;
+        if (pv->range[c] < 1)           pv->range[c] = 1;
+        if (pv->nframes[c] < 1)         pv->nframes[c] = 1;
+        if (pv->nframes[c] > NLMEANS_FRAMES_MAX) pv->nframes[c] = NLMEANS_FRAMES_MAX;
+        if (pv->prefilter[c] < 0)       pv->prefilter[c] = 0;
+
+        if (pv->max_frames < pv->nframes[c]) pv->max_frames = pv->nframes[c];
+
+        if (pv->prefilter[c] != 0)
+        {
+            hb_error("nlmeans(cuda): prefilter mode %d is not implemented on the GPU path", pv->prefilter[c]);
+            goto fail;
+        }
+
+        /* strength scales with bit depth (nlmeans.c:343) */
+        pv->strength[c] *= pv->depth > 8 ? (pv->depth - 8) * (pv->depth - 8) : 1;
+
+        /* exp table: these expressions are the numeric contract (nlmeans.c:346-358);
+         * evaluated on the host exactly as written there */
+        hbcu_nlmeans_plane_t *pp = &cfg.plane[c];
+        const float weight_factor        = 1.0/pv->patch_size[c]/pv->patch_size[c] / (pv->strength[c] * pv->strength[c]);
+        const float min_weight_in_table  = 0.0005;
+        const float stretch              = NLMEANS_EXPSIZE / (-log(min_weight_in_table));
+        pp->weight_fact                  = weight_factor * stretch;
+        pp->diff_max                     = NLMEANS_EXPSIZE / pp->weight_fact;
+        for (int i = 0; i < NLMEANS_EXPSIZE; i++)
+        {
+            pp->exptable[i] = exp(-i/stretch);
+        }
+        pp->exptable[NLMEANS_EXPSIZE-1] = 0;
+
+        pp->patch_size  = pv->patch_size[c];
+        pp->range       = pv->range[c];
+        pp->nframes     = pv->nframes[c];
+        pp->origin_tune = pv->origin_tune[c];
+        pp->bypass      = pv->strength[c] == 0;   /* nlmeans.c:493-499 */
+    }
+
+    /* `threads` CPU workers -> that many output frames in flight on the streams */
+    pv->inflight_max = pv->threads < 1 ? 4 : pv->threads;
+    if (pv->inflight_max > NLM_MAX_INFLIGHT) pv->inflight_max = NLM_MAX_INFLIGHT;
+    pv->ring = pv->max_frames + pv->inflight_max + 1;
+    pv->cap  = pv->ring + 2;
+    pv->pending = calloc(pv->cap, sizeof(*pv->pending));
+    if (pv->pending == NULL)
+    {
+        hb_error("nlmeans(cuda): calloc failed");
+        goto fail;
+    }
+
+    cfg.width          = init->geometry.width;
+    cfg.height         = init->geometry.height;
+    cfg.depth          = pv->depth;
+    cfg.chroma_shift_w = desc->log2_chroma_w;
+    cfg.chroma_shift_h = desc->log2_chroma_h;
+    cfg.device         = 0;
+    const char *dev_env = getenv("HBCU_DEVICE");
+    if (dev_env != NULL) cfg.device = atoi(dev_env);
+    cfg.ring_frames    = pv->ring;
+    cfg.out_slots      = pv->inflight_max;
+    if (hbcu_nlmeans_create(&pv->gpu, &cfg) != 0)
+    {
+        /* no CPU fallback: the job continues without the filter (work.c:1861-1868) */
+        hb_error("nlmeans(cuda): %s", hbcu_last_error());
+        goto fail;
+    }
+    hb_log("NLMeans (CUDA) on device %d, %d frames in flight", cfg.device, pv->inflight_max);
+
+    pv->output = *init;
+    return 0;
+
+fail:
+    free(pv->pending);
+    free(pv);
+    filter->private_data = NULL;
+    return -1;
+}
+
+static void nlmeans_cuda_close(hb_filter_object_t *filter)
+{
+    hb_filter_private_t *pv = filter->private_data;
+    if (pv == NULL) return;
+    if (pv->gpu != NULL) hbcu_nlmeans_destroy(pv->gpu);   /* synchronises the device first */
+    for (int i = 0; i < pv->count; i++)
+    {
+        nlm_pending_t *p = pending_at(pv, i);
+        hb_buffer_close(&p->in);
+        hb_buffer_close(&p->out);
+    }
+    free(pv->pending);
+    free(pv);
+    filter->private_data = NULL;
+}
+
+/* hand frame `index` to the GPU: kernels + download into a fresh output buffer */
+static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
+{
+    hb_buffer_t *out = hb_frame_buffer_init(pv->output.pix_fmt, pv->output.geometry.width, pv->output.geometry.height);
+    if (out == NULL) return -1;
+    out->f.color_prim      = pv->output.color_prim;
+    out->f.color_transfer  = pv->output.color_transfer;
+    out->f.color_matrix    = pv->output.color_matrix;
+    out->f.color_range     = pv->output.color_range;
+    out->f.chroma_location = pv->output.chroma_location;
+    hb_buffer_copy_props(out, p->in);                      /* nlmeans.c:519 */
+
+    void *planes[3];
+    int   strides[3];
+    for (int c = 0; c < 3; c++)
+    {
+        planes[c]  = out->plane[c].data;
+        strides[c] = out->plane[c].stride;
+    }
+    if (hbcu_nlmeans_filter(pv->gpu, p->index, navail, planes, strides) != 0)
+    {
+        hb_error("nlmeans(cuda): %s", hbcu_last_error());
+        hb_buffer_close(&out);
+        return -1;
+    }
+    p->out = out;
+    return 0;
+}
+
+/* enqueue every frame whose look-ahead window is complete (or, at EOF, whatever is left) */
+static int enqueue_ready(hb_filter_private_t *pv, int flushing)
+{
+    while (pv->next_enqueue < pv->next_in)
+    {
+        const int64_t t = pv->next_enqueue;
+        const int avail = (int)(pv->next_in - t);
+        if (!flushing && avail < pv->max_frames) break;
+        nlm_pending_t *oldest = pending_at(pv, 0);
+        const int inflight = (int)(t - oldest->index);       /* enqueued but not yet emitted */
+        if (inflight >= pv->inflight_max) break;
+        nlm_pending_t *p = pending_at(pv, (int)(t - oldest->index));
+        if (enqueue_frame(pv, p, avail) != 0) return -1;
+        pv->next_enqueue++;
+    }
+    return 0;
+}
+
+/* move finished frames (oldest first) to the list; block == wait for the oldest in flight */
+static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int block_one, int block_all)
+{
+    while (pv->count > 0)
+    {
+        nlm_pending_t *p = pending_at(pv, 0);
+        if (p->out == NULL) break;                           /* not enqueued yet */
+        if (block_all || block_one)
+        {
+            if (hbcu_nlmeans_wait(pv->gpu, p->index) != 0) goto gpu_error;
+            block_one = 0;
+        }
+        else
+        {
+            int done = hbcu_nlmeans_poll(pv->gpu, p->index);
+            if (done < 0) goto gpu_error;
+            if (done == 0) break;
+        }
+        hb_buffer_list_append(list, p->out);
+        p->out = NULL;
+        hb_buffer_close(&p->in);
+        pv->head = (pv->head + 1) % pv->cap;
+        pv->count--;
+    }
+    return 0;
+
+gpu_error:
+    hb_error("nlmeans(cuda): %s", hbcu_last_error());
+    return -1;
+}
+
+static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, hb_buffer_t **buf_out)
+{
+    hb_filter_private_t *pv = filter->private_data;
+    hb_buffer_t *in = *buf_in;
+    hb_buffer_list_t list;
+    hb_buffer_list_clear(&list);
+
+    if (in->s.flags & HB_BUF_FLAG_EOF)
+    {
+        /* flush with the shrinking window (nlmeans.c:599-664), then forward EOF */
+        while (pv->count > 0)
+        {
+            if (enqueue_ready(pv, 1) != 0 || harvest(pv, &list, 1, 0) != 0)
+            {
+                hb_buffer_list_close(&list);
+                return HB_FILTER_FAILED;
+            }
+        }
+        hb_buffer_list_append(&list, in);
+        *buf_out = hb_buffer_list_clear(&list);
+        *buf_in  = NULL;
+        return HB_FILTER_DONE;
+    }
+
+    /* nlmeans_add_frame: the frame goes to the device; we keep the buffer until its
+     * output is emitted because the upload reads it asynchronously */
+    const void *planes[3];
+    int strides[3];
+    for (int c = 0; c < 3; c++)
+    {
+        planes[c]  = in->plane[c].data;
+        strides[c] = in->plane[c].stride;
+    }
+    if (pv->count == pv->cap)
+    {
+        hb_error("nlmeans(cuda): internal queue overflow");
+        return HB_FILTER_FAILED;
+    }
+    if (hbcu_nlmeans_upload(pv->gpu, pv->next_in, planes, strides) != 0)
+    {
+        hb_error("nlmeans(cuda): %s", hbcu_last_error());
+        return HB_FILTER_FAILED;
+    }
+    nlm_pending_t *p = pending_at(pv, pv->count);
+    p->index = pv->next_in;
+    p->in    = in;
+    p->out   = NULL;
+    pv->count++;
+    pv->next_in++;
+    *buf_in = NULL;
+
+    if (enqueue_ready(pv, 0) != 0) return HB_FILTER_FAILED;
+    /* keep the device queue bounded: once `inflight_max` outputs are pending, wait for the oldest */
+    const int enq_inflight = (int)(pv->next_enqueue - pending_at(pv, 0)->index);
+    if (harvest(pv, &list, enq_inflight >= pv->inflight_max, 0) != 0)
+    {
+        hb_buffer_list_close(&list);
+        return HB_FILTER_FAILED;
+    }
+    if (enqueue_ready(pv, 0) != 0)
+    {
+        hb_buffer_list_close(&list);
+        return HB_FILTER_FAILED;
+    }
+    *buf_out = hb_buffer_list_clear(&list);
+    return HB_FILTER_OK;
+}

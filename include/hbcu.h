@@ -1,0 +1,127 @@
+/* hbcu.h -- C-ABI of the B200 (sm_100a) implementation of libhb's per-pixel
+ * video-filter hot path.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * This is the boundary a libhb maintainer binds: the filter objects in
+ * handbrake_b200/libhb/ (nlmeans_cuda.c, ...) (drop-ins for hb_filter_nlmeans, ...) are
+ * ordinary C that call ONLY the functions below.  Each group names the
+ * reference code it replaces (paths relative to /root/reference/libhb).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     hbcu_last_error() then describes the failure (thread-local string).
+ *   - "planes"/"strides": arrays of 3 host pointers / byte strides in
+ *     hb_buffer_t.plane[] order (Y, Cb, Cr).  Host memory may be pageable;
+ *     page-locked memory from hbcu_host_alloc() makes the copies asynchronous.
+ *   - nothing here falls back to the CPU: with no usable sm_100 device the
+ *     create functions fail (=> filter init() returns non-zero, and libhb drops
+ *     the filter exactly as for any failing init, work.c:1861-1868).
+ */
+#ifndef HBCU_H
+#define HBCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBCU_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------- */
+/* runtime                                                                    */
+/* ------------------------------------------------------------------------- */
+int          hbcu_abi_version(void);
+const char * hbcu_last_error(void);
+/* number of CUDA devices visible (0 when no driver / no GPU) */
+int          hbcu_device_count(void);
+/* page-locked host memory: the "pinned backing" of hb_buffer_t
+ * (replaces av_malloc in hb_buffer_init_internal, fifo.c:358-441).  Freed blocks
+ * are kept in power-of-two size pools like libhb's buffer pools (fifo.c:70-135)
+ * because cudaHostAlloc costs milliseconds; hbcu_host_trim() releases them. */
+void *       hbcu_host_alloc(size_t bytes);
+void         hbcu_host_free(void *p);
+void         hbcu_host_trim(void);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t     hbcu_kernel_launches(void);
+
+/* ------------------------------------------------------------------------- */
+/* NLMeans      replaces nlmeans.c:464-664 + templates/nlmeans_template.c       */
+/*              (nlmeans_alloc/border, build_integral_*, nlmeans_plane) and    */
+/*              nlmeans_x86.c; taskset fork/join becomes stream ordering       */
+/* ------------------------------------------------------------------------- */
+#define HBCU_NLMEANS_EXPSIZE 128   /* NLMEANS_EXPSIZE, nlmeans.c:88 */
+
+typedef struct hbcu_nlmeans_plane_s
+{
+    int    patch_size;      /* n, odd >= 1            (pv->patch_size[c]) */
+    int    range;           /* r, odd >= 1            (pv->range[c])      */
+    int    nframes;         /* temporal depth 1..32   (pv->nframes[c])    */
+    int    bypass;          /* strength == 0: plane is copied (nlmeans.c:493-499) */
+    double origin_tune;     /* pv->origin_tune[c] */
+    float  weight_fact;     /* pv->weight_fact_table[c]  (nlmeans.c:352) */
+    int    diff_max;        /* pv->diff_max[c]           (nlmeans.c:353) */
+    float  exptable[HBCU_NLMEANS_EXPSIZE];   /* pv->exptable[c], computed by the host exactly as nlmeans.c:354-358 */
+} hbcu_nlmeans_plane_t;
+
+typedef struct hbcu_nlmeans_config_s
+{
+    int width, height;          /* luma geometry */
+    int depth;                  /* bits per sample: 8 -> uint8 planes, 9..16 -> uint16 planes */
+    int chroma_shift_w;         /* log2 chroma subsampling (1,1 for yuv420p) */
+    int chroma_shift_h;
+    int device;                 /* CUDA device ordinal */
+    int ring_frames;            /* input frames kept on the device (>= max nframes + in-flight outputs) */
+    int out_slots;              /* device output frames in flight */
+    hbcu_nlmeans_plane_t plane[3];
+} hbcu_nlmeans_config_t;
+
+typedef struct hbcu_nlmeans_s hbcu_nlmeans_t;
+
+int  hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg);
+void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h);
+
+/* nlmeans_add_frame (nlmeans.c:524-544): copy frame `index` to the device and
+ * build its mirror-bordered planes.  Asynchronous when the source is pinned;
+ * the source may be reused once hbcu_nlmeans_wait_upload(index) returned. */
+int  hbcu_nlmeans_upload(hbcu_nlmeans_t *h, int64_t index,
+                         const void *const planes[3], const int strides[3]);
+int  hbcu_nlmeans_wait_upload(hbcu_nlmeans_t *h, int64_t index);
+
+/* nlmeans_filter_work / nlmeans_plane (nlmeans.c:464-522): denoise frame
+ * `index` from frames index .. index+navail-1 (navail is clamped per plane to
+ * its nframes; the EOF flush passes the shrinking count, nlmeans.c:636-640)
+ * and copy the result to the host planes.  Asynchronous; hbcu_nlmeans_wait()
+ * blocks until the host planes hold the result. */
+int  hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail,
+                         void *const planes[3], const int strides[3]);
+int  hbcu_nlmeans_wait(hbcu_nlmeans_t *h, int64_t index);
+/* non-blocking: 1 = the host planes of frame `index` are complete, 0 = still in flight, <0 = error */
+int  hbcu_nlmeans_poll(hbcu_nlmeans_t *h, int64_t index);
+
+/* device-resident entry points (frames never leave HBM): used by chained
+ * filters and by bench.py's kernel-only arm.
+ *   upload_device : src = device pointers to unbordered planes
+ *   filter_device : result stays in the handle's output slot; pointers to it
+ *                   are returned through out_planes/out_strides (may be NULL) */
+int  hbcu_nlmeans_upload_device(hbcu_nlmeans_t *h, int64_t index,
+                                const void *const dplanes[3], const int strides[3]);
+int  hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail,
+                                void *out_planes[3], int out_strides[3]);
+int  hbcu_nlmeans_sync(hbcu_nlmeans_t *h);
+/* implementation selector for tests: 0 = auto (tiled sm_100a kernel when the
+ * parameters fit, generic otherwise), 1 = force generic, 2 = force tiled */
+int  hbcu_nlmeans_set_impl(hbcu_nlmeans_t *h, int impl);
+
+/* CUDA-event timing on the handle's compute stream (bench.py):
+ * mark 0 = start, mark 1 = stop; elapsed_ms synchronises on mark 1. */
+int  hbcu_nlmeans_mark(hbcu_nlmeans_t *h, int which);
+int  hbcu_nlmeans_elapsed_ms(hbcu_nlmeans_t *h, float *ms);
+/* device time spent in the main kernel alone between the two marks */
+int  hbcu_nlmeans_kernel_ms(hbcu_nlmeans_t *h, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HBCU_H */

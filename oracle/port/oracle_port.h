@@ -1,0 +1,49 @@
+/* oracle_port.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C restatement of the reference's per-pixel algorithms for the hot path
+ * (HandBrake libhb, /root/reference/libhb), written independently of the
+ * reference's data flow (no integral images, no bordered copies) so that it
+ * checks the *mathematics*: a mistake shared by the CUDA path and this port is
+ * unlikely, and both are pinned against the compiled reference itself
+ * (oracle/_ref/libhbref.so, tests/test_oracle.py) plus the golden digests in
+ * tests/golden/.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg may load this library.
+ *
+ * Frames are packed planar arrays (Y, U, V; row pitch = width * bps).
+ */
+#ifndef ORACLE_PORT_H
+#define ORACLE_PORT_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct
+{
+    double strength;      /* as given in the settings (before bit-depth scaling) */
+    double origin_tune;
+    int    patch_size;
+    int    range;
+    int    nframes;
+} oracle_nlmeans_plane_params_t;
+
+/* nlmeans.c:343-358: derived weight table for one plane */
+void oracle_nlmeans_table(double strength, int patch_size, int depth,
+                          float *weight_fact, int *diff_max, float exptable[128]);
+
+/* templates/nlmeans_template.c:593-717 for one plane; frames[f] = current + f following,
+ * each w*h samples, tightly packed; sample type uint8_t (depth 8) or uint16_t. */
+void oracle_nlmeans_plane(const void *const *frames, int nframes, int w, int h, int depth,
+                          const oracle_nlmeans_plane_params_t *pp, void *dst);
+
+/* nlmeans.c:464-694 for a whole yuv420p clip: n_in packed frames in, n_in out
+ * (look-ahead window, shrinking at EOF). */
+int oracle_nlmeans_clip(const uint8_t *in, int n_in, int width, int height, int depth,
+                        const oracle_nlmeans_plane_params_t pp[3], uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

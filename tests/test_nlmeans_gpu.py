@@ -1,0 +1,83 @@
+"""GPU parity: hb_filter_nlmeans_cuda vs the reference's hb_filter_nlmeans (bit-exact)."""
+import numpy as np
+import pytest
+
+from handbrake_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FMT8, FMT10 = synth.PIX_FMT_YUV420P, synth.PIX_FMT_YUV420P10
+
+
+def run_both(ref, cuda, settings, clip, fmt, w, h, ref_threads=2):
+    r = ref.run("hb_filter_nlmeans", settings + f":threads={ref_threads}", clip, fmt, w, h)
+    g = cuda.run("hb_filter_nlmeans_cuda", settings, clip, fmt, w, h)
+    return r, g
+
+
+def assert_same(r, g):
+    assert g.saw_eof and r.saw_eof
+    assert g.frames.shape == r.frames.shape
+    assert np.array_equal(g.start, r.start)
+    if not np.array_equal(g.frames, r.frames):
+        d = np.abs(g.frames.astype(np.int32) - r.frames.astype(np.int32))
+        bad = np.argwhere(d.max(axis=1) > 0).ravel()
+        raise AssertionError(f"mismatch: max abs {d.max()}, {np.count_nonzero(d)} bytes differ, frames {bad[:8]}")
+
+
+@pytest.mark.parametrize("strength", [3, 6, 10])
+def test_config1_640x360_presets(ref, cuda_filters, strength):
+    """BASELINE config 1 (light) + medium/strong on the same clip: 10 frames, bit-exact."""
+    w, h = 640, 360
+    clip = synth.progressive_clip(FMT8, w, h, 10)
+    r, g = run_both(ref, cuda_filters, f"y-strength={strength}", clip, FMT8, w, h)
+    assert_same(r, g)
+    assert cuda_filters.buffers_alive() == 0
+
+
+def test_ragged_geometry_and_chroma_params(ref, cuda_filters):
+    """width/height not multiples of the tile, odd chroma size, per-plane parameters"""
+    w, h = 333, 211
+    clip = synth.progressive_clip(FMT8, w, h, 6, seed=7)
+    s = "y-strength=6:y-origin-tune=0.8:y-patch-size=7:y-range=3:y-frame-count=2:cb-strength=4:cb-patch-size=5:cb-range=5:cb-frame-count=3"
+    r, g = run_both(ref, cuda_filters, s, clip, FMT8, w, h)
+    assert_same(r, g)
+
+
+def test_10bit(ref, cuda_filters):
+    w, h = 320, 192
+    clip = synth.progressive_clip(FMT10, w, h, 5)
+    r, g = run_both(ref, cuda_filters, "y-strength=6", clip, FMT10, w, h)
+    assert_same(r, g)
+
+
+def test_generic_kernel_matches(ref, cuda_filters):
+    """patch 11 does not fit the tiled kernel (n/2 <= 4): exercises the generic kernel"""
+    w, h = 200, 120
+    clip = synth.progressive_clip(FMT8, w, h, 4)
+    r, g = run_both(ref, cuda_filters, "y-strength=6:y-patch-size=11:y-range=5", clip, FMT8, w, h)
+    assert_same(r, g)
+
+
+def test_strength_zero_bypass_and_single_frame(ref, cuda_filters):
+    w, h = 160, 96
+    clip = synth.progressive_clip(FMT8, w, h, 3)
+    r, g = run_both(ref, cuda_filters, "y-strength=0:cb-strength=5:y-frame-count=1", clip, FMT8, w, h)
+    assert_same(r, g)
+    assert np.array_equal(g.frames[:, : w * h], clip[:, : w * h])   # luma untouched
+
+
+def test_fewer_frames_than_window(ref, cuda_filters):
+    """EOF before the look-ahead window ever fills: shrinking window only (nlmeans.c:636-640)"""
+    w, h = 160, 96
+    clip = synth.progressive_clip(FMT8, w, h, 2)
+    r, g = run_both(ref, cuda_filters, "y-strength=6:y-frame-count=4", clip, FMT8, w, h)
+    assert_same(r, g)
+
+
+def test_prefilter_is_refused(cuda_filters):
+    w, h = 160, 96
+    clip = synth.progressive_clip(FMT8, w, h, 2)
+    g = cuda_filters.run("hb_filter_nlmeans_cuda", "y-strength=6:y-prefilter=1", clip, FMT8, w, h)
+    assert g.init_failed == 1          # filter dropped, frames pass through untouched (work.c:1861-1868)
+    assert np.array_equal(g.frames, clip)
