@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
 ]
 CU_SOURCES = ["hbcu_core.cu", "nlmeans.cu"]
-C_SOURCES = ["hb_runtime.c", "hb_harness.c", "hbcu_registry.c", "nlmeans_cuda.c"]
+C_SOURCES = ["hb_runtime.c", "hb_harness.c", "hb_bench.c", "hbcu_registry.c", "hbcu_pinned.c", "nlmeans_cuda.c"]
 CFLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wno-unused-function", "-D__LIBHB__", "-pthread"]
 
 

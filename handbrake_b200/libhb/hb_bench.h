@@ -1,0 +1,22 @@
+/* hb_bench.h -- see hb_bench.c */
+#ifndef HBCU_HB_BENCH_H
+#define HBCU_HB_BENCH_H
+#include "handbrake/handbrake.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct hb_bench_s hb_bench_t;
+typedef struct
+{
+    double   seconds;      /* wall clock, first work() call to last output consumed */
+    int64_t  frames_out;
+    int64_t  bytes_in;     /* host bytes handed to work() */
+    int64_t  bytes_out;    /* host bytes received from work() */
+    uint64_t checksum;
+} hb_bench_stats_t;
+hb_bench_t *hb_bench_open(hb_filter_object_t *proto, const char *settings, int pix_fmt, int w, int h);
+int hb_bench_run(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st);
+#ifdef __cplusplus
+}
+#endif
+#endif

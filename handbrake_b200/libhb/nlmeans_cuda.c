@@ -45,11 +45,6 @@ struct hb_filter_private_s
     int depth;
     int bps;
 
-    double strength[3];
-    double origin_tune[3];
-    int    patch_size[3];
-    int    range[3];
-    int    nframes[3];
     int    prefilter[3];
     int    threads;
     int    max_frames;
@@ -102,99 +97,87 @@ static nlm_pending_t *pending_at(hb_filter_private_t *pv, int i)
     return &pv->pending[(pv->head + i) % pv->cap];
 }
 
-static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
+/* settings dict -> device configuration (nlmeans.c:279-358).  Exported so that bench.py
+ * builds its kernel-only handle from exactly the code path init() uses. */
+int hb_nlmeans_cuda_build_config(const hb_dict_t *dict, int pix_fmt, int width, int height,
+                                 hbcu_nlmeans_config_t *cfg, int *max_frames_out, int *threads_out,
+                                 int prefilter_out[3])
 {
     static const char *const prefix[3] = { "y", "cb", "cr" };
-    hb_filter_private_t *pv = calloc(1, sizeof(*pv));
-    if (pv == NULL)
-    {
-        hb_error("nlmeans(cuda): calloc failed");
-        return -1;
-    }
-    filter->private_data = pv;
-    pv->input = *init;
+    double strength[3], origin_tune[3];
+    int patch_size[3], range[3], nframes[3], prefilter[3];
+    int threads = -1, max_frames = 0;
 
-    const AVPixFmtDescriptor *desc = av_pix_fmt_desc_get(init->pix_fmt);
+    const AVPixFmtDescriptor *desc = av_pix_fmt_desc_get(pix_fmt);
     if (desc == NULL || desc->nb_components < 3)
     {
-        hb_error("nlmeans(cuda): unsupported pixel format %d", init->pix_fmt);
-        goto fail;
+        hb_error("nlmeans(cuda): unsupported pixel format %d", pix_fmt);
+        return -1;
     }
-    pv->depth = desc->comp[0].depth;
-    pv->bps   = pv->depth > 8 ? 2 : 1;
+    const int depth = desc->comp[0].depth;
 
     for (int c = 0; c < 3; c++)
     {
-        pv->strength[c] = pv->origin_tune[c] = -1;
-        pv->patch_size[c] = pv->range[c] = pv->nframes[c] = pv->prefilter[c] = -1;
+        strength[c] = origin_tune[c] = -1;
+        patch_size[c] = range[c] = nframes[c] = prefilter[c] = -1;
     }
-    pv->threads = -1;
-
-    if (filter->settings != NULL)
+    if (dict != NULL)
     {
-        hb_dict_t *dict = filter->settings;
         char key[32];
         for (int c = 0; c < 3; c++)
         {
-            snprintf(key, sizeof(key), "%s-strength", prefix[c]);    hb_dict_extract_double(&pv->strength[c], dict, key);
-            snprintf(key, sizeof(key), "%s-origin-tune", prefix[c]); hb_dict_extract_double(&pv->origin_tune[c], dict, key);
-            snprintf(key, sizeof(key), "%s-patch-size", prefix[c]);  hb_dict_extract_int(&pv->patch_size[c], dict, key);
-            snprintf(key, sizeof(key), "%s-range", prefix[c]);       hb_dict_extract_int(&pv->range[c], dict, key);
-            snprintf(key, sizeof(key), "%s-frame-count", prefix[c]); hb_dict_extract_int(&pv->nframes[c], dict, key);
-            snprintf(key, sizeof(key), "%s-prefilter", prefix[c]);   hb_dict_extract_int(&pv->prefilter[c], dict, key);
+            snprintf(key, sizeof(key), "%s-strength", prefix[c]);    hb_dict_extract_double(&strength[c], dict, key);
+            snprintf(key, sizeof(key), "%s-origin-tune", prefix[c]); hb_dict_extract_double(&origin_tune[c], dict, key);
+            snprintf(key, sizeof(key), "%s-patch-size", prefix[c]);  hb_dict_extract_int(&patch_size[c], dict, key);
+            snprintf(key, sizeof(key), "%s-range", prefix[c]);       hb_dict_extract_int(&range[c], dict, key);
+            snprintf(key, sizeof(key), "%s-frame-count", prefix[c]); hb_dict_extract_int(&nframes[c], dict, key);
+            snprintf(key, sizeof(key), "%s-prefilter", prefix[c]);   hb_dict_extract_int(&prefilter[c], dict, key);
         }
-        hb_dict_extract_int(&pv->threads, dict, "threads");
+        hb_dict_extract_int(&threads, dict, "threads");
     }
 
     /* Cr inherits Cb, Cb inherits Y, Y takes the defaults (nlmeans.c:306-326) */
     for (int c = 1; c < 3; c++)
     {
-        if (pv->strength[c]    == -1) pv->strength[c]    = pv->strength[c-1];
-        if (pv->origin_tune[c] == -1) pv->origin_tune[c] = pv->origin_tune[c-1];
-        if (pv->patch_size[c]  == -1) pv->patch_size[c]  = pv->patch_size[c-1];
-        if (pv->range[c]       == -1) pv->range[c]       = pv->range[c-1];
-        if (pv->nframes[c]     == -1) pv->nframes[c]     = pv->nframes[c-1];
-        if (pv->prefilter[c]   == -1) pv->prefilter[c]   = pv->prefilter[c-1];
+        if (strength[c]    == -1) strength[c]    = strength[c-1];
+        if (origin_tune[c] == -1) origin_tune[c] = origin_tune[c-1];
+        if (patch_size[c]  == -1) patch_size[c]  = patch_size[c-1];
+        if (range[c]       == -1) range[c]       = range[c-1];
+        if (nframes[c]     == -1) nframes[c]     = nframes[c-1];
+        if (prefilter[c]   == -1) prefilter[c]   = prefilter[c-1];
     }
 
-    hbcu_nlmeans_config_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    memset(cfg, 0, sizeof(*cfg));
     for (int c = 0; c < 3; c++)
     {
-        if (pv->strength[c]    == -1) pv->strength[c]    = NLMEANS_STRENGTH_DEFAULT;
-        if (pv->origin_tune[c] == -1) pv->origin_tune[c] = NLMEANS_ORIGIN_TUNE_DEFAULT;
-        if (pv->patch_size[c]  == -1) pv->patch_size[c]  = NLMEANS_PATCH_SIZE_DEFAULT;
-        if (pv->range[c]       == -1) pv->range[c]       = NLMEANS_RANGE_DEFAULT;
-        if (pv->nframes[c]     == -1) pv->nframes[c]     = NLMEANS_FRAMES_DEFAULT;
-        if (pv->prefilter[c]   == -1) pv->prefilter[c]   = NLMEANS_PREFILTER_DEFAULT;
+        if (strength[c]    == -1) strength[c]    = NLMEANS_STRENGTH_DEFAULT;
+        if (origin_tune[c] == -1) origin_tune[c] = NLMEANS_ORIGIN_TUNE_DEFAULT;
+        if (patch_size[c]  == -1) patch_size[c]  = NLMEANS_PATCH_SIZE_DEFAULT;
+        if (range[c]       == -1) range[c]       = NLMEANS_RANGE_DEFAULT;
+        if (nframes[c]     == -1) nframes[c]     = NLMEANS_FRAMES_DEFAULT;
+        if (prefilter[c]   == -1) prefilter[c]   = NLMEANS_PREFILTER_DEFAULT;
 
         /* sanitise (nlmeans.c:328-338) */
-        if (pv->strength[c] < 0)        pv->strength[c] = 0;
-        if (pv->origin_tune[c] < 0.01)  pv->origin_tune[c] = 0.01;
-        if (pv->origin_tune[c] > 1)     pv->origin_tune[c] = 1;
-        if (pv->patch_size[c] % 2 == 0) pv->patch_size[c]--;
-        if (pv->patch_size[c] < 1)      pv->patch_size[c] = 1;
-        if (pv->range[c] % 2 == 0)      pv->range[c]--;
-        if (pv->range[c] < 1)           pv->range[c] = 1;
-        if (pv->nframes[c] < 1)         pv->nframes[c] = 1;
-        if (pv->nframes[c] > NLMEANS_FRAMES_MAX) pv->nframes[c] = NLMEANS_FRAMES_MAX;
-        if (pv->prefilter[c] < 0)       pv->prefilter[c] = 0;
+        if (strength[c] < 0)        strength[c] = 0;
+        if (origin_tune[c] < 0.01)  origin_tune[c] = 0.01;
+        if (origin_tune[c] > 1)     origin_tune[c] = 1;
+        if (patch_size[c] % 2 == 0) patch_size[c]--;
+        if (patch_size[c] < 1)      patch_size[c] = 1;
+        if (range[c] % 2 == 0)      range[c]--;
+        if (range[c] < 1)           range[c] = 1;
+        if (nframes[c] < 1)         nframes[c] = 1;
+        if (nframes[c] > NLMEANS_FRAMES_MAX) nframes[c] = NLMEANS_FRAMES_MAX;
+        if (prefilter[c] < 0)       prefilter[c] = 0;
 
-        if (pv->max_frames < pv->nframes[c]) pv->max_frames = pv->nframes[c];
-
-        if (pv->prefilter[c] != 0)
-        {
-            hb_error("nlmeans(cuda): prefilter mode %d is not implemented on the GPU path", pv->prefilter[c]);
-            goto fail;
-        }
+        if (max_frames < nframes[c]) max_frames = nframes[c];
 
         /* strength scales with bit depth (nlmeans.c:343) */
-        pv->strength[c] *= pv->depth > 8 ? (pv->depth - 8) * (pv->depth - 8) : 1;
+        strength[c] *= depth > 8 ? (depth - 8) * (depth - 8) : 1;
 
         /* exp table: these expressions are the numeric contract (nlmeans.c:346-358);
          * evaluated on the host exactly as written there */
-        hbcu_nlmeans_plane_t *pp = &cfg.plane[c];
-        const float weight_factor        = 1.0/pv->patch_size[c]/pv->patch_size[c] / (pv->strength[c] * pv->strength[c]);
+        hbcu_nlmeans_plane_t *pp = &cfg->plane[c];
+        const float weight_factor        = 1.0/patch_size[c]/patch_size[c] / (strength[c] * strength[c]);
         const float min_weight_in_table  = 0.0005;
         const float stretch              = NLMEANS_EXPSIZE / (-log(min_weight_in_table));
         pp->weight_fact                  = weight_factor * stretch;
@@ -205,11 +188,52 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
         }
         pp->exptable[NLMEANS_EXPSIZE-1] = 0;
 
-        pp->patch_size  = pv->patch_size[c];
-        pp->range       = pv->range[c];
-        pp->nframes     = pv->nframes[c];
-        pp->origin_tune = pv->origin_tune[c];
-        pp->bypass      = pv->strength[c] == 0;   /* nlmeans.c:493-499 */
+        pp->patch_size  = patch_size[c];
+        pp->range       = range[c];
+        pp->nframes     = nframes[c];
+        pp->origin_tune = origin_tune[c];
+        pp->bypass      = strength[c] == 0;   /* nlmeans.c:493-499 */
+        if (prefilter_out) prefilter_out[c] = prefilter[c];
+    }
+    cfg->width          = width;
+    cfg->height         = height;
+    cfg->depth          = depth;
+    cfg->chroma_shift_w = desc->log2_chroma_w;
+    cfg->chroma_shift_h = desc->log2_chroma_h;
+    cfg->device         = 0;
+    const char *dev_env = getenv("HBCU_DEVICE");
+    if (dev_env != NULL) cfg->device = atoi(dev_env);
+    if (max_frames_out) *max_frames_out = max_frames;
+    if (threads_out) *threads_out = threads;
+    return 0;
+}
+
+static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
+{
+    hb_filter_private_t *pv = calloc(1, sizeof(*pv));
+    if (pv == NULL)
+    {
+        hb_error("nlmeans(cuda): calloc failed");
+        return -1;
+    }
+    filter->private_data = pv;
+    pv->input = *init;
+
+    hbcu_nlmeans_config_t cfg;
+    if (hb_nlmeans_cuda_build_config(filter->settings, init->pix_fmt, init->geometry.width, init->geometry.height,
+                                     &cfg, &pv->max_frames, &pv->threads, pv->prefilter) != 0)
+    {
+        goto fail;
+    }
+    pv->depth = cfg.depth;
+    pv->bps   = pv->depth > 8 ? 2 : 1;
+    for (int c = 0; c < 3; c++)
+    {
+        if (pv->prefilter[c] != 0)
+        {
+            hb_error("nlmeans(cuda): prefilter mode %d is not implemented on the GPU path", pv->prefilter[c]);
+            goto fail;
+        }
     }
 
     /* `threads` CPU workers -> that many output frames in flight on the streams */
@@ -224,14 +248,6 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
         goto fail;
     }
 
-    cfg.width          = init->geometry.width;
-    cfg.height         = init->geometry.height;
-    cfg.depth          = pv->depth;
-    cfg.chroma_shift_w = desc->log2_chroma_w;
-    cfg.chroma_shift_h = desc->log2_chroma_h;
-    cfg.device         = 0;
-    const char *dev_env = getenv("HBCU_DEVICE");
-    if (dev_env != NULL) cfg.device = atoi(dev_env);
     cfg.ring_frames    = pv->ring;
     cfg.out_slots      = pv->inflight_max;
     if (hbcu_nlmeans_create(&pv->gpu, &cfg) != 0)
