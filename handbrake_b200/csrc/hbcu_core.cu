@@ -5,6 +5,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace hbcu {
 
@@ -127,6 +128,30 @@ void hbcu_host_free(void *p)
     std::lock_guard<std::mutex> g(g_pin_lock);
     h->next = g_pin_free[h->cls];
     g_pin_free[h->cls] = h;
+}
+
+int hbcu_host_reserve(size_t bytes, int count)
+{
+    std::vector<void *> blocks;
+    for (int i = 0; i < count; i++)
+    {
+        // bypass the free list so that `count` NEW blocks are created
+        uint32_t cls = 10;
+        while (((size_t)1 << cls) < bytes + sizeof(PinHeader) && cls < 31) cls++;
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, (size_t)1 << cls, cudaHostAllocPortable) != cudaSuccess)
+        {
+            cudaGetLastError();
+            break;
+        }
+        PinHeader *h = (PinHeader *)p;
+        h->magic = kPinMagic;
+        h->cls = cls;
+        h->next = nullptr;
+        blocks.push_back((void *)(h + 1));
+    }
+    for (void *b : blocks) hbcu_host_free(b);
+    return (int)blocks.size();
 }
 
 void hbcu_host_trim(void)

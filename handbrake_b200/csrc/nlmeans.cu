@@ -26,6 +26,7 @@
 #include "hbcu_common.h"
 #include "../../include/hbcu.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -435,6 +436,295 @@ __global__ void __launch_bounds__(kThreads, 1) nlmeans_tiled_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------
+// Fast 8-bit kernel (v2).  Same tiling and the same arithmetic results as the
+// kernel above, re-expressed for the B200 issue ports measured in
+// profiles/r01_microbench_instruction_throughput.txt:
+//   * FADD/FMUL/FFMA issue at 4 warp-instr/clk/SM, integer ALU ops (PRMT, LOP3,
+//     IADD3, IMAD) at 2, F2I / I2F.U8 at 0.5, LDS at ~1.
+//   * For 8-bit pixels every quantity of the patch distance is an integer
+//     below 2^24 (7*7*255^2 = 3.2M), so it is computed in fp32 EXACTLY: the
+//     squared difference is one FFMA into a running prefix sum, the patch-row
+//     sum one FADD, the vertical window two FADDs.  No int->float conversion.
+//   * Pixels are fetched as 32-bit words (conflict-free LDS.32) and unpacked
+//     with PRMT straight into the float 2^23+v (bits 0x4B0000vv): differences
+//     of two such floats are exact.
+//   * idx = (int)(diff*wfact) and the test diff < diff_max collapse into
+//     FMUL.SAT by wfact/128 (power-of-two scaling is exact), FADD.RZ with 2^16
+//     (the mantissa then holds floor(128*t)), and a 129-entry table whose
+//     entries 127 and 128 are 0.  Valid while wfact < 0.99 (then diff >=
+//     diff_max implies idx >= 127); launch_plane() checks it.  No F2I.
+// ---------------------------------------------------------------------------
+constexpr int kLutEntries = HBCU_NLMEANS_EXPSIZE + 1;
+
+template <int TH>
+struct FastLayout
+{
+    static constexpr int kRows      = TH + 2 * kHalo;
+    static constexpr int kTileBytes = kRows * kTilePW;
+    static constexpr int kAccBytes  = TH * kTileW * (int)sizeof(float);
+    static constexpr int kLutBytes  = kLutEntries * 32 * (int)sizeof(float);
+    static constexpr int kOffCur    = 0;
+    static constexpr int kOffCmp    = kOffCur + kTileBytes;
+    static constexpr int kOffWs     = kOffCmp + kTileBytes;
+    static constexpr int kOffPs     = kOffWs + kAccBytes;
+    static constexpr int kOffLut    = kOffPs + kAccBytes;
+    static constexpr int kOffBar    = kOffLut + kLutBytes;
+    static constexpr int kTotal     = kOffBar + 64;
+    static_assert(kTileBytes % 128 == 0, "TMA destination must stay 128-byte aligned");
+};
+
+// byte k (0..3) of word w as the float 2^23 + value
+__device__ __forceinline__ float byte_as_biased_float(uint32_t w, int k)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k));
+}
+
+template <int NH, int TH>
+__device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp,
+                                               float *__restrict__ acc_ws, float *__restrict__ acc_ps,
+                                               uint32_t lut_lane_addr, float wscale, double origin_tune,
+                                               int seg_y0, int lane, int dy, int dx0, int ng, int origin_g)
+{
+    constexpr int N   = 2 * NH + 1;
+    constexpr int RS  = TH / 8;
+    constexpr int NA  = 4 + 2 * NH;                 // source values per row
+    constexpr int NB  = NA + kGroup - 1;            // compare values per row
+    constexpr int PW  = kTilePW / 4;                // tile pitch in words
+    constexpr int OA  = (kHaloX - NH) & 3;          // byte offset of a[0] in its first word
+    constexpr int WA0 = (kHaloX - NH) >> 2;         // first word of the a window (relative to lane word)
+    constexpr int NWA = (OA + NA + 3) / 4;
+    constexpr int NWB = (NB + 3) / 4;               // aligned compare words
+    constexpr float kBias = 8388608.0f;             // 2^23
+
+    const int fb  = kHaloX - NH + dx0;              // first compare column relative to the lane's x
+    const int wb0 = fb >> 2;
+    const int ob  = (fb & 3) * 8;                   // funnel shift (bits) that aligns the compare window
+
+    float V[kGroup][4];
+    float hist[N][kGroup][4];
+#pragma unroll
+    for (int g = 0; g < kGroup; g++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            V[g][i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < N; k++) hist[k][g][i] = 0.f;
+        }
+    // aligned compare words of the last NH rows: they hold the pixels cmp[y+dy][x+dx] of the
+    // output row that completes NH steps after its own compare row was loaded
+    uint32_t delay[NH][NWB];
+#pragma unroll
+    for (int r = 0; r < NH; r++)
+#pragma unroll
+        for (int j = 0; j < NWB; j++) delay[r][j] = 0;
+
+#pragma unroll 1
+    for (int base = -NH; base < RS + NH; base += N)
+    {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+        {
+            const int yy = base + k;
+            if (yy < RS + NH)
+            {
+                const int ty = seg_y0 + yy + kHalo;
+                const uint32_t *aw = cur + ty * PW + lane + WA0;
+                const uint32_t *bw = cmp + (ty + dy) * PW + lane + wb0;
+                uint32_t wa[NWA], wraw[NWB + 1], wbv[NWB];
+#pragma unroll
+                for (int j = 0; j < NWA; j++) wa[j] = aw[j];
+#pragma unroll
+                for (int j = 0; j < NWB + 1; j++) wraw[j] = bw[j];
+#pragma unroll
+                for (int j = 0; j < NWB; j++) wbv[j] = __funnelshift_r(wraw[j], wraw[j + 1], ob);
+
+                float a[NA], b[NB];
+#pragma unroll
+                for (int j = 0; j < NA; j++) a[j] = byte_as_biased_float(wa[(OA + j) >> 2], (OA + j) & 3);
+#pragma unroll
+                for (int j = 0; j < NB; j++) b[j] = byte_as_biased_float(wbv[j >> 2], j & 3);
+
+#pragma unroll
+                for (int g = 0; g < kGroup; g++)
+                {
+                    if (g < ng && g != origin_g)
+                    {
+                        float c[NA + 1];
+                        c[0] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NA; j++)
+                        {
+                            const float d = __fsub_rn(a[j], b[j + g]);        // exact
+                            c[j + 1] = __fmaf_rn(d, d, c[j]);                  // exact: integers < 2^24
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                        {
+                            const float hsum = __fsub_rn(c[i + N], c[i]);
+                            V[g][i] = __fadd_rn(V[g][i], __fsub_rn(hsum, hist[k][g][i]));
+                            hist[k][g][i] = hsum;
+                        }
+                    }
+                }
+                if (yy >= NH)
+                {
+                    const int oy = seg_y0 + yy - NH;
+                    float4 ws4 = *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + lane * 4);
+                    float4 ps4 = *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + lane * 4);
+                    float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+                    float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+                    // pixel values cmp[oy+dy][x+dx0+g+i] = element NH+g+i of the compare window loaded NH rows ago
+                    float pixv[kGroup + 3];
+#pragma unroll
+                    for (int j = 0; j < kGroup + 3; j++)
+                        pixv[j] = __fsub_rn(byte_as_biased_float(delay[0][(NH + j) >> 2], (NH + j) & 3), kBias);
+#pragma unroll
+                    for (int g = 0; g < kGroup; g++)
+                    {
+                        if (g < ng)
+                        {
+                            if (g == origin_g)
+                            {
+                                const uint32_t cw = cur[(oy + kHalo) * PW + lane + kHaloX / 4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    add_origin(ws[i], ps[i], origin_tune, (int)((cw >> (8 * i)) & 0xffu));
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                {
+                                    float t, u, wgt;
+                                    asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(t) : "f"(V[g][i]), "f"(wscale));
+                                    asm("add.rz.f32 %0, %1, 0f47800000;" : "=f"(u) : "f"(t));   // 65536 + floor(128 t)
+                                    const uint32_t addr = (__float_as_uint(u) << 7) + lut_lane_addr;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(wgt) : "r"(addr));
+                                    ws[i] = __fadd_rn(ws[i], wgt);
+                                    ps[i] = __fadd_rn(ps[i], __fmul_rn(wgt, pixv[g + i]));
+                                }
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + lane * 4) = make_float4(ws[0], ws[1], ws[2], ws[3]);
+                    *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + lane * 4) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+                }
+                // advance the delay line
+#pragma unroll
+                for (int r = 0; r + 1 < NH; r++)
+#pragma unroll
+                    for (int j = 0; j < NWB; j++) delay[r][j] = delay[r + 1][j];
+#pragma unroll
+                for (int j = 0; j < NWB; j++) delay[NH - 1][j] = wbv[j];
+            }
+        }
+    }
+}
+
+template <int NH, int TH>
+__global__ void __launch_bounds__(kThreads, 1) nlmeans_fast8_kernel(const __grid_constant__ TiledParams tp)
+{
+    const KernelParams &p = tp.k;
+    using L = FastLayout<TH>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *cur  = smem + L::kOffCur;
+    uint8_t *cmp  = smem + L::kOffCmp;
+    float *acc_ws = reinterpret_cast<float *>(smem + L::kOffWs);
+    float *acc_ps = reinterpret_cast<float *>(smem + L::kOffPs);
+    float *lut    = reinterpret_cast<float *>(smem + L::kOffLut);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * kTileW, Y0 = blockIdx.y * TH;
+    const int gx = X0 + kBorder - kHaloX, gy = Y0 + kBorder - kHalo;
+
+    if (tid == 0)
+    {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    if (tid == 0)
+    {
+        mbar_expect_tx(bar, L::kTileBytes);
+        tma_load_2d(cur, &tp.maps[0], gx, gy, bar);
+    }
+    for (int i = tid; i < kLutEntries * 32; i += kThreads)
+    {
+        const int e = i >> 5;
+        lut[i] = e < HBCU_NLMEANS_EXPSIZE ? p.exptable[e] : 0.f;
+    }
+    for (int i = tid; i < TH * kTileW; i += kThreads)
+    {
+        acc_ws[i] = 0.f;
+        acc_ps[i] = 0.f;
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    __syncthreads();
+
+    const int seg_y0 = warp * (TH / 8);
+    const float wscale = p.wfact * 0.0078125f;                         // wfact / 128, exact
+    // shared address of this lane's copy of table entry 0, pre-biased by -(0x47800000 << 7)
+    const uint32_t lut_lane_addr = smem_u32(lut) + (uint32_t)lane * 4u - (0x47800000u << 7);
+    for (int f = 0; f < p.nf; f++)
+    {
+        const uint8_t *B = cur;
+        if (f > 0)
+        {
+            __syncthreads();
+            if (tid == 0)
+            {
+                fence_proxy_async();
+                mbar_expect_tx(bar, L::kTileBytes);
+                tma_load_2d(cmp, &tp.maps[f], gx, gy, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            B = cmp;
+        }
+        for (int dy = -p.r_half; dy <= p.r_half; dy++)
+        {
+            for (int dx0 = -p.r_half; dx0 <= p.r_half; dx0 += kGroup)
+            {
+                const int ng = min(kGroup, p.r_half - dx0 + 1);
+                const int origin_g = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : -1;
+                nlm_group_fast<NH, TH>(reinterpret_cast<const uint32_t *>(cur), reinterpret_cast<const uint32_t *>(B),
+                                       acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+            }
+        }
+    }
+
+    const int x = lane * 4;
+    uint8_t *dst = reinterpret_cast<uint8_t *>(p.dst);
+    for (int r = 0; r < TH / 8; r++)
+    {
+        const int oy = seg_y0 + r;
+        const int y = Y0 + oy;
+        if (y >= p.h) break;
+        const float4 ws4 = *reinterpret_cast<const float4 *>(acc_ws + oy * kTileW + x);
+        const float4 ps4 = *reinterpret_cast<const float4 *>(acc_ps + oy * kTileW + x);
+        const float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+        const float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+        uint8_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            o[i] = finish_pixel<uint8_t>(ws[i], ps[i], cur[(oy + kHalo) * kTilePW + x + kHaloX + i]);
+        uint8_t *drow = dst + (size_t)y * p.dpitch + X0 + x;
+        if (X0 + x + 3 < p.w)
+            *reinterpret_cast<uchar4 *>(drow) = make_uchar4(o[0], o[1], o[2], o[3]);
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (X0 + x + i < p.w) drow[i] = o[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct PlaneGeom
@@ -493,6 +783,34 @@ int launch_tiled(const TiledParams &kp, cudaStream_t st)
     return 0;
 }
 
+template <int NH, int TH>
+int launch_fast8(const TiledParams &kp, cudaStream_t st)
+{
+    using L = FastLayout<TH>;
+    static bool configured = false;
+    if (!configured)
+    {
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast8_kernel<NH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    dim3 grid((kp.k.w + kTileW - 1) / kTileW, (kp.k.h + TH - 1) / TH);
+    nlmeans_fast8_kernel<NH, TH><<<grid, kThreads, L::kTotal, st>>>(kp);
+    hbcu::count_launch();
+    return 0;
+}
+
+int launch_fast8_nh(const TiledParams &kp, cudaStream_t st)
+{
+    switch (kp.k.n_half)
+    {
+        case 1: return launch_fast8<1, 128>(kp, st);
+        case 2: return launch_fast8<2, 128>(kp, st);
+        case 3: return launch_fast8<3, 128>(kp, st);
+        case 4: return launch_fast8<4, 128>(kp, st);
+        default: return 1;
+    }
+}
+
 template <typename PIX, int TH>
 int launch_tiled_nh(const TiledParams &kp, cudaStream_t st)
 {
@@ -524,8 +842,11 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
         TiledParams tp;
         tp.k = kp;
         for (int f = 0; f < kp.nf; f++) tp.maps[f] = h->maps[slots[f] * 3 + plane];
-        int rc = h->bps == 1 ? launch_tiled_nh<uint8_t, 128>(tp, h->s_compute)
-                             : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
+        // impl 0/2: fp32-exact fast kernel for 8-bit planes when the table trick is valid; impl 3: integer tiled kernel
+        const bool fast_ok = h->bps == 1 && kp.wfact < 0.99f && kp.wfact > 1e-5f;
+        int rc = (fast_ok && h->impl != 3) ? launch_fast8_nh(tp, h->s_compute)
+                 : h->bps == 1           ? launch_tiled_nh<uint8_t, 128>(tp, h->s_compute)
+                                         : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
         if (rc < 0) return rc;
         if (rc == 0)
         {
@@ -696,6 +1017,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->cfg = *cfg;
     h->bps = cfg->depth > 8 ? 2 : 1;
     h->impl = 0;
+    if (const char *e = getenv("HBCU_NLMEANS_IMPL")) h->impl = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;   // test hook
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;
@@ -913,7 +1235,7 @@ int hbcu_nlmeans_sync(hbcu_nlmeans_t *h)
 
 int hbcu_nlmeans_set_impl(hbcu_nlmeans_t *h, int impl)
 {
-    if (h == nullptr || impl < 0 || impl > 2) { set_error("nlmeans_set_impl: bad argument"); return -1; }
+    if (h == nullptr || impl < 0 || impl > 3) { set_error("nlmeans_set_impl: bad argument"); return -1; }
     h->impl = impl;
     return 0;
 }

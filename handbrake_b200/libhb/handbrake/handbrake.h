@@ -223,6 +223,9 @@ void          hb_buffer_copy_props(hb_buffer_t *dst, const hb_buffer_t *src);
 typedef void *(*hb_shim_alloc_fn)(size_t);
 typedef void  (*hb_shim_free_fn)(void *);
 void hb_shim_set_frame_allocator(hb_shim_alloc_fn a, hb_shim_free_fn f);
+/* new buffers are zero-filled by default (deterministic oracle runs); libhb's own pool hands out
+ * recycled memory, so throughput measurements switch this off */
+void hb_shim_set_zero_buffers(int on);
 /* statistics used by the tests (leak check: HB_BUFFER_DEBUG analogue, fifo.c:137-278) */
 long hb_shim_buffers_alive(void);
 

@@ -194,6 +194,9 @@ void hb_thread_close(hb_thread_t **t)
 static hb_shim_alloc_fn g_alloc = NULL;
 static hb_shim_free_fn  g_free  = NULL;
 static long g_alive = 0;
+static int  g_zero  = 1;   /* zero-fill new buffers (deterministic oracle); libhb's pool does not */
+
+void hb_shim_set_zero_buffers(int on) { g_zero = on; }
 
 void hb_shim_set_frame_allocator(hb_shim_alloc_fn a, hb_shim_free_fn f)
 {
@@ -223,11 +226,11 @@ hb_buffer_t *hb_buffer_init(int size)
         {
             base = g_alloc(total);
             ffn  = g_free;
-            if (base != NULL) memset(base, 0, total);
+            if (base != NULL && g_zero) memset(base, 0, total);
         }
         else
         {
-            base = calloc(1, total);
+            base = g_zero ? calloc(1, total) : malloc(total);
         }
         if (base == NULL)
         {

@@ -6,12 +6,14 @@
 #include "handbrake/handbrake.h"
 
 extern hb_filter_object_t hb_filter_nlmeans_cuda;
+extern hb_filter_object_t hb_filter_comb_detect_cuda;
 
 hb_filter_object_t *hb_filter_get(int filter_id)
 {
     switch (filter_id)
     {
-        case HB_FILTER_NLMEANS: return &hb_filter_nlmeans_cuda;
+        case HB_FILTER_NLMEANS:     return &hb_filter_nlmeans_cuda;
+        case HB_FILTER_COMB_DETECT: return &hb_filter_comb_detect_cuda;
         default:                return NULL;
     }
 }

@@ -42,6 +42,9 @@ int          hbcu_device_count(void);
 void *       hbcu_host_alloc(size_t bytes);
 void         hbcu_host_free(void *p);
 void         hbcu_host_trim(void);
+/* pre-populates the pool with `count` blocks able to hold `bytes` each (steady state of a running
+ * pipeline, where every frame buffer is a recycled one); returns the number of blocks added */
+int          hbcu_host_reserve(size_t bytes, int count);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t     hbcu_kernel_launches(void);
 
@@ -110,7 +113,8 @@ int  hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail,
                                 void *out_planes[3], int out_strides[3]);
 int  hbcu_nlmeans_sync(hbcu_nlmeans_t *h);
 /* implementation selector for tests: 0 = auto (tiled sm_100a kernel when the
- * parameters fit, generic otherwise), 1 = force generic, 2 = force tiled */
+ * parameters fit, generic otherwise), 1 = force generic, 2 = force tiled,
+ * 3 = tiled but integer-arithmetic variant (the one 16-bit planes use) */
 int  hbcu_nlmeans_set_impl(hbcu_nlmeans_t *h, int impl);
 
 /* CUDA-event timing on the handle's compute stream (bench.py):
@@ -119,6 +123,45 @@ int  hbcu_nlmeans_mark(hbcu_nlmeans_t *h, int which);
 int  hbcu_nlmeans_elapsed_ms(hbcu_nlmeans_t *h, float *ms);
 /* device time spent in the main kernel alone between the two marks */
 int  hbcu_nlmeans_kernel_ms(hbcu_nlmeans_t *h, float *ms, int *launches);
+
+/* ------------------------------------------------------------------------- */
+/* Comb detect   replaces comb_detect.c:221-276,384-454,556-966,1051-1072 and  */
+/*               templates/comb_detect_template.c:288-402,789-933 (the five     */
+/*               tasksets become three kernels on one stream)                  */
+/* ------------------------------------------------------------------------- */
+typedef struct hbcu_comb_detect_config_s
+{
+    int width, height;        /* luma geometry (only luma is examined) */
+    int depth;
+    int device;
+    int slots;                /* luma planes kept on the device (>= 4) */
+    int mode;                 /* bit0 MODE_GAMMA, bit1 MODE_FILTER (comb_detect.c:23-26) */
+    int spatial_metric;
+    int filter_mode;          /* 1 FILTER_CLASSIC, 2 FILTER_ERODE_DILATE */
+    int motion_threshold;     /* already shifted by depth-8 (comb_detect.c:1152-1153) */
+    int spatial_threshold;
+    int block_threshold, block_width, block_height;
+    float gamma_motion_threshold, gamma_spatial_threshold, gamma_spatial_threshold6;
+    int comb32detect_min, comb32detect_max;
+    const float *gamma_lut;   /* (1<<depth) floats built by the host as comb_detect.c:1074-1081 */
+} hbcu_comb_detect_config_t;
+
+typedef struct hbcu_comb_detect_s hbcu_comb_detect_t;
+
+int  hbcu_comb_detect_create(hbcu_comb_detect_t **out, const hbcu_comb_detect_config_t *cfg);
+void hbcu_comb_detect_destroy(hbcu_comb_detect_t *h);
+/* luma plane of frame `index` to the device (asynchronous from pinned memory) */
+int  hbcu_comb_detect_upload(hbcu_comb_detect_t *h, int64_t index, const void *luma, int stride);
+int  hbcu_comb_detect_upload_device(hbcu_comb_detect_t *h, int64_t index, const void *dluma, int stride);
+/* comb_segmenter (comb_detect.c:1051-1072) for frame `cur` against `prev` and `next`; asynchronous */
+int  hbcu_comb_detect_run(hbcu_comb_detect_t *h, int64_t prev, int64_t cur, int64_t next, int force_exhaustive);
+/* blocks until the verdict of frame `cur` is known: HB_COMB_NONE 0 / LIGHT 1 / HEAVY 2 */
+int  hbcu_comb_detect_result(hbcu_comb_detect_t *h, int64_t cur, int *combed);
+/* test hook: raw and scored masks (width*height bytes each, may be NULL) of the latest run */
+int  hbcu_comb_detect_masks(hbcu_comb_detect_t *h, uint8_t *raw, uint8_t *scored);
+int  hbcu_comb_detect_sync(hbcu_comb_detect_t *h);
+int  hbcu_comb_detect_mark(hbcu_comb_detect_t *h, int which);
+int  hbcu_comb_detect_elapsed_ms(hbcu_comb_detect_t *h, float *ms);
 
 #ifdef __cplusplus
 }

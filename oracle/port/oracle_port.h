@@ -43,6 +43,30 @@ void oracle_nlmeans_plane(const void *const *frames, int nframes, int w, int h, 
 int oracle_nlmeans_clip(const uint8_t *in, int n_in, int width, int height, int depth,
                         const oracle_nlmeans_plane_params_t pp[3], uint8_t *out);
 
+/* ---------------- comb detect (libhb/comb_detect.c + templates/comb_detect_template.c) ---------------- */
+typedef struct
+{
+    int mode;               /* bit0 gamma, bit1 filter (comb_detect.c:23-26) */
+    int spatial_metric;
+    int motion_threshold;   /* as given in the settings (before the depth shift) */
+    int spatial_threshold;
+    int filter_mode;        /* 1 classic, 2 erode-dilate */
+    int block_threshold, block_width, block_height;
+} oracle_comb_params_t;
+
+/* one verdict: luma planes prev/cur/next (w*h samples each, tightly packed, uint8_t or uint16_t by depth);
+ * mask_out / filtered_out (w*h bytes each) may be NULL.  Returns HB_COMB_NONE/LIGHT/HEAVY (0/1/2). */
+int oracle_comb_detect(const void *prev, const void *cur, const void *next, int w, int h, int depth,
+                       const oracle_comb_params_t *p, int force_exhaustive,
+                       uint8_t *mask_out, uint8_t *filtered_out);
+
+/* gamma table, comb_detect.c:1074-1081: (1<<depth) floats */
+void oracle_comb_gamma_lut(int depth, float *out);
+
+/* whole clip through comb_detect_work's ref window (comb_detect.c:1499-1584): verdict per input frame */
+int oracle_comb_detect_clip(const uint8_t *in, int n_in, int width, int height, int depth,
+                            const oracle_comb_params_t *p, uint8_t *verdicts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,3 +32,58 @@ class OraclePort:
         rc = self.lib.oracle_nlmeans_clip(clip.ctypes.data, clip.shape[0], width, height, depth, pp, out.ctypes.data)
         assert rc == 0
         return out
+
+
+class CombParams(C.Structure):
+    _fields_ = [("mode", C.c_int), ("spatial_metric", C.c_int), ("motion_threshold", C.c_int),
+                ("spatial_threshold", C.c_int), ("filter_mode", C.c_int), ("block_threshold", C.c_int),
+                ("block_width", C.c_int), ("block_height", C.c_int)]
+
+
+COMB_DEFAULTS = dict(mode=3, spatial_metric=2, motion_threshold=3, spatial_threshold=3, filter_mode=2,
+                     block_threshold=40, block_width=16, block_height=16)      # comb_detect.c:1118-1125
+COMB_KEYS = {"mode": "mode", "spatial-metric": "spatial_metric", "motion-thresh": "motion_threshold",
+             "spatial-thresh": "spatial_threshold", "filter-mode": "filter_mode", "block-thresh": "block_threshold",
+             "block-width": "block_width", "block-height": "block_height"}
+
+
+def comb_params(settings):
+    d = dict(COMB_DEFAULTS)
+    if settings:
+        for kv in settings.split(":"):
+            k, v = kv.split("=")
+            d[COMB_KEYS[k]] = int(v)
+    return CombParams(**d)
+
+
+def _comb_bind(self):
+    self.lib.oracle_comb_detect_clip.restype = C.c_int
+    self.lib.oracle_comb_detect_clip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CombParams), C.c_void_p]
+    self.lib.oracle_comb_detect.restype = C.c_int
+    self.lib.oracle_comb_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(CombParams), C.c_int, C.c_void_p, C.c_void_p]
+
+
+def comb_detect_clip(self, clip, width, height, depth, settings=None):
+    _comb_bind(self)
+    clip = np.ascontiguousarray(clip, dtype=np.uint8)
+    v = np.zeros(clip.shape[0], dtype=np.uint8)
+    p = comb_params(settings)
+    self.lib.oracle_comb_detect_clip(clip.ctypes.data, clip.shape[0], width, height, depth, C.byref(p), v.ctypes.data)
+    return v
+
+
+def comb_detect_masks(self, prev, cur, nxt, width, height, depth, settings=None, force=0):
+    """luma planes (2-D arrays) -> (verdict, raw mask, scored mask)"""
+    _comb_bind(self)
+    p = comb_params(settings)
+    a, b, c = (np.ascontiguousarray(x) for x in (prev, cur, nxt))
+    m = np.zeros((height, width), np.uint8)
+    f = np.zeros((height, width), np.uint8)
+    v = self.lib.oracle_comb_detect(a.ctypes.data, b.ctypes.data, c.ctypes.data, width, height, depth, C.byref(p), force,
+                                    m.ctypes.data, f.ctypes.data)
+    return v, m, f
+
+
+OraclePort.comb_detect_clip = comb_detect_clip
+OraclePort.comb_detect_masks = comb_detect_masks

@@ -81,3 +81,38 @@ def test_prefilter_is_refused(cuda_filters):
     g = cuda_filters.run("hb_filter_nlmeans_cuda", "y-strength=6:y-prefilter=1", clip, FMT8, w, h)
     assert g.init_failed == 1          # filter dropped, frames pass through untouched (work.c:1861-1868)
     assert np.array_equal(g.frames, clip)
+
+
+@pytest.mark.parametrize("impl", ["1", "3"])
+def test_other_kernels_agree(ref, cuda_filters, monkeypatch, impl):
+    """generic (1) and integer-tiled (3) kernels on the same 8-bit clip the fast kernel handles by default"""
+    monkeypatch.setenv("HBCU_NLMEANS_IMPL", impl)
+    w, h = 300, 150
+    clip = synth.progressive_clip(FMT8, w, h, 4, seed=21)
+    r, g = run_both(ref, cuda_filters, "y-strength=6:cb-strength=3:cb-range=5", clip, FMT8, w, h)
+    assert_same(r, g)
+
+
+def test_flat_and_extreme_content(ref, cuda_filters):
+    """all-zero frames (result==0 -> source pixel fallback), saturated frames, and full-range noise"""
+    w, h = 192, 112
+    fb = synth.frame_bytes(FMT8, w, h)
+    rng = np.random.default_rng(5)
+    clip = np.stack([np.zeros(fb, np.uint8), np.full(fb, 255, np.uint8),
+                     rng.integers(0, 256, fb, dtype=np.uint8), rng.integers(0, 256, fb, dtype=np.uint8),
+                     np.zeros(fb, np.uint8)])
+    for s in ("y-strength=3", "y-strength=10:y-origin-tune=0.15", "y-strength=1.5"):
+        r, g = run_both(ref, cuda_filters, s, clip, FMT8, w, h)
+        assert_same(r, g)
+
+
+def test_golden_digests(cuda_filters):
+    """the committed digests of the reference output (tests/golden), no reference needed at run time"""
+    import hashlib, json
+    from pathlib import Path
+    golden = json.loads((Path(__file__).parent / "golden" / "nlmeans_golden.json").read_text())
+    for name, c in golden.items():
+        fmt = FMT8 if c["depth"] == 8 else FMT10
+        clip = synth.progressive_clip(fmt, c["width"], c["height"], c["frames"], seed=c["seed"])
+        g = cuda_filters.run("hb_filter_nlmeans_cuda", c["settings"], clip, fmt, c["width"], c["height"])
+        assert [hashlib.sha256(f.tobytes()).hexdigest() for f in g.frames] == c["sha256"], name
