@@ -1,0 +1,546 @@
+// decomb.cu -- decomb (yadif / cubic / blend line filters, bob, per-frame mode) for sm_100a
+// behind the C-ABI of include/hbcu.h.
+//
+// Replaces (reference /root/reference/libhb):
+//   cubic_interpolate_pixel/line  templates/decomb_template.c:43-107
+//   blend_filter_pixel/line       templates/decomb_template.c:279-361
+//   yadif_filter_line/YADIF_CHECK templates/decomb_template.c:482-710
+//   yadif_decomb_filter_work      templates/decomb_template.c:714-808   (cpu_count row segments)
+//   filter_{8,16}                 templates/decomb_template.c:810-898
+// The reference splits every plane into cpu_count row segments joined by a taskset barrier; rows
+// are independent, so here one kernel covers a whole plane: a thread produces four adjacent
+// output pixels of one row (kept rows are straight copies, rebuilt rows run the line filter).
+// Integer arithmetic only -> bit-exact.  The kernel is HBM-bound: it reads the three input
+// frames once (rows are re-touched through L1/L2) and writes one.
+#include "hbcu_common.h"
+#include "../../include/hbcu.h"
+#include "eedi2.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using hbcu::set_error;
+
+struct FieldParams
+{
+    const void *prev, *cur, *next;   // plane base pointers
+    const void *eedi;                // EEDI2 full-height interpolation of this plane or nullptr
+    void *dst;
+    int w, h;
+    int pitch;                       // input planes, elements
+    int dpitch;                      // output plane, elements
+    int epitch;
+    int mode;                        // per-frame mode (EEDI2 bit kept: selects the spatial predictor)
+    int parity, tff;
+    int maxv;
+};
+
+__device__ __forceinline__ int crop(int v, int maxv) { return min(max(v, 0), maxv); }
+
+// template :43-49 (C division truncates toward zero, as does CUDA's)
+__device__ __forceinline__ int cubic_px(int maxv, int y0, int y1, int y2, int y3)
+{
+    const int r = (y0 * -3) + (y1 * 23) + (y2 * 23) + (y3 * -3);
+    return crop(r / 40, maxv);
+}
+
+template <typename PIX>
+__device__ __forceinline__ int cubic_line_px(const PIX *c, int pitch, int h, int x, int y, int maxv)
+{
+    const PIX *p = c + (size_t)y * pitch + x;
+    int a = 0, b = 0, cc = 0, d = 0;
+    if (y >= 3)                { a = p[-3 * pitch]; b = p[-pitch]; }
+    else if (y == 2 || y == 1) { a = p[-pitch]; b = a; }
+    else if (y == 0)           { a = p[pitch]; b = a; }
+    if (y <= h - 4)                     { cc = p[pitch]; d = p[3 * pitch]; }
+    else if (y == h - 3 || y == h - 2)  { cc = p[pitch]; d = cc; }
+    else if (y == h - 1)                { cc = p[-pitch]; d = cc; }
+    return cubic_px(maxv, a, b, cc, d);
+}
+
+template <typename PIX>
+__device__ __forceinline__ int blend_line_px(const PIX *c, int pitch, int h, int x, int y, int maxv)
+{
+    const PIX *p = c + (size_t)y * pitch + x;
+    int u1, u2, d1, d2;
+    if (y > 1 && y < h - 2) { u1 = -pitch; u2 = -2 * pitch; d1 = pitch; d2 = 2 * pitch; }
+    else if (y == 0)        { u1 = u2 = 0; d1 = pitch; d2 = 2 * pitch; }
+    else if (y == 1)        { u1 = u2 = -pitch; d1 = pitch; d2 = 2 * pitch; }
+    else if (y == h - 2)    { u1 = -pitch; u2 = -2 * pitch; d1 = d2 = pitch; }
+    else                    { u1 = -pitch; u2 = -2 * pitch; d1 = d2 = 0; }
+    int r = -(int)p[u2] + 2 * (int)p[u1] + 6 * (int)p[0] + 2 * (int)p[d1] - (int)p[d2];
+    r >>= 3;
+    return crop(r, maxv);
+}
+
+template <typename PIX>
+__device__ __forceinline__ int yadif_px(const FieldParams &fp, int x, int y)
+{
+    const PIX *prev = (const PIX *)fp.prev, *cur = (const PIX *)fp.cur, *next = (const PIX *)fp.next;
+    const int pitch = fp.pitch, w = fp.w, h = fp.h, maxv = fp.maxv;
+    const int par = fp.parity ^ fp.tff;
+    const PIX *prev2 = par ? prev : cur, *next2 = par ? cur : next;
+    const int sp = y ? -pitch : pitch;                       // mirrored at the first / last line
+    const int sn = y + 1 < h ? pitch : -pitch;
+    const bool vertical_edge = (y < 3) || (y > h - 4);
+    const bool cubic = (fp.mode & HBCU_DECOMB_CUBIC) != 0;
+    const int margin = cubic ? 3 : 2;
+    const size_t o = (size_t)y * pitch + x;
+
+    const int c = cur[o + sp];
+    const int p2 = prev2[o], n2 = next2[o];
+    const int d = (p2 + n2) >> 1;
+    const int e = cur[o + sn];
+    const int td0 = abs(p2 - n2);
+    const int td1 = (abs((int)prev[o + sp] - c) + abs((int)prev[o + sn] - e)) >> 1;
+    const int td2 = (abs((int)next[o + sp] - c) + abs((int)next[o + sn] - e)) >> 1;
+    int diff = max(max(td0 >> 1, td1), td2);
+    int spatial_pred;
+
+    if (fp.eedi != nullptr)
+    {
+        spatial_pred = ((const PIX *)fp.eedi)[(size_t)y * fp.epitch + x];
+    }
+    else
+    {
+        const PIX *q = cur + o;
+        if (cubic && !vertical_edge)
+            spatial_pred = cubic_px(maxv, q[-3 * pitch], q[-pitch], q[pitch], q[3 * pitch]);
+        else
+            spatial_pred = (c + e) >> 1;
+        if (x > margin && x < w - (margin + 1))
+        {
+            int score = abs((int)q[sp - 1] - (int)q[sn - 1]) + abs(c - e) + abs((int)q[sp + 1] - (int)q[sn + 1]) - 1;
+#pragma unroll
+            for (int dir = -1; dir <= 1; dir += 2)
+            {
+#pragma unroll
+                for (int step = 1; step <= 2; step++)
+                {
+                    const int j = dir * step;
+                    const int s = abs((int)q[sp - 1 + j] - (int)q[sn - 1 - j]) + abs((int)q[sp + j] - (int)q[sn - j]) +
+                                  abs((int)q[sp + 1 + j] - (int)q[sn + 1 - j]);
+                    if (!(s < score)) break;                 // the +-2 probe lives inside a successful +-1 probe
+                    score = s;
+                    if (cubic && !vertical_edge)
+                    {
+                        if (step == 1)
+                            spatial_pred = cubic_px(maxv, q[-3 * pitch + 3 * j], q[-pitch + j], q[pitch - j], q[3 * pitch - 3 * j]);
+                        else
+                            spatial_pred = cubic_px(maxv, ((int)q[-3 * pitch + 2 * j] + (int)q[-pitch + 2 * j]) / 2, q[-pitch + j],
+                                                    q[pitch - j], ((int)q[3 * pitch - 2 * j] + (int)q[pitch - 2 * j]) / 2);
+                    }
+                    else
+                    {
+                        spatial_pred = ((int)q[sp + j] + (int)q[sn - j]) >> 1;
+                    }
+                }
+            }
+        }
+    }
+    if (!vertical_edge)
+    {
+        const int b = ((int)prev2[o - 2 * pitch] + (int)next2[o - 2 * pitch]) >> 1;
+        const int f = ((int)prev2[o + 2 * pitch] + (int)next2[o + 2 * pitch]) >> 1;
+        const int mx = max(max(d - e, d - c), min(b - c, f - e));
+        const int mn = min(min(d - e, d - c), max(b - c, f - e));
+        diff = max(max(diff, mn), -mx);
+    }
+    if (spatial_pred > d + diff) spatial_pred = d + diff;
+    else if (spatial_pred < d - diff) spatial_pred = d - diff;
+    return spatial_pred;
+}
+
+// one thread = 4 adjacent pixels of one output row
+template <typename PIX>
+__global__ void __launch_bounds__(256) decomb_field_kernel(FieldParams fp)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= fp.w || y >= fp.h) return;
+    const PIX *cur = (const PIX *)fp.cur;
+    PIX *dst = (PIX *)fp.dst + (size_t)y * fp.dpitch;
+    const bool filtered = fp.parity ? !(y & 1) : (y & 1);     // template :744, :796
+    int v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int x = min(x0 + i, fp.w - 1);
+        if (!filtered)                           v[i] = cur[(size_t)y * fp.pitch + x];
+        else if (fp.mode == HBCU_DECOMB_BLEND)   v[i] = blend_line_px<PIX>(cur, fp.pitch, fp.h, x, y, fp.maxv);
+        else if (fp.mode == HBCU_DECOMB_CUBIC)   v[i] = cubic_line_px<PIX>(cur, fp.pitch, fp.h, x, y, fp.maxv);
+        else if (fp.mode & HBCU_DECOMB_YADIF)    v[i] = yadif_px<PIX>(fp, x, y);
+        else                                     v[i] = 0;    // no line filter runs: a fresh (zeroed) buffer row
+    }
+    if (x0 + 3 < fp.w)
+    {
+        if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(dst + x0) = make_uchar4(v[0], v[1], v[2], v[3]);
+        else                  *reinterpret_cast<ushort4 *>(dst + x0) = make_ushort4(v[0], v[1], v[2], v[3]);
+    }
+    else
+    {
+        for (int i = 0; i < 4; i++)
+            if (x0 + i < fp.w) dst[x0 + i] = (PIX)v[i];
+    }
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) copy_rows_kernel(const PIX *__restrict__ src, int spitch, PIX *__restrict__ dst, int dpitch, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w && y < h) dst[(size_t)y * dpitch + x] = src[(size_t)y * spitch + x];
+}
+
+struct Geom { int w, h, pitch; size_t bytes; };
+
+}  // namespace
+
+struct hbcu_decomb_s
+{
+    hbcu_decomb_config_t cfg;
+    int bps, maxv;
+    Geom g[3];
+    int slots, out_slots;
+    std::vector<uint8_t *> in_mem;       // [slot*3+plane]
+    std::vector<int64_t> in_index;
+    std::vector<cudaEvent_t> ev_upload, ev_readers;
+    std::vector<uint8_t *> out_mem;      // [oslot*3+plane]
+    std::vector<int64_t> out_ticket;
+    std::vector<cudaEvent_t> ev_kernel, ev_d2h;
+    int next_out;
+    hbcu::Eedi2 *eedi;                   // EEDI2 state (mask carry-over) + scratch, one per handle
+    cudaStream_t s_h2d, s_compute, s_d2h;
+    cudaEvent_t ev_mark[2];
+};
+
+namespace {
+
+int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next, int frame_mode, int parity, int tff, int oslot)
+{
+    const int64_t idx[3] = { prev, cur, next };
+    int slot[3];
+    for (int k = 0; k < 3; k++)
+    {
+        slot[k] = (int)(idx[k] % h->slots);
+        if (idx[k] < 0 || h->in_index[slot[k]] != idx[k])
+        {
+            set_error("decomb: frame %lld is not resident", (long long)idx[k]);
+            return -1;
+        }
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_upload[slot[k]], 0));
+    }
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_d2h[oslot], 0));
+    const bool use_eedi = (frame_mode & HBCU_DECOMB_EEDI2) != 0;
+    if (use_eedi)
+    {
+        if (h->eedi == nullptr)
+        {
+            set_error("decomb: EEDI2 requested but the handle was created without mode bit 8");
+            return -1;
+        }
+        // eedi2_planer (decomb template :455-473): field `!tff_eedi` of cur, tff_eedi = !parity (decomb.c:539-542)
+        const void *planes[3] = { h->in_mem[slot[1] * 3 + 0], h->in_mem[slot[1] * 3 + 1], h->in_mem[slot[1] * 3 + 2] };
+        if (hbcu::eedi2_run(h->eedi, planes, !parity, h->s_compute) != 0) return -1;
+    }
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const Geom &g = h->g[pl];
+        uint8_t *dst = h->out_mem[oslot * 3 + pl];
+        if (frame_mode == 0 || (use_eedi && !(frame_mode & HBCU_DECOMB_YADIF)))
+        {
+            // pass-through (hb_buffer_copy) or "just EEDI2": whole-plane copy (decomb template :855-875, :893-896)
+            const uint8_t *src = frame_mode == 0 ? h->in_mem[slot[1] * 3 + pl] : (const uint8_t *)hbcu::eedi2_output(h->eedi, pl);
+            dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
+            if (h->bps == 1) copy_rows_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(src, g.pitch, dst, g.pitch, g.w, g.h);
+            else copy_rows_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.pitch, (uint16_t *)dst, g.pitch, g.w, g.h);
+            hbcu::count_launch();
+            HBCU_CHECK(cudaGetLastError());
+            continue;
+        }
+        FieldParams fp;
+        fp.prev = h->in_mem[slot[0] * 3 + pl];
+        fp.cur  = h->in_mem[slot[1] * 3 + pl];
+        fp.next = h->in_mem[slot[2] * 3 + pl];
+        fp.eedi = use_eedi ? hbcu::eedi2_output(h->eedi, pl) : nullptr;
+        fp.dst = dst;
+        fp.w = g.w; fp.h = g.h; fp.pitch = g.pitch; fp.dpitch = g.pitch; fp.epitch = g.pitch;
+        fp.mode = frame_mode; fp.parity = parity; fp.tff = tff; fp.maxv = h->maxv;
+        dim3 blk(64, 4), grid(((g.w + 3) / 4 + 63) / 64, (g.h + 3) / 4);
+        if (h->bps == 1) decomb_field_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(fp);
+        else             decomb_field_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>(fp);
+        hbcu::count_launch();
+        HBCU_CHECK(cudaGetLastError());
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_kernel[oslot], h->s_compute));
+    // prev leaves the window once the last field of this frame is done; recording after every field is harmless
+    HBCU_CHECK(cudaEventRecord(h->ev_readers[slot[0]], h->s_compute));
+    h->out_ticket[oslot] = ticket;
+    return 0;
+}
+
+int find_ticket(hbcu_decomb_s *h, int64_t ticket)
+{
+    for (int s = 0; s < h->out_slots; s++)
+        if (h->out_ticket[s] == ticket) return s;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
+{
+    if (out == nullptr || cfg == nullptr) { set_error("decomb_create: null argument"); return -1; }
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->depth < 8 || cfg->depth > 16)
+    {
+        set_error("decomb_create: unsupported geometry %dx%d depth %d", cfg->width, cfg->height, cfg->depth);
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+    {
+        cudaGetLastError();
+        set_error("decomb_create: CUDA device %d not available (%d devices); there is no CPU fallback", cfg->device, ndev);
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(cfg->device));
+    hbcu_decomb_s *h = new (std::nothrow) hbcu_decomb_s();
+    if (h == nullptr) { set_error("decomb_create: out of memory"); return -1; }
+    h->cfg = *cfg;
+    h->bps = cfg->depth > 8 ? 2 : 1;
+    h->maxv = (1 << cfg->depth) - 1;
+    h->slots = cfg->slots >= 4 ? cfg->slots : 4;
+    h->out_slots = cfg->out_slots >= 2 ? cfg->out_slots : 4;
+    h->next_out = 0;
+    h->eedi = nullptr;
+    h->s_h2d = h->s_compute = h->s_d2h = nullptr;
+    h->ev_mark[0] = h->ev_mark[1] = nullptr;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        Geom &g = h->g[pl];
+        g.w = pl == 0 ? cfg->width : -((-cfg->width) >> cfg->chroma_shift_w);
+        g.h = pl == 0 ? cfg->height : -((-cfg->height) >> cfg->chroma_shift_h);
+        // the reference's planes have stride == hb_image_stride (64-byte multiple); EEDI2 reads across row ends
+        // (SURVEY.md 8a/a26), so the device pitch reproduces exactly that stride
+        g.pitch = ((g.w * h->bps + 63) / 64 * 64) / h->bps;
+        g.bytes = (size_t)g.pitch * g.h * h->bps;
+    }
+#define CK(expr)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));            \
+            hbcu_decomb_destroy(h);                                               \
+            return -1;                                                            \
+        }                                                                         \
+    } while (0)
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    h->in_mem.assign(h->slots * 3, nullptr);
+    h->in_index.assign(h->slots, -1);
+    h->ev_upload.assign(h->slots, nullptr);
+    h->ev_readers.assign(h->slots, nullptr);
+    h->out_mem.assign(h->out_slots * 3, nullptr);
+    h->out_ticket.assign(h->out_slots, -1);
+    h->ev_kernel.assign(h->out_slots, nullptr);
+    h->ev_d2h.assign(h->out_slots, nullptr);
+    for (int s = 0; s < h->slots; s++)
+    {
+        CK(cudaEventCreateWithFlags(&h->ev_upload[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_readers[s], cudaEventDisableTiming));
+        for (int pl = 0; pl < 3; pl++)
+        {
+            // one guard row above and below: EEDI2's linear addressing may step one row outside (never used for results)
+            CK(cudaMalloc(&h->in_mem[s * 3 + pl], h->g[pl].bytes));
+            CK(cudaMemset(h->in_mem[s * 3 + pl], 0, h->g[pl].bytes));
+        }
+    }
+    for (int s = 0; s < h->out_slots; s++)
+    {
+        CK(cudaEventCreateWithFlags(&h->ev_kernel[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_d2h[s], cudaEventDisableTiming));
+        for (int pl = 0; pl < 3; pl++) CK(cudaMalloc(&h->out_mem[s * 3 + pl], h->g[pl].bytes));
+    }
+    CK(cudaEventCreate(&h->ev_mark[0]));
+    CK(cudaEventCreate(&h->ev_mark[1]));
+#undef CK
+    if (cfg->mode & HBCU_DECOMB_EEDI2)
+    {
+        hbcu::Eedi2Config ec;
+        ec.depth = cfg->depth;
+        for (int pl = 0; pl < 3; pl++) { ec.w[pl] = h->g[pl].w; ec.h[pl] = h->g[pl].h; ec.pitch[pl] = h->g[pl].pitch; }
+        ec.mthresh = cfg->magnitude_threshold; ec.vthresh = cfg->variance_threshold; ec.lthresh = cfg->laplacian_threshold;
+        ec.dstr = cfg->dilation_threshold; ec.estr = cfg->erosion_threshold; ec.nt = cfg->noise_threshold;
+        ec.maxd = cfg->maximum_search_distance; ec.pp = cfg->post_processing;
+        // decomb.c:291-296: the half-height EEDI2 buffers are frames of height/2 (chroma rounds up from that)
+        ec.half_frame_height = cfg->height / 2;
+        ec.chroma_shift_h = cfg->chroma_shift_h;
+        h->eedi = hbcu::eedi2_create(ec);
+        if (h->eedi == nullptr)
+        {
+            hbcu_decomb_destroy(h);
+            return -1;
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+void hbcu_decomb_destroy(hbcu_decomb_t *h)
+{
+    if (h == nullptr) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    if (h->eedi) hbcu::eedi2_destroy(h->eedi);
+    for (auto p : h->in_mem) if (p) cudaFree(p);
+    for (auto p : h->out_mem) if (p) cudaFree(p);
+    for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_readers) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_kernel) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_d2h) if (e) cudaEventDestroy(e);
+    if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
+    if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+static int decomb_upload(hbcu_decomb_t *h, int64_t index, const void *const planes[3], const int strides[3], cudaMemcpyKind kind)
+{
+    if (h == nullptr || planes == nullptr || strides == nullptr || index < 0) { set_error("decomb_upload: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int slot = (int)(index % h->slots);
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_readers[slot], 0));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const Geom &g = h->g[pl];
+        // copy whole strides when the layouts agree (the stride padding is part of what EEDI2 may read)
+        const size_t row = (size_t)strides[pl] == (size_t)g.pitch * h->bps ? (size_t)g.pitch * h->bps : (size_t)g.w * h->bps;
+        HBCU_CHECK(cudaMemcpy2DAsync(h->in_mem[slot * 3 + pl], (size_t)g.pitch * h->bps, planes[pl], (size_t)strides[pl],
+                                     row, (size_t)g.h, kind, h->s_h2d));
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_upload[slot], h->s_h2d));
+    h->in_index[slot] = index;
+    return 0;
+}
+
+int hbcu_decomb_upload(hbcu_decomb_t *h, int64_t index, const void *const planes[3], const int strides[3])
+{
+    return decomb_upload(h, index, planes, strides, cudaMemcpyHostToDevice);
+}
+
+int hbcu_decomb_upload_device(hbcu_decomb_t *h, int64_t index, const void *const dplanes[3], const int strides[3])
+{
+    return decomb_upload(h, index, dplanes, strides, cudaMemcpyDeviceToDevice);
+}
+
+int hbcu_decomb_wait_upload(hbcu_decomb_t *h, int64_t index)
+{
+    if (h == nullptr || index < 0) { set_error("decomb_wait_upload: bad argument"); return -1; }
+    const int slot = (int)(index % h->slots);
+    if (h->in_index[slot] != index) return 0;     // overwritten since: that upload waited for its readers, which waited for ours
+    HBCU_CHECK(cudaEventSynchronize(h->ev_upload[slot]));
+    return 0;
+}
+
+int hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
+                       int frame_mode, int parity, int tff, void *const planes[3], const int strides[3])
+{
+    if (h == nullptr || planes == nullptr || strides == nullptr) { set_error("decomb_filter: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = h->next_out;
+    h->next_out = (h->next_out + 1) % h->out_slots;
+    if (run_field(h, ticket, prev, cur, next, frame_mode, parity, tff, oslot) != 0) return -1;
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_kernel[oslot], 0));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const Geom &g = h->g[pl];
+        HBCU_CHECK(cudaMemcpy2DAsync(planes[pl], (size_t)strides[pl], h->out_mem[oslot * 3 + pl], (size_t)g.pitch * h->bps,
+                                     (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_d2h));
+    return 0;
+}
+
+int hbcu_decomb_filter_device(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
+                              int frame_mode, int parity, int tff, void *out_planes[3], int out_strides[3])
+{
+    if (h == nullptr) { set_error("decomb_filter_device: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = h->next_out;
+    h->next_out = (h->next_out + 1) % h->out_slots;
+    if (run_field(h, ticket, prev, cur, next, frame_mode, parity, tff, oslot) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_compute));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (out_planes) out_planes[pl] = h->out_mem[oslot * 3 + pl];
+        if (out_strides) out_strides[pl] = h->g[pl].pitch * h->bps;
+    }
+    return 0;
+}
+
+int hbcu_decomb_wait(hbcu_decomb_t *h, int64_t ticket)
+{
+    if (h == nullptr) { set_error("decomb_wait: null handle"); return -1; }
+    const int s = find_ticket(h, ticket);
+    if (s < 0) { set_error("decomb_wait: ticket %lld is not in flight", (long long)ticket); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_d2h[s]));
+    return 0;
+}
+
+int hbcu_decomb_poll(hbcu_decomb_t *h, int64_t ticket)
+{
+    if (h == nullptr) { set_error("decomb_poll: null handle"); return -1; }
+    const int s = find_ticket(h, ticket);
+    if (s < 0) { set_error("decomb_poll: ticket %lld is not in flight", (long long)ticket); return -1; }
+    cudaError_t e = cudaEventQuery(h->ev_d2h[s]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    set_error("decomb_poll: %s", cudaGetErrorString(e));
+    return -1;
+}
+
+int hbcu_decomb_debug_eedi2(hbcu_decomb_t *h, int which, void *host, size_t host_bytes)
+{
+    if (h == nullptr || h->eedi == nullptr) { set_error("decomb_debug_eedi2: no EEDI2 state"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaDeviceSynchronize());
+    return hbcu::eedi2_debug_read(h->eedi, which, host, host_bytes);
+}
+
+int hbcu_decomb_sync(hbcu_decomb_t *h)
+{
+    if (h == nullptr) { set_error("decomb_sync: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
+    return 0;
+}
+
+int hbcu_decomb_mark(hbcu_decomb_t *h, int which)
+{
+    if (h == nullptr || which < 0 || which > 1) { set_error("decomb_mark: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaEventRecord(h->ev_mark[which], h->s_compute));
+    return 0;
+}
+
+int hbcu_decomb_elapsed_ms(hbcu_decomb_t *h, float *ms)
+{
+    if (h == nullptr || ms == nullptr) { set_error("decomb_elapsed_ms: bad argument"); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_mark[1]));
+    HBCU_CHECK(cudaEventElapsedTime(ms, h->ev_mark[0], h->ev_mark[1]));
+    return 0;
+}
+
+}  // extern "C"

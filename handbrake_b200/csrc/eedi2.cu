@@ -1,0 +1,919 @@
+// eedi2.cu -- EEDI2 edge-directed interpolation of one field to a full frame, for sm_100a.
+//
+// Replaces the stage chain eedi2_interpolate_plane (reference libhb/templates/decomb_template.c:366-441)
+// and the stages it calls (libhb/templates/eedi2_template.c, HandBrake's fork of tritical's EEDI2):
+//   fill_half_height_buffer_plane :79-92     upscale_by_2 :101-111      build_edge_mask :122-195
+//   dilate :207-247   erode :259-293   remove_small_gaps :308-342       calc_directions :358-525
+//   filter_map :538-635   filter_dir_map :649-709   expand_dir_map :722-773
+//   mark_directions_2x :787-858   filter_dir_map_2x :872-939   expand_dir_map_2x :953-1011
+//   fill_gaps_2x :1025-1132   interpolate_lattice :1148-1335   post_process :1349-1378
+// The reference runs the three planes on three CPU threads; here every stage is one kernel per
+// plane on the decomb stream (planes are independent, stages are ordered by the stream).
+//
+// Bit-exactness notes (all reproduced on purpose):
+//   * buffers keep the reference's LINEAR layout: one allocation per "frame buffer", planes
+//     back to back, row pitch = hb_image_stride; several stages index x-1-u / x+1+u without
+//     clamping, i.e. they read the neighbouring rows (or the neighbouring plane) through the
+//     linear address, and interpolate_lattice reads dmskp[-1] / dmskp[width];
+//   * the edge mask buffer is cleared only in its top half on each call (:132), the bottom half
+//     carries the previous field's final mask: the buffers are persistent and fields are
+//     processed in stream order;
+//   * constants declared `pixel` wrap at 8 bits (nt13 = 138, nt19 = 182, nt4 = 200, nt7 = 94,
+//     nt8 = 144) while `min == 7*nt` compares against the unwrapped 350;
+//   * build_edge_mask is called with (magnitude, variance, laplacian) but declares
+//     (mthresh, lthresh, vthresh): the two are swapped inside, as in the reference;
+//   * mark_directions_2x compares dmskp[x+1] with dmskpn[x-1] (:835);
+//   * interpolate_lattice rewrites the direction map in place and pixel x reads the rewritten
+//     dmskp[x-1]: a parallel pass computes both possible outcomes per pixel, a per-row
+//     sequential pass resolves the chain;
+//   * float/double expressions ((float)sum/(float)count, j*step+0.5) are evaluated with explicit
+//     round-to-nearest operations, no FMA contraction.
+// Memory outside the planes (before the first plane, after the last) reads as zero, which is
+// what the zero-initialised shim buffers of the oracle give (libhb proper leaves it undefined).
+#include "hbcu_common.h"
+#include "eedi2.cuh"
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace hbcu {
+
+namespace {
+
+constexpr int kLeadSlack = 1024;          // zero bytes in front of every frame buffer
+constexpr int kTailRows  = 4;             // zero rows (of the luma pitch) behind every frame buffer
+
+enum { SRCPF = 0, MSKPF = 1, TMPPF = 2, DSTPF = 3 };                       // decomb.c:64-68
+enum { DST2PF = 0, TMP2PF2 = 1, MSK2PF = 2, TMP2PF = 3, DST2MPF = 4 };     // decomb.c:70-74
+
+struct Lim { int v[33]; };                // eedi_limlut, pixel-typed values widened to int
+
+__device__ __forceinline__ int iabs(int a) { return a < 0 ? -a : a; }
+
+// eedi2_sort_metrics (eedi2.c:66-80)
+__device__ __forceinline__ void sort_metrics(int *order, int length)
+{
+    for (int i = 1; i < length; ++i)
+    {
+        int j = i;
+        const int temp = order[j];
+        while (j > 0 && order[j - 1] > temp)
+        {
+            order[j] = order[j - 1];
+            --j;
+        }
+        order[j] = temp;
+    }
+}
+
+__device__ __forceinline__ int median_of(const int *order, int n)
+{
+    return (n & 1) ? order[n >> 1] : (order[(n - 1) >> 1] + order[n >> 1] + 1) >> 1;
+}
+
+// (int)(((float)(sum + mid) / (float)(count + 1)) + 0.5f)
+__device__ __forceinline__ int avg_round(int sum, int mid, int count)
+{
+    return (int)__fadd_rn(__fdiv_rn((float)(sum + mid), (float)(count + 1)), 0.5f);
+}
+
+template <typename PIX>
+struct K            // per-depth constants
+{
+    int depth, shift, shift2, peak, neutral;
+    __host__ __device__ explicit K(int d) : depth(d), shift(d - 8), shift2(2 + d - 8), peak((1 << d) - 1), neutral(1 << (d - 1)) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// copies
+// ---------------------------------------------------------------------------------------------
+template <typename PIX>
+__global__ void k_fill_half(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int rows)
+{
+    // row r of the field buffer = row 2r of src (src already points at the field's first line); whole pitch
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (x < pitch && r < rows) dst[(size_t)r * pitch + x] = src[(size_t)2 * r * pitch + x];
+}
+
+template <typename PIX>
+__global__ void k_upscale2(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int rows)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (x < pitch && r < rows)
+    {
+        const PIX v = src[(size_t)r * pitch + x];
+        dst[(size_t)(2 * r) * pitch + x] = v;
+        dst[(size_t)(2 * r + 1) * pitch + x] = v;
+    }
+}
+
+template <typename PIX>
+__global__ void k_blit(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int width, int rows)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (x < width && r < rows) dst[(size_t)r * pitch + x] = src[(size_t)r * pitch + x];
+}
+
+template <typename PIX>
+__global__ void k_fill(PIX *__restrict__ dst, size_t n, int value)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (PIX)value;
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge mask (:122-195).  NB parameter names follow the callee: lthresh receives the variance
+// setting and vthresh the laplacian setting.
+// ---------------------------------------------------------------------------------------------
+template <typename PIX>
+__global__ void k_edge_mask(PIX *__restrict__ dstp, const PIX *__restrict__ srcp, int pitch, int width, int height,
+                            int mthresh10, int lthresh, int vthresh81, int depth)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < 1 || x >= width - 1 || y < 1 || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const int ten = (int)(PIX)(10 << k.shift);
+    const PIX *c = srcp + (size_t)y * pitch, *p = c - pitch, *n = c + pitch;
+    const int pm = p[x - 1], pc = p[x], pp = p[x + 1], cm = c[x - 1], cc = c[x], cp = c[x + 1], nm = n[x - 1], nc = n[x], np = n[x + 1];
+    if ((iabs(pc - cc) < ten && iabs(cc - nc) < ten && iabs(pc - nc) < ten) ||
+        (iabs(pm - cm) < ten && iabs(cm - nm) < ten && iabs(pm - nm) < ten &&
+         iabs(pp - cp) < ten && iabs(cp - np) < ten && iabs(pp - np) < ten))
+        return;
+    const int s = k.shift;
+    const int sum = (pm + pc + pp + cm + cc + cp + nm + nc + np) >> s;
+    const int sumsq = (pm >> s) * (pm >> s) + (pc >> s) * (pc >> s) + (pp >> s) * (pp >> s) +
+                      (cm >> s) * (cm >> s) + (cc >> s) * (cc >> s) + (cp >> s) * (cp >> s) +
+                      (nm >> s) * (nm >> s) + (nc >> s) * (nc >> s) + (np >> s) * (np >> s);
+    if (9 * sumsq - sum * sum < vthresh81) return;
+    const int Ix = (cp - cm) >> s;
+    const int Iy = max(max(iabs(pc - nc), iabs(pc - cc)), iabs(cc - nc)) >> s;
+    if (Ix * Ix + Iy * Iy >= mthresh10)
+    {
+        dstp[(size_t)y * pitch + x] = (PIX)k.peak;
+        return;
+    }
+    const int Ixx = (cm - 2 * cc + cp) >> s;
+    const int Iyy = (pc - 2 * cc + nc) >> s;
+    if (iabs(Ixx) + iabs(Iyy) >= lthresh) dstp[(size_t)y * pitch + x] = (PIX)k.peak;
+}
+
+// erode (:259-293) / dilate (:207-247): dst = copy of src over `width`, interior rule applied
+template <typename PIX, bool DILATE>
+__global__ void k_morph(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height, int str, int depth)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const int peak = (1 << depth) - 1;
+    const PIX *c = mskp + (size_t)y * pitch;
+    int v = c[x];
+    if (x >= 1 && x < width - 1 && y >= 1 && y < height - 1 && (DILATE ? v == 0 : v == peak))
+    {
+        const PIX *p = c - pitch, *n = c + pitch;
+        int count = 0;
+        count += p[x - 1] == peak; count += p[x] == peak; count += p[x + 1] == peak;
+        count += c[x - 1] == peak; count += c[x + 1] == peak;
+        count += n[x - 1] == peak; count += n[x] == peak; count += n[x + 1] == peak;
+        if (DILATE) { if (count >= str) v = peak; }
+        else        { if (count < str) v = 0; }
+    }
+    dstp[(size_t)y * pitch + x] = (PIX)v;
+}
+
+// remove_small_gaps (:308-342)
+template <typename PIX>
+__global__ void k_gaps(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height, int depth)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const int peak = (1 << depth) - 1;
+    const PIX *m = mskp + (size_t)y * pitch;
+    int v = m[x];
+    if (y >= 1 && y < height - 1 && x >= 3 && x < width - 3)
+    {
+        if (m[x])
+        {
+            if (!(m[x - 3] || m[x - 2] || m[x - 1] || m[x + 1] || m[x + 2] || m[x + 3])) v = 0;
+        }
+        else
+        {
+            if ((m[x + 1] && (m[x - 1] || m[x - 2] || m[x - 3])) || (m[x + 2] && (m[x - 1] || m[x - 2])) || (m[x + 3] && m[x - 1]))
+                v = peak;
+        }
+    }
+    dstp[(size_t)y * pitch + x] = (PIX)v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calc_directions (:358-525): dst pre-filled with peak (whole pitch); one thread per pixel
+// ---------------------------------------------------------------------------------------------
+template <typename PIX>
+__global__ void k_calc_directions(int plane, const PIX *__restrict__ mskp, const PIX *__restrict__ srcp, PIX *__restrict__ dstp,
+                                  int pitch, int width, int height, int maxd, int nt, int depth, Lim lim)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < 1 || x >= width - 1 || y < 1 || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const PIX *mc = mskp + (size_t)y * pitch, *mp = mc - pitch, *mn = mc + pitch;
+    if (mc[x] != k.peak || (mc[x - 1] != k.peak && mc[x + 1] != k.peak)) return;
+    const PIX *sc = srcp + (size_t)y * pitch, *sp = sc - pitch, *sn = sc + pitch, *s2p = sc - 2 * pitch, *s2n = sc + 2 * pitch;
+    const int nt13 = (int)(PIX)((nt << (depth - 8)) * 13);
+    const int nt19 = (int)(PIX)((nt << (depth - 8)) * 19);
+    const int maxdt = plane == 0 ? maxd : (maxd >> 1);
+    const int startu = max(-x + 1, -maxdt), stopu = min(width - 2 - x, maxdt);
+    const int base = iabs((int)sc[x] - (int)sn[x]) + iabs((int)sc[x] - (int)sp[x]);
+    int minb = min(nt13, base * 6), mina = min(nt19, base * 9);
+    int minc = mina, mind = minb, mine = minb;
+    int dira = -5000, dirb = -5000, dirc = -5000, dird = -5000, dire = -5000;
+    const int c0 = sc[x - 1], c1 = sc[x], c2 = sc[x + 1];
+    const int p0 = sp[x - 1], p1 = sp[x], p2 = sp[x + 1];
+    const int n0 = sn[x - 1], n1 = sn[x], n2 = sn[x + 1];
+    for (int u = startu; u <= stopu; ++u)
+    {
+        if (!(y == 1 || mp[x - 1 + u] == k.peak || mp[x + u] == k.peak || mp[x + 1 + u] == k.peak)) continue;
+        if (!(y == height - 2 || mn[x - 1 - u] == k.peak || mn[x - u] == k.peak || mn[x + 1 - u] == k.peak)) continue;
+        const int diffsn = iabs(c0 - (int)sn[x - 1 - u]) + iabs(c1 - (int)sn[x - u]) + iabs(c2 - (int)sn[x + 1 - u]);
+        const int diffsp = iabs(c0 - (int)sp[x - 1 + u]) + iabs(c1 - (int)sp[x + u]) + iabs(c2 - (int)sp[x + 1 + u]);
+        const int diffps = iabs(p0 - (int)sc[x - 1 - u]) + iabs(p1 - (int)sc[x - u]) + iabs(p2 - (int)sc[x + 1 - u]);
+        const int diffns = iabs(n0 - (int)sc[x - 1 + u]) + iabs(n1 - (int)sc[x + u]) + iabs(n2 - (int)sc[x + 1 + u]);
+        const int diff = diffsn + diffsp + diffps + diffns;
+        int diffd = diffsp + diffns, diffe = diffsn + diffps;
+        if (diff < minb) { dirb = u; minb = diff; }
+        if (y > 1)
+        {
+            const int diff2pp = iabs((int)s2p[x - 1] - (int)sp[x - 1 - u]) + iabs((int)s2p[x] - (int)sp[x - u]) + iabs((int)s2p[x + 1] - (int)sp[x + 1 - u]);
+            const int diffp2p = iabs(p0 - (int)s2p[x - 1 + u]) + iabs(p1 - (int)s2p[x + u]) + iabs(p2 - (int)s2p[x + 1 + u]);
+            const int diffa = diff + diff2pp + diffp2p;
+            diffd += diffp2p;
+            diffe += diff2pp;
+            if (diffa < mina) { dira = u; mina = diffa; }
+        }
+        if (y < height - 2)
+        {
+            const int diff2nn = iabs((int)s2n[x - 1] - (int)sn[x - 1 + u]) + iabs((int)s2n[x] - (int)sn[x + u]) + iabs((int)s2n[x + 1] - (int)sn[x + 1 + u]);
+            const int diffn2n = iabs(n0 - (int)s2n[x - 1 - u]) + iabs(n1 - (int)s2n[x - u]) + iabs(n2 - (int)s2n[x + 1 - u]);
+            const int diffc = diff + diff2nn + diffn2n;
+            diffd += diff2nn;
+            diffe += diffn2n;
+            if (diffc < minc) { dirc = u; minc = diffc; }
+        }
+        if (diffd < mind) { dird = u; mind = diffd; }
+        if (diffe < mine) { dire = u; mine = diffe; }
+    }
+    int order[5], n = 0;
+    if (dira != -5000) order[n++] = dira;
+    if (dirb != -5000) order[n++] = dirb;
+    if (dirc != -5000) order[n++] = dirc;
+    if (dird != -5000) order[n++] = dird;
+    if (dire != -5000) order[n++] = dire;
+    int out = k.neutral;
+    if (n > 1)
+    {
+        sort_metrics(order, n);
+        const int mid = median_of(order, n);
+        const int tlim = max(lim.v[iabs(mid)] >> 2, 2);
+        int sum = 0, count = 0;
+        for (int i = 0; i < n; ++i)
+            if (iabs(order[i] - mid) <= tlim) { ++count; sum += order[i]; }
+        if (count > 1) out = k.neutral + ((int)__fdiv_rn((float)sum, (float)count)) * (1 << k.shift2);
+    }
+    dstp[(size_t)y * pitch + x] = (PIX)out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter_dir_map (:649-709) and expand_dir_map (:722-773); also their 2x variants (:872-1011)
+//   TWOX = false: rows 1..h-2, neighbours at +-pitch
+//   TWOX = true : rows y = 2-field, +2 ...; neighbours at +-2*pitch, gated by y>1 / y<h-2; the
+//                 mask test uses rows y-1 and y+1 of the (line-doubled) edge mask
+// ---------------------------------------------------------------------------------------------
+template <typename PIX, bool EXPAND, bool TWOX>
+__global__ void k_dir_map(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                          int pitch, int width, int height, int field, int depth, Lim lim)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const K<PIX> k(depth);
+    const PIX *dc = dmskp + (size_t)y * pitch;
+    int v = dc[x];                                   // bit_blit: dst starts as a copy of dmsk (over width)
+    const bool row_ok = TWOX ? (y >= 2 - field && y < height - 1 && ((y - (2 - field)) & 1) == 0) : (y >= 1 && y < height - 1);
+    if (row_ok && x >= 1 && x < width - 1)
+    {
+        bool active;
+        if (TWOX)
+        {
+            const PIX *m0 = mskp + (size_t)(y - 1) * pitch, *m1 = mskp + (size_t)(y + 1) * pitch;
+            active = !(m0[x] != k.peak && m1[x] != k.peak);
+        }
+        else
+        {
+            active = mskp[(size_t)y * pitch + x] == k.peak;
+        }
+        if (EXPAND) active = active && dc[x] == k.peak;
+        if (active)
+        {
+            const int step = TWOX ? 2 * pitch : pitch;
+            const PIX *dp = dc - step, *dn = dc + step;
+            const bool up = !TWOX || y > 1, down = !TWOX || y < height - 2;
+            int u = 0, order[9];
+            if (up)
+            {
+                if (dp[x - 1] != k.peak) order[u++] = dp[x - 1];
+                if (dp[x]     != k.peak) order[u++] = dp[x];
+                if (dp[x + 1] != k.peak) order[u++] = dp[x + 1];
+            }
+            if (dc[x - 1] != k.peak) order[u++] = dc[x - 1];
+            if (!EXPAND && dc[x] != k.peak) order[u++] = dc[x];
+            if (dc[x + 1] != k.peak) order[u++] = dc[x + 1];
+            if (down)
+            {
+                if (dn[x - 1] != k.peak) order[u++] = dn[x - 1];
+                if (dn[x]     != k.peak) order[u++] = dn[x];
+                if (dn[x + 1] != k.peak) order[u++] = dn[x + 1];
+            }
+            if (EXPAND)
+            {
+                if (u >= 5)
+                {
+                    sort_metrics(order, u);
+                    const int mid = median_of(order, u);
+                    const int l = lim.v[iabs(mid - k.neutral) >> k.shift2];
+                    int sum = 0, count = 0;
+                    for (int i = 0; i < u; ++i)
+                        if (iabs(order[i] - mid) <= l) { ++count; sum += order[i]; }
+                    if (count >= 5) v = (int)(PIX)avg_round(sum, mid, count);
+                }
+            }
+            else
+            {
+                if (u < 4)
+                    v = k.peak;
+                else
+                {
+                    sort_metrics(order, u);
+                    const int mid = median_of(order, u);
+                    const int l = lim.v[iabs(mid - k.neutral) >> k.shift2];
+                    int sum = 0, count = 0;
+                    for (int i = 0; i < u; ++i)
+                        if (iabs(order[i] - mid) <= l) { ++count; sum += order[i]; }
+                    if (count < 4 || (count < 5 && dc[x] == k.peak)) v = k.peak;
+                    else v = (int)(PIX)avg_round(sum, mid, count);
+                }
+            }
+        }
+    }
+    dstp[(size_t)y * pitch + x] = (PIX)v;
+}
+
+// filter_map (:538-635)
+template <typename PIX>
+__global__ void k_filter_map(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                             int pitch, int width, int height, int depth)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const K<PIX> k(depth);
+    const PIX *dc = dmskp + (size_t)y * pitch;
+    int v = dc[x];
+    if (y >= 1 && y < height - 1 && x >= 1 && x < width - 1 && !(dc[x] == k.peak || mskp[(size_t)y * pitch + x] != k.peak))
+    {
+        const PIX *dp = dc - pitch, *dn = dc + pitch;
+        const int shift = k.shift2;                       // `shift` in the callee is 2 + (depth - 8)
+        const int twelve = 12 << shift;
+        const int cur = dc[x];
+        int dir = (cur - k.neutral) >> 2;
+        const int lm = max(iabs(dir) * 2, twelve);
+        dir >>= shift;
+        int ict = 0, icb = 0;
+#define EEDI_BAD(row, j) ((iabs((int)(row)[x + (j)] - cur) > lm && (row)[x + (j)] != k.peak))
+        if (dir < 0)
+        {
+            const int dirt = max(-x, dir);
+            for (int j = dirt; j <= 0; ++j)
+                if (EEDI_BAD(dp, j) || (dc[x + j] == k.peak && dp[x + j] == k.peak) || EEDI_BAD(dc, j)) { ict = 1; break; }
+        }
+        else
+        {
+            const int dirt = min(width - x - 1, dir);
+            for (int j = 0; j <= dirt; ++j)
+                if (EEDI_BAD(dp, j) || (dc[x + j] == k.peak && dp[x + j] == k.peak) || EEDI_BAD(dc, j)) { ict = 1; break; }
+        }
+        if (ict)
+        {
+            if (dir < 0)
+            {
+                const int dirt = min(width - x - 1, iabs(dir));
+                for (int j = 0; j <= dirt; ++j)
+                    if (EEDI_BAD(dn, j) || (dn[x + j] == k.peak && dc[x + j] == k.peak) || EEDI_BAD(dc, j)) { icb = 1; break; }
+            }
+            else
+            {
+                const int dirt = max(-x, -dir);
+                for (int j = dirt; j <= 0; ++j)
+                    if (EEDI_BAD(dn, j) || (dn[x + j] == k.peak && dc[x + j] == k.peak) || EEDI_BAD(dc, j)) { icb = 1; break; }
+            }
+            if (icb) v = k.peak;
+        }
+#undef EEDI_BAD
+    }
+    dstp[(size_t)y * pitch + x] = (PIX)v;
+}
+
+// mark_directions_2x (:787-858): dst pre-filled with peak (whole pitch)
+template <typename PIX>
+__global__ void k_mark_directions_2x(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                     int pitch, int width, int height, int tff, int depth, Lim lim)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 2 - tff + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    if (x < 1 || x >= width - 1 || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const PIX *m0 = mskp + (size_t)(y - 1) * pitch, *m1 = m0 + 2 * pitch;
+    if (m0[x] != k.peak && m1[x] != k.peak) return;
+    const PIX *d0 = dmskp + (size_t)(y - 1) * pitch, *d1 = d0 + 2 * pitch;
+    int v = 0, order[6];
+    if (d0[x - 1] != k.peak) order[v++] = d0[x - 1];
+    if (d0[x]     != k.peak) order[v++] = d0[x];
+    if (d0[x + 1] != k.peak) order[v++] = d0[x + 1];
+    if (d1[x - 1] != k.peak) order[v++] = d1[x - 1];
+    if (d1[x]     != k.peak) order[v++] = d1[x];
+    if (d1[x + 1] != k.peak) order[v++] = d1[x + 1];
+    if (v < 3) return;
+    sort_metrics(order, v);
+    const int mid = median_of(order, v);
+    const int l = lim.v[iabs(mid - k.neutral) >> k.shift2];
+    int u = 0;
+    if (iabs((int)d0[x - 1] - (int)d1[x - 1]) <= l || d0[x - 1] == k.peak || d1[x - 1] == k.peak) ++u;
+    if (iabs((int)d0[x] - (int)d1[x]) <= l || d0[x] == k.peak || d1[x] == k.peak) ++u;
+    if (iabs((int)d0[x + 1] - (int)d1[x - 1]) <= l || d0[x + 1] == k.peak || d1[x + 1] == k.peak) ++u;    // sic (:835)
+    if (u < 2) return;
+    int count = 0, sum = 0;
+    for (int i = 0; i < v; ++i)
+        if (iabs(order[i] - mid) <= l) { ++count; sum += order[i]; }
+    if (count < v - 2 || count < 2) return;
+    dstp[(size_t)y * pitch + x] = (PIX)avg_round(sum, mid, count);
+}
+
+// fill_gaps_2x (:1025-1132): dst already holds a copy of dmsk (k_blit); threads of one gap write identical values
+template <typename PIX>
+__global__ void k_fill_gaps_2x(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                               int pitch, int width, int height, int field, int depth)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 2 - field + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    if (x < 1 || x >= width - 1 || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const int eight = 8 << k.shift, twenty = 20 << k.shift, fiveHundred = 500 << k.shift;
+    const PIX *dc = dmskp + (size_t)y * pitch, *dp = dc - 2 * pitch, *dn = dc + 2 * pitch;
+    const PIX *mc = mskp + (size_t)(y - 1) * pitch, *mpp = mc - 2 * pitch, *mn = mc + 2 * pitch, *mnn = mn + 2 * pitch;
+    if (dc[x] != k.peak || (mc[x] != k.peak && mn[x] != k.peak)) return;
+    int u = x - 1, back = fiveHundred, forward = -fiveHundred;
+    while (u)
+    {
+        if (dc[u] != k.peak) { back = dc[u]; break; }
+        if (mc[u] != k.peak && mn[u] != k.peak) break;
+        --u;
+    }
+    int v = x + 1;
+    while (v < width)
+    {
+        if (dc[v] != k.peak) { forward = dc[v]; break; }
+        if (mc[v] != k.peak && mn[v] != k.peak) break;
+        ++v;
+    }
+    int tc = 1, bc = 1;
+    int mint = fiveHundred, maxt = -twenty, minb = fiveHundred, maxb = -twenty;
+    for (int j = u; j <= v; ++j)
+    {
+        if (tc)
+        {
+            if (y <= 2 || dp[j] == k.peak || (mpp[j] != k.peak && mc[j] != k.peak)) { tc = 0; mint = maxt = twenty; }
+            else { if ((int)dp[j] < mint) mint = dp[j]; if ((int)dp[j] > maxt) maxt = dp[j]; }
+        }
+        if (bc)
+        {
+            if (y >= height - 3 || dn[j] == k.peak || (mn[j] != k.peak && mnn[j] != k.peak)) { bc = 0; minb = maxb = twenty; }
+            else { if ((int)dn[j] < minb) minb = dn[j]; if ((int)dn[j] > maxb) maxb = dn[j]; }
+        }
+    }
+    if (maxt == -twenty) maxt = mint = twenty;
+    if (maxb == -twenty) maxb = minb = twenty;
+    const int fb = max(iabs(forward - k.neutral), iabs(back - k.neutral));
+    const int thresh = max(max(fb >> 2, eight), max(iabs(mint - maxt), iabs(minb - maxb)));
+    const int flim = min(fb >> k.shift2, 6);
+    if (iabs(forward - back) <= thresh && (v - u - 1 <= flim || tc || bc))
+    {
+        const double step = __ddiv_rn((double)(forward - back), (double)(v - u));
+        PIX *drow = dstp + (size_t)y * pitch;
+        for (int j = 0; j < v - u - 1; ++j)
+            drow[u + j + 1] = (PIX)(back + (int)__dadd_rn(__dmul_rn((double)j, step), 0.5));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// interpolate_lattice (:1148-1335)
+//   pass A (parallel): per pixel, everything that does not depend on the rewritten dmskp[x-1]:
+//     codeA  = what happens when the first test fires (always: vertical average; mask -> neutral unless dir==peak)
+//     resB   = (pixel value, new mask) of the remaining path
+//     gate   = dir==peak (fires regardless) / cond on dmskp[x+1] / lim
+//   pass B (one thread per row): walks x = 0..w-1 carrying the rewritten dmskp[x-1]
+// ---------------------------------------------------------------------------------------------
+struct LatticeTmp            // per pixel, 8 bytes
+{
+    uint16_t valB;           // pixel value of the non-early path
+    uint16_t mskB;           // rewritten mask of the non-early path
+    uint16_t lim;            // lim for the first test
+    uint8_t  nextfar;        // |dmskp[x] - dmskp[x+1]| > lim (uses the ORIGINAL x+1)
+    uint8_t  pad;
+};
+
+template <typename PIX>
+__global__ void k_lattice_a(int plane, const PIX *__restrict__ dmskp, const PIX *__restrict__ dstp_base, const PIX *__restrict__ omsk_base,
+                            LatticeTmp *__restrict__ tmp, int pitch, int width, int height, int field, int nt, int depth, Lim lim)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y;
+    const int y = 2 - field + 2 * row;
+    if (x >= width || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const int three = (int)(PIX)(3 << k.shift), nine = (int)(PIX)(9 << k.shift);
+    const int nt4 = (int)(PIX)((nt << (depth - 8)) * 4);
+    const int nt7 = (int)(PIX)((nt << (depth - 8)) * 7);
+    const int nt8 = (int)(PIX)((nt << (depth - 8)) * 8);
+    const PIX *dm = dmskp + (size_t)y * pitch;
+    const PIX *dstp = dstp_base + (size_t)(y - 1) * pitch, *dstpnn = dstp + 2 * pitch;
+    const PIX *omskp = omsk_base + (size_t)(y - 1) * pitch, *omskn = omskp + 2 * pitch;
+    LatticeTmp t;
+    int dir = dm[x];
+    const int cur = dir;
+    const int l = lim.v[iabs(dir - k.neutral) >> k.shift2];
+    t.lim = (uint16_t)l;
+    t.nextfar = iabs(cur - (int)dm[x + 1]) > l;
+    t.pad = 0;
+    const int avg = ((int)dstp[x] + (int)dstpnn[x] + 1) >> 1;
+    int val = avg, msk = 0;
+    bool done = false;
+    if (dir == k.peak)
+    {
+        done = true;            // early path regardless; values unused
+        msk = k.peak;
+    }
+    if (!done && l < nine)
+    {
+        const int s = k.shift;
+        const int a0 = dstp[x - 1], a1 = dstp[x], a2 = dstp[x + 1], b0 = dstpnn[x - 1], b1 = dstpnn[x], b2 = dstpnn[x + 1];
+        const int sum = (a0 + a1 + a2 + b0 + b1 + b2) >> s;
+        const int sumsq = (a0 >> s) * (a0 >> s) + (a1 >> s) * (a1 >> s) + (a2 >> s) * (a2 >> s) +
+                          (b0 >> s) * (b0 >> s) + (b1 >> s) * (b1 >> s) + (b2 >> s) * (b2 >> s);
+        if (6 * sumsq - sum * sum < 576) { val = avg; msk = k.peak; done = true; }
+    }
+    if (!done && x > 1 && x < width - 2)
+    {
+        const int a = dstp[x], b = dstpnn[x];
+        if ((a < max((int)dstp[x - 2], (int)dstp[x - 1]) - three && a < max((int)dstp[x + 2], (int)dstp[x + 1]) - three &&
+             b < max((int)dstpnn[x - 2], (int)dstpnn[x - 1]) - three && b < max((int)dstpnn[x + 2], (int)dstpnn[x + 1]) - three) ||
+            (a > min((int)dstp[x - 2], (int)dstp[x - 1]) + three && a > min((int)dstp[x + 2], (int)dstp[x + 1]) + three &&
+             b > min((int)dstpnn[x - 2], (int)dstpnn[x - 1]) + three && b > min((int)dstpnn[x + 2], (int)dstpnn[x + 1]) + three))
+        {
+            val = avg; msk = k.neutral; done = true;
+        }
+    }
+    if (!done)
+    {
+        dir = (dir - k.neutral + (1 << (k.shift2 - 1))) >> k.shift2;
+        const int startu = (dir - 2 < 0) ? max(-x + 1, max(dir - 2, -width + 2 + x)) : min(x - 1, min(dir - 2, width - 2 - x));
+        const int stopu  = (dir + 2 < 0) ? max(-x + 1, max(dir + 2, -width + 2 + x)) : min(x - 1, min(dir + 2, width - 2 - x));
+        int mn = nt8;
+        for (int u = startu; u <= stopu; ++u)
+        {
+            const int diff = iabs((int)dstp[x - 1] - (int)dstpnn[x - u - 1]) + iabs((int)dstp[x] - (int)dstpnn[x - u]) +
+                             iabs((int)dstp[x + 1] - (int)dstpnn[x - u + 1]) + iabs((int)dstpnn[x - 1] - (int)dstp[x + u - 1]) +
+                             iabs((int)dstpnn[x] - (int)dstp[x + u]) + iabs((int)dstpnn[x + 1] - (int)dstp[x + u + 1]);
+#define NEAR(arr, idx) ((arr)[(idx)] != k.peak && iabs((int)(arr)[(idx)] - cur) <= l)
+            if (diff < mn &&
+                (NEAR(omskp, x - 1 + u) || NEAR(omskp, x + u) || NEAR(omskp, x + 1 + u)) &&
+                (NEAR(omskn, x - 1 - u) || NEAR(omskn, x - u) || NEAR(omskn, x + 1 - u)))
+            {
+                const int h0 = u >> 1, h1 = (u + 1) >> 1;
+                const int diff2 = iabs((int)dstp[x + h0 - 1] - (int)dstpnn[x - h0 - 1]) + iabs((int)dstp[x + h0] - (int)dstpnn[x - h0]) +
+                                  iabs((int)dstp[x + h0 + 1] - (int)dstpnn[x - h0 + 1]);
+                if (diff2 < nt4 &&
+                    (((iabs((int)omskp[x + h0] - (int)omskn[x - h0]) <= l || iabs((int)omskp[x + h0] - (int)omskn[x - h1]) <= l) && omskp[x + h0] != k.peak) ||
+                     ((iabs((int)omskp[x + h1] - (int)omskn[x - h0]) <= l || iabs((int)omskp[x + h1] - (int)omskn[x - h1]) <= l) && omskp[x + h1] != k.peak)))
+                {
+                    if ((iabs(cur - (int)omskp[x + h0]) <= l || iabs(cur - (int)omskp[x + h1]) <= l) &&
+                        (iabs(cur - (int)omskn[x - h0]) <= l || iabs(cur - (int)omskn[x - h1]) <= l))
+                    {
+                        val = ((int)dstp[x + h0] + (int)dstp[x + h1] + (int)dstpnn[x - h0] + (int)dstpnn[x - h1] + 2) >> 2;
+                        mn = diff;
+                        dir = u;
+                    }
+                }
+            }
+#undef NEAR
+        }
+        if (mn != nt8)
+        {
+            msk = k.neutral + dir * (1 << k.shift2);
+        }
+        else
+        {
+            const int minm = min((int)dstp[x], (int)dstpnn[x]), maxm = max((int)dstp[x], (int)dstpnn[x]);
+            const int d = plane == 0 ? 4 : 2;
+            const int su = max(-x + 1, -d), eu = min(width - 2 - x, d);
+            mn = nt7;
+            for (int u = su; u <= eu; ++u)
+            {
+                const int h0 = u >> 1, h1 = (u + 1) >> 1;
+                const int p1 = (int)dstp[x + h0] + (int)dstp[x + h1];
+                const int p2 = (int)dstpnn[x - h0] + (int)dstpnn[x - h1];
+                const int diff = iabs((int)dstp[x - 1] - (int)dstpnn[x - u - 1]) + iabs((int)dstp[x] - (int)dstpnn[x - u]) +
+                                 iabs((int)dstp[x + 1] - (int)dstpnn[x - u + 1]) + iabs((int)dstpnn[x - 1] - (int)dstp[x + u - 1]) +
+                                 iabs((int)dstpnn[x] - (int)dstp[x + u]) + iabs((int)dstpnn[x + 1] - (int)dstp[x + u + 1]) + iabs(p1 - p2);
+                if (diff < mn)
+                {
+                    const int valt = (p1 + p2 + 2) >> 2;
+                    if (valt >= minm && valt <= maxm) { val = valt; mn = diff; dir = u; }
+                }
+            }
+            if (mn == 7 * nt) msk = k.neutral;                  // unwrapped constant, as in the reference (:1324)
+            else msk = k.neutral + dir * (1 << k.shift2);
+        }
+    }
+    t.valB = (uint16_t)(PIX)val;
+    t.mskB = (uint16_t)(PIX)msk;
+    tmp[(size_t)row * width + x] = t;
+}
+
+template <typename PIX>
+__global__ void k_lattice_b(PIX *__restrict__ dmskp, PIX *__restrict__ dst_base, const LatticeTmp *__restrict__ tmp,
+                            int pitch, int width, int height, int field, int depth)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 2 - field + 2 * row;
+    if (y >= height - 1) return;
+    const int peak = (1 << depth) - 1, neutral = 1 << (depth - 1);
+    PIX *dm = dmskp + (size_t)y * pitch;
+    PIX *dn = dst_base + (size_t)y * pitch;
+    const PIX *up = dn - pitch, *down = dn + pitch;
+    const LatticeTmp *t = tmp + (size_t)row * width;
+    int prev = dm[-1];                                    // linear predecessor of the row (unwritten by this pass)
+    for (int x = 0; x < width; ++x)
+    {
+        const int cur = dm[x];
+        const LatticeTmp e = t[x];
+        int newm, val;
+        if (cur == peak || (abs(cur - prev) > (int)e.lim && e.nextfar))
+        {
+            val = ((int)up[x] + (int)down[x] + 1) >> 1;
+            newm = cur != peak ? neutral : cur;
+        }
+        else
+        {
+            val = e.valB;
+            newm = e.mskB;
+        }
+        dn[x] = (PIX)val;
+        dm[x] = (PIX)newm;
+        prev = newm;
+    }
+}
+
+// post_process (:1349-1378)
+template <typename PIX>
+__global__ void k_post_process(const PIX *__restrict__ nmskp, const PIX *__restrict__ omskp, PIX *__restrict__ dstp,
+                               int pitch, int width, int height, int field, int depth, Lim lim)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 2 - field + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    if (x >= width || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const size_t o = (size_t)y * pitch + x;
+    const int nm = nmskp[o], om = omskp[o];
+    const int l = lim.v[iabs(nm - k.neutral) >> k.shift2];
+    if (iabs(nm - om) > l && om != k.peak && om != k.neutral)
+        dstp[o] = (PIX)(((int)dstp[o - pitch] + (int)dstp[o + pitch] + 1) >> 1);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Eedi2
+{
+    Eedi2Config cfg;
+    int bps;
+    int half_h[3];                 // field-buffer plane heights
+    size_t half_off[3], full_off[3], half_bytes, full_bytes;
+    uint8_t *half_mem[4], *full_mem[5];      // allocation starts (incl. lead slack)
+    LatticeTmp *lattice_tmp;
+    Lim lim;
+    int stop_after;                // debug: number of stage launches to run per plane (0 = all); HBCU_EEDI2_STOP
+};
+
+namespace {
+
+template <typename PIX>
+int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
+{
+    const Eedi2Config &c = e->cfg;
+    const int pitch = c.pitch[pl], width = c.w[pl], height = c.h[pl], hh = e->half_h[pl], depth = c.depth;
+    auto H = [&](int k) { return reinterpret_cast<PIX *>(e->half_mem[k] + kLeadSlack + e->half_off[pl]); };
+    auto F = [&](int k) { return reinterpret_cast<PIX *>(e->full_mem[k] + kLeadSlack + e->full_off[pl]); };
+    PIX *srcp = H(SRCPF), *mskp = H(MSKPF), *tmpp = H(TMPPF), *dstp = H(DSTPF);
+    PIX *dst2p = F(DST2PF), *tmp2p2 = F(TMP2PF2), *msk2p = F(MSK2PF), *tmp2p = F(TMP2PF), *dst2mp = F(DST2MPF);
+    const dim3 blk(64, 4);
+    auto grid2 = [&](int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); };
+    const dim3 rowblk(256, 1);
+    auto gridrows = [&](int w, int rows) { return dim3((w + 255) / 256, rows); };
+    int launches = 0;
+#define LAUNCH(...) do { if (e->stop_after == 0 || launches < e->stop_after) { __VA_ARGS__; } ++launches; } while (0)
+
+    // eedi2_planer: field start_line = !tff of the current frame, whole strides (:455-466, :79-92)
+    const int field_rows = (height + 1) / 2;
+    LAUNCH((k_fill_half<PIX><<<gridrows(pitch, field_rows), rowblk, 0, st>>>(cur_plane + (size_t)pitch * (!tff), srcp, pitch, field_rows)));
+
+    // edge mask: top half cleared, bottom half keeps the previous field's mask (:132)
+    if (e->stop_after == 0 || launches < e->stop_after) cudaMemsetAsync(mskp, 0, (size_t)(hh / 2) * pitch * sizeof(PIX), st);
+    LAUNCH((k_edge_mask<PIX><<<grid2(width, hh), blk, 0, st>>>(mskp, srcp, pitch, width, hh, c.mthresh * 10, c.vthresh /* lthresh <- variance */,
+                                                              c.lthresh * 81 /* vthresh <- laplacian */, depth)));
+    LAUNCH((k_morph<PIX, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, pitch, width, hh, c.estr, depth)));
+    LAUNCH((k_morph<PIX, true><<<grid2(width, hh), blk, 0, st>>>(tmpp, mskp, pitch, width, hh, c.dstr, depth)));
+    LAUNCH((k_morph<PIX, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, pitch, width, hh, c.estr, depth)));
+    LAUNCH((k_gaps<PIX><<<grid2(width, hh), blk, 0, st>>>(tmpp, mskp, pitch, width, hh, depth)));
+
+    // direction mask
+    const int peak = (1 << depth) - 1;
+    {
+        const size_t n = (size_t)pitch * hh;
+        LAUNCH((k_fill<PIX><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmpp, n, peak)));
+    }
+    LAUNCH((k_calc_directions<PIX><<<grid2(width, hh), blk, 0, st>>>(pl, mskp, srcp, tmpp, pitch, width, hh, c.maxd, c.nt, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, false, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, 0, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, true, false><<<grid2(width, hh), blk, 0, st>>>(mskp, dstp, tmpp, pitch, width, hh, 0, depth, e->lim)));
+    LAUNCH((k_filter_map<PIX><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, depth)));
+
+    // upscale 2x vertically (whole strides)
+    LAUNCH((k_upscale2<PIX><<<gridrows(pitch, hh), rowblk, 0, st>>>(srcp, dst2p, pitch, hh)));
+    LAUNCH((k_upscale2<PIX><<<gridrows(pitch, hh), rowblk, 0, st>>>(dstp, tmp2p2, pitch, hh)));
+    LAUNCH((k_upscale2<PIX><<<gridrows(pitch, hh), rowblk, 0, st>>>(mskp, msk2p, pitch, hh)));
+
+    // direction mask at frame height
+    const int rows2 = (height - 1 - (2 - tff) + 1) / 2 > 0 ? (height - 1 - (2 - tff) + 1) / 2 : 0;   // y = 2-tff, +2, ... < height-1
+    {
+        const size_t n = (size_t)pitch * height;
+        LAUNCH((k_fill<PIX><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp2p, n, peak)));
+    }
+    LAUNCH((k_mark_directions_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, tmp2p2, tmp2p, pitch, width, height, tff, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, false, true><<<grid2(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, true, true><<<grid2(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
+    LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(tmp2p, dst2mp, pitch, width, height)));
+    LAUNCH((k_fill_gaps_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth)));
+    LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(dst2mp, tmp2p, pitch, width, height)));
+    LAUNCH((k_fill_gaps_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth)));
+
+    // interpolate the missing lines (:1148-1335): first copy one border row, then the two passes
+    if (tff == 1) LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + (size_t)(height - 2) * pitch, dst2p + (size_t)(height - 1) * pitch, pitch, width, 1)));
+    else          LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + pitch, dst2p, pitch, width, 1)));
+    LAUNCH((k_lattice_a<PIX><<<grid2(width, rows2), blk, 0, st>>>(pl, tmp2p, dst2p, tmp2p2, e->lattice_tmp, pitch, width, height, tff, c.nt, depth, e->lim)));
+    LAUNCH((k_lattice_b<PIX><<<(rows2 + 63) / 64, 64, 0, st>>>(tmp2p, dst2p, e->lattice_tmp, pitch, width, height, tff, depth)));
+
+    if (c.pp == 1 || c.pp == 3)
+    {
+        LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(tmp2p, tmp2p2, pitch, width, height)));
+        LAUNCH((k_dir_map<PIX, false, true><<<grid2(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
+        LAUNCH((k_dir_map<PIX, true, true><<<grid2(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
+        LAUNCH((k_post_process<PIX><<<grid2(width, rows2), blk, 0, st>>>(tmp2p, tmp2p2, dst2p, pitch, width, height, tff, depth, e->lim)));
+    }
+#undef LAUNCH
+    hbcu::count_launch(launches);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+    {
+        set_error("eedi2: kernel launch failed: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+Eedi2 *eedi2_create(const Eedi2Config &cfg)
+{
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (cfg.h[pl] & 1)
+        {
+            // odd plane heights make the reference copy one line beyond the plane into the field buffer (:79-92)
+            set_error("eedi2: plane %d has odd height %d; EEDI2 needs a frame height that keeps every plane even", pl, cfg.h[pl]);
+            return nullptr;
+        }
+    }
+    if (cfg.pp > 1)
+    {
+        set_error("eedi2: postproc %d is not implemented", cfg.pp);
+        return nullptr;
+    }
+    Eedi2 *e = new (std::nothrow) Eedi2();
+    if (e == nullptr) { set_error("eedi2: out of memory"); return nullptr; }
+    e->cfg = cfg;
+    e->bps = cfg.depth > 8 ? 2 : 1;
+    for (int k = 0; k < 4; k++) e->half_mem[k] = nullptr;
+    for (int k = 0; k < 5; k++) e->full_mem[k] = nullptr;
+    e->lattice_tmp = nullptr;
+    e->stop_after = 0;
+    if (const char *sa = getenv("HBCU_EEDI2_STOP")) e->stop_after = atoi(sa);   // test hook: stage-by-stage parity
+    // field buffers are frames of height frame_height/2 (decomb.c:291-296): chroma rounds up from that
+    e->half_h[0] = cfg.half_frame_height;
+    e->half_h[1] = e->half_h[2] = -((-cfg.half_frame_height) >> cfg.chroma_shift_h);
+    size_t ho = 0, fo = 0;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (e->half_h[pl] * 2 != cfg.h[pl])
+        {
+            set_error("eedi2: plane %d: field buffer height %d is not half of %d", pl, e->half_h[pl], cfg.h[pl]);
+            delete e;
+            return nullptr;
+        }
+        e->half_off[pl] = ho;
+        e->full_off[pl] = fo;
+        ho += (size_t)cfg.pitch[pl] * e->half_h[pl] * e->bps;
+        fo += (size_t)cfg.pitch[pl] * cfg.h[pl] * e->bps;
+    }
+    e->half_bytes = ho;
+    e->full_bytes = fo;
+    const size_t tail = (size_t)kTailRows * cfg.pitch[0] * e->bps;
+    bool ok = true;
+    for (int k = 0; k < 4 && ok; k++)
+    {
+        ok = cudaMalloc(&e->half_mem[k], kLeadSlack + ho + tail) == cudaSuccess &&
+             cudaMemset(e->half_mem[k], 0, kLeadSlack + ho + tail) == cudaSuccess;
+    }
+    for (int k = 0; k < 5 && ok; k++)
+    {
+        ok = cudaMalloc(&e->full_mem[k], kLeadSlack + fo + tail) == cudaSuccess &&
+             cudaMemset(e->full_mem[k], 0, kLeadSlack + fo + tail) == cudaSuccess;
+    }
+    if (ok) ok = cudaMalloc(&e->lattice_tmp, sizeof(LatticeTmp) * (size_t)cfg.w[0] * (cfg.h[0] / 2 + 1)) == cudaSuccess;
+    if (!ok)
+    {
+        set_error("eedi2: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        eedi2_destroy(e);
+        return nullptr;
+    }
+    // eedi2_init_limlut (:23-33): ((pixel)limlut[i]) << shift, -1 entries wrap in the pixel type
+    static const int base[33] = { 6, 6, 7, 7, 8, 8, 9, 9, 9, 10, 10, 11, 11, 12, 12, 12, 12, 12, 12, 12,
+                                  12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, -1, -1 };
+    const unsigned shift = cfg.depth - 8;
+    for (int i = 0; i < 33; i++)
+    {
+        if (e->bps == 1) e->lim.v[i] = (int)(uint8_t)(((uint8_t)base[i]) << shift);
+        else             e->lim.v[i] = (int)(uint16_t)(((uint16_t)base[i]) << shift);
+    }
+    return e;
+}
+
+void eedi2_destroy(Eedi2 *e)
+{
+    if (e == nullptr) return;
+    for (int k = 0; k < 4; k++) if (e->half_mem[k]) cudaFree(e->half_mem[k]);
+    for (int k = 0; k < 5; k++) if (e->full_mem[k]) cudaFree(e->full_mem[k]);
+    if (e->lattice_tmp) cudaFree(e->lattice_tmp);
+    delete e;
+}
+
+int eedi2_run(Eedi2 *e, const void *const planes[3], int tff, cudaStream_t st)
+{
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const int rc = e->bps == 1 ? run_plane<uint8_t>(e, pl, (const uint8_t *)planes[pl], tff, st)
+                                   : run_plane<uint16_t>(e, pl, (const uint16_t *)planes[pl], tff, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+// test hook: copies one EEDI2 work buffer (0-3 field buffers SRCPF..DSTPF, 4-8 frame buffers DST2PF..DST2MPF),
+// all three planes with their strides, to the host
+int eedi2_debug_read(const Eedi2 *e, int which, void *host, size_t host_bytes)
+{
+    const bool half = which < 4;
+    const size_t n = half ? e->half_bytes : e->full_bytes;
+    if (which < 0 || which > 8 || host_bytes < n)
+    {
+        set_error("eedi2_debug_read: bad buffer %d or size %zu < %zu", which, host_bytes, n);
+        return -1;
+    }
+    const uint8_t *src = (half ? e->half_mem[which] : e->full_mem[which - 4]) + kLeadSlack;
+    cudaError_t err = cudaMemcpy(host, src, n, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) { set_error("eedi2_debug_read: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+const void *eedi2_output(const Eedi2 *e, int plane)
+{
+    return e->full_mem[DST2PF] + kLeadSlack + e->full_off[plane];
+}
+
+}  // namespace hbcu

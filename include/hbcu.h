@@ -163,6 +163,59 @@ int  hbcu_comb_detect_sync(hbcu_comb_detect_t *h);
 int  hbcu_comb_detect_mark(hbcu_comb_detect_t *h, int which);
 int  hbcu_comb_detect_elapsed_ms(hbcu_comb_detect_t *h, float *ms);
 
+/* ------------------------------------------------------------------------- */
+/* Decomb        replaces decomb.c:500-571 (per-field work) and                 */
+/*               templates/decomb_template.c:43-107,279-361,482-898 (cubic,     */
+/*               blend, yadif line filters, segment driver, frame filter);      */
+/*               EEDI2 (eedi2.c, templates/eedi2_template.c) plugs in below     */
+/* ------------------------------------------------------------------------- */
+#define HBCU_DECOMB_YADIF     1
+#define HBCU_DECOMB_BLEND     2
+#define HBCU_DECOMB_CUBIC     4
+#define HBCU_DECOMB_EEDI2     8
+#define HBCU_DECOMB_BOB       16
+#define HBCU_DECOMB_SELECTIVE 32
+
+typedef struct hbcu_decomb_config_s
+{
+    int width, height;
+    int depth;
+    int chroma_shift_w, chroma_shift_h;
+    int device;
+    int slots;                  /* input frames kept on the device (>= 4) */
+    int out_slots;              /* output fields in flight */
+    int mode;                   /* filter-level mode bits (selects whether EEDI2 buffers are needed) */
+    /* EEDI2 thresholds, decomb.c:234-243 */
+    int magnitude_threshold, variance_threshold, laplacian_threshold;
+    int dilation_threshold, erosion_threshold, noise_threshold;
+    int maximum_search_distance, post_processing;
+} hbcu_decomb_config_t;
+
+typedef struct hbcu_decomb_s hbcu_decomb_t;
+
+int  hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg);
+void hbcu_decomb_destroy(hbcu_decomb_t *h);
+int  hbcu_decomb_upload(hbcu_decomb_t *h, int64_t index, const void *const planes[3], const int strides[3]);
+int  hbcu_decomb_upload_device(hbcu_decomb_t *h, int64_t index, const void *const dplanes[3], const int strides[3]);
+/* blocks until the host planes of frame `index` have been read (no-op if the frame left the device ring) */
+int  hbcu_decomb_wait_upload(hbcu_decomb_t *h, int64_t index);
+/* one output picture (filter_{8,16}, decomb template :810-898): `frame_mode` is the mode chosen for
+ * this frame (BLEND for lightly combed frames, else the filter mode without SELECTIVE), `parity`
+ * the field being rebuilt, `tff` the field order.  Result goes to the host planes asynchronously;
+ * `ticket` is a caller-chosen id (monotonic) for wait/poll. */
+int  hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
+                        int frame_mode, int parity, int tff, void *const planes[3], const int strides[3]);
+int  hbcu_decomb_filter_device(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
+                               int frame_mode, int parity, int tff, void *out_planes[3], int out_strides[3]);
+int  hbcu_decomb_wait(hbcu_decomb_t *h, int64_t ticket);
+int  hbcu_decomb_poll(hbcu_decomb_t *h, int64_t ticket);
+int  hbcu_decomb_sync(hbcu_decomb_t *h);
+/* test hook: EEDI2 work buffer `which` (0-3 field buffers SRCPF MSKPF TMPPF DSTPF, 4-8 frame buffers
+ * DST2PF TMP2PF2 MSK2PF TMP2PF DST2MPF; decomb.c:64-74), three planes back to back with their strides */
+int  hbcu_decomb_debug_eedi2(hbcu_decomb_t *h, int which, void *host, size_t host_bytes);
+int  hbcu_decomb_mark(hbcu_decomb_t *h, int which);
+int  hbcu_decomb_elapsed_ms(hbcu_decomb_t *h, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,28 @@ void oracle_comb_gamma_lut(int depth, float *out);
 int oracle_comb_detect_clip(const uint8_t *in, int n_in, int width, int height, int depth,
                             const oracle_comb_params_t *p, uint8_t *verdicts);
 
+/* ---------------- decomb (libhb/decomb.c + templates/decomb_template.c), EEDI2 excluded ---------------- */
+#define ORACLE_DECOMB_YADIF     1
+#define ORACLE_DECOMB_BLEND     2
+#define ORACLE_DECOMB_CUBIC     4
+#define ORACLE_DECOMB_EEDI2     8
+#define ORACLE_DECOMB_BOB       16
+#define ORACLE_DECOMB_SELECTIVE 32
+
+/* one output field/frame of filter_{8,16} (decomb template :810-898) for all three planes.
+ * prev/cur/next/dst: packed planar yuv420 frames; `mode` is the per-frame mode chosen by the
+ * caller (decomb template :823-831) with the EEDI2 bit clear; rows the reference leaves
+ * unwritten (mode combinations without a line filter) stay as they are in dst. */
+void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, uint8_t *dst,
+                         int width, int height, int depth, int filter_mode, int mode, int parity, int tff);
+
+/* whole clip through hb_decomb_work/process_frame (decomb.c:500-612).  flags/combed: per input
+ * frame s.flags and s.combed; out must hold 2*n_in frames; returns the number of output frames.
+ * out_src (may be NULL) receives the index of the input frame each output came from. */
+int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const uint8_t *combed,
+                       int width, int height, int depth, int mode, int parity_setting,
+                       uint8_t *out, int *out_src);
+
 #ifdef __cplusplus
 }
 #endif

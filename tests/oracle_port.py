@@ -87,3 +87,23 @@ def comb_detect_masks(self, prev, cur, nxt, width, height, depth, settings=None,
 
 OraclePort.comb_detect_clip = comb_detect_clip
 OraclePort.comb_detect_masks = comb_detect_masks
+
+
+def decomb_clip(self, clip, width, height, depth, mode, parity=-1, flags=None, combed=None):
+    """-> (out frames, source index per output)"""
+    clip = np.ascontiguousarray(clip, dtype=np.uint8)
+    n = clip.shape[0]
+    out = np.zeros((2 * n, clip.shape[1]), np.uint8)
+    src = np.zeros(2 * n, np.int32)
+    fl = np.ascontiguousarray(flags, np.uint16) if flags is not None else None
+    cb = np.ascontiguousarray(combed, np.uint8) if combed is not None else None
+    self.lib.oracle_decomb_clip.restype = C.c_int
+    self.lib.oracle_decomb_clip.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    k = self.lib.oracle_decomb_clip(clip.ctypes.data, n, fl.ctypes.data if fl is not None else None,
+                                    cb.ctypes.data if cb is not None else None, width, height, depth, mode, parity,
+                                    out.ctypes.data, src.ctypes.data)
+    return out[:k], src[:k]
+
+
+OraclePort.decomb_clip = decomb_clip

@@ -69,7 +69,7 @@ def test_masks_match_oracle_through_c_abi(cuda_filters, settings, depth):
     mth, sth = p.motion_threshold << (depth - 8), p.spatial_threshold << (depth - 8)
     lut = np.zeros(maxv + 1, np.float32)
     port.lib.oracle_comb_gamma_lut(depth, C.c_void_p(lut.ctypes.data))     # the C expression, not numpy's pow
-    cfg = CombConfig(w, h, depth, 0, 6, p.mode, p.spatial_metric, p.filter_mode, mth, sth, p.block_threshold,
+    cfg = CombConfig(w, h, depth, 0, 8, p.mode, p.spatial_metric, p.filter_mode, mth, sth, p.block_threshold,
                      min(p.block_width, w), min(p.block_height, h),
                      np.float32(mth) / np.float32(maxv), np.float32(sth) / np.float32(maxv),
                      np.float32(6) * (np.float32(sth) / np.float32(maxv)), 10 << (depth - 8), 15 << (depth - 8),
