@@ -1,0 +1,299 @@
+// lapsharp.cu -- Laplacian sharpen for sm_100a behind the C-ABI of include/hbcu.h.
+//
+// Replaces DEF_LAPSHARP_FUNC (reference libhb/lapsharp.c:125-182) and the frame batching of
+// mt_frame_filter.c:169-237: frames are independent, so each one is upload -> kernel -> download
+// on the handle's streams with `slots` frames in flight.
+//
+// Numeric contract kept bit for bit: the convolution accumulates in int16 (8-bit) / int32 (16-bit),
+// the sharpening term is evaluated in double exactly as written in the reference
+// ((acc*coef - src)*strength, truncated toward zero), then clamped.  Border rule as in the
+// reference, including its dependence on the stride: pixels with x < (stride-width)/2 + offset_max
+// are copied, and the last columns read the stride region to the right of the picture.
+#include "hbcu_common.h"
+#include "../../include/hbcu.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using hbcu::set_error;
+
+__constant__ int c_kernels[4][25] = {
+    { 0, -1, 0, -1, 5, -1, 0, -1, 0 },                                                    // lap
+    { -1, -4, -1, -4, 25, -4, -1, -4, -1 },                                               // isolap
+    { 0, 0, -1, 0, 0, 0, -1, -2, -1, 0, -1, -2, 21, -2, -1, 0, -1, -2, -1, 0, 0, 0, -1, 0, 0 },        // log
+    { 0, -1, -1, -1, 0, -1, -3, -4, -3, -1, -1, -4, 55, -4, -1, -1, -3, -4, -3, -1, 0, -1, -1, -1, 0 } // isolog
+};
+__constant__ int c_ksize[4] = { 3, 3, 5, 5 };
+
+template <typename PIX, typename ACC>
+__global__ void __launch_bounds__(256) lapsharp_kernel(const PIX *__restrict__ src, PIX *__restrict__ dst, int width, int height,
+                                                      int spitch, int dpitch, int kid, double coef, double strength, int max_value)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const int size = c_ksize[kid];
+    const int offset_min = -((size - 1) / 2), offset_max = (size + 1) / 2;
+    const int stride_border = (spitch - width) / 2;
+    const int s0 = src[(size_t)y * spitch + x];
+    if ((y < offset_max) || (y > height - offset_max) || (x < stride_border + offset_max) || (x > width + stride_border - offset_max))
+    {
+        dst[(size_t)y * dpitch + x] = (PIX)s0;
+        return;
+    }
+    int acc = 0;
+    for (int k = offset_min; k < offset_max; k++)
+        for (int j = offset_min; j < offset_max; j++)
+            acc += c_kernels[kid][(j - offset_min) * size + k - offset_min] * (int)src[(size_t)(y + j) * spitch + (x + k)];
+    ACC pixel = (ACC)acc;                                   // the reference accumulates in ACC (wraps like it)
+    // pixel = (ACC)(((pixel * coef) - src) * strength) + src
+    const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
+    pixel = (ACC)((int)(ACC)(int)t + s0);
+    int v = pixel;
+    v = v < 0 ? 0 : v;
+    v = v > max_value ? max_value : v;
+    dst[(size_t)y * dpitch + x] = (PIX)v;
+}
+
+struct Geom { int w, h, pitch; size_t bytes; };
+
+}  // namespace
+
+struct hbcu_lapsharp_s
+{
+    hbcu_lapsharp_config_t cfg;
+    int bps, maxv, slots, next;
+    Geom g[3];
+    std::vector<uint8_t *> in_mem, out_mem;
+    std::vector<int64_t> ticket;
+    std::vector<cudaEvent_t> ev_up, ev_k, ev_down;
+    cudaStream_t s_h2d, s_compute, s_d2h;
+    cudaEvent_t ev_mark[2];
+};
+
+namespace {
+
+const double kCoef[4] = { 1.0, 1.0 / 5, 1.0 / 5, 1.0 / 15 };     // lapsharp.c:95-101
+
+int launch(hbcu_lapsharp_s *h, int pl, const void *src, int spitch_elems, void *dst)
+{
+    const Geom &g = h->g[pl];
+    dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
+    const int kid = h->cfg.kernel[pl];
+    if (h->bps == 1)
+        lapsharp_kernel<uint8_t, int16_t><<<grid, blk, 0, h->s_compute>>>((const uint8_t *)src, (uint8_t *)dst, g.w, g.h, spitch_elems,
+                                                                        g.pitch, kid, kCoef[kid], h->cfg.strength[pl], h->maxv);
+    else
+        lapsharp_kernel<uint16_t, int32_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, (uint16_t *)dst, g.w, g.h, spitch_elems,
+                                                                          g.pitch, kid, kCoef[kid], h->cfg.strength[pl], h->maxv);
+    hbcu::count_launch();
+    HBCU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int find_ticket(hbcu_lapsharp_s *h, int64_t t)
+{
+    for (int s = 0; s < h->slots; s++) if (h->ticket[s] == t) return s;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbcu_lapsharp_create(hbcu_lapsharp_t **out, const hbcu_lapsharp_config_t *cfg)
+{
+    if (out == nullptr || cfg == nullptr) { set_error("lapsharp_create: null argument"); return -1; }
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->depth < 8 || cfg->depth > 16)
+    {
+        set_error("lapsharp_create: unsupported geometry %dx%d depth %d", cfg->width, cfg->height, cfg->depth);
+        return -1;
+    }
+    for (int c = 0; c < 3; c++)
+        if (cfg->kernel[c] < 0 || cfg->kernel[c] > 3) { set_error("lapsharp_create: bad kernel id %d", cfg->kernel[c]); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+    {
+        cudaGetLastError();
+        set_error("lapsharp_create: CUDA device %d not available (%d devices); there is no CPU fallback", cfg->device, ndev);
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(cfg->device));
+    hbcu_lapsharp_s *h = new (std::nothrow) hbcu_lapsharp_s();
+    if (h == nullptr) { set_error("lapsharp_create: out of memory"); return -1; }
+    h->cfg = *cfg;
+    h->bps = cfg->depth > 8 ? 2 : 1;
+    h->maxv = (1 << cfg->depth) - 1;
+    h->slots = cfg->slots >= 2 ? cfg->slots : 4;
+    h->next = 0;
+    h->s_h2d = h->s_compute = h->s_d2h = nullptr;
+    h->ev_mark[0] = h->ev_mark[1] = nullptr;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        Geom &g = h->g[pl];
+        g.w = pl == 0 ? cfg->width : -((-cfg->width) >> cfg->chroma_shift_w);
+        g.h = pl == 0 ? cfg->height : -((-cfg->height) >> cfg->chroma_shift_h);
+        g.pitch = ((g.w * h->bps + 63) / 64 * 64) / h->bps;          // hb_image_stride
+        g.bytes = (size_t)g.pitch * g.h * h->bps;
+    }
+#define CK(expr)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));            \
+            hbcu_lapsharp_destroy(h);                                             \
+            return -1;                                                            \
+        }                                                                         \
+    } while (0)
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    h->in_mem.assign(h->slots * 3, nullptr);
+    h->out_mem.assign(h->slots * 3, nullptr);
+    h->ticket.assign(h->slots, -1);
+    h->ev_up.assign(h->slots, nullptr);
+    h->ev_k.assign(h->slots, nullptr);
+    h->ev_down.assign(h->slots, nullptr);
+    for (int s = 0; s < h->slots; s++)
+    {
+        CK(cudaEventCreateWithFlags(&h->ev_up[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_k[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_down[s], cudaEventDisableTiming));
+        for (int pl = 0; pl < 3; pl++)
+        {
+            CK(cudaMalloc(&h->in_mem[s * 3 + pl], h->g[pl].bytes + 256));
+            CK(cudaMemset(h->in_mem[s * 3 + pl], 0, h->g[pl].bytes + 256));
+            CK(cudaMalloc(&h->out_mem[s * 3 + pl], h->g[pl].bytes));
+        }
+    }
+    CK(cudaEventCreate(&h->ev_mark[0]));
+    CK(cudaEventCreate(&h->ev_mark[1]));
+#undef CK
+    *out = h;
+    return 0;
+}
+
+void hbcu_lapsharp_destroy(hbcu_lapsharp_t *h)
+{
+    if (h == nullptr) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto p : h->in_mem) if (p) cudaFree(p);
+    for (auto p : h->out_mem) if (p) cudaFree(p);
+    for (auto e : h->ev_up) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_k) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_down) if (e) cudaEventDestroy(e);
+    if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
+    if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+int hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const in_planes[3], const int in_strides[3],
+                         void *const out_planes[3], const int out_strides[3])
+{
+    if (h == nullptr || in_planes == nullptr || out_planes == nullptr) { set_error("lapsharp_filter: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int s = h->next;
+    h->next = (h->next + 1) % h->slots;
+    // the slot's previous frame must have left it (kernel read the input, download read the output)
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_k[s], 0));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const Geom &g = h->g[pl];
+        const bool same = (size_t)in_strides[pl] == (size_t)g.pitch * h->bps;
+        HBCU_CHECK(cudaMemcpy2DAsync(h->in_mem[s * 3 + pl], (size_t)g.pitch * h->bps, in_planes[pl], (size_t)in_strides[pl],
+                                     same ? (size_t)g.pitch * h->bps : (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_up[s], h->s_h2d));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_up[s], 0));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
+    for (int pl = 0; pl < 3; pl++)
+        if (launch(h, pl, h->in_mem[s * 3 + pl], h->g[pl].pitch, h->out_mem[s * 3 + pl]) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_k[s], 0));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const Geom &g = h->g[pl];
+        HBCU_CHECK(cudaMemcpy2DAsync(out_planes[pl], (size_t)out_strides[pl], h->out_mem[s * 3 + pl], (size_t)g.pitch * h->bps,
+                                     (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_d2h));
+    h->ticket[s] = ticket;
+    return 0;
+}
+
+int hbcu_lapsharp_filter_device(hbcu_lapsharp_t *h, int64_t ticket, const void *const dplanes[3], const int strides[3],
+                                void *out_planes[3], int out_strides[3])
+{
+    if (h == nullptr || dplanes == nullptr || strides == nullptr) { set_error("lapsharp_filter_device: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int s = h->next;
+    h->next = (h->next + 1) % h->slots;
+    for (int pl = 0; pl < 3; pl++)
+        if (launch(h, pl, dplanes[pl], strides[pl] / h->bps, h->out_mem[s * 3 + pl]) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
+    HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_compute));
+    h->ticket[s] = ticket;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (out_planes) out_planes[pl] = h->out_mem[s * 3 + pl];
+        if (out_strides) out_strides[pl] = h->g[pl].pitch * h->bps;
+    }
+    return 0;
+}
+
+int hbcu_lapsharp_wait(hbcu_lapsharp_t *h, int64_t ticket)
+{
+    if (h == nullptr) { set_error("lapsharp_wait: null handle"); return -1; }
+    const int s = find_ticket(h, ticket);
+    if (s < 0) { set_error("lapsharp_wait: ticket %lld is not in flight", (long long)ticket); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_down[s]));
+    return 0;
+}
+
+int hbcu_lapsharp_poll(hbcu_lapsharp_t *h, int64_t ticket)
+{
+    if (h == nullptr) { set_error("lapsharp_poll: null handle"); return -1; }
+    const int s = find_ticket(h, ticket);
+    if (s < 0) { set_error("lapsharp_poll: ticket %lld is not in flight", (long long)ticket); return -1; }
+    cudaError_t e = cudaEventQuery(h->ev_down[s]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    set_error("lapsharp_poll: %s", cudaGetErrorString(e));
+    return -1;
+}
+
+int hbcu_lapsharp_sync(hbcu_lapsharp_t *h)
+{
+    if (h == nullptr) { set_error("lapsharp_sync: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
+    return 0;
+}
+
+int hbcu_lapsharp_mark(hbcu_lapsharp_t *h, int which)
+{
+    if (h == nullptr || which < 0 || which > 1) { set_error("lapsharp_mark: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaEventRecord(h->ev_mark[which], h->s_compute));
+    return 0;
+}
+
+int hbcu_lapsharp_elapsed_ms(hbcu_lapsharp_t *h, float *ms)
+{
+    if (h == nullptr || ms == nullptr) { set_error("lapsharp_elapsed_ms: bad argument"); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_mark[1]));
+    HBCU_CHECK(cudaEventElapsedTime(ms, h->ev_mark[0], h->ev_mark[1]));
+    return 0;
+}
+
+}  // extern "C"

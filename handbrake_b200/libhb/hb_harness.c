@@ -166,10 +166,19 @@ int hb_harness_run_chain(int n_filters, hb_filter_object_t *const *protos,
         memcpy(f, protos[k], sizeof(*f));
         f->settings = settings && settings[k] ? hb_parse_filter_settings(settings[k]) : NULL;
         f->done = &done_flag;
+        if (f->sub_filter != NULL)
+        {
+            /* wrapper filters (mt_frame): the wrapped filter gets its own copy of the settings (hb.c:1697-1700) */
+            hb_filter_object_t *sub = malloc(sizeof(*sub));
+            memcpy(sub, f->sub_filter, sizeof(*sub));
+            sub->settings = settings && settings[k] ? hb_parse_filter_settings(settings[k]) : NULL;
+            f->sub_filter = sub;
+        }
         if (f->init(f, &init) != 0)
         {
             io->init_failed |= 1 << k;
             if (f->settings) hb_dict_free(&f->settings);
+            if (f->sub_filter) { if (f->sub_filter->settings) hb_dict_free(&f->sub_filter->settings); free(f->sub_filter); }
             free(f);
             continue;
         }
@@ -205,6 +214,7 @@ int hb_harness_run_chain(int n_filters, hb_filter_object_t *const *protos,
     {
         c.f[k]->close(c.f[k]);
         if (c.f[k]->settings) hb_dict_free(&c.f[k]->settings);
+        if (c.f[k]->sub_filter) { if (c.f[k]->sub_filter->settings) hb_dict_free(&c.f[k]->sub_filter->settings); free(c.f[k]->sub_filter); }
         free(c.f[k]);
     }
     free(c.f);

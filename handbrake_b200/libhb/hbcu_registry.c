@@ -8,6 +8,7 @@
 extern hb_filter_object_t hb_filter_nlmeans_cuda;
 extern hb_filter_object_t hb_filter_comb_detect_cuda;
 extern hb_filter_object_t hb_filter_decomb_cuda;
+extern hb_filter_object_t hb_filter_lapsharp_cuda;
 
 hb_filter_object_t *hb_filter_get(int filter_id)
 {
@@ -16,6 +17,7 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_NLMEANS:     return &hb_filter_nlmeans_cuda;
         case HB_FILTER_COMB_DETECT: return &hb_filter_comb_detect_cuda;
         case HB_FILTER_DECOMB:      return &hb_filter_decomb_cuda;
+        case HB_FILTER_LAPSHARP:    return &hb_filter_lapsharp_cuda;   /* no mt_frame wrapper needed: streams */
         default:                return NULL;
     }
 }

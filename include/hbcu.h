@@ -216,6 +216,37 @@ int  hbcu_decomb_debug_eedi2(hbcu_decomb_t *h, int which, void *host, size_t hos
 int  hbcu_decomb_mark(hbcu_decomb_t *h, int which);
 int  hbcu_decomb_elapsed_ms(hbcu_decomb_t *h, float *ms);
 
+/* ------------------------------------------------------------------------- */
+/* Lapsharp      replaces lapsharp.c:125-182 (DEF_LAPSHARP_FUNC) and, for the   */
+/*               frame batching, mt_frame_filter.c:169-237 (stream dispatch)    */
+/* ------------------------------------------------------------------------- */
+typedef struct hbcu_lapsharp_config_s
+{
+    int width, height, depth;
+    int chroma_shift_w, chroma_shift_h;
+    int device;
+    int slots;                   /* frames in flight */
+    double strength[3];          /* sanitised, lapsharp.c:289-296 */
+    int    kernel[3];            /* 0 lap, 1 isolap, 2 log, 3 isolog (lapsharp.c:36-93) */
+} hbcu_lapsharp_config_t;
+
+typedef struct hbcu_lapsharp_s hbcu_lapsharp_t;
+
+int  hbcu_lapsharp_create(hbcu_lapsharp_t **out, const hbcu_lapsharp_config_t *cfg);
+void hbcu_lapsharp_destroy(hbcu_lapsharp_t *h);
+/* one frame: host planes in (whole strides are transferred: the filter reads the stride region next
+ * to the right picture edge, lapsharp.c:145-158), host planes out; asynchronous, `ticket` for wait/poll */
+int  hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const in_planes[3], const int in_strides[3],
+                          void *const out_planes[3], const int out_strides[3]);
+/* device-resident variant: dplanes are device pointers with the given strides, result stays on the device */
+int  hbcu_lapsharp_filter_device(hbcu_lapsharp_t *h, int64_t ticket, const void *const dplanes[3], const int strides[3],
+                                 void *out_planes[3], int out_strides[3]);
+int  hbcu_lapsharp_wait(hbcu_lapsharp_t *h, int64_t ticket);
+int  hbcu_lapsharp_poll(hbcu_lapsharp_t *h, int64_t ticket);
+int  hbcu_lapsharp_sync(hbcu_lapsharp_t *h);
+int  hbcu_lapsharp_mark(hbcu_lapsharp_t *h, int which);
+int  hbcu_lapsharp_elapsed_ms(hbcu_lapsharp_t *h, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,11 @@ int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const
                        int width, int height, int depth, int mode, int parity_setting,
                        uint8_t *out, int *out_src);
 
+/* ---------------- lapsharp (libhb/lapsharp.c) ---------------- */
+/* one plane WITH its strides (bytes); kernel_id 0 lap, 1 isolap, 2 log, 3 isolog */
+void oracle_lapsharp_plane(const void *src, void *dst, int width, int height, int stride_src, int stride_dst,
+                           int depth, int kernel_id, double strength);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,3 +44,16 @@ void hb_filter_close(hb_filter_object_t **pf)
     free(f);
     *pf = NULL;
 }
+
+/* lapsharp as libhb instantiates it: wrapped in mt_frame (common.c:5497-5517).  A ready-made object
+ * for the harness, which copies filter prototypes instead of calling hb_filter_init(). */
+static hb_filter_object_t lapsharp_sub;
+hb_filter_object_t hb_filter_lapsharp_mt;
+
+__attribute__((constructor)) static void build_lapsharp_mt(void)
+{
+    memcpy(&lapsharp_sub, &hb_filter_lapsharp, sizeof(lapsharp_sub));
+    memcpy(&hb_filter_lapsharp_mt, &hb_filter_mt_frame, sizeof(hb_filter_lapsharp_mt));
+    hb_filter_lapsharp_mt.sub_filter = &lapsharp_sub;
+    hb_filter_lapsharp_mt.id = HB_FILTER_LAPSHARP;
+}

@@ -107,3 +107,38 @@ def decomb_clip(self, clip, width, height, depth, mode, parity=-1, flags=None, c
 
 
 OraclePort.decomb_clip = decomb_clip
+
+
+def lapsharp_frame(self, frame, fmt_planes, depth, strengths, kernels):
+    """frame: packed planar; fmt_planes: [(w,h)]*3.  Builds libhb-style strided planes (64-byte stride,
+    zero stride region, 16-bit mirror applied when bps == 2 -- for 8-bit content libhb's mirror is a no-op),
+    runs the port per plane, returns the packed result."""
+    bps = 2 if depth > 8 else 1
+    dt = np.uint16 if bps == 2 else np.uint8
+    self.lib.oracle_lapsharp_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+    a = frame.view(dt)
+    out, off = [], 0
+    for c, (w, h) in enumerate(fmt_planes):
+        stride_el = ((w * bps + 63) // 64 * 64) // bps
+        src = np.zeros((h + 1, stride_el), dt)          # one spare row: the mirror writes the start of the next row
+        src[:h, :w] = a[off:off + w * h].reshape(h, w)
+        if bps == 2:
+            margin = stride_el - w
+            mf, mb = margin // 2, margin - margin // 2
+            flat = src.reshape(-1)
+            for yy in range(h):
+                pos = yy * stride_el + w
+                for ii in range(mb):
+                    flat[pos + ii] = flat[pos - ii - 1]
+                pos = (yy + 1) * stride_el - 1
+                for ii in range(mf):
+                    flat[pos - ii] = flat[pos + ii + 1]
+        dst = np.zeros((h, stride_el), dt)
+        self.lib.oracle_lapsharp_plane(src.ctypes.data, dst.ctypes.data, w, h, stride_el * bps, stride_el * bps, depth,
+                                       kernels[c], float(strengths[c]))
+        out.append(dst[:, :w].reshape(-1))
+        off += w * h
+    return np.concatenate(out).view(np.uint8)
+
+
+OraclePort.lapsharp_frame = lapsharp_frame
