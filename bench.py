@@ -292,8 +292,8 @@ def run_ours(args, wl, rank, world, local_rank):
         "config": {"workload": args.workload, "desc": wl["desc"], "frames_per_step_per_gpu": B,
                    "sharding": f"frame blocks x{world}, {NFRAMES - 1}-frame temporal halo per block, no data-path collective",
                    "l2": f"step inputs {input_mb:.0f} MB in distinct buffers > 126 MB L2" if input_mb > 126 else f"step inputs {input_mb:.0f} MB (fits L2)"},
-        "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(st.bytes_in // K),
-                "d2h_bytes_per_step": int(st.bytes_out // K), "seconds": round(e2e_s, 4), "checksum": int(st.checksum)},
+        "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(world * st.bytes_in // K),
+                "d2h_bytes_per_step": int(world * st.bytes_out // K), "seconds": round(e2e_s, 4), "checksum": int(st.checksum)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",

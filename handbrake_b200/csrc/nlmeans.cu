@@ -479,14 +479,14 @@ __device__ __forceinline__ float byte_as_biased_float(uint32_t w, int k)
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k));
 }
 
-template <int NH, int TH>
+template <int NH, int TH, int NW, bool ORIGIN>
 __device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp,
                                                float *__restrict__ acc_ws, float *__restrict__ acc_ps,
                                                uint32_t lut_lane_addr, float wscale, double origin_tune,
                                                int seg_y0, int lane, int dy, int dx0, int ng, int origin_g)
 {
     constexpr int N   = 2 * NH + 1;
-    constexpr int RS  = TH / 8;
+    constexpr int RS  = TH / NW;
     constexpr int NA  = 4 + 2 * NH;                 // source values per row
     constexpr int NB  = NA + kGroup - 1;            // compare values per row
     constexpr int PW  = kTilePW / 4;                // tile pitch in words
@@ -548,7 +548,7 @@ __device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur,
 #pragma unroll
                 for (int g = 0; g < kGroup; g++)
                 {
-                    if (g < ng && g != origin_g)
+                    if (g < ng && (!ORIGIN || g != origin_g))
                     {
                         float c[NA + 1];
                         c[0] = 0.f;
@@ -584,7 +584,7 @@ __device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur,
                     {
                         if (g < ng)
                         {
-                            if (g == origin_g)
+                            if (ORIGIN && g == origin_g)
                             {
                                 const uint32_t cw = cur[(oy + kHalo) * PW + lane + kHaloX / 4];
 #pragma unroll
@@ -622,9 +622,10 @@ __device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur,
     }
 }
 
-template <int NH, int TH>
-__global__ void __launch_bounds__(kThreads, 1) nlmeans_fast8_kernel(const __grid_constant__ TiledParams tp)
+template <int NH, int TH, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_constant__ TiledParams tp)
 {
+    constexpr int kThreads = NW * 32;
     const KernelParams &p = tp.k;
     using L = FastLayout<TH>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -665,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) nlmeans_fast8_kernel(const __grid
     phase ^= 1;
     __syncthreads();
 
-    const int seg_y0 = warp * (TH / 8);
+    const int seg_y0 = warp * (TH / NW);
     const float wscale = p.wfact * 0.0078125f;                         // wfact / 128, exact
     // shared address of this lane's copy of table entry 0, pre-biased by -(0x47800000 << 7)
     const uint32_t lut_lane_addr = smem_u32(lut) + (uint32_t)lane * 4u - (0x47800000u << 7);
@@ -691,15 +692,21 @@ __global__ void __launch_bounds__(kThreads, 1) nlmeans_fast8_kernel(const __grid
             {
                 const int ng = min(kGroup, p.r_half - dx0 + 1);
                 const int origin_g = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : -1;
-                nlm_group_fast<NH, TH>(reinterpret_cast<const uint32_t *>(cur), reinterpret_cast<const uint32_t *>(B),
-                                       acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+                // the origin variant (double-precision add of origin_tune) runs for one group per plane;
+                // keeping it out of the common instantiation keeps that loop body small
+                if (origin_g >= 0)
+                    nlm_group_fast<NH, TH, NW, true>(reinterpret_cast<const uint32_t *>(cur), reinterpret_cast<const uint32_t *>(B),
+                                                     acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+                else
+                    nlm_group_fast<NH, TH, NW, false>(reinterpret_cast<const uint32_t *>(cur), reinterpret_cast<const uint32_t *>(B),
+                                                      acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, -1);
             }
         }
     }
 
     const int x = lane * 4;
     uint8_t *dst = reinterpret_cast<uint8_t *>(p.dst);
-    for (int r = 0; r < TH / 8; r++)
+    for (int r = 0; r < TH / NW; r++)
     {
         const int oy = seg_y0 + r;
         const int y = Y0 + oy;
@@ -783,30 +790,33 @@ int launch_tiled(const TiledParams &kp, cudaStream_t st)
     return 0;
 }
 
-template <int NH, int TH>
+template <int NH, int TH, int NW>
 int launch_fast8(const TiledParams &kp, cudaStream_t st)
 {
     using L = FastLayout<TH>;
     static bool configured = false;
     if (!configured)
     {
-        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast8_kernel<NH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast8_kernel<NH, TH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured = true;
     }
     dim3 grid((kp.k.w + kTileW - 1) / kTileW, (kp.k.h + TH - 1) / TH);
-    nlmeans_fast8_kernel<NH, TH><<<grid, kThreads, L::kTotal, st>>>(kp);
+    nlmeans_fast8_kernel<NH, TH, NW><<<grid, NW * 32, L::kTotal, st>>>(kp);
     hbcu::count_launch();
     return 0;
 }
 
+int g_fast8_variant = 0;     // 0: 8 warps x 16 rows (TH 128); 1: 12 warps x 12 rows (TH 144); HBCU_NLMEANS_VARIANT
+
 int launch_fast8_nh(const TiledParams &kp, cudaStream_t st)
 {
+    if (g_fast8_variant == 1 && kp.k.n_half == 3) return launch_fast8<3, 144, 12>(kp, st);
     switch (kp.k.n_half)
     {
-        case 1: return launch_fast8<1, 128>(kp, st);
-        case 2: return launch_fast8<2, 128>(kp, st);
-        case 3: return launch_fast8<3, 128>(kp, st);
-        case 4: return launch_fast8<4, 128>(kp, st);
+        case 1: return launch_fast8<1, 128, 8>(kp, st);
+        case 2: return launch_fast8<2, 128, 8>(kp, st);
+        case 3: return launch_fast8<3, 128, 8>(kp, st);
+        case 4: return launch_fast8<4, 128, 8>(kp, st);
         default: return 1;
     }
 }
@@ -1018,6 +1028,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->bps = cfg->depth > 8 ? 2 : 1;
     h->impl = 0;
     if (const char *e = getenv("HBCU_NLMEANS_IMPL")) h->impl = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;   // test hook
+    if (const char *e = getenv("HBCU_NLMEANS_VARIANT")) g_fast8_variant = atoi(e);                            // tuning hook
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;
@@ -1065,7 +1076,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         {
             CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
             CK(cudaMalloc(&h->raw_mem[s * 3 + pl], h->g[pl].rbytes));
-            const int th = h->bps == 1 ? 128 : 96;
+            const int th = h->bps == 1 ? (g_fast8_variant == 1 ? 144 : 128) : 96;
             if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
                                            (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
                                            th + 2 * kHalo) != 0)

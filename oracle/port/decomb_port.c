@@ -157,10 +157,16 @@ static void put(uint8_t *base, int w, int depth, int x, int y, int v)
     else base[i] = (uint8_t)v;
 }
 
-void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, uint8_t *dst,
-                         int width, int height, int depth, int filter_mode_unused, int mode, int parity, int tff)
+void *oracle_eedi2_create(int width, int height, int depth, int mthresh, int vthresh, int lthresh, int dstr, int estr,
+                          int nt, int maxd, int pp);
+void oracle_eedi2_destroy(void *e);
+void oracle_eedi2_field(void *e, const uint8_t *cur, int tff, uint8_t *out);
+
+/* `eedi`: packed EEDI2 interpolation of this field (or NULL).  With it, mode carries the EEDI2 bit:
+ * yadif takes its spatial prediction from it (:648-653); without yadif the picture IS the interpolation (:855-875) */
+static void decomb_field_ex(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, const uint8_t *eedi, uint8_t *dst,
+                            int width, int height, int depth, int mode, int parity, int tff)
 {
-    (void)filter_mode_unused;
     const int bps = depth > 8 ? 2 : 1, maxv = (1 << depth) - 1;
     const int cw = -((-width) >> 1), ch = -((-height) >> 1);
     const int pw[3] = { width, cw, cw }, ph[3] = { height, ch, ch };
@@ -168,8 +174,14 @@ void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t 
     for (int pp = 0; pp < 3; pp++)
     {
         plane_t P = { prev + off, pw[pp], ph[pp], depth }, C = { cur + off, pw[pp], ph[pp], depth },
-                N = { next + off, pw[pp], ph[pp], depth };
+                N = { next + off, pw[pp], ph[pp], depth }, E = { eedi ? eedi + off : NULL, pw[pp], ph[pp], depth };
         uint8_t *D = dst + off;
+        if (eedi != NULL && !(mode & ORACLE_DECOMB_YADIF))
+        {
+            memcpy(D, E.base, (size_t)pw[pp] * ph[pp] * bps);
+            off += (size_t)pw[pp] * ph[pp] * bps;
+            continue;
+        }
         for (int y = 0; y < ph[pp]; y++)
         {
             /* parity 1 filters the even rows, parity 0 the odd rows (template :744, :796) */
@@ -183,12 +195,19 @@ void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t 
                 else if (mode == ORACLE_DECOMB_CUBIC)
                     put(D, pw[pp], depth, x, y, cubic_line_px(&C, x, y, maxv));
                 else if (mode & ORACLE_DECOMB_YADIF)
-                    put(D, pw[pp], depth, x, y, yadif_px(&P, &C, &N, NULL, x, y, parity ^ tff, mode, maxv));
+                    put(D, pw[pp], depth, x, y, yadif_px(&P, &C, &N, eedi ? &E : NULL, x, y, parity ^ tff, mode, maxv));
                 /* else: no line filter runs; the reference leaves the row unwritten */
             }
         }
         off += (size_t)pw[pp] * ph[pp] * bps;
     }
+}
+
+void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, uint8_t *dst,
+                         int width, int height, int depth, int filter_mode_unused, int mode, int parity, int tff)
+{
+    (void)filter_mode_unused;
+    decomb_field_ex(prev, cur, next, NULL, dst, width, height, depth, mode, parity, tff);
 }
 
 int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const uint8_t *combed,
@@ -199,6 +218,9 @@ int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const
     const int cw = -((-width) >> 1), ch = -((-height) >> 1);
     const size_t fb = ((size_t)width * height + 2 * (size_t)cw * ch) * bps;
     int n_out = 0;
+    /* EEDI2 with the filter's default thresholds (decomb.c:234-243); its edge-mask state lives for the whole clip */
+    void *eedi_state = (mode & ORACLE_DECOMB_EEDI2) ? oracle_eedi2_create(width, height, depth, 10, 20, 20, 4, 2, 50, 24, 1) : NULL;
+    uint8_t *eedi_frame = eedi_state ? malloc(fb) : NULL;
     for (int t = 0; t < n_in; t++)
     {
         const uint8_t *cur = in + (size_t)t * fb;
@@ -231,10 +253,17 @@ int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const
             uint8_t *dst = out + (size_t)n_out * fb;
             memset(dst, 0, fb);                                  /* shim buffers start zeroed */
             if (fmode == 0) memcpy(dst, cur, fb);
-            else oracle_decomb_field(prev, cur, next, dst, width, height, depth, 0, fmode & ~ORACLE_DECOMB_EEDI2, parity, tff);
+            else if (fmode & ORACLE_DECOMB_EEDI2)
+            {
+                oracle_eedi2_field(eedi_state, cur, !parity, eedi_frame);        /* pv->tff = !parity (decomb.c:539-542) */
+                decomb_field_ex(prev, cur, next, eedi_frame, dst, width, height, depth, fmode, parity, tff);
+            }
+            else decomb_field_ex(prev, cur, next, NULL, dst, width, height, depth, fmode, parity, tff);
             if (out_src) out_src[n_out] = t;
             n_out++;
         }
     }
+    if (eedi_state) oracle_eedi2_destroy(eedi_state);
+    free(eedi_frame);
     return n_out;
 }

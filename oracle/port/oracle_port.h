@@ -77,10 +77,17 @@ int oracle_comb_detect_clip(const uint8_t *in, int n_in, int width, int height, 
 
 /* one output field/frame of filter_{8,16} (decomb template :810-898) for all three planes.
  * prev/cur/next/dst: packed planar yuv420 frames; `mode` is the per-frame mode chosen by the
- * caller (decomb template :823-831) with the EEDI2 bit clear; rows the reference leaves
+ * caller (decomb template :823-831) with the EEDI2 bit clear (oracle_decomb_clip handles EEDI2 modes); rows the reference leaves
  * unwritten (mode combinations without a line filter) stay as they are in dst. */
 void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, uint8_t *dst,
                          int width, int height, int depth, int filter_mode, int mode, int parity, int tff);
+
+/* EEDI2 (libhb/templates/eedi2_template.c via eedi2_interpolate_plane): a handle carries the edge-mask
+ * state from field to field; one call interpolates field `!tff` of `cur` (packed planar) to a full frame */
+void *oracle_eedi2_create(int width, int height, int depth, int mthresh, int vthresh, int lthresh, int dstr, int estr,
+                          int nt, int maxd, int pp);
+void  oracle_eedi2_destroy(void *e);
+void  oracle_eedi2_field(void *e, const uint8_t *cur, int tff, uint8_t *out);
 
 /* whole clip through hb_decomb_work/process_frame (decomb.c:500-612).  flags/combed: per input
  * frame s.flags and s.combed; out must hold 2*n_in frames; returns the number of output frames.
