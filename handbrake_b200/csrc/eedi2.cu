@@ -645,11 +645,40 @@ __global__ void k_lattice_a(int plane, const PIX *__restrict__ dmskp, const PIX 
     tmp[(size_t)row * width + x] = t;
 }
 
-template <typename PIX>
-__global__ void k_lattice_b(PIX *__restrict__ dmskp, PIX *__restrict__ dst_base, const LatticeTmp *__restrict__ tmp,
-                            int pitch, int width, int height, int field, int depth)
+// Pass B as a parallel scan.  Pixel x maps the rewritten mask of its left neighbour m to its own
+// rewritten mask:  f_x(m) = peak                         if cur == peak
+//                          B_x                          if |cur - dm[x+1]| <= lim          (first test cannot fire)
+//                          (|cur - m| > lim) ? neutral : B_x   otherwise
+// i.e. every f_x, and every composition of them, has the form  F(m) = (lo <= m <= hi) ? vin : vout.
+// That family is closed under composition, so the chain m_x = f_x(m_{x-1}) is an associative scan:
+// each thread composes a contiguous chunk, a block-wide Hillis-Steele scan composes the chunks, and a
+// second walk applies the now-known incoming value.  One CTA per row; the row is staged in shared memory.
+struct LatFn { int lo, hi, vin, vout; };
+__device__ __forceinline__ int lat_apply(const LatFn &f, int m) { return (m >= f.lo && m <= f.hi) ? f.vin : f.vout; }
+__device__ __forceinline__ LatFn lat_compose(const LatFn &later, const LatFn &earlier)
 {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    return LatFn{ earlier.lo, earlier.hi, lat_apply(later, earlier.vin), lat_apply(later, earlier.vout) };
+}
+__device__ __forceinline__ LatFn lat_pixel(int cur, const LatticeTmp &e, int peak, int neutral)
+{
+    if (cur == peak) return LatFn{ 1, 0, peak, peak };                       // empty interval: constant
+    if (!e.nextfar) return LatFn{ 1, 0, (int)e.mskB, (int)e.mskB };
+    return LatFn{ cur - (int)e.lim, cur + (int)e.lim, (int)e.mskB, neutral };
+}
+
+constexpr int kLatThreads = 256;
+
+template <typename PIX>
+__global__ void __launch_bounds__(kLatThreads) k_lattice_b(PIX *__restrict__ dmskp, PIX *__restrict__ dst_base, const LatticeTmp *__restrict__ tmp,
+                                                           int pitch, int width, int height, int field, int depth)
+{
+    extern __shared__ __align__(16) unsigned char lat_smem[];
+    LatticeTmp *s_t = reinterpret_cast<LatticeTmp *>(lat_smem);                       // width entries
+    int *s_cur = reinterpret_cast<int *>(lat_smem + (size_t)width * sizeof(LatticeTmp));      // width
+    int *s_prevm = s_cur + width;                                                    // width: rewritten mask of x-1
+    __shared__ LatFn s_fn[kLatThreads];
+
+    const int row = blockIdx.x;
     const int y = 2 - field + 2 * row;
     if (y >= height - 1) return;
     const int peak = (1 << depth) - 1, neutral = 1 << (depth - 1);
@@ -657,13 +686,59 @@ __global__ void k_lattice_b(PIX *__restrict__ dmskp, PIX *__restrict__ dst_base,
     PIX *dn = dst_base + (size_t)y * pitch;
     const PIX *up = dn - pitch, *down = dn + pitch;
     const LatticeTmp *t = tmp + (size_t)row * width;
-    int prev = dm[-1];                                    // linear predecessor of the row (unwritten by this pass)
-    for (int x = 0; x < width; ++x)
+    const int tid = threadIdx.x;
+    for (int x = tid; x < width; x += kLatThreads)
     {
-        const int cur = dm[x];
-        const LatticeTmp e = t[x];
+        s_t[x] = t[x];
+        s_cur[x] = dm[x];
+    }
+    __syncthreads();
+    const int chunk = (width + kLatThreads - 1) / kLatThreads;
+    const int x0 = tid * chunk, x1 = min(x0 + chunk, width);
+    LatFn f{ 1, 0, 0, 0 };
+    bool have = false;
+    for (int x = x0; x < x1; ++x)
+    {
+        const LatFn g = lat_pixel(s_cur[x], s_t[x], peak, neutral);
+        f = have ? lat_compose(g, f) : g;
+        have = true;
+    }
+    // identity for empty chunks: F(m) = m cannot be written as an interval test, so mark them and skip
+    s_fn[tid] = f;
+    __shared__ unsigned char s_has[kLatThreads];
+    s_has[tid] = have;
+    __syncthreads();
+    // inclusive scan of compositions (later o earlier) over the non-empty chunks
+    for (int off = 1; off < kLatThreads; off <<= 1)
+    {
+        LatFn mine = s_fn[tid];
+        bool mh = s_has[tid];
+        LatFn other{ 1, 0, 0, 0 };
+        bool oh = false;
+        if (tid >= off) { other = s_fn[tid - off]; oh = s_has[tid - off]; }
+        __syncthreads();
+        if (oh)
+        {
+            s_fn[tid] = mh ? lat_compose(mine, other) : other;
+            s_has[tid] = true;
+        }
+        __syncthreads();
+    }
+    const int m_init = dm[-1];                                  // linear predecessor of the row (not rewritten by this pass)
+    int prev = m_init;
+    if (tid > 0 && s_has[tid - 1]) prev = lat_apply(s_fn[tid - 1], m_init);
+    for (int x = x0; x < x1; ++x)
+    {
+        s_prevm[x] = prev;
+        prev = lat_apply(lat_pixel(s_cur[x], s_t[x], peak, neutral), prev);
+    }
+    __syncthreads();
+    for (int x = tid; x < width; x += kLatThreads)
+    {
+        const int cur = s_cur[x];
+        const LatticeTmp e = s_t[x];
         int newm, val;
-        if (cur == peak || (abs(cur - prev) > (int)e.lim && e.nextfar))
+        if (cur == peak || (abs(cur - s_prevm[x]) > (int)e.lim && e.nextfar))
         {
             val = ((int)up[x] + (int)down[x] + 1) >> 1;
             newm = cur != peak ? neutral : cur;
@@ -675,7 +750,6 @@ __global__ void k_lattice_b(PIX *__restrict__ dmskp, PIX *__restrict__ dst_base,
         }
         dn[x] = (PIX)val;
         dm[x] = (PIX)newm;
-        prev = newm;
     }
 }
 
@@ -777,7 +851,7 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     if (tff == 1) LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + (size_t)(height - 2) * pitch, dst2p + (size_t)(height - 1) * pitch, pitch, width, 1)));
     else          LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + pitch, dst2p, pitch, width, 1)));
     LAUNCH((k_lattice_a<PIX><<<grid2(width, rows2), blk, 0, st>>>(pl, tmp2p, dst2p, tmp2p2, e->lattice_tmp, pitch, width, height, tff, c.nt, depth, e->lim)));
-    LAUNCH((k_lattice_b<PIX><<<(rows2 + 63) / 64, 64, 0, st>>>(tmp2p, dst2p, e->lattice_tmp, pitch, width, height, tff, depth)));
+    LAUNCH((k_lattice_b<PIX><<<rows2, kLatThreads, (size_t)width * (sizeof(LatticeTmp) + 2 * sizeof(int)), st>>>(tmp2p, dst2p, e->lattice_tmp, pitch, width, height, tff, depth)));
 
     if (c.pp == 1 || c.pp == 3)
     {
@@ -854,6 +928,14 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
     {
         ok = cudaMalloc(&e->full_mem[k], kLeadSlack + fo + tail) == cudaSuccess &&
              cudaMemset(e->full_mem[k], 0, kLeadSlack + fo + tail) == cudaSuccess;
+    }
+    {
+        const int need = cfg.w[0] * (int)(sizeof(LatticeTmp) + 2 * sizeof(int));
+        if (need > 48 * 1024)
+        {
+            cudaFuncSetAttribute(k_lattice_b<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+            cudaFuncSetAttribute(k_lattice_b<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+        }
     }
     if (ok) ok = cudaMalloc(&e->lattice_tmp, sizeof(LatticeTmp) * (size_t)cfg.w[0] * (cfg.h[0] / 2 + 1)) == cudaSuccess;
     if (!ok)

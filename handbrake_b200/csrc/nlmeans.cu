@@ -806,17 +806,19 @@ int launch_fast8(const TiledParams &kp, cudaStream_t st)
     return 0;
 }
 
-int g_fast8_variant = 0;     // 0: 8 warps x 16 rows (TH 128); 1: 12 warps x 12 rows (TH 144); HBCU_NLMEANS_VARIANT
+// 8-bit tiles are 128 x 144: 12 warps x 12 rows for patch <= 7 (measured 7 % faster than 8 warps x 16 rows:
+// more warps hide the dependent-issue latency better than the extra warm-up rows cost), 8 warps x 18 rows
+// for patch 9 whose register footprint does not allow 384 threads.
+constexpr int kTH8 = 144;
 
 int launch_fast8_nh(const TiledParams &kp, cudaStream_t st)
 {
-    if (g_fast8_variant == 1 && kp.k.n_half == 3) return launch_fast8<3, 144, 12>(kp, st);
     switch (kp.k.n_half)
     {
-        case 1: return launch_fast8<1, 128, 8>(kp, st);
-        case 2: return launch_fast8<2, 128, 8>(kp, st);
-        case 3: return launch_fast8<3, 128, 8>(kp, st);
-        case 4: return launch_fast8<4, 128, 8>(kp, st);
+        case 1: return launch_fast8<1, kTH8, 12>(kp, st);
+        case 2: return launch_fast8<2, kTH8, 12>(kp, st);
+        case 3: return launch_fast8<3, kTH8, 12>(kp, st);
+        case 4: return launch_fast8<4, kTH8, 8>(kp, st);
         default: return 1;
     }
 }
@@ -855,7 +857,7 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
         // impl 0/2: fp32-exact fast kernel for 8-bit planes when the table trick is valid; impl 3: integer tiled kernel
         const bool fast_ok = h->bps == 1 && kp.wfact < 0.99f && kp.wfact > 1e-5f;
         int rc = (fast_ok && h->impl != 3) ? launch_fast8_nh(tp, h->s_compute)
-                 : h->bps == 1           ? launch_tiled_nh<uint8_t, 128>(tp, h->s_compute)
+                 : h->bps == 1           ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute)
                                          : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
         if (rc < 0) return rc;
         if (rc == 0)
@@ -1028,7 +1030,6 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->bps = cfg->depth > 8 ? 2 : 1;
     h->impl = 0;
     if (const char *e = getenv("HBCU_NLMEANS_IMPL")) h->impl = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;   // test hook
-    if (const char *e = getenv("HBCU_NLMEANS_VARIANT")) g_fast8_variant = atoi(e);                            // tuning hook
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;
@@ -1076,7 +1077,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         {
             CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
             CK(cudaMalloc(&h->raw_mem[s * 3 + pl], h->g[pl].rbytes));
-            const int th = h->bps == 1 ? (g_fast8_variant == 1 ? 144 : 128) : 96;
+            const int th = h->bps == 1 ? kTH8 : 96;
             if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
                                            (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
                                            th + 2 * kHalo) != 0)
