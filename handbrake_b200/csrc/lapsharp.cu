@@ -27,35 +27,89 @@ __constant__ int c_kernels[4][25] = {
     { 0, 0, -1, 0, 0, 0, -1, -2, -1, 0, -1, -2, 21, -2, -1, 0, -1, -2, -1, 0, 0, 0, -1, 0, 0 },        // log
     { 0, -1, -1, -1, 0, -1, -3, -4, -3, -1, -1, -4, 55, -4, -1, -1, -3, -4, -3, -1, 0, -1, -1, -1, 0 } // isolog
 };
-__constant__ int c_ksize[4] = { 3, 3, 5, 5 };
 
-template <typename PIX, typename ACC>
+// one thread = 4 adjacent pixels of one row; the SIZE x (SIZE+3) input window is read once into registers
+template <typename PIX, typename ACC, int SIZE>
 __global__ void __launch_bounds__(256) lapsharp_kernel(const PIX *__restrict__ src, PIX *__restrict__ dst, int width, int height,
                                                       int spitch, int dpitch, int kid, double coef, double strength, int max_value)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= width || y >= height) return;
-    const int size = c_ksize[kid];
-    const int offset_min = -((size - 1) / 2), offset_max = (size + 1) / 2;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= width || y >= height) return;
+    constexpr int offset_min = -((SIZE - 1) / 2), offset_max = (SIZE + 1) / 2;
     const int stride_border = (spitch - width) / 2;
-    const int s0 = src[(size_t)y * spitch + x];
-    if ((y < offset_max) || (y > height - offset_max) || (x < stride_border + offset_max) || (x > width + stride_border - offset_max))
+    const PIX *row = src + (size_t)y * spitch;
+    int out[4];
+    const bool row_copy = (y < offset_max) || (y > height - offset_max);
+    // the whole group of 4 is interior when its first and last pixel are (the x conditions are monotone)
+    const bool all_interior = !row_copy && !(x0 < stride_border + offset_max) && !(x0 + 3 > width + stride_border - offset_max) && (x0 + 3 < width);
+    if (all_interior)
     {
-        dst[(size_t)y * dpitch + x] = (PIX)s0;
-        return;
-    }
-    int acc = 0;
-    for (int k = offset_min; k < offset_max; k++)
+        int acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
         for (int j = offset_min; j < offset_max; j++)
-            acc += c_kernels[kid][(j - offset_min) * size + k - offset_min] * (int)src[(size_t)(y + j) * spitch + (x + k)];
-    ACC pixel = (ACC)acc;                                   // the reference accumulates in ACC (wraps like it)
-    // pixel = (ACC)(((pixel * coef) - src) * strength) + src
-    const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
-    pixel = (ACC)((int)(ACC)(int)t + s0);
-    int v = pixel;
-    v = v < 0 ? 0 : v;
-    v = v > max_value ? max_value : v;
-    dst[(size_t)y * dpitch + x] = (PIX)v;
+        {
+            const PIX *r = src + (size_t)(y + j) * spitch + x0 + offset_min;
+            int v[SIZE + 3];
+#pragma unroll
+            for (int t = 0; t < SIZE + 3; t++) v[t] = r[t];
+#pragma unroll
+            for (int k = 0; k < SIZE; k++)
+            {
+                const int c = c_kernels[kid][(j - offset_min) * SIZE + k];
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] += c * v[i + k];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            const int s0 = row[x0 + i];
+            ACC pixel = (ACC)acc[i];                                // the reference accumulates in ACC (wraps like it)
+            const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
+            pixel = (ACC)((int)(ACC)(int)t + s0);
+            int v = pixel;
+            v = v < 0 ? 0 : v;
+            out[i] = v > max_value ? max_value : v;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            const int x = x0 + i;
+            if (x >= width) { out[i] = 0; continue; }
+            const int s0 = row[x];
+            if (row_copy || (x < stride_border + offset_max) || (x > width + stride_border - offset_max))
+            {
+                out[i] = s0;
+                continue;
+            }
+            int acc = 0;
+#pragma unroll
+            for (int k = offset_min; k < offset_max; k++)
+#pragma unroll
+                for (int j = offset_min; j < offset_max; j++)
+                    acc += c_kernels[kid][(j - offset_min) * SIZE + k - offset_min] * (int)src[(size_t)(y + j) * spitch + (x + k)];
+            ACC pixel = (ACC)acc;
+            const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
+            pixel = (ACC)((int)(ACC)(int)t + s0);
+            int v = pixel;
+            v = v < 0 ? 0 : v;
+            out[i] = v > max_value ? max_value : v;
+        }
+    }
+    PIX *drow = dst + (size_t)y * dpitch;
+    if (x0 + 3 < width)
+    {
+        if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(drow + x0) = make_uchar4(out[0], out[1], out[2], out[3]);
+        else                  *reinterpret_cast<ushort4 *>(drow + x0) = make_ushort4(out[0], out[1], out[2], out[3]);
+    }
+    else
+    {
+        for (int i = 0; i < 4; i++)
+            if (x0 + i < width) drow[x0 + i] = (PIX)out[i];
+    }
 }
 
 struct Geom { int w, h, pitch; size_t bytes; };
@@ -81,14 +135,14 @@ const double kCoef[4] = { 1.0, 1.0 / 5, 1.0 / 5, 1.0 / 15 };     // lapsharp.c:9
 int launch(hbcu_lapsharp_s *h, int pl, const void *src, int spitch_elems, void *dst)
 {
     const Geom &g = h->g[pl];
-    dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
+    dim3 blk(32, 8), grid(((g.w + 3) / 4 + 31) / 32, (g.h + 7) / 8);
     const int kid = h->cfg.kernel[pl];
-    if (h->bps == 1)
-        lapsharp_kernel<uint8_t, int16_t><<<grid, blk, 0, h->s_compute>>>((const uint8_t *)src, (uint8_t *)dst, g.w, g.h, spitch_elems,
-                                                                        g.pitch, kid, kCoef[kid], h->cfg.strength[pl], h->maxv);
-    else
-        lapsharp_kernel<uint16_t, int32_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, (uint16_t *)dst, g.w, g.h, spitch_elems,
-                                                                          g.pitch, kid, kCoef[kid], h->cfg.strength[pl], h->maxv);
+    const bool small = kid < 2;                       // lap / isolap are 3x3, log / isolog 5x5
+#define LAP_LAUNCH(PIX, ACC, SIZE) lapsharp_kernel<PIX, ACC, SIZE><<<grid, blk, 0, h->s_compute>>>((const PIX *)src, (PIX *)dst, g.w, g.h, \
+        spitch_elems, g.pitch, kid, kCoef[kid], h->cfg.strength[pl], h->maxv)
+    if (h->bps == 1) { if (small) LAP_LAUNCH(uint8_t, int16_t, 3); else LAP_LAUNCH(uint8_t, int16_t, 5); }
+    else             { if (small) LAP_LAUNCH(uint16_t, int32_t, 3); else LAP_LAUNCH(uint16_t, int32_t, 5); }
+#undef LAP_LAUNCH
     hbcu::count_launch();
     HBCU_CHECK(cudaGetLastError());
     return 0;

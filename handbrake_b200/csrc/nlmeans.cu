@@ -86,6 +86,39 @@ __global__ void pad_mirror_kernel(const PIX *__restrict__ src, int spitch, int w
     dst[(size_t)by * bpitch + bx] = src[(size_t)y * spitch + x];
 }
 
+// 16 bytes per thread: interior chunks are straight uint4 copies, the chunks that touch the mirror border go element by element
+template <typename PIX>
+__global__ void __launch_bounds__(256) pad_mirror_vec_kernel(const PIX *__restrict__ src, int spitch, int w, int h,
+                                                            PIX *__restrict__ dst, int bpitch, int border)
+{
+    constexpr int EPC = 16 / (int)sizeof(PIX);
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y * blockDim.y + threadIdx.y;
+    const int bw = w + 2 * border, bh = h + 2 * border;
+    const int bx0 = cx * EPC;
+    if (bx0 >= bw || by >= bh) return;
+    int y = by - border;
+    if (y < 0) y = -1 - y; else if (y >= h) y = 2 * h - 1 - y;
+    y = min(max(y, 0), h - 1);
+    PIX *drow = dst + (size_t)by * bpitch;
+    const PIX *srow = src + (size_t)y * spitch;
+    if (bx0 >= border && bx0 + EPC <= border + w)
+    {
+        *reinterpret_cast<uint4 *>(drow + bx0) = *reinterpret_cast<const uint4 *>(srow + (bx0 - border));
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < EPC; i++)
+    {
+        const int bx = bx0 + i;
+        if (bx >= bw) break;
+        int x = bx - border;
+        if (x < 0) x = -1 - x; else if (x >= w) x = 2 * w - 1 - x;
+        x = min(max(x, 0), w - 1);
+        drow[bx] = srow[x];
+    }
+}
+
 template <typename PIX>
 __global__ void copy_plane_kernel(const PIX *__restrict__ src, int spitch, int w, int h,
                                   PIX *__restrict__ dst, int dpitch)
@@ -331,6 +364,18 @@ struct TiledParams
 {
     KernelParams k;
     CUtensorMap  maps[kMaxTiledFrames];   // one TMA descriptor per frame of the temporal window
+};
+
+// The fast 8-bit kernel takes up to three planes in ONE launch (tiles of Y, U and V in one grid):
+// three separate launches end in three partial waves (510 + 135 + 135 CTAs on 148 SMs = 6 rounds),
+// one launch of all tiles needs 5.
+struct FusedParams
+{
+    int nplanes;
+    int first_tile[4];                    // first linear tile index of each plane, [nplanes] = total
+    int tiles_x[3];
+    KernelParams k[3];
+    CUtensorMap  maps[3][kMaxTiledFrames];
 };
 
 template <typename PIX, int NH, int TH>
@@ -622,11 +667,191 @@ __device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur,
     }
 }
 
-template <int NH, int TH, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_constant__ TiledParams tp)
+template <int NH, int TH, int NW, bool ORIGIN>
+__device__ __forceinline__ void nlm_group_dp4a(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp,
+                                               float *__restrict__ acc_ws, float *__restrict__ acc_ps,
+                                               uint32_t lut_lane_addr, float wscale, double origin_tune,
+                                               int seg_y0, int lane, int dy, int dx0, int ng, int origin_g)
+{
+    constexpr int N   = 2 * NH + 1;
+    constexpr int RS  = TH / NW;
+    constexpr int NA  = 4 + 2 * NH;                 // source values per row
+    constexpr int NB  = NA + kGroup - 1;            // compare values per row
+    constexpr int PW  = kTilePW / 4;                // tile pitch in words
+    constexpr int OA  = (kHaloX - NH) & 3;          // byte offset of a[0] in its first word
+    constexpr int WA0 = (kHaloX - NH) >> 2;         // first word of the a window (relative to lane word)
+    constexpr int NWA = (OA + NA + 3) / 4;
+    constexpr int NWB = (NB + 3) / 4;               // aligned compare words
+    constexpr float kBias = 8388608.0f;             // 2^23
+
+    const int fb  = kHaloX - NH + dx0;              // first compare column relative to the lane's x
+    const int wb0 = fb >> 2;
+    const int ob  = (fb & 3) * 8;                   // funnel shift (bits) that aligns the compare window
+
+    int V[kGroup][4];
+    int hist[N][kGroup][4];
+#pragma unroll
+    for (int g = 0; g < kGroup; g++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            V[g][i] = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) hist[k][g][i] = 0;
+        }
+    // aligned compare words of the last NH rows: they hold the pixels cmp[y+dy][x+dx] of the
+    // output row that completes NH steps after its own compare row was loaded
+    uint32_t delay[NH][NWB];
+#pragma unroll
+    for (int r = 0; r < NH; r++)
+#pragma unroll
+        for (int j = 0; j < NWB; j++) delay[r][j] = 0;
+
+#pragma unroll 1
+    for (int base = -NH; base < RS + NH; base += N)
+    {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+        {
+            const int yy = base + k;
+            if (yy < RS + NH)
+            {
+                const int ty = seg_y0 + yy + kHalo;
+                const uint32_t *aw = cur + ty * PW + lane + WA0;
+                const uint32_t *bw = cmp + (ty + dy) * PW + lane + wb0;
+                uint32_t wa[NWA], wraw[NWB + 1], wbv[NWB];
+#pragma unroll
+                for (int j = 0; j < NWA; j++) wa[j] = aw[j];
+#pragma unroll
+                for (int j = 0; j < NWB + 1; j++) wraw[j] = bw[j];
+#pragma unroll
+                for (int j = 0; j < NWB; j++) wbv[j] = __funnelshift_r(wraw[j], wraw[j + 1], ob);
+
+                // Patch-row sums straight from the packed bytes: |a-b| for four pixels per VABSDIFF4, sums of
+                // squares over the 2NH+1 byte window per IDP4A (whole words) plus masked IDP4As for the partial
+                // words at both ends.  Integer-exact, no unpacking.
+                constexpr int NWD = (NA + 3) / 4;                    // words holding a[0..NA-1]
+                uint32_t aw4[NWD];
+#pragma unroll
+                for (int w = 0; w < NWD; w++)
+                    aw4[w] = OA ? __funnelshift_r(wa[w], (w + 1 < NWA) ? wa[w + 1] : 0u, 8 * OA) : wa[w];
+#pragma unroll
+                for (int g = 0; g < kGroup; g++)
+                {
+                    if (g < ng && (!ORIGIN || g != origin_g))
+                    {
+                        uint32_t D[NWD];
+#pragma unroll
+                        for (int w = 0; w < NWD; w++)
+                        {
+                            const uint32_t bg = g ? __funnelshift_r(wbv[w], (w + 1 < NWB) ? wbv[w + 1] : 0u, 8 * g) : wbv[w];
+                            D[w] = __vabsdiffu4(aw4[w], bg);
+                        }
+                        uint32_t T[NWD];
+#pragma unroll
+                        for (int w = 0; w < NWD; w++) T[w] = __dp4a(D[w], D[w], 0u);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                        {
+                            // window = bytes i .. i+N-1 of the D stream
+                            uint32_t acc = 0;
+                            bool started = false;
+#pragma unroll
+                            for (int w = 0; w < NWD; w++)
+                            {
+                                const int lo = max(i, 4 * w), hi = min(i + N - 1, 4 * w + 3);
+                                if (lo == 4 * w && hi == 4 * w + 3 && !started) { acc = T[w]; started = true; }
+                            }
+                            bool used_full = false;
+#pragma unroll
+                            for (int w = 0; w < NWD; w++)
+                            {
+                                const int lo = max(i, 4 * w), hi = min(i + N - 1, 4 * w + 3);
+                                if (lo > hi) continue;
+                                if (lo == 4 * w && hi == 4 * w + 3)
+                                {
+                                    if (started && !used_full) { used_full = true; continue; }   // already in acc
+                                    acc = __dp4a(D[w], D[w], acc);
+                                }
+                                else
+                                {
+                                    uint32_t m = 0;
+#pragma unroll
+                                    for (int bb = 0; bb < 4; bb++)
+                                        if (4 * w + bb >= lo && 4 * w + bb <= hi) m |= 0xFFu << (8 * bb);
+                                    acc = __dp4a(D[w] & m, D[w], acc);
+                                }
+                            }
+                            const int hsum = (int)acc;
+                            V[g][i] = V[g][i] + hsum - hist[k][g][i];
+                            hist[k][g][i] = hsum;
+                        }
+                    }
+                }
+                if (yy >= NH)
+                {
+                    const int oy = seg_y0 + yy - NH;
+                    float4 ws4 = *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + lane * 4);
+                    float4 ps4 = *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + lane * 4);
+                    float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+                    float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+                    // pixel values cmp[oy+dy][x+dx0+g+i] = element NH+g+i of the compare window loaded NH rows ago
+                    float pixv[kGroup + 3];
+#pragma unroll
+                    for (int j = 0; j < kGroup + 3; j++)
+                        pixv[j] = __fsub_rn(byte_as_biased_float(delay[0][(NH + j) >> 2], (NH + j) & 3), kBias);
+#pragma unroll
+                    for (int g = 0; g < kGroup; g++)
+                    {
+                        if (g < ng)
+                        {
+                            if (ORIGIN && g == origin_g)
+                            {
+                                const uint32_t cw = cur[(oy + kHalo) * PW + lane + kHaloX / 4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    add_origin(ws[i], ps[i], origin_tune, (int)((cw >> (8 * i)) & 0xffu));
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                {
+                                    float t, u, wgt;
+                                    asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(t) : "f"(__int2float_rn(V[g][i])), "f"(wscale));
+                                    asm("add.rz.f32 %0, %1, 0f47800000;" : "=f"(u) : "f"(t));   // 65536 + floor(128 t)
+                                    const uint32_t addr = (__float_as_uint(u) << 7) + lut_lane_addr;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(wgt) : "r"(addr));
+                                    ws[i] = __fadd_rn(ws[i], wgt);
+                                    ps[i] = __fadd_rn(ps[i], __fmul_rn(wgt, pixv[g + i]));
+                                }
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + lane * 4) = make_float4(ws[0], ws[1], ws[2], ws[3]);
+                    *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + lane * 4) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+                }
+                // advance the delay line
+#pragma unroll
+                for (int r = 0; r + 1 < NH; r++)
+#pragma unroll
+                    for (int j = 0; j < NWB; j++) delay[r][j] = delay[r + 1][j];
+#pragma unroll
+                for (int j = 0; j < NWB; j++) delay[NH - 1][j] = wbv[j];
+            }
+        }
+    }
+}
+
+template <int NH, int TH, int NW, bool DP4A>
+__global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_constant__ FusedParams fp)
 {
     constexpr int kThreads = NW * 32;
-    const KernelParams &p = tp.k;
+    int pl = 0;
+    while (pl + 1 < fp.nplanes && (int)blockIdx.x >= fp.first_tile[pl + 1]) pl++;
+    const KernelParams &p = fp.k[pl];
+    const CUtensorMap *maps = fp.maps[pl];
+    const int tile = (int)blockIdx.x - fp.first_tile[pl];
     using L = FastLayout<TH>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *cur  = smem + L::kOffCur;
@@ -637,7 +862,7 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int X0 = blockIdx.x * kTileW, Y0 = blockIdx.y * TH;
+    const int X0 = (tile % fp.tiles_x[pl]) * kTileW, Y0 = (tile / fp.tiles_x[pl]) * TH;
     const int gx = X0 + kBorder - kHaloX, gy = Y0 + kBorder - kHalo;
 
     if (tid == 0)
@@ -650,7 +875,7 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_
     if (tid == 0)
     {
         mbar_expect_tx(bar, L::kTileBytes);
-        tma_load_2d(cur, &tp.maps[0], gx, gy, bar);
+        tma_load_2d(cur, &maps[0], gx, gy, bar);
     }
     for (int i = tid; i < kLutEntries * 32; i += kThreads)
     {
@@ -680,7 +905,7 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_
             {
                 fence_proxy_async();
                 mbar_expect_tx(bar, L::kTileBytes);
-                tma_load_2d(cmp, &tp.maps[f], gx, gy, bar);
+                tma_load_2d(cmp, &maps[f], gx, gy, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -694,12 +919,21 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_
                 const int origin_g = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : -1;
                 // the origin variant (double-precision add of origin_tune) runs for one group per plane;
                 // keeping it out of the common instantiation keeps that loop body small
-                if (origin_g >= 0)
-                    nlm_group_fast<NH, TH, NW, true>(reinterpret_cast<const uint32_t *>(cur), reinterpret_cast<const uint32_t *>(B),
-                                                     acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *bw32 = reinterpret_cast<const uint32_t *>(B);
+                if (DP4A)
+                {
+                    if (origin_g >= 0)
+                        nlm_group_dp4a<NH, TH, NW, true>(cw, bw32, acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+                    else
+                        nlm_group_dp4a<NH, TH, NW, false>(cw, bw32, acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, -1);
+                }
                 else
-                    nlm_group_fast<NH, TH, NW, false>(reinterpret_cast<const uint32_t *>(cur), reinterpret_cast<const uint32_t *>(B),
-                                                      acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, -1);
+                {
+                    if (origin_g >= 0)
+                        nlm_group_fast<NH, TH, NW, true>(cw, bw32, acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+                    else
+                        nlm_group_fast<NH, TH, NW, false>(cw, bw32, acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, -1);
+                }
             }
         }
     }
@@ -790,18 +1024,25 @@ int launch_tiled(const TiledParams &kp, cudaStream_t st)
     return 0;
 }
 
-template <int NH, int TH, int NW>
-int launch_fast8(const TiledParams &kp, cudaStream_t st)
+template <int NH, int TH, int NW, bool DP4A>
+int launch_fast8(FusedParams &fp, cudaStream_t st)
 {
     using L = FastLayout<TH>;
     static bool configured = false;
     if (!configured)
     {
-        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast8_kernel<NH, TH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast8_kernel<NH, TH, NW, DP4A>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured = true;
     }
-    dim3 grid((kp.k.w + kTileW - 1) / kTileW, (kp.k.h + TH - 1) / TH);
-    nlmeans_fast8_kernel<NH, TH, NW><<<grid, NW * 32, L::kTotal, st>>>(kp);
+    int total = 0;
+    for (int i = 0; i < fp.nplanes; i++)
+    {
+        fp.first_tile[i] = total;
+        fp.tiles_x[i] = (fp.k[i].w + kTileW - 1) / kTileW;
+        total += fp.tiles_x[i] * ((fp.k[i].h + TH - 1) / TH);
+    }
+    fp.first_tile[fp.nplanes] = total;
+    nlmeans_fast8_kernel<NH, TH, NW, DP4A><<<total, NW * 32, L::kTotal, st>>>(fp);
     hbcu::count_launch();
     return 0;
 }
@@ -811,14 +1052,28 @@ int launch_fast8(const TiledParams &kp, cudaStream_t st)
 // for patch 9 whose register footprint does not allow 384 threads.
 constexpr int kTH8 = 144;
 
-int launch_fast8_nh(const TiledParams &kp, cudaStream_t st)
+int g_ssd_variant = 1;     // 1: packed-byte VABSDIFF4 + IDP4A patch-row sums (measured 7 % faster), 0: fp32 prefix sums (FFMA);
+                           // HBCU_NLMEANS_SSD selects (test/tuning hook: both are exact, tests run both)
+
+int launch_fast8_nh(FusedParams &kp, cudaStream_t st)
 {
-    switch (kp.k.n_half)
+    if (g_ssd_variant == 1)
     {
-        case 1: return launch_fast8<1, kTH8, 12>(kp, st);
-        case 2: return launch_fast8<2, kTH8, 12>(kp, st);
-        case 3: return launch_fast8<3, kTH8, 12>(kp, st);
-        case 4: return launch_fast8<4, kTH8, 8>(kp, st);
+        switch (kp.k[0].n_half)
+        {
+            case 1: return launch_fast8<1, kTH8, 12, true>(kp, st);
+            case 2: return launch_fast8<2, kTH8, 12, true>(kp, st);
+            case 3: return launch_fast8<3, kTH8, 12, true>(kp, st);
+            case 4: return launch_fast8<4, kTH8, 8, true>(kp, st);
+            default: return 1;
+        }
+    }
+    switch (kp.k[0].n_half)
+    {
+        case 1: return launch_fast8<1, kTH8, 12, false>(kp, st);
+        case 2: return launch_fast8<2, kTH8, 12, false>(kp, st);
+        case 3: return launch_fast8<3, kTH8, 12, false>(kp, st);
+        case 4: return launch_fast8<4, kTH8, 8, false>(kp, st);
         default: return 1;
     }
 }
@@ -841,6 +1096,12 @@ bool tiled_supported(const KernelParams &kp)
     return kp.n_half >= 1 && kp.n_half <= 4 && kp.n_half + kp.r_half <= kHalo && kp.nf <= kMaxTiledFrames;
 }
 
+bool fast8_ok(const hbcu_nlmeans_s *h, const KernelParams &kp)
+{
+    // fp32-exact fast kernel: 8-bit planes, halo fits, the saturating table trick is valid (wfact < 0.99)
+    return h->bps == 1 && h->impl != 1 && h->impl != 3 && tiled_supported(kp) && kp.wfact < 0.99f && kp.wfact > 1e-5f;
+}
+
 int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, int plane)
 {
     const bool want_tiled = h->impl != 1 && tiled_supported(kp);
@@ -855,10 +1116,18 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
         tp.k = kp;
         for (int f = 0; f < kp.nf; f++) tp.maps[f] = h->maps[slots[f] * 3 + plane];
         // impl 0/2: fp32-exact fast kernel for 8-bit planes when the table trick is valid; impl 3: integer tiled kernel
-        const bool fast_ok = h->bps == 1 && kp.wfact < 0.99f && kp.wfact > 1e-5f;
-        int rc = (fast_ok && h->impl != 3) ? launch_fast8_nh(tp, h->s_compute)
-                 : h->bps == 1           ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute)
-                                         : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
+        const bool fast_ok = fast8_ok(h, kp);
+        int rc;
+        if (fast_ok && h->impl != 3)
+        {
+            FusedParams fp;
+            fp.nplanes = 1;
+            fp.k[0] = kp;
+            for (int f = 0; f < kp.nf; f++) fp.maps[0][f] = tp.maps[f];
+            rc = launch_fast8_nh(fp, h->s_compute);
+        }
+        else
+            rc = h->bps == 1 ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute) : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
         if (rc < 0) return rc;
         if (rc == 0)
         {
@@ -877,18 +1146,31 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
 int pad_plane(hbcu_nlmeans_s *h, int slot, int pl, const void *src, int spitch_elems, cudaStream_t st)
 {
     const PlaneGeom &g = h->g[pl];
-    dim3 blk(64, 4), grid((g.bw + 63) / 64, (g.bh + 3) / 4);
     uint8_t *dst = h->ring_mem[slot * 3 + pl];
-    if (h->bps == 1)
-        pad_mirror_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder);
+    const bool aligned = ((uintptr_t)src % 16 == 0) && (((size_t)spitch_elems * h->bps) % 16 == 0);
+    if (aligned)
+    {
+        const int chunks = (g.bw * h->bps + 15) / 16;
+        dim3 blk(64, 4), grid((chunks + 63) / 64, (g.bh + 3) / 4);
+        if (h->bps == 1)
+            pad_mirror_vec_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder);
+        else
+            pad_mirror_vec_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder);
+    }
     else
-        pad_mirror_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder);
+    {
+        dim3 blk(64, 4), grid((g.bw + 63) / 64, (g.bh + 3) / 4);
+        if (h->bps == 1)
+            pad_mirror_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder);
+        else
+            pad_mirror_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder);
+    }
     hbcu::count_launch();
     HBCU_CHECK(cudaGetLastError());
     return 0;
 }
 
-int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot)
+int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *const *ext_dst = nullptr, const int *ext_strides = nullptr)
 {
     if (navail < 1)
     {
@@ -917,46 +1199,87 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot)
 
     const int pair = h->pool_used < (int)h->ev_pool.size() / 2 ? h->pool_used : -1;
     if (pair >= 0) HBCU_CHECK(cudaEventRecord(h->ev_pool[2 * pair], h->s_compute));
+    KernelParams kps[3];
+    int slots[3][kMaxFrames];
+    bool active[3] = { false, false, false };
     for (int pl = 0; pl < 3; pl++)
     {
         const hbcu_nlmeans_plane_t &pp = h->cfg.plane[pl];
         const PlaneGeom &g = h->g[pl];
-        uint8_t *dst = h->out_mem[oslot * 3 + pl];
+        uint8_t *dst = ext_dst ? (uint8_t *)ext_dst[pl] : h->out_mem[oslot * 3 + pl];
+        const int dpitch = ext_dst ? ext_strides[pl] / h->bps : g.rpitch;
+        if (ext_dst && (((uintptr_t)dst % 8) || ((size_t)ext_strides[pl] % 8)))
+        {
+            set_error("nlmeans: external output plane %d must be 8-byte aligned (pointer and stride)", pl);
+            return -1;
+        }
         const int slot0 = (int)(index % h->ring);
         if (pp.bypass)
         {
             // nlmeans_deborder (template :45-67): plane passes through untouched
             dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
             const uint8_t *src = h->ring_mem[slot0 * 3 + pl] + ((size_t)kBorder * g.bpitch + kBorder) * h->bps;
-            if (h->bps == 1) copy_plane_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(src, g.bpitch, g.w, g.h, dst, g.rpitch);
-            else copy_plane_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.bpitch, g.w, g.h, (uint16_t *)dst, g.rpitch);
+            if (h->bps == 1) copy_plane_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(src, g.bpitch, g.w, g.h, dst, dpitch);
+            else copy_plane_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.bpitch, g.w, g.h, (uint16_t *)dst, dpitch);
             hbcu::count_launch();
             HBCU_CHECK(cudaGetLastError());
             continue;
         }
-        KernelParams kp;
+        KernelParams &kp = kps[pl];
         memset(&kp, 0, sizeof(kp));
-        int slots[kMaxFrames];
         kp.nf    = navail < pp.nframes ? navail : pp.nframes;
         for (int f = 0; f < kp.nf; f++)
         {
             const int slot = (int)((index + f) % h->ring);
-            slots[f]     = slot;
+            slots[pl][f] = slot;
             kp.planes[f] = h->ring_mem[slot * 3 + pl];
         }
         kp.w = g.w;
         kp.h = g.h;
         kp.bpitch = g.bpitch;
         kp.dst = dst;
-        kp.dpitch = g.rpitch;
+        kp.dpitch = dpitch;
         kp.n_half = (pp.patch_size - 1) / 2;
         kp.r_half = (pp.range - 1) / 2;
         kp.wfact = pp.weight_fact;
         kp.diff_max = pp.diff_max;
         kp.origin_tune = pp.origin_tune;
         kp.exptable = h->d_exptable + pl * HBCU_NLMEANS_EXPSIZE;
-        if (launch_plane(h, kp, slots, pl) != 0) return -1;
+        active[pl] = true;
+    }
+    // all active planes in one launch when they can share the fast 8-bit kernel instantiation
+    bool fused = h->impl == 0 || h->impl == 2;
+    int nact = 0, nh = -1;
+    for (int pl = 0; pl < 3 && fused; pl++)
+    {
+        if (!active[pl]) continue;
+        nact++;
+        if (!fast8_ok(h, kps[pl])) fused = false;
+        if (nh < 0) nh = kps[pl].n_half; else if (nh != kps[pl].n_half) fused = false;
+    }
+    if (fused && nact > 1)
+    {
+        FusedParams fp;
+        fp.nplanes = 0;
+        for (int pl = 0; pl < 3; pl++)
+        {
+            if (!active[pl]) continue;
+            fp.k[fp.nplanes] = kps[pl];
+            for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = h->maps[slots[pl][f] * 3 + pl];
+            fp.nplanes++;
+        }
+        if (launch_fast8_nh(fp, h->s_compute) != 0) { set_error("nlmeans: fused launch failed"); return -1; }
+        HBCU_CHECK(cudaGetLastError());
         h->kernel_launches++;
+    }
+    else
+    {
+        for (int pl = 0; pl < 3; pl++)
+        {
+            if (!active[pl]) continue;
+            if (launch_plane(h, kps[pl], slots[pl], pl) != 0) return -1;
+            h->kernel_launches++;
+        }
     }
     if (pair >= 0)
     {
@@ -1030,6 +1353,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->bps = cfg->depth > 8 ? 2 : 1;
     h->impl = 0;
     if (const char *e = getenv("HBCU_NLMEANS_IMPL")) h->impl = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;   // test hook
+    if (const char *e = getenv("HBCU_NLMEANS_SSD")) g_ssd_variant = atoi(e);                                  // tuning hook
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;
@@ -1056,9 +1380,14 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
             return -1;                                                                                    \
         }                                                                                                 \
     } while (0)
-    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    // The NLMeans kernel fills every SM (one CTA takes the whole register file); the small border kernels
+    // of the upload stream must not queue behind a whole frame of it, or the upload -> kernel chain stalls:
+    // give the upload stream the highest priority so its CTAs are placed as soon as any SM frees up.
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->s_h2d, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->s_compute, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&h->s_d2h, cudaStreamNonBlocking, prio_hi));
     h->ring_mem.assign(h->ring * 3, nullptr);
     h->raw_mem.assign(h->ring * 3, nullptr);
     h->out_mem.assign(h->out_slots * 3, nullptr);
@@ -1232,6 +1561,26 @@ int hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail, voi
         if (out_planes) out_planes[pl] = h->out_mem[oslot * 3 + pl];
         if (out_strides) out_strides[pl] = h->g[pl].rpitch * h->bps;
     }
+    return 0;
+}
+
+int hbcu_nlmeans_filter_into(hbcu_nlmeans_t *h, int64_t index, int navail, void *const dplanes[3], const int strides[3])
+{
+    if (h == nullptr || index < 0 || dplanes == nullptr || strides == nullptr) { set_error("nlmeans_filter_into: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = (int)(index % h->out_slots);
+    if (run_filter(h, index, navail, oslot, dplanes, strides) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_compute));
+    return 0;
+}
+
+int hbcu_nlmeans_stream_wait(hbcu_nlmeans_t *h, void *cuda_stream)
+{
+    // makes a caller-owned stream (e.g. the one NCCL runs on) wait for everything queued on the compute stream
+    if (h == nullptr) { set_error("nlmeans_stream_wait: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaEventRecord(h->ev_mark[1], h->s_compute));
+    HBCU_CHECK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->ev_mark[1], 0));
     return 0;
 }
 

@@ -135,3 +135,122 @@ int hb_bench_run(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, 
     free(b);
     return rc;
 }
+
+/* ------------------------------------------------------------------ */
+/* chains: the filters in libhb's order, each fed by the previous one    */
+/* ------------------------------------------------------------------ */
+typedef struct
+{
+    int n;
+    hb_filter_object_t **f;
+    int *done;
+    int failed;
+    hb_bench_stats_t *st;
+} bench_chain_t;
+
+static void chain_feed(bench_chain_t *c, int k, hb_buffer_t *list)
+{
+    if (k >= c->n)
+    {
+        consume(list, c->st);
+        return;
+    }
+    while (list != NULL)
+    {
+        hb_buffer_t *in = list;
+        list = in->next;
+        in->next = NULL;
+        if (c->done[k])
+        {
+            hb_buffer_close(&in);
+            continue;
+        }
+        hb_buffer_t *out = NULL;
+        const int status = c->f[k]->work(c->f[k], &in, &out);
+        if (in != NULL) hb_buffer_close(&in);
+        if (status == HB_FILTER_FAILED) c->failed = 1;
+        if (out != NULL) chain_feed(c, k + 1, out);
+        if (status == HB_FILTER_DONE) c->done[k] = 1;
+    }
+}
+
+int hb_bench_run_chain(int n_filters, hb_filter_object_t *const *protos, const char *const *settings,
+                       int pix_fmt, int w, int h, int frame_flags,
+                       const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st)
+{
+    memset(st, 0, sizeof(*st));
+    bench_chain_t c;
+    memset(&c, 0, sizeof(c));
+    c.f = calloc(n_filters, sizeof(*c.f));
+    c.done = calloc(n_filters, sizeof(int));
+    c.st = st;
+    int volatile done_flag = 0;
+    hb_filter_init_t init;
+    memset(&init, 0, sizeof(init));
+    init.pix_fmt = pix_fmt;
+    init.geometry.width = w;
+    init.geometry.height = h;
+    init.geometry.par.num = init.geometry.par.den = 1;
+    init.vrate.num = 30000;
+    init.vrate.den = 1001;
+    for (int k = 0; k < n_filters; k++)
+    {
+        hb_filter_object_t *f = malloc(sizeof(*f));
+        memcpy(f, protos[k], sizeof(*f));
+        f->settings = settings && settings[k] ? hb_parse_filter_settings(settings[k]) : NULL;
+        f->done = &done_flag;
+        if (f->sub_filter != NULL)
+        {
+            hb_filter_object_t *sub = malloc(sizeof(*sub));
+            memcpy(sub, f->sub_filter, sizeof(*sub));
+            sub->settings = settings && settings[k] ? hb_parse_filter_settings(settings[k]) : NULL;
+            f->sub_filter = sub;
+        }
+        if (f->init(f, &init) != 0)
+        {
+            free(f);
+            free(c.f);
+            free(c.done);
+            return -2;
+        }
+        c.f[c.n++] = f;
+    }
+    const size_t fb = hb_harness_frame_bytes(pix_fmt, w, h);
+    hb_buffer_t **in = calloc(n_frames, sizeof(*in));
+    for (int i = 0; i < n_frames; i++)
+    {
+        in[i] = hb_harness_frame_from_packed(pix_fmt, w, h, src + (size_t)(i % n_unique) * fb);
+        in[i]->s.start = (int64_t)i * 3003;
+        in[i]->s.stop = in[i]->s.start + 3003;
+        in[i]->s.duration = 3003;
+        in[i]->s.flags = (uint16_t)frame_flags;
+    }
+    hb_buffer_t *eof = hb_buffer_eof_init();
+    const double t0 = now_s();
+    for (int i = 0; i < n_frames && !c.failed; i++)
+    {
+        hb_buffer_t *b = in[i];
+        in[i] = NULL;
+        st->bytes_in += fb;
+        chain_feed(&c, 0, b);
+    }
+    if (!c.failed)
+    {
+        chain_feed(&c, 0, eof);
+        eof = NULL;
+    }
+    st->seconds = now_s() - t0;
+    for (int i = 0; i < n_frames; i++) if (in[i]) hb_buffer_close(&in[i]);
+    if (eof) hb_buffer_close(&eof);
+    free(in);
+    for (int k = 0; k < c.n; k++)
+    {
+        c.f[k]->close(c.f[k]);
+        if (c.f[k]->settings) hb_dict_free(&c.f[k]->settings);
+        if (c.f[k]->sub_filter) { if (c.f[k]->sub_filter->settings) hb_dict_free(&c.f[k]->sub_filter->settings); free(c.f[k]->sub_filter); }
+        free(c.f[k]);
+    }
+    free(c.f);
+    free(c.done);
+    return c.failed ? -1 : 0;
+}

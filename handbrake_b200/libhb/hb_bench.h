@@ -16,6 +16,10 @@ typedef struct
 } hb_bench_stats_t;
 hb_bench_t *hb_bench_open(hb_filter_object_t *proto, const char *settings, int pix_fmt, int w, int h);
 int hb_bench_run(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st);
+/* a chain of filters in libhb's order (init, stream, EOF, close); frame_flags = s.flags of every input frame */
+int hb_bench_run_chain(int n_filters, hb_filter_object_t *const *protos, const char *const *settings,
+                       int pix_fmt, int w, int h, int frame_flags,
+                       const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st);
 #ifdef __cplusplus
 }
 #endif

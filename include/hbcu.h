@@ -111,6 +111,12 @@ int  hbcu_nlmeans_upload_device(hbcu_nlmeans_t *h, int64_t index,
                                 const void *const dplanes[3], const int strides[3]);
 int  hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail,
                                 void *out_planes[3], int out_strides[3]);
+/* like filter_device, but the result is written straight into caller-owned DEVICE planes (the next
+ * filter's input, or a buffer an NCCL send reads): the device-resident hand-off between filters */
+int  hbcu_nlmeans_filter_into(hbcu_nlmeans_t *h, int64_t index, int navail,
+                              void *const dplanes[3], const int strides[3]);
+/* orders a caller-owned CUDA stream (passed as void*) after all work queued on the handle so far */
+int  hbcu_nlmeans_stream_wait(hbcu_nlmeans_t *h, void *cuda_stream);
 int  hbcu_nlmeans_sync(hbcu_nlmeans_t *h);
 /* implementation selector for tests: 0 = auto (tiled sm_100a kernel when the
  * parameters fit, generic otherwise), 1 = force generic, 2 = force tiled,

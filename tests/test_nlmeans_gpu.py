@@ -116,3 +116,15 @@ def test_golden_digests(cuda_filters):
         clip = synth.progressive_clip(fmt, c["width"], c["height"], c["frames"], seed=c["seed"])
         g = cuda_filters.run("hb_filter_nlmeans_cuda", c["settings"], clip, fmt, c["width"], c["height"])
         assert [hashlib.sha256(f.tobytes()).hexdigest() for f in g.frames] == c["sha256"], name
+
+
+@pytest.mark.parametrize("ssd", ["0", "1"])
+def test_both_ssd_formulations(ref, cuda_filters, monkeypatch, ssd):
+    """fp32-prefix-sum (0) and VABSDIFF4+IDP4A (1) patch-row sums, patch sizes 3/5/7/9 over the three planes"""
+    monkeypatch.setenv("HBCU_NLMEANS_SSD", ssd)
+    w, h = 300, 170
+    clip = synth.progressive_clip(FMT8, w, h, 4, seed=23)
+    for s in ("y-strength=6:y-patch-size=7:cb-strength=5:cb-patch-size=5:cb-range=5:cr-patch-size=3",
+              "y-strength=8:y-patch-size=9:y-range=5:y-frame-count=3"):
+        r, g = run_both(ref, cuda_filters, s, clip, FMT8, w, h)
+        assert_same(r, g)
