@@ -143,6 +143,28 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """one process per GPU: keep the process (and the pinned frame buffers it is about to allocate) on the
+    NUMA node the GPU's PCIe link hangs off; best effort, silently skipped when sysfs does not say"""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        cpus = Path(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def nlm_config(flt, wl, device, ring, out_slots):
     """device configuration from the settings string, built by the filter's own init code
     (hb_nlmeans_cuda_build_config in nlmeans_cuda.c: the numeric contract of nlmeans.c:343-358)"""
@@ -166,6 +188,7 @@ def run_ours(args, wl, rank, world, local_rank):
     handbrake_b200.require_native()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     os.environ["HBCU_DEVICE"] = str(local_rank)
     if world > 1:
@@ -327,6 +350,13 @@ def run_ours(args, wl, rank, world, local_rank):
     kern_ms_per_frame = kms.value / max(kcalls.value, 1)
     achieved = alg_bytes_per_frame / (kern_ms_per_frame / 1e3) / 1e9 if kcalls.value else None
 
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    # (not measured live: a run under ncu is never a bench value)
+    traffic, traffic_src = None, None
+    cap = REPO / "profiles" / "r01g_nlmeans_fused_ncu.json"
+    if args.workload == "4k_nlmeans_strong" and cap.exists():
+        traffic = int(json.loads(cap.read_text())["dram_bytes_total"])
+        traffic_src = "profiles/r01g_nlmeans_fused_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch = one frame)"
     out = {
         "metric": "4K NLMeans frames/sec" if W == 3840 else "NLMeans frames/sec",
         "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -334,14 +364,16 @@ def run_ours(args, wl, rank, world, local_rank):
         "dtype": "u8" if depth == 8 else "u16", "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"], "frames_per_step_per_gpu": B,
                    "sharding": f"frame blocks x{world}, {NFRAMES - 1}-frame temporal halo per block, no data-path collective",
+                   "cpu_affinity": numa_cpus,
                    "l2": f"step inputs {input_mb:.0f} MB in distinct buffers > 126 MB L2" if input_mb > 126 else f"step inputs {input_mb:.0f} MB (fits L2)"},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(world * st.bytes_in // K),
                 "d2h_bytes_per_step": int(world * st.bytes_out // K), "seconds": round(e2e_s, 4), "checksum": int(st.checksum)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
-                     "kernel": "nlmeans_fast8_kernel (all tiles of Y, U, V of one frame in one launch)",
+                     "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+                     "traffic_source": traffic_src,
+                     "kernel": ("nlmeans_fast8_kernel" if depth == 8 else "nlmeans_fast16_kernel") + " (all tiles of Y, U, V of one frame in one launch)",
                      "kernel_ms_per_frame": round(kern_ms_per_frame, 4), "algorithmic_bytes_per_frame": alg_bytes_per_frame,
                      "peak_source": peak_src,
                      "note": "NLMeans is instruction-issue bound on B200, not HBM bound (DESIGN.md): frac is the honest HBM fraction, not the kernel's quality"},

@@ -155,6 +155,125 @@ __device__ __forceinline__ int yadif_px(const FieldParams &fp, int x, int y)
     return spatial_pred;
 }
 
+// 4 / 12 consecutive samples starting at a 4-sample-aligned position, as one or three vector loads
+template <typename PIX> __device__ __forceinline__ void load4(const PIX *__restrict__ p, int *v);
+template <> __device__ __forceinline__ void load4<uint8_t>(const uint8_t *__restrict__ p, int *v)
+{
+    const uchar4 t = *reinterpret_cast<const uchar4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void load4<uint16_t>(const uint16_t *__restrict__ p, int *v)
+{
+    const ushort4 t = *reinterpret_cast<const ushort4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <typename PIX> __device__ __forceinline__ void load12(const PIX *__restrict__ p, int *v)
+{
+    load4<PIX>(p, v); load4<PIX>(p + 4, v + 4); load4<PIX>(p + 8, v + 8);
+}
+
+// yadif for the 4 pixels x0..x0+3 of row y, everything read once into registers (same arithmetic as
+// yadif_px, which stays the reference formulation and handles the groups next to the left/right edge).
+// Requires 4 <= x0 and x0 + 8 <= w.
+template <typename PIX>
+__device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, int *out)
+{
+    const PIX *prev = (const PIX *)fp.prev, *cur = (const PIX *)fp.cur, *next = (const PIX *)fp.next;
+    const int pitch = fp.pitch, w = fp.w, h = fp.h, maxv = fp.maxv;
+    const int par = fp.parity ^ fp.tff;
+    const PIX *prev2 = par ? prev : cur, *next2 = par ? cur : next;
+    const int yp = y ? y - 1 : y + 1, yn = y + 1 < h ? y + 1 : y - 1;
+    const bool vertical_edge = (y < 3) || (y > h - 4);
+    const bool cubic = (fp.mode & HBCU_DECOMB_CUBIC) != 0;
+    const int margin = cubic ? 3 : 2;
+    const int o = y * pitch + x0, op = yp * pitch + x0, on = yn * pitch + x0;
+
+    int P[12], N[12], A[12], D[12];                   // cur rows yp, yn, y-3, y+3 over x0-4 .. x0+7
+    load12<PIX>(cur + op - 4, P);
+    load12<PIX>(cur + on - 4, N);
+    const bool use_cubic = cubic && !vertical_edge && fp.eedi == nullptr;
+    if (use_cubic)
+    {
+        load12<PIX>(cur + o - 3 * pitch - 4, A);
+        load12<PIX>(cur + o + 3 * pitch - 4, D);
+    }
+    int p2[4], n2[4], pp[4], pn[4], np_[4], nn[4], b2p[4], b2n[4], f2p[4], f2n[4], ee[4];
+    load4<PIX>(prev2 + o, p2);
+    load4<PIX>(next2 + o, n2);
+    load4<PIX>(prev + op, pp);
+    load4<PIX>(prev + on, pn);
+    load4<PIX>(next + op, np_);
+    load4<PIX>(next + on, nn);
+    if (!vertical_edge)
+    {
+        load4<PIX>(prev2 + o - 2 * pitch, b2p);
+        load4<PIX>(next2 + o - 2 * pitch, b2n);
+        load4<PIX>(prev2 + o + 2 * pitch, f2p);
+        load4<PIX>(next2 + o + 2 * pitch, f2n);
+    }
+    if (fp.eedi != nullptr) load4<PIX>((const PIX *)fp.eedi + y * fp.epitch + x0, ee);
+
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int x = x0 + i, li = 4 + i;
+        const int c = P[li], e = N[li];
+        const int d = (p2[i] + n2[i]) >> 1;
+        const int td0 = abs(p2[i] - n2[i]);
+        const int td1 = (abs(pp[i] - c) + abs(pn[i] - e)) >> 1;
+        const int td2 = (abs(np_[i] - c) + abs(nn[i] - e)) >> 1;
+        int diff = max(max(td0 >> 1, td1), td2);
+        int spatial_pred;
+        if (fp.eedi != nullptr)
+        {
+            spatial_pred = ee[i];
+        }
+        else
+        {
+            if (use_cubic) spatial_pred = cubic_px(maxv, A[li], P[li], N[li], D[li]);
+            else           spatial_pred = (c + e) >> 1;
+            if (x > margin && x < w - (margin + 1))
+            {
+                int score = abs(P[li - 1] - N[li - 1]) + abs(c - e) + abs(P[li + 1] - N[li + 1]) - 1;
+#pragma unroll
+                for (int dir = -1; dir <= 1; dir += 2)
+                {
+                    bool go = true;
+#pragma unroll
+                    for (int step = 1; step <= 2; step++)
+                    {
+                        const int j = dir * step;
+                        const int sc = abs(P[li - 1 + j] - N[li - 1 - j]) + abs(P[li + j] - N[li - j]) + abs(P[li + 1 + j] - N[li + 1 - j]);
+                        go = go && (sc < score);
+                        if (go)
+                        {
+                            score = sc;
+                            if (use_cubic)
+                            {
+                                if (step == 1) spatial_pred = cubic_px(maxv, A[li + 3 * j], P[li + j], N[li - j], D[li - 3 * j]);
+                                else           spatial_pred = cubic_px(maxv, (A[li + 2 * j] + P[li + 2 * j]) / 2, P[li + j], N[li - j],
+                                                                       (D[li - 2 * j] + N[li - 2 * j]) / 2);
+                            }
+                            else
+                                spatial_pred = (P[li + j] + N[li - j]) >> 1;
+                        }
+                    }
+                }
+            }
+        }
+        if (!vertical_edge)
+        {
+            const int b = (b2p[i] + b2n[i]) >> 1, f = (f2p[i] + f2n[i]) >> 1;
+            const int mx = max(max(d - e, d - c), min(b - c, f - e));
+            const int mn = min(min(d - e, d - c), max(b - c, f - e));
+            diff = max(max(diff, mn), -mx);
+        }
+        if (spatial_pred > d + diff) spatial_pred = d + diff;
+        else if (spatial_pred < d - diff) spatial_pred = d - diff;
+        out[i] = spatial_pred;
+    }
+}
+
 // one thread = 4 adjacent pixels of one output row
 template <typename PIX>
 __global__ void __launch_bounds__(256) decomb_field_kernel(FieldParams fp)
@@ -166,6 +285,21 @@ __global__ void __launch_bounds__(256) decomb_field_kernel(FieldParams fp)
     PIX *dst = (PIX *)fp.dst + (size_t)y * fp.dpitch;
     const bool filtered = fp.parity ? !(y & 1) : (y & 1);     // template :744, :796
     int v[4];
+    if (filtered && fp.mode != HBCU_DECOMB_BLEND && fp.mode != HBCU_DECOMB_CUBIC && (fp.mode & HBCU_DECOMB_YADIF) &&
+        x0 >= 4 && x0 + 8 <= fp.w)
+    {
+        yadif_px4<PIX>(fp, x0, y, v);
+        if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(dst + x0) = make_uchar4(v[0], v[1], v[2], v[3]);
+        else                  *reinterpret_cast<ushort4 *>(dst + x0) = make_ushort4(v[0], v[1], v[2], v[3]);
+        return;
+    }
+    if (!filtered && x0 + 3 < fp.w)
+    {
+        // kept rows are straight copies: one vector load, one vector store
+        if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(dst + x0) = *reinterpret_cast<const uchar4 *>(cur + (size_t)y * fp.pitch + x0);
+        else                  *reinterpret_cast<ushort4 *>(dst + x0) = *reinterpret_cast<const ushort4 *>(cur + (size_t)y * fp.pitch + x0);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {

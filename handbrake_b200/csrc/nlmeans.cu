@@ -50,6 +50,10 @@ constexpr int kGroup     = 3;     // horizontal displacements handled per pass
 
 constexpr int kMaxTiledFrames = 8; // temporal depth the tiled kernel takes (tensor maps travel as kernel parameters)
 
+// largest sample value the fp32-exact 16-bit kernel accepts (10-bit video), and the bits above it in a packed pair
+constexpr unsigned kFast16Max      = 1023u;
+constexpr unsigned kFast16HighBits = 0xFC00FC00u;
+
 struct KernelParams
 {
     const void *planes[kMaxFrames];   // bordered plane base pointers, frame f = current + f
@@ -72,7 +76,7 @@ struct KernelParams
 // ---------------------------------------------------------------------------
 template <typename PIX>
 __global__ void pad_mirror_kernel(const PIX *__restrict__ src, int spitch, int w, int h,
-                                  PIX *__restrict__ dst, int bpitch, int border)
+                                  PIX *__restrict__ dst, int bpitch, int border, unsigned *range_flag)
 {
     const int bx = blockIdx.x * blockDim.x + threadIdx.x;
     const int by = blockIdx.y * blockDim.y + threadIdx.y;
@@ -83,13 +87,15 @@ __global__ void pad_mirror_kernel(const PIX *__restrict__ src, int spitch, int w
     if (y < 0) y = -1 - y; else if (y >= h) y = 2 * h - 1 - y;
     x = min(max(x, 0), w - 1);   // only reachable when w < border; the reference reads out of bounds there
     y = min(max(y, 0), h - 1);
-    dst[(size_t)by * bpitch + bx] = src[(size_t)y * spitch + x];
+    const PIX v = src[(size_t)y * spitch + x];
+    dst[(size_t)by * bpitch + bx] = v;
+    if (sizeof(PIX) == 2 && range_flag != nullptr && (unsigned)v > kFast16Max) atomicOr(range_flag, 1u);
 }
 
 // 16 bytes per thread: interior chunks are straight uint4 copies, the chunks that touch the mirror border go element by element
 template <typename PIX>
 __global__ void __launch_bounds__(256) pad_mirror_vec_kernel(const PIX *__restrict__ src, int spitch, int w, int h,
-                                                            PIX *__restrict__ dst, int bpitch, int border)
+                                                            PIX *__restrict__ dst, int bpitch, int border, unsigned *range_flag)
 {
     constexpr int EPC = 16 / (int)sizeof(PIX);
     const int cx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,9 +110,13 @@ __global__ void __launch_bounds__(256) pad_mirror_vec_kernel(const PIX *__restri
     const PIX *srow = src + (size_t)y * spitch;
     if (bx0 >= border && bx0 + EPC <= border + w)
     {
-        *reinterpret_cast<uint4 *>(drow + bx0) = *reinterpret_cast<const uint4 *>(srow + (bx0 - border));
+        const uint4 v = *reinterpret_cast<const uint4 *>(srow + (bx0 - border));
+        *reinterpret_cast<uint4 *>(drow + bx0) = v;
+        // samples above kFast16Max in a 16-bit plane: tell the fast 10-bit kernel to stand down (see nlmeans_fast16_kernel)
+        if (sizeof(PIX) == 2 && range_flag != nullptr && ((v.x | v.y | v.z | v.w) & kFast16HighBits) != 0u) atomicOr(range_flag, 1u);
         return;
     }
+    bool bad = false;
 #pragma unroll
     for (int i = 0; i < EPC; i++)
     {
@@ -115,8 +125,11 @@ __global__ void __launch_bounds__(256) pad_mirror_vec_kernel(const PIX *__restri
         int x = bx - border;
         if (x < 0) x = -1 - x; else if (x >= w) x = 2 * w - 1 - x;
         x = min(max(x, 0), w - 1);
-        drow[bx] = srow[x];
+        const PIX v = srow[x];
+        drow[bx] = v;
+        bad |= sizeof(PIX) == 2 && (unsigned)v > kFast16Max;
     }
+    if (bad && range_flag != nullptr) atomicOr(range_flag, 1u);
 }
 
 template <typename PIX>
@@ -364,6 +377,7 @@ struct TiledParams
 {
     KernelParams k;
     CUtensorMap  maps[kMaxTiledFrames];   // one TMA descriptor per frame of the temporal window
+    const unsigned *only_if_flag;         // when set: run only if *only_if_flag != 0 (stand-in for the fast 16-bit kernel)
 };
 
 // The fast 8-bit kernel takes up to three planes in ONE launch (tiles of Y, U and V in one grid):
@@ -376,12 +390,14 @@ struct FusedParams
     int tiles_x[3];
     KernelParams k[3];
     CUtensorMap  maps[3][kMaxTiledFrames];
+    const unsigned *range_flag;           // 16-bit fast kernel: non-zero = some sample exceeded kFast16Max, do nothing
 };
 
 template <typename PIX, int NH, int TH>
 __global__ void __launch_bounds__(kThreads, 1) nlmeans_tiled_kernel(const __grid_constant__ TiledParams tp)
 {
     const KernelParams &p = tp.k;
+    if (tp.only_if_flag != nullptr && *tp.only_if_flag == 0u) return;
     using L = TileLayout<PIX, TH>;
     extern __shared__ __align__(128) uint8_t smem[];
     PIX *cur      = reinterpret_cast<PIX *>(smem + L::kOffCur);
@@ -966,6 +982,311 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast8_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------
+// Fast kernel for 9/10-bit planes (16-bit containers), patch <= 7.  Same tiling, same results.
+// With samples <= 1023 a squared difference is < 2^20, the prefix sum over the <= 10 values a lane touches
+// per row < 2^24 and one patch-row sum (7 * 1023^2) < 2^23, so the row sums are exact in fp32 (FSUB + FFMA per
+// pixel pair like the 8-bit fp32 variant).  The n x n sum (up to 5.1e7) is not, so the vertical running sum is an
+// integer: hsum + 2^23 carries hsum in its mantissa bits and V += bits(new) - bits(old) is one IADD3 with no
+// unbiasing.  Samples travel as LDS.64 (4 samples; a warp reads 256 contiguous bytes, conflict free) and are
+// unpacked by PRMT into the float 2^23 + v.
+// A 16-bit container can hold samples above 1023.  The border kernel raises a sticky flag when it sees one; this
+// kernel then returns at once and the integer kernel launched right behind it (which returns at once when the
+// flag is clear) does the frame: same output either way, no host round trip.
+// ---------------------------------------------------------------------------
+template <int TH>
+struct Fast16Layout
+{
+    static constexpr int kRows      = TH + 2 * kHalo;
+    static constexpr int kTileBytes = kRows * kTilePW * 2;
+    static constexpr int kAccBytes  = TH * kTileW * (int)sizeof(float);
+    static constexpr int kLutBytes  = kLutEntries * 32 * (int)sizeof(float);
+    static constexpr int kOffCur    = 0;
+    static constexpr int kOffCmp    = kOffCur + kTileBytes;
+    static constexpr int kOffWs     = kOffCmp + kTileBytes;
+    static constexpr int kOffPs     = kOffWs + kAccBytes;
+    static constexpr int kOffLut    = kOffPs + kAccBytes;
+    static constexpr int kOffBar    = kOffLut + kLutBytes;
+    static constexpr int kTotal     = kOffBar + 64;
+    static_assert(kTileBytes % 128 == 0, "TMA destination must stay 128-byte aligned");
+};
+
+// half k (0/1) of word w as the float 2^23 + value
+__device__ __forceinline__ float half_as_biased_float(uint32_t w, int k)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, k ? 0x7432 : 0x7410));
+}
+
+template <int NH, int TH, int NW, bool ORIGIN>
+__device__ __forceinline__ void nlm_group_fast16(const uint2 *__restrict__ cur, const uint2 *__restrict__ cmp,
+                                                 float *__restrict__ acc_ws, float *__restrict__ acc_ps,
+                                                 uint32_t lut_lane_addr, float wscale, double origin_tune,
+                                                 int seg_y0, int lane, int dy, int dx0, int ng, int origin_g)
+{
+    constexpr int N   = 2 * NH + 1;
+    constexpr int RS  = TH / NW;
+    constexpr int NA  = 4 + 2 * NH;                 // source samples per row
+    constexpr int NB  = NA + kGroup - 1;            // compare samples per row
+    constexpr int PQ  = kTilePW / 4;                // tile pitch in 4-sample quads (uint2)
+    constexpr int OA  = (kHaloX - NH) & 3;          // sample offset of a[0] in its first quad
+    constexpr int QA0 = (kHaloX - NH) >> 2;         // first quad of the a window (relative to the lane's quad)
+    constexpr int NQA = (OA + NA + 3) / 4;
+    constexpr int NQB = (3 + NB + 3) / 4;           // quads loaded for the compare window (covers any alignment)
+    constexpr int NWB = (NB + 1) / 2;               // aligned compare words (two samples each)
+    constexpr float kBias = 8388608.0f;             // 2^23
+    constexpr int kBiasBits = 0x4B000000;
+    static_assert(NH <= 3, "patch-row sums must stay below 2^23");
+    static_assert(NWB + 2 <= 2 * NQB, "compare window must fit the loaded quads");
+
+    const int fb   = kHaloX - NH + dx0;             // first compare column relative to the lane's x
+    const int qb0  = fb >> 2;
+    const bool odd_word = (fb & 2) != 0;            // the aligned stream starts in the second word of the first quad
+    const int sh   = (fb & 1) * 16;                 // and, for odd fb, half a word further
+
+    int V[kGroup][4];
+    int hist[N][kGroup][4];
+#pragma unroll
+    for (int g = 0; g < kGroup; g++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            V[g][i] = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) hist[k][g][i] = kBiasBits;
+        }
+    uint32_t delay[NH][NWB];
+#pragma unroll
+    for (int r = 0; r < NH; r++)
+#pragma unroll
+        for (int j = 0; j < NWB; j++) delay[r][j] = 0;
+
+#pragma unroll 1
+    for (int base = -NH; base < RS + NH; base += N)
+    {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+        {
+            const int yy = base + k;
+            if (yy < RS + NH)
+            {
+                const int ty = seg_y0 + yy + kHalo;
+                const uint2 *aq = cur + ty * PQ + lane + QA0;
+                const uint2 *bq = cmp + (ty + dy) * PQ + lane + qb0;
+                uint32_t wa[2 * NQA], wraw[2 * NQB], wbv[NWB];
+#pragma unroll
+                for (int j = 0; j < NQA; j++)
+                {
+                    const uint2 q = aq[j];
+                    wa[2 * j] = q.x;
+                    wa[2 * j + 1] = q.y;
+                }
+#pragma unroll
+                for (int j = 0; j < NQB; j++)
+                {
+                    const uint2 q = bq[j];
+                    wraw[2 * j] = q.x;
+                    wraw[2 * j + 1] = q.y;
+                }
+                uint32_t wsel[NWB + 1];
+#pragma unroll
+                for (int j = 0; j < NWB + 1; j++) wsel[j] = odd_word ? wraw[j + 1] : wraw[j];
+#pragma unroll
+                for (int j = 0; j < NWB; j++) wbv[j] = __funnelshift_r(wsel[j], wsel[j + 1], sh);
+
+                float a[NA], b[NB];
+#pragma unroll
+                for (int j = 0; j < NA; j++) a[j] = half_as_biased_float(wa[(OA + j) >> 1], (OA + j) & 1);
+#pragma unroll
+                for (int j = 0; j < NB; j++) b[j] = half_as_biased_float(wbv[j >> 1], j & 1);
+
+#pragma unroll
+                for (int g = 0; g < kGroup; g++)
+                {
+                    if (g < ng && (!ORIGIN || g != origin_g))
+                    {
+                        float c[NA + 1];
+                        c[0] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NA; j++)
+                        {
+                            const float d = __fsub_rn(a[j], b[j + g]);        // exact
+                            c[j + 1] = __fmaf_rn(d, d, c[j]);                  // exact: integers < 2^24
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                        {
+                            const float hsum = __fsub_rn(c[i + N], c[i]);      // < 2^23
+                            const int hb = __float_as_int(__fadd_rn(hsum, kBias));
+                            V[g][i] = V[g][i] + hb - hist[k][g][i];
+                            hist[k][g][i] = hb;
+                        }
+                    }
+                }
+                if (yy >= NH)
+                {
+                    const int oy = seg_y0 + yy - NH;
+                    float4 ws4 = *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + lane * 4);
+                    float4 ps4 = *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + lane * 4);
+                    float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+                    float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+                    // cmp[oy+dy][x+dx0+g+i] = sample NH+g+i of the compare window loaded NH rows ago
+                    float pixv[kGroup + 3];
+#pragma unroll
+                    for (int j = 0; j < kGroup + 3; j++)
+                        pixv[j] = __fsub_rn(half_as_biased_float(delay[0][(NH + j) >> 1], (NH + j) & 1), kBias);
+#pragma unroll
+                    for (int g = 0; g < kGroup; g++)
+                    {
+                        if (g < ng)
+                        {
+                            if (ORIGIN && g == origin_g)
+                            {
+                                const uint2 cq = cur[(oy + kHalo) * PQ + lane + kHaloX / 4];
+                                add_origin(ws[0], ps[0], origin_tune, (int)(cq.x & 0xffffu));
+                                add_origin(ws[1], ps[1], origin_tune, (int)(cq.x >> 16));
+                                add_origin(ws[2], ps[2], origin_tune, (int)(cq.y & 0xffffu));
+                                add_origin(ws[3], ps[3], origin_tune, (int)(cq.y >> 16));
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                {
+                                    float t, u, wgt;
+                                    asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(t) : "f"(__int2float_rn(V[g][i])), "f"(wscale));
+                                    asm("add.rz.f32 %0, %1, 0f47800000;" : "=f"(u) : "f"(t));   // 65536 + floor(128 t)
+                                    const uint32_t addr = (__float_as_uint(u) << 7) + lut_lane_addr;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(wgt) : "r"(addr));
+                                    ws[i] = __fadd_rn(ws[i], wgt);
+                                    ps[i] = __fadd_rn(ps[i], __fmul_rn(wgt, pixv[g + i]));
+                                }
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(acc_ws + oy * kTileW + lane * 4) = make_float4(ws[0], ws[1], ws[2], ws[3]);
+                    *reinterpret_cast<float4 *>(acc_ps + oy * kTileW + lane * 4) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+                }
+#pragma unroll
+                for (int r = 0; r + 1 < NH; r++)
+#pragma unroll
+                    for (int j = 0; j < NWB; j++) delay[r][j] = delay[r + 1][j];
+#pragma unroll
+                for (int j = 0; j < NWB; j++) delay[NH - 1][j] = wbv[j];
+            }
+        }
+    }
+}
+
+template <int NH, int TH, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) nlmeans_fast16_kernel(const __grid_constant__ FusedParams fp)
+{
+    if (*fp.range_flag != 0u) return;               // out-of-range samples seen: the integer kernel takes over
+    constexpr int kThreads = NW * 32;
+    int pl = 0;
+    while (pl + 1 < fp.nplanes && (int)blockIdx.x >= fp.first_tile[pl + 1]) pl++;
+    const KernelParams &p = fp.k[pl];
+    const CUtensorMap *maps = fp.maps[pl];
+    const int tile = (int)blockIdx.x - fp.first_tile[pl];
+    using L = Fast16Layout<TH>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint16_t *cur = reinterpret_cast<uint16_t *>(smem + L::kOffCur);
+    uint16_t *cmp = reinterpret_cast<uint16_t *>(smem + L::kOffCmp);
+    float *acc_ws = reinterpret_cast<float *>(smem + L::kOffWs);
+    float *acc_ps = reinterpret_cast<float *>(smem + L::kOffPs);
+    float *lut    = reinterpret_cast<float *>(smem + L::kOffLut);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = (tile % fp.tiles_x[pl]) * kTileW, Y0 = (tile / fp.tiles_x[pl]) * TH;
+    const int gx = X0 + kBorder - kHaloX, gy = Y0 + kBorder - kHalo;
+
+    if (tid == 0)
+    {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    if (tid == 0)
+    {
+        mbar_expect_tx(bar, L::kTileBytes);
+        tma_load_2d(cur, &maps[0], gx, gy, bar);
+    }
+    for (int i = tid; i < kLutEntries * 32; i += kThreads)
+    {
+        const int e = i >> 5;
+        lut[i] = e < HBCU_NLMEANS_EXPSIZE ? p.exptable[e] : 0.f;
+    }
+    for (int i = tid; i < TH * kTileW; i += kThreads)
+    {
+        acc_ws[i] = 0.f;
+        acc_ps[i] = 0.f;
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    __syncthreads();
+
+    const int seg_y0 = warp * (TH / NW);
+    const float wscale = p.wfact * 0.0078125f;                         // wfact / 128, exact
+    const uint32_t lut_lane_addr = smem_u32(lut) + (uint32_t)lane * 4u - (0x47800000u << 7);
+    for (int f = 0; f < p.nf; f++)
+    {
+        const uint16_t *B = cur;
+        if (f > 0)
+        {
+            __syncthreads();
+            if (tid == 0)
+            {
+                fence_proxy_async();
+                mbar_expect_tx(bar, L::kTileBytes);
+                tma_load_2d(cmp, &maps[f], gx, gy, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            B = cmp;
+        }
+        const uint2 *cq = reinterpret_cast<const uint2 *>(cur), *bq = reinterpret_cast<const uint2 *>(B);
+        for (int dy = -p.r_half; dy <= p.r_half; dy++)
+        {
+            for (int dx0 = -p.r_half; dx0 <= p.r_half; dx0 += kGroup)
+            {
+                const int ng = min(kGroup, p.r_half - dx0 + 1);
+                const int origin_g = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : -1;
+                if (origin_g >= 0)
+                    nlm_group_fast16<NH, TH, NW, true>(cq, bq, acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, origin_g);
+                else
+                    nlm_group_fast16<NH, TH, NW, false>(cq, bq, acc_ws, acc_ps, lut_lane_addr, wscale, p.origin_tune, seg_y0, lane, dy, dx0, ng, -1);
+            }
+        }
+    }
+
+    const int x = lane * 4;
+    uint16_t *dst = reinterpret_cast<uint16_t *>(p.dst);
+    for (int r = 0; r < TH / NW; r++)
+    {
+        const int oy = seg_y0 + r;
+        const int y = Y0 + oy;
+        if (y >= p.h) break;
+        const float4 ws4 = *reinterpret_cast<const float4 *>(acc_ws + oy * kTileW + x);
+        const float4 ps4 = *reinterpret_cast<const float4 *>(acc_ps + oy * kTileW + x);
+        const float ws[4] = { ws4.x, ws4.y, ws4.z, ws4.w };
+        const float ps[4] = { ps4.x, ps4.y, ps4.z, ps4.w };
+        uint16_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            o[i] = finish_pixel<uint16_t>(ws[i], ps[i], cur[(oy + kHalo) * kTilePW + x + kHaloX + i]);
+        uint16_t *drow = dst + (size_t)y * p.dpitch + X0 + x;
+        if (X0 + x + 3 < p.w)
+            *reinterpret_cast<ushort4 *>(drow) = make_ushort4(o[0], o[1], o[2], o[3]);
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (X0 + x + i < p.w) drow[i] = o[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct PlaneGeom
@@ -993,7 +1314,9 @@ struct hbcu_nlmeans_s
     std::vector<int64_t>   ring_index;    // frame index held by each slot
     std::vector<CUtensorMap> maps;        // [slot*3+plane] TMA descriptors of the bordered planes
     float *d_exptable;                    // 3 x 128
-    cudaStream_t s_h2d, s_compute, s_d2h;
+    unsigned *d_range_flag;               // sticky: a 16-bit plane held a sample above kFast16Max (see nlmeans_fast16_kernel)
+    cudaStream_t s_h2d, s_pad, s_compute, s_d2h;
+    std::vector<cudaEvent_t> ev_h2d;      // per ring slot: raw planes have arrived (H2D done), border kernels may start
     std::vector<cudaEvent_t> ev_upload;   // per ring slot: bordered planes ready
     std::vector<cudaEvent_t> ev_readers;  // per ring slot: last kernel reading it is done
     std::vector<cudaEvent_t> ev_kernel;   // per out slot
@@ -1045,6 +1368,43 @@ int launch_fast8(FusedParams &fp, cudaStream_t st)
     nlmeans_fast8_kernel<NH, TH, NW, DP4A><<<total, NW * 32, L::kTotal, st>>>(fp);
     hbcu::count_launch();
     return 0;
+}
+
+template <int NH, int TH, int NW>
+int launch_fast16(FusedParams &fp, cudaStream_t st)
+{
+    using L = Fast16Layout<TH>;
+    static bool configured = false;
+    if (!configured)
+    {
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast16_kernel<NH, TH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    int total = 0;
+    for (int i = 0; i < fp.nplanes; i++)
+    {
+        fp.first_tile[i] = total;
+        fp.tiles_x[i] = (fp.k[i].w + kTileW - 1) / kTileW;
+        total += fp.tiles_x[i] * ((fp.k[i].h + TH - 1) / TH);
+    }
+    fp.first_tile[fp.nplanes] = total;
+    nlmeans_fast16_kernel<NH, TH, NW><<<total, NW * 32, L::kTotal, st>>>(fp);
+    hbcu::count_launch();
+    return 0;
+}
+
+// 16-bit tiles are 128 x 96 for every kernel (they share the tensor maps): 8 warps x 12 rows
+constexpr int kTH16 = 96;
+
+int launch_fast16_nh(FusedParams &kp, cudaStream_t st)
+{
+    switch (kp.k[0].n_half)
+    {
+        case 1: return launch_fast16<1, kTH16, 8>(kp, st);
+        case 2: return launch_fast16<2, kTH16, 8>(kp, st);
+        case 3: return launch_fast16<3, kTH16, 8>(kp, st);
+        default: return 1;
+    }
 }
 
 // 8-bit tiles are 128 x 144: 12 warps x 12 rows for patch <= 7 (measured 7 % faster than 8 warps x 16 rows:
@@ -1102,7 +1462,14 @@ bool fast8_ok(const hbcu_nlmeans_s *h, const KernelParams &kp)
     return h->bps == 1 && h->impl != 1 && h->impl != 3 && tiled_supported(kp) && kp.wfact < 0.99f && kp.wfact > 1e-5f;
 }
 
-int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, int plane)
+bool fast16_ok(const hbcu_nlmeans_s *h, const KernelParams &kp)
+{
+    // fp32-exact fast kernel for 9/10-bit planes: patch <= 7, same table trick
+    return h->bps == 2 && h->cfg.depth <= 10 && h->impl != 1 && h->impl != 3 && tiled_supported(kp) && kp.n_half <= 3 &&
+           kp.wfact < 0.99f && kp.wfact > 1e-5f;
+}
+
+int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, int plane, const unsigned *only_if_flag = nullptr)
 {
     const bool want_tiled = h->impl != 1 && tiled_supported(kp);
     if (h->impl == 2 && !want_tiled)
@@ -1114,6 +1481,7 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
     {
         TiledParams tp;
         tp.k = kp;
+        tp.only_if_flag = only_if_flag;
         for (int f = 0; f < kp.nf; f++) tp.maps[f] = h->maps[slots[f] * 3 + plane];
         // impl 0/2: fp32-exact fast kernel for 8-bit planes when the table trick is valid; impl 3: integer tiled kernel
         const bool fast_ok = fast8_ok(h, kp);
@@ -1122,12 +1490,13 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
         {
             FusedParams fp;
             fp.nplanes = 1;
+            fp.range_flag = nullptr;
             fp.k[0] = kp;
             for (int f = 0; f < kp.nf; f++) fp.maps[0][f] = tp.maps[f];
             rc = launch_fast8_nh(fp, h->s_compute);
         }
         else
-            rc = h->bps == 1 ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute) : launch_tiled_nh<uint16_t, 96>(tp, h->s_compute);
+            rc = h->bps == 1 ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute) : launch_tiled_nh<uint16_t, kTH16>(tp, h->s_compute);
         if (rc < 0) return rc;
         if (rc == 0)
         {
@@ -1153,17 +1522,17 @@ int pad_plane(hbcu_nlmeans_s *h, int slot, int pl, const void *src, int spitch_e
         const int chunks = (g.bw * h->bps + 15) / 16;
         dim3 blk(64, 4), grid((chunks + 63) / 64, (g.bh + 3) / 4);
         if (h->bps == 1)
-            pad_mirror_vec_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder);
+            pad_mirror_vec_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder, nullptr);
         else
-            pad_mirror_vec_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder);
+            pad_mirror_vec_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder, h->d_range_flag);
     }
     else
     {
         dim3 blk(64, 4), grid((g.bw + 63) / 64, (g.bh + 3) / 4);
         if (h->bps == 1)
-            pad_mirror_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder);
+            pad_mirror_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, spitch_elems, g.w, g.h, dst, g.bpitch, kBorder, nullptr);
         else
-            pad_mirror_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder);
+            pad_mirror_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, spitch_elems, g.w, g.h, (uint16_t *)dst, g.bpitch, kBorder, h->d_range_flag);
     }
     hbcu::count_launch();
     HBCU_CHECK(cudaGetLastError());
@@ -1250,17 +1619,51 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
     // all active planes in one launch when they can share the fast 8-bit kernel instantiation
     bool fused = h->impl == 0 || h->impl == 2;
     int nact = 0, nh = -1;
+    for (int pl = 0; pl < 3; pl++) nact += active[pl] ? 1 : 0;
     for (int pl = 0; pl < 3 && fused; pl++)
     {
         if (!active[pl]) continue;
-        nact++;
         if (!fast8_ok(h, kps[pl])) fused = false;
         if (nh < 0) nh = kps[pl].n_half; else if (nh != kps[pl].n_half) fused = false;
     }
-    if (fused && nact > 1)
+    bool fused16 = (h->impl == 0 || h->impl == 2) && h->bps == 2;
+    nh = -1;
+    for (int pl = 0; pl < 3 && fused16; pl++)
+    {
+        if (!active[pl]) continue;
+        if (!fast16_ok(h, kps[pl])) fused16 = false;
+        if (nh < 0) nh = kps[pl].n_half; else if (nh != kps[pl].n_half) fused16 = false;
+    }
+    if (fused16 && nact > 0)
     {
         FusedParams fp;
         fp.nplanes = 0;
+        fp.range_flag = h->d_range_flag;
+        for (int pl = 0; pl < 3; pl++)
+        {
+            if (!active[pl]) continue;
+            fp.k[fp.nplanes] = kps[pl];
+            for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = h->maps[slots[pl][f] * 3 + pl];
+            fp.nplanes++;
+        }
+        if (launch_fast16_nh(fp, h->s_compute) != 0) { set_error("nlmeans: fused 16-bit launch failed"); return -1; }
+        HBCU_CHECK(cudaGetLastError());
+        h->kernel_launches++;
+        // stand-in for frames with samples above 10 bit: returns immediately unless the border kernel raised the flag
+        const int saved_impl = h->impl;
+        h->impl = 3;
+        for (int pl = 0; pl < 3; pl++)
+        {
+            if (!active[pl]) continue;
+            if (launch_plane(h, kps[pl], slots[pl], pl, h->d_range_flag) != 0) { h->impl = saved_impl; return -1; }
+        }
+        h->impl = saved_impl;
+    }
+    else if (fused && nact > 1)
+    {
+        FusedParams fp;
+        fp.nplanes = 0;
+        fp.range_flag = nullptr;
         for (int pl = 0; pl < 3; pl++)
         {
             if (!active[pl]) continue;
@@ -1357,6 +1760,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;
+    h->d_range_flag = nullptr;
     h->pool_used = 0;
     h->kernel_launches = 0;
     for (int pl = 0; pl < 3; pl++)
@@ -1386,6 +1790,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&h->s_h2d, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->s_pad, cudaStreamNonBlocking, prio_hi));    // border kernels: off the copy stream, so the
+                                                                                   // copy engine never waits for an SM to free up
     CK(cudaStreamCreateWithPriority(&h->s_compute, cudaStreamNonBlocking, prio_lo));
     CK(cudaStreamCreateWithPriority(&h->s_d2h, cudaStreamNonBlocking, prio_hi));
     h->ring_mem.assign(h->ring * 3, nullptr);
@@ -1394,6 +1800,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ring_index.assign(h->ring, -1);
     h->out_index.assign(h->out_slots, -1);
     h->ev_upload.assign(h->ring, nullptr);
+    h->ev_h2d.assign(h->ring, nullptr);
     h->ev_readers.assign(h->ring, nullptr);
     h->ev_kernel.assign(h->out_slots, nullptr);
     h->ev_d2h.assign(h->out_slots, nullptr);
@@ -1401,6 +1808,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     for (int s = 0; s < h->ring; s++)
     {
         CK(cudaEventCreateWithFlags(&h->ev_upload[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_readers[s], cudaEventDisableTiming));
         for (int pl = 0; pl < 3; pl++)
         {
@@ -1427,6 +1835,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ev_pool.assign(2 * 256, nullptr);
     for (auto &e : h->ev_pool) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&h->d_exptable, 3 * HBCU_NLMEANS_EXPSIZE * sizeof(float)));
+    CK(cudaMalloc(&h->d_range_flag, sizeof(unsigned)));
+    CK(cudaMemset(h->d_range_flag, 0, sizeof(unsigned)));
     for (int pl = 0; pl < 3; pl++)
         CK(cudaMemcpy(h->d_exptable + pl * HBCU_NLMEANS_EXPSIZE, cfg->plane[pl].exptable,
                       HBCU_NLMEANS_EXPSIZE * sizeof(float), cudaMemcpyHostToDevice));
@@ -1451,7 +1861,10 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
     if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
     for (auto e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->d_exptable) cudaFree(h->d_exptable);
+    if (h->d_range_flag) cudaFree(h->d_range_flag);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_pad) cudaStreamDestroy(h->s_pad);
+    for (auto e : h->ev_h2d) if (e) cudaEventDestroy(e);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
@@ -1467,22 +1880,33 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     const int slot = (int)(index % h->ring);
     // do not overwrite a slot a queued kernel still reads
-    HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_readers[slot], 0));
+    // raw staging of this slot is free once its previous border kernels ran; the bordered planes once their readers are done
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_upload[slot], 0));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[slot], 0));
+    if (!from_device)
+    {
+        for (int pl = 0; pl < 3; pl++)
+        {
+            const PlaneGeom &g = h->g[pl];
+            HBCU_CHECK(cudaMemcpy2DAsync(h->raw_mem[slot * 3 + pl], (size_t)g.rpitch * h->bps, planes[pl], (size_t)strides[pl],
+                                         (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        HBCU_CHECK(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_h2d[slot], 0));
+    }
     for (int pl = 0; pl < 3; pl++)
     {
         const PlaneGeom &g = h->g[pl];
         if (from_device)
         {
-            if (pad_plane(h, slot, pl, planes[pl], strides[pl] / h->bps, h->s_h2d) != 0) return -1;
+            if (pad_plane(h, slot, pl, planes[pl], strides[pl] / h->bps, h->s_pad) != 0) return -1;
         }
         else
         {
-            HBCU_CHECK(cudaMemcpy2DAsync(h->raw_mem[slot * 3 + pl], (size_t)g.rpitch * h->bps, planes[pl], (size_t)strides[pl],
-                                         (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
-            if (pad_plane(h, slot, pl, h->raw_mem[slot * 3 + pl], g.rpitch, h->s_h2d) != 0) return -1;
+            if (pad_plane(h, slot, pl, h->raw_mem[slot * 3 + pl], g.rpitch, h->s_pad) != 0) return -1;
         }
     }
-    HBCU_CHECK(cudaEventRecord(h->ev_upload[slot], h->s_h2d));
+    HBCU_CHECK(cudaEventRecord(h->ev_upload[slot], h->s_pad));
     h->ring_index[slot] = index;
     return 0;
 }
@@ -1589,6 +2013,7 @@ int hbcu_nlmeans_sync(hbcu_nlmeans_t *h)
     if (h == nullptr) { set_error("nlmeans_sync: null handle"); return -1; }
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_pad));
     HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
     HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
     return 0;

@@ -128,3 +128,44 @@ def test_both_ssd_formulations(ref, cuda_filters, monkeypatch, ssd):
               "y-strength=8:y-patch-size=9:y-range=5:y-frame-count=3"):
         r, g = run_both(ref, cuda_filters, s, clip, FMT8, w, h)
         assert_same(r, g)
+
+
+def clip10_extreme(w, h, seed=9):
+    """full-range 10-bit noise, flat 0 and flat 1023 frames (worst case for the fp32-exact row sums: d = 1023 everywhere)"""
+    n = synth.frame_bytes(FMT10, w, h) // 2
+    rng = np.random.default_rng(seed)
+    frames = [rng.integers(0, 1024, n, dtype=np.uint16), np.zeros(n, np.uint16), np.full(n, 1023, np.uint16),
+              rng.integers(0, 2, n, dtype=np.uint16) * 1023, rng.integers(0, 1024, n, dtype=np.uint16)]
+    return np.stack(frames).view(np.uint8).reshape(len(frames), -1)
+
+
+@pytest.mark.parametrize("impl", ["0", "3", "1"])
+def test_10bit_kernels_agree(ref, cuda_filters, monkeypatch, impl):
+    """fast fp32-exact 10-bit kernel (0), integer tiled kernel (3), generic kernel (1): patch 7/5/3, ranges 3/5/7,
+    every alignment of the compare window (dx0 mod 4), 3-frame window, ragged size"""
+    monkeypatch.setenv("HBCU_NLMEANS_IMPL", impl)
+    w, h = 330, 210
+    clip = synth.progressive_clip(FMT10, w, h, 4, seed=31)
+    for s in ("y-strength=6", "y-strength=10:y-patch-size=5:y-range=7:y-frame-count=3:cb-strength=4:cb-patch-size=3:cb-range=5"):
+        r, g = run_both(ref, cuda_filters, s, clip, FMT10, w, h)
+        assert_same(r, g)
+
+
+def test_10bit_extreme_content(ref, cuda_filters):
+    w, h = 256, 128
+    clip = clip10_extreme(w, h)
+    for s in ("y-strength=3", "y-strength=10:y-origin-tune=0.15", "y-strength=1.5:y-patch-size=5"):
+        r, g = run_both(ref, cuda_filters, s, clip, FMT10, w, h)
+        assert_same(r, g)
+
+
+def test_10bit_container_with_out_of_range_samples(ref, cuda_filters):
+    """a yuv420p10 stream whose 16-bit words exceed 1023 from the third frame on: the border kernel raises the range
+    flag, the fast kernel stands down and the integer kernel produces the frames -- still the reference's output"""
+    w, h = 256, 128
+    clip = synth.progressive_clip(FMT10, w, h, 5, seed=33).copy()
+    v = clip.view(np.uint16).reshape(5, -1)
+    v[2, 1000:1040] = 4095
+    v[3, ::97] = 3000
+    r, g = run_both(ref, cuda_filters, "y-strength=6", clip, FMT10, w, h)
+    assert_same(r, g)
