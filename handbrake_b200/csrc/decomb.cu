@@ -274,13 +274,12 @@ __device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, 
     }
 }
 
-// one thread = 4 adjacent pixels of one output row
+// one thread = 4 adjacent pixels of two consecutive output rows (one kept, one rebuilt): every warp carries the same
+// amount of work.  With one row per thread half of the warps (kept rows) retire at once and the SM runs at half its
+// already register-limited occupancy (ncu, profiles/r01h_decomb_ncu.txt: 12.9 % warps active, long-scoreboard bound).
 template <typename PIX>
-__global__ void __launch_bounds__(256) decomb_field_kernel(FieldParams fp)
+__device__ __forceinline__ void decomb_row4(const FieldParams &fp, int x0, int y)
 {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= fp.w || y >= fp.h) return;
     const PIX *cur = (const PIX *)fp.cur;
     PIX *dst = (PIX *)fp.dst + (size_t)y * fp.dpitch;
     const bool filtered = fp.parity ? !(y & 1) : (y & 1);     // template :744, :796
@@ -320,6 +319,16 @@ __global__ void __launch_bounds__(256) decomb_field_kernel(FieldParams fp)
         for (int i = 0; i < 4; i++)
             if (x0 + i < fp.w) dst[x0 + i] = (PIX)v[i];
     }
+}
+
+template <typename PIX, int MINB>
+__global__ void __launch_bounds__(256, MINB) decomb_field_kernel(FieldParams fp)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+    if (x0 >= fp.w || y0 >= fp.h) return;
+    decomb_row4<PIX>(fp, x0, y0);
+    if (y0 + 1 < fp.h) decomb_row4<PIX>(fp, x0, y0 + 1);
 }
 
 template <typename PIX>
@@ -404,9 +413,21 @@ int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64
         fp.dst = dst;
         fp.w = g.w; fp.h = g.h; fp.pitch = g.pitch; fp.dpitch = g.pitch; fp.epitch = g.pitch;
         fp.mode = frame_mode; fp.parity = parity; fp.tff = tff; fp.maxv = h->maxv;
-        dim3 blk(64, 4), grid(((g.w + 3) / 4 + 63) / 64, (g.h + 3) / 4);
-        if (h->bps == 1) decomb_field_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(fp);
-        else             decomb_field_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>(fp);
+        dim3 blk(64, 4), grid(((g.w + 3) / 4 + 63) / 64, ((g.h + 1) / 2 + 3) / 4);   // 4 px x 2 rows per thread
+        // resident CTAs per SM the kernel is compiled for (register cap 128 / 85 / 64); HBCU_DECOMB_OCC is a tuning hook
+        static const int occ = getenv("HBCU_DECOMB_OCC") ? atoi(getenv("HBCU_DECOMB_OCC")) : 3;
+        if (h->bps == 1)
+        {
+            if (occ == 4)      decomb_field_kernel<uint8_t, 4><<<grid, blk, 0, h->s_compute>>>(fp);
+            else if (occ == 3) decomb_field_kernel<uint8_t, 3><<<grid, blk, 0, h->s_compute>>>(fp);
+            else               decomb_field_kernel<uint8_t, 2><<<grid, blk, 0, h->s_compute>>>(fp);
+        }
+        else
+        {
+            if (occ == 4)      decomb_field_kernel<uint16_t, 4><<<grid, blk, 0, h->s_compute>>>(fp);
+            else if (occ == 3) decomb_field_kernel<uint16_t, 3><<<grid, blk, 0, h->s_compute>>>(fp);
+            else               decomb_field_kernel<uint16_t, 2><<<grid, blk, 0, h->s_compute>>>(fp);
+        }
         hbcu::count_launch();
         HBCU_CHECK(cudaGetLastError());
     }

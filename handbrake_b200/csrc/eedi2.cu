@@ -89,38 +89,55 @@ struct K            // per-depth constants
 // ---------------------------------------------------------------------------------------------
 // copies
 // ---------------------------------------------------------------------------------------------
+// The copy-like stages move 16 bytes per thread.  Every row starts 16-byte aligned: plane bases are 64-byte
+// aligned (own allocations / 64-byte plane offsets) and the pitch is the reference's 64-byte-rounded stride.
 template <typename PIX>
-__global__ void k_fill_half(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int rows)
+__global__ void __launch_bounds__(256) k_fill_half(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int rows)
 {
     // row r of the field buffer = row 2r of src (src already points at the field's first line); whole pitch
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (x < pitch && r < rows) dst[(size_t)r * pitch + x] = src[(size_t)2 * r * pitch + x];
+    constexpr int EPC = 16 / (int)sizeof(PIX);
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * EPC, r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < pitch && r < rows)
+        *reinterpret_cast<uint4 *>(dst + (size_t)r * pitch + x) = *reinterpret_cast<const uint4 *>(src + (size_t)2 * r * pitch + x);
 }
 
 template <typename PIX>
-__global__ void k_upscale2(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int rows)
+__global__ void __launch_bounds__(256) k_upscale2(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int rows)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    constexpr int EPC = 16 / (int)sizeof(PIX);
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * EPC, r = blockIdx.y * blockDim.y + threadIdx.y;
     if (x < pitch && r < rows)
     {
-        const PIX v = src[(size_t)r * pitch + x];
-        dst[(size_t)(2 * r) * pitch + x] = v;
-        dst[(size_t)(2 * r + 1) * pitch + x] = v;
+        const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)r * pitch + x);
+        *reinterpret_cast<uint4 *>(dst + (size_t)(2 * r) * pitch + x) = v;
+        *reinterpret_cast<uint4 *>(dst + (size_t)(2 * r + 1) * pitch + x) = v;
     }
 }
 
+// bit_blit over `width` samples per row (not the stride): whole 16-byte chunks as vectors, the ragged tail by element
 template <typename PIX>
-__global__ void k_blit(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int width, int rows)
+__global__ void __launch_bounds__(256) k_blit(const PIX *__restrict__ src, PIX *__restrict__ dst, int pitch, int width, int rows)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (x < width && r < rows) dst[(size_t)r * pitch + x] = src[(size_t)r * pitch + x];
+    constexpr int EPC = 16 / (int)sizeof(PIX);
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * EPC, r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || r >= rows) return;
+    const PIX *s = src + (size_t)r * pitch + x;
+    PIX *d = dst + (size_t)r * pitch + x;
+    if (x + EPC <= width)
+        *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(s);
+    else
+        for (int i = 0; x + i < width; i++) d[i] = s[i];
 }
 
+// n is a multiple of the pitch (whole rows), so of 16 bytes
 template <typename PIX>
-__global__ void k_fill(PIX *__restrict__ dst, size_t n, int value)
+__global__ void __launch_bounds__(256) k_fill(PIX *__restrict__ dst, size_t n, int value)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (PIX)value;
+    constexpr int EPC = 16 / (int)sizeof(PIX);
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * EPC;
+    if (i >= n) return;
+    const uint32_t w = sizeof(PIX) == 1 ? (uint32_t)(value & 0xff) * 0x01010101u : (uint32_t)(value & 0xffff) * 0x00010001u;
+    *reinterpret_cast<uint4 *>(dst + i) = make_uint4(w, w, w, w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -799,11 +816,17 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     PIX *dst2p = F(DST2PF), *tmp2p2 = F(TMP2PF2), *msk2p = F(MSK2PF), *tmp2p = F(TMP2PF), *dst2mp = F(DST2MPF);
     const dim3 blk(64, 4);
     auto grid2 = [&](int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); };
-    const dim3 rowblk(256, 1);
-    auto gridrows = [&](int w, int rows) { return dim3((w + 255) / 256, rows); };
+    const dim3 rowblk(64, 4);                                    // 16-byte chunks x rows
+    const int epc = 16 / (int)sizeof(PIX);
+    auto gridrows = [&](int w, int rows) { return dim3(((w + epc - 1) / epc + 63) / 64, (rows + 3) / 4); };
     int launches = 0;
 #define LAUNCH(...) do { if (e->stop_after == 0 || launches < e->stop_after) { __VA_ARGS__; } ++launches; } while (0)
 
+    if ((uintptr_t)cur_plane % 16)
+    {
+        set_error("eedi2: source plane %d is not 16-byte aligned", pl);
+        return -1;
+    }
     // eedi2_planer: field start_line = !tff of the current frame, whole strides (:455-466, :79-92)
     const int field_rows = (height + 1) / 2;
     LAUNCH((k_fill_half<PIX><<<gridrows(pitch, field_rows), rowblk, 0, st>>>(cur_plane + (size_t)pitch * (!tff), srcp, pitch, field_rows)));
@@ -821,7 +844,7 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     const int peak = (1 << depth) - 1;
     {
         const size_t n = (size_t)pitch * hh;
-        LAUNCH((k_fill<PIX><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmpp, n, peak)));
+        LAUNCH((k_fill<PIX><<<(unsigned)((n / epc + 255) / 256), 256, 0, st>>>(tmpp, n, peak)));
     }
     LAUNCH((k_calc_directions<PIX><<<grid2(width, hh), blk, 0, st>>>(pl, mskp, srcp, tmpp, pitch, width, hh, c.maxd, c.nt, depth, e->lim)));
     LAUNCH((k_dir_map<PIX, false, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, 0, depth, e->lim)));
@@ -837,7 +860,7 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     const int rows2 = (height - 1 - (2 - tff) + 1) / 2 > 0 ? (height - 1 - (2 - tff) + 1) / 2 : 0;   // y = 2-tff, +2, ... < height-1
     {
         const size_t n = (size_t)pitch * height;
-        LAUNCH((k_fill<PIX><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp2p, n, peak)));
+        LAUNCH((k_fill<PIX><<<(unsigned)((n / epc + 255) / 256), 256, 0, st>>>(tmp2p, n, peak)));
     }
     LAUNCH((k_mark_directions_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, tmp2p2, tmp2p, pitch, width, height, tff, depth, e->lim)));
     LAUNCH((k_dir_map<PIX, false, true><<<grid2(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
@@ -888,6 +911,14 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
     {
         set_error("eedi2: postproc %d is not implemented", cfg.pp);
         return nullptr;
+    }
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (((size_t)cfg.pitch[pl] * (cfg.depth > 8 ? 2 : 1)) % 64)
+        {
+            set_error("eedi2: plane %d pitch %d is not the reference's 64-byte rounded stride", pl, cfg.pitch[pl]);
+            return nullptr;
+        }
     }
     Eedi2 *e = new (std::nothrow) Eedi2();
     if (e == nullptr) { set_error("eedi2: out of memory"); return nullptr; }

@@ -29,7 +29,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
+#include <cstdio>
 
 namespace {
 
@@ -47,6 +49,10 @@ constexpr int kHaloX     = kBorder;
 constexpr int kTilePW    = kTileW + 2 * kHaloX;  // 160 elements per tile row
 constexpr int kThreads   = 256;
 constexpr int kGroup     = 3;     // horizontal displacements handled per pass
+
+// trace points per frame (HBCU_NLMEANS_TRACE)
+enum { TR_H2D_BEGIN, TR_H2D_END, TR_PAD_BEGIN, TR_PAD_END, TR_KERNEL_BEGIN, TR_KERNEL_END, TR_D2H_BEGIN, TR_D2H_END, kTracePoints };
+constexpr int kTraceFrames = 512;
 
 constexpr int kMaxTiledFrames = 8; // temporal depth the tiled kernel takes (tensor maps travel as kernel parameters)
 
@@ -1315,16 +1321,26 @@ struct hbcu_nlmeans_s
     std::vector<CUtensorMap> maps;        // [slot*3+plane] TMA descriptors of the bordered planes
     float *d_exptable;                    // 3 x 128
     unsigned *d_range_flag;               // sticky: a 16-bit plane held a sample above kFast16Max (see nlmeans_fast16_kernel)
-    cudaStream_t s_h2d, s_pad, s_compute, s_d2h;
+    cudaStream_t s_h2d, s_pad, s_compute, s_d2h;   // s_compute = s_comp[frame index & (n_comp - 1)] of the launch being queued
+    cudaStream_t s_comp[2];               // consecutive frames alternate between two compute streams: the next frame's CTAs
+                                          // fill the SMs the previous launch's last partial wave leaves idle
+    int n_comp;
+    cudaEvent_t ev_join[2];
     std::vector<cudaEvent_t> ev_h2d;      // per ring slot: raw planes have arrived (H2D done), border kernels may start
     std::vector<cudaEvent_t> ev_upload;   // per ring slot: bordered planes ready
-    std::vector<cudaEvent_t> ev_readers;  // per ring slot: last kernel reading it is done
+    std::vector<cudaEvent_t> ev_readers;  // [slot*2 + compute stream]: last kernel on that stream reading the slot is done
     std::vector<cudaEvent_t> ev_kernel;   // per out slot
     std::vector<cudaEvent_t> ev_d2h;      // per out slot
     std::vector<int64_t>     out_index;
     cudaEvent_t ev_mark[2];
     std::vector<cudaEvent_t> ev_pool;     // event pairs around the main kernels (kernel-only timing)
     int pool_used;                        // pairs recorded since mark 0
+    // HBCU_NLMEANS_TRACE=<file>: per-frame timeline of the four streams (timing events, written at destroy);
+    // the tracing hook that stands in for libhb's per-filter hb_log timing (work.c:2552-2560)
+    std::string trace_path;
+    std::vector<cudaEvent_t> tr;          // [frame * kTracePoints + point]
+    cudaEvent_t tr_base;
+    int tr_frames;
     int kernel_launches;                  // main-kernel launches since mark 0
 };
 
@@ -1512,6 +1528,13 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
     return 0;
 }
 
+inline void trace(hbcu_nlmeans_s *h, int64_t index, int point, cudaStream_t st)
+{
+    if (h->tr.empty() || index < 0 || index >= kTraceFrames) return;
+    cudaEventRecord(h->tr[(size_t)index * kTracePoints + point], st);
+    if (index + 1 > h->tr_frames) h->tr_frames = (int)index + 1;
+}
+
 int pad_plane(hbcu_nlmeans_s *h, int slot, int pl, const void *src, int spitch_elems, cudaStream_t st)
 {
     const PlaneGeom &g = h->g[pl];
@@ -1546,6 +1569,8 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         set_error("nlmeans: navail must be >= 1");
         return -1;
     }
+    const int cs = (int)(index & (h->n_comp - 1));
+    h->s_compute = h->s_comp[cs];
     int max_nf = 1;
     for (int pl = 0; pl < 3; pl++)
     {
@@ -1568,6 +1593,7 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
 
     const int pair = h->pool_used < (int)h->ev_pool.size() / 2 ? h->pool_used : -1;
     if (pair >= 0) HBCU_CHECK(cudaEventRecord(h->ev_pool[2 * pair], h->s_compute));
+    trace(h, index, TR_KERNEL_BEGIN, h->s_compute);
     KernelParams kps[3];
     int slots[3][kMaxFrames];
     bool active[3] = { false, false, false };
@@ -1689,9 +1715,12 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         HBCU_CHECK(cudaEventRecord(h->ev_pool[2 * pair + 1], h->s_compute));
         h->pool_used++;
     }
+    trace(h, index, TR_KERNEL_END, h->s_compute);
     HBCU_CHECK(cudaEventRecord(h->ev_kernel[oslot], h->s_compute));
-    // frame `index` is read last by this very launch: its slot may be overwritten afterwards
-    HBCU_CHECK(cudaEventRecord(h->ev_readers[(int)(index % h->ring)], h->s_compute));
+    // every slot this launch read may be overwritten once it is done (per compute stream: launches on the other
+    // stream that read the same slot record their own event)
+    for (int f = 0; f < max_nf; f++)
+        HBCU_CHECK(cudaEventRecord(h->ev_readers[(int)((index + f) % h->ring) * 2 + cs], h->s_compute));
     h->out_index[oslot] = index;
     return 0;
 }
@@ -1792,7 +1821,13 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     CK(cudaStreamCreateWithPriority(&h->s_h2d, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&h->s_pad, cudaStreamNonBlocking, prio_hi));    // border kernels: off the copy stream, so the
                                                                                    // copy engine never waits for an SM to free up
-    CK(cudaStreamCreateWithPriority(&h->s_compute, cudaStreamNonBlocking, prio_lo));
+    h->n_comp = 2;
+    if (const char *e = getenv("HBCU_NLMEANS_STREAMS")) h->n_comp = atoi(e) == 1 ? 1 : 2;                     // tuning hook
+    CK(cudaStreamCreateWithPriority(&h->s_comp[0], cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&h->s_comp[1], cudaStreamNonBlocking, prio_lo));
+    h->s_compute = h->s_comp[0];
+    CK(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
     CK(cudaStreamCreateWithPriority(&h->s_d2h, cudaStreamNonBlocking, prio_hi));
     h->ring_mem.assign(h->ring * 3, nullptr);
     h->raw_mem.assign(h->ring * 3, nullptr);
@@ -1801,7 +1836,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->out_index.assign(h->out_slots, -1);
     h->ev_upload.assign(h->ring, nullptr);
     h->ev_h2d.assign(h->ring, nullptr);
-    h->ev_readers.assign(h->ring, nullptr);
+    h->ev_readers.assign(h->ring * 2, nullptr);
     h->ev_kernel.assign(h->out_slots, nullptr);
     h->ev_d2h.assign(h->out_slots, nullptr);
     h->maps.resize(h->ring * 3);
@@ -1809,7 +1844,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     {
         CK(cudaEventCreateWithFlags(&h->ev_upload[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&h->ev_readers[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_readers[2 * s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_readers[2 * s + 1], cudaEventDisableTiming));
         for (int pl = 0; pl < 3; pl++)
         {
             CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
@@ -1832,6 +1868,16 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     }
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
+    h->tr_frames = 0;
+    h->tr_base = nullptr;
+    if (const char *e = getenv("HBCU_NLMEANS_TRACE"))
+    {
+        h->trace_path = e;
+        h->tr.assign((size_t)kTraceFrames * kTracePoints, nullptr);
+        for (auto &ev : h->tr) CK(cudaEventCreate(&ev));
+        CK(cudaEventCreate(&h->tr_base));
+        CK(cudaEventRecord(h->tr_base, h->s_h2d));
+    }
     h->ev_pool.assign(2 * 256, nullptr);
     for (auto &e : h->ev_pool) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&h->d_exptable, 3 * HBCU_NLMEANS_EXPSIZE * sizeof(float)));
@@ -1850,6 +1896,27 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
     if (h == nullptr) return;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    if (!h->tr.empty())
+    {
+        if (FILE *fp = fopen(h->trace_path.c_str(), "a"))
+        {
+            fprintf(fp, "# frame,h2d_begin,h2d_end,pad_begin,pad_end,kernel_begin,kernel_end,d2h_begin,d2h_end (ms since create; -1 = not recorded)\n");
+            for (int f = 0; f < h->tr_frames; f++)
+            {
+                fprintf(fp, "%d", f);
+                for (int k = 0; k < kTracePoints; k++)
+                {
+                    float ms = -1.f;
+                    if (cudaEventElapsedTime(&ms, h->tr_base, h->tr[(size_t)f * kTracePoints + k]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+                    fprintf(fp, ",%.4f", ms);
+                }
+                fprintf(fp, "\n");
+            }
+            fclose(fp);
+        }
+        for (auto ev : h->tr) if (ev) cudaEventDestroy(ev);
+        if (h->tr_base) cudaEventDestroy(h->tr_base);
+    }
     for (auto p : h->ring_mem) if (p) cudaFree(p);
     for (auto p : h->raw_mem) if (p) cudaFree(p);
     for (auto p : h->out_mem) if (p) cudaFree(p);
@@ -1865,7 +1932,11 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_pad) cudaStreamDestroy(h->s_pad);
     for (auto e : h->ev_h2d) if (e) cudaEventDestroy(e);
-    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    for (int i = 0; i < 2; i++)
+    {
+        if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
 }
@@ -1882,18 +1953,22 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
     // do not overwrite a slot a queued kernel still reads
     // raw staging of this slot is free once its previous border kernels ran; the bordered planes once their readers are done
     HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_upload[slot], 0));
-    HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[slot], 0));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[2 * slot], 0));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[2 * slot + 1], 0));
     if (!from_device)
     {
+        trace(h, index, TR_H2D_BEGIN, h->s_h2d);
         for (int pl = 0; pl < 3; pl++)
         {
             const PlaneGeom &g = h->g[pl];
             HBCU_CHECK(cudaMemcpy2DAsync(h->raw_mem[slot * 3 + pl], (size_t)g.rpitch * h->bps, planes[pl], (size_t)strides[pl],
                                          (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
         }
+        trace(h, index, TR_H2D_END, h->s_h2d);
         HBCU_CHECK(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
         HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_h2d[slot], 0));
     }
+    trace(h, index, TR_PAD_BEGIN, h->s_pad);
     for (int pl = 0; pl < 3; pl++)
     {
         const PlaneGeom &g = h->g[pl];
@@ -1906,6 +1981,7 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
             if (pad_plane(h, slot, pl, h->raw_mem[slot * 3 + pl], g.rpitch, h->s_pad) != 0) return -1;
         }
     }
+    trace(h, index, TR_PAD_END, h->s_pad);
     HBCU_CHECK(cudaEventRecord(h->ev_upload[slot], h->s_pad));
     h->ring_index[slot] = index;
     return 0;
@@ -1941,12 +2017,14 @@ int hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, void *cons
     const int oslot = (int)(index % h->out_slots);
     if (run_filter(h, index, navail, oslot) != 0) return -1;
     HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_kernel[oslot], 0));
+    trace(h, index, TR_D2H_BEGIN, h->s_d2h);
     for (int pl = 0; pl < 3; pl++)
     {
         const PlaneGeom &g = h->g[pl];
         HBCU_CHECK(cudaMemcpy2DAsync(planes[pl], (size_t)strides[pl], h->out_mem[oslot * 3 + pl], (size_t)g.rpitch * h->bps,
                                      (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
     }
+    trace(h, index, TR_D2H_END, h->s_d2h);
     HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_d2h));
     return 0;
 }
@@ -2003,8 +2081,11 @@ int hbcu_nlmeans_stream_wait(hbcu_nlmeans_t *h, void *cuda_stream)
     // makes a caller-owned stream (e.g. the one NCCL runs on) wait for everything queued on the compute stream
     if (h == nullptr) { set_error("nlmeans_stream_wait: null handle"); return -1; }
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
-    HBCU_CHECK(cudaEventRecord(h->ev_mark[1], h->s_compute));
-    HBCU_CHECK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->ev_mark[1], 0));
+    for (int i = 0; i < 2; i++)
+    {
+        HBCU_CHECK(cudaEventRecord(h->ev_join[i], h->s_comp[i]));
+        HBCU_CHECK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->ev_join[i], 0));
+    }
     return 0;
 }
 
@@ -2014,7 +2095,8 @@ int hbcu_nlmeans_sync(hbcu_nlmeans_t *h)
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
     HBCU_CHECK(cudaStreamSynchronize(h->s_pad));
-    HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_comp[0]));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_comp[1]));
     HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
     return 0;
 }
@@ -2035,7 +2117,11 @@ int hbcu_nlmeans_mark(hbcu_nlmeans_t *h, int which)
         h->pool_used = 0;
         h->kernel_launches = 0;
     }
-    HBCU_CHECK(cudaEventRecord(h->ev_mark[which], h->s_compute));
+    // the mark sits behind everything queued on both compute streams; work queued after it starts after it
+    HBCU_CHECK(cudaEventRecord(h->ev_join[1], h->s_comp[1]));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_comp[0], h->ev_join[1], 0));
+    HBCU_CHECK(cudaEventRecord(h->ev_mark[which], h->s_comp[0]));
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_comp[1], h->ev_mark[which], 0));
     return 0;
 }
 

@@ -88,3 +88,18 @@ def test_4k_lapsharp(ref, cuda_filters):
     clip = synth.progressive_clip(FMT[10], w, h, 3, noise=20)
     same(ref.run("hb_filter_lapsharp", "y-strength=0.2:y-kernel=isolap", clip, FMT[10], w, h),
          cuda_filters.run("hb_filter_lapsharp_cuda", "y-strength=0.2:y-kernel=isolap", clip, FMT[10], w, h))
+
+
+def test_config5_8k_10bit_chain(ref, cuda_filters):
+    """BASELINE config 5: 7680x4320 yuv420p10, decomb -> NLMeans medium -> lapsharp, in libhb's enforced filter
+    order (hb.c:1701-1720).  A 99.5 MB frame is above the buffer pool's largest size class (fifo.c:111-112)."""
+    w, h = 7680, 4320
+    clip, flags, _ = decomb_inputs(10, w, h, 1, seed=5)
+    clip, flags = clip[:3], flags[:3]
+    names_r = ["hb_filter_decomb", "hb_filter_nlmeans", "hb_filter_lapsharp_mt"]
+    names_g = ["hb_filter_decomb_cuda", "hb_filter_nlmeans_cuda", "hb_filter_lapsharp_cuda"]
+    s = ["mode=7", "y-strength=6", "y-strength=0.2:y-kernel=isolap"]
+    r = ref.run(names_r, [s[0], s[1] + ":threads=3", s[2]], clip, FMT[10], w, h, flags=flags)
+    g = cuda_filters.run(names_g, s, clip, FMT[10], w, h, flags=flags)
+    same(r, g)
+    assert g.frames.shape[0] == 3
