@@ -17,6 +17,7 @@
 // Integer work is bit-exact by construction; the segment decomposition of the reference does
 // not influence its result (block grid is globally aligned).
 #include "hbcu_common.h"
+#include "hbcu_frames.h"
 #include "../../include/hbcu.h"
 
 #include <cstdlib>
@@ -386,6 +387,19 @@ int hbcu_comb_detect_upload(hbcu_comb_detect_t *h, int64_t index, const void *lu
 int hbcu_comb_detect_upload_device(hbcu_comb_detect_t *h, int64_t index, const void *dluma, int stride)
 {
     return comb_upload(h, index, dluma, stride, cudaMemcpyDeviceToDevice);
+}
+
+int hbcu_comb_detect_upload_frame(hbcu_comb_detect_t *h, int64_t index, hbcu_frame_t *in)
+{
+    if (h == nullptr || in == nullptr || in->device != h->cfg.device || in->row_bytes[0] != h->cfg.width * h->bps || in->rows[0] != h->cfg.height)
+    {
+        set_error("comb_detect_upload_frame: bad argument or frame geometry");
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    if (hbcu::frame_begin_read(in, h->s_h2d) != 0) return -1;
+    if (comb_upload(h, index, in->plane[0], in->stride[0], cudaMemcpyDeviceToDevice) != 0) return -1;
+    return hbcu::frame_end_read(in, h->s_h2d);
 }
 
 int hbcu_comb_detect_run(hbcu_comb_detect_t *h, int64_t prev, int64_t cur, int64_t next, int force)

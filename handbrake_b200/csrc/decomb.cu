@@ -13,6 +13,7 @@
 // Integer arithmetic only -> bit-exact.  The kernel is HBM-bound: it reads the three input
 // frames once (rows are re-touched through L1/L2) and writes one.
 #include "hbcu_common.h"
+#include "hbcu_frames.h"
 #include "../../include/hbcu.h"
 #include "eedi2.cuh"
 
@@ -349,6 +350,8 @@ struct hbcu_decomb_s
     int bps, maxv;
     Geom g[3];
     int slots, out_slots;
+    std::vector<uint8_t *> in_base, out_base;   // one allocation per frame, planes back to back at the reference stride:
+    size_t frame_bytes, plane_off[3];            // the layout of a STANDARD hb_buffer_t, so a frame moves as one copy
     std::vector<uint8_t *> in_mem;       // [slot*3+plane]
     std::vector<int64_t> in_index;
     std::vector<cudaEvent_t> ev_upload, ev_readers;
@@ -363,7 +366,8 @@ struct hbcu_decomb_s
 
 namespace {
 
-int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next, int frame_mode, int parity, int tff, int oslot)
+int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next, int frame_mode, int parity, int tff, int oslot,
+              uint8_t *const *ext_dst = nullptr)
 {
     const int64_t idx[3] = { prev, cur, next };
     int slot[3];
@@ -393,7 +397,7 @@ int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64
     for (int pl = 0; pl < 3; pl++)
     {
         const Geom &g = h->g[pl];
-        uint8_t *dst = h->out_mem[oslot * 3 + pl];
+        uint8_t *dst = ext_dst ? ext_dst[pl] : h->out_mem[oslot * 3 + pl];     // external planes share the reference stride
         if (frame_mode == 0 || (use_eedi && !(frame_mode & HBCU_DECOMB_YADIF)))
         {
             // pass-through (hb_buffer_copy) or "just EEDI2": whole-plane copy (decomb template :855-875, :893-896)
@@ -486,6 +490,8 @@ int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
         // (SURVEY.md 8a/a26), so the device pitch reproduces exactly that stride
         g.pitch = ((g.w * h->bps + 63) / 64 * 64) / h->bps;
         g.bytes = (size_t)g.pitch * g.h * h->bps;
+        h->plane_off[pl] = pl == 0 ? 0 : h->plane_off[pl - 1] + h->g[pl - 1].bytes;
+        h->frame_bytes = h->plane_off[pl] + g.bytes;
     }
 #define CK(expr)                                                                  \
     do {                                                                          \
@@ -500,6 +506,8 @@ int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
     CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     h->in_mem.assign(h->slots * 3, nullptr);
+    h->in_base.assign(h->slots, nullptr);
+    h->out_base.assign(h->out_slots, nullptr);
     h->in_index.assign(h->slots, -1);
     h->ev_upload.assign(h->slots, nullptr);
     h->ev_readers.assign(h->slots, nullptr);
@@ -511,18 +519,17 @@ int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
     {
         CK(cudaEventCreateWithFlags(&h->ev_upload[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_readers[s], cudaEventDisableTiming));
-        for (int pl = 0; pl < 3; pl++)
-        {
-            // one guard row above and below: EEDI2's linear addressing may step one row outside (never used for results)
-            CK(cudaMalloc(&h->in_mem[s * 3 + pl], h->g[pl].bytes));
-            CK(cudaMemset(h->in_mem[s * 3 + pl], 0, h->g[pl].bytes));
-        }
+        CK(cudaMalloc(&h->in_base[s], h->frame_bytes));
+        CK(cudaMemset(h->in_base[s], 0, h->frame_bytes));
+        for (int pl = 0; pl < 3; pl++) h->in_mem[s * 3 + pl] = h->in_base[s] + h->plane_off[pl];
     }
     for (int s = 0; s < h->out_slots; s++)
     {
         CK(cudaEventCreateWithFlags(&h->ev_kernel[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_d2h[s], cudaEventDisableTiming));
-        for (int pl = 0; pl < 3; pl++) CK(cudaMalloc(&h->out_mem[s * 3 + pl], h->g[pl].bytes));
+        CK(cudaMalloc(&h->out_base[s], h->frame_bytes));
+        CK(cudaMemset(h->out_base[s], 0, h->frame_bytes));          // the stride padding is never written
+        for (int pl = 0; pl < 3; pl++) h->out_mem[s * 3 + pl] = h->out_base[s] + h->plane_off[pl];
     }
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
@@ -555,8 +562,8 @@ void hbcu_decomb_destroy(hbcu_decomb_t *h)
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     if (h->eedi) hbcu::eedi2_destroy(h->eedi);
-    for (auto p : h->in_mem) if (p) cudaFree(p);
-    for (auto p : h->out_mem) if (p) cudaFree(p);
+    for (auto p : h->in_base) if (p) cudaFree(p);
+    for (auto p : h->out_base) if (p) cudaFree(p);
     for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_readers) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_kernel) if (e) cudaEventDestroy(e);
@@ -569,13 +576,26 @@ void hbcu_decomb_destroy(hbcu_decomb_t *h)
     delete h;
 }
 
+// the caller's planes have exactly the device layout (back to back, reference stride): the frame is one copy
+static bool same_layout(const hbcu_decomb_t *h, const void *const planes[3], const int strides[3])
+{
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if ((size_t)strides[pl] != (size_t)h->g[pl].pitch * h->bps) return false;
+        if ((const uint8_t *)planes[pl] != (const uint8_t *)planes[0] + h->plane_off[pl]) return false;
+    }
+    return true;
+}
+
 static int decomb_upload(hbcu_decomb_t *h, int64_t index, const void *const planes[3], const int strides[3], cudaMemcpyKind kind)
 {
     if (h == nullptr || planes == nullptr || strides == nullptr || index < 0) { set_error("decomb_upload: bad argument"); return -1; }
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     const int slot = (int)(index % h->slots);
     HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_readers[slot], 0));
-    for (int pl = 0; pl < 3; pl++)
+    const bool whole = same_layout(h, planes, strides);
+    if (whole) HBCU_CHECK(cudaMemcpyAsync(h->in_base[slot], planes[0], h->frame_bytes, kind, h->s_h2d));
+    for (int pl = 0; pl < 3 && !whole; pl++)
     {
         const Geom &g = h->g[pl];
         // copy whole strides when the layouts agree (the stride padding is part of what EEDI2 may read)
@@ -616,7 +636,9 @@ int hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t c
     h->next_out = (h->next_out + 1) % h->out_slots;
     if (run_field(h, ticket, prev, cur, next, frame_mode, parity, tff, oslot) != 0) return -1;
     HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_kernel[oslot], 0));
-    for (int pl = 0; pl < 3; pl++)
+    const bool whole = same_layout(h, planes, strides);
+    if (whole) HBCU_CHECK(cudaMemcpyAsync(planes[0], h->out_base[oslot], h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+    for (int pl = 0; pl < 3 && !whole; pl++)
     {
         const Geom &g = h->g[pl];
         HBCU_CHECK(cudaMemcpy2DAsync(planes[pl], (size_t)strides[pl], h->out_mem[oslot * 3 + pl], (size_t)g.pitch * h->bps,
@@ -641,6 +663,37 @@ int hbcu_decomb_filter_device(hbcu_decomb_t *h, int64_t ticket, int64_t prev, in
         if (out_strides) out_strides[pl] = h->g[pl].pitch * h->bps;
     }
     return 0;
+}
+
+static bool frame_fits(const hbcu_decomb_t *h, const hbcu_frame_t *f)
+{
+    if (f == nullptr || f->device != h->cfg.device) return false;
+    for (int pl = 0; pl < 3; pl++)
+        if (f->row_bytes[pl] != h->g[pl].w * h->bps || f->rows[pl] != h->g[pl].h || f->stride[pl] != h->g[pl].pitch * h->bps) return false;
+    return true;
+}
+
+int hbcu_decomb_upload_frame(hbcu_decomb_t *h, int64_t index, hbcu_frame_t *in)
+{
+    if (h == nullptr || index < 0 || !frame_fits(h, in)) { set_error("decomb_upload_frame: bad argument or frame geometry"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    if (hbcu::frame_begin_read(in, h->s_h2d) != 0) return -1;
+    const void *planes[3] = { in->plane[0], in->plane[1], in->plane[2] };
+    if (decomb_upload(h, index, planes, in->stride, cudaMemcpyDeviceToDevice) != 0) return -1;
+    return hbcu::frame_end_read(in, h->s_h2d);
+}
+
+int hbcu_decomb_filter_frame(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
+                             int frame_mode, int parity, int tff, hbcu_frame_t *out)
+{
+    if (h == nullptr || !frame_fits(h, out)) { set_error("decomb_filter_frame: bad argument or frame geometry"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = h->next_out;
+    h->next_out = (h->next_out + 1) % h->out_slots;
+    if (hbcu::frame_begin_write(out, h->s_compute) != 0) return -1;
+    if (run_field(h, ticket, prev, cur, next, frame_mode, parity, tff, oslot, out->plane) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_compute));
+    return hbcu::frame_end_write(out, h->s_compute);
 }
 
 int hbcu_decomb_wait(hbcu_decomb_t *h, int64_t ticket)

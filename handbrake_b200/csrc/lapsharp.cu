@@ -10,6 +10,7 @@
 // reference, including its dependence on the stride: pixels with x < (stride-width)/2 + offset_max
 // are copied, and the last columns read the stride region to the right of the picture.
 #include "hbcu_common.h"
+#include "hbcu_frames.h"
 #include "../../include/hbcu.h"
 
 #include <cstdlib>
@@ -121,6 +122,8 @@ struct hbcu_lapsharp_s
     hbcu_lapsharp_config_t cfg;
     int bps, maxv, slots, next;
     Geom g[3];
+    std::vector<uint8_t *> in_base, out_base;    // one allocation per frame, planes back to back at the reference stride
+    size_t frame_bytes, plane_off[3];             // = the layout of a STANDARD hb_buffer_t: a frame moves as one copy
     std::vector<uint8_t *> in_mem, out_mem;
     std::vector<int64_t> ticket;
     std::vector<cudaEvent_t> ev_up, ev_k, ev_down;
@@ -131,6 +134,19 @@ struct hbcu_lapsharp_s
 namespace {
 
 const double kCoef[4] = { 1.0, 1.0 / 5, 1.0 / 5, 1.0 / 15 };     // lapsharp.c:95-101
+
+// hb_frame_buffer_mirror_stride (fifo.c:906-959) for a frame that never visits the host.  The reference runs its 16-bit
+// variant for every format with `width` in samples as the word index: for 8-bit frames the margin comes out negative
+// and nothing is written, so only 16-bit planes with a padded stride need this.
+__global__ void mirror_stride16_kernel(uint16_t *d, int width, int height, int stride)
+{
+    const int yy = blockIdx.x * blockDim.y + threadIdx.y;
+    if (yy >= height) return;
+    const int margin = stride - width, margin_front = margin / 2, margin_back = margin - margin_front;
+    const size_t row = (size_t)yy * stride;
+    for (int ii = threadIdx.x; ii < margin_back; ii += blockDim.x) d[row + width + ii] = d[row + width - ii - 1];
+    for (int ii = threadIdx.x; ii < margin_front; ii += blockDim.x) d[row + stride - 1 - ii] = d[row + stride + ii];
+}
 
 int launch(hbcu_lapsharp_s *h, int pl, const void *src, int spitch_elems, void *dst)
 {
@@ -193,6 +209,8 @@ int hbcu_lapsharp_create(hbcu_lapsharp_t **out, const hbcu_lapsharp_config_t *cf
         g.h = pl == 0 ? cfg->height : -((-cfg->height) >> cfg->chroma_shift_h);
         g.pitch = ((g.w * h->bps + 63) / 64 * 64) / h->bps;          // hb_image_stride
         g.bytes = (size_t)g.pitch * g.h * h->bps;
+        h->plane_off[pl] = pl == 0 ? 0 : h->plane_off[pl - 1] + h->g[pl - 1].bytes;
+        h->frame_bytes = h->plane_off[pl] + g.bytes;
     }
 #define CK(expr)                                                                  \
     do {                                                                          \
@@ -208,6 +226,8 @@ int hbcu_lapsharp_create(hbcu_lapsharp_t **out, const hbcu_lapsharp_config_t *cf
     CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     h->in_mem.assign(h->slots * 3, nullptr);
     h->out_mem.assign(h->slots * 3, nullptr);
+    h->in_base.assign(h->slots, nullptr);
+    h->out_base.assign(h->slots, nullptr);
     h->ticket.assign(h->slots, -1);
     h->ev_up.assign(h->slots, nullptr);
     h->ev_k.assign(h->slots, nullptr);
@@ -217,11 +237,14 @@ int hbcu_lapsharp_create(hbcu_lapsharp_t **out, const hbcu_lapsharp_config_t *cf
         CK(cudaEventCreateWithFlags(&h->ev_up[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_k[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_down[s], cudaEventDisableTiming));
+        CK(cudaMalloc(&h->in_base[s], h->frame_bytes + 256));
+        CK(cudaMemset(h->in_base[s], 0, h->frame_bytes + 256));
+        CK(cudaMalloc(&h->out_base[s], h->frame_bytes));
+        CK(cudaMemset(h->out_base[s], 0, h->frame_bytes));
         for (int pl = 0; pl < 3; pl++)
         {
-            CK(cudaMalloc(&h->in_mem[s * 3 + pl], h->g[pl].bytes + 256));
-            CK(cudaMemset(h->in_mem[s * 3 + pl], 0, h->g[pl].bytes + 256));
-            CK(cudaMalloc(&h->out_mem[s * 3 + pl], h->g[pl].bytes));
+            h->in_mem[s * 3 + pl] = h->in_base[s] + h->plane_off[pl];
+            h->out_mem[s * 3 + pl] = h->out_base[s] + h->plane_off[pl];
         }
     }
     CK(cudaEventCreate(&h->ev_mark[0]));
@@ -236,8 +259,8 @@ void hbcu_lapsharp_destroy(hbcu_lapsharp_t *h)
     if (h == nullptr) return;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    for (auto p : h->in_mem) if (p) cudaFree(p);
-    for (auto p : h->out_mem) if (p) cudaFree(p);
+    for (auto p : h->in_base) if (p) cudaFree(p);
+    for (auto p : h->out_base) if (p) cudaFree(p);
     for (auto e : h->ev_up) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_k) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_down) if (e) cudaEventDestroy(e);
@@ -249,6 +272,17 @@ void hbcu_lapsharp_destroy(hbcu_lapsharp_t *h)
     delete h;
 }
 
+// the caller's planes have exactly the device layout (back to back, reference stride): the frame is one copy
+static bool same_layout(const hbcu_lapsharp_t *h, const void *const planes[3], const int strides[3])
+{
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if ((size_t)strides[pl] != (size_t)h->g[pl].pitch * h->bps) return false;
+        if ((const uint8_t *)planes[pl] != (const uint8_t *)planes[0] + h->plane_off[pl]) return false;
+    }
+    return true;
+}
+
 int hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const in_planes[3], const int in_strides[3],
                          void *const out_planes[3], const int out_strides[3])
 {
@@ -258,7 +292,9 @@ int hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const i
     h->next = (h->next + 1) % h->slots;
     // the slot's previous frame must have left it (kernel read the input, download read the output)
     HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_k[s], 0));
-    for (int pl = 0; pl < 3; pl++)
+    const bool whole_in = same_layout(h, in_planes, in_strides);
+    if (whole_in) HBCU_CHECK(cudaMemcpyAsync(h->in_base[s], in_planes[0], h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    for (int pl = 0; pl < 3 && !whole_in; pl++)
     {
         const Geom &g = h->g[pl];
         const bool same = (size_t)in_strides[pl] == (size_t)g.pitch * h->bps;
@@ -272,13 +308,102 @@ int hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const i
         if (launch(h, pl, h->in_mem[s * 3 + pl], h->g[pl].pitch, h->out_mem[s * 3 + pl]) != 0) return -1;
     HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_k[s], 0));
-    for (int pl = 0; pl < 3; pl++)
+    const bool whole_out = same_layout(h, out_planes, out_strides);
+    if (whole_out) HBCU_CHECK(cudaMemcpyAsync(out_planes[0], h->out_base[s], h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+    for (int pl = 0; pl < 3 && !whole_out; pl++)
     {
         const Geom &g = h->g[pl];
         HBCU_CHECK(cudaMemcpy2DAsync(out_planes[pl], (size_t)out_strides[pl], h->out_mem[s * 3 + pl], (size_t)g.pitch * h->bps,
                                      (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
     }
     HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_d2h));
+    h->ticket[s] = ticket;
+    return 0;
+}
+
+static bool frame_fits(const hbcu_lapsharp_t *h, const hbcu_frame_t *f)
+{
+    if (f->device != h->cfg.device) return false;
+    for (int pl = 0; pl < 3; pl++)
+        if (f->row_bytes[pl] != h->g[pl].w * h->bps || f->rows[pl] != h->g[pl].h || f->stride[pl] != h->g[pl].pitch * h->bps) return false;
+    return true;
+}
+
+int hbcu_lapsharp_filter_frames(hbcu_lapsharp_t *h, int64_t ticket,
+                                hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                                hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
+{
+    if (h == nullptr || (in_frame == nullptr && (in_planes == nullptr || in_strides == nullptr)) ||
+        (out_frame == nullptr && (out_planes == nullptr || out_strides == nullptr)) ||
+        (in_frame && !frame_fits(h, in_frame)) || (out_frame && !frame_fits(h, out_frame)))
+    {
+        set_error("lapsharp_filter_frames: bad argument or frame geometry");
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int s = h->next;
+    h->next = (h->next + 1) % h->slots;
+    if (in_frame == nullptr)
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_k[s], 0));
+        const bool whole_in = same_layout(h, in_planes, in_strides);
+        if (whole_in) HBCU_CHECK(cudaMemcpyAsync(h->in_base[s], in_planes[0], h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        for (int pl = 0; pl < 3 && !whole_in; pl++)
+        {
+            const Geom &g = h->g[pl];
+            const bool same = (size_t)in_strides[pl] == (size_t)g.pitch * h->bps;
+            HBCU_CHECK(cudaMemcpy2DAsync(h->in_mem[s * 3 + pl], (size_t)g.pitch * h->bps, in_planes[pl], (size_t)in_strides[pl],
+                                         same ? (size_t)g.pitch * h->bps : (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        HBCU_CHECK(cudaEventRecord(h->ev_up[s], h->s_h2d));
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_up[s], 0));
+    }
+    else if (hbcu::frame_begin_read(in_frame, h->s_compute) != 0) return -1;
+    // lapsharp.c:333 mirrors the picture into the stride padding first; a device frame gets that in a private copy
+    bool staged = false;
+    if (in_frame != nullptr && h->bps == 2)
+        for (int pl = 0; pl < 3; pl++) staged = staged || h->g[pl].pitch != h->g[pl].w;
+    if (staged)
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_k[s], 0));
+        HBCU_CHECK(cudaMemcpyAsync(h->in_base[s], in_frame->base, h->frame_bytes, cudaMemcpyDeviceToDevice, h->s_compute));
+        for (int pl = 0; pl < 3; pl++)
+        {
+            const Geom &g = h->g[pl];
+            if (g.pitch == g.w) continue;
+            mirror_stride16_kernel<<<(g.h + 7) / 8, dim3(32, 8), 0, h->s_compute>>>((uint16_t *)h->in_mem[s * 3 + pl], g.w, g.h, g.pitch);
+            hbcu::count_launch();
+        }
+        HBCU_CHECK(cudaGetLastError());
+    }
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
+    if (out_frame && hbcu::frame_begin_write(out_frame, h->s_compute) != 0) return -1;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const void *src = (in_frame && !staged) ? (const void *)in_frame->plane[pl] : (const void *)h->in_mem[s * 3 + pl];
+        void *dst = out_frame ? (void *)out_frame->plane[pl] : (void *)h->out_mem[s * 3 + pl];
+        if (launch(h, pl, src, h->g[pl].pitch, dst) != 0) return -1;
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
+    if (in_frame && hbcu::frame_end_read(in_frame, h->s_compute) != 0) return -1;
+    if (out_frame)
+    {
+        if (hbcu::frame_end_write(out_frame, h->s_compute) != 0) return -1;
+        HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_compute));
+    }
+    else
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_k[s], 0));
+        const bool whole_out = same_layout(h, out_planes, out_strides);
+        if (whole_out) HBCU_CHECK(cudaMemcpyAsync(out_planes[0], h->out_base[s], h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        for (int pl = 0; pl < 3 && !whole_out; pl++)
+        {
+            const Geom &g = h->g[pl];
+            HBCU_CHECK(cudaMemcpy2DAsync(out_planes[pl], (size_t)out_strides[pl], h->out_mem[s * 3 + pl], (size_t)g.pitch * h->bps,
+                                         (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
+        }
+        HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_d2h));
+    }
     h->ticket[s] = ticket;
     return 0;
 }

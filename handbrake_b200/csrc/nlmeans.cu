@@ -24,6 +24,7 @@
 // pass; weight/pixel accumulators live in shared memory.  HBM traffic is the
 // algorithmic minimum: every input tile is read once per output tile.
 #include "hbcu_common.h"
+#include "hbcu_frames.h"
 #include "../../include/hbcu.h"
 
 #include <cstdlib>
@@ -1315,7 +1316,10 @@ struct hbcu_nlmeans_s
     PlaneGeom g[3];
     int ring, out_slots;
     std::vector<uint8_t *> ring_mem;      // [slot*3+plane] bordered planes
-    std::vector<uint8_t *> raw_mem;       // [slot*3+plane] unbordered staging (H2D target)
+    std::vector<uint8_t *> raw_base;      // [slot] one allocation per staged frame: a frame whose planes lie back to back on
+    std::vector<uint8_t *> out_base;      // [oslot] the host (hb_frame_buffer_init, fifo.c:839-881) moves as ONE copy each way
+    size_t frame_cap, plane_off[3];       // capacity of such an allocation; default plane offsets inside it
+    std::vector<uint8_t *> raw_mem;       // [slot*3+plane] unbordered staging (H2D target), default layout
     std::vector<uint8_t *> out_mem;       // [oslot*3+plane]
     std::vector<int64_t>   ring_index;    // frame index held by each slot
     std::vector<CUtensorMap> maps;        // [slot*3+plane] TMA descriptors of the bordered planes
@@ -1803,6 +1807,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         g.bbytes = (size_t)g.bpitch * g.bh * h->bps;
         g.rpitch = (g.w + 127) / 128 * 128;
         g.rbytes = (size_t)g.rpitch * g.h * h->bps;
+        h->plane_off[pl] = pl == 0 ? 0 : h->plane_off[pl - 1] + h->g[pl - 1].rbytes;
+        h->frame_cap = h->plane_off[pl] + g.rbytes;
     }
 #define CK(expr)                                                                                          \
     do {                                                                                                  \
@@ -1832,6 +1838,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ring_mem.assign(h->ring * 3, nullptr);
     h->raw_mem.assign(h->ring * 3, nullptr);
     h->out_mem.assign(h->out_slots * 3, nullptr);
+    h->raw_base.assign(h->ring, nullptr);
+    h->out_base.assign(h->out_slots, nullptr);
     h->ring_index.assign(h->ring, -1);
     h->out_index.assign(h->out_slots, -1);
     h->ev_upload.assign(h->ring, nullptr);
@@ -1846,10 +1854,11 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         CK(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_readers[2 * s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_readers[2 * s + 1], cudaEventDisableTiming));
+        CK(cudaMalloc(&h->raw_base[s], h->frame_cap));
         for (int pl = 0; pl < 3; pl++)
         {
             CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
-            CK(cudaMalloc(&h->raw_mem[s * 3 + pl], h->g[pl].rbytes));
+            h->raw_mem[s * 3 + pl] = h->raw_base[s] + h->plane_off[pl];
             const int th = h->bps == 1 ? kTH8 : 96;
             if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
                                            (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
@@ -1864,7 +1873,9 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     {
         CK(cudaEventCreateWithFlags(&h->ev_kernel[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_d2h[s], cudaEventDisableTiming));
-        for (int pl = 0; pl < 3; pl++) CK(cudaMalloc(&h->out_mem[s * 3 + pl], h->g[pl].rbytes));
+        CK(cudaMalloc(&h->out_base[s], h->frame_cap));
+        CK(cudaMemset(h->out_base[s], 0, h->frame_cap));       // stride padding is never written by the kernels
+        for (int pl = 0; pl < 3; pl++) h->out_mem[s * 3 + pl] = h->out_base[s] + h->plane_off[pl];
     }
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
@@ -1918,8 +1929,8 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
         if (h->tr_base) cudaEventDestroy(h->tr_base);
     }
     for (auto p : h->ring_mem) if (p) cudaFree(p);
-    for (auto p : h->raw_mem) if (p) cudaFree(p);
-    for (auto p : h->out_mem) if (p) cudaFree(p);
+    for (auto p : h->raw_base) if (p) cudaFree(p);
+    for (auto p : h->out_base) if (p) cudaFree(p);
     for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_readers) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_kernel) if (e) cudaEventDestroy(e);
@@ -1941,6 +1952,24 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
     delete h;
 }
 
+// Planes laid out back to back (plane p+1 starts where plane p's stride x height ends), the way hb_frame_buffer_init
+// builds a STANDARD hb_buffer_t: such a frame crosses PCIe as one copy instead of three (measured with
+// tools/copy_bench.cu, both directions busy: 0.278 vs 0.307 ms per 4K frame).
+static bool frame_is_contiguous(const hbcu_nlmeans_t *h, const void *const planes[3], const int strides[3], size_t off[3], size_t *total)
+{
+    size_t o = 0;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const PlaneGeom &g = h->g[pl];
+        if ((const uint8_t *)planes[pl] != (const uint8_t *)planes[0] + o) return false;
+        if (strides[pl] < g.w * h->bps || (strides[pl] % 16) != 0) return false;
+        off[pl] = o;
+        o += (size_t)strides[pl] * g.h;
+    }
+    *total = o;
+    return o <= h->frame_cap;
+}
+
 static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const planes[3], const int strides[3], bool from_device)
 {
     if (h == nullptr || planes == nullptr || strides == nullptr || index < 0)
@@ -1955,14 +1984,23 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
     HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_upload[slot], 0));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[2 * slot], 0));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[2 * slot + 1], 0));
+    size_t off[3] = { 0, 0, 0 }, total = 0;
+    const bool whole = !from_device && frame_is_contiguous(h, planes, strides, off, &total);
     if (!from_device)
     {
         trace(h, index, TR_H2D_BEGIN, h->s_h2d);
-        for (int pl = 0; pl < 3; pl++)
+        if (whole)
         {
-            const PlaneGeom &g = h->g[pl];
-            HBCU_CHECK(cudaMemcpy2DAsync(h->raw_mem[slot * 3 + pl], (size_t)g.rpitch * h->bps, planes[pl], (size_t)strides[pl],
-                                         (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
+            HBCU_CHECK(cudaMemcpyAsync(h->raw_base[slot], planes[0], total, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        else
+        {
+            for (int pl = 0; pl < 3; pl++)
+            {
+                const PlaneGeom &g = h->g[pl];
+                HBCU_CHECK(cudaMemcpy2DAsync(h->raw_mem[slot * 3 + pl], (size_t)g.rpitch * h->bps, planes[pl], (size_t)strides[pl],
+                                             (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyHostToDevice, h->s_h2d));
+            }
         }
         trace(h, index, TR_H2D_END, h->s_h2d);
         HBCU_CHECK(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
@@ -1975,6 +2013,10 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
         if (from_device)
         {
             if (pad_plane(h, slot, pl, planes[pl], strides[pl] / h->bps, h->s_pad) != 0) return -1;
+        }
+        else if (whole)
+        {
+            if (pad_plane(h, slot, pl, h->raw_base[slot] + off[pl], strides[pl] / h->bps, h->s_pad) != 0) return -1;
         }
         else
         {
@@ -2015,14 +2057,29 @@ int hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, void *cons
     }
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     const int oslot = (int)(index % h->out_slots);
-    if (run_filter(h, index, navail, oslot) != 0) return -1;
+    size_t off[3] = { 0, 0, 0 }, total = 0;
+    const bool whole = frame_is_contiguous(h, planes, strides, off, &total);
+    if (whole)
+    {
+        // the kernels write the output slot in the host buffer's own layout: one copy brings the frame back
+        void *dst[3] = { h->out_base[oslot] + off[0], h->out_base[oslot] + off[1], h->out_base[oslot] + off[2] };
+        if (run_filter(h, index, navail, oslot, dst, strides) != 0) return -1;
+    }
+    else if (run_filter(h, index, navail, oslot) != 0) return -1;
     HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_kernel[oslot], 0));
     trace(h, index, TR_D2H_BEGIN, h->s_d2h);
-    for (int pl = 0; pl < 3; pl++)
+    if (whole)
     {
-        const PlaneGeom &g = h->g[pl];
-        HBCU_CHECK(cudaMemcpy2DAsync(planes[pl], (size_t)strides[pl], h->out_mem[oslot * 3 + pl], (size_t)g.rpitch * h->bps,
-                                     (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
+        HBCU_CHECK(cudaMemcpyAsync(planes[0], h->out_base[oslot], total, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    else
+    {
+        for (int pl = 0; pl < 3; pl++)
+        {
+            const PlaneGeom &g = h->g[pl];
+            HBCU_CHECK(cudaMemcpy2DAsync(planes[pl], (size_t)strides[pl], h->out_mem[oslot * 3 + pl], (size_t)g.rpitch * h->bps,
+                                         (size_t)g.w * h->bps, (size_t)g.h, cudaMemcpyDeviceToHost, h->s_d2h));
+        }
     }
     trace(h, index, TR_D2H_END, h->s_d2h);
     HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_d2h));
@@ -2074,6 +2131,38 @@ int hbcu_nlmeans_filter_into(hbcu_nlmeans_t *h, int64_t index, int navail, void 
     if (run_filter(h, index, navail, oslot, dplanes, strides) != 0) return -1;
     HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_compute));
     return 0;
+}
+
+static bool frame_fits(const hbcu_nlmeans_t *h, const hbcu_frame_t *f)
+{
+    if (f == nullptr || f->device != h->cfg.device) return false;
+    for (int pl = 0; pl < 3; pl++)
+        if (f->row_bytes[pl] != h->g[pl].w * h->bps || f->rows[pl] != h->g[pl].h) return false;
+    return true;
+}
+
+int hbcu_nlmeans_upload_frame(hbcu_nlmeans_t *h, int64_t index, hbcu_frame_t *in)
+{
+    if (h == nullptr || index < 0 || !frame_fits(h, in)) { set_error("nlmeans_upload_frame: bad argument or frame geometry"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    // the border kernels are the only readers: they run on s_pad
+    if (hbcu::frame_begin_read(in, h->s_pad) != 0) return -1;
+    const void *planes[3] = { in->plane[0], in->plane[1], in->plane[2] };
+    if (upload_common(h, index, planes, in->stride, true) != 0) return -1;
+    return hbcu::frame_end_read(in, h->s_pad);
+}
+
+int hbcu_nlmeans_filter_frame(hbcu_nlmeans_t *h, int64_t index, int navail, hbcu_frame_t *out)
+{
+    if (h == nullptr || index < 0 || !frame_fits(h, out)) { set_error("nlmeans_filter_frame: bad argument or frame geometry"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int oslot = (int)(index % h->out_slots);
+    cudaStream_t st = h->s_comp[index & (h->n_comp - 1)];          // the stream run_filter() will launch on
+    if (hbcu::frame_begin_write(out, st) != 0) return -1;
+    void *planes[3] = { out->plane[0], out->plane[1], out->plane[2] };
+    if (run_filter(h, index, navail, oslot, planes, out->stride) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h[oslot], h->s_compute));  // no download: the slot is free once the kernel is done
+    return hbcu::frame_end_write(out, h->s_compute);
 }
 
 int hbcu_nlmeans_stream_wait(hbcu_nlmeans_t *h, void *cuda_stream)

@@ -76,6 +76,9 @@ enum AVPixelFormat
     AV_PIX_FMT_YUV444P10LE = 68,
     AV_PIX_FMT_YUV420P12LE = 123,
     AV_PIX_FMT_YUV420P16LE = 47,
+    /* FFmpeg's hardware pixel format for CUDA frames.  libhb signals hardware frames through
+     * hb_filter_init_t.hw_pix_fmt / job->hw_pix_fmt (nvenc_common.c:329-336); the value is only ever compared */
+    AV_PIX_FMT_CUDA        = 117,
 };
 #define AV_PIX_FMT_YUV420P10 AV_PIX_FMT_YUV420P10LE
 #define AV_PIX_FMT_YUV420P12 AV_PIX_FMT_YUV420P12LE
@@ -226,6 +229,12 @@ void hb_shim_set_frame_allocator(hb_shim_alloc_fn a, hb_shim_free_fn f);
 /* new buffers are zero-filled by default (deterministic oracle runs); libhb's own pool hands out
  * recycled memory, so throughput measurements switch this off */
 void hb_shim_set_zero_buffers(int on);
+/* HBCU_DEVICE buffers: hb_buffer_close() hands b->storage to this hook (fifo.c:1037-1083 does the same for
+ * AVFRAME / COREMEDIA storage); set by hbcu_device_frames.c */
+void hb_shim_set_device_release(void (*release)(void *storage));
+/* hb_buffer_shallow_dup()/hb_buffer_dup() of an HBCU_DEVICE buffer take another reference on the same device frame
+ * (frames are written once by their producer, then only read), like av_frame_ref for AVFRAME storage (fifo.c:718-760) */
+void hb_shim_set_device_retain(void (*retain)(void *storage));
 /* statistics used by the tests (leak check: HB_BUFFER_DEBUG analogue, fifo.c:137-278) */
 long hb_shim_buffers_alive(void);
 

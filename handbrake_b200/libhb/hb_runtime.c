@@ -198,6 +198,11 @@ static int  g_zero  = 1;   /* zero-fill new buffers (deterministic oracle); libh
 
 void hb_shim_set_zero_buffers(int on) { g_zero = on; }
 
+static void (*g_device_release)(void *) = NULL;
+void hb_shim_set_device_release(void (*release)(void *storage)) { g_device_release = release; }
+static void (*g_device_retain)(void *) = NULL;
+void hb_shim_set_device_retain(void (*retain)(void *storage)) { g_device_retain = retain; }
+
 void hb_shim_set_frame_allocator(hb_shim_alloc_fn a, hb_shim_free_fn f)
 {
     g_alloc = a;
@@ -306,7 +311,12 @@ void hb_buffer_close(hb_buffer_t **_b)
     while (b != NULL)
     {
         hb_buffer_t *next = b->next;
-        if (b->data != NULL)
+        if (b->storage_type == HBCU_DEVICE)
+        {
+            /* device frame: plane[].data are device pointers, b->data is NULL (fifo.c:1016-1034 pattern) */
+            if (b->storage != NULL && g_device_release != NULL) g_device_release(b->storage);
+        }
+        else if (b->data != NULL)
         {
             alloc_tag_t *tag = (alloc_tag_t *)(b->data - sizeof(alloc_tag_t));
             if (tag->free_fn != NULL) tag->free_fn(tag->base);
@@ -327,6 +337,20 @@ void hb_buffer_copy_props(hb_buffer_t *dst, const hb_buffer_t *src)
 hb_buffer_t *hb_buffer_dup(const hb_buffer_t *src)
 {
     if (src == NULL) return NULL;
+    if (src->storage_type == HBCU_DEVICE)
+    {
+        /* another reference on the same device frame */
+        hb_buffer_t *ref = hb_buffer_init(0);
+        if (ref == NULL || g_device_retain == NULL) { if (ref) hb_buffer_close(&ref); return NULL; }
+        ref->f = src->f;
+        hb_buffer_copy_props(ref, src);
+        memcpy(ref->plane, src->plane, sizeof(ref->plane));
+        ref->size = src->size;
+        ref->storage_type = HBCU_DEVICE;
+        ref->storage = src->storage;
+        g_device_retain(ref->storage);
+        return ref;
+    }
     hb_buffer_t *buf = hb_buffer_init(src->size);
     if (buf == NULL) return NULL;
     buf->f = src->f;

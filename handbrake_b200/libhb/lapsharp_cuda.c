@@ -9,6 +9,7 @@
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
+#include "hbcu_device_frames.h"
 #include <strings.h>
 
 #define LAPSHARP_STRENGTH_DEFAULT 0.2
@@ -28,6 +29,7 @@ struct hb_filter_private_s
     lapsharp_pending_t pending[LAPSHARP_MAX_PENDING];
     int head, count, inflight_max;
     int64_t next_ticket;
+    int device, device_out;            /* device_out: hand the output on as HBCU_DEVICE buffers (hw_pix_fmt == AV_PIX_FMT_CUDA) */
     hb_filter_init_t input, output;
 };
 
@@ -110,9 +112,9 @@ static int lapsharp_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init
     cfg.depth          = desc->comp[0].depth;
     cfg.chroma_shift_w = desc->log2_chroma_w;
     cfg.chroma_shift_h = desc->log2_chroma_h;
-    cfg.device         = 0;
-    const char *dev_env = getenv("HBCU_DEVICE");
-    if (dev_env != NULL) cfg.device = atoi(dev_env);
+    cfg.device         = hbcu_env_device();
+    pv->device         = cfg.device;
+    pv->device_out     = hbcu_init_wants_device_output(init);
     pv->inflight_max   = 6;
     cfg.slots          = pv->inflight_max + 2;
     if (hbcu_lapsharp_create(&pv->gpu, &cfg) != 0)
@@ -149,7 +151,11 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int all)
     while (pv->count > 0)
     {
         lapsharp_pending_t *p = &pv->pending[pv->head];
-        if (all || pv->count > pv->inflight_max)
+        if (hbcu_buffer_frame(p->out) != NULL && hbcu_buffer_frame(p->in) != NULL)
+        {
+            /* device in, device out: nothing for the host to wait for, the frame's events order the GPU work */
+        }
+        else if (all || pv->count > pv->inflight_max)
         {
             if (hbcu_lapsharp_wait(pv->gpu, p->ticket) != 0) goto gpu_error;
         }
@@ -188,9 +194,12 @@ static int lapsharp_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, 
         return failed ? HB_FILTER_FAILED : HB_FILTER_DONE;
     }
 
-    /* lapsharp.c:333: the stride region next to the right edge is part of the filter's input */
-    hb_frame_buffer_mirror_stride(in);
-    hb_buffer_t *out = hb_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height);
+    /* lapsharp.c:333: the stride region next to the right edge is part of the filter's input
+     * (for a device frame hbcu_lapsharp_filter_frames does the same in HBM) */
+    hbcu_frame_t *fin = hbcu_buffer_frame(in);
+    if (fin == NULL) hb_frame_buffer_mirror_stride(in);
+    hb_buffer_t *out = pv->device_out ? hbcu_device_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height, pv->device)
+                                      : hb_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height);
     if (out == NULL)
     {
         hb_buffer_close(&in);
@@ -212,7 +221,7 @@ static int lapsharp_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, 
         op[c] = out->plane[c].data; os[c] = out->plane[c].stride;
     }
     const int64_t ticket = pv->next_ticket++;
-    if (hbcu_lapsharp_filter(pv->gpu, ticket, ip, is, op, os) != 0)
+    if (hbcu_lapsharp_filter_frames(pv->gpu, ticket, fin, ip, is, hbcu_buffer_frame(out), op, os) != 0)
     {
         hb_error("lapsharp(cuda): %s", hbcu_last_error());
         hb_buffer_close(&in);

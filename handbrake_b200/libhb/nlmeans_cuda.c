@@ -21,6 +21,7 @@
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
+#include "hbcu_device_frames.h"
 
 #define NLMEANS_STRENGTH_DEFAULT    6
 #define NLMEANS_ORIGIN_TUNE_DEFAULT 1
@@ -42,6 +43,7 @@ typedef struct
 
 struct hb_filter_private_s
 {
+    int device, device_out;        /* device_out: outputs leave as HBCU_DEVICE buffers (hw_pix_fmt == AV_PIX_FMT_CUDA) */
     int depth;
     int bps;
 
@@ -287,7 +289,9 @@ static void nlmeans_cuda_close(hb_filter_object_t *filter)
 /* hand frame `index` to the GPU: kernels + download into a fresh output buffer */
 static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
 {
-    hb_buffer_t *out = hb_frame_buffer_init(pv->output.pix_fmt, pv->output.geometry.width, pv->output.geometry.height);
+    hb_buffer_t *out = pv->device_out
+        ? hbcu_device_frame_buffer_init(pv->output.pix_fmt, pv->output.geometry.width, pv->output.geometry.height, pv->device)
+        : hb_frame_buffer_init(pv->output.pix_fmt, pv->output.geometry.width, pv->output.geometry.height);
     if (out == NULL) return -1;
     out->f.color_prim      = pv->output.color_prim;
     out->f.color_transfer  = pv->output.color_transfer;
@@ -303,7 +307,9 @@ static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
         planes[c]  = out->plane[c].data;
         strides[c] = out->plane[c].stride;
     }
-    if (hbcu_nlmeans_filter(pv->gpu, p->index, navail, planes, strides) != 0)
+    const int rc = pv->device_out ? hbcu_nlmeans_filter_frame(pv->gpu, p->index, navail, hbcu_buffer_frame(out))
+                                  : hbcu_nlmeans_filter(pv->gpu, p->index, navail, planes, strides);
+    if (rc != 0)
     {
         hb_error("nlmeans(cuda): %s", hbcu_last_error());
         hb_buffer_close(&out);
@@ -338,7 +344,13 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int block_on
     {
         nlm_pending_t *p = pending_at(pv, 0);
         if (p->out == NULL) break;                           /* not enqueued yet */
-        if (block_all || block_one)
+        if (hbcu_buffer_frame(p->out) != NULL)
+        {
+            /* device output: its consumer orders itself behind the kernel through the frame's events.  A host input
+             * buffer may be released once its (asynchronous) upload has left it */
+            if (hbcu_buffer_frame(p->in) == NULL && hbcu_nlmeans_wait_upload(pv->gpu, p->index) != 0) goto gpu_error;
+        }
+        else if (block_all || block_one)
         {
             if (hbcu_nlmeans_wait(pv->gpu, p->index) != 0) goto gpu_error;
             block_one = 0;
@@ -400,7 +412,9 @@ static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
         hb_error("nlmeans(cuda): internal queue overflow");
         return HB_FILTER_FAILED;
     }
-    if (hbcu_nlmeans_upload(pv->gpu, pv->next_in, planes, strides) != 0)
+    hbcu_frame_t *fin = hbcu_buffer_frame(in);
+    if ((fin != NULL ? hbcu_nlmeans_upload_frame(pv->gpu, pv->next_in, fin)
+                     : hbcu_nlmeans_upload(pv->gpu, pv->next_in, planes, strides)) != 0)
     {
         hb_error("nlmeans(cuda): %s", hbcu_last_error());
         return HB_FILTER_FAILED;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HBCU_ABI_VERSION 1
+#define HBCU_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------- */
 /* runtime                                                                    */
@@ -47,6 +47,36 @@ void         hbcu_host_trim(void);
 int          hbcu_host_reserve(size_t bytes, int count);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t     hbcu_kernel_launches(void);
+
+/* ------------------------------------------------------------------------- */
+/* device frames: the HBCU_DEVICE backing of hb_buffer_t      */
+/*   what AVFRAME / COREMEDIA storage is to the other hardware paths           */
+/*   (handbrake/internal.h:152-153, fifo.c:1016-1034): between two CUDA        */
+/*   filters a frame stays in HBM.  A frame is one allocation, planes back to   */
+/*   back at the given strides (use hb_image_stride: the layout of a STANDARD  */
+/*   hb_buffer_t).  Frames are pooled; release never blocks -- two CUDA events */
+/*   per frame (producer done / readers done) order the streams that touch it. */
+/* ------------------------------------------------------------------------- */
+typedef struct hbcu_frame_s hbcu_frame_t;
+int    hbcu_frame_alloc(hbcu_frame_t **f, int device, const int row_bytes[3], const int rows[3], const int strides[3]);
+void   hbcu_frame_retain(hbcu_frame_t *f);             /* hb_buffer_shallow_dup(): one more reference (frames are written once) */
+void   hbcu_frame_release(hbcu_frame_t *f);            /* hb_buffer_close() of an HBCU_DEVICE buffer (fifo.c:1037-1083); pooled at the last one */
+void * hbcu_frame_plane(const hbcu_frame_t *f, int plane);      /* DEVICE pointer: never dereference on the host */
+int    hbcu_frame_stride(const hbcu_frame_t *f, int plane);
+int    hbcu_frame_device(const hbcu_frame_t *f);
+long   hbcu_frames_alive(void);                         /* handed out and not released (leak check) */
+void   hbcu_frame_trim(void);                           /* frees the pooled frames */
+/* the two ends of a device-resident chain (the role of libhb's adapter filters,
+ * platform/macosx/adapter_vt.c): host frame -> device frame in front of the first CUDA filter,
+ * device frame -> host frame in front of the encoder.  Asynchronous; `ticket`s complete in order,
+ * `depth` of them may be in flight. */
+typedef struct hbcu_xfer_s hbcu_xfer_t;
+int    hbcu_xfer_create(hbcu_xfer_t **x, int device, int depth);
+void   hbcu_xfer_destroy(hbcu_xfer_t *x);
+int    hbcu_xfer_upload(hbcu_xfer_t *x, int64_t ticket, hbcu_frame_t *f, const void *const planes[3], const int strides[3]);
+int    hbcu_xfer_download(hbcu_xfer_t *x, int64_t ticket, hbcu_frame_t *f, void *const planes[3], const int strides[3]);
+int    hbcu_xfer_wait(hbcu_xfer_t *x, int64_t ticket);
+int    hbcu_xfer_poll(hbcu_xfer_t *x, int64_t ticket);  /* 1 done, 0 running, <0 error */
 
 /* ------------------------------------------------------------------------- */
 /* NLMeans      replaces nlmeans.c:464-664 + templates/nlmeans_template.c       */
@@ -115,6 +145,10 @@ int  hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail,
  * filter's input, or a buffer an NCCL send reads): the device-resident hand-off between filters */
 int  hbcu_nlmeans_filter_into(hbcu_nlmeans_t *h, int64_t index, int navail,
                               void *const dplanes[3], const int strides[3]);
+/* device-resident chain: frame `index` arrives in / leaves in an hbcu_frame_t.  Stream-ordered against the frame's
+ * producer and readers, never blocks; the output needs no wait/poll -- its consumer orders itself behind it. */
+int  hbcu_nlmeans_upload_frame(hbcu_nlmeans_t *h, int64_t index, hbcu_frame_t *in);
+int  hbcu_nlmeans_filter_frame(hbcu_nlmeans_t *h, int64_t index, int navail, hbcu_frame_t *out);
 /* orders a caller-owned CUDA stream (passed as void*) after all work queued on the handle so far */
 int  hbcu_nlmeans_stream_wait(hbcu_nlmeans_t *h, void *cuda_stream);
 int  hbcu_nlmeans_sync(hbcu_nlmeans_t *h);
@@ -159,6 +193,7 @@ void hbcu_comb_detect_destroy(hbcu_comb_detect_t *h);
 /* luma plane of frame `index` to the device (asynchronous from pinned memory) */
 int  hbcu_comb_detect_upload(hbcu_comb_detect_t *h, int64_t index, const void *luma, int stride);
 int  hbcu_comb_detect_upload_device(hbcu_comb_detect_t *h, int64_t index, const void *dluma, int stride);
+int  hbcu_comb_detect_upload_frame(hbcu_comb_detect_t *h, int64_t index, hbcu_frame_t *in);   /* luma of a device frame */
 /* comb_segmenter (comb_detect.c:1051-1072) for frame `cur` against `prev` and `next`; asynchronous */
 int  hbcu_comb_detect_run(hbcu_comb_detect_t *h, int64_t prev, int64_t cur, int64_t next, int force_exhaustive);
 /* blocks until the verdict of frame `cur` is known: HB_COMB_NONE 0 / LIGHT 1 / HEAVY 2 */
@@ -213,6 +248,10 @@ int  hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t 
                         int frame_mode, int parity, int tff, void *const planes[3], const int strides[3]);
 int  hbcu_decomb_filter_device(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
                                int frame_mode, int parity, int tff, void *out_planes[3], int out_strides[3]);
+/* device-resident chain (see hbcu_frame_t): input frame from / output picture into a device frame, stream-ordered */
+int  hbcu_decomb_upload_frame(hbcu_decomb_t *h, int64_t index, hbcu_frame_t *in);
+int  hbcu_decomb_filter_frame(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
+                              int frame_mode, int parity, int tff, hbcu_frame_t *out);
 int  hbcu_decomb_wait(hbcu_decomb_t *h, int64_t ticket);
 int  hbcu_decomb_poll(hbcu_decomb_t *h, int64_t ticket);
 int  hbcu_decomb_sync(hbcu_decomb_t *h);
@@ -247,6 +286,10 @@ int  hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const 
 /* device-resident variant: dplanes are device pointers with the given strides, result stays on the device */
 int  hbcu_lapsharp_filter_device(hbcu_lapsharp_t *h, int64_t ticket, const void *const dplanes[3], const int strides[3],
                                  void *out_planes[3], int out_strides[3]);
+/* device-resident chain: either side may be a device frame (NULL = use the host planes / strides of that side) */
+int  hbcu_lapsharp_filter_frames(hbcu_lapsharp_t *h, int64_t ticket,
+                                 hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                                 hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3]);
 int  hbcu_lapsharp_wait(hbcu_lapsharp_t *h, int64_t ticket);
 int  hbcu_lapsharp_poll(hbcu_lapsharp_t *h, int64_t ticket);
 int  hbcu_lapsharp_sync(hbcu_lapsharp_t *h);

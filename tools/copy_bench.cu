@@ -9,19 +9,26 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
-int main()
+int main(int argc, char **argv)
 {
-    const int W = 3840, H = 2160, N = 64, NBUF = 8;
+    const int W = 3840, H = 2160;
+    const int NBUF = argc > 1 ? atoi(argv[1]) : 8;      // distinct pinned frames (working set)
+    const int N = NBUF > 64 ? NBUF : 64;
+    const int NDEV = 8;
     const size_t Y = (size_t)W * H, Cb = Y / 4, F = Y + 2 * Cb;
-    std::vector<unsigned char *> hin(NBUF), hout(NBUF), din(NBUF), dout(NBUF);
+    std::vector<unsigned char *> hin(NBUF), hout(NBUF), din(NDEV), dout(NDEV);
     for (int i = 0; i < NBUF; i++)
     {
         CK(cudaHostAlloc(&hin[i], F, cudaHostAllocDefault));
         CK(cudaHostAlloc(&hout[i], F, cudaHostAllocDefault));
-        CK(cudaMalloc(&din[i], F));
-        CK(cudaMalloc(&dout[i], F));
         for (size_t k = 0; k < F; k += 4096) hin[i][k] = (unsigned char)k;
     }
+    for (int i = 0; i < NDEV; i++)
+    {
+        CK(cudaMalloc(&din[i], F));
+        CK(cudaMalloc(&dout[i], F));
+    }
+    printf("working set: %d + %d pinned frames of %.2f MB\n", NBUF, NBUF, F / 1e6);
     cudaStream_t s_in, s_out;
     CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
@@ -29,7 +36,7 @@ int main()
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&f0)); CK(cudaEventCreate(&f1));
 
     auto copy_frame = [&](bool h2d, int i, int mode, cudaStream_t st) {
-        unsigned char *h = h2d ? hin[i] : hout[i], *d = h2d ? din[i] : dout[i];
+        unsigned char *h = h2d ? hin[i] : hout[i], *d = h2d ? din[i % NDEV] : dout[i % NDEV];
         const cudaMemcpyKind kind = h2d ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
         void *dst = h2d ? (void *)d : (void *)h;
         const void *src = h2d ? (const void *)h : (const void *)d;
