@@ -18,6 +18,7 @@
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
+#include "hbcu_device_frames.h"
 
 #define MODE_GAMMA        1
 #define MODE_FILTER       2
@@ -209,7 +210,10 @@ static void store_ref(hb_filter_private_t *pv, hb_buffer_t *b, int64_t index)
 
 static int upload_luma(hb_filter_private_t *pv, hb_buffer_t *b, int64_t index)
 {
-    if (hbcu_comb_detect_upload(pv->gpu, index, b->plane[0].data, b->plane[0].stride) != 0)
+    /* the frame itself passes through untouched, host or device; only its luma is looked at */
+    hbcu_frame_t *fin = hbcu_buffer_frame(b);
+    if ((fin != NULL ? hbcu_comb_detect_upload_frame(pv->gpu, index, fin)
+                     : hbcu_comb_detect_upload(pv->gpu, index, b->plane[0].data, b->plane[0].stride)) != 0)
     {
         hb_error("comb_detect(cuda): %s", hbcu_last_error());
         return -1;

@@ -17,6 +17,7 @@
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
+#include "hbcu_device_frames.h"
 
 #define PARITY_DEFAULT -1
 #define DECOMB_MAX_PENDING 16
@@ -29,6 +30,7 @@ typedef struct
 
 struct hb_filter_private_s
 {
+    int device, device_out;        /* device_out: pictures leave as HBCU_DEVICE buffers (hw_pix_fmt == AV_PIX_FMT_CUDA) */
     hbcu_decomb_t *gpu;
     int mode;
     int parity;
@@ -133,9 +135,9 @@ static int decomb_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     cfg.depth          = desc->comp[0].depth;
     cfg.chroma_shift_w = desc->log2_chroma_w;
     cfg.chroma_shift_h = desc->log2_chroma_h;
-    cfg.device         = 0;
-    const char *dev_env = getenv("HBCU_DEVICE");
-    if (dev_env != NULL) cfg.device = atoi(dev_env);
+    cfg.device         = hbcu_env_device();
+    pv->device         = cfg.device;
+    pv->device_out     = hbcu_init_wants_device_output(init);
     pv->inflight_max   = 6;
     cfg.slots          = 6;
     cfg.out_slots      = pv->inflight_max + 2;
@@ -182,7 +184,7 @@ static void store_ref(hb_filter_private_t *pv, hb_buffer_t *b, int64_t index)
 {
     /* the upload of a frame reads its buffer asynchronously: make sure it is over before the
      * buffer goes back to the pool (normally long done -- the frame entered three calls ago) */
-    if (pv->ref[0] != NULL && pv->ref_index[0] >= 0)
+    if (pv->ref[0] != NULL && pv->ref_index[0] >= 0 && hbcu_buffer_frame(pv->ref[0]) == NULL)
         hbcu_decomb_wait_upload(pv->gpu, pv->ref_index[0]);
     hb_buffer_close(&pv->ref[0]);
     for (int k = 0; k < 2; k++)
@@ -272,7 +274,8 @@ static int process_frame(hb_filter_private_t *pv)
         else                           pv->unfiltered++;
         pv->frames++;
 
-        hb_buffer_t *buf = hb_frame_buffer_init(cur->f.fmt, cur->f.width, cur->f.height);
+        hb_buffer_t *buf = pv->device_out ? hbcu_device_frame_buffer_init(cur->f.fmt, cur->f.width, cur->f.height, pv->device)
+                                          : hb_frame_buffer_init(cur->f.fmt, cur->f.width, cur->f.height);
         if (buf == NULL) return -1;
         buf->f.color_prim      = pv->output.color_prim;
         buf->f.color_transfer  = pv->output.color_transfer;
@@ -290,8 +293,12 @@ static int process_frame(hb_filter_private_t *pv)
         const int64_t ticket = pv->next_ticket++;
         /* `mode` keeps the bob bit: the reference tests `mode == BLEND` / `mode == CUBIC` on it
          * (decomb template :756,:776), so e.g. cubic+bob runs no line filter at all */
-        if (hbcu_decomb_filter(pv->gpu, ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2],
-                               mode, parity, tff, planes, strides) != 0)
+        const int rc = pv->device_out
+            ? hbcu_decomb_filter_frame(pv->gpu, ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2], mode, parity, tff,
+                                       hbcu_buffer_frame(buf))
+            : hbcu_decomb_filter(pv->gpu, ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2], mode, parity, tff,
+                                 planes, strides);
+        if (rc != 0)
         {
             hb_error("decomb(cuda): %s", hbcu_last_error());
             hb_buffer_close(&buf);
@@ -299,7 +306,8 @@ static int process_frame(hb_filter_private_t *pv)
         }
         hb_buffer_copy_props(buf, cur);
         made[frame] = buf;
-        push_pending(pv, buf, ticket);
+        /* a device picture needs no wait: its consumer orders itself behind the kernel through the frame's events */
+        push_pending(pv, buf, pv->device_out ? -1 : ticket);
     }
     if (pv->mode & HBCU_DECOMB_BOB)
     {
@@ -343,7 +351,8 @@ static int decomb_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, hb
         planes[c]  = in->plane[c].data;
         strides[c] = in->plane[c].stride;
     }
-    if (hbcu_decomb_upload(pv->gpu, index, planes, strides) != 0)
+    hbcu_frame_t *fin = hbcu_buffer_frame(in);
+    if ((fin != NULL ? hbcu_decomb_upload_frame(pv->gpu, index, fin) : hbcu_decomb_upload(pv->gpu, index, planes, strides)) != 0)
     {
         hb_error("decomb(cuda): %s", hbcu_last_error());
         hb_buffer_close(&in);

@@ -69,7 +69,7 @@ static void consume(hb_buffer_t *list, hb_bench_stats_t *st)
         hb_buffer_t *b = list;
         list = b->next;
         b->next = NULL;
-        if (!(b->s.flags & HB_BUF_FLAG_EOF))
+        if (!(b->s.flags & HB_BUF_FLAG_EOF) && b->storage_type != HBCU_DEVICE)
         {
             /* read the result on the host: one sample per plane row start */
             for (int p = 0; p <= b->f.max_plane; p++)

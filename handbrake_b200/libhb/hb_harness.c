@@ -77,6 +77,13 @@ static void sink(chain_t *c, hb_buffer_t *list)
         {
             io->saw_eof = 1;
         }
+        else if (b->storage_type == HBCU_DEVICE)
+        {
+            /* a device frame reached the end of the chain: the chain lacks its download adapter */
+            hb_error("harness: HBCU_DEVICE buffer at the sink (no hb_filter_hbcu_download at the end of the chain)");
+            c->failed = 1;
+            io->n_dropped++;
+        }
         else if (io->n_out < io->out_capacity)
         {
             const int i = io->n_out;

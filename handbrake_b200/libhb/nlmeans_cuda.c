@@ -260,6 +260,8 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     }
     hb_log("NLMeans (CUDA) on device %d, %d frames in flight", cfg.device, pv->inflight_max);
 
+    pv->device     = cfg.device;
+    pv->device_out = hbcu_init_wants_device_output(init);
     pv->output = *init;
     return 0;
 
