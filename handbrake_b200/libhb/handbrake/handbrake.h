@@ -444,6 +444,8 @@ extern hb_filter_object_t hb_filter_nlmeans;
 extern hb_filter_object_t hb_filter_comb_detect;
 extern hb_filter_object_t hb_filter_decomb;
 extern hb_filter_object_t hb_filter_lapsharp;
+extern hb_filter_object_t hb_filter_unsharp;
+extern hb_filter_object_t hb_filter_chroma_smooth;
 extern hb_filter_object_t hb_filter_mt_frame;
 
 #ifdef __cplusplus

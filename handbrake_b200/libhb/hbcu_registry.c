@@ -9,6 +9,8 @@ extern hb_filter_object_t hb_filter_nlmeans_cuda;
 extern hb_filter_object_t hb_filter_comb_detect_cuda;
 extern hb_filter_object_t hb_filter_decomb_cuda;
 extern hb_filter_object_t hb_filter_lapsharp_cuda;
+extern hb_filter_object_t hb_filter_unsharp_cuda;
+extern hb_filter_object_t hb_filter_chroma_smooth_cuda;
 
 hb_filter_object_t *hb_filter_get(int filter_id)
 {
@@ -18,6 +20,8 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_COMB_DETECT: return &hb_filter_comb_detect_cuda;
         case HB_FILTER_DECOMB:      return &hb_filter_decomb_cuda;
         case HB_FILTER_LAPSHARP:    return &hb_filter_lapsharp_cuda;   /* no mt_frame wrapper needed: streams */
+        case HB_FILTER_UNSHARP:     return &hb_filter_unsharp_cuda;
+        case HB_FILTER_CHROMA_SMOOTH: return &hb_filter_chroma_smooth_cuda;
         default:                return NULL;
     }
 }

@@ -296,6 +296,37 @@ int  hbcu_lapsharp_sync(hbcu_lapsharp_t *h);
 int  hbcu_lapsharp_mark(hbcu_lapsharp_t *h, int which);
 int  hbcu_lapsharp_elapsed_ms(hbcu_lapsharp_t *h, float *ms);
 
+/* ------------------------------------------------------------------------- */
+/* unsharp / chroma smooth   replaces DEF_UNSHARP_FUNC (unsharp.c:88-168) and    */
+/*              DEF_CHROMA_SMOOTH_FUNC (chroma_smooth.c:86-168), with lapsharp  */
+/*              the three clients of mt_frame_filter.c (common.c:5497-5517)     */
+/* ------------------------------------------------------------------------- */
+typedef struct hbcu_unsharp_config_s
+{
+    int width, height, depth;
+    int chroma_shift_w, chroma_shift_h;
+    int device;
+    int slots;              /* frames in flight */
+    int smooth;             /* 0 = unsharp.c, 1 = chroma_smooth.c */
+    int amount[3];          /* (int)(strength * 65536.0) per plane after the filter's sanitising; 0 copies the plane
+                             * (chroma_smooth: always 0 for luma) */
+    int steps[3];           /* size / 2 per plane, 1..7 */
+} hbcu_unsharp_config_t;
+
+typedef struct hbcu_unsharp_s hbcu_unsharp_t;
+
+int  hbcu_unsharp_create(hbcu_unsharp_t **out, const hbcu_unsharp_config_t *cfg);
+void hbcu_unsharp_destroy(hbcu_unsharp_t *h);
+/* one frame; either side may be a device frame (NULL = the host planes / strides of that side); asynchronous */
+int  hbcu_unsharp_filter_frames(hbcu_unsharp_t *h, int64_t ticket,
+                                hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                                hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3]);
+int  hbcu_unsharp_wait(hbcu_unsharp_t *h, int64_t ticket);
+int  hbcu_unsharp_poll(hbcu_unsharp_t *h, int64_t ticket);
+int  hbcu_unsharp_sync(hbcu_unsharp_t *h);
+int  hbcu_unsharp_mark(hbcu_unsharp_t *h, int which);
+int  hbcu_unsharp_elapsed_ms(hbcu_unsharp_t *h, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

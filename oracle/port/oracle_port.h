@@ -101,6 +101,14 @@ int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const
 void oracle_lapsharp_plane(const void *src, void *dst, int width, int height, int stride_src, int stride_dst,
                            int depth, int kernel_id, double strength);
 
+/* ---------------- unsharp / chroma_smooth (libhb/unsharp.c, libhb/chroma_smooth.c) ---------------- */
+/* one tightly packed plane; smooth = 0 unsharp, 1 chroma_smooth (is_chroma = 0 copies the plane) */
+void oracle_unsharp_plane(const void *src, void *dst, int w, int h, int depth, double strength, int size, int smooth, int is_chroma);
+/* n packed yuv420p frames; strength/size per plane AFTER the cascade and defaults of unsharp.c:232-260 /
+ * chroma_smooth.c:215-241 */
+void oracle_unsharp_clip(const uint8_t *in, int n, int width, int height, int depth, const double strength[3], const int size[3],
+                         int smooth, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

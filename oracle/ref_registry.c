@@ -12,6 +12,8 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_COMB_DETECT: return &hb_filter_comb_detect;
         case HB_FILTER_DECOMB:      return &hb_filter_decomb;
         case HB_FILTER_LAPSHARP:    return &hb_filter_lapsharp;
+        case HB_FILTER_UNSHARP:     return &hb_filter_unsharp;
+        case HB_FILTER_CHROMA_SMOOTH: return &hb_filter_chroma_smooth;
         case HB_FILTER_MT_FRAME:    return &hb_filter_mt_frame;
         default:                    return NULL;
     }
@@ -24,7 +26,7 @@ hb_filter_object_t *hb_filter_init(int filter_id)
     if (src == NULL) return NULL;
     hb_filter_object_t *f = malloc(sizeof(*f));
     memcpy(f, src, sizeof(*f));
-    if (filter_id == HB_FILTER_LAPSHARP)
+    if (filter_id == HB_FILTER_LAPSHARP || filter_id == HB_FILTER_UNSHARP || filter_id == HB_FILTER_CHROMA_SMOOTH)
     {
         hb_filter_object_t *wrapper = malloc(sizeof(*wrapper));
         memcpy(wrapper, &hb_filter_mt_frame, sizeof(*wrapper));
@@ -47,8 +49,16 @@ void hb_filter_close(hb_filter_object_t **pf)
 
 /* lapsharp as libhb instantiates it: wrapped in mt_frame (common.c:5497-5517).  A ready-made object
  * for the harness, which copies filter prototypes instead of calling hb_filter_init(). */
-static hb_filter_object_t lapsharp_sub;
-hb_filter_object_t hb_filter_lapsharp_mt;
+static hb_filter_object_t lapsharp_sub, unsharp_sub, chroma_smooth_sub;
+hb_filter_object_t hb_filter_lapsharp_mt, hb_filter_unsharp_mt, hb_filter_chroma_smooth_mt;
+
+static void wrap_mt(hb_filter_object_t *wrapper, hb_filter_object_t *sub, const hb_filter_object_t *src, int id)
+{
+    memcpy(sub, src, sizeof(*sub));
+    memcpy(wrapper, &hb_filter_mt_frame, sizeof(*wrapper));
+    wrapper->sub_filter = sub;
+    wrapper->id = id;
+}
 
 __attribute__((constructor)) static void build_lapsharp_mt(void)
 {
@@ -56,4 +66,6 @@ __attribute__((constructor)) static void build_lapsharp_mt(void)
     memcpy(&hb_filter_lapsharp_mt, &hb_filter_mt_frame, sizeof(hb_filter_lapsharp_mt));
     hb_filter_lapsharp_mt.sub_filter = &lapsharp_sub;
     hb_filter_lapsharp_mt.id = HB_FILTER_LAPSHARP;
+    wrap_mt(&hb_filter_unsharp_mt, &unsharp_sub, &hb_filter_unsharp, HB_FILTER_UNSHARP);
+    wrap_mt(&hb_filter_chroma_smooth_mt, &chroma_smooth_sub, &hb_filter_chroma_smooth, HB_FILTER_CHROMA_SMOOTH);
 }

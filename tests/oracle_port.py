@@ -142,3 +142,19 @@ def lapsharp_frame(self, frame, fmt_planes, depth, strengths, kernels):
 
 
 OraclePort.lapsharp_frame = lapsharp_frame
+
+
+def unsharp_clip(self, clip, w, h, depth, strength, size, smooth):
+    """libhb/unsharp.c (smooth=0) / chroma_smooth.c (smooth=1) on packed yuv420p frames; strength/size are the per-plane
+    values after the filter's cascade and defaults"""
+    self.lib.oracle_unsharp_clip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                             C.c_int, C.c_void_p]
+    clip = np.ascontiguousarray(clip, dtype=np.uint8)
+    out = np.zeros_like(clip)
+    st = (C.c_double * 3)(*strength)
+    sz = (C.c_int * 3)(*size)
+    self.lib.oracle_unsharp_clip(clip.ctypes.data, clip.shape[0], w, h, depth, st, sz, int(smooth), out.ctypes.data)
+    return out
+
+
+OraclePort.unsharp_clip = unsharp_clip
