@@ -165,6 +165,27 @@ def bind_to_gpu_numa_node(local_rank):
             return cpus
     except Exception:
         pass
+    try:
+        # containers often hide the PCI sysfs tree: `nvidia-smi topo -m` prints the same list in its "CPU Affinity" column
+        import re
+        topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=30).stdout
+        for line in topo.splitlines():
+            line = re.sub(r"\x1b\[[0-9;]*m", "", line)
+            tok = line.split()
+            if not tok or tok[0] != f"GPU{local_rank}":
+                continue
+            for t in tok[1:]:
+                if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t) and ("-" in t or "," in t):
+                    ids = set()
+                    for part in t.split(","):
+                        a, _, b = part.partition("-")
+                        ids.update(range(int(a), int(b or a) + 1))
+                    ids &= os.sched_getaffinity(0)
+                    if ids:
+                        os.sched_setaffinity(0, ids)
+                        return t
+    except Exception:
+        pass
     return None
 
 
