@@ -241,6 +241,257 @@ __global__ void __launch_bounds__(128) comb_score_kernel(const uint8_t *__restri
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Bit-packed path (default).  The combing mask is one bit per pixel: a warp evaluates 32 neighbouring pixels and
+// __ballot_sync() delivers their mask word; the whole filter chain (filter -> erode -> dilate -> erode, comb_detect.c:
+// 556-966) then runs on 32 pixels per integer instruction -- neighbours are shifted words, the "n of 8 neighbours"
+// rules a bit-sliced adder tree -- and block scores are popcounts.  Mask traffic drops from 8 bytes to 4 bits per pixel
+// and the three mask passes from ~165 us to a few us per 4K frame.
+//   bit plane layout: row y, word wx at  bits[(y + kGuard) * wpitch + 1 + wx];  kGuard zero rows above and below and one
+//   zero word left and right of every row are never written, so neighbours need no bounds checks.
+// ---------------------------------------------------------------------------
+constexpr int kGuard = 4;
+constexpr int kMaskRows = 16;                  // rows a thread marches down in the mask kernel
+
+template <typename PIX, bool GAMMA>
+__device__ __forceinline__ int comb_px(const PIX *__restrict__ prev, const PIX *__restrict__ next, const float *__restrict__ lut,
+                                       const CombParams &p, size_t i, int pu2, int pu1, int pc, int pd1, int pd2,
+                                       float gu2, float gu1, float gc, float gd1, float gd2)
+{
+    if (GAMMA)
+    {
+        const float up = __fsub_rn(gc, gu1), down = __fsub_rn(gc, gd1);
+        if (!((up > p.g_athresh && down > p.g_athresh) || (up < -p.g_athresh && down < -p.g_athresh))) return 0;
+        int motion = 0;
+        if (p.g_mthresh > 0)
+        {
+            const float qc = lut[prev[i]], nc = lut[next[i]];
+            const float qu1 = lut[prev[i - p.pitch]], qd1 = lut[prev[i + p.pitch]];
+            const float nu1 = lut[next[i - p.pitch]], nd1 = lut[next[i + p.pitch]];
+            if (fabsf(__fsub_rn(qc, gc)) > p.g_mthresh && fabsf(__fsub_rn(gu1, nu1)) > p.g_mthresh &&
+                fabsf(__fsub_rn(gd1, nd1)) > p.g_mthresh)
+                motion++;
+            if (fabsf(__fsub_rn(nc, gc)) > p.g_mthresh && fabsf(__fsub_rn(qu1, gu1)) > p.g_mthresh &&
+                fabsf(__fsub_rn(qd1, gd1)) > p.g_mthresh)
+                motion++;
+        }
+        else
+            motion = 1;
+        if (!(motion || p.force)) return 0;
+        const float lhs = __fadd_rn(__fadd_rn(gu2, __fmul_rn(4.0f, gc)), gd2);     // left to right, no contraction
+        const float rhs = __fmul_rn(3.0f, __fadd_rn(gu1, gd1));
+        return fabsf(__fsub_rn(lhs, rhs)) > p.g_athresh6;
+    }
+    const int up = pc - pu1, down = pc - pd1;
+    if (!((up > p.athresh && down > p.athresh) || (up < -p.athresh && down < -p.athresh))) return 0;
+    int motion = 0;
+    if (p.mthresh > 0)
+    {
+        const int qc = prev[i], nc = next[i];
+        const int qu1 = prev[i - p.pitch], qd1 = prev[i + p.pitch];
+        const int nu1 = next[i - p.pitch], nd1 = next[i + p.pitch];
+        if (abs(qc - pc) > p.mthresh && abs(pu1 - nu1) > p.mthresh && abs(pd1 - nd1) > p.mthresh) motion++;
+        if (abs(nc - pc) > p.mthresh && abs(qu1 - pu1) > p.mthresh && abs(qd1 - pd1) > p.mthresh) motion++;
+    }
+    else
+        motion = 1;
+    if (!(motion || p.force)) return 0;
+    if (p.spatial_metric == 0) return (abs(pc - pd2) < p.c32min) && (abs(pc - pd1) > p.c32max);
+    if (p.spatial_metric == 1) return (pu1 - pc) * (pd1 - pc) > p.athresh_sq;
+    if (p.spatial_metric == 2) return abs(pu2 + 4 * pc + pd2 - 3 * (pu1 + pd1)) > p.athresh6;
+    return 0;
+}
+
+// one warp = 32 neighbouring columns marching down kMaskRows rows: every luma sample of the current frame is read
+// once (five-row window in registers); previous / next frame only where the spatial test already fired
+template <typename PIX, bool GAMMA>
+__global__ void __launch_bounds__(256) comb_mask_bits_kernel(const PIX *__restrict__ prev, const PIX *__restrict__ cur,
+                                                            const PIX *__restrict__ next, uint32_t *__restrict__ bits,
+                                                            int wpitch, CombParams p)
+{
+    extern __shared__ float s_lut[];
+    if (GAMMA)
+    {
+        for (int i = threadIdx.x; i < p.lut_size; i += blockDim.x) s_lut[i] = p.gamma_lut[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wx = blockIdx.x * 8 + warp;
+    if (wx * 32 >= p.w) return;                               // whole warp
+    const int x = wx * 32 + lane;
+    const bool colok = x < p.w;
+    const int xc = colok ? x : p.w - 1;
+    const int y0 = blockIdx.y * kMaskRows;
+    // the whole column segment first (kMaskRows + 4 independent loads in flight), its gamma values looked up once
+    int c[kMaskRows + 4];
+    float g[kMaskRows + 4];
+#pragma unroll
+    for (int k = 0; k < kMaskRows + 4; k++)
+        c[k] = cur[(size_t)min(max(y0 - 2 + k, 0), p.h - 1) * p.pitch + xc];
+#pragma unroll
+    for (int k = 0; k < kMaskRows + 4; k++)
+        g[k] = GAMMA ? s_lut[c[k]] : 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaskRows; r++)
+    {
+        const int y = y0 + r;
+        if (y >= p.h) break;                                  // warp uniform
+        int m = 0;
+        if (colok && y >= 2 && y < p.h - 2)
+            m = comb_px<PIX, GAMMA>(prev, next, s_lut, p, (size_t)y * p.pitch + x, c[r], c[r + 1], c[r + 2], c[r + 3], c[r + 4],
+                                    g[r], g[r + 1], g[r + 2], g[r + 3], g[r + 4]);
+        const uint32_t word = __ballot_sync(0xffffffffu, m != 0);
+        if (lane == 0) bits[(size_t)(y + kGuard) * wpitch + 1 + wx] = word;
+    }
+}
+
+struct Nb { uint32_t l, c, r; };      // the words of the left / same / right pixel of every bit position
+__device__ __forceinline__ Nb neighbours(const uint32_t *row, int ci, int ncols)
+{
+    const uint32_t w = row[ci], wl = ci > 0 ? row[ci - 1] : 0u, wr = ci + 1 < ncols ? row[ci + 1] : 0u;
+    return Nb{ (w << 1) | (wl >> 31), w, (w >> 1) | (wr << 31) };
+}
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &s, uint32_t &cy)
+{
+    const uint32_t t = a ^ b;
+    s = t ^ c;
+    cy = (a & b) | (c & t);
+}
+
+constexpr int BT_W = 8, BT_R = 32;                           // tile: 8 words (256 pixels) x 32 rows, halo kGuard rows / one word
+constexpr int BS_W = BT_W + 2, BS_R = BT_R + 2 * kGuard;
+
+__device__ __forceinline__ void bits_stage(const uint32_t *src, uint32_t *dst, int op, int shrink, int wx0, int gy0, int w, int h)
+{
+    const int rows = BS_R - 2 * shrink;
+    for (int i = threadIdx.x; i < rows * BS_W; i += blockDim.x)
+    {
+        const int r = shrink + i / BS_W, ci = i % BS_W;
+        const int gy = gy0 + r, wx = wx0 + ci;
+        uint32_t v = 0;
+        if (gy >= 1 && gy <= h - 2)
+        {
+            const Nb c = neighbours(src + r * BS_W, ci, BS_W);
+            if (op == OP_CLASSIC || op == OP_HV)
+            {
+                v = c.l & c.c & c.r;
+                if (op == OP_HV) v &= src[(r - 1) * BS_W + ci] & src[(r + 1) * BS_W + ci];
+            }
+            else
+            {
+                const Nb u = neighbours(src + (r - 1) * BS_W, ci, BS_W), d = neighbours(src + (r + 1) * BS_W, ci, BS_W);
+                // bit-sliced count of the 8 neighbours
+                uint32_t s1, c1, s2, c2, b0, c4, t, c5;
+                full_add(u.l, u.c, u.r, s1, c1);
+                full_add(d.l, d.c, d.r, s2, c2);
+                const uint32_t s3 = c.l ^ c.r, c3 = c.l & c.r;
+                full_add(s1, s2, s3, b0, c4);
+                full_add(c1, c2, c3, t, c5);
+                const uint32_t b1 = t ^ c4, c6 = t & c4;
+                const uint32_t b2 = c5 ^ c6, b3 = c5 & c6;
+                (void)b0;
+                if (op == OP_ERODE) v = c.c & (b1 | b2 | b3);            // keep a set pixel with >= 2 set neighbours
+                else                v = c.c | b2 | b3;                   // set a pixel with >= 4 set neighbours
+            }
+            // columns 1 .. w-2 only
+            const int gx0 = wx * 32;
+            uint32_t vm = 0xffffffffu;
+            if (gx0 < 1) vm &= ~1u;
+            if (gx0 + 31 > w - 2) vm = (w - 2 - gx0 >= 0) ? (vm & (0xffffffffu >> (31 - (w - 2 - gx0)))) : 0u;
+            if (wx < 0) vm = 0u;
+            v &= vm;
+        }
+        dst[r * BS_W + ci] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) comb_filter_bits_kernel(const uint32_t *__restrict__ raw, uint32_t *__restrict__ out,
+                                                              int wpitch, int nwords, int w, int h, int filter_mode)
+{
+    __shared__ uint32_t a[BS_R * BS_W], b[BS_R * BS_W];
+    const int wx0 = blockIdx.x * BT_W - 1, gy0 = blockIdx.y * BT_R - kGuard;
+    for (int i = threadIdx.x; i < BS_R * BS_W; i += blockDim.x)
+    {
+        const int gy = gy0 + i / BS_W, wx = wx0 + i % BS_W;
+        a[i] = (gy >= -kGuard && gy < h + kGuard && wx >= -1 && wx <= nwords) ? raw[(size_t)(gy + kGuard) * wpitch + 1 + wx] : 0u;
+        b[i] = 0;
+    }
+    __syncthreads();
+    const uint32_t *res;
+    if (filter_mode == 1)
+    {
+        bits_stage(a, b, OP_CLASSIC, 1, wx0, gy0, w, h);
+        res = b;
+    }
+    else
+    {
+        bits_stage(a, b, OP_HV, 1, wx0, gy0, w, h);              // mask -> temp
+        if (filter_mode == 2)
+        {
+            bits_stage(b, a, OP_ERODE, 2, wx0, gy0, w, h);       // temp -> filtered
+            bits_stage(a, b, OP_DILATE, 3, wx0, gy0, w, h);      // filtered -> temp
+            bits_stage(b, a, OP_ERODE, 4, wx0, gy0, w, h);       // temp -> filtered
+            res = a;
+        }
+        else
+            res = nullptr;                                        // nothing ever writes mask_filtered: stays 0
+    }
+    for (int i = threadIdx.x; i < BT_R * BT_W; i += blockDim.x)
+    {
+        const int r = kGuard + i / BT_W, ci = 1 + i % BT_W;
+        const int gy = gy0 + r, wx = wx0 + ci;
+        if (gy < h && wx < nwords) out[(size_t)(gy + kGuard) * wpitch + 1 + wx] = res ? res[r * BS_W + ci] : 0u;
+    }
+}
+
+// block scores on a bit plane: one warp per block, a lane per row
+__global__ void __launch_bounds__(128) comb_score_bits_kernel(const uint32_t *__restrict__ bits, int wpitch, int w, int h,
+                                                             int bw, int bh, int nbx, int nby, int threshold, int filtered,
+                                                             int *__restrict__ flags)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nbx * nby) return;
+    const int x0 = (warp % nbx) * bw, y0 = (warp / nbx) * bh;
+    int score = 0;
+    for (int r = lane; r < bh; r += 32)
+    {
+        const uint32_t *row = bits + (size_t)(y0 + r + kGuard) * wpitch + 1;
+        for (int wx = x0 >> 5; wx <= (x0 + bw - 1) >> 5; wx++)
+        {
+            uint32_t v = row[wx];
+            if (!filtered)
+            {
+                // check_combing_mask (:384-454): score counts p[x-1] & p[x] & p[x+1]; at x == 0 / x == w-1 the missing side is dropped
+                uint32_t l = (v << 1) | (row[wx - 1] >> 31), rr = (v >> 1) | (row[wx + 1] << 31);
+                if (wx == 0) l |= 1u;
+                if (wx == (w - 1) >> 5) rr |= 1u << ((w - 1) & 31);
+                v &= l & rr;
+            }
+            const int lo = max(x0 - wx * 32, 0), hi = min(x0 + bw - 1 - wx * 32, 31);
+            const uint32_t m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+            score += __popc(v & m);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(0xffffffffu, score, o);
+    if (lane == 0)
+    {
+        int f = 0;
+        if (score >= threshold / 2) f |= 1;
+        if (score > threshold) f |= 2;
+        if (f) atomicOr(flags, f);
+    }
+}
+
+// test hook: bit plane -> byte mask
+__global__ void __launch_bounds__(256) comb_unpack_bits_kernel(const uint32_t *__restrict__ bits, int wpitch, uint8_t *__restrict__ mask, int mpitch, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w && y < h) mask[(size_t)y * mpitch + x] = (bits[(size_t)(y + kGuard) * wpitch + 1 + (x >> 5)] >> (x & 31)) & 1u;
+}
+
 }  // namespace
 
 struct hbcu_comb_detect_s
@@ -253,6 +504,8 @@ struct hbcu_comb_detect_s
     std::vector<int64_t> index;
     std::vector<cudaEvent_t> ev_upload, ev_readers;
     uint8_t *d_mask, *d_scored;
+    uint32_t *d_bits, *d_fbits;      // raw / filtered bit planes (bit-packed path)
+    int wpitch, nwords, use_bits;
     float *d_lut;
     int nres;
     int *d_flags;            // nres ints
@@ -298,6 +551,11 @@ int hbcu_comb_detect_create(hbcu_comb_detect_t **out, const hbcu_comb_detect_con
     h->nres = 16;
     h->next_res = 0;
     h->d_mask = h->d_scored = nullptr;
+    h->d_bits = h->d_fbits = nullptr;
+    h->nwords = (cfg->width + 31) / 32;
+    h->wpitch = h->nwords + 2;
+    h->use_bits = 1;
+    if (const char *e = getenv("HBCU_COMB_IMPL")) h->use_bits = strcmp(e, "bytes") != 0;      // A/B hook: the byte-mask kernels
     h->d_lut = nullptr;
     h->d_flags = nullptr;
     h->h_flags = nullptr;
@@ -329,6 +587,11 @@ int hbcu_comb_detect_create(hbcu_comb_detect_t **out, const hbcu_comb_detect_con
     CK(cudaMalloc(&h->d_scored, mbytes));
     CK(cudaMemset(h->d_mask, 0, mbytes));
     CK(cudaMemset(h->d_scored, 0, mbytes));
+    const size_t bbytes = (size_t)h->wpitch * (cfg->height + 2 * kGuard) * sizeof(uint32_t);
+    CK(cudaMalloc(&h->d_bits, bbytes));
+    CK(cudaMalloc(&h->d_fbits, bbytes));
+    CK(cudaMemset(h->d_bits, 0, bbytes));
+    CK(cudaMemset(h->d_fbits, 0, bbytes));
     const int lut_size = 1 << cfg->depth;
     CK(cudaMalloc(&h->d_lut, lut_size * sizeof(float)));
     CK(cudaMemcpy(h->d_lut, cfg->gamma_lut, lut_size * sizeof(float), cudaMemcpyHostToDevice));
@@ -356,6 +619,8 @@ void hbcu_comb_detect_destroy(hbcu_comb_detect_t *h)
     for (auto e : h->ev_result) if (e) cudaEventDestroy(e);
     if (h->d_mask) cudaFree(h->d_mask);
     if (h->d_scored) cudaFree(h->d_scored);
+    if (h->d_bits) cudaFree(h->d_bits);
+    if (h->d_fbits) cudaFree(h->d_fbits);
     if (h->d_lut) cudaFree(h->d_lut);
     if (h->d_flags) cudaFree(h->d_flags);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -436,49 +701,99 @@ int hbcu_comb_detect_run(hbcu_comb_detect_t *h, int64_t prev, int64_t cur, int64
     p.block_threshold = c.block_threshold; p.block_width = c.block_width; p.block_height = c.block_height;
 
     HBCU_CHECK(cudaMemsetAsync(h->d_flags + r, 0, sizeof(int), h->s_compute));
-    dim3 blk(64, 4), grid((c.width + 63) / 64, (c.height + 3) / 4);
-    const bool gamma = (c.mode & 1) != 0;
-    const size_t lut_bytes = gamma ? (size_t)p.lut_size * sizeof(float) : 0;
-    if (lut_bytes > 48 * 1024)
+    // block grid: y = k*bh while y + bh <= height; x = j*bw while x < width - bw   (comb_detect.c:238-240)
+    const int bw_ = c.block_width < c.width ? c.block_width : c.width;
+    const int bh_ = c.block_height < c.height ? c.block_height : c.height;
+    const int nby_ = c.height / bh_;
+    const int nbx_ = (c.width - bw_ + bw_ - 1) / bw_;       // number of j with j*bw < width - bw
+    if (h->use_bits)
     {
-        set_error("comb_detect: gamma table for depth %d does not fit shared memory", c.depth);
-        return -1;
-    }
-    if (h->bps == 1)
-    {
-        if (gamma) comb_mask_kernel<uint8_t, true><<<grid, blk, lut_bytes, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_mask, h->mpitch, p);
-        else       comb_mask_kernel<uint8_t, false><<<grid, blk, 0, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_mask, h->mpitch, p);
+        const bool gamma = (c.mode & 1) != 0;
+        const size_t lut_bytes = gamma ? (size_t)p.lut_size * sizeof(float) : 0;
+        if (lut_bytes > 48 * 1024)
+        {
+            set_error("comb_detect: gamma table for depth %d does not fit shared memory", c.depth);
+            return -1;
+        }
+        dim3 mgrid((h->nwords + 7) / 8, (c.height + kMaskRows - 1) / kMaskRows);
+        if (h->bps == 1)
+        {
+            if (gamma) comb_mask_bits_kernel<uint8_t, true><<<mgrid, 256, lut_bytes, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_bits, h->wpitch, p);
+            else       comb_mask_bits_kernel<uint8_t, false><<<mgrid, 256, 0, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_bits, h->wpitch, p);
+        }
+        else
+        {
+            const uint16_t *a = (const uint16_t *)pl[0], *b = (const uint16_t *)pl[1], *d = (const uint16_t *)pl[2];
+            if (gamma) comb_mask_bits_kernel<uint16_t, true><<<mgrid, 256, lut_bytes, h->s_compute>>>(a, b, d, h->d_bits, h->wpitch, p);
+            else       comb_mask_bits_kernel<uint16_t, false><<<mgrid, 256, 0, h->s_compute>>>(a, b, d, h->d_bits, h->wpitch, p);
+        }
+        hbcu::count_launch();
+        HBCU_CHECK(cudaGetLastError());
+        const bool filtered = (c.mode & 2) != 0;
+        const uint32_t *scored = h->d_bits;
+        if (filtered)
+        {
+            dim3 fgrid((h->nwords + BT_W - 1) / BT_W, (c.height + BT_R - 1) / BT_R);
+            comb_filter_bits_kernel<<<fgrid, 256, 0, h->s_compute>>>(h->d_bits, h->d_fbits, h->wpitch, h->nwords, c.width, c.height, c.filter_mode);
+            hbcu::count_launch();
+            HBCU_CHECK(cudaGetLastError());
+            scored = h->d_fbits;
+        }
+        if (nbx_ > 0 && nby_ > 0)
+        {
+            const int warps = nbx_ * nby_;
+            comb_score_bits_kernel<<<(warps * 32 + 127) / 128, 128, 0, h->s_compute>>>(scored, h->wpitch, c.width, c.height, bw_, bh_, nbx_, nby_,
+                                                                                        c.block_threshold, filtered ? 1 : 0, h->d_flags + r);
+            hbcu::count_launch();
+            HBCU_CHECK(cudaGetLastError());
+        }
     }
     else
     {
-        const uint16_t *a = (const uint16_t *)pl[0], *b = (const uint16_t *)pl[1], *d = (const uint16_t *)pl[2];
-        if (gamma) comb_mask_kernel<uint16_t, true><<<grid, blk, lut_bytes, h->s_compute>>>(a, b, d, h->d_mask, h->mpitch, p);
-        else       comb_mask_kernel<uint16_t, false><<<grid, blk, 0, h->s_compute>>>(a, b, d, h->d_mask, h->mpitch, p);
-    }
-    hbcu::count_launch();
-    HBCU_CHECK(cudaGetLastError());
-    const bool filtered = (c.mode & 2) != 0;
-    const uint8_t *scored = h->d_mask;
-    if (filtered)
-    {
-        dim3 fgrid((c.width + FT_W - 1) / FT_W, (c.height + FT_H - 1) / FT_H);
-        comb_filter_kernel<<<fgrid, 256, 0, h->s_compute>>>(h->d_mask, h->d_scored, h->mpitch, c.width, c.height, c.filter_mode);
+        dim3 blk(64, 4), grid((c.width + 63) / 64, (c.height + 3) / 4);
+        const bool gamma = (c.mode & 1) != 0;
+        const size_t lut_bytes = gamma ? (size_t)p.lut_size * sizeof(float) : 0;
+        if (lut_bytes > 48 * 1024)
+        {
+            set_error("comb_detect: gamma table for depth %d does not fit shared memory", c.depth);
+            return -1;
+        }
+        if (h->bps == 1)
+        {
+            if (gamma) comb_mask_kernel<uint8_t, true><<<grid, blk, lut_bytes, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_mask, h->mpitch, p);
+            else       comb_mask_kernel<uint8_t, false><<<grid, blk, 0, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_mask, h->mpitch, p);
+        }
+        else
+        {
+            const uint16_t *a = (const uint16_t *)pl[0], *b = (const uint16_t *)pl[1], *d = (const uint16_t *)pl[2];
+            if (gamma) comb_mask_kernel<uint16_t, true><<<grid, blk, lut_bytes, h->s_compute>>>(a, b, d, h->d_mask, h->mpitch, p);
+            else       comb_mask_kernel<uint16_t, false><<<grid, blk, 0, h->s_compute>>>(a, b, d, h->d_mask, h->mpitch, p);
+        }
         hbcu::count_launch();
         HBCU_CHECK(cudaGetLastError());
-        scored = h->d_scored;
-    }
-    // block grid: y = k*bh while y + bh <= height; x = j*bw while x < width - bw   (comb_detect.c:238-240)
-    const int bw = c.block_width < c.width ? c.block_width : c.width;
-    const int bh = c.block_height < c.height ? c.block_height : c.height;
-    const int nby = c.height / bh;
-    const int nbx = (c.width - bw + bw - 1) / bw;       // number of j with j*bw < width - bw
-    if (nbx > 0 && nby > 0)
-    {
-        const int warps = nbx * nby;
-        comb_score_kernel<<<(warps * 32 + 127) / 128, 128, 0, h->s_compute>>>(scored, h->mpitch, c.width, c.height, bw, bh, nbx, nby,
-                                                                               c.block_threshold, filtered ? 1 : 0, h->d_flags + r);
-        hbcu::count_launch();
-        HBCU_CHECK(cudaGetLastError());
+        const bool filtered = (c.mode & 2) != 0;
+        const uint8_t *scored = h->d_mask;
+        if (filtered)
+        {
+            dim3 fgrid((c.width + FT_W - 1) / FT_W, (c.height + FT_H - 1) / FT_H);
+            comb_filter_kernel<<<fgrid, 256, 0, h->s_compute>>>(h->d_mask, h->d_scored, h->mpitch, c.width, c.height, c.filter_mode);
+            hbcu::count_launch();
+            HBCU_CHECK(cudaGetLastError());
+            scored = h->d_scored;
+        }
+        // block grid: y = k*bh while y + bh <= height; x = j*bw while x < width - bw   (comb_detect.c:238-240)
+        const int bw = c.block_width < c.width ? c.block_width : c.width;
+        const int bh = c.block_height < c.height ? c.block_height : c.height;
+        const int nby = c.height / bh;
+        const int nbx = (c.width - bw + bw - 1) / bw;       // number of j with j*bw < width - bw
+        if (nbx > 0 && nby > 0)
+        {
+            const int warps = nbx * nby;
+            comb_score_kernel<<<(warps * 32 + 127) / 128, 128, 0, h->s_compute>>>(scored, h->mpitch, c.width, c.height, bw, bh, nbx, nby,
+                                                                                   c.block_threshold, filtered ? 1 : 0, h->d_flags + r);
+            hbcu::count_launch();
+            HBCU_CHECK(cudaGetLastError());
+        }
     }
     HBCU_CHECK(cudaMemcpyAsync(h->h_flags + r, h->d_flags + r, sizeof(int), cudaMemcpyDeviceToHost, h->s_compute));
     HBCU_CHECK(cudaEventRecord(h->ev_result[r], h->s_compute));
@@ -511,6 +826,16 @@ int hbcu_comb_detect_masks(hbcu_comb_detect_t *h, uint8_t *raw, uint8_t *scored)
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
     const size_t w = h->cfg.width, hh = h->cfg.height;
+    if (h->use_bits)
+    {
+        dim3 blk(64, 4), grid(((int)w + 63) / 64, ((int)hh + 3) / 4);
+        comb_unpack_bits_kernel<<<grid, blk, 0, h->s_compute>>>(h->d_bits, h->wpitch, h->d_mask, h->mpitch, (int)w, (int)hh);
+        comb_unpack_bits_kernel<<<grid, blk, 0, h->s_compute>>>((h->cfg.mode & 2) ? h->d_fbits : h->d_bits, h->wpitch, h->d_scored, h->mpitch, (int)w, (int)hh);
+        HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
+        if (raw) HBCU_CHECK(cudaMemcpy2D(raw, w, h->d_mask, h->mpitch, w, hh, cudaMemcpyDeviceToHost));
+        if (scored) HBCU_CHECK(cudaMemcpy2D(scored, w, h->d_scored, h->mpitch, w, hh, cudaMemcpyDeviceToHost));
+        return 0;
+    }
     if (raw) HBCU_CHECK(cudaMemcpy2D(raw, w, h->d_mask, h->mpitch, w, hh, cudaMemcpyDeviceToHost));
     if (scored)
         HBCU_CHECK(cudaMemcpy2D(scored, w, (h->cfg.mode & 2) ? h->d_scored : h->d_mask, h->mpitch, w, hh, cudaMemcpyDeviceToHost));

@@ -87,6 +87,107 @@ struct K            // per-depth constants
 };
 
 // ---------------------------------------------------------------------------------------------
+// 16 bytes (8 or 16 samples) per thread.  Most stencil stages only do work where the edge mask is set, and the mask is
+// sparse (edges): a thread first looks at the 16-byte vectors of the gating planes and, when no sample of its group
+// can be active, finishes with one vector copy (or nothing); only groups that contain an active sample run the
+// per-sample code -- which is the reference's arithmetic, untouched.  Rows are 16-byte aligned (64-byte strides).
+// ---------------------------------------------------------------------------------------------
+template <typename PIX> struct Vec { static constexpr int N = 16 / (int)sizeof(PIX); };
+__device__ __forceinline__ uint4 ld16(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void st16(void *p, const uint4 &v) { *reinterpret_cast<uint4 *>(p) = v; }
+template <typename PIX> __device__ __forceinline__ uint32_t splat(int v)
+{
+    return sizeof(PIX) == 1 ? (uint32_t)(v & 0xff) * 0x01010101u : (uint32_t)(v & 0xffff) * 0x00010001u;
+}
+template <typename PIX> __device__ __forceinline__ uint32_t cmpeq(uint32_t a, uint32_t b) { return sizeof(PIX) == 1 ? __vcmpeq4(a, b) : __vcmpeq2(a, b); }
+template <typename PIX> __device__ __forceinline__ bool any_eq(const uint4 &v, int val)
+{
+    const uint32_t p = splat<PIX>(val);
+    return (cmpeq<PIX>(v.x, p) | cmpeq<PIX>(v.y, p) | cmpeq<PIX>(v.z, p) | cmpeq<PIX>(v.w, p)) != 0u;
+}
+template <typename PIX> __device__ __forceinline__ bool any_ne(const uint4 &v, int val)
+{
+    const uint32_t p = splat<PIX>(val);
+    return (cmpeq<PIX>(v.x, p) & cmpeq<PIX>(v.y, p) & cmpeq<PIX>(v.z, p) & cmpeq<PIX>(v.w, p)) != 0xffffffffu;
+}
+
+// bit i set <=> sample i of the 16-byte vector equals val
+template <typename PIX> __device__ __forceinline__ uint32_t eq_bits(const uint4 &v, int val)
+{
+    const uint32_t p = splat<PIX>(val);
+    const uint32_t m[4] = { cmpeq<PIX>(v.x, p), cmpeq<PIX>(v.y, p), cmpeq<PIX>(v.z, p), cmpeq<PIX>(v.w, p) };
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        if (sizeof(PIX) == 2)
+            bits |= ((m[k] & 1u) | ((m[k] >> 15) & 2u)) << (2 * k);
+        else
+        {
+            uint32_t t = m[k] & 0x01010101u;
+            t = (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xfu;
+            bits |= t << (4 * k);
+        }
+    }
+    return bits;
+}
+// bits of the samples x0 .. x0+N-1 that lie in [lo, hi]
+template <int N> __device__ __forceinline__ uint32_t range_bits(int x0, int lo, int hi)
+{
+    const int a = max(lo - x0, 0), b = min(hi - x0, N - 1);
+    if (a > b) return 0u;
+    return (0xffffffffu >> (31 - b)) & (0xffffffffu << a);
+}
+
+// The active samples of a stage cluster along edges: a vertical edge puts them into a few lanes of a warp, a horizontal
+// one into every lane of the few warps that own that row.  Handing every thread the samples of its own group serialises
+// the first case (measured: calc_directions 3.5x slower), pooling per warp serialises the second (a warp owning a fully
+// active 256-sample row segment needs 8 rounds while the rest of the GPU idles: 218 us vs 66 us, profiles/r01m).  So
+// the whole CTA (256 threads = 4 rows x 512 samples at 16 bit) pools its active samples in shared memory and deals them
+// out one per thread.  Every thread of the CTA must call this (no early returns before it).
+constexpr int kStageThreads = 256;             // stage kernels run blocks of 64 x 4 threads
+template <int N, typename F>
+__device__ __forceinline__ void block_deal(uint32_t bits, uint16_t *list, int *warp_sums, F fn)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cnt = __popc(bits);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+    }
+    if (lane == 31) warp_sums[warp] = pre;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kStageThreads / 32; w++)
+    {
+        const int v = warp_sums[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    if (total == 0) return;                    // uniform over the CTA
+    pre += base - cnt;
+    while (bits)
+    {
+        const int j = __ffs(bits) - 1;
+        bits &= bits - 1;
+        list[pre++] = (uint16_t)(tid * N + j);
+    }
+    __syncthreads();
+    for (int k = tid; k < total; k += kStageThreads)
+    {
+        const int e = list[k], t = e / N, j = e - t * N;
+        // owner thread t = (tx, ty) of the 64 x 4 block -> its group's first sample and its row index
+        fn((int)((blockIdx.x * blockDim.x + (t % blockDim.x)) * N + j), (int)(blockIdx.y * blockDim.y + t / blockDim.x));
+    }
+}
+#define STAGE_LIST(PIX) __shared__ uint16_t list[kStageThreads * Vec<PIX>::N]; __shared__ int warp_sums[kStageThreads / 32]
+
+// ---------------------------------------------------------------------------------------------
 // copies
 // ---------------------------------------------------------------------------------------------
 // The copy-like stages move 16 bytes per thread.  Every row starts 16-byte aligned: plane bases are 64-byte
@@ -145,15 +246,9 @@ __global__ void __launch_bounds__(256) k_fill(PIX *__restrict__ dst, size_t n, i
 // setting and vthresh the laplacian setting.
 // ---------------------------------------------------------------------------------------------
 template <typename PIX>
-__global__ void k_edge_mask(PIX *__restrict__ dstp, const PIX *__restrict__ srcp, int pitch, int width, int height,
-                            int mthresh10, int lthresh, int vthresh81, int depth)
+__device__ __forceinline__ void edge_mask_eval(PIX *__restrict__ dstp, size_t o, const K<PIX> &k, int ten, int mthresh10, int lthresh, int vthresh81,
+                                               int pm, int pc, int pp, int cm, int cc, int cp, int nm, int nc, int np)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < 1 || x >= width - 1 || y < 1 || y >= height - 1) return;
-    const K<PIX> k(depth);
-    const int ten = (int)(PIX)(10 << k.shift);
-    const PIX *c = srcp + (size_t)y * pitch, *p = c - pitch, *n = c + pitch;
-    const int pm = p[x - 1], pc = p[x], pp = p[x + 1], cm = c[x - 1], cc = c[x], cp = c[x + 1], nm = n[x - 1], nc = n[x], np = n[x + 1];
     if ((iabs(pc - cc) < ten && iabs(cc - nc) < ten && iabs(pc - nc) < ten) ||
         (iabs(pm - cm) < ten && iabs(cm - nm) < ten && iabs(pm - nm) < ten &&
          iabs(pp - cp) < ten && iabs(cp - np) < ten && iabs(pp - np) < ten))
@@ -168,21 +263,63 @@ __global__ void k_edge_mask(PIX *__restrict__ dstp, const PIX *__restrict__ srcp
     const int Iy = max(max(iabs(pc - nc), iabs(pc - cc)), iabs(cc - nc)) >> s;
     if (Ix * Ix + Iy * Iy >= mthresh10)
     {
-        dstp[(size_t)y * pitch + x] = (PIX)k.peak;
+        dstp[o] = (PIX)k.peak;
         return;
     }
     const int Ixx = (cm - 2 * cc + cp) >> s;
     const int Iyy = (pc - 2 * cc + nc) >> s;
-    if (iabs(Ixx) + iabs(Iyy) >= lthresh) dstp[(size_t)y * pitch + x] = (PIX)k.peak;
+    if (iabs(Ixx) + iabs(Iyy) >= lthresh) dstp[o] = (PIX)k.peak;
+}
+
+// one thread = N samples of one row; the three source rows are read once into a register window of N + 2 samples
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_edge_mask(PIX *__restrict__ dstp, const PIX *__restrict__ srcp, int pitch, int width, int height,
+                                                   int mthresh10, int lthresh, int vthresh81, int depth)
+{
+    constexpr int N = Vec<PIX>::N;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= width || y < 1 || y >= height - 1) return;
+    const K<PIX> k(depth);
+    const int ten = (int)(PIX)(10 << k.shift);
+    const PIX *c = srcp + (size_t)y * pitch, *p = c - pitch, *n = c + pitch;
+    if (x0 + N <= width)
+    {
+        int w[3][N + 2];
+        const PIX *rows[3] = { p, c, n };
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+            const uint4 v = ld16(rows[r] + x0);
+            const uint32_t u[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                w[r][i + 1] = sizeof(PIX) == 1 ? (int)((u[i >> 2] >> (8 * (i & 3))) & 0xffu) : (int)((u[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+            w[r][0] = x0 >= 1 ? (int)rows[r][x0 - 1] : 0;
+            w[r][N + 1] = x0 + N < width ? (int)rows[r][x0 + N] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++)
+        {
+            const int x = x0 + i;
+            if (x < 1 || x >= width - 1) continue;
+            edge_mask_eval<PIX>(dstp, (size_t)y * pitch + x, k, ten, mthresh10, lthresh, vthresh81,
+                                w[0][i], w[0][i + 1], w[0][i + 2], w[1][i], w[1][i + 1], w[1][i + 2], w[2][i], w[2][i + 1], w[2][i + 2]);
+        }
+        return;
+    }
+    for (int i = 0; i < N && x0 + i < width; i++)
+    {
+        const int x = x0 + i;
+        if (x < 1 || x >= width - 1) continue;
+        edge_mask_eval<PIX>(dstp, (size_t)y * pitch + x, k, ten, mthresh10, lthresh, vthresh81,
+                            p[x - 1], p[x], p[x + 1], c[x - 1], c[x], c[x + 1], n[x - 1], n[x], n[x + 1]);
+    }
 }
 
 // erode (:259-293) / dilate (:207-247): dst = copy of src over `width`, interior rule applied
 template <typename PIX, bool DILATE>
-__global__ void k_morph(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height, int str, int depth)
+__device__ __forceinline__ int morph_px(const PIX *__restrict__ mskp, int pitch, int width, int height, int str, int peak, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= width || y >= height) return;
-    const int peak = (1 << depth) - 1;
     const PIX *c = mskp + (size_t)y * pitch;
     int v = c[x];
     if (x >= 1 && x < width - 1 && y >= 1 && y < height - 1 && (DILATE ? v == 0 : v == peak))
@@ -195,16 +332,48 @@ __global__ void k_morph(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, in
         if (DILATE) { if (count >= str) v = peak; }
         else        { if (count < str) v = 0; }
     }
-    dstp[(size_t)y * pitch + x] = (PIX)v;
+    return v;
+}
+
+template <typename PIX, bool DILATE>
+__global__ void __launch_bounds__(256) k_morph(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height, int str, int depth)
+{
+    constexpr int N = Vec<PIX>::N;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= width || y >= height) return;
+    const int peak = (1 << depth) - 1;
+    PIX *out = dstp + (size_t)y * pitch;
+    if (x0 + N <= width)
+    {
+        const PIX *c = mskp + (size_t)y * pitch + x0;
+        const uint4 cv = ld16(c);
+        bool any = false;
+        if (y >= 1 && y < height - 1)
+        {
+            if (DILATE)
+            {
+                // a clear sample is set only if set samples surround it: nothing set in the 3 x (N+2) neighbourhood -> copy
+                any = any_eq<PIX>(cv, peak) || any_eq<PIX>(ld16(c - pitch), peak) || any_eq<PIX>(ld16(c + pitch), peak);
+                if (x0 >= 1)        any = any || c[-1] == peak || c[-1 - pitch] == peak || c[-1 + pitch] == peak;
+                if (x0 + N < width) any = any || c[N] == peak || c[N - pitch] == peak || c[N + pitch] == peak;
+            }
+            else
+                any = any_eq<PIX>(cv, peak);             // only set samples can be eroded
+        }
+        if (!any)
+        {
+            st16(out + x0, cv);
+            return;
+        }
+    }
+    for (int i = 0; i < N && x0 + i < width; i++)
+        out[x0 + i] = (PIX)morph_px<PIX, DILATE>(mskp, pitch, width, height, str, peak, x0 + i, y);
 }
 
 // remove_small_gaps (:308-342)
 template <typename PIX>
-__global__ void k_gaps(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height, int depth)
+__device__ __forceinline__ int gaps_px(const PIX *__restrict__ mskp, int pitch, int width, int height, int peak, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= width || y >= height) return;
-    const int peak = (1 << depth) - 1;
     const PIX *m = mskp + (size_t)y * pitch;
     int v = m[x];
     if (y >= 1 && y < height - 1 && x >= 3 && x < width - 3)
@@ -219,19 +388,51 @@ __global__ void k_gaps(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int
                 v = peak;
         }
     }
-    dstp[(size_t)y * pitch + x] = (PIX)v;
+    return v;
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_gaps(const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height, int depth)
+{
+    constexpr int N = Vec<PIX>::N;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= width || y >= height) return;
+    const int peak = (1 << depth) - 1;
+    PIX *out = dstp + (size_t)y * pitch;
+    if (x0 + N <= width)
+    {
+        const PIX *m = mskp + (size_t)y * pitch + x0;
+        const uint4 mv = ld16(m);
+        // nothing set in the group: samples change only if set samples lie within 3 to both sides -- one non-zero
+        // neighbour within reach is enough to look closer
+        bool any = any_ne<PIX>(mv, 0);
+        if (!any && y >= 1 && y < height - 1)
+        {
+            for (int j = 1; j <= 3; j++)
+            {
+                if (x0 - j >= 0)        any = any || m[-j] != 0;
+                if (x0 + N - 1 + j < width) any = any || m[N - 1 + j] != 0;
+            }
+        }
+        if (!any)
+        {
+            st16(out + x0, mv);
+            return;
+        }
+    }
+    for (int i = 0; i < N && x0 + i < width; i++)
+        out[x0 + i] = (PIX)gaps_px<PIX>(mskp, pitch, width, height, peak, x0 + i, y);
 }
 
 // ---------------------------------------------------------------------------------------------
 // calc_directions (:358-525): dst pre-filled with peak (whole pitch); one thread per pixel
 // ---------------------------------------------------------------------------------------------
 template <typename PIX>
-__global__ void k_calc_directions(int plane, const PIX *__restrict__ mskp, const PIX *__restrict__ srcp, PIX *__restrict__ dstp,
-                                  int pitch, int width, int height, int maxd, int nt, int depth, Lim lim)
+__device__ __forceinline__ void calc_directions_px(int plane, const PIX *__restrict__ mskp, const PIX *__restrict__ srcp, PIX *__restrict__ dstp,
+                                                   int pitch, int width, int height, int maxd, int nt, int depth, const K<PIX> &k, const Lim &lim,
+                                                   int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < 1 || x >= width - 1 || y < 1 || y >= height - 1) return;
-    const K<PIX> k(depth);
+    if (x < 1 || x >= width - 1) return;
     const PIX *mc = mskp + (size_t)y * pitch, *mp = mc - pitch, *mn = mc + pitch;
     if (mc[x] != k.peak || (mc[x - 1] != k.peak && mc[x + 1] != k.peak)) return;
     const PIX *sc = srcp + (size_t)y * pitch, *sp = sc - pitch, *sn = sc + pitch, *s2p = sc - 2 * pitch, *s2n = sc + 2 * pitch;
@@ -298,6 +499,23 @@ __global__ void k_calc_directions(int plane, const PIX *__restrict__ mskp, const
     dstp[(size_t)y * pitch + x] = (PIX)out;
 }
 
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_calc_directions(int plane, const PIX *__restrict__ mskp, const PIX *__restrict__ srcp, PIX *__restrict__ dstp,
+                                                         int pitch, int width, int height, int maxd, int nt, int depth, Lim lim)
+{
+    constexpr int N = Vec<PIX>::N;
+    STAGE_LIST(PIX);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const K<PIX> k(depth);
+    uint32_t bits = 0;
+    if (y < 1 || y >= height - 1) bits = 0;
+    else if (x0 + N <= width)  bits = eq_bits<PIX>(ld16(mskp + (size_t)y * pitch + x0), k.peak) & range_bits<N>(x0, 1, width - 2);
+    else if (x0 < width)  bits = range_bits<N>(x0, 1, width - 2);
+    block_deal<N>(bits, list, warp_sums, [&](int x, int yy) {
+        calc_directions_px<PIX>(plane, mskp, srcp, dstp, pitch, width, height, maxd, nt, depth, k, lim, x, yy);   // dst keeps its peak fill elsewhere
+    });
+}
+
 // ---------------------------------------------------------------------------------------------
 // filter_dir_map (:649-709) and expand_dir_map (:722-773); also their 2x variants (:872-1011)
 //   TWOX = false: rows 1..h-2, neighbours at +-pitch
@@ -305,12 +523,9 @@ __global__ void k_calc_directions(int plane, const PIX *__restrict__ mskp, const
 //                 mask test uses rows y-1 and y+1 of the (line-doubled) edge mask
 // ---------------------------------------------------------------------------------------------
 template <typename PIX, bool EXPAND, bool TWOX>
-__global__ void k_dir_map(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
-                          int pitch, int width, int height, int field, int depth, Lim lim)
+__device__ __forceinline__ int dir_map_px(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp,
+                                          int pitch, int width, int height, int field, const K<PIX> &k, const Lim &lim, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= width || y >= height) return;
-    const K<PIX> k(depth);
     const PIX *dc = dmskp + (size_t)y * pitch;
     int v = dc[x];                                   // bit_blit: dst starts as a copy of dmsk (over width)
     const bool row_ok = TWOX ? (y >= 2 - field && y < height - 1 && ((y - (2 - field)) & 1) == 0) : (y >= 1 && y < height - 1);
@@ -379,17 +594,47 @@ __global__ void k_dir_map(const PIX *__restrict__ mskp, const PIX *__restrict__ 
             }
         }
     }
-    dstp[(size_t)y * pitch + x] = (PIX)v;
+    return v;
+}
+
+template <typename PIX, bool EXPAND, bool TWOX>
+__global__ void __launch_bounds__(256) k_dir_map(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                                 int pitch, int width, int height, int field, int depth, Lim lim)
+{
+    constexpr int N = Vec<PIX>::N;
+    STAGE_LIST(PIX);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const K<PIX> k(depth);
+    PIX *out = dstp + (size_t)y * pitch;
+    uint32_t bits = 0;
+    if (x0 < width && y < height)
+    {
+        const bool row_ok = TWOX ? (y >= 2 - field && y < height - 1 && ((y - (2 - field)) & 1) == 0) : (y >= 1 && y < height - 1);
+        if (x0 + N <= width)
+        {
+            const uint4 dv = ld16(dmskp + (size_t)y * pitch + x0);
+            st16(out + x0, dv);                               // bit_blit: dst = dmsk; active samples are overwritten below
+            if (row_ok)
+            {
+                if (TWOX) bits = eq_bits<PIX>(ld16(mskp + (size_t)(y - 1) * pitch + x0), k.peak) | eq_bits<PIX>(ld16(mskp + (size_t)(y + 1) * pitch + x0), k.peak);
+                else      bits = eq_bits<PIX>(ld16(mskp + (size_t)y * pitch + x0), k.peak);
+                if (EXPAND) bits &= eq_bits<PIX>(dv, k.peak);
+                bits &= range_bits<N>(x0, 1, width - 2);
+            }
+        }
+        else
+            bits = range_bits<N>(x0, 0, width - 1);           // ragged row end: every sample goes through the per-sample code
+    }
+    block_deal<N>(bits, list, warp_sums, [&](int x, int yy) {
+        dstp[(size_t)yy * pitch + x] = (PIX)dir_map_px<PIX, EXPAND, TWOX>(mskp, dmskp, pitch, width, height, field, k, lim, x, yy);
+    });
 }
 
 // filter_map (:538-635)
 template <typename PIX>
-__global__ void k_filter_map(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
-                             int pitch, int width, int height, int depth)
+__device__ __forceinline__ int filter_map_px(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp,
+                                             int pitch, int width, int height, const K<PIX> &k, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= width || y >= height) return;
-    const K<PIX> k(depth);
     const PIX *dc = dmskp + (size_t)y * pitch;
     int v = dc[x];
     if (y >= 1 && y < height - 1 && x >= 1 && x < width - 1 && !(dc[x] == k.peak || mskp[(size_t)y * pitch + x] != k.peak))
@@ -433,18 +678,43 @@ __global__ void k_filter_map(const PIX *__restrict__ mskp, const PIX *__restrict
         }
 #undef EEDI_BAD
     }
-    dstp[(size_t)y * pitch + x] = (PIX)v;
+    return v;
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_filter_map(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                                    int pitch, int width, int height, int depth)
+{
+    constexpr int N = Vec<PIX>::N;
+    STAGE_LIST(PIX);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const K<PIX> k(depth);
+    PIX *out = dstp + (size_t)y * pitch;
+    uint32_t bits = 0;
+    if (x0 < width && y < height)
+    {
+        if (x0 + N <= width)
+        {
+            const uint4 dv = ld16(dmskp + (size_t)y * pitch + x0);
+            st16(out + x0, dv);
+            // a sample is looked at only where the edge mask is set and a direction exists
+            if (y >= 1 && y < height - 1)
+                bits = eq_bits<PIX>(ld16(mskp + (size_t)y * pitch + x0), k.peak) & ~eq_bits<PIX>(dv, k.peak) & range_bits<N>(x0, 1, width - 2);
+        }
+        else
+            bits = range_bits<N>(x0, 0, width - 1);
+    }
+    block_deal<N>(bits, list, warp_sums, [&](int x, int yy) {
+        dstp[(size_t)yy * pitch + x] = (PIX)filter_map_px<PIX>(mskp, dmskp, pitch, width, height, k, x, yy);
+    });
 }
 
 // mark_directions_2x (:787-858): dst pre-filled with peak (whole pitch)
 template <typename PIX>
-__global__ void k_mark_directions_2x(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
-                                     int pitch, int width, int height, int tff, int depth, Lim lim)
+__device__ __forceinline__ void mark_directions_2x_px(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                                      int pitch, int width, int height, const K<PIX> &k, const Lim &lim, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = 2 - tff + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
-    if (x < 1 || x >= width - 1 || y >= height - 1) return;
-    const K<PIX> k(depth);
+    if (x < 1 || x >= width - 1) return;
     const PIX *m0 = mskp + (size_t)(y - 1) * pitch, *m1 = m0 + 2 * pitch;
     if (m0[x] != k.peak && m1[x] != k.peak) return;
     const PIX *d0 = dmskp + (size_t)(y - 1) * pitch, *d1 = d0 + 2 * pitch;
@@ -471,15 +741,33 @@ __global__ void k_mark_directions_2x(const PIX *__restrict__ mskp, const PIX *__
     dstp[(size_t)y * pitch + x] = (PIX)avg_round(sum, mid, count);
 }
 
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_mark_directions_2x(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                                            int pitch, int width, int height, int tff, int depth, Lim lim)
+{
+    constexpr int N = Vec<PIX>::N;
+    STAGE_LIST(PIX);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N;
+    const int y = 2 - tff + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    const K<PIX> k(depth);
+    uint32_t bits = 0;
+    if (y >= height - 1) bits = 0;
+    else if (x0 + N <= width)
+        bits = (eq_bits<PIX>(ld16(mskp + (size_t)(y - 1) * pitch + x0), k.peak) | eq_bits<PIX>(ld16(mskp + (size_t)(y + 1) * pitch + x0), k.peak)) &
+               range_bits<N>(x0, 1, width - 2);
+    else if (x0 < width)
+        bits = range_bits<N>(x0, 1, width - 2);
+    block_deal<N>(bits, list, warp_sums, [&](int x, int row) {
+        mark_directions_2x_px<PIX>(mskp, dmskp, dstp, pitch, width, height, k, lim, x, 2 - tff + 2 * row);   // dst keeps its peak fill elsewhere
+    });
+}
+
 // fill_gaps_2x (:1025-1132): dst already holds a copy of dmsk (k_blit); threads of one gap write identical values
 template <typename PIX>
-__global__ void k_fill_gaps_2x(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
-                               int pitch, int width, int height, int field, int depth)
+__device__ __forceinline__ void fill_gaps_2x_px(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                                int pitch, int width, int height, const K<PIX> &k, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = 2 - field + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
-    if (x < 1 || x >= width - 1 || y >= height - 1) return;
-    const K<PIX> k(depth);
+    if (x < 1 || x >= width - 1) return;
     const int eight = 8 << k.shift, twenty = 20 << k.shift, fiveHundred = 500 << k.shift;
     const PIX *dc = dmskp + (size_t)y * pitch, *dp = dc - 2 * pitch, *dn = dc + 2 * pitch;
     const PIX *mc = mskp + (size_t)(y - 1) * pitch, *mpp = mc - 2 * pitch, *mn = mc + 2 * pitch, *mnn = mn + 2 * pitch;
@@ -527,6 +815,29 @@ __global__ void k_fill_gaps_2x(const PIX *__restrict__ mskp, const PIX *__restri
     }
 }
 
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_fill_gaps_2x(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
+                                                      int pitch, int width, int height, int field, int depth)
+{
+    constexpr int N = Vec<PIX>::N;
+    STAGE_LIST(PIX);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N;
+    const int y = 2 - field + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    const K<PIX> k(depth);
+    // a gap starts at a sample without direction (peak) that lies on the (line-doubled) edge mask
+    uint32_t bits = 0;
+    if (y >= height - 1) bits = 0;
+    else if (x0 + N <= width)
+        bits = eq_bits<PIX>(ld16(dmskp + (size_t)y * pitch + x0), k.peak) &
+               (eq_bits<PIX>(ld16(mskp + (size_t)(y - 1) * pitch + x0), k.peak) | eq_bits<PIX>(ld16(mskp + (size_t)(y + 1) * pitch + x0), k.peak)) &
+               range_bits<N>(x0, 1, width - 2);
+    else if (x0 < width)
+        bits = range_bits<N>(x0, 1, width - 2);
+    block_deal<N>(bits, list, warp_sums, [&](int x, int row) {
+        fill_gaps_2x_px<PIX>(mskp, dmskp, dstp, pitch, width, height, k, x, 2 - field + 2 * row);
+    });
+}
+
 // ---------------------------------------------------------------------------------------------
 // interpolate_lattice (:1148-1335)
 //   pass A (parallel): per pixel, everything that does not depend on the rewritten dmskp[x-1]:
@@ -545,14 +856,10 @@ struct LatticeTmp            // per pixel, 8 bytes
 };
 
 template <typename PIX>
-__global__ void k_lattice_a(int plane, const PIX *__restrict__ dmskp, const PIX *__restrict__ dstp_base, const PIX *__restrict__ omsk_base,
-                            LatticeTmp *__restrict__ tmp, int pitch, int width, int height, int field, int nt, int depth, Lim lim)
+__device__ __forceinline__ void lattice_a_px(int plane, const PIX *__restrict__ dmskp, const PIX *__restrict__ dstp_base, const PIX *__restrict__ omsk_base,
+                                             LatticeTmp *__restrict__ tmp, int pitch, int width, int height, int nt, int depth,
+                                             const K<PIX> &k, const Lim &lim, int x, int y, int row)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = blockIdx.y * blockDim.y + threadIdx.y;
-    const int y = 2 - field + 2 * row;
-    if (x >= width || y >= height - 1) return;
-    const K<PIX> k(depth);
     const int three = (int)(PIX)(3 << k.shift), nine = (int)(PIX)(9 << k.shift);
     const int nt4 = (int)(PIX)((nt << (depth - 8)) * 4);
     const int nt7 = (int)(PIX)((nt << (depth - 8)) * 7);
@@ -662,6 +969,27 @@ __global__ void k_lattice_a(int plane, const PIX *__restrict__ dmskp, const PIX 
     tmp[(size_t)row * width + x] = t;
 }
 
+// Samples without a direction (dmsk == peak) take the vertical average in pass B whatever their LatticeTmp holds
+// (lat_pixel() and the final select both test cur == peak first), so such samples write nothing.
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_lattice_a(int plane, const PIX *__restrict__ dmskp, const PIX *__restrict__ dstp_base, const PIX *__restrict__ omsk_base,
+                                                   LatticeTmp *__restrict__ tmp, int pitch, int width, int height, int field, int nt, int depth, Lim lim)
+{
+    constexpr int N = Vec<PIX>::N;
+    STAGE_LIST(PIX);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y;
+    const int y = 2 - field + 2 * row;
+    const K<PIX> k(depth);
+    uint32_t bits = 0;
+    if (y >= height - 1) bits = 0;
+    else if (x0 + N <= width)  bits = ~eq_bits<PIX>(ld16(dmskp + (size_t)y * pitch + x0), k.peak) & range_bits<N>(x0, 0, width - 1);
+    else if (x0 < width)  bits = range_bits<N>(x0, 0, width - 1);
+    block_deal<N>(bits, list, warp_sums, [&](int x, int r) {
+        lattice_a_px<PIX>(plane, dmskp, dstp_base, omsk_base, tmp, pitch, width, height, nt, depth, k, lim, x, 2 - field + 2 * r, r);
+    });
+}
+
 // Pass B as a parallel scan.  Pixel x maps the rewritten mask of its left neighbour m to its own
 // rewritten mask:  f_x(m) = peak                         if cur == peak
 //                          B_x                          if |cur - dm[x+1]| <= lim          (first test cannot fire)
@@ -704,14 +1032,51 @@ __global__ void __launch_bounds__(kLatThreads) k_lattice_b(PIX *__restrict__ dms
     const PIX *up = dn - pitch, *down = dn + pitch;
     const LatticeTmp *t = tmp + (size_t)row * width;
     const int tid = threadIdx.x;
-    for (int x = tid; x < width; x += kLatThreads)
-    {
-        s_t[x] = t[x];
-        s_cur[x] = dm[x];
-    }
+    for (int x = tid; x < width; x += kLatThreads) s_cur[x] = dm[x];
     __syncthreads();
     const int chunk = (width + kLatThreads - 1) / kLatThreads;
     const int x0 = tid * chunk, x1 = min(x0 + chunk, width);
+
+    // Fast path.  A sample without direction (cur == peak) maps every incoming mask to peak, so the chain only runs
+    // inside runs of samples that have a direction, and every run starts from a known value.  When every thread's
+    // chunk contains such a reset sample no run is longer than two chunks: the thread that owns a run's first sample
+    // walks it serially.  (Textured rows with long runs take the scan below.)
+    {
+        bool full = x0 < x1;
+        for (int x = x0; x < x1 && full; ++x) full = s_cur[x] != peak;
+        if (!__syncthreads_or(full ? 1 : 0))
+        {
+            for (int x = tid; x < width; x += kLatThreads)
+                if (s_cur[x] == peak) dn[x] = (PIX)(((int)up[x] + (int)down[x] + 1) >> 1);       // mask stays peak
+            for (int x = x0; x < x1; ++x)
+            {
+                if (s_cur[x] == peak || (x > 0 && s_cur[x - 1] != peak)) continue;              // not the head of a run
+                int prev = x > 0 ? peak : (int)dm[-1];
+                for (int xx = x; xx < width && s_cur[xx] != peak; ++xx)
+                {
+                    const LatticeTmp e = t[xx];
+                    const int cur = s_cur[xx];
+                    int newm, val;
+                    if (abs(cur - prev) > (int)e.lim && e.nextfar)
+                    {
+                        val = ((int)up[xx] + (int)down[xx] + 1) >> 1;
+                        newm = neutral;
+                    }
+                    else
+                    {
+                        val = e.valB;
+                        newm = e.mskB;
+                    }
+                    dn[xx] = (PIX)val;
+                    dm[xx] = (PIX)newm;
+                    prev = newm;
+                }
+            }
+            return;
+        }
+    }
+    for (int x = tid; x < width; x += kLatThreads) s_t[x] = t[x];
+    __syncthreads();
     LatFn f{ 1, 0, 0, 0 };
     bool have = false;
     for (int x = x0; x < x1; ++x)
@@ -772,18 +1137,25 @@ __global__ void __launch_bounds__(kLatThreads) k_lattice_b(PIX *__restrict__ dms
 
 // post_process (:1349-1378)
 template <typename PIX>
-__global__ void k_post_process(const PIX *__restrict__ nmskp, const PIX *__restrict__ omskp, PIX *__restrict__ dstp,
-                               int pitch, int width, int height, int field, int depth, Lim lim)
+__global__ void __launch_bounds__(256) k_post_process(const PIX *__restrict__ nmskp, const PIX *__restrict__ omskp, PIX *__restrict__ dstp,
+                                                      int pitch, int width, int height, int field, int depth, Lim lim)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int N = Vec<PIX>::N;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N;
     const int y = 2 - field + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
-    if (x >= width || y >= height - 1) return;
+    if (x0 >= width || y >= height - 1) return;
     const K<PIX> k(depth);
-    const size_t o = (size_t)y * pitch + x;
-    const int nm = nmskp[o], om = omskp[o];
-    const int l = lim.v[iabs(nm - k.neutral) >> k.shift2];
-    if (iabs(nm - om) > l && om != k.peak && om != k.neutral)
-        dstp[o] = (PIX)(((int)dstp[o - pitch] + (int)dstp[o + pitch] + 1) >> 1);
+    // only samples whose OLD direction exists (not peak) can change
+    if (x0 + N <= width && !any_ne<PIX>(ld16(omskp + (size_t)y * pitch + x0), k.peak)) return;
+    for (int i = 0; i < N && x0 + i < width; i++)
+    {
+        const int x = x0 + i;
+        const size_t o = (size_t)y * pitch + x;
+        const int nm = nmskp[o], om = omskp[o];
+        const int l = lim.v[iabs(nm - k.neutral) >> k.shift2];
+        if (iabs(nm - om) > l && om != k.peak && om != k.neutral)
+            dstp[o] = (PIX)(((int)dstp[o - pitch] + (int)dstp[o + pitch] + 1) >> 1);
+    }
 }
 
 }  // namespace
@@ -816,6 +1188,8 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     PIX *dst2p = F(DST2PF), *tmp2p2 = F(TMP2PF2), *msk2p = F(MSK2PF), *tmp2p = F(TMP2PF), *dst2mp = F(DST2MPF);
     const dim3 blk(64, 4);
     auto grid2 = [&](int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); };
+    const int vn = 16 / (int)sizeof(PIX);                         // samples per thread of the vector-gated stages
+    auto gridv = [&](int w, int h) { return dim3(((w + vn - 1) / vn + 63) / 64, (h + 3) / 4); };
     const dim3 rowblk(64, 4);                                    // 16-byte chunks x rows
     const int epc = 16 / (int)sizeof(PIX);
     auto gridrows = [&](int w, int rows) { return dim3(((w + epc - 1) / epc + 63) / 64, (rows + 3) / 4); };
@@ -833,12 +1207,12 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
 
     // edge mask: top half cleared, bottom half keeps the previous field's mask (:132)
     if (e->stop_after == 0 || launches < e->stop_after) cudaMemsetAsync(mskp, 0, (size_t)(hh / 2) * pitch * sizeof(PIX), st);
-    LAUNCH((k_edge_mask<PIX><<<grid2(width, hh), blk, 0, st>>>(mskp, srcp, pitch, width, hh, c.mthresh * 10, c.vthresh /* lthresh <- variance */,
+    LAUNCH((k_edge_mask<PIX><<<gridv(width, hh), blk, 0, st>>>(mskp, srcp, pitch, width, hh, c.mthresh * 10, c.vthresh /* lthresh <- variance */,
                                                               c.lthresh * 81 /* vthresh <- laplacian */, depth)));
-    LAUNCH((k_morph<PIX, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, pitch, width, hh, c.estr, depth)));
-    LAUNCH((k_morph<PIX, true><<<grid2(width, hh), blk, 0, st>>>(tmpp, mskp, pitch, width, hh, c.dstr, depth)));
-    LAUNCH((k_morph<PIX, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, pitch, width, hh, c.estr, depth)));
-    LAUNCH((k_gaps<PIX><<<grid2(width, hh), blk, 0, st>>>(tmpp, mskp, pitch, width, hh, depth)));
+    LAUNCH((k_morph<PIX, false><<<gridv(width, hh), blk, 0, st>>>(mskp, tmpp, pitch, width, hh, c.estr, depth)));
+    LAUNCH((k_morph<PIX, true><<<gridv(width, hh), blk, 0, st>>>(tmpp, mskp, pitch, width, hh, c.dstr, depth)));
+    LAUNCH((k_morph<PIX, false><<<gridv(width, hh), blk, 0, st>>>(mskp, tmpp, pitch, width, hh, c.estr, depth)));
+    LAUNCH((k_gaps<PIX><<<gridv(width, hh), blk, 0, st>>>(tmpp, mskp, pitch, width, hh, depth)));
 
     // direction mask
     const int peak = (1 << depth) - 1;
@@ -846,10 +1220,10 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
         const size_t n = (size_t)pitch * hh;
         LAUNCH((k_fill<PIX><<<(unsigned)((n / epc + 255) / 256), 256, 0, st>>>(tmpp, n, peak)));
     }
-    LAUNCH((k_calc_directions<PIX><<<grid2(width, hh), blk, 0, st>>>(pl, mskp, srcp, tmpp, pitch, width, hh, c.maxd, c.nt, depth, e->lim)));
-    LAUNCH((k_dir_map<PIX, false, false><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, 0, depth, e->lim)));
-    LAUNCH((k_dir_map<PIX, true, false><<<grid2(width, hh), blk, 0, st>>>(mskp, dstp, tmpp, pitch, width, hh, 0, depth, e->lim)));
-    LAUNCH((k_filter_map<PIX><<<grid2(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, depth)));
+    LAUNCH((k_calc_directions<PIX><<<gridv(width, hh), blk, 0, st>>>(pl, mskp, srcp, tmpp, pitch, width, hh, c.maxd, c.nt, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, false, false><<<gridv(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, 0, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, true, false><<<gridv(width, hh), blk, 0, st>>>(mskp, dstp, tmpp, pitch, width, hh, 0, depth, e->lim)));
+    LAUNCH((k_filter_map<PIX><<<gridv(width, hh), blk, 0, st>>>(mskp, tmpp, dstp, pitch, width, hh, depth)));
 
     // upscale 2x vertically (whole strides)
     LAUNCH((k_upscale2<PIX><<<gridrows(pitch, hh), rowblk, 0, st>>>(srcp, dst2p, pitch, hh)));
@@ -862,26 +1236,26 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
         const size_t n = (size_t)pitch * height;
         LAUNCH((k_fill<PIX><<<(unsigned)((n / epc + 255) / 256), 256, 0, st>>>(tmp2p, n, peak)));
     }
-    LAUNCH((k_mark_directions_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, tmp2p2, tmp2p, pitch, width, height, tff, depth, e->lim)));
-    LAUNCH((k_dir_map<PIX, false, true><<<grid2(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
-    LAUNCH((k_dir_map<PIX, true, true><<<grid2(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
+    LAUNCH((k_mark_directions_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, tmp2p2, tmp2p, pitch, width, height, tff, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, false, true><<<gridv(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
+    LAUNCH((k_dir_map<PIX, true, true><<<gridv(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
     LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(tmp2p, dst2mp, pitch, width, height)));
-    LAUNCH((k_fill_gaps_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth)));
+    LAUNCH((k_fill_gaps_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth)));
     LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(dst2mp, tmp2p, pitch, width, height)));
-    LAUNCH((k_fill_gaps_2x<PIX><<<grid2(width, rows2), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth)));
+    LAUNCH((k_fill_gaps_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth)));
 
     // interpolate the missing lines (:1148-1335): first copy one border row, then the two passes
     if (tff == 1) LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + (size_t)(height - 2) * pitch, dst2p + (size_t)(height - 1) * pitch, pitch, width, 1)));
     else          LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + pitch, dst2p, pitch, width, 1)));
-    LAUNCH((k_lattice_a<PIX><<<grid2(width, rows2), blk, 0, st>>>(pl, tmp2p, dst2p, tmp2p2, e->lattice_tmp, pitch, width, height, tff, c.nt, depth, e->lim)));
+    LAUNCH((k_lattice_a<PIX><<<gridv(width, rows2), blk, 0, st>>>(pl, tmp2p, dst2p, tmp2p2, e->lattice_tmp, pitch, width, height, tff, c.nt, depth, e->lim)));
     LAUNCH((k_lattice_b<PIX><<<rows2, kLatThreads, (size_t)width * (sizeof(LatticeTmp) + 2 * sizeof(int)), st>>>(tmp2p, dst2p, e->lattice_tmp, pitch, width, height, tff, depth)));
 
     if (c.pp == 1 || c.pp == 3)
     {
         LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(tmp2p, tmp2p2, pitch, width, height)));
-        LAUNCH((k_dir_map<PIX, false, true><<<grid2(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
-        LAUNCH((k_dir_map<PIX, true, true><<<grid2(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
-        LAUNCH((k_post_process<PIX><<<grid2(width, rows2), blk, 0, st>>>(tmp2p, tmp2p2, dst2p, pitch, width, height, tff, depth, e->lim)));
+        LAUNCH((k_dir_map<PIX, false, true><<<gridv(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
+        LAUNCH((k_dir_map<PIX, true, true><<<gridv(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
+        LAUNCH((k_post_process<PIX><<<gridv(width, rows2), blk, 0, st>>>(tmp2p, tmp2p2, dst2p, pitch, width, height, tff, depth, e->lim)));
     }
 #undef LAUNCH
     hbcu::count_launch(launches);

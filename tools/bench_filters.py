@@ -151,6 +151,62 @@ def main():
         return r
     jobs.append(("4k_lapsharp", lapsharp_job))
 
+    def unsharp_job(name, smooth, settings, ref_name, desc):
+        depth = 8; fmt = fmt_of(depth)
+        fb = synth.frame_bytes(fmt, W, H)
+        host = np.stack([synth.progressive_frame(fmt, W, H, t) for t in range(4)])
+        core.hbcu_host_reserve(fb + 4096, 3 * n + 24)
+
+        class UnsharpConfig(C.Structure):
+            _fields_ = [("width", C.c_int), ("height", C.c_int), ("depth", C.c_int), ("chroma_shift_w", C.c_int), ("chroma_shift_h", C.c_int),
+                        ("device", C.c_int), ("slots", C.c_int), ("smooth", C.c_int), ("amount", C.c_int * 3), ("steps", C.c_int * 3)]
+
+        class Frame(C.Structure):
+            pass
+
+        # kernel-only: device frames in, device frames out (the device-resident chain's view of the filter)
+        amount = (C.c_int * 3)(0 if smooth else 16384, 16384, 16384)        # strength 0.25 (defaults); chroma_smooth copies luma
+        cfg = UnsharpConfig(W, H, depth, 1, 1, 0, 8, int(smooth), amount, (C.c_int * 3)(3, 3, 3))
+        h = C.c_void_p(); ck(core.hbcu_unsharp_create(C.byref(h), C.byref(cfg)))
+        dims = synth.plane_dims(W, H)
+        rb = (C.c_int * 3)(*[d[0] for d in dims]); rows = (C.c_int * 3)(*[d[1] for d in dims]); st = (C.c_int * 3)(*[d[0] for d in dims])
+        core.hbcu_frame_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        core.hbcu_frame_plane.restype = C.c_void_p
+        core.hbcu_frame_plane.argtypes = [C.c_void_p, C.c_int]
+        core.hbcu_frame_release.argtypes = [C.c_void_p]
+        core.hbcu_unsharp_filter_frames.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        fin, fout = [], []
+        x = C.c_void_p(); ck(core.hbcu_xfer_create(C.byref(x), 0, 8))
+        core.hbcu_xfer_upload.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        core.hbcu_xfer_wait.argtypes = [C.c_void_p, C.c_int64]
+        core.hbcu_xfer_destroy.argtypes = [C.c_void_p]
+        for i in range(16):                                              # 16 x 12.4 MB in + out > L2
+            a, b = C.c_void_p(), C.c_void_p()
+            ck(core.hbcu_frame_alloc(C.byref(a), 0, rb, rows, st)); ck(core.hbcu_frame_alloc(C.byref(b), 0, rb, rows, st))
+            base = host[i % 4].ctypes.data
+            offs = [0, dims[0][0] * dims[0][1], dims[0][0] * dims[0][1] + dims[1][0] * dims[1][1]]
+            planes = (C.c_void_p * 3)(*[base + o for o in offs])
+            ck(core.hbcu_xfer_upload(x, i, a, planes, st)); ck(core.hbcu_xfer_wait(x, i))
+            fin.append(a); fout.append(b)
+        core.hbcu_xfer_destroy(x)
+        for i in range(8):
+            ck(core.hbcu_unsharp_filter_frames(h, i, fin[i % 16], None, None, fout[i % 16], None, None))
+        ck(core.hbcu_unsharp_sync(h)); ck(core.hbcu_unsharp_mark(h, 0))
+        for i in range(n):
+            ck(core.hbcu_unsharp_filter_frames(h, 100 + i, fin[i % 16], None, None, fout[i % 16], None, None))
+        ck(core.hbcu_unsharp_mark(h, 1))
+        ms = C.c_float(); ck(core.hbcu_unsharp_elapsed_ms(h, C.byref(ms)))
+        core.hbcu_unsharp_destroy(h)
+        for f in fin + fout: core.hbcu_frame_release(f)
+        alg = 2 * fb * n
+        r = {"workload": name, "desc": desc, "value": round(n / (ms.value / 1e3), 1), "unit": "frames/s",
+             "roofline": {"bound": "hbm", "achieved": round(alg / (ms.value / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(alg / (ms.value / 1e3) / 1e9 / peak, 4), "algorithmic_bytes_per_output": 2 * fb, "peak_source": peak_src}}
+        r.update(e2e_and_cpu(flt, ref, f"hb_filter_{ref_name}_cuda", f"hb_filter_{ref_name}_mt", settings, fmt, host, n, max(args.cpu_frames, 16)))
+        return r
+    jobs.append(("4k_unsharp", lambda: unsharp_job("4k_unsharp", False, None, "unsharp", "3840x2160 yuv420p 8-bit, unsharp defaults (0.25, size 7)")))
+    jobs.append(("4k_chroma_smooth", lambda: unsharp_job("4k_chroma_smooth", True, None, "chroma_smooth", "3840x2160 yuv420p 8-bit, chroma_smooth defaults (0.25, size 7)")))
+
     def comb_job():
         depth = 10; fmt = fmt_of(depth)
         host = np.stack([synth.interlaced_frame(fmt, W, H, t) for t in range(4)])
