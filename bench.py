@@ -66,7 +66,7 @@ class BenchStats(C.Structure):
 class NlmPlane(C.Structure):
     _fields_ = [("patch_size", C.c_int), ("range", C.c_int), ("nframes", C.c_int), ("bypass", C.c_int),
                 ("origin_tune", C.c_double), ("weight_fact", C.c_float), ("diff_max", C.c_int),
-                ("exptable", C.c_float * 128)]
+                ("exptable", C.c_float * 128), ("prefilter", C.c_int)]
 
 
 class NlmConfig(C.Structure):

@@ -1173,6 +1173,13 @@ struct Eedi2
     LatticeTmp *lattice_tmp;
     Lim lim;
     int stop_after;                // debug: number of stage launches to run per plane (0 = all); HBCU_EEDI2_STOP
+    // HBCU_EEDI2_TIMING=1: CUDA-event pair around every stage launch, per-stage totals printed at destroy (warm,
+    // in-pipeline times; an ncu launch list gives cold, serialised ones)
+    int timing;
+    cudaEvent_t tev[2];
+    double stage_ms[3][40];
+    const char *stage_name[40];
+    long stage_calls;
 };
 
 namespace {
@@ -1194,7 +1201,11 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     const int epc = 16 / (int)sizeof(PIX);
     auto gridrows = [&](int w, int rows) { return dim3(((w + epc - 1) / epc + 63) / 64, (rows + 3) / 4); };
     int launches = 0;
-#define LAUNCH(...) do { if (e->stop_after == 0 || launches < e->stop_after) { __VA_ARGS__; } ++launches; } while (0)
+#define LAUNCH(...) do { if (e->stop_after == 0 || launches < e->stop_after) {                                        \
+        if (e->timing && launches < 40) { cudaEventRecord(e->tev[0], st); __VA_ARGS__; cudaEventRecord(e->tev[1], st);    \
+            cudaEventSynchronize(e->tev[1]); float ms_ = 0.f; cudaEventElapsedTime(&ms_, e->tev[0], e->tev[1]);          \
+            e->stage_ms[pl][launches] += ms_; e->stage_name[launches] = #__VA_ARGS__; }                                  \
+        else { __VA_ARGS__; } } ++launches; } while (0)
 
     if ((uintptr_t)cur_plane % 16)
     {
@@ -1303,6 +1314,12 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
     e->lattice_tmp = nullptr;
     e->stop_after = 0;
     if (const char *sa = getenv("HBCU_EEDI2_STOP")) e->stop_after = atoi(sa);   // test hook: stage-by-stage parity
+    e->timing = getenv("HBCU_EEDI2_TIMING") != nullptr;
+    e->tev[0] = e->tev[1] = nullptr;
+    memset(e->stage_ms, 0, sizeof(e->stage_ms));
+    memset(e->stage_name, 0, sizeof(e->stage_name));
+    e->stage_calls = 0;
+    if (e->timing) { cudaEventCreate(&e->tev[0]); cudaEventCreate(&e->tev[1]); }
     // field buffers are frames of height frame_height/2 (decomb.c:291-296): chroma rounds up from that
     e->half_h[0] = cfg.half_frame_height;
     e->half_h[1] = e->half_h[2] = -((-cfg.half_frame_height) >> cfg.chroma_shift_h);
@@ -1364,6 +1381,23 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
 void eedi2_destroy(Eedi2 *e)
 {
     if (e == nullptr) return;
+    if (e->timing && e->stage_calls > 0)
+    {
+        double tot = 0;
+        for (int i = 0; i < 40; i++) tot += e->stage_ms[0][i] + e->stage_ms[1][i] + e->stage_ms[2][i];
+        fprintf(stderr, "eedi2 stage times over %ld fields (us per field: luma / cb / cr), total %.1f us per field\n", e->stage_calls, 1e3 * tot / e->stage_calls);
+        for (int i = 0; i < 40; i++)
+        {
+            if (e->stage_name[i] == nullptr) continue;
+            char name[40];
+            snprintf(name, sizeof(name), "%s", e->stage_name[i] + 1);
+            for (char *c = name; *c; c++) if (*c == '<' && c[1] == '<') { *c = 0; break; }
+            fprintf(stderr, "  %2d %-34s %8.1f %8.1f %8.1f\n", i, name, 1e3 * e->stage_ms[0][i] / e->stage_calls, 1e3 * e->stage_ms[1][i] / e->stage_calls,
+                    1e3 * e->stage_ms[2][i] / e->stage_calls);
+        }
+    }
+    if (e->tev[0]) cudaEventDestroy(e->tev[0]);
+    if (e->tev[1]) cudaEventDestroy(e->tev[1]);
     for (int k = 0; k < 4; k++) if (e->half_mem[k]) cudaFree(e->half_mem[k]);
     for (int k = 0; k < 5; k++) if (e->full_mem[k]) cudaFree(e->full_mem[k]);
     if (e->lattice_tmp) cudaFree(e->lattice_tmp);
@@ -1372,6 +1406,7 @@ void eedi2_destroy(Eedi2 *e)
 
 int eedi2_run(Eedi2 *e, const void *const planes[3], int tff, cudaStream_t st)
 {
+    e->stage_calls++;
     for (int pl = 0; pl < 3; pl++)
     {
         const int rc = e->bps == 1 ? run_plane<uint8_t>(e, pl, (const uint8_t *)planes[pl], tff, st)

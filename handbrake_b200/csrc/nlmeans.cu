@@ -64,6 +64,9 @@ constexpr unsigned kFast16HighBits = 0xFC00FC00u;
 struct KernelParams
 {
     const void *planes[kMaxFrames];   // bordered plane base pointers, frame f = current + f
+    const void *pre[kMaxFrames];      // prefiltered planes the patch distances are taken from (== planes[] without prefilter)
+    const void *src_pre;              // source-patch image: pre[0], or planes[0] where the reference's pointer is stale
+    int   use_pre;                    // prefiltered planes in use: only the generic kernel reads them
     int   nf;
     int   w, h;                       // plane size
     int   bpitch;                     // bordered plane pitch in elements
@@ -149,6 +152,76 @@ __global__ void copy_plane_kernel(const PIX *__restrict__ src, int spitch, int w
 }
 
 // ---------------------------------------------------------------------------
+// nlmeans_prefilter (templates/nlmeans_template.c:103-543): the pre-denoised image the patch distances are taken
+// from.  One thread per picture sample; src/pre point at sample (0,0) of the bordered planes (the mirror border is
+// real data, 16 >= 2 samples wide).  The border of `pre` is rebuilt afterwards by pad_mirror_kernel.
+//   mean   : pixel_2 sum times the double 1/size^2, truncated (:115-129)
+//   median : the sorting networks of :135-198 return the true median
+//   csm    : min / max of the neighbours -- but the reference leaves the row loop with `goto end` after its first sample
+//            and at the origin (:253-266), so column -size/2 contributes one sample and the centre column only the
+//            samples above the origin; reproduced
+//   reduce : (wet * pre + dry * src) / (wet + dry) (:510-526)
+// edgeboost (:325-426) decides in raster order (every cleared mask sample changes the counts after it): not here.
+// ---------------------------------------------------------------------------
+template <typename PIX>
+__global__ void __launch_bounds__(256) prefilter_kernel(const PIX *__restrict__ src, PIX *__restrict__ pre, int bpitch, int w, int h, int filter_type)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int kind = (filter_type & (16 | 32)) ? 2 : (filter_type & (4 | 8)) ? 1 : 0;
+    const int size = kind == 2 ? ((filter_type & 32) ? 5 : 3) : kind == 1 ? ((filter_type & 8) ? 5 : 3) : ((filter_type & 2) ? 5 : 3);
+    const int lo = -((size - 1) / 2), hi = (size + 1) / 2;
+    const PIX *c = src + (ptrdiff_t)y * bpitch + x;
+    const int cv = *c;
+    int out = cv;
+    if (kind == 0)
+    {
+        unsigned sum = 0;
+        for (int k = lo; k < hi; k++)
+            for (int j = lo; j < hi; j++) sum += c[(ptrdiff_t)j * bpitch + k];
+        out = (int)__double2uint_rz(__dmul_rn((double)sum, 1.0 / (double)(size * size)));
+    }
+    else if (kind == 1)
+    {
+        int v[25], n = 0;
+        for (int k = lo; k < hi; k++)
+            for (int j = lo; j < hi; j++) v[n++] = c[(ptrdiff_t)j * bpitch + k];
+        // rank selection: the median is the sample with exactly n/2 samples ordered before it (ties broken by position)
+        const int half = n >> 1;
+        for (int i = 0; i < n; i++)
+        {
+            int rank = 0;
+            for (int q = 0; q < n; q++) rank += (v[q] < v[i]) || (v[q] == v[i] && q < i);
+            if (rank == half) out = v[i];
+        }
+    }
+    else
+    {
+        int mn = c[(ptrdiff_t)lo * bpitch + lo], mx = mn;
+        for (int k = lo + 1; k < hi; k++)
+            for (int j = lo; j < hi; j++)
+            {
+                if (k == 0 && j == 0) break;
+                const int pv = c[(ptrdiff_t)j * bpitch + k];
+                mn = min(mn, pv);
+                mx = max(mx, pv);
+            }
+        const int median = (mn + mx) / 2;
+        const int mn2 = (mn + median) / 2, mx2 = (mx + median) / 2;
+        const int mn3 = (mn2 + median) / 2, mx3 = (mx2 + median) / 2;
+        if (cv < mn) out = mn; else if (cv > mx) out = mx;
+        else if (cv < mn2) out = mn2; else if (cv > mx2) out = mx2;
+        else if (cv < mn3) out = mn3; else if (cv > mx3) out = mx3;
+    }
+    int wet = 1, dry = 0;
+    if ((filter_type & 512) && (filter_type & 256)) { wet = 1; dry = 3; }
+    else if (filter_type & 512) { wet = 1; dry = 1; }
+    else if (filter_type & 256) { wet = 3; dry = 1; }
+    if (dry > 0) out = (wet * (int)(PIX)out + dry * cv) / (wet + dry);
+    pre[(ptrdiff_t)y * bpitch + x] = (PIX)out;
+}
+
+// ---------------------------------------------------------------------------
 // shared numeric pieces
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void add_origin(float &ws, float &ps, double ot, int src)
@@ -194,10 +267,12 @@ __global__ void nlmeans_generic_kernel(KernelParams p)
     const int bp = p.bpitch;
     const size_t org = (size_t)kBorder * bp + kBorder;
     const PIX *src = (const PIX *)p.planes[0] + org;
+    const PIX *src_pre = (const PIX *)p.src_pre + org;
     float ws = 0.f, ps = 0.f;
     for (int f = 0; f < p.nf; f++)
     {
         const PIX *cmp = (const PIX *)p.planes[f] + org;
+        const PIX *cmp_pre = (const PIX *)p.pre[f] + org;
         for (int dy = -p.r_half; dy <= p.r_half; dy++)
         {
             for (int dx = -p.r_half; dx <= p.r_half; dx++)
@@ -210,8 +285,8 @@ __global__ void nlmeans_generic_kernel(KernelParams p)
                 unsigned ssd = 0;
                 for (int j = -p.n_half; j <= p.n_half; j++)
                 {
-                    const PIX *a = src + (ptrdiff_t)(y + j) * bp + x;
-                    const PIX *b = cmp + (ptrdiff_t)(y + j + dy) * bp + x + dx;
+                    const PIX *a = src_pre + (ptrdiff_t)(y + j) * bp + x;
+                    const PIX *b = cmp_pre + (ptrdiff_t)(y + j + dy) * bp + x + dx;
                     for (int k = -p.n_half; k <= p.n_half; k++)
                     {
                         const int d = (int)a[k] - (int)b[k];
@@ -1316,6 +1391,8 @@ struct hbcu_nlmeans_s
     PlaneGeom g[3];
     int ring, out_slots;
     std::vector<uint8_t *> ring_mem;      // [slot*3+plane] bordered planes
+    std::vector<uint8_t *> pre_mem;       // [slot*3+plane] prefiltered bordered planes (planes whose prefilter mode has a filter bit)
+    bool has_pre[3];
     std::vector<uint8_t *> raw_base;      // [slot] one allocation per staged frame: a frame whose planes lie back to back on
     std::vector<uint8_t *> out_base;      // [oslot] the host (hb_frame_buffer_init, fifo.c:839-881) moves as ONE copy each way
     size_t frame_cap, plane_off[3];       // capacity of such an allocation; default plane offsets inside it
@@ -1473,7 +1550,7 @@ int launch_tiled_nh(const TiledParams &kp, cudaStream_t st)
 
 bool tiled_supported(const KernelParams &kp)
 {
-    return kp.n_half >= 1 && kp.n_half <= 4 && kp.n_half + kp.r_half <= kHalo && kp.nf <= kMaxTiledFrames;
+    return !kp.use_pre && kp.n_half >= 1 && kp.n_half <= 4 && kp.n_half + kp.r_half <= kHalo && kp.nf <= kMaxTiledFrames;
 }
 
 bool fast8_ok(const hbcu_nlmeans_s *h, const KernelParams &kp)
@@ -1613,11 +1690,14 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
             return -1;
         }
         const int slot0 = (int)(index % h->ring);
-        if (pp.bypass)
+        const bool passthru = (pp.prefilter & 2048) != 0;
+        if (pp.bypass || passthru)
         {
-            // nlmeans_deborder (template :45-67): plane passes through untouched
+            // nlmeans_deborder (template :45-67): plane passes through untouched -- or, with the passthru bit, the
+            // prefiltered image IS the output and NLMeans does not run (nlmeans.c:485-491; tested before strength == 0)
             dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
-            const uint8_t *src = h->ring_mem[slot0 * 3 + pl] + ((size_t)kBorder * g.bpitch + kBorder) * h->bps;
+            const uint8_t *plane0 = (passthru && h->has_pre[pl]) ? h->pre_mem[slot0 * 3 + pl] : h->ring_mem[slot0 * 3 + pl];
+            const uint8_t *src = plane0 + ((size_t)kBorder * g.bpitch + kBorder) * h->bps;
             if (h->bps == 1) copy_plane_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(src, g.bpitch, g.w, g.h, dst, dpitch);
             else copy_plane_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.bpitch, g.w, g.h, (uint16_t *)dst, dpitch);
             hbcu::count_launch();
@@ -1632,7 +1712,12 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
             const int slot = (int)((index + f) % h->ring);
             slots[pl][f] = slot;
             kp.planes[f] = h->ring_mem[slot * 3 + pl];
+            kp.pre[f]    = h->has_pre[pl] ? h->pre_mem[slot * 3 + pl] : h->ring_mem[slot * 3 + pl];
         }
+        kp.use_pre = h->has_pre[pl] ? 1 : 0;
+        // nlmeans_plane reads frame[0].image_pre before it prefilters frame 0 (template :612 vs :628): a frame that was
+        // never a compare frame of an earlier output contributes its UNFILTERED image as the source patch
+        kp.src_pre = (h->has_pre[pl] && index >= 1 && pp.nframes >= 2) ? kp.pre[0] : kp.planes[0];
         kp.w = g.w;
         kp.h = g.h;
         kp.bpitch = g.bpitch;
@@ -1771,6 +1856,11 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
             set_error("nlmeans_create: plane %d has invalid patch/range/frames %d/%d/%d", pl, pp.patch_size, pp.range, pp.nframes);
             return -1;
         }
+        if ((pp.prefilter & 1024) && (pp.prefilter & 63))
+        {
+            set_error("nlmeans_create: plane %d: prefilter %d asks for edgeboost, which is decided in raster order and not implemented", pl, pp.prefilter);
+            return -1;
+        }
         if (pp.patch_size / 2 + pp.range / 2 > kBorder)
         {
             // the reference reads outside its 16-pixel border here (undefined behaviour); refuse instead
@@ -1836,6 +1926,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     CK(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
     CK(cudaStreamCreateWithPriority(&h->s_d2h, cudaStreamNonBlocking, prio_hi));
     h->ring_mem.assign(h->ring * 3, nullptr);
+    h->pre_mem.assign(h->ring * 3, nullptr);
+    for (int pl = 0; pl < 3; pl++) h->has_pre[pl] = (cfg->plane[pl].prefilter & 63) != 0;
     h->raw_mem.assign(h->ring * 3, nullptr);
     h->out_mem.assign(h->out_slots * 3, nullptr);
     h->raw_base.assign(h->ring, nullptr);
@@ -1858,6 +1950,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         for (int pl = 0; pl < 3; pl++)
         {
             CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
+            if (h->has_pre[pl]) CK(cudaMalloc(&h->pre_mem[s * 3 + pl], h->g[pl].bbytes));
             h->raw_mem[s * 3 + pl] = h->raw_base[s] + h->plane_off[pl];
             const int th = h->bps == 1 ? kTH8 : 96;
             if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
@@ -1929,6 +2022,7 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
         if (h->tr_base) cudaEventDestroy(h->tr_base);
     }
     for (auto p : h->ring_mem) if (p) cudaFree(p);
+    for (auto p : h->pre_mem) if (p) cudaFree(p);
     for (auto p : h->raw_base) if (p) cudaFree(p);
     for (auto p : h->out_base) if (p) cudaFree(p);
     for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
@@ -2022,6 +2116,29 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
         {
             if (pad_plane(h, slot, pl, h->raw_mem[slot * 3 + pl], g.rpitch, h->s_pad) != 0) return -1;
         }
+    }
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (!h->has_pre[pl]) continue;
+        // nlmeans_prefilter (template :428-543): filtered copy of the picture, then its own mirror border
+        const PlaneGeom &g = h->g[pl];
+        const size_t org = ((size_t)kBorder * g.bpitch + kBorder) * h->bps;
+        const uint8_t *srcb = h->ring_mem[slot * 3 + pl] + org;
+        uint8_t *preb = h->pre_mem[slot * 3 + pl];
+        dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4), bgrid((g.bw + 63) / 64, (g.bh + 3) / 4);
+        const int ft = h->cfg.plane[pl].prefilter;
+        if (h->bps == 1)
+        {
+            prefilter_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, preb + org, g.bpitch, g.w, g.h, ft);
+            pad_mirror_kernel<uint8_t><<<bgrid, blk, 0, h->s_pad>>>(preb + org, g.bpitch, g.w, g.h, preb, g.bpitch, kBorder, nullptr);
+        }
+        else
+        {
+            prefilter_kernel<uint16_t><<<grid, blk, 0, h->s_pad>>>((const uint16_t *)srcb, (uint16_t *)(preb + org), g.bpitch, g.w, g.h, ft);
+            pad_mirror_kernel<uint16_t><<<bgrid, blk, 0, h->s_pad>>>((const uint16_t *)(preb + org), g.bpitch, g.w, g.h, (uint16_t *)preb, g.bpitch, kBorder, nullptr);
+        }
+        hbcu::count_launch(2);
+        HBCU_CHECK(cudaGetLastError());
     }
     trace(h, index, TR_PAD_END, h->s_pad);
     HBCU_CHECK(cudaEventRecord(h->ev_upload[slot], h->s_pad));

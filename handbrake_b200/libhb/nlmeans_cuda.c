@@ -15,9 +15,9 @@
  * finished frames are handed downstream in order.  Burst sizes therefore
  * differ from the reference (which emits `threads` frames at a time); output
  * order and content do not.  The `threads` setting is accepted and sizes the
- * number of frames kept in flight.  Prefilter modes (nlmeans.c:72-83) are not
- * implemented yet: init() fails for prefilter != 0, so libhb drops the filter
- * instead of silently producing different pictures.
+ * number of frames kept in flight.  The prefilter modes (nlmeans.c:72-83) run on
+ * the GPU too, except the edgeboost bit (a raster-order recurrence): init() fails
+ * for it, so libhb drops the filter instead of silently producing different pictures.
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
@@ -195,6 +195,7 @@ int hb_nlmeans_cuda_build_config(const hb_dict_t *dict, int pix_fmt, int width, 
         pp->nframes     = nframes[c];
         pp->origin_tune = origin_tune[c];
         pp->bypass      = strength[c] == 0;   /* nlmeans.c:493-499 */
+        pp->prefilter   = prefilter[c];
         if (prefilter_out) prefilter_out[c] = prefilter[c];
     }
     cfg->width          = width;
@@ -231,9 +232,10 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     pv->bps   = pv->depth > 8 ? 2 : 1;
     for (int c = 0; c < 3; c++)
     {
-        if (pv->prefilter[c] != 0)
+        if ((pv->prefilter[c] & 1024) && (pv->prefilter[c] & 63))
         {
-            hb_error("nlmeans(cuda): prefilter mode %d is not implemented on the GPU path", pv->prefilter[c]);
+            /* edgeboost clears false positives in raster order: every decision depends on the ones before it */
+            hb_error("nlmeans(cuda): prefilter mode %d (edgeboost) is not implemented on the GPU path", pv->prefilter[c]);
             goto fail;
         }
     }

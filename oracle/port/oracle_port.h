@@ -27,7 +27,12 @@ typedef struct
     int    patch_size;
     int    range;
     int    nframes;
+    int    prefilter;     /* nlmeans.c:72-83 bit mask (mean 1/2, median 4/8, csm 16/32, reduce 256/512, edgeboost 1024, passthru 2048) */
 } oracle_nlmeans_plane_params_t;
+
+/* templates/nlmeans_template.c:103-543: the pre-denoised image the patch distances are taken from.  src, pre: w*h samples,
+ * tightly packed.  Returns 1 when `pre` was produced, 0 when the mode has no filter bit (image_pre == image). */
+int oracle_nlmeans_prefilter(const void *src, int w, int h, int depth, int filter_type, void *pre);
 
 /* nlmeans.c:343-358: derived weight table for one plane */
 void oracle_nlmeans_table(double strength, int patch_size, int depth,

@@ -10,7 +10,7 @@ PORT_SO = REPO / "oracle" / "_ref" / "liboracle_port.so"
 
 class PlaneParams(C.Structure):
     _fields_ = [("strength", C.c_double), ("origin_tune", C.c_double),
-                ("patch_size", C.c_int), ("range", C.c_int), ("nframes", C.c_int)]
+                ("patch_size", C.c_int), ("range", C.c_int), ("nframes", C.c_int), ("prefilter", C.c_int)]
 
 
 class OraclePort:
@@ -28,7 +28,7 @@ class OraclePort:
         for c in range(3):
             d = params[c]
             pp[c] = PlaneParams(d.get("strength", 6), d.get("origin_tune", 1), d.get("patch_size", 7),
-                                d.get("range", 3), d.get("nframes", 2))
+                                d.get("range", 3), d.get("nframes", 2), d.get("prefilter", 0))
         rc = self.lib.oracle_nlmeans_clip(clip.ctypes.data, clip.shape[0], width, height, depth, pp, out.ctypes.data)
         assert rc == 0
         return out

@@ -75,12 +75,26 @@ def test_fewer_frames_than_window(ref, cuda_filters):
     assert_same(r, g)
 
 
-def test_prefilter_is_refused(cuda_filters):
+def test_edgeboost_prefilter_is_refused(cuda_filters):
+    """edgeboost clears false positives in raster order (a serial recurrence): init fails, libhb drops the filter"""
     w, h = 160, 96
     clip = synth.progressive_clip(FMT8, w, h, 2)
-    g = cuda_filters.run("hb_filter_nlmeans_cuda", "y-strength=6:y-prefilter=1", clip, FMT8, w, h)
+    g = cuda_filters.run("hb_filter_nlmeans_cuda", "y-strength=6:y-prefilter=1025", clip, FMT8, w, h)
     assert g.init_failed == 1          # filter dropped, frames pass through untouched (work.c:1861-1868)
     assert np.array_equal(g.frames, clip)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 4, 8, 16, 32, 1 + 256, 2 + 512, 4 + 256 + 512, 2049, 2048 + 8 + 512, 2048, 256, 1024])
+@pytest.mark.parametrize("fmt", [FMT8, FMT10])
+def test_prefilter_modes(ref, cuda_filters, mode, fmt):
+    """mean / median / csm prefilters (3x3, 5x5), reduce 25/50/75, passthru, the no-op modes; chroma inherits luma.
+    The reference with threads=1: with more workers it races on frame[0].image_pre."""
+    w, h = 200, 120
+    clip = synth.progressive_clip(fmt, w, h, 4, seed=81)
+    s = f"y-strength=6:y-patch-size=5:y-range=3:y-frame-count=2:cb-frame-count=1:y-prefilter={mode}"
+    r = ref.run("hb_filter_nlmeans", s + ":threads=1", clip, fmt, w, h)
+    g = cuda_filters.run("hb_filter_nlmeans_cuda", s, clip, fmt, w, h)
+    assert_same(r, g)
 
 
 @pytest.mark.parametrize("impl", ["1", "3"])
