@@ -37,6 +37,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace hbcu {
 
@@ -183,6 +184,51 @@ __device__ __forceinline__ void block_deal(uint32_t bits, uint16_t *list, int *w
         const int e = list[k], t = e / N, j = e - t * N;
         // owner thread t = (tx, ty) of the 64 x 4 block -> its group's first sample and its row index
         fn((int)((blockIdx.x * blockDim.x + (t % blockDim.x)) * N + j), (int)(blockIdx.y * blockDim.y + t / blockDim.x));
+    }
+}
+// Same pooling, but every active sample is handed to G neighbouring lanes (a stage whose per-sample work is a long
+// loop splits the loop over them).  fn(x, row, sub, valid) is called by EVERY thread in every round -- it may use
+// warp shuffles inside groups of G lanes; valid == false means "no sample this round, touch no memory".
+template <int N, int G, typename F>
+__device__ __forceinline__ void block_deal_groups(uint32_t bits, uint16_t *list, int *warp_sums, F fn)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cnt = __popc(bits);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+    }
+    if (lane == 31) warp_sums[warp] = pre;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kStageThreads / 32; w++)
+    {
+        const int v = warp_sums[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    if (total == 0) return;                    // uniform over the CTA
+    pre += base - cnt;
+    while (bits)
+    {
+        const int j = __ffs(bits) - 1;
+        bits &= bits - 1;
+        list[pre++] = (uint16_t)(tid * N + j);
+    }
+    __syncthreads();
+    constexpr int per_round = kStageThreads / G;
+    const int rounds = (total + per_round - 1) / per_round;
+    for (int r = 0; r < rounds; r++)
+    {
+        const int kk = r * per_round + tid / G;
+        const bool valid = kk < total;
+        const int e = valid ? (int)list[kk] : 0, t = e / N, j = e - t * N;
+        fn((int)((blockIdx.x * blockDim.x + (t % blockDim.x)) * N + j), (int)(blockIdx.y * blockDim.y + t / blockDim.x), tid % G, valid);
     }
 }
 #define STAGE_LIST(PIX) __shared__ uint16_t list[kStageThreads * Vec<PIX>::N]; __shared__ int warp_sums[kStageThreads / 32]
@@ -427,58 +473,81 @@ __global__ void __launch_bounds__(256) k_gaps(const PIX *__restrict__ mskp, PIX 
 // ---------------------------------------------------------------------------------------------
 // calc_directions (:358-525): dst pre-filled with peak (whole pitch); one thread per pixel
 // ---------------------------------------------------------------------------------------------
+// The direction search of one sample is split over G neighbouring lanes (lane `sub` takes u = startu + sub, + G, ...):
+// every family keeps the FIRST u that reaches its minimum (strict <), i.e. the lexicographic minimum of (difference, u),
+// so the lanes' partial results combine with a butterfly of (min, dir) pairs.  Called by every lane of the warp.
+constexpr int kDirLanes = 8;
+__device__ __forceinline__ void dir_combine(int &mn, int &dir)
+{
+#pragma unroll
+    for (int o = 1; o < kDirLanes; o <<= 1)
+    {
+        const int om = __shfl_xor_sync(0xffffffffu, mn, o), od = __shfl_xor_sync(0xffffffffu, dir, o);
+        if (om < mn || (om == mn && od < dir)) { mn = om; dir = od; }     // equal minima: both valid (lower u wins) or both -5000
+    }
+}
+
 template <typename PIX>
 __device__ __forceinline__ void calc_directions_px(int plane, const PIX *__restrict__ mskp, const PIX *__restrict__ srcp, PIX *__restrict__ dstp,
                                                    int pitch, int width, int height, int maxd, int nt, int depth, const K<PIX> &k, const Lim &lim,
-                                                   int x, int y)
+                                                   int x, int y, int sub, bool valid)
 {
-    if (x < 1 || x >= width - 1) return;
     const PIX *mc = mskp + (size_t)y * pitch, *mp = mc - pitch, *mn = mc + pitch;
-    if (mc[x] != k.peak || (mc[x - 1] != k.peak && mc[x + 1] != k.peak)) return;
+    const bool active = valid && x >= 1 && x < width - 1 && mc[x] == k.peak && (mc[x - 1] == k.peak || mc[x + 1] == k.peak);
     const PIX *sc = srcp + (size_t)y * pitch, *sp = sc - pitch, *sn = sc + pitch, *s2p = sc - 2 * pitch, *s2n = sc + 2 * pitch;
     const int nt13 = (int)(PIX)((nt << (depth - 8)) * 13);
     const int nt19 = (int)(PIX)((nt << (depth - 8)) * 19);
-    const int maxdt = plane == 0 ? maxd : (maxd >> 1);
-    const int startu = max(-x + 1, -maxdt), stopu = min(width - 2 - x, maxdt);
-    const int base = iabs((int)sc[x] - (int)sn[x]) + iabs((int)sc[x] - (int)sp[x]);
-    int minb = min(nt13, base * 6), mina = min(nt19, base * 9);
-    int minc = mina, mind = minb, mine = minb;
+    int minb = 0, mina = 0, minc = 0, mind = 0, mine = 0;
     int dira = -5000, dirb = -5000, dirc = -5000, dird = -5000, dire = -5000;
-    const int c0 = sc[x - 1], c1 = sc[x], c2 = sc[x + 1];
-    const int p0 = sp[x - 1], p1 = sp[x], p2 = sp[x + 1];
-    const int n0 = sn[x - 1], n1 = sn[x], n2 = sn[x + 1];
-    for (int u = startu; u <= stopu; ++u)
+    if (active)
     {
-        if (!(y == 1 || mp[x - 1 + u] == k.peak || mp[x + u] == k.peak || mp[x + 1 + u] == k.peak)) continue;
-        if (!(y == height - 2 || mn[x - 1 - u] == k.peak || mn[x - u] == k.peak || mn[x + 1 - u] == k.peak)) continue;
-        const int diffsn = iabs(c0 - (int)sn[x - 1 - u]) + iabs(c1 - (int)sn[x - u]) + iabs(c2 - (int)sn[x + 1 - u]);
-        const int diffsp = iabs(c0 - (int)sp[x - 1 + u]) + iabs(c1 - (int)sp[x + u]) + iabs(c2 - (int)sp[x + 1 + u]);
-        const int diffps = iabs(p0 - (int)sc[x - 1 - u]) + iabs(p1 - (int)sc[x - u]) + iabs(p2 - (int)sc[x + 1 - u]);
-        const int diffns = iabs(n0 - (int)sc[x - 1 + u]) + iabs(n1 - (int)sc[x + u]) + iabs(n2 - (int)sc[x + 1 + u]);
-        const int diff = diffsn + diffsp + diffps + diffns;
-        int diffd = diffsp + diffns, diffe = diffsn + diffps;
-        if (diff < minb) { dirb = u; minb = diff; }
-        if (y > 1)
+        const int maxdt = plane == 0 ? maxd : (maxd >> 1);
+        const int startu = max(-x + 1, -maxdt), stopu = min(width - 2 - x, maxdt);
+        const int base = iabs((int)sc[x] - (int)sn[x]) + iabs((int)sc[x] - (int)sp[x]);
+        minb = min(nt13, base * 6); mina = min(nt19, base * 9);
+        minc = mina; mind = minb; mine = minb;
+        const int c0 = sc[x - 1], c1 = sc[x], c2 = sc[x + 1];
+        const int p0 = sp[x - 1], p1 = sp[x], p2 = sp[x + 1];
+        const int n0 = sn[x - 1], n1 = sn[x], n2 = sn[x + 1];
+        for (int u = startu + sub; u <= stopu; u += kDirLanes)
         {
-            const int diff2pp = iabs((int)s2p[x - 1] - (int)sp[x - 1 - u]) + iabs((int)s2p[x] - (int)sp[x - u]) + iabs((int)s2p[x + 1] - (int)sp[x + 1 - u]);
-            const int diffp2p = iabs(p0 - (int)s2p[x - 1 + u]) + iabs(p1 - (int)s2p[x + u]) + iabs(p2 - (int)s2p[x + 1 + u]);
-            const int diffa = diff + diff2pp + diffp2p;
-            diffd += diffp2p;
-            diffe += diff2pp;
-            if (diffa < mina) { dira = u; mina = diffa; }
+            if (!(y == 1 || mp[x - 1 + u] == k.peak || mp[x + u] == k.peak || mp[x + 1 + u] == k.peak)) continue;
+            if (!(y == height - 2 || mn[x - 1 - u] == k.peak || mn[x - u] == k.peak || mn[x + 1 - u] == k.peak)) continue;
+            const int diffsn = iabs(c0 - (int)sn[x - 1 - u]) + iabs(c1 - (int)sn[x - u]) + iabs(c2 - (int)sn[x + 1 - u]);
+            const int diffsp = iabs(c0 - (int)sp[x - 1 + u]) + iabs(c1 - (int)sp[x + u]) + iabs(c2 - (int)sp[x + 1 + u]);
+            const int diffps = iabs(p0 - (int)sc[x - 1 - u]) + iabs(p1 - (int)sc[x - u]) + iabs(p2 - (int)sc[x + 1 - u]);
+            const int diffns = iabs(n0 - (int)sc[x - 1 + u]) + iabs(n1 - (int)sc[x + u]) + iabs(n2 - (int)sc[x + 1 + u]);
+            const int diff = diffsn + diffsp + diffps + diffns;
+            int diffd = diffsp + diffns, diffe = diffsn + diffps;
+            if (diff < minb) { dirb = u; minb = diff; }
+            if (y > 1)
+            {
+                const int diff2pp = iabs((int)s2p[x - 1] - (int)sp[x - 1 - u]) + iabs((int)s2p[x] - (int)sp[x - u]) + iabs((int)s2p[x + 1] - (int)sp[x + 1 - u]);
+                const int diffp2p = iabs(p0 - (int)s2p[x - 1 + u]) + iabs(p1 - (int)s2p[x + u]) + iabs(p2 - (int)s2p[x + 1 + u]);
+                const int diffa = diff + diff2pp + diffp2p;
+                diffd += diffp2p;
+                diffe += diff2pp;
+                if (diffa < mina) { dira = u; mina = diffa; }
+            }
+            if (y < height - 2)
+            {
+                const int diff2nn = iabs((int)s2n[x - 1] - (int)sn[x - 1 + u]) + iabs((int)s2n[x] - (int)sn[x + u]) + iabs((int)s2n[x + 1] - (int)sn[x + 1 + u]);
+                const int diffn2n = iabs(n0 - (int)s2n[x - 1 - u]) + iabs(n1 - (int)s2n[x - u]) + iabs(n2 - (int)s2n[x + 1 - u]);
+                const int diffc = diff + diff2nn + diffn2n;
+                diffd += diff2nn;
+                diffe += diffn2n;
+                if (diffc < minc) { dirc = u; minc = diffc; }
+            }
+            if (diffd < mind) { dird = u; mind = diffd; }
+            if (diffe < mine) { dire = u; mine = diffe; }
         }
-        if (y < height - 2)
-        {
-            const int diff2nn = iabs((int)s2n[x - 1] - (int)sn[x - 1 + u]) + iabs((int)s2n[x] - (int)sn[x + u]) + iabs((int)s2n[x + 1] - (int)sn[x + 1 + u]);
-            const int diffn2n = iabs(n0 - (int)s2n[x - 1 - u]) + iabs(n1 - (int)s2n[x - u]) + iabs(n2 - (int)s2n[x + 1 - u]);
-            const int diffc = diff + diff2nn + diffn2n;
-            diffd += diff2nn;
-            diffe += diffn2n;
-            if (diffc < minc) { dirc = u; minc = diffc; }
-        }
-        if (diffd < mind) { dird = u; mind = diffd; }
-        if (diffe < mine) { dire = u; mine = diffe; }
     }
+    dir_combine(mina, dira);
+    dir_combine(minb, dirb);
+    dir_combine(minc, dirc);
+    dir_combine(mind, dird);
+    dir_combine(mine, dire);
+    if (!active || sub != 0) return;
     int order[5], n = 0;
     if (dira != -5000) order[n++] = dira;
     if (dirb != -5000) order[n++] = dirb;
@@ -511,8 +580,8 @@ __global__ void __launch_bounds__(256) k_calc_directions(int plane, const PIX *_
     if (y < 1 || y >= height - 1) bits = 0;
     else if (x0 + N <= width)  bits = eq_bits<PIX>(ld16(mskp + (size_t)y * pitch + x0), k.peak) & range_bits<N>(x0, 1, width - 2);
     else if (x0 < width)  bits = range_bits<N>(x0, 1, width - 2);
-    block_deal<N>(bits, list, warp_sums, [&](int x, int yy) {
-        calc_directions_px<PIX>(plane, mskp, srcp, dstp, pitch, width, height, maxd, nt, depth, k, lim, x, yy);   // dst keeps its peak fill elsewhere
+    block_deal_groups<N, kDirLanes>(bits, list, warp_sums, [&](int x, int yy, int sub, bool valid) {
+        calc_directions_px<PIX>(plane, mskp, srcp, dstp, pitch, width, height, maxd, nt, depth, k, lim, x, yy, sub, valid);   // dst keeps its peak fill elsewhere
     });
 }
 
@@ -1180,6 +1249,11 @@ struct Eedi2
     double stage_ms[3][40];
     const char *stage_name[40];
     long stage_calls;
+    // The ~90 stage launches of a field are captured once per (source frame slot, field order) into a CUDA graph and
+    // replayed: the chroma stages are a few microseconds each, launch-bound when issued one by one.
+    struct GraphEntry { const void *planes[3]; int tff; cudaGraphExec_t exec; int launches; };
+    std::vector<GraphEntry> graphs;
+    int use_graphs;                // HBCU_EEDI2_GRAPHS=0 turns the replay off (A/B)
 };
 
 namespace {
@@ -1315,6 +1389,8 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
     e->stop_after = 0;
     if (const char *sa = getenv("HBCU_EEDI2_STOP")) e->stop_after = atoi(sa);   // test hook: stage-by-stage parity
     e->timing = getenv("HBCU_EEDI2_TIMING") != nullptr;
+    e->use_graphs = 1;
+    if (const char *g = getenv("HBCU_EEDI2_GRAPHS")) e->use_graphs = atoi(g) != 0;
     e->tev[0] = e->tev[1] = nullptr;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
     memset(e->stage_name, 0, sizeof(e->stage_name));
@@ -1398,20 +1474,77 @@ void eedi2_destroy(Eedi2 *e)
     }
     if (e->tev[0]) cudaEventDestroy(e->tev[0]);
     if (e->tev[1]) cudaEventDestroy(e->tev[1]);
+    for (auto &g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int k = 0; k < 4; k++) if (e->half_mem[k]) cudaFree(e->half_mem[k]);
     for (int k = 0; k < 5; k++) if (e->full_mem[k]) cudaFree(e->full_mem[k]);
     if (e->lattice_tmp) cudaFree(e->lattice_tmp);
     delete e;
 }
 
-int eedi2_run(Eedi2 *e, const void *const planes[3], int tff, cudaStream_t st)
+static int run_planes(Eedi2 *e, const void *const planes[3], int tff, cudaStream_t st)
 {
-    e->stage_calls++;
     for (int pl = 0; pl < 3; pl++)
     {
         const int rc = e->bps == 1 ? run_plane<uint8_t>(e, pl, (const uint8_t *)planes[pl], tff, st)
                                    : run_plane<uint16_t>(e, pl, (const uint16_t *)planes[pl], tff, st);
         if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+int eedi2_run(Eedi2 *e, const void *const planes[3], int tff, cudaStream_t st)
+{
+    e->stage_calls++;
+    if (!e->use_graphs || e->timing || e->stop_after != 0) return run_planes(e, planes, tff, st);
+    for (auto &g : e->graphs)
+    {
+        if (g.planes[0] == planes[0] && g.planes[1] == planes[1] && g.planes[2] == planes[2] && g.tff == tff)
+        {
+            if (cudaGraphLaunch(g.exec, st) != cudaSuccess)
+            {
+                set_error("eedi2: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return -1;
+            }
+            hbcu::count_launch(g.launches);
+            return 0;
+        }
+    }
+    // first time for this (source slot, field order): record the launches while they are issued
+    if (e->graphs.size() >= 64) return run_planes(e, planes, tff, st);         // callers rotate a handful of slots; never hit
+    const uint64_t before = hbcu::g_kernel_launches.load();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return run_planes(e, planes, tff, st);
+    }
+    const int rc = run_planes(e, planes, tff, st);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr)
+    {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == 0) set_error("eedi2: stream capture failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return -1;
+    }
+    Eedi2::GraphEntry g;
+    for (int pl = 0; pl < 3; pl++) g.planes[pl] = planes[pl];
+    g.tff = tff;
+    g.exec = nullptr;
+    g.launches = (int)(hbcu::g_kernel_launches.load() - before);
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess)
+    {
+        set_error("eedi2: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        cudaGetLastError();
+        return -1;
+    }
+    e->graphs.push_back(g);
+    if (cudaGraphLaunch(g.exec, st) != cudaSuccess)
+    {
+        set_error("eedi2: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
     }
     return 0;
 }
