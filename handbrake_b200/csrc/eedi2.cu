@@ -186,51 +186,6 @@ __device__ __forceinline__ void block_deal(uint32_t bits, uint16_t *list, int *w
         fn((int)((blockIdx.x * blockDim.x + (t % blockDim.x)) * N + j), (int)(blockIdx.y * blockDim.y + t / blockDim.x));
     }
 }
-// Same pooling, but every active sample is handed to G neighbouring lanes (a stage whose per-sample work is a long
-// loop splits the loop over them).  fn(x, row, sub, valid) is called by EVERY thread in every round -- it may use
-// warp shuffles inside groups of G lanes; valid == false means "no sample this round, touch no memory".
-template <int N, int G, typename F>
-__device__ __forceinline__ void block_deal_groups(uint32_t bits, uint16_t *list, int *warp_sums, F fn)
-{
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int cnt = __popc(bits);
-    int pre = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const int t = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += t;
-    }
-    if (lane == 31) warp_sums[warp] = pre;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kStageThreads / 32; w++)
-    {
-        const int v = warp_sums[w];
-        if (w < warp) base += v;
-        total += v;
-    }
-    if (total == 0) return;                    // uniform over the CTA
-    pre += base - cnt;
-    while (bits)
-    {
-        const int j = __ffs(bits) - 1;
-        bits &= bits - 1;
-        list[pre++] = (uint16_t)(tid * N + j);
-    }
-    __syncthreads();
-    constexpr int per_round = kStageThreads / G;
-    const int rounds = (total + per_round - 1) / per_round;
-    for (int r = 0; r < rounds; r++)
-    {
-        const int kk = r * per_round + tid / G;
-        const bool valid = kk < total;
-        const int e = valid ? (int)list[kk] : 0, t = e / N, j = e - t * N;
-        fn((int)((blockIdx.x * blockDim.x + (t % blockDim.x)) * N + j), (int)(blockIdx.y * blockDim.y + t / blockDim.x), tid % G, valid);
-    }
-}
 #define STAGE_LIST(PIX) __shared__ uint16_t list[kStageThreads * Vec<PIX>::N]; __shared__ int warp_sums[kStageThreads / 32]
 
 // ---------------------------------------------------------------------------------------------
@@ -473,81 +428,58 @@ __global__ void __launch_bounds__(256) k_gaps(const PIX *__restrict__ mskp, PIX 
 // ---------------------------------------------------------------------------------------------
 // calc_directions (:358-525): dst pre-filled with peak (whole pitch); one thread per pixel
 // ---------------------------------------------------------------------------------------------
-// The direction search of one sample is split over G neighbouring lanes (lane `sub` takes u = startu + sub, + G, ...):
-// every family keeps the FIRST u that reaches its minimum (strict <), i.e. the lexicographic minimum of (difference, u),
-// so the lanes' partial results combine with a butterfly of (min, dir) pairs.  Called by every lane of the warp.
-constexpr int kDirLanes = 8;
-__device__ __forceinline__ void dir_combine(int &mn, int &dir)
-{
-#pragma unroll
-    for (int o = 1; o < kDirLanes; o <<= 1)
-    {
-        const int om = __shfl_xor_sync(0xffffffffu, mn, o), od = __shfl_xor_sync(0xffffffffu, dir, o);
-        if (om < mn || (om == mn && od < dir)) { mn = om; dir = od; }     // equal minima: both valid (lower u wins) or both -5000
-    }
-}
-
 template <typename PIX>
 __device__ __forceinline__ void calc_directions_px(int plane, const PIX *__restrict__ mskp, const PIX *__restrict__ srcp, PIX *__restrict__ dstp,
                                                    int pitch, int width, int height, int maxd, int nt, int depth, const K<PIX> &k, const Lim &lim,
-                                                   int x, int y, int sub, bool valid)
+                                                   int x, int y)
 {
+    if (x < 1 || x >= width - 1) return;
     const PIX *mc = mskp + (size_t)y * pitch, *mp = mc - pitch, *mn = mc + pitch;
-    const bool active = valid && x >= 1 && x < width - 1 && mc[x] == k.peak && (mc[x - 1] == k.peak || mc[x + 1] == k.peak);
+    if (mc[x] != k.peak || (mc[x - 1] != k.peak && mc[x + 1] != k.peak)) return;
     const PIX *sc = srcp + (size_t)y * pitch, *sp = sc - pitch, *sn = sc + pitch, *s2p = sc - 2 * pitch, *s2n = sc + 2 * pitch;
     const int nt13 = (int)(PIX)((nt << (depth - 8)) * 13);
     const int nt19 = (int)(PIX)((nt << (depth - 8)) * 19);
-    int minb = 0, mina = 0, minc = 0, mind = 0, mine = 0;
+    const int maxdt = plane == 0 ? maxd : (maxd >> 1);
+    const int startu = max(-x + 1, -maxdt), stopu = min(width - 2 - x, maxdt);
+    const int base = iabs((int)sc[x] - (int)sn[x]) + iabs((int)sc[x] - (int)sp[x]);
+    int minb = min(nt13, base * 6), mina = min(nt19, base * 9);
+    int minc = mina, mind = minb, mine = minb;
     int dira = -5000, dirb = -5000, dirc = -5000, dird = -5000, dire = -5000;
-    if (active)
+    const int c0 = sc[x - 1], c1 = sc[x], c2 = sc[x + 1];
+    const int p0 = sp[x - 1], p1 = sp[x], p2 = sp[x + 1];
+    const int n0 = sn[x - 1], n1 = sn[x], n2 = sn[x + 1];
+    for (int u = startu; u <= stopu; ++u)
     {
-        const int maxdt = plane == 0 ? maxd : (maxd >> 1);
-        const int startu = max(-x + 1, -maxdt), stopu = min(width - 2 - x, maxdt);
-        const int base = iabs((int)sc[x] - (int)sn[x]) + iabs((int)sc[x] - (int)sp[x]);
-        minb = min(nt13, base * 6); mina = min(nt19, base * 9);
-        minc = mina; mind = minb; mine = minb;
-        const int c0 = sc[x - 1], c1 = sc[x], c2 = sc[x + 1];
-        const int p0 = sp[x - 1], p1 = sp[x], p2 = sp[x + 1];
-        const int n0 = sn[x - 1], n1 = sn[x], n2 = sn[x + 1];
-        for (int u = startu + sub; u <= stopu; u += kDirLanes)
+        if (!(y == 1 || mp[x - 1 + u] == k.peak || mp[x + u] == k.peak || mp[x + 1 + u] == k.peak)) continue;
+        if (!(y == height - 2 || mn[x - 1 - u] == k.peak || mn[x - u] == k.peak || mn[x + 1 - u] == k.peak)) continue;
+        const int diffsn = iabs(c0 - (int)sn[x - 1 - u]) + iabs(c1 - (int)sn[x - u]) + iabs(c2 - (int)sn[x + 1 - u]);
+        const int diffsp = iabs(c0 - (int)sp[x - 1 + u]) + iabs(c1 - (int)sp[x + u]) + iabs(c2 - (int)sp[x + 1 + u]);
+        const int diffps = iabs(p0 - (int)sc[x - 1 - u]) + iabs(p1 - (int)sc[x - u]) + iabs(p2 - (int)sc[x + 1 - u]);
+        const int diffns = iabs(n0 - (int)sc[x - 1 + u]) + iabs(n1 - (int)sc[x + u]) + iabs(n2 - (int)sc[x + 1 + u]);
+        const int diff = diffsn + diffsp + diffps + diffns;
+        int diffd = diffsp + diffns, diffe = diffsn + diffps;
+        if (diff < minb) { dirb = u; minb = diff; }
+        if (y > 1)
         {
-            if (!(y == 1 || mp[x - 1 + u] == k.peak || mp[x + u] == k.peak || mp[x + 1 + u] == k.peak)) continue;
-            if (!(y == height - 2 || mn[x - 1 - u] == k.peak || mn[x - u] == k.peak || mn[x + 1 - u] == k.peak)) continue;
-            const int diffsn = iabs(c0 - (int)sn[x - 1 - u]) + iabs(c1 - (int)sn[x - u]) + iabs(c2 - (int)sn[x + 1 - u]);
-            const int diffsp = iabs(c0 - (int)sp[x - 1 + u]) + iabs(c1 - (int)sp[x + u]) + iabs(c2 - (int)sp[x + 1 + u]);
-            const int diffps = iabs(p0 - (int)sc[x - 1 - u]) + iabs(p1 - (int)sc[x - u]) + iabs(p2 - (int)sc[x + 1 - u]);
-            const int diffns = iabs(n0 - (int)sc[x - 1 + u]) + iabs(n1 - (int)sc[x + u]) + iabs(n2 - (int)sc[x + 1 + u]);
-            const int diff = diffsn + diffsp + diffps + diffns;
-            int diffd = diffsp + diffns, diffe = diffsn + diffps;
-            if (diff < minb) { dirb = u; minb = diff; }
-            if (y > 1)
-            {
-                const int diff2pp = iabs((int)s2p[x - 1] - (int)sp[x - 1 - u]) + iabs((int)s2p[x] - (int)sp[x - u]) + iabs((int)s2p[x + 1] - (int)sp[x + 1 - u]);
-                const int diffp2p = iabs(p0 - (int)s2p[x - 1 + u]) + iabs(p1 - (int)s2p[x + u]) + iabs(p2 - (int)s2p[x + 1 + u]);
-                const int diffa = diff + diff2pp + diffp2p;
-                diffd += diffp2p;
-                diffe += diff2pp;
-                if (diffa < mina) { dira = u; mina = diffa; }
-            }
-            if (y < height - 2)
-            {
-                const int diff2nn = iabs((int)s2n[x - 1] - (int)sn[x - 1 + u]) + iabs((int)s2n[x] - (int)sn[x + u]) + iabs((int)s2n[x + 1] - (int)sn[x + 1 + u]);
-                const int diffn2n = iabs(n0 - (int)s2n[x - 1 - u]) + iabs(n1 - (int)s2n[x - u]) + iabs(n2 - (int)s2n[x + 1 - u]);
-                const int diffc = diff + diff2nn + diffn2n;
-                diffd += diff2nn;
-                diffe += diffn2n;
-                if (diffc < minc) { dirc = u; minc = diffc; }
-            }
-            if (diffd < mind) { dird = u; mind = diffd; }
-            if (diffe < mine) { dire = u; mine = diffe; }
+            const int diff2pp = iabs((int)s2p[x - 1] - (int)sp[x - 1 - u]) + iabs((int)s2p[x] - (int)sp[x - u]) + iabs((int)s2p[x + 1] - (int)sp[x + 1 - u]);
+            const int diffp2p = iabs(p0 - (int)s2p[x - 1 + u]) + iabs(p1 - (int)s2p[x + u]) + iabs(p2 - (int)s2p[x + 1 + u]);
+            const int diffa = diff + diff2pp + diffp2p;
+            diffd += diffp2p;
+            diffe += diff2pp;
+            if (diffa < mina) { dira = u; mina = diffa; }
         }
+        if (y < height - 2)
+        {
+            const int diff2nn = iabs((int)s2n[x - 1] - (int)sn[x - 1 + u]) + iabs((int)s2n[x] - (int)sn[x + u]) + iabs((int)s2n[x + 1] - (int)sn[x + 1 + u]);
+            const int diffn2n = iabs(n0 - (int)s2n[x - 1 - u]) + iabs(n1 - (int)s2n[x - u]) + iabs(n2 - (int)s2n[x + 1 - u]);
+            const int diffc = diff + diff2nn + diffn2n;
+            diffd += diff2nn;
+            diffe += diffn2n;
+            if (diffc < minc) { dirc = u; minc = diffc; }
+        }
+        if (diffd < mind) { dird = u; mind = diffd; }
+        if (diffe < mine) { dire = u; mine = diffe; }
     }
-    dir_combine(mina, dira);
-    dir_combine(minb, dirb);
-    dir_combine(minc, dirc);
-    dir_combine(mind, dird);
-    dir_combine(mine, dire);
-    if (!active || sub != 0) return;
     int order[5], n = 0;
     if (dira != -5000) order[n++] = dira;
     if (dirb != -5000) order[n++] = dirb;
@@ -580,8 +512,10 @@ __global__ void __launch_bounds__(256) k_calc_directions(int plane, const PIX *_
     if (y < 1 || y >= height - 1) bits = 0;
     else if (x0 + N <= width)  bits = eq_bits<PIX>(ld16(mskp + (size_t)y * pitch + x0), k.peak) & range_bits<N>(x0, 1, width - 2);
     else if (x0 < width)  bits = range_bits<N>(x0, 1, width - 2);
-    block_deal_groups<N, kDirLanes>(bits, list, warp_sums, [&](int x, int yy, int sub, bool valid) {
-        calc_directions_px<PIX>(plane, mskp, srcp, dstp, pitch, width, height, maxd, nt, depth, k, lim, x, yy, sub, valid);   // dst keeps its peak fill elsewhere
+    // (splitting one sample's 49-step search over 8 lanes was measured slower: 163 vs 119 us -- the densely active CTAs
+    //  that set the kernel's duration need 8x the rounds and 30 shuffles per round)
+    block_deal<N>(bits, list, warp_sums, [&](int x, int yy) {
+        calc_directions_px<PIX>(plane, mskp, srcp, dstp, pitch, width, height, maxd, nt, depth, k, lim, x, yy);   // dst keeps its peak fill elsewhere
     });
 }
 
