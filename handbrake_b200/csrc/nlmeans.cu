@@ -31,6 +31,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include <cstdio>
 
@@ -217,8 +218,85 @@ __global__ void __launch_bounds__(256) prefilter_kernel(const PIX *__restrict__ 
     if ((filter_type & 512) && (filter_type & 256)) { wet = 1; dry = 3; }
     else if (filter_type & 512) { wet = 1; dry = 1; }
     else if (filter_type & 256) { wet = 3; dry = 1; }
-    if (dry > 0) out = (wet * (int)(PIX)out + dry * cv) / (wet + dry);
+    if (dry > 0 && !(filter_type & 1024)) out = (wet * (int)(PIX)out + dry * cv) / (wet + dry);   // with edgeboost the blend runs after it
     pre[(ptrdiff_t)y * bpitch + x] = (PIX)out;
+}
+
+// ---------------------------------------------------------------------------
+// edgeboost (template :325-426).  Pass 1 classifies every sample from two 3x3 gradient kernels (pixel_2 arithmetic,
+// i.e. unsigned and wrapping, a double coefficient, constants that do not scale with the bit depth): 0 = no edge,
+// 1 = weak (128), 2 = strong (235).  Pass 2 visits the samples IN RASTER ORDER and clears an edge sample whose 3x3
+// neighbourhood holds fewer than 3 edge samples -- counting the already cleared neighbours as cleared -- and blends the
+// source back into the surviving edge samples.  The raster-order rule is a recurrence c(p) = f(c(NW), c(N), c(NE), c(W))
+// with a unique solution; any fixed point of the Jacobi iteration c' = f(c) IS that solution, so the kernel below is
+// iterated until nothing changes (typically 2-3 rounds; a diagonal line of isolated pairs needs one round per sample).
+// ---------------------------------------------------------------------------
+template <typename PIX>
+__global__ void __launch_bounds__(256) edgeboost_mask_kernel(const PIX *__restrict__ src, int bpitch, int w, int h, uint8_t *__restrict__ cls, int cpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    typedef typename std::conditional<sizeof(PIX) == 1, uint16_t, uint32_t>::type PIX2;
+    const int kern[3][3] = { { -31, 0, 31 }, { -44, 0, 44 }, { -31, 0, 31 } };
+    const PIX *c = src + (ptrdiff_t)y * bpitch + x;
+    PIX2 p1 = 0, p2 = 0;
+    for (int k = -1; k < 2; k++)
+        for (int j = -1; j < 2; j++)
+        {
+            const int sv = c[(ptrdiff_t)j * bpitch + k];
+            p1 = (PIX2)(p1 + kern[j + 1][k + 1] * sv);
+            p2 = (PIX2)(p2 + kern[k + 1][j + 1] * sv);
+        }
+    // `pixelN = pixelN > 0 ? pixelN : -pixelN` is the identity on an unsigned value
+    const double coef = 1.0 / 126.42;
+    p1 = (PIX2)__double2uint_rz(__dadd_rn(__dmul_rn((double)p1, coef), 128.0));
+    p2 = (PIX2)__double2uint_rz(__dadd_rn(__dmul_rn((double)p2, coef), 128.0));
+    const int m = (int)(PIX)(p1 + p2);
+    cls[(size_t)(y + 1) * cpitch + x + 1] = m > 160 ? 2 : m > 16 ? 1 : 0;        // class plane has a 1-sample zero border
+}
+
+__global__ void __launch_bounds__(256) edgeboost_clear_kernel(const uint8_t *__restrict__ cls, int cpitch, int w, int h,
+                                                             const uint8_t *__restrict__ clr_old, uint8_t *__restrict__ clr_new, int *__restrict__ changed)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t i = (size_t)(y + 1) * cpitch + x + 1;
+    uint8_t c = 0;
+    if (cls[i])
+    {
+        // neighbours before p in raster order (NW, N, NE, W) count only if they were not cleared; the others as classified
+        int n = 1;
+        n += cls[i - cpitch - 1] && !clr_old[i - cpitch - 1];
+        n += cls[i - cpitch] && !clr_old[i - cpitch];
+        n += cls[i - cpitch + 1] && !clr_old[i - cpitch + 1];
+        n += cls[i - 1] && !clr_old[i - 1];
+        n += cls[i + 1] != 0;
+        n += cls[i + cpitch - 1] != 0;
+        n += cls[i + cpitch] != 0;
+        n += cls[i + cpitch + 1] != 0;
+        c = n < 3;
+    }
+    clr_new[i] = c;
+    if (c != clr_old[i]) *changed = 1;
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) edgeboost_apply_kernel(const PIX *__restrict__ src, PIX *__restrict__ pre, int bpitch, int w, int h,
+                                                             const uint8_t *__restrict__ cls, const uint8_t *__restrict__ clr, int cpitch, int filter_type)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t i = (size_t)(y + 1) * cpitch + x + 1;
+    const ptrdiff_t o = (ptrdiff_t)y * bpitch + x;
+    const int sv = src[o];
+    int out = pre[o];
+    if (cls[i] && !clr[i]) out = cls[i] == 2 ? (3 * sv + out) / 4 : (2 * sv + 3 * out) / 5;
+    int wet = 1, dry = 0;                                   // the blend the filter kernel left for us (:510-526)
+    if ((filter_type & 512) && (filter_type & 256)) { wet = 1; dry = 3; }
+    else if (filter_type & 512) { wet = 1; dry = 1; }
+    else if (filter_type & 256) { wet = 3; dry = 1; }
+    if (dry > 0) out = (wet * (int)(PIX)out + dry * sv) / (wet + dry);
+    pre[o] = (PIX)out;
 }
 
 // ---------------------------------------------------------------------------
@@ -1393,6 +1471,9 @@ struct hbcu_nlmeans_s
     std::vector<uint8_t *> ring_mem;      // [slot*3+plane] bordered planes
     std::vector<uint8_t *> pre_mem;       // [slot*3+plane] prefiltered bordered planes (planes whose prefilter mode has a filter bit)
     bool has_pre[3];
+    uint8_t *eb_cls, *eb_clr[2];          // edgeboost: class plane and the two cleared-flag planes (luma size + 1-sample border)
+    int *eb_changed, *eb_changed_host;    // device flag + pinned copy of the Jacobi iteration
+    int eb_cpitch;
     std::vector<uint8_t *> raw_base;      // [slot] one allocation per staged frame: a frame whose planes lie back to back on
     std::vector<uint8_t *> out_base;      // [oslot] the host (hb_frame_buffer_init, fifo.c:839-881) moves as ONE copy each way
     size_t frame_cap, plane_off[3];       // capacity of such an allocation; default plane offsets inside it
@@ -1856,11 +1937,6 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
             set_error("nlmeans_create: plane %d has invalid patch/range/frames %d/%d/%d", pl, pp.patch_size, pp.range, pp.nframes);
             return -1;
         }
-        if ((pp.prefilter & 1024) && (pp.prefilter & 63))
-        {
-            set_error("nlmeans_create: plane %d: prefilter %d asks for edgeboost, which is decided in raster order and not implemented", pl, pp.prefilter);
-            return -1;
-        }
         if (pp.patch_size / 2 + pp.range / 2 > kBorder)
         {
             // the reference reads outside its 16-pixel border here (undefined behaviour); refuse instead
@@ -1928,6 +2004,20 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ring_mem.assign(h->ring * 3, nullptr);
     h->pre_mem.assign(h->ring * 3, nullptr);
     for (int pl = 0; pl < 3; pl++) h->has_pre[pl] = (cfg->plane[pl].prefilter & 63) != 0;
+    h->eb_cls = h->eb_clr[0] = h->eb_clr[1] = nullptr;
+    h->eb_changed = h->eb_changed_host = nullptr;
+    h->eb_cpitch = cfg->width + 2;
+    bool any_eb = false;
+    for (int pl = 0; pl < 3; pl++) any_eb = any_eb || (h->has_pre[pl] && (cfg->plane[pl].prefilter & 1024));
+    if (any_eb)
+    {
+        const size_t n = (size_t)h->eb_cpitch * (cfg->height + 2);
+        CK(cudaMalloc(&h->eb_cls, n));
+        CK(cudaMalloc(&h->eb_clr[0], n));
+        CK(cudaMalloc(&h->eb_clr[1], n));
+        CK(cudaMalloc(&h->eb_changed, sizeof(int)));
+        CK(cudaHostAlloc(&h->eb_changed_host, sizeof(int), cudaHostAllocPortable));
+    }
     h->raw_mem.assign(h->ring * 3, nullptr);
     h->out_mem.assign(h->out_slots * 3, nullptr);
     h->raw_base.assign(h->ring, nullptr);
@@ -2023,6 +2113,11 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
     }
     for (auto p : h->ring_mem) if (p) cudaFree(p);
     for (auto p : h->pre_mem) if (p) cudaFree(p);
+    if (h->eb_cls) cudaFree(h->eb_cls);
+    if (h->eb_clr[0]) cudaFree(h->eb_clr[0]);
+    if (h->eb_clr[1]) cudaFree(h->eb_clr[1]);
+    if (h->eb_changed) cudaFree(h->eb_changed);
+    if (h->eb_changed_host) cudaFreeHost(h->eb_changed_host);
     for (auto p : h->raw_base) if (p) cudaFree(p);
     for (auto p : h->out_base) if (p) cudaFree(p);
     for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
@@ -2127,17 +2222,39 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
         uint8_t *preb = h->pre_mem[slot * 3 + pl];
         dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4), bgrid((g.bw + 63) / 64, (g.bh + 3) / 4);
         const int ft = h->cfg.plane[pl].prefilter;
-        if (h->bps == 1)
+        if (h->bps == 1) prefilter_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, preb + org, g.bpitch, g.w, g.h, ft);
+        else             prefilter_kernel<uint16_t><<<grid, blk, 0, h->s_pad>>>((const uint16_t *)srcb, (uint16_t *)(preb + org), g.bpitch, g.w, g.h, ft);
+        hbcu::count_launch();
+        if (ft & 1024)
         {
-            prefilter_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, preb + org, g.bpitch, g.w, g.h, ft);
-            pad_mirror_kernel<uint8_t><<<bgrid, blk, 0, h->s_pad>>>(preb + org, g.bpitch, g.w, g.h, preb, g.bpitch, kBorder, nullptr);
+            // edgeboost: classify, iterate the raster-order clearing rule to its fixed point (host reads a flag per
+            // round: this rarely used mode makes the upload synchronous), blend
+            const int cp = h->eb_cpitch;
+            const size_t n = (size_t)cp * (g.h + 2);
+            HBCU_CHECK(cudaMemsetAsync(h->eb_cls, 0, n, h->s_pad));
+            HBCU_CHECK(cudaMemsetAsync(h->eb_clr[0], 0, n, h->s_pad));
+            HBCU_CHECK(cudaMemsetAsync(h->eb_clr[1], 0, n, h->s_pad));
+            if (h->bps == 1) edgeboost_mask_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, g.bpitch, g.w, g.h, h->eb_cls, cp);
+            else             edgeboost_mask_kernel<uint16_t><<<grid, blk, 0, h->s_pad>>>((const uint16_t *)srcb, g.bpitch, g.w, g.h, h->eb_cls, cp);
+            hbcu::count_launch();
+            int cur = 0;
+            for (int round = 0; round < g.w + g.h + 2; round++)
+            {
+                HBCU_CHECK(cudaMemsetAsync(h->eb_changed, 0, sizeof(int), h->s_pad));
+                edgeboost_clear_kernel<<<grid, blk, 0, h->s_pad>>>(h->eb_cls, cp, g.w, g.h, h->eb_clr[cur], h->eb_clr[cur ^ 1], h->eb_changed);
+                hbcu::count_launch();
+                HBCU_CHECK(cudaMemcpyAsync(h->eb_changed_host, h->eb_changed, sizeof(int), cudaMemcpyDeviceToHost, h->s_pad));
+                HBCU_CHECK(cudaStreamSynchronize(h->s_pad));
+                cur ^= 1;
+                if (*h->eb_changed_host == 0) break;
+            }
+            if (h->bps == 1) edgeboost_apply_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, preb + org, g.bpitch, g.w, g.h, h->eb_cls, h->eb_clr[cur], cp, ft);
+            else             edgeboost_apply_kernel<uint16_t><<<grid, blk, 0, h->s_pad>>>((const uint16_t *)srcb, (uint16_t *)(preb + org), g.bpitch, g.w, g.h, h->eb_cls, h->eb_clr[cur], cp, ft);
+            hbcu::count_launch();
         }
-        else
-        {
-            prefilter_kernel<uint16_t><<<grid, blk, 0, h->s_pad>>>((const uint16_t *)srcb, (uint16_t *)(preb + org), g.bpitch, g.w, g.h, ft);
-            pad_mirror_kernel<uint16_t><<<bgrid, blk, 0, h->s_pad>>>((const uint16_t *)(preb + org), g.bpitch, g.w, g.h, (uint16_t *)preb, g.bpitch, kBorder, nullptr);
-        }
-        hbcu::count_launch(2);
+        if (h->bps == 1) pad_mirror_kernel<uint8_t><<<bgrid, blk, 0, h->s_pad>>>(preb + org, g.bpitch, g.w, g.h, preb, g.bpitch, kBorder, nullptr);
+        else             pad_mirror_kernel<uint16_t><<<bgrid, blk, 0, h->s_pad>>>((const uint16_t *)(preb + org), g.bpitch, g.w, g.h, (uint16_t *)preb, g.bpitch, kBorder, nullptr);
+        hbcu::count_launch();
         HBCU_CHECK(cudaGetLastError());
     }
     trace(h, index, TR_PAD_END, h->s_pad);

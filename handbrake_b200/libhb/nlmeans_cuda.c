@@ -16,8 +16,7 @@
  * differ from the reference (which emits `threads` frames at a time); output
  * order and content do not.  The `threads` setting is accepted and sizes the
  * number of frames kept in flight.  The prefilter modes (nlmeans.c:72-83) run on
- * the GPU too, except the edgeboost bit (a raster-order recurrence): init() fails
- * for it, so libhb drops the filter instead of silently producing different pictures.
+ * the GPU too, with the reference's single-worker behaviour.
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
@@ -230,16 +229,6 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     }
     pv->depth = cfg.depth;
     pv->bps   = pv->depth > 8 ? 2 : 1;
-    for (int c = 0; c < 3; c++)
-    {
-        if ((pv->prefilter[c] & 1024) && (pv->prefilter[c] & 63))
-        {
-            /* edgeboost clears false positives in raster order: every decision depends on the ones before it */
-            hb_error("nlmeans(cuda): prefilter mode %d (edgeboost) is not implemented on the GPU path", pv->prefilter[c]);
-            goto fail;
-        }
-    }
-
     /* `threads` CPU workers -> that many output frames in flight on the streams */
     pv->inflight_max = pv->threads < 1 ? 4 : pv->threads;
     if (pv->inflight_max > NLM_MAX_INFLIGHT) pv->inflight_max = NLM_MAX_INFLIGHT;

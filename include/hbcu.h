@@ -95,9 +95,8 @@ typedef struct hbcu_nlmeans_plane_s
     float  weight_fact;     /* pv->weight_fact_table[c]  (nlmeans.c:352) */
     int    diff_max;        /* pv->diff_max[c]           (nlmeans.c:353) */
     float  exptable[HBCU_NLMEANS_EXPSIZE];   /* pv->exptable[c], computed by the host exactly as nlmeans.c:354-358 */
-    int    prefilter;       /* pv->prefilter[c] (nlmeans.c:72-83): mean 1/2, median 4/8, csm 16/32, reduce 256/512, passthru 2048
-                             * are implemented (patch distances on the pre-denoised image, template :103-543); edgeboost
-                             * (1024) has a raster-order recurrence and is refused by create() */
+    int    prefilter;       /* pv->prefilter[c] (nlmeans.c:72-83): mean 1/2, median 4/8, csm 16/32, reduce 256/512, edgeboost 1024,
+                             * passthru 2048; patch distances are taken from the pre-denoised image (template :103-543) */
 } hbcu_nlmeans_plane_t;
 
 typedef struct hbcu_nlmeans_config_s

@@ -75,19 +75,12 @@ def test_fewer_frames_than_window(ref, cuda_filters):
     assert_same(r, g)
 
 
-def test_edgeboost_prefilter_is_refused(cuda_filters):
-    """edgeboost clears false positives in raster order (a serial recurrence): init fails, libhb drops the filter"""
-    w, h = 160, 96
-    clip = synth.progressive_clip(FMT8, w, h, 2)
-    g = cuda_filters.run("hb_filter_nlmeans_cuda", "y-strength=6:y-prefilter=1025", clip, FMT8, w, h)
-    assert g.init_failed == 1          # filter dropped, frames pass through untouched (work.c:1861-1868)
-    assert np.array_equal(g.frames, clip)
-
-
-@pytest.mark.parametrize("mode", [1, 2, 4, 8, 16, 32, 1 + 256, 2 + 512, 4 + 256 + 512, 2049, 2048 + 8 + 512, 2048, 256, 1024])
+@pytest.mark.parametrize("mode", [1, 2, 4, 8, 16, 32, 1 + 256, 2 + 512, 4 + 256 + 512, 2049, 2048 + 8 + 512, 2048, 256, 1024,
+                                  1 + 1024, 16 + 1024, 2 + 1024 + 256, 8 + 1024 + 2048 + 512])
 @pytest.mark.parametrize("fmt", [FMT8, FMT10])
 def test_prefilter_modes(ref, cuda_filters, mode, fmt):
-    """mean / median / csm prefilters (3x3, 5x5), reduce 25/50/75, passthru, the no-op modes; chroma inherits luma.
+    """mean / median / csm prefilters (3x3, 5x5), reduce 25/50/75, edgeboost (a raster-order recurrence, solved as a
+    fixed-point iteration), passthru, the no-op modes; chroma inherits luma.
     The reference with threads=1: with more workers it races on frame[0].image_pre."""
     w, h = 200, 120
     clip = synth.progressive_clip(fmt, w, h, 4, seed=81)
@@ -182,4 +175,20 @@ def test_10bit_container_with_out_of_range_samples(ref, cuda_filters):
     v[2, 1000:1040] = 4095
     v[3, ::97] = 3000
     r, g = run_both(ref, cuda_filters, "y-strength=6", clip, FMT10, w, h)
+    assert_same(r, g)
+
+
+def test_edgeboost_long_dependency_chain(ref, cuda_filters):
+    """a diagonal line of isolated edge pairs: clearing the first one clears the next ... one Jacobi round per sample"""
+    w, h = 96, 80
+    n = synth.frame_bytes(FMT8, w, h)
+    frame = np.full(n, 60, np.uint8)
+    y = frame[: w * h].reshape(h, w)
+    for i in range(2, 70, 2):                     # isolated bright dots on a diagonal
+        y[i, i] = 220
+    clip = np.stack([frame, frame.copy(), frame.copy()])
+    clip[1, : w * h].reshape(h, w)[5:40:3, 50] = 200
+    s = "y-strength=6:y-patch-size=5:y-frame-count=2:y-prefilter=1025:cb-prefilter=0"
+    r = ref.run("hb_filter_nlmeans", s + ":threads=1", clip, FMT8, w, h)
+    g = cuda_filters.run("hb_filter_nlmeans_cuda", s, clip, FMT8, w, h)
     assert_same(r, g)
