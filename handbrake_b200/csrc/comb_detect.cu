@@ -603,6 +603,8 @@ int hbcu_comb_detect_create(hbcu_comb_detect_t **out, const hbcu_comb_detect_con
     for (int r = 0; r < h->nres; r++) CK(cudaEventCreateWithFlags(&h->ev_result[r], cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
+    // the clearing memsets above ran on the legacy default stream; the handle's non-blocking streams do not wait for it
+    CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;
     return 0;

@@ -552,6 +552,13 @@ int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
             return -1;
         }
     }
+    // the clearing memsets above (and EEDI2's) ran on the legacy default stream; the handle's non-blocking streams do not wait for it
+    if (cudaDeviceSynchronize() != cudaSuccess)
+    {
+        set_error("decomb_create: %s", cudaGetErrorString(cudaGetLastError()));
+        hbcu_decomb_destroy(h);
+        return -1;
+    }
     *out = h;
     return 0;
 }

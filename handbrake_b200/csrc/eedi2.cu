@@ -1370,6 +1370,8 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
         }
     }
     if (ok) ok = cudaMalloc(&e->lattice_tmp, sizeof(LatticeTmp) * (size_t)cfg.w[0] * (cfg.h[0] / 2 + 1)) == cudaSuccess;
+    // entries of direction-less samples are never written (and never used): keep them defined
+    if (ok) ok = cudaMemset(e->lattice_tmp, 0, sizeof(LatticeTmp) * (size_t)cfg.w[0] * (cfg.h[0] / 2 + 1)) == cudaSuccess;
     if (!ok)
     {
         set_error("eedi2: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -144,6 +144,17 @@ int hbcu_frame_alloc(hbcu_frame_t **out, int device, const int row_bytes[3], con
         delete f;
         return -1;
     }
+    // the clearing memset runs on the legacy default stream, which the filters' non-blocking streams do not wait for:
+    // the first producer of the frame orders itself behind `consumed`, so record it behind the memset
+    if (cudaEventRecord(f->consumed, 0) != cudaSuccess)
+    {
+        hbcu::set_error("hbcu_frame_alloc: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(f->base);
+        cudaEventDestroy(f->ready);
+        cudaEventDestroy(f->consumed);
+        delete f;
+        return -1;
+    }
     off = 0;
     for (int p = 0; p < 3; p++)
     {

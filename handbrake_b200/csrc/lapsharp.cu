@@ -249,6 +249,8 @@ int hbcu_lapsharp_create(hbcu_lapsharp_t **out, const hbcu_lapsharp_config_t *cf
     }
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
+    // the clearing memsets above ran on the legacy default stream; the handle's non-blocking streams do not wait for it
+    CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;
     return 0;

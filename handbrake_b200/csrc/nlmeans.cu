@@ -2080,6 +2080,8 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     for (int pl = 0; pl < 3; pl++)
         CK(cudaMemcpy(h->d_exptable + pl * HBCU_NLMEANS_EXPSIZE, cfg->plane[pl].exptable,
                       HBCU_NLMEANS_EXPSIZE * sizeof(float), cudaMemcpyHostToDevice));
+    // the clearing memsets above ran on the legacy default stream; the handle's non-blocking streams do not wait for it
+    CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;
     return 0;

@@ -304,6 +304,8 @@ int hbcu_unsharp_create(hbcu_unsharp_t **out, const hbcu_unsharp_config_t *cfg)
     }
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
+    // the clearing memsets above ran on the legacy default stream; the handle's non-blocking streams do not wait for it
+    CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;
     return 0;
