@@ -1,0 +1,448 @@
+// hqdn3d.cu -- hqdn3d ("high quality 3-D denoise") for sm_100a behind the C-ABI of include/hbcu.h.
+//
+// Replaces hqdn3d_denoise_spatial / _temporal / _depth (reference /root/reference/libhb/denoise.c:102-201).
+// The reference sweeps a plane once, carrying three recursive low-passes: along the row (pixel_ant), down the column
+// (line_ant[]) and through time (frame_ant[]).  lowpass(prev, cur) = cur + coef[(prev - cur) >> (8 - LUT_BITS)] is a table
+// lookup, not a linear filter, so the recursions cannot be turned into scans -- but they separate:
+//   H  rows are independent of each other        -> one thread per row marches along x      (hqdn3d_h_kernel)
+//   V  columns are independent once H is known    -> one thread per column marches down y,
+//   T  the temporal step is per sample               fused into the same march               (hqdn3d_vt_kernel)
+// (oracle/port/hqdn3d_port.c restates the filter in exactly this three-pass form and is pinned against the compiled
+// reference.)  Parallelism is the plane's height resp. width, each thread a dependent chain of table lookups: the kernels
+// are latency bound by construction; tiles go through shared memory so that global accesses stay coalesced although a
+// thread owns a row.  The 16-bit fixed-point domain, the bias of LOAD, the uint16 truncation of the stored states and the
+// first-row special case (h(0) = lowpass(LOAD(0), LOAD(0)) only in row 0) are reproduced: bit-exact.
+#include "hbcu_common.h"
+#include "hbcu_frames.h"
+#include "../../include/hbcu.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using hbcu::set_error;
+
+__device__ __forceinline__ int lowpass(int prev, int cur, const int16_t *__restrict__ coef, int shift)
+{
+    return cur + (int)coef[(prev - cur) >> shift];          // coef points at the table's centre
+}
+
+template <typename PIX>
+__device__ __forceinline__ int load16(const PIX *p, int sh, int bias) { return ((int)*p << sh) + bias; }
+
+// H pass: warp = 32 rows, lane = row; 32 x 32 tiles staged through shared memory (pitch 33: conflict free both ways)
+template <typename PIX, bool SMEM_LUT>
+__global__ void __launch_bounds__(128) hqdn3d_h_kernel(const PIX *__restrict__ src, int spitch, uint16_t *__restrict__ hbuf,
+                                                      int w, int h, int depth, const int16_t *__restrict__ table, int half)
+{
+    extern __shared__ int16_t s_lut[];
+    __shared__ uint16_t tile[4][32][33];
+    const int16_t *coef = table + half;
+    if (SMEM_LUT)
+    {
+        for (int i = threadIdx.x; i < 2 * half; i += blockDim.x) s_lut[i] = table[i];
+        __syncthreads();
+        coef = s_lut + half;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row0 = (blockIdx.x * 4 + warp) * 32, row = row0 + lane;
+    if (row0 >= h) return;
+    const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1, lsh = depth == 16 ? 0 : 4;
+    int p = 0;
+    for (int x0 = 0; x0 < w; x0 += 32)
+    {
+#pragma unroll 8
+        for (int r = 0; r < 32; r++)
+        {
+            const int y = row0 + r, x = x0 + lane;
+            tile[warp][r][lane] = (y < h && x < w) ? (uint16_t)load16(src + (size_t)y * spitch + x, sh, bias) : 0;
+        }
+        __syncwarp();
+        if (row < h)
+        {
+            const int n = min(32, w - x0);
+            for (int c = 0; c < n; c++)
+            {
+                const int cur = tile[warp][lane][c];
+                if (x0 + c == 0) p = row == 0 ? lowpass(cur, cur, coef, lsh) : cur;      // denoise.c:140-143 vs :152
+                else             p = lowpass(p, cur, coef, lsh);
+                tile[warp][lane][c] = (uint16_t)p;
+            }
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < 32; r++)
+        {
+            const int y = row0 + r, x = x0 + lane;
+            if (y < h && x < w) hbuf[(size_t)y * w + x] = tile[warp][r][lane];
+        }
+        __syncwarp();
+    }
+}
+
+// V + T pass: thread = column.  SPATIAL = false is the temporal-only mode (denoise.c:102-124): v = LOAD(src).
+template <typename PIX, bool SMEM_LUT, bool SPATIAL>
+__global__ void __launch_bounds__(128) hqdn3d_vt_kernel(const PIX *__restrict__ src, int spitch, const uint16_t *__restrict__ hbuf,
+                                                       uint16_t *__restrict__ ant, int first, PIX *__restrict__ dst, int dpitch,
+                                                       int w, int h, int depth, const int16_t *__restrict__ stable,
+                                                       const int16_t *__restrict__ ttable, int half)
+{
+    extern __shared__ int16_t s_lut[];
+    const int16_t *scoef = stable + half, *tcoef = ttable + half;
+    if (SMEM_LUT)
+    {
+        for (int i = threadIdx.x; i < 2 * half; i += blockDim.x)
+        {
+            s_lut[i] = stable[i];
+            s_lut[2 * half + i] = ttable[i];
+        }
+        __syncthreads();
+        scoef = s_lut + half;
+        tcoef = s_lut + 3 * half;
+    }
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1, lsh = depth == 16 ? 0 : 4;
+    constexpr int U = 8;                                   // rows fetched ahead of the dependent chain
+    int v = 0;
+    for (int y0 = 0; y0 < h; y0 += U)
+    {
+        int cur[U], a[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+        {
+            const int y = min(y0 + k, h - 1);
+            const int s = load16(src + (size_t)y * spitch + x, sh, bias);
+            cur[k] = SPATIAL ? (int)hbuf[(size_t)y * w + x] : s;
+            a[k] = first ? s : (int)ant[(size_t)y * w + x];            // denoise.c:175-189: the state starts as the first frame
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+        {
+            const int y = y0 + k;
+            if (y >= h) break;
+            if (SPATIAL) v = y == 0 ? cur[k] : lowpass(v, cur[k], scoef, lsh);
+            else         v = cur[k];
+            v &= 0xffff;                                   // line_ant[] is uint16_t
+            const int t = lowpass(a[k], v, tcoef, lsh);
+            ant[(size_t)y * w + x] = (uint16_t)t;
+            dst[(size_t)y * dpitch + x] = (PIX)((unsigned)t >> sh);
+        }
+    }
+}
+
+struct Geom { int w, h, pitch; size_t bytes; };
+
+}  // namespace
+
+struct hbcu_hqdn3d_s
+{
+    hbcu_hqdn3d_config_t cfg;
+    int bps, slots, next, half;
+    Geom g[3];
+    size_t frame_bytes, plane_off[3];
+    std::vector<uint8_t *> in_base, out_base;
+    std::vector<int64_t> ticket;
+    int16_t *d_coef[6];
+    uint16_t *d_ant[3], *d_h[3];
+    int first[3];
+    bool spatial[3];
+    cudaStream_t s_h2d, s_compute, s_d2h;
+    std::vector<cudaEvent_t> ev_up, ev_k, ev_down;
+    cudaEvent_t ev_mark[2];
+};
+
+namespace {
+
+template <typename PIX>
+int launch_plane_t(hbcu_hqdn3d_s *h, int pl, const void *src, void *dst)
+{
+    const Geom &g = h->g[pl];
+    const bool smem = h->cfg.depth < 16;
+    const size_t lut1 = smem ? (size_t)2 * h->half * sizeof(int16_t) : 0;
+    const int depth = h->cfg.depth;
+    if (h->spatial[pl])
+    {
+        const int hgrid = (g.h + 127) / 128;
+        if (smem) hqdn3d_h_kernel<PIX, true><<<hgrid, 128, lut1, h->s_compute>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
+        else      hqdn3d_h_kernel<PIX, false><<<hgrid, 128, 0, h->s_compute>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
+        hbcu::count_launch();
+    }
+    const int vgrid = (g.w + 127) / 128;
+#define VT(SM, SP) hqdn3d_vt_kernel<PIX, SM, SP><<<vgrid, 128, 2 * lut1, h->s_compute>>>((const PIX *)src, g.pitch, h->d_h[pl], h->d_ant[pl], h->first[pl], \
+                       (PIX *)dst, g.pitch, g.w, g.h, depth, h->d_coef[2 * pl], h->d_coef[2 * pl + 1], h->half)
+    if (smem) { if (h->spatial[pl]) VT(true, true); else VT(true, false); }
+    else      { if (h->spatial[pl]) VT(false, true); else VT(false, false); }
+#undef VT
+    hbcu::count_launch();
+    h->first[pl] = 0;
+    HBCU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+bool same_layout(const hbcu_hqdn3d_s *h, const void *const planes[3], const int strides[3])
+{
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if ((size_t)strides[pl] != (size_t)h->g[pl].pitch * h->bps) return false;
+        if ((const uint8_t *)planes[pl] != (const uint8_t *)planes[0] + h->plane_off[pl]) return false;
+    }
+    return true;
+}
+
+bool frame_fits(const hbcu_hqdn3d_s *h, const hbcu_frame_t *f)
+{
+    if (f->device != h->cfg.device) return false;
+    for (int pl = 0; pl < 3; pl++)
+        if (f->row_bytes[pl] != h->g[pl].w * h->bps || f->rows[pl] != h->g[pl].h || f->stride[pl] != h->g[pl].pitch * h->bps) return false;
+    return true;
+}
+
+int find_slot(const hbcu_hqdn3d_s *h, int64_t ticket)
+{
+    for (int s = 0; s < h->slots; s++)
+        if (h->ticket[s] == ticket) return s;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbcu_hqdn3d_create(hbcu_hqdn3d_t **out, const hbcu_hqdn3d_config_t *cfg)
+{
+    if (out == nullptr || cfg == nullptr) { set_error("hqdn3d_create: null argument"); return -1; }
+    *out = nullptr;
+    for (int i = 0; i < 6; i++)
+        if (cfg->coef[i] == nullptr) { set_error("hqdn3d_create: coefficient table %d missing", i); return -1; }
+    if (cfg->width < 1 || cfg->height < 1 || cfg->depth < 8 || cfg->depth > 16)
+    {
+        set_error("hqdn3d_create: unsupported geometry %dx%d depth %d", cfg->width, cfg->height, cfg->depth);
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+    {
+        cudaGetLastError();
+        set_error("hqdn3d_create: CUDA device %d not available (%d devices); there is no CPU fallback", cfg->device, ndev);
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    HBCU_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10)
+    {
+        set_error("hqdn3d_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        return -1;
+    }
+    hbcu_hqdn3d_s *h = new (std::nothrow) hbcu_hqdn3d_s();
+    if (h == nullptr) { set_error("hqdn3d_create: out of memory"); return -1; }
+    h->cfg = *cfg;
+    h->bps = cfg->depth > 8 ? 2 : 1;
+    h->slots = cfg->slots >= 2 ? cfg->slots : 4;
+    h->next = 0;
+    h->half = 256 << (cfg->depth == 16 ? 8 : 4);             // LUT_BITS, denoise.c:30
+    h->s_h2d = h->s_compute = h->s_d2h = nullptr;
+    h->ev_mark[0] = h->ev_mark[1] = nullptr;
+    for (int i = 0; i < 6; i++) h->d_coef[i] = nullptr;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        h->d_ant[pl] = h->d_h[pl] = nullptr;
+        h->first[pl] = 1;
+        h->spatial[pl] = cfg->coef[2 * pl][0] != 0;         // ct[0] = !!dist25 (denoise.c:93, :192)
+        Geom &g = h->g[pl];
+        g.w = pl == 0 ? cfg->width : -((-cfg->width) >> cfg->chroma_shift_w);
+        g.h = pl == 0 ? cfg->height : -((-cfg->height) >> cfg->chroma_shift_h);
+        g.pitch = ((g.w * h->bps + 63) / 64 * 64) / h->bps;
+        g.bytes = (size_t)g.pitch * g.h * h->bps;
+        h->plane_off[pl] = pl == 0 ? 0 : h->plane_off[pl - 1] + h->g[pl - 1].bytes;
+        h->frame_bytes = h->plane_off[pl] + g.bytes;
+    }
+#define CK(expr)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));            \
+            hbcu_hqdn3d_destroy(h);                                               \
+            return -1;                                                            \
+        }                                                                         \
+    } while (0)
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++)
+    {
+        CK(cudaMalloc(&h->d_coef[i], (size_t)2 * h->half * sizeof(int16_t)));
+        CK(cudaMemcpy(h->d_coef[i], cfg->coef[i], (size_t)2 * h->half * sizeof(int16_t), cudaMemcpyHostToDevice));
+        h->cfg.coef[i] = nullptr;                           // the caller's tables are not kept
+    }
+    if (cfg->depth < 16)
+    {
+        const int lut = 4 * h->half * (int)sizeof(int16_t);
+        if (lut > 48 * 1024)
+        {
+            CK(cudaFuncSetAttribute(hqdn3d_vt_kernel<uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut));
+            CK(cudaFuncSetAttribute(hqdn3d_vt_kernel<uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut));
+            CK(cudaFuncSetAttribute(hqdn3d_vt_kernel<uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut));
+            CK(cudaFuncSetAttribute(hqdn3d_vt_kernel<uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut));
+        }
+    }
+    for (int pl = 0; pl < 3; pl++)
+    {
+        CK(cudaMalloc(&h->d_ant[pl], (size_t)h->g[pl].w * h->g[pl].h * sizeof(uint16_t)));
+        CK(cudaMalloc(&h->d_h[pl], (size_t)h->g[pl].w * h->g[pl].h * sizeof(uint16_t)));
+    }
+    h->in_base.assign(h->slots, nullptr);
+    h->out_base.assign(h->slots, nullptr);
+    h->ticket.assign(h->slots, -1);
+    h->ev_up.assign(h->slots, nullptr);
+    h->ev_k.assign(h->slots, nullptr);
+    h->ev_down.assign(h->slots, nullptr);
+    for (int s = 0; s < h->slots; s++)
+    {
+        CK(cudaEventCreateWithFlags(&h->ev_up[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_k[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_down[s], cudaEventDisableTiming));
+        CK(cudaMalloc(&h->in_base[s], h->frame_bytes));
+        CK(cudaMalloc(&h->out_base[s], h->frame_bytes));
+        CK(cudaMemset(h->out_base[s], 0, h->frame_bytes));       // the stride padding is never written
+    }
+    CK(cudaEventCreate(&h->ev_mark[0]));
+    CK(cudaEventCreate(&h->ev_mark[1]));
+    // the clearing memsets above ran on the legacy default stream; the handle's non-blocking streams do not wait for it
+    CK(cudaDeviceSynchronize());
+#undef CK
+    *out = h;
+    return 0;
+}
+
+void hbcu_hqdn3d_destroy(hbcu_hqdn3d_t *h)
+{
+    if (h == nullptr) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto p : h->in_base) if (p) cudaFree(p);
+    for (auto p : h->out_base) if (p) cudaFree(p);
+    for (int i = 0; i < 6; i++) if (h->d_coef[i]) cudaFree(h->d_coef[i]);
+    for (int pl = 0; pl < 3; pl++) { if (h->d_ant[pl]) cudaFree(h->d_ant[pl]); if (h->d_h[pl]) cudaFree(h->d_h[pl]); }
+    for (auto e : h->ev_up) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_k) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_down) if (e) cudaEventDestroy(e);
+    if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
+    if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+// frames MUST be submitted in display order: the temporal state makes every frame depend on the previous one
+int hbcu_hqdn3d_filter_frames(hbcu_hqdn3d_t *h, int64_t ticket,
+                              hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                              hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
+{
+    if (h == nullptr || (in_frame == nullptr && (in_planes == nullptr || in_strides == nullptr)) ||
+        (out_frame == nullptr && (out_planes == nullptr || out_strides == nullptr)) ||
+        (in_frame && !frame_fits(h, in_frame)) || (out_frame && !frame_fits(h, out_frame)))
+    {
+        set_error("hqdn3d_filter_frames: bad argument or frame geometry");
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    const int s = h->next;
+    h->next = (h->next + 1) % h->slots;
+    if (in_frame == nullptr)
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_k[s], 0));
+        if (same_layout(h, in_planes, in_strides))
+            HBCU_CHECK(cudaMemcpyAsync(h->in_base[s], in_planes[0], h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        else
+            for (int pl = 0; pl < 3; pl++)
+                HBCU_CHECK(cudaMemcpy2DAsync(h->in_base[s] + h->plane_off[pl], (size_t)h->g[pl].pitch * h->bps, in_planes[pl], (size_t)in_strides[pl],
+                                             (size_t)h->g[pl].w * h->bps, (size_t)h->g[pl].h, cudaMemcpyHostToDevice, h->s_h2d));
+        HBCU_CHECK(cudaEventRecord(h->ev_up[s], h->s_h2d));
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_up[s], 0));
+    }
+    else if (hbcu::frame_begin_read(in_frame, h->s_compute) != 0) return -1;
+    HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
+    if (out_frame && hbcu::frame_begin_write(out_frame, h->s_compute) != 0) return -1;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const void *src = in_frame ? (const void *)in_frame->plane[pl] : (const void *)(h->in_base[s] + h->plane_off[pl]);
+        void *dst = out_frame ? (void *)out_frame->plane[pl] : (void *)(h->out_base[s] + h->plane_off[pl]);
+        const int rc = h->bps == 1 ? launch_plane_t<uint8_t>(h, pl, src, dst) : launch_plane_t<uint16_t>(h, pl, src, dst);
+        if (rc != 0) return -1;
+    }
+    HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
+    if (in_frame && hbcu::frame_end_read(in_frame, h->s_compute) != 0) return -1;
+    if (out_frame)
+    {
+        if (hbcu::frame_end_write(out_frame, h->s_compute) != 0) return -1;
+        HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_compute));
+    }
+    else
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_k[s], 0));
+        if (same_layout(h, out_planes, out_strides))
+            HBCU_CHECK(cudaMemcpyAsync(out_planes[0], h->out_base[s], h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        else
+            for (int pl = 0; pl < 3; pl++)
+                HBCU_CHECK(cudaMemcpy2DAsync(out_planes[pl], (size_t)out_strides[pl], h->out_base[s] + h->plane_off[pl], (size_t)h->g[pl].pitch * h->bps,
+                                             (size_t)h->g[pl].w * h->bps, (size_t)h->g[pl].h, cudaMemcpyDeviceToHost, h->s_d2h));
+        HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_d2h));
+    }
+    h->ticket[s] = ticket;
+    return 0;
+}
+
+int hbcu_hqdn3d_wait(hbcu_hqdn3d_t *h, int64_t ticket)
+{
+    if (h == nullptr) { set_error("hqdn3d_wait: null handle"); return -1; }
+    const int s = find_slot(h, ticket);
+    if (s < 0) { set_error("hqdn3d_wait: ticket %lld is not in flight", (long long)ticket); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_down[s]));
+    return 0;
+}
+
+int hbcu_hqdn3d_poll(hbcu_hqdn3d_t *h, int64_t ticket)
+{
+    if (h == nullptr) { set_error("hqdn3d_poll: null handle"); return -1; }
+    const int s = find_slot(h, ticket);
+    if (s < 0) { set_error("hqdn3d_poll: ticket %lld is not in flight", (long long)ticket); return -1; }
+    cudaError_t e = cudaEventQuery(h->ev_down[s]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    set_error("hqdn3d_poll: %s", cudaGetErrorString(e));
+    return -1;
+}
+
+int hbcu_hqdn3d_sync(hbcu_hqdn3d_t *h)
+{
+    if (h == nullptr) { set_error("hqdn3d_sync: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
+    HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
+    return 0;
+}
+
+int hbcu_hqdn3d_mark(hbcu_hqdn3d_t *h, int which)
+{
+    if (h == nullptr || which < 0 || which > 1) { set_error("hqdn3d_mark: bad argument"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaEventRecord(h->ev_mark[which], h->s_compute));
+    return 0;
+}
+
+int hbcu_hqdn3d_elapsed_ms(hbcu_hqdn3d_t *h, float *ms)
+{
+    if (h == nullptr || ms == nullptr) { set_error("hqdn3d_elapsed_ms: bad argument"); return -1; }
+    HBCU_CHECK(cudaEventSynchronize(h->ev_mark[1]));
+    HBCU_CHECK(cudaEventElapsedTime(ms, h->ev_mark[0], h->ev_mark[1]));
+    return 0;
+}
+
+}  // extern "C"

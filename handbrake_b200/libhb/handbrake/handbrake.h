@@ -443,6 +443,18 @@ void                hb_filter_close(hb_filter_object_t **);
 extern hb_filter_object_t hb_filter_nlmeans;
 extern hb_filter_object_t hb_filter_comb_detect;
 extern hb_filter_object_t hb_filter_decomb;
+/* libavutil helpers libhb/denoise.c uses */
+#ifndef FFMIN
+#define FFMIN(a, b) ((a) > (b) ? (b) : (a))
+#define FFMAX(a, b) ((a) > (b) ? (a) : (b))
+#endif
+#ifndef AV_CEIL_RSHIFT
+#define AV_CEIL_RSHIFT(a, b) (-((-(a)) >> (b)))
+#endif
+static inline void *av_malloc(size_t size) { void *p = NULL; if (posix_memalign(&p, 64, size ? size : 1) != 0) return NULL; return p; }
+static inline void av_freep(void *arg) { void **pp = (void **)arg; free(*pp); *pp = NULL; }
+
+extern hb_filter_object_t hb_filter_denoise;
 extern hb_filter_object_t hb_filter_lapsharp;
 extern hb_filter_object_t hb_filter_unsharp;
 extern hb_filter_object_t hb_filter_chroma_smooth;

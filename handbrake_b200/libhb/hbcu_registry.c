@@ -10,6 +10,7 @@ extern hb_filter_object_t hb_filter_comb_detect_cuda;
 extern hb_filter_object_t hb_filter_decomb_cuda;
 extern hb_filter_object_t hb_filter_lapsharp_cuda;
 extern hb_filter_object_t hb_filter_unsharp_cuda;
+extern hb_filter_object_t hb_filter_denoise_cuda;
 extern hb_filter_object_t hb_filter_chroma_smooth_cuda;
 
 hb_filter_object_t *hb_filter_get(int filter_id)
@@ -21,6 +22,7 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_DECOMB:      return &hb_filter_decomb_cuda;
         case HB_FILTER_LAPSHARP:    return &hb_filter_lapsharp_cuda;   /* no mt_frame wrapper needed: streams */
         case HB_FILTER_UNSHARP:     return &hb_filter_unsharp_cuda;
+        case HB_FILTER_DENOISE:     return &hb_filter_denoise_cuda;    /* hqdn3d */
         case HB_FILTER_CHROMA_SMOOTH: return &hb_filter_chroma_smooth_cuda;
         default:                return NULL;
     }

@@ -329,6 +329,34 @@ int  hbcu_unsharp_sync(hbcu_unsharp_t *h);
 int  hbcu_unsharp_mark(hbcu_unsharp_t *h, int which);
 int  hbcu_unsharp_elapsed_ms(hbcu_unsharp_t *h, float *ms);
 
+/* ------------------------------------------------------------------------- */
+/* hqdn3d       replaces hqdn3d_denoise_spatial/_temporal/_depth                 */
+/*              (denoise.c:102-201); SURVEY.md 8 f4                              */
+/* ------------------------------------------------------------------------- */
+typedef struct hbcu_hqdn3d_config_s
+{
+    int width, height, depth;
+    int chroma_shift_w, chroma_shift_h;
+    int device;
+    int slots;                 /* frames in flight */
+    const int16_t *coef[6];    /* hqdn3d_precalc_coef tables (denoise.c:78-94), 512 << LUT_BITS entries each, computed by the host
+                                * exactly as there: y-spatial, y-temporal, cb-spatial, cb-temporal, cr-spatial, cr-temporal */
+} hbcu_hqdn3d_config_t;
+
+typedef struct hbcu_hqdn3d_s hbcu_hqdn3d_t;
+
+int  hbcu_hqdn3d_create(hbcu_hqdn3d_t **out, const hbcu_hqdn3d_config_t *cfg);
+void hbcu_hqdn3d_destroy(hbcu_hqdn3d_t *h);
+/* one frame, IN DISPLAY ORDER (the temporal state chains the frames); either side may be a device frame */
+int  hbcu_hqdn3d_filter_frames(hbcu_hqdn3d_t *h, int64_t ticket,
+                               hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                               hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3]);
+int  hbcu_hqdn3d_wait(hbcu_hqdn3d_t *h, int64_t ticket);
+int  hbcu_hqdn3d_poll(hbcu_hqdn3d_t *h, int64_t ticket);
+int  hbcu_hqdn3d_sync(hbcu_hqdn3d_t *h);
+int  hbcu_hqdn3d_mark(hbcu_hqdn3d_t *h, int which);
+int  hbcu_hqdn3d_elapsed_ms(hbcu_hqdn3d_t *h, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

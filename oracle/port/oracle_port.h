@@ -114,6 +114,12 @@ void oracle_unsharp_plane(const void *src, void *dst, int w, int h, int depth, d
 void oracle_unsharp_clip(const uint8_t *in, int n, int width, int height, int depth, const double strength[3], const int size[3],
                          int smooth, uint8_t *out);
 
+/* ---------------- hqdn3d (libhb/denoise.c) ---------------- */
+void oracle_hqdn3d_coef(int16_t *ct, int depth, double dist25);      /* hqdn3d_precalc_coef, table of 512 << LUT_BITS entries */
+void oracle_hqdn3d_plane(const void *src, void *dst, uint16_t *ant, int *ant_valid, int w, int h, int depth,
+                         const int16_t *spatial_tab, const int16_t *temporal_tab);
+void oracle_hqdn3d_clip(const uint8_t *in, int n, int width, int height, int depth, const double strengths[6], uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

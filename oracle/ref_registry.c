@@ -12,6 +12,7 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_COMB_DETECT: return &hb_filter_comb_detect;
         case HB_FILTER_DECOMB:      return &hb_filter_decomb;
         case HB_FILTER_LAPSHARP:    return &hb_filter_lapsharp;
+        case HB_FILTER_DENOISE:     return &hb_filter_denoise;
         case HB_FILTER_UNSHARP:     return &hb_filter_unsharp;
         case HB_FILTER_CHROMA_SMOOTH: return &hb_filter_chroma_smooth;
         case HB_FILTER_MT_FRAME:    return &hb_filter_mt_frame;

@@ -158,3 +158,17 @@ def unsharp_clip(self, clip, w, h, depth, strength, size, smooth):
 
 
 OraclePort.unsharp_clip = unsharp_clip
+
+
+def hqdn3d_clip(self, clip, w, h, depth, strengths):
+    """libhb/denoise.c on packed yuv420p frames; strengths = [y-spatial, y-temporal, cb-spatial, cb-temporal, cr-spatial,
+    cr-temporal] after the filter's defaults"""
+    self.lib.oracle_hqdn3d_clip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    clip = np.ascontiguousarray(clip, dtype=np.uint8)
+    out = np.zeros_like(clip)
+    st = (C.c_double * 6)(*strengths)
+    self.lib.oracle_hqdn3d_clip(clip.ctypes.data, clip.shape[0], w, h, depth, st, out.ctypes.data)
+    return out
+
+
+OraclePort.hqdn3d_clip = hqdn3d_clip
