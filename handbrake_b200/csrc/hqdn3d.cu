@@ -63,14 +63,23 @@ __global__ void __launch_bounds__(128) hqdn3d_h_kernel(const PIX *__restrict__ s
         __syncwarp();
         if (row < h)
         {
+            // the row's 32 samples first (independent loads), then the dependent chain: one table lookup per step
             const int n = min(32, w - x0);
-            for (int c = 0; c < n; c++)
+            int v[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) v[c] = tile[warp][lane][c];
+#pragma unroll
+            for (int c = 0; c < 32; c++)
             {
-                const int cur = tile[warp][lane][c];
-                if (x0 + c == 0) p = row == 0 ? lowpass(cur, cur, coef, lsh) : cur;      // denoise.c:140-143 vs :152
-                else             p = lowpass(p, cur, coef, lsh);
-                tile[warp][lane][c] = (uint16_t)p;
+                if (c < n)
+                {
+                    if (c == 0 && x0 == 0) p = row == 0 ? lowpass(v[0], v[0], coef, lsh) : v[0];   // denoise.c:140-143 vs :152
+                    else                   p = lowpass(p, v[c], coef, lsh);
+                    v[c] = p;
+                }
             }
+#pragma unroll
+            for (int c = 0; c < 32; c++) tile[warp][lane][c] = (uint16_t)v[c];
         }
         __syncwarp();
 #pragma unroll 8
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(128) hqdn3d_vt_kernel(const PIX *__restrict__ 
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
     const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1, lsh = depth == 16 ? 0 : 4;
-    constexpr int U = 8;                                   // rows fetched ahead of the dependent chain
+    constexpr int U = 16;                                  // rows fetched ahead of the dependent chain
     int v = 0;
     for (int y0 = 0; y0 < h; y0 += U)
     {
@@ -151,6 +160,8 @@ struct hbcu_hqdn3d_s
     int first[3];
     bool spatial[3];
     cudaStream_t s_h2d, s_compute, s_d2h;
+    cudaStream_t s_pl[3];                // the three planes are independent: they run side by side, forked from / joined to s_compute
+    cudaEvent_t ev_fork, ev_join[3];
     std::vector<cudaEvent_t> ev_up, ev_k, ev_down;
     cudaEvent_t ev_mark[2];
 };
@@ -158,7 +169,7 @@ struct hbcu_hqdn3d_s
 namespace {
 
 template <typename PIX>
-int launch_plane_t(hbcu_hqdn3d_s *h, int pl, const void *src, void *dst)
+int launch_plane_t(hbcu_hqdn3d_s *h, int pl, const void *src, void *dst, cudaStream_t st)
 {
     const Geom &g = h->g[pl];
     const bool smem = h->cfg.depth < 16;
@@ -167,12 +178,12 @@ int launch_plane_t(hbcu_hqdn3d_s *h, int pl, const void *src, void *dst)
     if (h->spatial[pl])
     {
         const int hgrid = (g.h + 127) / 128;
-        if (smem) hqdn3d_h_kernel<PIX, true><<<hgrid, 128, lut1, h->s_compute>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
-        else      hqdn3d_h_kernel<PIX, false><<<hgrid, 128, 0, h->s_compute>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
+        if (smem) hqdn3d_h_kernel<PIX, true><<<hgrid, 128, lut1, st>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
+        else      hqdn3d_h_kernel<PIX, false><<<hgrid, 128, 0, st>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
         hbcu::count_launch();
     }
     const int vgrid = (g.w + 127) / 128;
-#define VT(SM, SP) hqdn3d_vt_kernel<PIX, SM, SP><<<vgrid, 128, 2 * lut1, h->s_compute>>>((const PIX *)src, g.pitch, h->d_h[pl], h->d_ant[pl], h->first[pl], \
+#define VT(SM, SP) hqdn3d_vt_kernel<PIX, SM, SP><<<vgrid, 128, 2 * lut1, st>>>((const PIX *)src, g.pitch, h->d_h[pl], h->d_ant[pl], h->first[pl], \
                        (PIX *)dst, g.pitch, g.w, g.h, depth, h->d_coef[2 * pl], h->d_coef[2 * pl + 1], h->half)
     if (smem) { if (h->spatial[pl]) VT(true, true); else VT(true, false); }
     else      { if (h->spatial[pl]) VT(false, true); else VT(false, false); }
@@ -247,6 +258,8 @@ int hbcu_hqdn3d_create(hbcu_hqdn3d_t **out, const hbcu_hqdn3d_config_t *cfg)
     h->half = 256 << (cfg->depth == 16 ? 8 : 4);             // LUT_BITS, denoise.c:30
     h->s_h2d = h->s_compute = h->s_d2h = nullptr;
     h->ev_mark[0] = h->ev_mark[1] = nullptr;
+    h->ev_fork = nullptr;
+    for (int pl = 0; pl < 3; pl++) { h->s_pl[pl] = nullptr; h->ev_join[pl] = nullptr; }
     for (int i = 0; i < 6; i++) h->d_coef[i] = nullptr;
     for (int pl = 0; pl < 3; pl++)
     {
@@ -273,6 +286,12 @@ int hbcu_hqdn3d_create(hbcu_hqdn3d_t **out, const hbcu_hqdn3d_config_t *cfg)
     CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int pl = 0; pl < 3; pl++)
+    {
+        CK(cudaStreamCreateWithFlags(&h->s_pl[pl], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_join[pl], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 6; i++)
     {
         CK(cudaMalloc(&h->d_coef[i], (size_t)2 * h->half * sizeof(int16_t)));
@@ -333,6 +352,12 @@ void hbcu_hqdn3d_destroy(hbcu_hqdn3d_t *h)
     for (auto e : h->ev_down) if (e) cudaEventDestroy(e);
     if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
     if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int pl = 0; pl < 3; pl++)
+    {
+        if (h->ev_join[pl]) cudaEventDestroy(h->ev_join[pl]);
+        if (h->s_pl[pl]) cudaStreamDestroy(h->s_pl[pl]);
+    }
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -369,12 +394,17 @@ int hbcu_hqdn3d_filter_frames(hbcu_hqdn3d_t *h, int64_t ticket,
     else if (hbcu::frame_begin_read(in_frame, h->s_compute) != 0) return -1;
     HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
     if (out_frame && hbcu::frame_begin_write(out_frame, h->s_compute) != 0) return -1;
+    // fork: every plane on its own stream (stream order per plane also chains the plane's temporal state frame to frame)
+    HBCU_CHECK(cudaEventRecord(h->ev_fork, h->s_compute));
     for (int pl = 0; pl < 3; pl++)
     {
         const void *src = in_frame ? (const void *)in_frame->plane[pl] : (const void *)(h->in_base[s] + h->plane_off[pl]);
         void *dst = out_frame ? (void *)out_frame->plane[pl] : (void *)(h->out_base[s] + h->plane_off[pl]);
-        const int rc = h->bps == 1 ? launch_plane_t<uint8_t>(h, pl, src, dst) : launch_plane_t<uint16_t>(h, pl, src, dst);
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_pl[pl], h->ev_fork, 0));
+        const int rc = h->bps == 1 ? launch_plane_t<uint8_t>(h, pl, src, dst, h->s_pl[pl]) : launch_plane_t<uint16_t>(h, pl, src, dst, h->s_pl[pl]);
         if (rc != 0) return -1;
+        HBCU_CHECK(cudaEventRecord(h->ev_join[pl], h->s_pl[pl]));
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_join[pl], 0));
     }
     HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
     if (in_frame && hbcu::frame_end_read(in_frame, h->s_compute) != 0) return -1;
@@ -424,6 +454,7 @@ int hbcu_hqdn3d_sync(hbcu_hqdn3d_t *h)
     if (h == nullptr) { set_error("hqdn3d_sync: null handle"); return -1; }
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     HBCU_CHECK(cudaStreamSynchronize(h->s_h2d));
+    for (int pl = 0; pl < 3; pl++) HBCU_CHECK(cudaStreamSynchronize(h->s_pl[pl]));
     HBCU_CHECK(cudaStreamSynchronize(h->s_compute));
     HBCU_CHECK(cudaStreamSynchronize(h->s_d2h));
     return 0;
