@@ -207,6 +207,16 @@ def main():
     jobs.append(("4k_unsharp", lambda: unsharp_job("4k_unsharp", False, None, "unsharp", "3840x2160 yuv420p 8-bit, unsharp defaults (0.25, size 7)")))
     jobs.append(("4k_chroma_smooth", lambda: unsharp_job("4k_chroma_smooth", True, None, "chroma_smooth", "3840x2160 yuv420p 8-bit, chroma_smooth defaults (0.25, size 7)")))
 
+    def hqdn3d_job():
+        depth = 8; fmt = fmt_of(depth)
+        fb = synth.frame_bytes(fmt, W, H)
+        host = np.stack([synth.progressive_frame(fmt, W, H, t) for t in range(4)])
+        core.hbcu_host_reserve(fb + 4096, 3 * n + 24)
+        r = {"workload": "4k_hqdn3d", "desc": "3840x2160 yuv420p 8-bit, hqdn3d defaults (4:3:6)"}
+        r.update(e2e_and_cpu(flt, ref, "hb_filter_denoise_cuda", "hb_filter_denoise", None, fmt, host, n, max(args.cpu_frames, 8)))
+        return r
+    jobs.append(("4k_hqdn3d", hqdn3d_job))
+
     def comb_job():
         depth = 10; fmt = fmt_of(depth)
         host = np.stack([synth.interlaced_frame(fmt, W, H, t) for t in range(4)])
