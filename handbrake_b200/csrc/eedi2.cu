@@ -1173,7 +1173,9 @@ struct Eedi2
     int half_h[3];                 // field-buffer plane heights
     size_t half_off[3], full_off[3], half_bytes, full_bytes;
     uint8_t *half_mem[4], *full_mem[5];      // allocation starts (incl. lead slack)
-    LatticeTmp *lattice_tmp;
+    LatticeTmp *lattice_tmp, *lattice_tmp_pl[3];   // one allocation, a private region per plane (the planes run side by side)
+    cudaStream_t s_aux[2];                          // chroma planes' branches of the captured graph
+    cudaEvent_t ev_fork, ev_join[2];
     Lim lim;
     int stop_after;                // debug: number of stage launches to run per plane (0 = all); HBCU_EEDI2_STOP
     // HBCU_EEDI2_TIMING=1: CUDA-event pair around every stage launch, per-stage totals printed at destroy (warm,
@@ -1266,8 +1268,8 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     // interpolate the missing lines (:1148-1335): first copy one border row, then the two passes
     if (tff == 1) LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + (size_t)(height - 2) * pitch, dst2p + (size_t)(height - 1) * pitch, pitch, width, 1)));
     else          LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + pitch, dst2p, pitch, width, 1)));
-    LAUNCH((k_lattice_a<PIX><<<gridv(width, rows2), blk, 0, st>>>(pl, tmp2p, dst2p, tmp2p2, e->lattice_tmp, pitch, width, height, tff, c.nt, depth, e->lim)));
-    LAUNCH((k_lattice_b<PIX><<<rows2, kLatThreads, (size_t)width * (sizeof(LatticeTmp) + 2 * sizeof(int)), st>>>(tmp2p, dst2p, e->lattice_tmp, pitch, width, height, tff, depth)));
+    LAUNCH((k_lattice_a<PIX><<<gridv(width, rows2), blk, 0, st>>>(pl, tmp2p, dst2p, tmp2p2, e->lattice_tmp_pl[pl], pitch, width, height, tff, c.nt, depth, e->lim)));
+    LAUNCH((k_lattice_b<PIX><<<rows2, kLatThreads, (size_t)width * (sizeof(LatticeTmp) + 2 * sizeof(int)), st>>>(tmp2p, dst2p, e->lattice_tmp_pl[pl], pitch, width, height, tff, depth)));
 
     if (c.pp == 1 || c.pp == 3)
     {
@@ -1320,6 +1322,8 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
     for (int k = 0; k < 4; k++) e->half_mem[k] = nullptr;
     for (int k = 0; k < 5; k++) e->full_mem[k] = nullptr;
     e->lattice_tmp = nullptr;
+    e->s_aux[0] = e->s_aux[1] = nullptr;
+    e->ev_fork = e->ev_join[0] = e->ev_join[1] = nullptr;
     e->stop_after = 0;
     if (const char *sa = getenv("HBCU_EEDI2_STOP")) e->stop_after = atoi(sa);   // test hook: stage-by-stage parity
     e->timing = getenv("HBCU_EEDI2_TIMING") != nullptr;
@@ -1369,9 +1373,21 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
             cudaFuncSetAttribute(k_lattice_b<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
         }
     }
-    if (ok) ok = cudaMalloc(&e->lattice_tmp, sizeof(LatticeTmp) * (size_t)cfg.w[0] * (cfg.h[0] / 2 + 1)) == cudaSuccess;
-    // entries of direction-less samples are never written (and never used): keep them defined
-    if (ok) ok = cudaMemset(e->lattice_tmp, 0, sizeof(LatticeTmp) * (size_t)cfg.w[0] * (cfg.h[0] / 2 + 1)) == cudaSuccess;
+    {
+        size_t n[3], total = 0;
+        for (int pl = 0; pl < 3; pl++) { n[pl] = (size_t)cfg.w[pl] * (cfg.h[pl] / 2 + 1); total += n[pl]; }
+        if (ok) ok = cudaMalloc(&e->lattice_tmp, sizeof(LatticeTmp) * total) == cudaSuccess;
+        // entries of direction-less samples are never written (and never used): keep them defined
+        if (ok) ok = cudaMemset(e->lattice_tmp, 0, sizeof(LatticeTmp) * total) == cudaSuccess;
+        e->lattice_tmp_pl[0] = e->lattice_tmp;
+        e->lattice_tmp_pl[1] = e->lattice_tmp_pl[0] + n[0];
+        e->lattice_tmp_pl[2] = e->lattice_tmp_pl[1] + n[1];
+    }
+    if (ok) ok = cudaStreamCreateWithFlags(&e->s_aux[0], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaStreamCreateWithFlags(&e->s_aux[1], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_join[1], cudaEventDisableTiming) == cudaSuccess;
     if (!ok)
     {
         set_error("eedi2: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1414,6 +1430,12 @@ void eedi2_destroy(Eedi2 *e)
     for (int k = 0; k < 4; k++) if (e->half_mem[k]) cudaFree(e->half_mem[k]);
     for (int k = 0; k < 5; k++) if (e->full_mem[k]) cudaFree(e->full_mem[k]);
     if (e->lattice_tmp) cudaFree(e->lattice_tmp);
+    for (int i = 0; i < 2; i++)
+    {
+        if (e->s_aux[i]) cudaStreamDestroy(e->s_aux[i]);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     delete e;
 }
 
@@ -1454,7 +1476,23 @@ int eedi2_run(Eedi2 *e, const void *const planes[3], int tff, cudaStream_t st)
         cudaGetLastError();
         return run_planes(e, planes, tff, st);
     }
-    const int rc = run_planes(e, planes, tff, st);
+    // The three planes never read outside their own plane of any work buffer (every stage clamps its horizontal reach to
+    // the row and guards rows +-1 / +-2 / +-3), so they are independent: luma stays on `st`, the chroma planes fork into
+    // two auxiliary streams and join again -- parallel branches of the captured graph.
+    int rc = 0;
+    bool forked = cudaEventRecord(e->ev_fork, st) == cudaSuccess;
+    for (int pl = 1; pl < 3 && forked && rc == 0; pl++)
+    {
+        forked = cudaStreamWaitEvent(e->s_aux[pl - 1], e->ev_fork, 0) == cudaSuccess;
+        if (!forked) break;
+        rc = e->bps == 1 ? run_plane<uint8_t>(e, pl, (const uint8_t *)planes[pl], tff, e->s_aux[pl - 1])
+                         : run_plane<uint16_t>(e, pl, (const uint16_t *)planes[pl], tff, e->s_aux[pl - 1]);
+        forked = cudaEventRecord(e->ev_join[pl - 1], e->s_aux[pl - 1]) == cudaSuccess;
+    }
+    if (forked && rc == 0)
+        rc = e->bps == 1 ? run_plane<uint8_t>(e, 0, (const uint8_t *)planes[0], tff, st) : run_plane<uint16_t>(e, 0, (const uint16_t *)planes[0], tff, st);
+    for (int pl = 1; pl < 3 && forked; pl++) forked = cudaStreamWaitEvent(st, e->ev_join[pl - 1], 0) == cudaSuccess;
+    if (!forked && rc == 0) rc = -2;
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != 0 || ce != cudaSuccess || graph == nullptr)
     {
