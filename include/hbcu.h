@@ -12,6 +12,10 @@
  *   - "planes"/"strides": arrays of 3 host pointers / byte strides in
  *     hb_buffer_t.plane[] order (Y, Cb, Cr).  Host memory may be pageable;
  *     page-locked memory from hbcu_host_alloc() makes the copies asynchronous.
+ *   - a handle belongs to one thread at a time (libhb calls a filter's work() from that filter's own thread only,
+ *     work.c:2527); different handles may be used from different threads concurrently.  All device work is queued
+ *     on the handle's own non-blocking streams and ordered by events; calls return before the work has run unless
+ *     they are named wait / sync / result.
  *   - nothing here falls back to the CPU: with no usable sm_100 device the
  *     create functions fail (=> filter init() returns non-zero, and libhb drops
  *     the filter exactly as for any failing init, work.c:1861-1868).
