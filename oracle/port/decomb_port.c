@@ -214,12 +214,19 @@ int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const
                        int width, int height, int depth, int mode, int parity_setting,
                        uint8_t *out, int *out_src)
 {
+    return oracle_decomb_clip_pp(in, n_in, flags, combed, width, height, depth, mode, parity_setting, 1, out, out_src);
+}
+
+int oracle_decomb_clip_pp(const uint8_t *in, int n_in, const uint16_t *flags, const uint8_t *combed,
+                          int width, int height, int depth, int mode, int parity_setting, int postproc,
+                          uint8_t *out, int *out_src)
+{
     const int bps = depth > 8 ? 2 : 1;
     const int cw = -((-width) >> 1), ch = -((-height) >> 1);
     const size_t fb = ((size_t)width * height + 2 * (size_t)cw * ch) * bps;
     int n_out = 0;
     /* EEDI2 with the filter's default thresholds (decomb.c:234-243); its edge-mask state lives for the whole clip */
-    void *eedi_state = (mode & ORACLE_DECOMB_EEDI2) ? oracle_eedi2_create(width, height, depth, 10, 20, 20, 4, 2, 50, 24, 1) : NULL;
+    void *eedi_state = (mode & ORACLE_DECOMB_EEDI2) ? oracle_eedi2_create(width, height, depth, 10, 20, 20, 4, 2, 50, 24, postproc) : NULL;
     uint8_t *eedi_frame = eedi_state ? malloc(fb) : NULL;
     for (int t = 0; t < n_in; t++)
     {

@@ -1,7 +1,7 @@
 /* eedi2_port.c -- TEST INFRASTRUCTURE (see oracle_port.h).
  *
  * Restates HandBrake's EEDI2 (libhb/templates/eedi2_template.c, driven by eedi2_interpolate_plane,
- * libhb/templates/decomb_template.c:366-441) for one field of a yuv420 frame, postproc 0/1.
+ * libhb/templates/decomb_template.c:366-441) for one field of a yuv420 frame, postproc 0..3.
  * Written as whole-image stage functions over a private copy of libhb's buffer layout:
  *   - every work buffer is one allocation holding the three planes back to back with libhb's
  *     64-byte stride (hb_frame_buffer_init), zero slack in front and behind, because several
@@ -25,6 +25,7 @@ typedef struct
     uint8_t *half[4], *full[5];     /* SRCPF MSKPF TMPPF DSTPF ; DST2PF TMP2PF2 MSK2PF TMP2PF DST2MPF */
     int lim[33];
     int mthresh, vthresh, lthresh, dstr, estr, nt, maxd, pp;
+    int *deriv[3][4];               /* postproc 2/3: x2, y2, xy, tmp per plane (see post_process_corner_stage) */
 } eedi2_t;
 
 static const int limlut_base[33] = { 6, 6, 7, 7, 8, 8, 9, 9, 9, 10, 10, 11, 11, 12, 12, 12, 12, 12, 12, 12,
@@ -79,6 +80,9 @@ void *oracle_eedi2_create(int width, int height, int depth, int mthresh, int vth
     const size_t tail = (size_t)4 * e->pitch[0] * e->bps;
     for (int k = 0; k < 4; k++) e->half[k] = (uint8_t *)calloc(1, LEAD + e->hbytes + tail) + LEAD;
     for (int k = 0; k < 5; k++) e->full[k] = (uint8_t *)calloc(1, LEAD + e->fbytes + tail) + LEAD;
+    if (pp > 1)
+        for (int p = 0; p < 3; p++)
+            for (int k = 0; k < 4; k++) e->deriv[p][k] = calloc((size_t)e->pitch[p] * (HH[p] + 1) + 16, sizeof(int));
     for (int i = 0; i < 33; i++)
         e->lim[i] = e->bps == 2 ? (uint16_t)(((uint16_t)limlut_base[i]) << e->shift) : (uint8_t)(((uint8_t)limlut_base[i]) << e->shift);
     return e;
@@ -90,6 +94,8 @@ void oracle_eedi2_destroy(void *ev)
     if (!e) return;
     for (int k = 0; k < 4; k++) free(e->half[k] - LEAD);
     for (int k = 0; k < 5; k++) free(e->full[k] - LEAD);
+    for (int p = 0; p < 3; p++)
+        for (int k = 0; k < 4; k++) free(e->deriv[p][k]);
     free(e);
 }
 
@@ -550,6 +556,109 @@ static void post_process(const eedi2_t *e, const uint8_t *nmskp, const uint8_t *
         }
 }
 
+/* ------------------------------------------------------------------ postproc 2/3: junctions and corners
+ * (eedi2 template :1391-1904, called from decomb template :431-440).
+ *
+ * The reference's two blurs are written out as one expression per edge case.  Read together they say: a symmetric
+ * kernel whose tap at distance k that would fall outside [0,n) is replaced by its point reflection through the centre
+ * sample (x-k <-> x+k, hence the doubled weights), with ONE exception: in the horizontal pass of gaussian_blur_sqrt2
+ * at x = width-2 the distance-3 tap reads srcp[x+3] for both sides (:1625) -- one element past the row, i.e. stride
+ * padding or the next row's second element.  The vertical pass of that blur divides by a further 4 (>> 18).
+ *
+ * The reference runs its three plane threads concurrently over ONE set of scratch arrays (decomb.c:396-403, template
+ * :380-383: a data race) and the exception above reads elements nothing ever wrote (malloc memory).  The contract
+ * restated here is the race-free reading: every plane owns its scratch arrays, zero-filled when the filter starts. */
+static const int blur1_taps[4] = { 26152, 15862, 3539, 291 };
+static const int blur_sqrt2_taps[5] = { 18508, 14415, 6809, 1951, 339 };
+
+static int blur_sample(const int *p, ptrdiff_t step, int i, int n, const int *taps, int radius, int typo_at, int typo_tap)
+{
+    int acc = p[0] * taps[0] + 32768;
+    for (int k = 1; k <= radius; k++)
+    {
+        int a = i - k >= 0 ? -k : k, b = i + k <= n - 1 ? k : -k;
+        if (i == typo_at && k == typo_tap) a = b = k;
+        acc += (p[a * step] + p[b * step]) * taps[k];
+    }
+    return acc;
+}
+
+/* int arrays, horizontal then vertical; src == dst allowed (tmp holds the intermediate) */
+static void blur_int(const int *src, int *tmp, int *dst, int pitch, int height, int width, const int *taps, int radius,
+                     int typo, int vshift)
+{
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+            tmp[(size_t)y * pitch + x] = blur_sample(src + (size_t)y * pitch + x, 1, x, width, taps, radius,
+                                                     typo ? width - 2 : -1, 3) >> 16;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+            dst[(size_t)y * pitch + x] = blur_sample(tmp + (size_t)y * pitch + x, pitch, y, height, taps, radius, -1, 0) >> vshift;
+}
+
+void oracle_eedi2_gaussian_blur_sqrt2(const int *src, int *tmp, int *dst, int pitch, int height, int width)
+{
+    blur_int(src, tmp, dst, pitch, height, width, blur_sqrt2_taps, 4, 1, 18);
+}
+
+/* pixel planes (:1402-1527); dst may be src */
+void oracle_eedi2_gaussian_blur1(const void *src, void *tmp, void *dst, int pitch, int height, int width, int bps)
+{
+    eedi2_t e = { .bps = bps };
+    int *a = malloc(((size_t)pitch * height + 8) * sizeof(int)), *b = malloc(((size_t)pitch * height + 8) * sizeof(int));
+    for (size_t i = 0; i < (size_t)pitch * height; i++) a[i] = rd(&e, src, (ptrdiff_t)i);
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+        {
+            b[(size_t)y * pitch + x] = pixwrap(&e, blur_sample(a + (size_t)y * pitch + x, 1, x, width, blur1_taps, 3, -1, 0) >> 16);
+            wr(&e, tmp, (ptrdiff_t)y * pitch + x, b[(size_t)y * pitch + x]);
+        }
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+            wr(&e, dst, (ptrdiff_t)y * pitch + x, blur_sample(b + (size_t)y * pitch + x, pitch, y, height, blur1_taps, 3, -1, 0) >> 16);
+    free(a); free(b);
+}
+
+/* central differences, one-sided at the plane's edges, scaled back to 8 bits (:1756-1845) */
+void oracle_eedi2_calc_derivatives(const void *src, int pitch, int height, int width, int *x2, int *y2, int *xy, int depth)
+{
+    eedi2_t e = { .bps = depth > 8 ? 2 : 1 };
+    const int shift = depth - 8;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+        {
+            const ptrdiff_t o = (ptrdiff_t)y * pitch;
+            const int Ix = (rd(&e, src, o + imin(x + 1, width - 1)) - rd(&e, src, o + imax(x - 1, 0))) >> shift;
+            const int Iy = (rd(&e, src, (ptrdiff_t)imax(y - 1, 0) * pitch + x) - rd(&e, src, (ptrdiff_t)imin(y + 1, height - 1) * pitch + x)) >> shift;
+            x2[o + x] = (Ix * Ix) >> 1;
+            y2[o + x] = (Iy * Iy) >> 1;
+            xy[o + x] = (Ix * Iy) >> 1;
+        }
+}
+
+static int corner_response(int a, int b, int c)        /* Harris-style test value (:1882-1885) */
+{
+    return (int)(a * b - c * c - 0.09 * (a + b) * (a + b));
+}
+
+/* full-height plane rows y = 8-field, +2, ... < height-7 against derivative rows 3, 4, ... (:1864-1900) */
+void oracle_eedi2_post_process_corner(const int *x2, const int *y2, const int *xy, int pitch, const void *mskp, void *dstp,
+                                      int height, int width, int field, int depth)
+{
+    eedi2_t e = { .bps = depth > 8 ? 2 : 1 };
+    const int neutral = 1 << (depth - 1), peak = (1 << depth) - 1;
+    for (int y = 8 - field, r = 3; y < height - 7; y += 2, r++)
+        for (int x = 4; x < width - 4; x++)
+        {
+            const ptrdiff_t o = (ptrdiff_t)y * pitch + x;
+            const int m = rd(&e, mskp, o);
+            if (m == peak || m == neutral) continue;
+            const size_t d = (size_t)r * pitch + x;
+            if (corner_response(x2[d], y2[d], xy[d]) > 775 || corner_response(x2[d + pitch], y2[d + pitch], xy[d + pitch]) > 775)
+                wr(&e, dstp, o, (rd(&e, dstp, o - pitch) + rd(&e, dstp, o + pitch) + 1) >> 1);
+        }
+}
+
 /* one field: `cur` = packed planar frame (tight rows); tff = pv->tff (decomb.c:539-542).  Result (full frame,
  * tight rows) into `out`.  The handle carries the edge-mask state from call to call. */
 void oracle_eedi2_field(void *ev, const uint8_t *cur, int tff, uint8_t *out)
@@ -593,6 +702,16 @@ void oracle_eedi2_field(void *ev, const uint8_t *cur, int tff, uint8_t *out)
             dir_map(e, msk2p, tmp2p, dst2mp, pitch, width, height, 0, 1, tff);
             dir_map(e, msk2p, dst2mp, tmp2p, pitch, width, height, 1, 1, tff);
             post_process(e, tmp2p, tmp2p2, dst2p, pitch, width, height, tff);
+        }
+        if (e->pp == 2 || e->pp == 3)
+        {
+            int *cx2 = e->deriv[pl][0], *cy2 = e->deriv[pl][1], *cxy = e->deriv[pl][2], *tmpc = e->deriv[pl][3];
+            oracle_eedi2_gaussian_blur1(srcp, tmpp, srcp, pitch, hh, width, e->bps);
+            oracle_eedi2_calc_derivatives(srcp, pitch, hh, width, cx2, cy2, cxy, e->depth);
+            oracle_eedi2_gaussian_blur_sqrt2(cx2, tmpc, cx2, pitch, hh, width);
+            oracle_eedi2_gaussian_blur_sqrt2(cy2, tmpc, cy2, pitch, hh, width);
+            oracle_eedi2_gaussian_blur_sqrt2(cxy, tmpc, cxy, pitch, hh, width);
+            oracle_eedi2_post_process_corner(cx2, cy2, cxy, pitch, tmp2p2, dst2p, height, width, tff, e->depth);
         }
         for (int y = 0; y < height; y++)
             memcpy(out + in_off + (size_t)y * width * e->bps, dst2p + (size_t)y * pitch * e->bps, (size_t)width * e->bps);

@@ -93,6 +93,13 @@ void *oracle_eedi2_create(int width, int height, int depth, int mthresh, int vth
                           int nt, int maxd, int pp);
 void  oracle_eedi2_destroy(void *e);
 void  oracle_eedi2_field(void *e, const uint8_t *cur, int tff, uint8_t *out);
+/* the four stages of postproc 2/3 (eedi2 template :1391-1904), exposed so that each can be pinned against the
+ * reference's exported function of the same name (the reference's own chain races, see eedi2_port.c) */
+void  oracle_eedi2_gaussian_blur1(const void *src, void *tmp, void *dst, int pitch, int height, int width, int bps);
+void  oracle_eedi2_calc_derivatives(const void *src, int pitch, int height, int width, int *x2, int *y2, int *xy, int depth);
+void  oracle_eedi2_gaussian_blur_sqrt2(const int *src, int *tmp, int *dst, int pitch, int height, int width);
+void  oracle_eedi2_post_process_corner(const int *x2, const int *y2, const int *xy, int pitch, const void *mskp, void *dstp,
+                                       int height, int width, int field, int depth);
 
 /* whole clip through hb_decomb_work/process_frame (decomb.c:500-612).  flags/combed: per input
  * frame s.flags and s.combed; out must hold 2*n_in frames; returns the number of output frames.
@@ -100,6 +107,10 @@ void  oracle_eedi2_field(void *e, const uint8_t *cur, int tff, uint8_t *out);
 int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const uint8_t *combed,
                        int width, int height, int depth, int mode, int parity_setting,
                        uint8_t *out, int *out_src);
+/* same with the EEDI2 `postproc` setting (0..3; oracle_decomb_clip uses the default 1) */
+int oracle_decomb_clip_pp(const uint8_t *in, int n_in, const uint16_t *flags, const uint8_t *combed,
+                          int width, int height, int depth, int mode, int parity_setting, int postproc,
+                          uint8_t *out, int *out_src);
 
 /* ---------------- lapsharp (libhb/lapsharp.c) ---------------- */
 /* one plane WITH its strides (bytes); kernel_id 0 lap, 1 isolap, 2 log, 3 isolog */

@@ -89,7 +89,7 @@ OraclePort.comb_detect_clip = comb_detect_clip
 OraclePort.comb_detect_masks = comb_detect_masks
 
 
-def decomb_clip(self, clip, width, height, depth, mode, parity=-1, flags=None, combed=None):
+def decomb_clip(self, clip, width, height, depth, mode, parity=-1, flags=None, combed=None, postproc=1):
     """-> (out frames, source index per output)"""
     clip = np.ascontiguousarray(clip, dtype=np.uint8)
     n = clip.shape[0]
@@ -97,12 +97,12 @@ def decomb_clip(self, clip, width, height, depth, mode, parity=-1, flags=None, c
     src = np.zeros(2 * n, np.int32)
     fl = np.ascontiguousarray(flags, np.uint16) if flags is not None else None
     cb = np.ascontiguousarray(combed, np.uint8) if combed is not None else None
-    self.lib.oracle_decomb_clip.restype = C.c_int
-    self.lib.oracle_decomb_clip.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    k = self.lib.oracle_decomb_clip(clip.ctypes.data, n, fl.ctypes.data if fl is not None else None,
-                                    cb.ctypes.data if cb is not None else None, width, height, depth, mode, parity,
-                                    out.ctypes.data, src.ctypes.data)
+    self.lib.oracle_decomb_clip_pp.restype = C.c_int
+    self.lib.oracle_decomb_clip_pp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    k = self.lib.oracle_decomb_clip_pp(clip.ctypes.data, n, fl.ctypes.data if fl is not None else None,
+                                       cb.ctypes.data if cb is not None else None, width, height, depth, mode, parity,
+                                       postproc, out.ctypes.data, src.ctypes.data)
     return out[:k], src[:k]
 
 
