@@ -7,6 +7,7 @@
 //   filter_map :538-635   filter_dir_map :649-709   expand_dir_map :722-773
 //   mark_directions_2x :787-858   filter_dir_map_2x :872-939   expand_dir_map_2x :953-1011
 //   fill_gaps_2x :1025-1132   interpolate_lattice :1148-1335   post_process :1349-1378
+//   gaussian_blur1 :1402-1527   gaussian_blur_sqrt2 :1540-1745   calc_derivatives :1756-1845   post_process_corner :1864-1900
 // The reference runs the three planes on three CPU threads; here every stage is one kernel per
 // plane on the decomb stream (planes are independent, stages are ordered by the stream).
 //
@@ -1161,6 +1162,85 @@ __global__ void __launch_bounds__(256) k_post_process(const PIX *__restrict__ nm
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// postproc 2/3: junctions and corners (:1391-1904, called from decomb template :431-440)
+//
+// The reference writes its two blurs out as one expression per edge case.  Read together: a symmetric kernel whose tap
+// at distance k that would fall outside [0,n) is replaced by its point reflection through the centre sample
+// (x-k <-> x+k, hence the doubled weights) -- with one exception, reproduced: the horizontal pass of
+// gaussian_blur_sqrt2 at x = width-2 reads srcp[x+3] for both distance-3 taps (:1625), one element past the row
+// (stride padding, or the next row's second element when pitch == width).
+// The reference shares ONE set of scratch arrays between its three concurrently running plane threads (decomb.c:396-403:
+// a data race) and that exception reads elements nothing ever wrote.  Implemented is the race-free reading: every plane
+// owns its four scratch arrays, zero-filled at create.
+struct BlurTaps { int v[5]; int radius; };
+
+template <typename Load>
+__device__ __forceinline__ int blur_sample(Load ld, int i, int n, const BlurTaps &t, int typo_at)
+{
+    int acc = ld(0) * t.v[0] + 32768;
+#pragma unroll 4
+    for (int k = 1; k <= t.radius; k++)
+    {
+        int a = i - k >= 0 ? -k : k, b = i + k <= n - 1 ? k : -k;
+        if (k == 3 && i == typo_at) a = b = k;
+        acc += (ld(a) + ld(b)) * t.v[k];
+    }
+    return acc;
+}
+
+// T = pixel type (gaussian_blur1, :1402-1527) or int (gaussian_blur_sqrt2, :1540-1745); VERT selects the pass
+template <typename T, bool VERT>
+__global__ void __launch_bounds__(256) k_blur(const T *__restrict__ src, T *__restrict__ dst, int pitch, int width, int height,
+                                              BlurTaps taps, int typo_at, int shift)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const T *p = src + (size_t)y * pitch + x;
+    const int acc = VERT ? blur_sample([&](int d) { return (int)p[(ptrdiff_t)d * pitch]; }, y, height, taps, -1)
+                         : blur_sample([&](int d) { return (int)p[d]; }, x, width, taps, typo_at);
+    dst[(size_t)y * pitch + x] = (T)(acc >> shift);
+}
+
+// calc_derivatives (:1756-1845): central differences, one-sided at the plane's edges, scaled back to 8 bits
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_derivatives(const PIX *__restrict__ src, int *__restrict__ x2, int *__restrict__ y2, int *__restrict__ xy,
+                                                     int pitch, int width, int height, int shift)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const PIX *row = src + (size_t)y * pitch;
+    const int Ix = ((int)row[min(x + 1, width - 1)] - (int)row[max(x - 1, 0)]) >> shift;
+    const int Iy = ((int)src[(size_t)max(y - 1, 0) * pitch + x] - (int)src[(size_t)min(y + 1, height - 1) * pitch + x]) >> shift;
+    const size_t o = (size_t)y * pitch + x;
+    x2[o] = (Ix * Ix) >> 1;
+    y2[o] = (Iy * Iy) >> 1;
+    xy[o] = (Ix * Iy) >> 1;
+}
+
+__device__ __forceinline__ int corner_response(int a, int b, int c)      // :1882-1885, double arithmetic without contraction
+{
+    const double s = (double)(a + b);
+    return __double2int_rz(__dsub_rn((double)(a * b - c * c), __dmul_rn(__dmul_rn(0.09, s), s)));
+}
+
+// post_process_corner (:1864-1900): picture rows y = 8-field, +2, ... < height-7 against derivative rows 3, 4, ...
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_corner(const int *__restrict__ x2, const int *__restrict__ y2, const int *__restrict__ xy,
+                                                const PIX *__restrict__ mskp, PIX *__restrict__ dstp, int pitch, int width, int height,
+                                                int field, int depth)
+{
+    const int x = 4 + blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int y = 8 - field + 2 * r;
+    if (x >= width - 4 || y >= height - 7) return;
+    const size_t o = (size_t)y * pitch + x;
+    const int m = mskp[o];
+    if (m == (1 << depth) - 1 || m == 1 << (depth - 1)) return;
+    const size_t d = (size_t)(r + 3) * pitch + x;
+    if (corner_response(x2[d], y2[d], xy[d]) > 775 || corner_response(x2[d + pitch], y2[d + pitch], xy[d + pitch]) > 775)
+        dstp[o] = (PIX)(((int)dstp[o - pitch] + (int)dstp[o + pitch] + 1) >> 1);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1174,6 +1254,7 @@ struct Eedi2
     size_t half_off[3], full_off[3], half_bytes, full_bytes;
     uint8_t *half_mem[4], *full_mem[5];      // allocation starts (incl. lead slack)
     LatticeTmp *lattice_tmp, *lattice_tmp_pl[3];   // one allocation, a private region per plane (the planes run side by side)
+    int *deriv_mem, *deriv[3][4];                   // postproc 2/3: x2, y2, xy, tmp per plane (pitch x (field rows + 1), zeroed)
     cudaStream_t s_aux[2];                          // chroma planes' branches of the captured graph
     cudaEvent_t ev_fork, ev_join[2];
     Lim lim;
@@ -1278,6 +1359,25 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
         LAUNCH((k_dir_map<PIX, true, true><<<gridv(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
         LAUNCH((k_post_process<PIX><<<gridv(width, rows2), blk, 0, st>>>(tmp2p, tmp2p2, dst2p, pitch, width, height, tff, depth, e->lim)));
     }
+    if (c.pp == 2 || c.pp == 3)
+    {
+        // filter junctions and corners (decomb template :431-440): blur the field in place, structure tensor of the
+        // blurred field, blur its three components, then replace flagged interpolated samples by the vertical average
+        const BlurTaps t1 = { { 26152, 15862, 3539, 291, 0 }, 3 }, t2 = { { 18508, 14415, 6809, 1951, 339 }, 4 };
+        int *cx2 = e->deriv[pl][0], *cy2 = e->deriv[pl][1], *cxy = e->deriv[pl][2], *tmpc = e->deriv[pl][3];
+        LAUNCH((k_blur<PIX, false><<<grid2(width, hh), blk, 0, st>>>(srcp, tmpp, pitch, width, hh, t1, -1, 16)));
+        LAUNCH((k_blur<PIX, true><<<grid2(width, hh), blk, 0, st>>>(tmpp, srcp, pitch, width, hh, t1, -1, 16)));
+        LAUNCH((k_derivatives<PIX><<<grid2(width, hh), blk, 0, st>>>(srcp, cx2, cy2, cxy, pitch, width, hh, depth - 8)));
+        int *const comp[3] = { cx2, cy2, cxy };
+        for (int k = 0; k < 3; k++)
+        {
+            LAUNCH((k_blur<int, false><<<grid2(width, hh), blk, 0, st>>>(comp[k], tmpc, pitch, width, hh, t2, width - 2, 16)));
+            LAUNCH((k_blur<int, true><<<grid2(width, hh), blk, 0, st>>>(tmpc, comp[k], pitch, width, hh, t2, -1, 18)));
+        }
+        const int crows = (height - 7 - (8 - tff) + 1) / 2;
+        if (crows > 0 && width > 8)
+            LAUNCH((k_corner<PIX><<<grid2(width - 8, crows), blk, 0, st>>>(cx2, cy2, cxy, tmp2p2, dst2p, pitch, width, height, tff, depth)));
+    }
 #undef LAUNCH
     hbcu::count_launch(launches);
     cudaError_t err = cudaGetLastError();
@@ -1302,10 +1402,19 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
             return nullptr;
         }
     }
-    if (cfg.pp > 1)
+    if (cfg.pp < 0 || cfg.pp > 3)
     {
-        set_error("eedi2: postproc %d is not implemented", cfg.pp);
+        set_error("eedi2: postproc %d is out of range", cfg.pp);
         return nullptr;
+    }
+    for (int pl = 0; pl < 3 && cfg.pp > 1; pl++)
+    {
+        if (cfg.w[pl] < 16 || cfg.h[pl] < 32)
+        {
+            // the reference's blurs spell out 4 edge columns / rows on either side; smaller planes run them into each other
+            set_error("eedi2: postproc %d needs planes of at least 16x32, plane %d is %dx%d", cfg.pp, pl, cfg.w[pl], cfg.h[pl]);
+            return nullptr;
+        }
     }
     for (int pl = 0; pl < 3; pl++)
     {
@@ -1322,6 +1431,7 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
     for (int k = 0; k < 4; k++) e->half_mem[k] = nullptr;
     for (int k = 0; k < 5; k++) e->full_mem[k] = nullptr;
     e->lattice_tmp = nullptr;
+    e->deriv_mem = nullptr;
     e->s_aux[0] = e->s_aux[1] = nullptr;
     e->ev_fork = e->ev_join[0] = e->ev_join[1] = nullptr;
     e->stop_after = 0;
@@ -1383,6 +1493,16 @@ Eedi2 *eedi2_create(const Eedi2Config &cfg)
         e->lattice_tmp_pl[1] = e->lattice_tmp_pl[0] + n[0];
         e->lattice_tmp_pl[2] = e->lattice_tmp_pl[1] + n[1];
     }
+    if (cfg.pp > 1)
+    {
+        size_t n[3], total = 0;
+        for (int pl = 0; pl < 3; pl++) { n[pl] = ((size_t)cfg.pitch[pl] * (e->half_h[pl] + 1) + 31) / 32 * 32; total += 4 * n[pl]; }
+        if (ok) ok = cudaMalloc(&e->deriv_mem, sizeof(int) * total) == cudaSuccess &&
+                     cudaMemset(e->deriv_mem, 0, sizeof(int) * total) == cudaSuccess;
+        int *p = e->deriv_mem;
+        for (int pl = 0; pl < 3; pl++)
+            for (int k = 0; k < 4; k++) { e->deriv[pl][k] = p; p += n[pl]; }
+    }
     if (ok) ok = cudaStreamCreateWithFlags(&e->s_aux[0], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaStreamCreateWithFlags(&e->s_aux[1], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -1430,6 +1550,7 @@ void eedi2_destroy(Eedi2 *e)
     for (int k = 0; k < 4; k++) if (e->half_mem[k]) cudaFree(e->half_mem[k]);
     for (int k = 0; k < 5; k++) if (e->full_mem[k]) cudaFree(e->full_mem[k]);
     if (e->lattice_tmp) cudaFree(e->lattice_tmp);
+    if (e->deriv_mem) cudaFree(e->deriv_mem);
     for (int i = 0; i < 2; i++)
     {
         if (e->s_aux[i]) cudaStreamDestroy(e->s_aux[i]);

@@ -122,14 +122,6 @@ static int decomb_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
             hb_dict_extract_int(&cfg.post_processing, dict, "postproc");
         }
     }
-    if ((pv->mode & HBCU_DECOMB_EEDI2) && cfg.post_processing > 1)
-    {
-        /* junction/corner post-processing (eedi2 template :1391-1904) is racy in the reference itself
-         * (scratch shared by its three plane threads) and reached by no preset */
-        hb_error("decomb(cuda): EEDI2 postproc %d is not implemented on the GPU path", cfg.post_processing);
-        goto fail;
-    }
-
     cfg.width          = init->geometry.width;
     cfg.height         = init->geometry.height;
     cfg.depth          = desc->comp[0].depth;
