@@ -23,8 +23,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
-CU_SOURCES = ["hbcu_core.cu", "hbcu_frames.cu", "nlmeans.cu", "comb_detect.cu", "decomb.cu", "eedi2.cu", "lapsharp.cu", "unsharp.cu", "hqdn3d.cu"]
-C_SOURCES = ["hb_runtime.c", "hb_harness.c", "hb_bench.c", "hbcu_registry.c", "hbcu_pinned.c", "hbcu_device_frames.c", "nlmeans_cuda.c", "comb_detect_cuda.c", "decomb_cuda.c", "lapsharp_cuda.c", "unsharp_cuda.c", "denoise_cuda.c"]
+CU_SOURCES = ["hbcu_core.cu", "hbcu_frames.cu", "nlmeans.cu", "comb_detect.cu", "decomb.cu", "eedi2.cu", "lapsharp.cu", "unsharp.cu", "hqdn3d.cu", "detelecine.cu"]
+C_SOURCES = ["hb_runtime.c", "hb_harness.c", "hb_bench.c", "hbcu_registry.c", "hbcu_pinned.c", "hbcu_device_frames.c", "nlmeans_cuda.c", "comb_detect_cuda.c", "decomb_cuda.c", "lapsharp_cuda.c", "unsharp_cuda.c", "denoise_cuda.c", "detelecine_cuda.c"]
 CFLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wno-unused-function", "-D__LIBHB__", "-pthread"]
 
 

@@ -455,6 +455,7 @@ static inline void *av_malloc(size_t size) { void *p = NULL; if (posix_memalign(
 static inline void av_freep(void *arg) { void **pp = (void **)arg; free(*pp); *pp = NULL; }
 
 extern hb_filter_object_t hb_filter_denoise;
+extern hb_filter_object_t hb_filter_detelecine;
 extern hb_filter_object_t hb_filter_lapsharp;
 extern hb_filter_object_t hb_filter_unsharp;
 extern hb_filter_object_t hb_filter_chroma_smooth;

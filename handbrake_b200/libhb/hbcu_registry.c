@@ -12,6 +12,7 @@ extern hb_filter_object_t hb_filter_lapsharp_cuda;
 extern hb_filter_object_t hb_filter_unsharp_cuda;
 extern hb_filter_object_t hb_filter_denoise_cuda;
 extern hb_filter_object_t hb_filter_chroma_smooth_cuda;
+extern hb_filter_object_t hb_filter_detelecine_cuda;
 
 hb_filter_object_t *hb_filter_get(int filter_id)
 {
@@ -24,6 +25,7 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_UNSHARP:     return &hb_filter_unsharp_cuda;
         case HB_FILTER_DENOISE:     return &hb_filter_denoise_cuda;    /* hqdn3d */
         case HB_FILTER_CHROMA_SMOOTH: return &hb_filter_chroma_smooth_cuda;
+        case HB_FILTER_DETELECINE:  return &hb_filter_detelecine_cuda;    /* pullup: metrics on the device, decisions on the host */
         default:                return NULL;
     }
 }

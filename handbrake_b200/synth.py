@@ -117,3 +117,49 @@ def split_planes(frame, pix_fmt, width, height):
         out.append(a[off:off + w * h].reshape(h, w))
         off += w * h
     return out
+
+
+PIC_FLAG_REPEAT_FIRST_FIELD = 0x0100
+
+
+def weave(top_frame, bottom_frame, pix_fmt, width, height):
+    """picture whose even lines come from top_frame and odd lines from bottom_frame (all planes)"""
+    depth = depth_of(pix_fmt)
+    dt = np.uint16 if depth > 8 else np.uint8
+    out = []
+    for a, b in zip(split_planes(top_frame, pix_fmt, width, height), split_planes(bottom_frame, pix_fmt, width, height)):
+        c = a.copy()
+        c[1::2] = b[1::2]
+        out.append(c.astype(dt).reshape(-1))
+    return np.concatenate(out).view(np.uint8)
+
+
+def telecined_clip(pix_fmt, width, height, n_film, seed=12345, noise=3, tff=True, soft=False, video_tail=0):
+    """24 -> 30 pulldown of n_film synthetic film frames (a multiple of 4 keeps the cadence whole).
+    hard: fields woven 2:3:2:3 into pictures (At Ab | Bt Bb | Bt Cb | Ct Db | Dt Db for TFF), flags carry only the field order;
+    soft: the film frames themselves with REPEAT_FIRST_FIELD on every other one, as an MPEG-2 soft-telecined stream has them.
+    video_tail: that many truly interlaced pictures appended (the cadence breaks).  Returns (clip, flags)."""
+    film = [progressive_frame(pix_fmt, width, height, 3 * t, seed, noise) for t in range(n_film)]
+    order = PIC_FLAG_TOP_FIELD_FIRST if tff else 0
+    frames, flags = [], []
+    if soft:
+        first_is_top = tff
+        for t, f in enumerate(film):
+            rff = t % 2 == 0
+            frames.append(f)
+            flags.append((PIC_FLAG_TOP_FIELD_FIRST if first_is_top else 0) | (PIC_FLAG_REPEAT_FIRST_FIELD if rff else 0) | PIC_FLAG_PROGRESSIVE_FRAME)
+            if rff:
+                first_is_top = not first_is_top
+    else:
+        fields = []                                     # film frame index per field, in display order
+        for t in range(n_film):
+            fields += [t] * (3 if t % 2 else 2)
+        for k in range(0, len(fields) - 1, 2):
+            first, second = film[fields[k]], film[fields[k + 1]]
+            top, bottom = (first, second) if tff else (second, first)
+            frames.append(weave(top, bottom, pix_fmt, width, height))
+            flags.append(order)
+    for t in range(video_tail):
+        frames.append(interlaced_frame(pix_fmt, width, height, 100 + t, seed))
+        flags.append(order)
+    return np.stack(frames), np.array(flags, np.uint16)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HBCU_ABI_VERSION 3
+#define HBCU_ABI_VERSION 4
 
 /* ------------------------------------------------------------------------- */
 /* runtime                                                                    */
@@ -360,6 +360,58 @@ int  hbcu_hqdn3d_poll(hbcu_hqdn3d_t *h, int64_t ticket);
 int  hbcu_hqdn3d_sync(hbcu_hqdn3d_t *h);
 int  hbcu_hqdn3d_mark(hbcu_hqdn3d_t *h, int which);
 int  hbcu_hqdn3d_elapsed_ms(hbcu_hqdn3d_t *h, float *ms);
+
+/* ------------------------------------------------------------------------- */
+/* detelecine   replaces the data-parallel half of pullup (libhb/detelecine.c): */
+/*              pullup_compute_metric + pullup_diff_y/licomb_y/var_y (:159-265), */
+/*              the max-reductions inside pullup_compute_breaks (:345-380) and   */
+/*              pullup_compute_affinity (:382-434), pullup_copy_field (:298-317) */
+/* ------------------------------------------------------------------------- */
+/* The field-queue state machine (what to compare with what, how long a frame is, which fields make it) is control
+ * flow on a handful of integers; it stays on the host (handbrake_b200/libhb/detelecine_cuda.c) and drives these calls.
+ * Pictures and the per-field metric arrays never leave the device.  Everything is queued on the handle's stream; only
+ * hbcu_detelecine_fetch() and hbcu_detelecine_download() wait. */
+typedef struct hbcu_detelecine_config_s
+{
+    int width, height, depth;
+    int chroma_shift_w, chroma_shift_h;
+    int device;
+    int pictures;              /* picture buffers (pullup's nbuffers, >= 10, detelecine.c:601-607) */
+    int fields;                /* metric slots, one per node of the field queue (9 to start with, :623) */
+    int results;               /* reduction result slots */
+    int metric_plane;
+    int junk_left, junk_right; /* in units of 8 pixels  (:615-618) */
+    int junk_top, junk_bottom; /* in units of 2 lines */
+} hbcu_detelecine_config_t;
+
+typedef struct hbcu_detelecine_s hbcu_detelecine_t;
+
+int  hbcu_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_config_t *cfg);
+void hbcu_detelecine_destroy(hbcu_detelecine_t *h);
+/* picture <- host planes with their strides (hb_image_copy_plane semantics: whole strides when they agree) */
+int  hbcu_detelecine_upload(hbcu_detelecine_t *h, int picture, const void *const planes[3], const int strides[3]);
+/* the three metric arrays of field slot `field` = field `parity` of `picture` (pullup_submit_field :973-978):
+ *   diffs against the same-parity field of diff_picture: -1 leaves the array as it is (the partner has no buffer, :242),
+ *         == picture zeroes it (the duplicate-field shortcut, :244-249);
+ *   comb  between the top field of comb_top_picture and the bottom field of comb_bottom_picture; -1 leaves it as it is;
+ *   var   of the field itself. */
+int  hbcu_detelecine_metrics(hbcu_detelecine_t *h, int field, int picture, int parity,
+                             int diff_picture, int comb_top_picture, int comb_bottom_picture);
+/* result[slot] = { max(0, max_i l_i), max(0, max_i -l_i) } with
+ *   breaks:   l_i = diffs2[i] - diffs3[i]                                                    (:369-374)
+ *   affinity: l_i = max(0, comb[i] - (v+lv) + |v-lv|) - max(0, comb_next[i] - (v+rv) + |v-rv|),
+ *             v = var[i], lv = var_prev[i], rv = var_next[i]                                  (:405-418) */
+int  hbcu_detelecine_breaks(hbcu_detelecine_t *h, int field2, int field3, int slot);
+int  hbcu_detelecine_affinity(hbcu_detelecine_t *h, int field_prev, int field, int field_next, int slot);
+/* waits for everything queued so far; dst <- result slots [0, nslots) (2 ints each) */
+int  hbcu_detelecine_fetch(hbcu_detelecine_t *h, int *dst, int nslots);
+/* lines of `parity` (whole strides) of src_picture -> dst_picture */
+int  hbcu_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_picture, int parity);
+/* picture -> host planes (plane height x stride bytes each, as the reference's memcpy of size[p], :1250-1252); waits */
+int  hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3]);
+/* benchmark hooks as for the other handles */
+int  hbcu_detelecine_mark(hbcu_detelecine_t *h, int which);
+int  hbcu_detelecine_elapsed_ms(hbcu_detelecine_t *h, float *ms);
 
 #ifdef __cplusplus
 }

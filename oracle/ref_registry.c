@@ -15,6 +15,7 @@ hb_filter_object_t *hb_filter_get(int filter_id)
         case HB_FILTER_DENOISE:     return &hb_filter_denoise;
         case HB_FILTER_UNSHARP:     return &hb_filter_unsharp;
         case HB_FILTER_CHROMA_SMOOTH: return &hb_filter_chroma_smooth;
+        case HB_FILTER_DETELECINE:  return &hb_filter_detelecine;
         case HB_FILTER_MT_FRAME:    return &hb_filter_mt_frame;
         default:                    return NULL;
     }

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) > 40
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.hbcu_abi_version() == 3
+    assert lib.hbcu_abi_version() == 4
 
 
 def test_filter_objects_exported_with_reference_ids():
@@ -42,7 +42,7 @@ def test_filter_objects_exported_with_reference_ids():
     expect = {"hb_filter_nlmeans_cuda": (16, b"nlmeans"), "hb_filter_comb_detect_cuda": (4, b"comb-detect"),
               "hb_filter_decomb_cuda": (6, b"decomb"), "hb_filter_lapsharp_cuda": (24, b"lapsharp"),
               "hb_filter_unsharp_cuda": (26, b"unsharp"), "hb_filter_chroma_smooth_cuda": (17, b"chromasmooth"),
-              "hb_filter_denoise_cuda": (14, b"hqdn3d")}
+              "hb_filter_denoise_cuda": (14, b"hqdn3d"), "hb_filter_detelecine_cuda": (3, b"detelecine")}
     for sym, (fid, short) in expect.items():
         obj = FilterObject.in_dll(flt.lib, sym)
         assert obj.id == fid and obj.short_name == short and obj.enforce_order == 1
@@ -59,7 +59,7 @@ def test_templates_match_reference(ref):
     for a, b in (("hb_filter_nlmeans_cuda", "hb_filter_nlmeans"), ("hb_filter_comb_detect_cuda", "hb_filter_comb_detect"),
                  ("hb_filter_decomb_cuda", "hb_filter_decomb"), ("hb_filter_lapsharp_cuda", "hb_filter_lapsharp"),
                  ("hb_filter_unsharp_cuda", "hb_filter_unsharp"), ("hb_filter_chroma_smooth_cuda", "hb_filter_chroma_smooth"),
-                 ("hb_filter_denoise_cuda", "hb_filter_denoise")):
+                 ("hb_filter_denoise_cuda", "hb_filter_denoise"), ("hb_filter_detelecine_cuda", "hb_filter_detelecine")):
         assert Head.in_dll(flt.lib, a).settings_template == Head.in_dll(ref.lib, b).settings_template, a
 
 
@@ -72,7 +72,8 @@ def test_no_cpu_fallback_without_gpu():
     w, h = 64, 48
     clip = synth.progressive_clip(synth.PIX_FMT_YUV420P, w, h, 2)
     for name in ("hb_filter_nlmeans_cuda", "hb_filter_comb_detect_cuda", "hb_filter_decomb_cuda", "hb_filter_lapsharp_cuda",
-                 "hb_filter_unsharp_cuda", "hb_filter_chroma_smooth_cuda", "hb_filter_denoise_cuda", "hb_filter_hbcu_upload"):
+                 "hb_filter_unsharp_cuda", "hb_filter_chroma_smooth_cuda", "hb_filter_denoise_cuda", "hb_filter_detelecine_cuda",
+                 "hb_filter_hbcu_upload"):
         g = flt.run(name, None, clip, synth.PIX_FMT_YUV420P, w, h)
         assert g.init_failed == 1 and np.array_equal(g.frames, clip)
     lib.hbcu_last_error.restype = C.c_char_p
