@@ -217,6 +217,17 @@ def main():
         return r
     jobs.append(("4k_hqdn3d", hqdn3d_job))
 
+    def detelecine_job():
+        depth = 8; fmt = fmt_of(depth)
+        fb = synth.frame_bytes(fmt, W, H)
+        # one 2:3 cadence cycle (4 film frames -> 5 pictures), bottom field first: the bench harness sets no TFF flag
+        host, _ = synth.telecined_clip(fmt, W, H, 4, tff=False)
+        core.hbcu_host_reserve(fb + 4096, 3 * n + 24)
+        r = {"workload": "4k_detelecine", "desc": "3840x2160 yuv420p 8-bit, hard 2:3 pulldown, detelecine defaults"}
+        r.update(e2e_and_cpu(flt, ref, "hb_filter_detelecine_cuda", "hb_filter_detelecine", None, fmt, host, n, max(args.cpu_frames, 20)))
+        return r
+    jobs.append(("4k_detelecine", detelecine_job))
+
     def comb_job():
         depth = 10; fmt = fmt_of(depth)
         host = np.stack([synth.interlaced_frame(fmt, W, H, t) for t in range(4)])
