@@ -63,7 +63,12 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=6)
     ap.add_argument("--only", default="")
     args = ap.parse_args()
-    import torch
+
+    class _LazyTorch:                   # only the kernel-only arms need torch (device tensors); its import costs a minute on a fresh box
+        def __getattr__(self, name):
+            import torch as t
+            return getattr(t, name)
+    torch = _LazyTorch()
     core = C.CDLL(str(handbrake_b200.LIBHBCU))
     core.hbcu_last_error.restype = C.c_char_p
     flt = C.CDLL(str(handbrake_b200.LIBHBCU_FILTERS))
