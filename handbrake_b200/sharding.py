@@ -37,20 +37,23 @@ def plan_blocks(n_frames: int, world: int, block: int, halo_before: int = 0, hal
 
 
 def run_rank(blocks: List[Block], rank: int, clip_loader: Callable[[int, int], np.ndarray],
-             run_filter: Callable[[np.ndarray], np.ndarray]):
-    """Runs this rank's blocks.  `clip_loader(a, b)` returns frames [a, b); `run_filter(frames)` returns one
-    output per input frame (a look-ahead filter run to EOF: the outputs of the halo frames come from a
-    shrunken window and are discarded here -- only the true end of the clip may shrink its window)."""
+             run_filter: Callable[[np.ndarray], np.ndarray], outputs_per_frame: int = 1):
+    """Runs this rank's blocks.  `clip_loader(a, b)` returns frames [a, b); `run_filter(frames)` returns
+    `outputs_per_frame` outputs per input frame, in order (2 for a bobbing deinterlacer).  The filter is run to EOF on
+    the block plus its halo: the outputs of the halo frames come from the filter's start-of-stream / end-of-stream rules
+    (a duplicated neighbour, a shrunken look-ahead window) and are discarded here -- only the true ends of the clip see
+    those rules."""
     results = {}
+    k = outputs_per_frame
     for blk in blocks:
         if blk.rank != rank:
             continue
         frames = clip_loader(blk.load_start, blk.load_stop)
         out = run_filter(frames)
-        if out.shape[0] != frames.shape[0]:
-            raise RuntimeError("filter must return one output per input frame")
-        lo = blk.start - blk.load_start
-        results[blk.index] = out[lo:lo + (blk.stop - blk.start)]
+        if out.shape[0] != frames.shape[0] * k:
+            raise RuntimeError(f"filter must return {k} output(s) per input frame")
+        lo = (blk.start - blk.load_start) * k
+        results[blk.index] = out[lo:lo + (blk.stop - blk.start) * k]
     return results
 
 

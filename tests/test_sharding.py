@@ -38,6 +38,58 @@ def test_sharded_nlmeans_equals_unsharded_single_process():
     assert np.array_equal(got, whole)
 
 
+def _sharded(blocks, world, clip_of, run, k=1):
+    parts = {}
+    for rank in range(world):
+        parts.update(sharding.run_rank(blocks, rank, clip_of, run, outputs_per_frame=k))
+    return np.concatenate([parts[b.index] for b in blocks])
+
+
+@pytest.mark.parametrize("world,block", [(2, 3), (4, 2), (3, 1)])
+def test_sharded_comb_detect_and_decomb_equal_unsharded(ref, world, block):
+    """comb-detect and decomb (without EEDI2) are pure functions of (prev, cur, next) plus per-frame tags, so
+    a one-frame halo either side reproduces the unsharded stream -- the first-frame / end-of-stream rules of the filters
+    (duplicated neighbour, exhaustive check) fall on halo frames whose outputs are dropped.  Run with the reference's own
+    filter objects; the CUDA objects have the same stream semantics (tests/test_*_gpu.py)."""
+    from test_oracle import decomb_inputs
+    w, h, depth = 96, 64, 8
+    fmt = synth.PIX_FMT_YUV420P
+    clip, flags, combed = decomb_inputs(depth, w, h, 8, seed=3)
+    n = clip.shape[0]
+    blocks = sharding.plan_blocks(n, world, block, halo_before=1, halo_after=1)
+    window = {}
+
+    def clip_of(a, b):
+        window["range"] = (a, b)
+        return clip[a:b]
+
+    # comb-detect: the verdict travels with the frame
+    def comb(frames):
+        a, b = window["range"]
+        r = ref.run("hb_filter_comb_detect", "mode=3:motion-thresh=1:spatial-thresh=1", frames, fmt, w, h, flags=flags[a:b])
+        return np.asarray(r.combed, np.uint8).reshape(-1, 1)
+    whole = np.asarray(ref.run("hb_filter_comb_detect", "mode=3:motion-thresh=1:spatial-thresh=1", clip, fmt, w, h, flags=flags).combed, np.uint8)
+    assert len(set(whole.tolist())) > 1
+    assert np.array_equal(_sharded(blocks, world, clip_of, comb).ravel(), whole)
+
+    # decomb: one picture per frame (mode 7, selective mode 39 on the tags) and two per frame (bob, mode 23)
+    for mode, k, tags in ((7, 1, None), (39, 1, combed), (23, 2, None)):
+        def decomb(frames):
+            a, b = window["range"]
+            return ref.run("hb_filter_decomb", f"mode={mode}", frames, fmt, w, h, flags=flags[a:b], combed=None if tags is None else tags[a:b]).frames
+        whole = ref.run("hb_filter_decomb", f"mode={mode}", clip, fmt, w, h, flags=flags, combed=tags).frames
+        assert whole.shape[0] == n * k
+        assert np.array_equal(_sharded(blocks, world, clip_of, decomb, k), whole), mode
+
+
+def test_sharded_lapsharp_needs_no_halo(ref):
+    w, h = 96, 64
+    clip = synth.progressive_clip(synth.PIX_FMT_YUV420P, w, h, 7, seed=4, noise=15)
+    run = lambda fr: ref.run("hb_filter_lapsharp", "y-strength=0.3:y-kernel=isolap", fr, synth.PIX_FMT_YUV420P, w, h).frames
+    blocks = sharding.plan_blocks(7, 3, 2)
+    assert np.array_equal(_sharded(blocks, 3, lambda a, b: clip[a:b], run), run(clip))
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, {repo!r}); sys.path.insert(0, {tests!r})
