@@ -382,6 +382,13 @@ static int detelecine_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *in
     }
     filter->private_data = pv;
     pv->input = *init;
+    if (init->hw_pix_fmt == AV_PIX_FMT_CUDA)
+    {
+        /* pictures arrive in host buffers and leave in host buffers for now: inside a device-resident
+         * chain the filter has to sit before hb_filter_hbcu_upload or after hb_filter_hbcu_download */
+        hb_error("detelecine(cuda): device-resident input is not supported yet");
+        goto fail;
+    }
 
     /* :1025-1047: junk margins of at least one 8-sample column and four line pairs */
     int top = 4, bottom = 4, left = 1, right = 1, plane = 0;
@@ -473,6 +480,11 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
         return HB_FILTER_DONE;
     }
     if (pv->failed) return HB_FILTER_FAILED;
+    if (in->storage_type == HBCU_DEVICE)
+    {
+        hb_error("detelecine(cuda): got a device-resident buffer; see init");
+        return HB_FILTER_FAILED;
+    }
 
     const int picture = get_whole_picture(pv);
     if (picture == DT_NONE)
