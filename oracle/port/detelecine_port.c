@@ -4,9 +4,9 @@
  * (pullup_diff_y / pullup_licomb_y / pullup_var_y, :159-207, walked by pullup_compute_metric, :230-265), the
  * max-reductions inside pullup_compute_breaks (:369-374) and pullup_compute_affinity (:405-418) and pullup_copy_field
  * (:298-317) -- behind the SAME call interface as the device implementation (include/hbcu.h, hbcu_detelecine_*), with
- * the prefix oracle_detelecine_.
+ * the prefix oracle_hbcu_detelecine_.
  *
- * Purpose: oracle/Makefile builds _ref/libdetelecine_hostlogic.so from the product's host-side state machine
+ * Purpose: oracle/Makefile builds _ref/libhostlogic.so from (among others) the product's host-side state machine
  * (handbrake_b200/libhb/detelecine_cuda.c, compiled with the hbcu_detelecine_* names redirected here) so that the state
  * machine + this restatement can be pinned, on a machine without a GPU, against the compiled reference filter.  The
  * product library never links this file; on the GPU the same host code drives the CUDA implementation and the GPU tests
@@ -30,8 +30,7 @@ struct hbcu_detelecine_s
     int *metrics, *results;
 };
 
-static char last_error[256] = "";
-const char *oracle_detelecine_last_error(void) { return last_error; }
+void oracle_hostlogic_set_error(const char *fmt, ...);
 
 static inline int iabs(int a) { return a < 0 ? -a : a; }
 static inline int sample(const struct hbcu_detelecine_s *h, const uint8_t *p, ptrdiff_t i)
@@ -47,7 +46,7 @@ static int *metric_of(const struct hbcu_detelecine_s *h, int field, int which)
     return h->metrics + ((size_t)field * 3 + which) * h->mlen;
 }
 
-int oracle_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_config_t *cfg)
+int oracle_hbcu_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_config_t *cfg)
 {
     struct hbcu_detelecine_s *h = calloc(1, sizeof(*h));
     h->cfg = *cfg;
@@ -65,7 +64,7 @@ int oracle_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_conf
     h->mh = (h->h[mp] - ((cfg->junk_top + cfg->junk_bottom) << 1)) >> 3;
     if (h->mw < 1 || h->mh < 1)
     {
-        snprintf(last_error, sizeof(last_error), "no metric blocks");
+        oracle_hostlogic_set_error("no metric blocks");
         free(h);
         return -1;
     }
@@ -78,13 +77,13 @@ int oracle_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_conf
     return 0;
 }
 
-void oracle_detelecine_destroy(hbcu_detelecine_t *h)
+void oracle_hbcu_detelecine_destroy(hbcu_detelecine_t *h)
 {
     if (h == NULL) return;
     free(h->pictures); free(h->metrics); free(h->results); free(h);
 }
 
-int oracle_detelecine_upload(hbcu_detelecine_t *h, int picture, const void *const planes[3], const int strides[3])
+int oracle_hbcu_detelecine_upload(hbcu_detelecine_t *h, int picture, const void *const planes[3], const int strides[3])
 {
     for (int p = 0; p < 3; p++)
     {
@@ -123,7 +122,7 @@ static int block_var(const struct hbcu_detelecine_s *h, const uint8_t *a, ptrdif
     return 4 * v;
 }
 
-int oracle_detelecine_metrics(hbcu_detelecine_t *h, int field, int picture, int parity, int diff_picture, int comb_top_picture, int comb_bottom_picture)
+int oracle_hbcu_detelecine_metrics(hbcu_detelecine_t *h, int field, int picture, int parity, int diff_picture, int comb_top_picture, int comb_bottom_picture)
 {
     const int mp = h->cfg.metric_plane, pitch = h->pitch[mp];
     const ptrdiff_t fs = 2 * (pitch / h->bps);
@@ -143,7 +142,7 @@ int oracle_detelecine_metrics(hbcu_detelecine_t *h, int field, int picture, int 
     return 0;
 }
 
-int oracle_detelecine_breaks(hbcu_detelecine_t *h, int field2, int field3, int slot)
+int oracle_hbcu_detelecine_breaks(hbcu_detelecine_t *h, int field2, int field3, int slot)
 {
     const int *d2 = metric_of(h, field2, 0), *d3 = metric_of(h, field3, 0);
     int max_l = 0, max_r = 0;
@@ -158,7 +157,7 @@ int oracle_detelecine_breaks(hbcu_detelecine_t *h, int field2, int field3, int s
     return 0;
 }
 
-int oracle_detelecine_affinity(hbcu_detelecine_t *h, int field_prev, int field, int field_next, int slot)
+int oracle_hbcu_detelecine_affinity(hbcu_detelecine_t *h, int field_prev, int field, int field_next, int slot)
 {
     const int *vp = metric_of(h, field_prev, 2), *vc = metric_of(h, field, 2), *vn = metric_of(h, field_next, 2);
     const int *cc = metric_of(h, field, 1), *cn = metric_of(h, field_next, 1);
@@ -178,13 +177,13 @@ int oracle_detelecine_affinity(hbcu_detelecine_t *h, int field_prev, int field, 
     return 0;
 }
 
-int oracle_detelecine_fetch(hbcu_detelecine_t *h, int *dst, int nslots)
+int oracle_hbcu_detelecine_fetch(hbcu_detelecine_t *h, int *dst, int nslots)
 {
     if (nslots > 0) memcpy(dst, h->results, sizeof(int) * 2 * nslots);
     return 0;
 }
 
-int oracle_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_picture, int parity)
+int oracle_hbcu_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_picture, int parity)
 {
     if (dst_picture == src_picture) return 0;
     for (int p = 0; p < 3; p++)
@@ -196,7 +195,7 @@ int oracle_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_
     return 0;
 }
 
-int oracle_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3])
+int oracle_hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3])
 {
     for (int p = 0; p < 3; p++)
     {
@@ -207,5 +206,5 @@ int oracle_detelecine_download(hbcu_detelecine_t *h, int picture, void *const pl
     return 0;
 }
 
-int oracle_detelecine_mark(hbcu_detelecine_t *h, int which) { (void)h; (void)which; return 0; }
-int oracle_detelecine_elapsed_ms(hbcu_detelecine_t *h, float *ms) { (void)h; *ms = 0.f; return 0; }
+int oracle_hbcu_detelecine_mark(hbcu_detelecine_t *h, int which) { (void)h; (void)which; return 0; }
+int oracle_hbcu_detelecine_elapsed_ms(hbcu_detelecine_t *h, float *ms) { (void)h; *ms = 0.f; return 0; }

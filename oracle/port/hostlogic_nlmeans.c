@@ -1,0 +1,118 @@
+/* hostlogic_nlmeans.c -- TEST INFRASTRUCTURE (see oracle_port.h).
+ *
+ * The hbcu_nlmeans_* calls the product's host filter (handbrake_b200/libhb/nlmeans_cuda.c) makes, implemented on the CPU
+ * with the plain-C restatement of NLMeans (nlmeans_port.c).  oracle/Makefile links this with the UNTOUCHED host filter
+ * (its hbcu_* references renamed to oracle_hbcu_*) into _ref/libhostlogic.so, so that everything the host side owns --
+ * settings cascade and sanitising, strength scaling and the weight tables, look-ahead buffering, the shrinking window at
+ * EOF, output order and properties -- is pinned against the compiled reference filter on a
+ * machine without a GPU.  The weight table used here is the one the host filter hands over, not a recomputed one.
+ * Never linked into the product.
+ */
+#include "../../include/hbcu.h"
+#include "oracle_port.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct hbcu_nlmeans_s
+{
+    hbcu_nlmeans_config_t cfg;
+    int bps, w[3], h[3];
+    size_t off[3], frame_bytes;
+    int ring;
+    uint8_t *frames;            /* ring of tightly packed frames */
+    int64_t *index;             /* which frame a ring slot holds */
+};
+
+void oracle_hostlogic_set_error(const char *fmt, ...);
+
+int oracle_hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
+{
+    struct hbcu_nlmeans_s *h = calloc(1, sizeof(*h));
+    h->cfg = *cfg;
+    h->bps = cfg->depth > 8 ? 2 : 1;
+    for (int c = 0; c < 3; c++)
+    {
+        h->w[c] = c ? -((-cfg->width) >> cfg->chroma_shift_w) : cfg->width;
+        h->h[c] = c ? -((-cfg->height) >> cfg->chroma_shift_h) : cfg->height;
+        h->off[c] = h->frame_bytes;
+        h->frame_bytes += (size_t)h->w[c] * h->h[c] * h->bps;
+    }
+    h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
+    h->frames = calloc(h->ring, h->frame_bytes);
+    h->index = malloc(sizeof(int64_t) * h->ring);
+    for (int i = 0; i < h->ring; i++) h->index[i] = -1;
+    *out = h;
+    return 0;
+}
+
+void oracle_hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
+{
+    if (h == NULL) return;
+    free(h->frames); free(h->index); free(h);
+}
+
+int oracle_hbcu_nlmeans_upload(hbcu_nlmeans_t *h, int64_t index, const void *const planes[3], const int strides[3])
+{
+    const int slot = (int)(index % h->ring);
+    uint8_t *dst = h->frames + (size_t)slot * h->frame_bytes;
+    for (int c = 0; c < 3; c++)
+        for (int y = 0; y < h->h[c]; y++)
+            memcpy(dst + h->off[c] + (size_t)y * h->w[c] * h->bps, (const uint8_t *)planes[c] + (size_t)y * strides[c], (size_t)h->w[c] * h->bps);
+    h->index[slot] = index;
+    return 0;
+}
+
+int oracle_hbcu_nlmeans_wait_upload(hbcu_nlmeans_t *h, int64_t index) { (void)h; (void)index; return 0; }
+
+int oracle_hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, void *const planes[3], const int strides[3])
+{
+    for (int c = 0; c < 3; c++)
+    {
+        const hbcu_nlmeans_plane_t *pp = &h->cfg.plane[c];
+        const int nf = pp->nframes < navail ? pp->nframes : navail;
+        const void *frames[32];
+        for (int f = 0; f < nf; f++)
+        {
+            const int slot = (int)((index + f) % h->ring);
+            if (h->index[slot] != index + f)
+            {   /* the host filter let a frame it still needs be overwritten: a ring-sizing bug */
+                oracle_hostlogic_set_error("frame %lld is no longer in the ring", (long long)(index + f));
+                return -1;
+            }
+            frames[f] = h->frames + (size_t)slot * h->frame_bytes + h->off[c];
+        }
+        uint8_t *tight = malloc((size_t)h->w[c] * h->h[c] * h->bps);
+        /* the reference's stale source-patch pointer (see nlmeans_port.c): frame 0 of the stream, or no temporal window */
+        oracle_nlmeans_plane_with_table(frames, nf, h->w[c], h->h[c], h->cfg.depth, pp->patch_size, pp->range, pp->origin_tune,
+                                        pp->bypass, pp->prefilter, pp->weight_fact, pp->diff_max, pp->exptable,
+                                        index == 0 || pp->nframes < 2, tight);
+        for (int y = 0; y < h->h[c]; y++)
+            memcpy((uint8_t *)planes[c] + (size_t)y * strides[c], tight + (size_t)y * h->w[c] * h->bps, (size_t)h->w[c] * h->bps);
+        free(tight);
+    }
+    return 0;
+}
+
+int oracle_hbcu_nlmeans_wait(hbcu_nlmeans_t *h, int64_t index) { (void)h; (void)index; return 0; }
+int oracle_hbcu_nlmeans_poll(hbcu_nlmeans_t *h, int64_t index) { (void)h; (void)index; return 1; }
+
+/* device-resident frames do not exist on this side */
+static int no_device(const char *what) { oracle_hostlogic_set_error("%s: no device in the host-logic build", what); return -1; }
+int oracle_hbcu_nlmeans_upload_frame(hbcu_nlmeans_t *h, int64_t index, hbcu_frame_t *in) { (void)h; (void)index; (void)in; return no_device("upload_frame"); }
+int oracle_hbcu_nlmeans_filter_frame(hbcu_nlmeans_t *h, int64_t index, int navail, hbcu_frame_t *out) { (void)h; (void)index; (void)navail; (void)out; return no_device("filter_frame"); }
+int    oracle_hbcu_frame_alloc(hbcu_frame_t **f, int device, const int row_bytes[3], const int rows[3], const int strides[3])
+{ (void)device; (void)row_bytes; (void)rows; (void)strides; *f = NULL; return no_device("frame_alloc"); }
+void   oracle_hbcu_frame_retain(hbcu_frame_t *f) { (void)f; }
+void   oracle_hbcu_frame_release(hbcu_frame_t *f) { (void)f; }
+void  *oracle_hbcu_frame_plane(const hbcu_frame_t *f, int plane) { (void)f; (void)plane; return NULL; }
+int    oracle_hbcu_frame_stride(const hbcu_frame_t *f, int plane) { (void)f; (void)plane; return 0; }
+int    oracle_hbcu_frame_device(const hbcu_frame_t *f) { (void)f; return -1; }
+long   oracle_hbcu_frames_alive(void) { return 0; }
+int    oracle_hbcu_xfer_create(hbcu_xfer_t **x, int device, int depth) { (void)device; (void)depth; *x = NULL; return no_device("xfer_create"); }
+void   oracle_hbcu_xfer_destroy(hbcu_xfer_t *x) { (void)x; }
+int    oracle_hbcu_xfer_upload(hbcu_xfer_t *x, int64_t t, hbcu_frame_t *f, const void *const p[3], const int s[3]) { (void)x; (void)t; (void)f; (void)p; (void)s; return -1; }
+int    oracle_hbcu_xfer_download(hbcu_xfer_t *x, int64_t t, hbcu_frame_t *f, void *const p[3], const int s[3]) { (void)x; (void)t; (void)f; (void)p; (void)s; return -1; }
+int    oracle_hbcu_xfer_wait(hbcu_xfer_t *x, int64_t t) { (void)x; (void)t; return -1; }
+int    oracle_hbcu_xfer_poll(hbcu_xfer_t *x, int64_t t) { (void)x; (void)t; return -1; }

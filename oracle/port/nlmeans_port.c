@@ -33,6 +33,8 @@ void oracle_nlmeans_table(double strength, int patch_size, int depth,
     exptable[EXPSIZE - 1] = 0;
 }
 
+typedef struct { float weight_fact; int diff_max; const float *exptable; } nlm_table_t;
+
 /* template :20-43: img[-1-x] = img[x]; img[w+x] = img[w-1-x] (rows likewise) */
 static inline int mirror(int v, int n)
 {
@@ -43,7 +45,8 @@ static inline int mirror(int v, int n)
 
 #define DEFINE_PLANE(NAME, PIXEL)                                                                   \
 static void NAME(const void *const *frames, const void *const *pres, int nframes, int w, int h, int depth, \
-                 const oracle_nlmeans_plane_params_t *pp, void *dst_v, const void *src_pre_v)      \
+                 const oracle_nlmeans_plane_params_t *pp, void *dst_v, const void *src_pre_v,       \
+                 const nlm_table_t *given)                                                          \
 {                                                                                                   \
     PIXEL *dst = dst_v;                                                                             \
     const PIXEL *src = frames[0];                                                                   \
@@ -55,7 +58,12 @@ static void NAME(const void *const *frames, const void *const *pres, int nframes
     }                                                                                               \
     float wfact, exptable[EXPSIZE];                                                                 \
     int diff_max;                                                                                   \
-    oracle_nlmeans_table(pp->strength, pp->patch_size, depth, &wfact, &diff_max, exptable);         \
+    if (given != NULL)                                                                              \
+    {   /* the caller's table (the C-ABI hands the device exactly this, hbcu_nlmeans_plane_t) */    \
+        wfact = given->weight_fact; diff_max = given->diff_max;                                     \
+        memcpy(exptable, given->exptable, sizeof(exptable));                                        \
+    }                                                                                               \
+    else oracle_nlmeans_table(pp->strength, pp->patch_size, depth, &wfact, &diff_max, exptable);    \
     const int nh = (pp->patch_size - 1) / 2, rh = (pp->range - 1) / 2;                              \
     const double origin_tune = pp->origin_tune;                                                     \
     for (int y = 0; y < h; y++)                                                                     \
@@ -238,7 +246,7 @@ int oracle_nlmeans_prefilter(const void *src, int w, int h, int depth, int filte
  * window is 1 -- contributes its UNFILTERED image as the source patch while the compare patches are prefiltered.
  * (With more than one worker thread the reference races on this; the contract restated here is threads=1.) */
 static void nlmeans_plane_ex(const void *const *frames, int nframes, int w, int h, int depth,
-                             const oracle_nlmeans_plane_params_t *pp, void *dst, int stale_src)
+                             const oracle_nlmeans_plane_params_t *pp, void *dst, int stale_src, const nlm_table_t *given)
 {
     const int bps = depth > 8 ? 2 : 1;
     const size_t bytes = (size_t)w * h * bps;
@@ -261,8 +269,8 @@ static void nlmeans_plane_ex(const void *const *frames, int nframes, int w, int 
     else
     {
         /* the source patch pointer may be stale; the compare patch of frame 0 is always the prefiltered image */
-        if (depth > 8) plane_u16(frames, pres, nframes, w, h, depth, pp, dst, stale_src ? frames[0] : pres[0]);
-        else           plane_u8(frames, pres, nframes, w, h, depth, pp, dst, stale_src ? frames[0] : pres[0]);
+        if (depth > 8) plane_u16(frames, pres, nframes, w, h, depth, pp, dst, stale_src ? frames[0] : pres[0], given);
+        else           plane_u8(frames, pres, nframes, w, h, depth, pp, dst, stale_src ? frames[0] : pres[0], given);
     }
     for (int f = 0; f < nframes; f++) free(pre_mem[f]);
 }
@@ -270,7 +278,18 @@ static void nlmeans_plane_ex(const void *const *frames, int nframes, int w, int 
 void oracle_nlmeans_plane(const void *const *frames, int nframes, int w, int h, int depth,
                           const oracle_nlmeans_plane_params_t *pp, void *dst)
 {
-    nlmeans_plane_ex(frames, nframes, w, h, depth, pp, dst, 0);
+    nlmeans_plane_ex(frames, nframes, w, h, depth, pp, dst, 0, NULL);
+}
+
+/* the same with the weight table GIVEN (what the C-ABI's hbcu_nlmeans_plane_t carries) instead of derived from a strength:
+ * lets the host filter's own table arithmetic be part of what is checked */
+void oracle_nlmeans_plane_with_table(const void *const *frames, int nframes, int w, int h, int depth,
+                                     int patch_size, int range, double origin_tune, int bypass, int prefilter,
+                                     float weight_fact, int diff_max, const float *exptable, int stale_src, void *dst)
+{
+    const oracle_nlmeans_plane_params_t pp = { bypass ? 0.0 : 1.0, origin_tune, patch_size, range, nframes, prefilter };
+    const nlm_table_t tab = { weight_fact, diff_max, exptable };
+    nlmeans_plane_ex(frames, nframes, w, h, depth, &pp, dst, stale_src, &tab);
 }
 
 int oracle_nlmeans_clip(const uint8_t *in, int n_in, int width, int height, int depth,
@@ -296,7 +315,7 @@ int oracle_nlmeans_clip(const uint8_t *in, int n_in, int width, int height, int 
             for (int f = 0; f < nf; f++)
                 frames[f] = in + (size_t)(t + f) * frame_bytes + off[c];
             nlmeans_plane_ex(frames, nf, pw[c], ph[c], depth, &pp[c], out + (size_t)t * frame_bytes + off[c],
-                             t == 0 || pp[c].nframes < 2);
+                             t == 0 || pp[c].nframes < 2, NULL);
         }
     }
     return 0;

@@ -43,6 +43,12 @@ void oracle_nlmeans_table(double strength, int patch_size, int depth,
 void oracle_nlmeans_plane(const void *const *frames, int nframes, int w, int h, int depth,
                           const oracle_nlmeans_plane_params_t *pp, void *dst);
 
+/* the same with the weight table given (weight_fact, diff_max, exptable[128] as in hbcu_nlmeans_plane_t); bypass = the
+ * plane is copied (strength 0); stale_src = the source patches are read from the unfiltered image (see nlmeans_port.c) */
+void oracle_nlmeans_plane_with_table(const void *const *frames, int nframes, int w, int h, int depth,
+                                     int patch_size, int range, double origin_tune, int bypass, int prefilter,
+                                     float weight_fact, int diff_max, const float *exptable, int stale_src, void *dst);
+
 /* nlmeans.c:464-694 for a whole yuv420p clip: n_in packed frames in, n_in out
  * (look-ahead window, shrinking at EOF). */
 int oracle_nlmeans_clip(const uint8_t *in, int n_in, int width, int height, int depth,

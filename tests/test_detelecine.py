@@ -1,6 +1,6 @@
 """CPU tests of the detelecine (pullup) drop-in, SURVEY.md 8 f4.
 
-oracle/_ref/libdetelecine_hostlogic.so is the PRODUCT's host-side state machine (handbrake_b200/libhb/detelecine_cuda.c,
+oracle/_ref/libhostlogic.so is the PRODUCT's host-side state machine (handbrake_b200/libhb/detelecine_cuda.c,
 compiled untouched) with its device calls redirected to the plain-C restatement oracle/port/detelecine_port.c.  Pinned
 here, frame for frame, against the reference's own hb_filter_detelecine compiled from /root/reference.  On the GPU box the
 same host code drives the CUDA kernels and tests/test_detelecine_gpu.py compares that with the reference."""
@@ -11,7 +11,7 @@ from handbrake_b200 import synth
 from conftest import ORACLE_DIR
 
 FMT = {8: synth.PIX_FMT_YUV420P, 10: synth.PIX_FMT_YUV420P10}
-HOSTLOGIC_SO = ORACLE_DIR / "_ref" / "libdetelecine_hostlogic.so"
+HOSTLOGIC_SO = ORACLE_DIR / "_ref" / "libhostlogic.so"
 
 # (telecined_clip keywords, settings)
 DETELECINE_CASES = [
@@ -34,7 +34,7 @@ DETELECINE_CASES = [
 def hostlogic():
     from handbrake_b200.hblib import FilterLib
     if not HOSTLOGIC_SO.exists():
-        pytest.skip("oracle/_ref/libdetelecine_hostlogic.so not built")
+        pytest.skip("oracle/_ref/libhostlogic.so not built")
     return FilterLib(HOSTLOGIC_SO)
 
 

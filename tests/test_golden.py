@@ -33,7 +33,7 @@ def test_detelecine_hostlogic_matches_golden(name):
     from handbrake_b200.hblib import FilterLib
     from test_detelecine import HOSTLOGIC_SO
     if not HOSTLOGIC_SO.exists():
-        pytest.skip("oracle/_ref/libdetelecine_hostlogic.so not built")
+        pytest.skip("oracle/_ref/libhostlogic.so not built")
     c, g = CASES[name], GOLDEN[name]
     r = FilterLib(HOSTLOGIC_SO).run(c["cuda"], c["settings"], c["clip"], FMT[c["depth"]], c["w"], c["h"], flags=c["flags"])
     d = digest(r)

@@ -1,0 +1,84 @@
+"""CPU tests of the product's HOST-SIDE filter code (settings cascade and sanitising, weight
+tables, look-ahead buffering, EOF flush, output order and properties).
+
+oracle/_ref/libhostlogic.so is handbrake_b200/libhb/*_cuda.c compiled UNTOUCHED, with every hbcu_* device call renamed to
+a plain-C stand-in built on the restatement (oracle/port/hostlogic_*.c).  Compared here with the reference's own filter
+objects compiled from /root/reference.  On the GPU box the same host code drives the CUDA kernels (tests/test_*_gpu.py)."""
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from handbrake_b200 import synth
+from conftest import ORACLE_DIR
+
+FMT = {8: synth.PIX_FMT_YUV420P, 10: synth.PIX_FMT_YUV420P10}
+HOSTLOGIC_SO = ORACLE_DIR / "_ref" / "libhostlogic.so"
+
+
+@pytest.fixture(scope="module")
+def hostlogic():
+    from handbrake_b200.hblib import FilterLib
+    if not HOSTLOGIC_SO.exists():
+        pytest.skip("oracle/_ref/libhostlogic.so not built")
+    return FilterLib(HOSTLOGIC_SO)
+
+
+def same_stream(r, g):
+    assert not g.init_failed and g.saw_eof
+    assert g.frames.shape == r.frames.shape, (g.frames.shape, r.frames.shape)
+    assert np.array_equal(g.start, r.start) and np.array_equal(g.stop, r.stop) and np.array_equal(g.flags, r.flags)
+    if not np.array_equal(g.frames, r.frames):
+        d = g.frames != r.frames
+        raise AssertionError(f"{np.count_nonzero(d)} bytes differ in frames {np.argwhere(d.any(axis=1)).ravel()[:8]}")
+
+
+NLMEANS_SETTINGS = [
+    None,                                                        # filter defaults (nlmeans.c:58-69)
+    "y-strength=1.5", "y-strength=3", "y-strength=6", "y-strength=10",          # presets ultralight .. strong (param.c:408-428)
+    "y-strength=6:y-origin-tune=0.8:y-patch-size=5:y-range=7:y-frame-count=4",  # tune animation-like (param.c:501-523)
+    "y-strength=4:cb-strength=8:cb-range=5:cr-strength=2:cr-patch-size=9",      # cascade Cr <- Cb <- Y, per-plane overrides
+    "y-strength=6:y-patch-size=4:y-range=6:y-frame-count=99:y-origin-tune=7",   # sanitised: odd sizes, frames <= 32, tune in [0.01, 1]
+    "y-strength=0:cb-strength=5:cr-strength=0",                                 # bypassed planes are copied
+    "y-strength=6:y-frame-count=1",                                             # no temporal window
+    "y-strength=6:threads=3",
+    "y-strength=6:y-prefilter=1:threads=1", "y-strength=6:y-prefilter=1032:cb-prefilter=272:threads=1",
+    "y-strength=5:y-prefilter=2048:threads=1",                                  # passthru
+]
+
+
+@pytest.mark.parametrize("settings", NLMEANS_SETTINGS)
+@pytest.mark.parametrize("depth", [8, 10])
+def test_nlmeans_host_filter_equals_reference(ref, hostlogic, settings, depth):
+    w, h = 48, 32
+    clip = synth.progressive_clip(FMT[depth], w, h, 6, seed=40 + depth)
+    ref_settings = settings
+    if settings and "frame-count=99" in settings:
+        clip = clip[:3]                               # 32 look-ahead frames of a naive O(n^2 r^2) restatement: keep it small
+    r = ref.run("hb_filter_nlmeans", ref_settings, clip, FMT[depth], w, h)
+    g = hostlogic.run("hb_filter_nlmeans_cuda", settings, clip, FMT[depth], w, h)
+    same_stream(r, g)
+    assert hostlogic.buffers_alive() == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 23])
+def test_nlmeans_host_filter_clip_lengths(ref, hostlogic, n):
+    """shorter than the temporal window (EOF flush with a shrinking window from the first frame on) and long enough to go
+    round the device ring several times"""
+    w, h = 32, 32
+    clip = synth.progressive_clip(FMT[8], w, h, n, seed=7)
+    s = "y-strength=6:y-frame-count=3:y-range=3:y-patch-size=3"
+    r = ref.run("hb_filter_nlmeans", s, clip, FMT[8], w, h)
+    g = hostlogic.run("hb_filter_nlmeans_cuda", s, clip, FMT[8], w, h)
+    same_stream(r, g)
+
+
+def test_nlmeans_host_filter_reproduces_golden_digests(hostlogic):
+    golden = json.loads((Path(__file__).parent / "golden" / "nlmeans_golden.json").read_text())
+    for name in ("tiny_light_96x64", "tiny_tuned_10bit_64x48"):
+        c = golden[name]
+        clip = synth.progressive_clip(FMT[c["depth"]], c["width"], c["height"], c["frames"], seed=c["seed"])
+        g = hostlogic.run("hb_filter_nlmeans_cuda", c["settings"], clip, FMT[c["depth"]], c["width"], c["height"])
+        assert [hashlib.sha256(f.tobytes()).hexdigest() for f in g.frames] == c["sha256"], name
