@@ -210,6 +210,13 @@ void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t 
     decomb_field_ex(prev, cur, next, NULL, dst, width, height, depth, mode, parity, tff);
 }
 
+/* one output picture with the EEDI2 picture of the same field given (mode may carry the EEDI2 bit) */
+void oracle_decomb_field_eedi2(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, const uint8_t *eedi, uint8_t *dst,
+                               int width, int height, int depth, int mode, int parity, int tff)
+{
+    decomb_field_ex(prev, cur, next, eedi, dst, width, height, depth, mode, parity, tff);
+}
+
 int oracle_decomb_clip(const uint8_t *in, int n_in, const uint16_t *flags, const uint8_t *combed,
                        int width, int height, int depth, int mode, int parity_setting,
                        uint8_t *out, int *out_src)

@@ -93,6 +93,9 @@ int oracle_comb_detect_clip(const uint8_t *in, int n_in, int width, int height, 
 void oracle_decomb_field(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, uint8_t *dst,
                          int width, int height, int depth, int filter_mode, int mode, int parity, int tff);
 
+void oracle_decomb_field_eedi2(const uint8_t *prev, const uint8_t *cur, const uint8_t *next, const uint8_t *eedi, uint8_t *dst,
+                               int width, int height, int depth, int mode, int parity, int tff);
+
 /* EEDI2 (libhb/templates/eedi2_template.c via eedi2_interpolate_plane): a handle carries the edge-mask
  * state from field to field; one call interpolates field `!tff` of `cur` (packed planar) to a full frame */
 void *oracle_eedi2_create(int width, int height, int depth, int mthresh, int vthresh, int lthresh, int dstr, int estr,

@@ -82,3 +82,67 @@ def test_nlmeans_host_filter_reproduces_golden_digests(hostlogic):
         clip = synth.progressive_clip(FMT[c["depth"]], c["width"], c["height"], c["frames"], seed=c["seed"])
         g = hostlogic.run("hb_filter_nlmeans_cuda", c["settings"], clip, FMT[c["depth"]], c["width"], c["height"])
         assert [hashlib.sha256(f.tobytes()).hexdigest() for f in g.frames] == c["sha256"], name
+
+
+# ---------------------------------------------------------------- comb-detect, decomb, lapsharp host filters
+from test_oracle import COMB_SETTINGS, DECOMB_CASES, LAPSHARP_CASES, decomb_inputs, mixed_interlaced_clip  # noqa: E402
+
+
+@pytest.mark.parametrize("settings", COMB_SETTINGS)
+@pytest.mark.parametrize("depth", [8, 10])
+def test_comb_detect_host_filter_equals_reference(ref, hostlogic, settings, depth):
+    """the three-frame window: first frame duplicated (HB_FILTER_DELAY), exhaustive check at both ends, buffers passed
+    through with their verdict; also that the host's gamma table and shifted thresholds are the reference's"""
+    w, h = 176, 112
+    clip = mixed_interlaced_clip(FMT[depth], w, h, 9)
+    flags = np.full(clip.shape[0], synth.PIC_FLAG_TOP_FIELD_FIRST, np.uint16)
+    r = ref.run("hb_filter_comb_detect", settings, clip, FMT[depth], w, h, flags=flags)
+    g = hostlogic.run("hb_filter_comb_detect_cuda", settings, clip, FMT[depth], w, h, flags=flags)
+    same_stream(r, g)
+    assert list(g.combed) == list(r.combed)
+    assert hostlogic.buffers_alive() == 0
+
+
+def test_comb_detect_host_filter_short_clips(ref, hostlogic):
+    w, h = 96, 64
+    for n in (1, 2, 3):
+        clip = synth.interlaced_clip(FMT[8], w, h, n, seed=3, static_every=0)
+        r = ref.run("hb_filter_comb_detect", None, clip, FMT[8], w, h)
+        g = hostlogic.run("hb_filter_comb_detect_cuda", None, clip, FMT[8], w, h)
+        same_stream(r, g)
+        assert list(g.combed) == list(r.combed)
+
+
+@pytest.mark.parametrize("mode,parity,tags", DECOMB_CASES + [(24, -1, False), (31, -1, False), (63, -1, True), (15, 1, True)])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_decomb_host_filter_equals_reference(ref, hostlogic, mode, parity, tags, depth):
+    """per-frame mode from the combed tag, parity / field order from flags and the setting, bob timestamps and frame
+    rate, one EEDI2 call per rebuilt field with the mask state carried along"""
+    w, h = (96, 52) if not mode & 8 else (112, 64)
+    clip, flags, combed = decomb_inputs(depth, w, h, 6)
+    s = f"mode={mode}:parity={parity}"
+    r = ref.run("hb_filter_decomb", s, clip, FMT[depth], w, h, flags=flags, combed=combed if tags else None)
+    g = hostlogic.run("hb_filter_decomb_cuda", s, clip, FMT[depth], w, h, flags=flags, combed=combed if tags else None)
+    same_stream(r, g)
+    assert list(g.combed) == list(r.combed) and g.vrate == r.vrate
+    assert hostlogic.buffers_alive() == 0
+
+
+def test_comb_detect_then_decomb_host_chain(ref, hostlogic):
+    w, h = 160, 96
+    clip, flags, _ = decomb_inputs(8, w, h, 8, seed=9)
+    s = [None, "mode=39"]
+    r = ref.run(["hb_filter_comb_detect", "hb_filter_decomb"], s, clip, FMT[8], w, h, flags=flags)
+    g = hostlogic.run(["hb_filter_comb_detect_cuda", "hb_filter_decomb_cuda"], s, clip, FMT[8], w, h, flags=flags)
+    same_stream(r, g)
+    assert list(g.combed) == list(r.combed) and len(set(r.combed)) > 1
+
+
+@pytest.mark.parametrize("settings,strengths,kernels", LAPSHARP_CASES + [("y-strength=9:y-kernel=nonsense", None, None)])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_lapsharp_host_filter_equals_reference(ref, hostlogic, settings, strengths, kernels, depth):
+    w, h = 200, 90
+    clip = synth.progressive_clip(FMT[depth], w, h, 5, seed=31, noise=20)
+    r = ref.run("hb_filter_lapsharp_mt", settings, clip, FMT[depth], w, h)
+    g = hostlogic.run("hb_filter_lapsharp_cuda", settings, clip, FMT[depth], w, h)
+    same_stream(r, g)
