@@ -1,6 +1,6 @@
 /* hostlogic_filters.c -- TEST INFRASTRUCTURE (see hostlogic_nlmeans.c for the idea).
  *
- * CPU stand-ins for the hbcu_comb_detect_*, hbcu_decomb_* and hbcu_lapsharp_* calls of the product's host filters
+ * CPU stand-ins for the hbcu_comb_detect_*, hbcu_decomb_*, hbcu_lapsharp_*, hbcu_unsharp_* and hbcu_hqdn3d_* calls of the product's host filters
  * (handbrake_b200/libhb/comb_detect_cuda.c, decomb_cuda.c, lapsharp_cuda.c), built on the plain-C restatement.  What the
  * host side owns and what is therefore pinned against the compiled reference through these: comb-detect's three-frame
  * window (first frame duplicated, HB_FILTER_DELAY, exhaustive check at both ends, the same hb_buffer_t passed through with
@@ -209,3 +209,106 @@ int oracle_hbcu_lapsharp_filter_frames(hbcu_lapsharp_t *h, int64_t ticket, hbcu_
 }
 int oracle_hbcu_lapsharp_wait(hbcu_lapsharp_t *h, int64_t ticket) { (void)h; (void)ticket; return 0; }
 int oracle_hbcu_lapsharp_poll(hbcu_lapsharp_t *h, int64_t ticket) { (void)h; (void)ticket; return 1; }
+
+/* ------------------------------------------------------------------------------------------ unsharp / chroma smooth, hqdn3d */
+static void plane_dims(int width, int height, int sw, int sh, int c, int *w, int *h)
+{
+    *w = c ? -((-width) >> sw) : width;
+    *h = c ? -((-height) >> sh) : height;
+}
+static uint8_t *tight_copy(const void *plane, int stride, int w, int h, int bps)
+{
+    uint8_t *t = malloc((size_t)w * h * bps);
+    for (int y = 0; y < h; y++) memcpy(t + (size_t)y * w * bps, (const uint8_t *)plane + (size_t)y * stride, (size_t)w * bps);
+    return t;
+}
+static void strided_copy(void *plane, int stride, const uint8_t *t, int w, int h, int bps)
+{
+    for (int y = 0; y < h; y++) memcpy((uint8_t *)plane + (size_t)y * stride, t + (size_t)y * w * bps, (size_t)w * bps);
+}
+
+struct hbcu_unsharp_s { hbcu_unsharp_config_t cfg; };
+
+int oracle_hbcu_unsharp_create(hbcu_unsharp_t **out, const hbcu_unsharp_config_t *cfg)
+{
+    struct hbcu_unsharp_s *h = calloc(1, sizeof(*h));
+    h->cfg = *cfg;
+    *out = h;
+    return 0;
+}
+void oracle_hbcu_unsharp_destroy(hbcu_unsharp_t *h) { free(h); }
+int oracle_hbcu_unsharp_filter_frames(hbcu_unsharp_t *h, int64_t ticket, hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                                      hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
+{
+    (void)ticket;
+    if (in_frame != NULL || out_frame != NULL) return -1;
+    const int bps = h->cfg.depth > 8 ? 2 : 1;
+    for (int c = 0; c < 3; c++)
+    {
+        int w, ht;
+        plane_dims(h->cfg.width, h->cfg.height, h->cfg.chroma_shift_w, h->cfg.chroma_shift_h, c, &w, &ht);
+        uint8_t *src = tight_copy(in_planes[c], in_strides[c], w, ht, bps), *dst = malloc((size_t)w * ht * bps);
+        /* the restatement takes (strength, size); amount / 65536 and 2 steps + 1 map back onto the host's (amount, steps)
+         * exactly, and its own sanitising is idempotent on sanitised values */
+        oracle_unsharp_plane(src, dst, w, ht, h->cfg.depth, h->cfg.amount[c] / 65536.0, 2 * h->cfg.steps[c] + 1, h->cfg.smooth, 1);
+        strided_copy(out_planes[c], out_strides[c], dst, w, ht, bps);
+        free(src); free(dst);
+    }
+    return 0;
+}
+int oracle_hbcu_unsharp_wait(hbcu_unsharp_t *h, int64_t ticket) { (void)h; (void)ticket; return 0; }
+int oracle_hbcu_unsharp_poll(hbcu_unsharp_t *h, int64_t ticket) { (void)h; (void)ticket; return 1; }
+
+struct hbcu_hqdn3d_s
+{
+    hbcu_hqdn3d_config_t cfg;
+    int16_t *coef[6];
+    uint16_t *ant[3];
+    int ant_valid[3];
+};
+
+int oracle_hbcu_hqdn3d_create(hbcu_hqdn3d_t **out, const hbcu_hqdn3d_config_t *cfg)
+{
+    struct hbcu_hqdn3d_s *h = calloc(1, sizeof(*h));
+    h->cfg = *cfg;
+    const size_t entries = (size_t)512 << (cfg->depth == 16 ? 8 : 4);
+    for (int i = 0; i < 6; i++)
+    {
+        h->coef[i] = malloc(entries * sizeof(int16_t));            /* the host frees its tables after create() */
+        memcpy(h->coef[i], cfg->coef[i], entries * sizeof(int16_t));
+    }
+    for (int c = 0; c < 3; c++)
+    {
+        int w, ht;
+        plane_dims(cfg->width, cfg->height, cfg->chroma_shift_w, cfg->chroma_shift_h, c, &w, &ht);
+        h->ant[c] = calloc((size_t)w * ht, sizeof(uint16_t));
+    }
+    *out = h;
+    return 0;
+}
+void oracle_hbcu_hqdn3d_destroy(hbcu_hqdn3d_t *h)
+{
+    if (h == NULL) return;
+    for (int i = 0; i < 6; i++) free(h->coef[i]);
+    for (int c = 0; c < 3; c++) free(h->ant[c]);
+    free(h);
+}
+int oracle_hbcu_hqdn3d_filter_frames(hbcu_hqdn3d_t *h, int64_t ticket, hbcu_frame_t *in_frame, const void *const in_planes[3], const int in_strides[3],
+                                     hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
+{
+    (void)ticket;
+    if (in_frame != NULL || out_frame != NULL) return -1;
+    const int bps = h->cfg.depth > 8 ? 2 : 1;
+    for (int c = 0; c < 3; c++)
+    {
+        int w, ht;
+        plane_dims(h->cfg.width, h->cfg.height, h->cfg.chroma_shift_w, h->cfg.chroma_shift_h, c, &w, &ht);
+        uint8_t *src = tight_copy(in_planes[c], in_strides[c], w, ht, bps), *dst = malloc((size_t)w * ht * bps);
+        oracle_hqdn3d_plane(src, dst, h->ant[c], &h->ant_valid[c], w, ht, h->cfg.depth, h->coef[2 * c], h->coef[2 * c + 1]);
+        strided_copy(out_planes[c], out_strides[c], dst, w, ht, bps);
+        free(src); free(dst);
+    }
+    return 0;
+}
+int oracle_hbcu_hqdn3d_wait(hbcu_hqdn3d_t *h, int64_t ticket) { (void)h; (void)ticket; return 0; }
+int oracle_hbcu_hqdn3d_poll(hbcu_hqdn3d_t *h, int64_t ticket) { (void)h; (void)ticket; return 1; }

@@ -11,7 +11,7 @@ from handbrake_b200 import synth
 from conftest import ORACLE_DIR
 
 FMT = {8: synth.PIX_FMT_YUV420P, 10: synth.PIX_FMT_YUV420P10}
-HOSTLOGIC_SO = ORACLE_DIR / "_ref" / "libhostlogic.so"
+HOSTLOGIC_SO = ORACLE_DIR / "_ref" / "libhostlogic.so"      # see tests/test_hostlogic.py
 
 # (telecined_clip keywords, settings)
 DETELECINE_CASES = [

@@ -27,14 +27,16 @@ def test_reference_matches_golden(ref, name):
     assert d["start"] == g["start"] and d["combed"] == g["combed"] and d["sha256"] == g["sha256"]
 
 
-@pytest.mark.parametrize("name", sorted(n for n in CASES if n.startswith("detelecine")))
-def test_detelecine_hostlogic_matches_golden(name):
-    """the product's pullup state machine over the plain-C metric restatement (see tests/test_detelecine.py)"""
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_host_filters_match_golden(name):
+    """the product's host-side filter objects (same names as on the GPU) over the plain-C stand-ins for the device calls
+    (oracle/_ref/libhostlogic.so, see tests/test_hostlogic.py): the committed digests again, chains included"""
     from handbrake_b200.hblib import FilterLib
-    from test_detelecine import HOSTLOGIC_SO
+    from test_hostlogic import HOSTLOGIC_SO
     if not HOSTLOGIC_SO.exists():
         pytest.skip("oracle/_ref/libhostlogic.so not built")
     c, g = CASES[name], GOLDEN[name]
-    r = FilterLib(HOSTLOGIC_SO).run(c["cuda"], c["settings"], c["clip"], FMT[c["depth"]], c["w"], c["h"], flags=c["flags"])
+    r = FilterLib(HOSTLOGIC_SO).run(c["cuda"], c["settings"], c["clip"], FMT[c["depth"]], c["w"], c["h"], flags=c["flags"], combed=c["combed"])
+    assert not r.init_failed and r.saw_eof
     d = digest(r)
-    assert d["start"] == g["start"] and d["sha256"] == g["sha256"]
+    assert d["start"] == g["start"] and d["combed"] == g["combed"] and d["sha256"] == g["sha256"]

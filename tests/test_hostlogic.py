@@ -146,3 +146,37 @@ def test_lapsharp_host_filter_equals_reference(ref, hostlogic, settings, strengt
     r = ref.run("hb_filter_lapsharp_mt", settings, clip, FMT[depth], w, h)
     g = hostlogic.run("hb_filter_lapsharp_cuda", settings, clip, FMT[depth], w, h)
     same_stream(r, g)
+
+
+# ---------------------------------------------------------------- unsharp, chroma smooth, hqdn3d host filters
+from test_oracle import CHROMA_SMOOTH_CASES, UNSHARP_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("settings", [c[0] for c in UNSHARP_CASES])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_unsharp_host_filter_equals_reference(ref, hostlogic, settings, depth):
+    w, h = 150, 98
+    clip = synth.progressive_clip(FMT[depth], w, h, 4, seed=51)
+    same_stream(ref.run("hb_filter_unsharp_mt", settings, clip, FMT[depth], w, h),
+                hostlogic.run("hb_filter_unsharp_cuda", settings, clip, FMT[depth], w, h))
+
+
+@pytest.mark.parametrize("settings", [c[0] for c in CHROMA_SMOOTH_CASES])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_chroma_smooth_host_filter_equals_reference(ref, hostlogic, settings, depth):
+    w, h = 150, 98
+    clip = synth.progressive_clip(FMT[depth], w, h, 4, seed=53)
+    same_stream(ref.run("hb_filter_chroma_smooth_mt", settings, clip, FMT[depth], w, h),
+                hostlogic.run("hb_filter_chroma_smooth_cuda", settings, clip, FMT[depth], w, h))
+
+
+@pytest.mark.parametrize("settings", [None, "y-spatial=2", "y-spatial=7:cb-spatial=7:cr-spatial=7:y-temporal=7:cb-temporal=5:cr-temporal=5",
+                                      "y-spatial=0:y-temporal=4", "y-spatial=3:cb-spatial=0:cr-temporal=0", "y-spatial=300:y-temporal=300"])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_hqdn3d_host_filter_equals_reference(ref, hostlogic, settings, depth):
+    """the default chain of denoise.c:237-266 and the coefficient tables the host computes (hqdn3d_precalc_coef)"""
+    w, h = 96, 64
+    clip = synth.progressive_clip(FMT[depth], w, h, 6, seed=61, noise=10)
+    same_stream(ref.run("hb_filter_denoise", settings, clip, FMT[depth], w, h),
+                hostlogic.run("hb_filter_denoise_cuda", settings, clip, FMT[depth], w, h))
+    assert hostlogic.buffers_alive() == 0
