@@ -168,7 +168,8 @@ int oracle_hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, in
     const uint8_t *p = ring_get(&h->ring, prev), *c = ring_get(&h->ring, cur), *n = ring_get(&h->ring, next);
     if (p == NULL || c == NULL || n == NULL) return -1;
     memset(h->out, 0, h->ring.bytes);                           /* libhb-shim output buffers start zeroed */
-    if (frame_mode & HBCU_DECOMB_EEDI2)
+    if (frame_mode == 0) memcpy(h->out, c, h->ring.bytes);      /* "just passing through": hb_buffer_copy (decomb template :893-896) */
+    else if (frame_mode & HBCU_DECOMB_EEDI2)
     {
         if (h->eedi == NULL) { oracle_hostlogic_set_error("decomb: EEDI2 asked of a handle created without it"); return -1; }
         oracle_eedi2_field(h->eedi, c, !parity, h->eedi_frame);  /* pv->tff = !parity (decomb.c:539-542) */

@@ -180,3 +180,54 @@ def test_hqdn3d_host_filter_equals_reference(ref, hostlogic, settings, depth):
     same_stream(ref.run("hb_filter_denoise", settings, clip, FMT[depth], w, h),
                 hostlogic.run("hb_filter_denoise_cuda", settings, clip, FMT[depth], w, h))
     assert hostlogic.buffers_alive() == 0
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_settings_all_host_filters(ref, hostlogic, seed):
+    """random (also out-of-range) settings for every filter object: whatever the reference's init() makes of them, the
+    drop-in's init() makes the same"""
+    rng = np.random.default_rng(seed)
+    depth = 8 if rng.random() < 0.6 else 10
+    fmt = FMT[depth]
+    jobs = []
+    mode = int(rng.integers(0, 64)) & ~8
+    w, h = 96, 52
+    clip, flags, combed = decomb_inputs(depth, w, h, 5, seed=seed)
+    flags = np.array([int(rng.choice([0, 0x08, 0x10, 0x18])) for _ in range(clip.shape[0])], np.uint16)
+    combed = rng.integers(0, 3, clip.shape[0]).astype(np.uint8)
+    jobs.append(("hb_filter_decomb", "hb_filter_decomb_cuda", f"mode={mode}:parity={int(rng.integers(-1, 2))}", clip, w, h, dict(flags=flags, combed=combed)))
+    s = (f"mode={int(rng.integers(0, 4))}:spatial-metric={int(rng.integers(0, 3))}:motion-thresh={int(rng.integers(0, 8))}:"
+         f"spatial-thresh={int(rng.integers(0, 8))}:filter-mode={int(rng.integers(0, 3))}:block-thresh={int(rng.integers(1, 120))}:"
+         f"block-width={int(rng.integers(4, 40))}:block-height={int(rng.integers(4, 40))}")
+    w, h = 112, 80
+    clip = mixed_interlaced_clip(fmt, w, h, 4, seed=seed)
+    jobs.append(("hb_filter_comb_detect", "hb_filter_comb_detect_cuda", s, clip, w, h, dict(flags=np.full(clip.shape[0], 8, np.uint16))))
+    parts = []
+    for c in ("y", "cb", "cr"):
+        if c == "y" or rng.random() < 0.5:
+            parts.append(f"{c}-strength={rng.choice([0, 1.5, 3, 6, 10, 20])}")
+        if rng.random() < 0.4:
+            parts.append(f"{c}-patch-size={int(rng.integers(0, 12))}")
+        if rng.random() < 0.4:
+            parts.append(f"{c}-range={int(rng.integers(0, 8))}")
+        if rng.random() < 0.4:
+            parts.append(f"{c}-frame-count={int(rng.integers(0, 5))}")
+        if rng.random() < 0.3:
+            parts.append(f"{c}-origin-tune={rng.choice([0, 0.005, 0.3, 1, 2.5])}")
+        if rng.random() < 0.3:
+            parts.append(f"{c}-prefilter={int(rng.choice([1, 2, 4, 8, 16, 32, 257, 514, 1028, 2049, 1024, 256]))}")
+    w, h = 40, 24
+    jobs.append(("hb_filter_nlmeans", "hb_filter_nlmeans_cuda", ":".join(parts + ["threads=1"]), synth.progressive_clip(fmt, w, h, 5, seed=seed), w, h, {}))
+    w, h = 88, 50
+    clip = synth.progressive_clip(fmt, w, h, 3, seed=seed, noise=15)
+    ks = ["lap", "isolap", "log", "isolog", "bogus"]
+    jobs.append(("hb_filter_lapsharp_mt", "hb_filter_lapsharp_cuda", f"y-strength={rng.choice([0, 0.2, 1.5, 3])}:y-kernel={rng.choice(ks)}:cb-strength={rng.choice([0, 0.5, 9])}:cr-kernel={rng.choice(ks)}", clip, w, h, {}))
+    jobs.append(("hb_filter_unsharp_mt", "hb_filter_unsharp_cuda", f"y-strength={rng.choice([-1, 0, 0.25, 1.5, 4])}:y-size={int(rng.integers(0, 20))}:cb-size={int(rng.integers(0, 20))}", clip, w, h, {}))
+    jobs.append(("hb_filter_chroma_smooth_mt", "hb_filter_chroma_smooth_cuda", f"cb-strength={rng.choice([-1, 0, 0.25, 3, 8])}:cb-size={int(rng.integers(0, 20))}:cr-size={int(rng.integers(0, 20))}", clip, w, h, {}))
+    jobs.append(("hb_filter_denoise", "hb_filter_denoise_cuda", f"y-spatial={rng.choice([0, 1, 4, 40, 300])}:cb-temporal={rng.choice([0, 2, 6, 100])}:cr-spatial={rng.choice([0, 3, 9])}", clip, w, h, {}))
+    for rname, gname, settings, clip, w, h, kw in jobs:
+        r = ref.run(rname, settings, clip, fmt, w, h, **kw)
+        g = hostlogic.run(gname, settings, clip, fmt, w, h, **kw)
+        assert r.init_failed == g.init_failed, (gname, settings)
+        same_stream(r, g) if not r.init_failed else None
+        assert list(g.combed) == list(r.combed) and g.vrate == r.vrate, (gname, settings)
