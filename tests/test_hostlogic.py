@@ -231,3 +231,22 @@ def test_random_settings_all_host_filters(ref, hostlogic, seed):
         assert r.init_failed == g.init_failed, (gname, settings)
         same_stream(r, g) if not r.init_failed else None
         assert list(g.combed) == list(r.combed) and g.vrate == r.vrate, (gname, settings)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2])
+@pytest.mark.parametrize("w,h", [(96, 64), (70, 50)])
+def test_empty_and_tiny_streams_all_host_filters(ref, hostlogic, n, w, h):
+    """EOF as the first buffer, one picture, two pictures; a size whose chroma planes are odd"""
+    fmt = FMT[8]
+    clip = synth.progressive_clip(fmt, w, h, max(n, 1), seed=2)[:n]
+    pairs = [("hb_filter_nlmeans", "hb_filter_nlmeans_cuda", "y-strength=6"), ("hb_filter_comb_detect", "hb_filter_comb_detect_cuda", None),
+             ("hb_filter_decomb", "hb_filter_decomb_cuda", "mode=23"), ("hb_filter_lapsharp_mt", "hb_filter_lapsharp_cuda", None),
+             ("hb_filter_unsharp_mt", "hb_filter_unsharp_cuda", None), ("hb_filter_chroma_smooth_mt", "hb_filter_chroma_smooth_cuda", None),
+             ("hb_filter_denoise", "hb_filter_denoise_cuda", None), ("hb_filter_detelecine", "hb_filter_detelecine_cuda", None)]
+    if (h // 2) % 2 == 0:
+        pairs.append(("hb_filter_decomb", "hb_filter_decomb_cuda", "mode=31"))
+    for rname, gname, settings in pairs:
+        r = ref.run(rname, settings, clip, fmt, w, h)
+        g = hostlogic.run(gname, settings, clip, fmt, w, h)
+        same_stream(r, g)
+    assert hostlogic.buffers_alive() == 0
