@@ -14,6 +14,8 @@
 #include <string.h>
 
 void oracle_hostlogic_set_error(const char *fmt, ...);
+const void *const *oracle_hostlogic_frame_planes(const hbcu_frame_t *f);      /* hostlogic_frames.c */
+const int *oracle_hostlogic_frame_strides(const hbcu_frame_t *f);
 
 /* ------------------------------------------------------------------------------------------ a ring of packed frames */
 typedef struct
@@ -111,7 +113,10 @@ int oracle_hbcu_comb_detect_upload(hbcu_comb_detect_t *h, int64_t index, const v
     ring_put(&h->ring, index, planes, strides);
     return 0;
 }
-int oracle_hbcu_comb_detect_upload_frame(hbcu_comb_detect_t *h, int64_t index, hbcu_frame_t *in) { (void)h; (void)index; (void)in; return -1; }
+int oracle_hbcu_comb_detect_upload_frame(hbcu_comb_detect_t *h, int64_t index, hbcu_frame_t *in)
+{
+    return oracle_hbcu_comb_detect_upload(h, index, oracle_hostlogic_frame_planes(in)[0], oracle_hostlogic_frame_strides(in)[0]);
+}
 int oracle_hbcu_comb_detect_run(hbcu_comb_detect_t *h, int64_t prev, int64_t cur, int64_t next, int force_exhaustive)
 {
     const uint8_t *p = ring_get(&h->ring, prev), *c = ring_get(&h->ring, cur), *n = ring_get(&h->ring, next);
@@ -159,7 +164,10 @@ void oracle_hbcu_decomb_destroy(hbcu_decomb_t *h)
     free(h->eedi_frame); free(h->out); ring_free(&h->ring); free(h);
 }
 int oracle_hbcu_decomb_upload(hbcu_decomb_t *h, int64_t index, const void *const planes[3], const int strides[3]) { ring_put(&h->ring, index, planes, strides); return 0; }
-int oracle_hbcu_decomb_upload_frame(hbcu_decomb_t *h, int64_t index, hbcu_frame_t *in) { (void)h; (void)index; (void)in; return -1; }
+int oracle_hbcu_decomb_upload_frame(hbcu_decomb_t *h, int64_t index, hbcu_frame_t *in)
+{
+    return oracle_hbcu_decomb_upload(h, index, oracle_hostlogic_frame_planes(in), oracle_hostlogic_frame_strides(in));
+}
 int oracle_hbcu_decomb_wait_upload(hbcu_decomb_t *h, int64_t index) { (void)h; (void)index; return 0; }
 int oracle_hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next,
                               int frame_mode, int parity, int tff, void *const planes[3], const int strides[3])
@@ -180,7 +188,10 @@ int oracle_hbcu_decomb_filter(hbcu_decomb_t *h, int64_t ticket, int64_t prev, in
     return 0;
 }
 int oracle_hbcu_decomb_filter_frame(hbcu_decomb_t *h, int64_t ticket, int64_t prev, int64_t cur, int64_t next, int frame_mode, int parity, int tff, hbcu_frame_t *out)
-{ (void)h; (void)ticket; (void)prev; (void)cur; (void)next; (void)frame_mode; (void)parity; (void)tff; (void)out; return -1; }
+{
+    return oracle_hbcu_decomb_filter(h, ticket, prev, cur, next, frame_mode, parity, tff, (void *const *)oracle_hostlogic_frame_planes(out),
+                                     oracle_hostlogic_frame_strides(out));
+}
 int oracle_hbcu_decomb_wait(hbcu_decomb_t *h, int64_t ticket) { (void)h; (void)ticket; return 0; }
 int oracle_hbcu_decomb_poll(hbcu_decomb_t *h, int64_t ticket) { (void)h; (void)ticket; return 1; }
 
@@ -199,7 +210,27 @@ int oracle_hbcu_lapsharp_filter_frames(hbcu_lapsharp_t *h, int64_t ticket, hbcu_
                                        hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
 {
     (void)ticket;
-    if (in_frame != NULL || out_frame != NULL) return -1;
+    if (in_frame != NULL)
+    {
+        /* the host mirrors the stride region of a host buffer before the call (lapsharp.c:333); for a device frame the
+         * device side does it: hb_frame_buffer_mirror_stride's word arithmetic (fifo.c:906-959), restated */
+        in_planes = oracle_hostlogic_frame_planes(in_frame); in_strides = oracle_hostlogic_frame_strides(in_frame);
+        for (int c = 0; c < 3; c++)
+        {
+            const int w = c ? -((-h->cfg.width) >> h->cfg.chroma_shift_w) : h->cfg.width;
+            const int ht = c ? -((-h->cfg.height) >> h->cfg.chroma_shift_h) : h->cfg.height;
+            uint16_t *d = (uint16_t *)in_planes[c];
+            const int stride = in_strides[c] / 2, margin = stride - w, front = margin / 2, back = margin - front;
+            for (int y = 0; y < ht; y++)
+            {
+                int pos = y * stride + w;
+                for (int i = 0; i < back; i++) d[pos + i] = d[pos - i - 1];
+                pos = (y + 1) * stride - 1;
+                for (int i = 0; i < front; i++) d[pos - i] = d[pos + i + 1];
+            }
+        }
+    }
+    if (out_frame != NULL) { out_planes = (void *const *)oracle_hostlogic_frame_planes(out_frame); out_strides = oracle_hostlogic_frame_strides(out_frame); }
     for (int c = 0; c < 3; c++)
     {
         const int w = c ? -((-h->cfg.width) >> h->cfg.chroma_shift_w) : h->cfg.width;
@@ -242,7 +273,8 @@ int oracle_hbcu_unsharp_filter_frames(hbcu_unsharp_t *h, int64_t ticket, hbcu_fr
                                       hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
 {
     (void)ticket;
-    if (in_frame != NULL || out_frame != NULL) return -1;
+    if (in_frame != NULL) { in_planes = oracle_hostlogic_frame_planes(in_frame); in_strides = oracle_hostlogic_frame_strides(in_frame); }
+    if (out_frame != NULL) { out_planes = (void *const *)oracle_hostlogic_frame_planes(out_frame); out_strides = oracle_hostlogic_frame_strides(out_frame); }
     const int bps = h->cfg.depth > 8 ? 2 : 1;
     for (int c = 0; c < 3; c++)
     {
@@ -298,7 +330,8 @@ int oracle_hbcu_hqdn3d_filter_frames(hbcu_hqdn3d_t *h, int64_t ticket, hbcu_fram
                                      hbcu_frame_t *out_frame, void *const out_planes[3], const int out_strides[3])
 {
     (void)ticket;
-    if (in_frame != NULL || out_frame != NULL) return -1;
+    if (in_frame != NULL) { in_planes = oracle_hostlogic_frame_planes(in_frame); in_strides = oracle_hostlogic_frame_strides(in_frame); }
+    if (out_frame != NULL) { out_planes = (void *const *)oracle_hostlogic_frame_planes(out_frame); out_strides = oracle_hostlogic_frame_strides(out_frame); }
     const int bps = h->cfg.depth > 8 ? 2 : 1;
     for (int c = 0; c < 3; c++)
     {

@@ -98,21 +98,15 @@ int oracle_hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, voi
 int oracle_hbcu_nlmeans_wait(hbcu_nlmeans_t *h, int64_t index) { (void)h; (void)index; return 0; }
 int oracle_hbcu_nlmeans_poll(hbcu_nlmeans_t *h, int64_t index) { (void)h; (void)index; return 1; }
 
-/* device-resident frames do not exist on this side */
-static int no_device(const char *what) { oracle_hostlogic_set_error("%s: no device in the host-logic build", what); return -1; }
-int oracle_hbcu_nlmeans_upload_frame(hbcu_nlmeans_t *h, int64_t index, hbcu_frame_t *in) { (void)h; (void)index; (void)in; return no_device("upload_frame"); }
-int oracle_hbcu_nlmeans_filter_frame(hbcu_nlmeans_t *h, int64_t index, int navail, hbcu_frame_t *out) { (void)h; (void)index; (void)navail; (void)out; return no_device("filter_frame"); }
-int    oracle_hbcu_frame_alloc(hbcu_frame_t **f, int device, const int row_bytes[3], const int rows[3], const int strides[3])
-{ (void)device; (void)row_bytes; (void)rows; (void)strides; *f = NULL; return no_device("frame_alloc"); }
-void   oracle_hbcu_frame_retain(hbcu_frame_t *f) { (void)f; }
-void   oracle_hbcu_frame_release(hbcu_frame_t *f) { (void)f; }
-void  *oracle_hbcu_frame_plane(const hbcu_frame_t *f, int plane) { (void)f; (void)plane; return NULL; }
-int    oracle_hbcu_frame_stride(const hbcu_frame_t *f, int plane) { (void)f; (void)plane; return 0; }
-int    oracle_hbcu_frame_device(const hbcu_frame_t *f) { (void)f; return -1; }
-long   oracle_hbcu_frames_alive(void) { return 0; }
-int    oracle_hbcu_xfer_create(hbcu_xfer_t **x, int device, int depth) { (void)device; (void)depth; *x = NULL; return no_device("xfer_create"); }
-void   oracle_hbcu_xfer_destroy(hbcu_xfer_t *x) { (void)x; }
-int    oracle_hbcu_xfer_upload(hbcu_xfer_t *x, int64_t t, hbcu_frame_t *f, const void *const p[3], const int s[3]) { (void)x; (void)t; (void)f; (void)p; (void)s; return -1; }
-int    oracle_hbcu_xfer_download(hbcu_xfer_t *x, int64_t t, hbcu_frame_t *f, void *const p[3], const int s[3]) { (void)x; (void)t; (void)f; (void)p; (void)s; return -1; }
-int    oracle_hbcu_xfer_wait(hbcu_xfer_t *x, int64_t t) { (void)x; (void)t; return -1; }
-int    oracle_hbcu_xfer_poll(hbcu_xfer_t *x, int64_t t) { (void)x; (void)t; return -1; }
+/* device frames: see hostlogic_frames.c */
+const void *const *oracle_hostlogic_frame_planes(const hbcu_frame_t *f);
+const int *oracle_hostlogic_frame_strides(const hbcu_frame_t *f);
+
+int oracle_hbcu_nlmeans_upload_frame(hbcu_nlmeans_t *h, int64_t index, hbcu_frame_t *in)
+{
+    return oracle_hbcu_nlmeans_upload(h, index, oracle_hostlogic_frame_planes(in), oracle_hostlogic_frame_strides(in));
+}
+int oracle_hbcu_nlmeans_filter_frame(hbcu_nlmeans_t *h, int64_t index, int navail, hbcu_frame_t *out)
+{
+    return oracle_hbcu_nlmeans_filter(h, index, navail, (void *const *)oracle_hostlogic_frame_planes(out), oracle_hostlogic_frame_strides(out));
+}

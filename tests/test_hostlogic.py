@@ -250,3 +250,53 @@ def test_empty_and_tiny_streams_all_host_filters(ref, hostlogic, n, w, h):
         g = hostlogic.run(gname, settings, clip, fmt, w, h)
         same_stream(r, g)
     assert hostlogic.buffers_alive() == 0
+
+
+# ---------------------------------------------------------------- device-resident chains, host side
+UP, DOWN = "hb_filter_hbcu_upload", "hb_filter_hbcu_download"
+
+
+def device_frames_alive(hostlogic):
+    import ctypes as C
+    hostlogic.lib.oracle_hbcu_frames_alive.restype = C.c_long
+    return hostlogic.lib.oracle_hbcu_frames_alive()
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_device_resident_chain_host_side(ref, hostlogic, depth):
+    """comb_detect -> decomb (selective) -> NLMeans -> lapsharp -> unsharp -> hqdn3d between the upload and download
+    adapters: HBCU_DEVICE buffers, shallow dups of passed-through frames, hw_pix_fmt propagation, reference counts --
+    with host memory standing in for device frames (oracle/port/hostlogic_frames.c).  Same pictures as the reference's
+    plain chain, nothing left alive."""
+    w, h = 144, 84                     # luma stride 192 > width: lapsharp reads the mirrored padding of a device frame
+    clip, flags, _ = decomb_inputs(depth, w, h, 7, seed=3)
+    names_r = ["hb_filter_comb_detect", "hb_filter_decomb", "hb_filter_denoise", "hb_filter_nlmeans", "hb_filter_chroma_smooth_mt", "hb_filter_lapsharp_mt",
+               "hb_filter_unsharp_mt"]
+    names_g = [UP] + [n.replace("_mt", "") + "_cuda" for n in names_r] + [DOWN]
+    s = [None, "mode=39", "y-spatial=2", "y-strength=6:y-patch-size=3:y-range=3:threads=1", "cb-strength=0.8", "y-strength=0.2:y-kernel=isolap", "y-strength=0.4:y-size=5"]
+    r = ref.run(names_r, s, clip, FMT[depth], w, h, flags=flags)
+    g = hostlogic.run(names_g, [None] + s + [None], clip, FMT[depth], w, h, flags=flags)
+    same_stream(r, g)
+    assert list(g.combed) == list(r.combed) and len(set(r.combed)) > 1
+    assert device_frames_alive(hostlogic) == 0 and hostlogic.buffers_alive() == 0
+
+
+def test_mixed_host_and_device_segments_host_side(ref, hostlogic):
+    w, h = 112, 64
+    clip, flags, _ = decomb_inputs(8, w, h, 6, seed=13)
+    r = ref.run(["hb_filter_comb_detect", "hb_filter_decomb", "hb_filter_nlmeans"], [None, "mode=63", "y-strength=3:y-patch-size=3:threads=1"], clip, FMT[8], w, h, flags=flags)
+    g = hostlogic.run([UP, "hb_filter_comb_detect_cuda", "hb_filter_decomb_cuda", DOWN, "hb_filter_nlmeans_cuda"],
+                      [None, None, "mode=63", None, "y-strength=3:y-patch-size=3"], clip, FMT[8], w, h, flags=flags)
+    same_stream(r, g)
+    assert g.vrate == r.vrate
+    assert device_frames_alive(hostlogic) == 0 and hostlogic.buffers_alive() == 0
+
+
+def test_device_chain_misuse_fails_loudly_host_side(hostlogic):
+    w, h = 96, 64
+    clip = synth.progressive_clip(FMT[8], w, h, 3)
+    with pytest.raises(RuntimeError):                    # no download adapter: the sink refuses device buffers
+        hostlogic.run([UP, "hb_filter_lapsharp_cuda"], [None, "y-strength=0.2"], clip, FMT[8], w, h)
+    g = hostlogic.run([UP, "hb_filter_detelecine_cuda", DOWN], [None, None, None], clip, FMT[8], w, h)
+    assert g.init_failed & 2                             # detelecine takes host buffers only, and says so at init
+    assert device_frames_alive(hostlogic) == 0 and hostlogic.buffers_alive() == 0
