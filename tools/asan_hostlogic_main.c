@@ -39,6 +39,32 @@ int main(void)
                 if (io.init_failed) { printf("init failed: %s %s\n", jobs[j].f->name, jobs[j].s[k] ? jobs[j].s[k] : ""); return 1; }
                 free(in); free(out);
             }
+    /* a device-resident chain (host memory stands in for device frames): reference counting of HBCU_DEVICE buffers */
+    {
+        extern hb_filter_object_t hb_filter_hbcu_upload, hb_filter_hbcu_download;
+        extern long oracle_hbcu_frames_alive(void);
+        hb_filter_object_t *chain[7] = { &hb_filter_hbcu_upload, &hb_filter_comb_detect_cuda, &hb_filter_decomb_cuda, &hb_filter_nlmeans_cuda,
+                                         &hb_filter_lapsharp_cuda, &hb_filter_unsharp_cuda, &hb_filter_hbcu_download };
+        const char *sets[7] = { NULL, NULL, "mode=63", "y-strength=6:y-patch-size=3", "y-strength=0.2", NULL, NULL };
+        for (int d = 0; d < 2; d++)
+        {
+            const int fmt = fmts[d], w = 112, h = 64, n = 6;
+            const size_t fb = hb_harness_frame_bytes(fmt, w, h);
+            uint8_t *in = malloc(fb * n), *out = malloc(fb * (2 * n + 8));
+            uint16_t flags[6];
+            for (int t = 0; t < n; t++)
+            {
+                for (size_t i = 0; i < fb; i++) in[t * fb + i] = (uint8_t)((d && (i & 1)) ? rnd() % 4 : ((i / w) & 1 ? i / 3 + t * 29 : i / 3 + t * 5));
+                flags[t] = 0x0008;
+            }
+            int64_t start[40], stop[40]; double dur[40]; uint8_t comb[40]; uint16_t oflags[40];
+            hb_harness_io_t io = { .pix_fmt = fmt, .width = w, .height = h, .n_in = n, .in = in, .in_flags = flags, .out = out, .out_capacity = 2 * n + 8,
+                                   .out_combed = comb, .out_flags = oflags, .out_start = start, .out_stop = stop, .out_duration = dur };
+            if (hb_harness_run_chain(7, chain, sets, &io) != 0 || io.init_failed) { printf("device chain failed\n"); return 1; }
+            free(in); free(out);
+        }
+        printf("device chain ran; device frames alive: %ld\n", oracle_hbcu_frames_alive());
+    }
     printf("all filters ran; alive buffers: %ld\n", hb_shim_buffers_alive());
     return 0;
 }
