@@ -82,6 +82,46 @@ def test_sharded_comb_detect_and_decomb_equal_unsharded(ref, world, block):
         assert np.array_equal(_sharded(blocks, world, clip_of, decomb, k), whole), mode
 
 
+def test_sharded_product_host_filters_equal_unsharded_reference(ref):
+    """the same property with the PRODUCT's filter objects (their host code over the CPU stand-ins for the device calls,
+    tests/test_hostlogic.py) on the sharded side and the reference, unsharded, on the other: what bench.py --gpus N and a
+    multi-GPU libhb would run per rank"""
+    from handbrake_b200.hblib import FilterLib
+    from test_hostlogic import HOSTLOGIC_SO
+    from test_oracle import decomb_inputs
+    if not HOSTLOGIC_SO.exists():
+        pytest.skip("oracle/_ref/libhostlogic.so not built")
+    prod = FilterLib(HOSTLOGIC_SO)
+    w, h, fmt = 96, 64, synth.PIX_FMT_YUV420P
+    clip, flags, combed = decomb_inputs(8, w, h, 8, seed=3)
+    n, world = clip.shape[0], 3
+    window = {}
+
+    def clip_of(a, b):
+        window["range"] = (a, b)
+        return clip[a:b]
+
+    blocks = sharding.plan_blocks(n, world, 2, halo_before=1, halo_after=1)
+    for mode, k in ((7, 1), (23, 2)):
+        def decomb(frames):
+            a, b = window["range"]
+            return prod.run("hb_filter_decomb_cuda", f"mode={mode}", frames, fmt, w, h, flags=flags[a:b]).frames
+        whole = ref.run("hb_filter_decomb", f"mode={mode}", clip, fmt, w, h, flags=flags).frames
+        assert np.array_equal(_sharded(blocks, world, clip_of, decomb, k), whole), mode
+
+    def comb(frames):
+        a, b = window["range"]
+        return np.asarray(prod.run("hb_filter_comb_detect_cuda", None, frames, fmt, w, h, flags=flags[a:b]).combed, np.uint8).reshape(-1, 1)
+    whole = np.asarray(ref.run("hb_filter_comb_detect", None, clip, fmt, w, h, flags=flags).combed, np.uint8)
+    assert np.array_equal(_sharded(blocks, world, clip_of, comb).ravel(), whole)
+
+    nf = 3
+    blocks = sharding.plan_blocks(n, world, 2, halo_after=nf - 1)
+    s = f"y-strength=6:y-patch-size=3:y-range=3:y-frame-count={nf}"
+    nlm = lambda fr: prod.run("hb_filter_nlmeans_cuda", s, fr, fmt, w, h).frames
+    assert np.array_equal(_sharded(blocks, world, lambda a, b: clip[a:b], nlm), ref.run("hb_filter_nlmeans", s, clip, fmt, w, h).frames)
+
+
 def test_sharded_lapsharp_needs_no_halo(ref):
     w, h = 96, 64
     clip = synth.progressive_clip(synth.PIX_FMT_YUV420P, w, h, 7, seed=4, noise=15)
