@@ -27,11 +27,13 @@
 #include "hbcu_frames.h"
 #include "../../include/hbcu.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 #include <cstdio>
 
@@ -699,6 +701,8 @@ __device__ __forceinline__ float byte_as_biased_float(uint32_t w, int k)
 {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k));
 }
+
+#include "nlmeans_v3.cuh"
 
 template <int NH, int TH, int NW, bool ORIGIN>
 __device__ __forceinline__ void nlm_group_fast(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp,
@@ -1481,6 +1485,8 @@ struct hbcu_nlmeans_s
     std::vector<uint8_t *> out_mem;       // [oslot*3+plane]
     std::vector<int64_t>   ring_index;    // frame index held by each slot
     std::vector<CUtensorMap> maps;        // [slot*3+plane] TMA descriptors of the bordered planes
+    std::vector<CUtensorMap> maps3;       // same planes, box height of the v3 8-bit kernel's tile
+    int v3_nw, v3_rs, v3_tmem;            // v3 kernel shape (warps, rows per warp, accumulators in tensor memory); v3_nw == 0: off
     float *d_exptable;                    // 3 x 128
     unsigned *d_range_flag;               // sticky: a 16-bit plane held a sample above kFast16Max (see nlmeans_fast16_kernel)
     cudaStream_t s_h2d, s_pad, s_compute, s_d2h;   // s_compute = s_comp[frame index & (n_comp - 1)] of the launch being queued
@@ -1593,6 +1599,63 @@ constexpr int kTH8 = 144;
 int g_ssd_variant = 1;     // 1: packed-byte VABSDIFF4 + IDP4A patch-row sums (measured 7 % faster), 0: fp32 prefix sums (FFMA);
                            // HBCU_NLMEANS_SSD selects (test/tuning hook: both are exact, tests run both)
 
+template <int NH, int NW, int RS, bool TMEM, int NBUF>
+int launch_v3(FusedParams &fp, cudaStream_t st)
+{
+    using L = V3Layout<NW, RS, TMEM, NBUF>;
+    static bool configured = false;
+    if (!configured)
+    {
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_v3_kernel<NH, NW, RS, TMEM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    int total = 0;
+    for (int i = 0; i < fp.nplanes; i++)
+    {
+        fp.first_tile[i] = total;
+        fp.tiles_x[i] = (fp.k[i].w + kTileW - 1) / kTileW;
+        total += fp.tiles_x[i] * ((fp.k[i].h + L::kTH - 1) / L::kTH);
+    }
+    fp.first_tile[fp.nplanes] = total;
+    nlmeans_v3_kernel<NH, NW, RS, TMEM, NBUF><<<total, NW * 32, L::kTotal, st>>>(fp);
+    hbcu::count_launch();
+    return 0;
+}
+
+// v3 shapes built into the library: {warps, rows per warp, accumulators in tensor memory}.  Patch 9 (NH = 4) needs
+// 8 warps (its 9-row history does not fit 168 registers).
+struct V3Shape { int nw, rs, tmem; };
+constexpr V3Shape kV3Default = { 12, 21, 1 };
+
+bool v3_shape_ok(int nw, int rs, int tmem, int n_half)
+{
+    if (n_half == 4) return nw == 8 && rs == 27 && tmem == 1;
+    if (nw == 12 && rs == 12 && tmem == 0) return true;
+    if (nw == 12 && rs == 21 && tmem == 1) return true;
+    if (n_half == 3) return tmem == 1 && ((nw == 12 && rs == 18) || (nw == 8 && rs == 28));
+    return false;
+}
+
+int launch_v3_nh(int nw, int rs, int tmem, FusedParams &fp, cudaStream_t st)
+{
+    const int nh = fp.k[0].n_half;
+    // every displacement row of this range must decompose into group shapes the kernels were built with
+    for (int pl = 0; pl < fp.nplanes; pl++)
+        for (int dx0 = -fp.k[pl].r_half; dx0 <= fp.k[pl].r_half; dx0 += kGroup)
+        {
+            const int ng = std::min(kGroup, fp.k[pl].r_half - dx0 + 1);
+            if (!v3_group_known(ng, (12 + dx0) & 3, kOrgNone)) return 1;
+            if (dx0 <= 0 && dx0 + ng > 0 && !v3_group_known(ng, (12 + dx0) & 3, -dx0)) return 1;
+        }
+#define V3CASE(NH_, NW_, RS_, TM_, NB_) if (nh == NH_ && nw == NW_ && rs == RS_ && tmem == TM_) return launch_v3<NH_, NW_, RS_, TM_ != 0, NB_>(fp, st)
+    V3CASE(1, 12, 12, 0, 1); V3CASE(2, 12, 12, 0, 1); V3CASE(3, 12, 12, 0, 1);
+    V3CASE(1, 12, 21, 1, 2); V3CASE(2, 12, 21, 1, 2); V3CASE(3, 12, 21, 1, 2);
+    V3CASE(3, 12, 18, 1, 2); V3CASE(3, 8, 28, 1, 2);
+    V3CASE(4, 8, 27, 1, 2);
+#undef V3CASE
+    return 1;
+}
+
 int launch_fast8_nh(FusedParams &kp, cudaStream_t st)
 {
     if (g_ssd_variant == 1)
@@ -1670,8 +1733,9 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
             fp.nplanes = 1;
             fp.range_flag = nullptr;
             fp.k[0] = kp;
-            for (int f = 0; f < kp.nf; f++) fp.maps[0][f] = tp.maps[f];
-            rc = launch_fast8_nh(fp, h->s_compute);
+            const bool v3 = h->v3_nw > 0 && v3_shape_ok(h->v3_nw, h->v3_rs, h->v3_tmem, kp.n_half);
+            for (int f = 0; f < kp.nf; f++) fp.maps[0][f] = v3 ? h->maps3[slots[f] * 3 + plane] : tp.maps[f];
+            rc = v3 ? launch_v3_nh(h->v3_nw, h->v3_rs, h->v3_tmem, fp, h->s_compute) : launch_fast8_nh(fp, h->s_compute);
         }
         else
             rc = h->bps == 1 ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute) : launch_tiled_nh<uint16_t, kTH16>(tp, h->s_compute);
@@ -1822,6 +1886,7 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         if (!fast8_ok(h, kps[pl])) fused = false;
         if (nh < 0) nh = kps[pl].n_half; else if (nh != kps[pl].n_half) fused = false;
     }
+    const int nh8 = nh;
     bool fused16 = (h->impl == 0 || h->impl == 2) && h->bps == 2;
     nh = -1;
     for (int pl = 0; pl < 3 && fused16; pl++)
@@ -1860,14 +1925,16 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         FusedParams fp;
         fp.nplanes = 0;
         fp.range_flag = nullptr;
+        const bool v3 = h->v3_nw > 0 && v3_shape_ok(h->v3_nw, h->v3_rs, h->v3_tmem, nh8);
         for (int pl = 0; pl < 3; pl++)
         {
             if (!active[pl]) continue;
             fp.k[fp.nplanes] = kps[pl];
-            for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = h->maps[slots[pl][f] * 3 + pl];
+            for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = (v3 ? h->maps3 : h->maps)[slots[pl][f] * 3 + pl];
             fp.nplanes++;
         }
-        if (launch_fast8_nh(fp, h->s_compute) != 0) { set_error("nlmeans: fused launch failed"); return -1; }
+        if ((v3 ? launch_v3_nh(h->v3_nw, h->v3_rs, h->v3_tmem, fp, h->s_compute) : launch_fast8_nh(fp, h->s_compute)) != 0)
+        { set_error("nlmeans: fused launch failed"); return -1; }
         HBCU_CHECK(cudaGetLastError());
         h->kernel_launches++;
     }
@@ -1956,6 +2023,15 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->impl = 0;
     if (const char *e = getenv("HBCU_NLMEANS_IMPL")) h->impl = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;   // test hook
     if (const char *e = getenv("HBCU_NLMEANS_SSD")) g_ssd_variant = atoi(e);                                  // tuning hook
+    // v3 8-bit kernel shape; HBCU_NLMEANS_V3=off | "warps,rows,tmem" (tuning hook, see v3_shape_ok)
+    h->v3_nw = kV3Default.nw; h->v3_rs = kV3Default.rs; h->v3_tmem = kV3Default.tmem;
+    if (const char *e = getenv("HBCU_NLMEANS_V3"))
+    {
+        int a = 0, b = 0, c = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && v3_shape_ok(a, b, c, 3)) { h->v3_nw = a; h->v3_rs = b; h->v3_tmem = c; }
+        else h->v3_nw = 0;
+    }
+    if (h->bps != 1) h->v3_nw = 0;
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;
@@ -2030,6 +2106,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ev_kernel.assign(h->out_slots, nullptr);
     h->ev_d2h.assign(h->out_slots, nullptr);
     h->maps.resize(h->ring * 3);
+    h->maps3.resize(h->ring * 3);
     for (int s = 0; s < h->ring; s++)
     {
         CK(cudaEventCreateWithFlags(&h->ev_upload[s], cudaEventDisableTiming));
@@ -2046,6 +2123,14 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
             if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
                                            (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
                                            th + 2 * kHalo) != 0)
+            {
+                hbcu_nlmeans_destroy(h);
+                return -1;
+            }
+            if (h->v3_nw > 0 &&
+                hbcu::encode_tensor_map_2d(&h->maps3[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
+                                           (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
+                                           h->v3_nw * h->v3_rs + 2 * kHalo) != 0)
             {
                 hbcu_nlmeans_destroy(h);
                 return -1;

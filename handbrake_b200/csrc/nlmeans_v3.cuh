@@ -1,0 +1,524 @@
+// nlmeans_v3.cuh -- third generation of the fused 8-bit NLMeans tile kernel (included by nlmeans.cu).
+//
+// Same arithmetic contract as nlmeans_fast8_kernel (bit-identical to templates/nlmeans_template.c:593-717), same
+// tiling idea (TMA tile in shared memory, a lane marches down a 4-pixel-wide column strip keeping the vertical running
+// sum of horizontal patch-row sums and its N-row history in registers).  What changed, each item from the r01 ncu
+// capture (profiles/r01g_nlmeans_fused_ncu.json: 29 thread-instructions per pixel x displacement, 68 % issue,
+// ALU pipe 57 %, 35 % of the shared-memory wavefront budget):
+//   * group shape (NG displacements), byte offset of the compare window and the origin slot are template parameters:
+//     no per-row predicate/branch chains, and for the range-3 presets the three compare windows come straight out of
+//     the raw words with 6 funnel shifts per row instead of 13 (the source window is never re-aligned: only the
+//     relative alignment of source and compare matters to VABSDIFF4);
+//   * the running sum V is kept as the integer 0x4B000000 + V: as a float that is 2^23 + V, so
+//     fma.rn.sat(2^23 + V, wfact/128, -2^23 * wfact/128) = rn(V * wfact/128) exactly -- I2F and FMUL.SAT collapse into
+//     one FFMA on the idle FMA pipe;
+//   * the three-row delay line of compare words is indexed by the unrolled row slot instead of being shifted: no MOVs;
+//   * warm-up rows are peeled: the steady-state loop has no "row >= NH" test;
+//   * the compare tile of frame 1 is in flight while frame 0 is compared with itself (second mbarrier);
+//   * accumulators (weight sum, pixel sum; 8 bytes per pixel) can live in TENSOR MEMORY (tcgen05.ld/st, 32x32b.x8:
+//     a lane's 4 x 2 floats are 8 columns of its own TMEM lane).  That takes their 16 wavefronts per row off the
+//     shared-memory pipe and -- shared memory no longer bounds the tile -- lets a warp march 18-20 rows instead of 12:
+//     the 2*NH warm-up rows drop from 50 % to 30-33 % of the patch-row-sum work.
+#pragma once
+
+template <int NW, int RS, bool TMEM, int NBUF>
+struct V3Layout
+{
+    static constexpr int kTH        = NW * RS;
+    static constexpr int kLoads     = kTH + 2 * kHalo > 256 ? 2 : 1;                     // a TMA box has at most 256 rows
+    static constexpr int kBoxRows   = ((kTH + 2 * kHalo + kLoads - 1) / kLoads + 3) / 4 * 4;   // 4 rows x 160 B keep every box 128-byte aligned
+    static constexpr int kRows      = kBoxRows * kLoads;                                 // >= kTH + 2 * kHalo; surplus rows are loaded, never used
+    static constexpr int kTileBytes = kRows * kTilePW;
+    static constexpr int kAccBytes  = TMEM ? 0 : kTH * kTileW * (int)sizeof(float);      // per accumulator array
+    static constexpr int kLutBytes  = kLutEntries * 32 * (int)sizeof(float);
+    static constexpr int kOffCur    = 0;
+    static constexpr int kOffCmp    = kOffCur + kTileBytes;
+    static constexpr int kOffWs     = kOffCmp + NBUF * kTileBytes;
+    static constexpr int kOffPs     = kOffWs + kAccBytes;
+    static constexpr int kOffLut    = kOffPs + kAccBytes;
+    static constexpr int kOffBar    = kOffLut + kLutBytes;                               // 1 + NBUF mbarriers, TMEM base word
+    static constexpr int kUsed      = kOffBar + 64;
+    // one CTA per SM by construction (the TMEM variant allocates all 512 columns; a second resident CTA would spin)
+    static constexpr int kTotal     = kUsed < 117 * 1024 ? 117 * 1024 : kUsed;
+    static_assert(kBoxRows <= 256, "TMA box rows");
+    static_assert((kBoxRows * kTilePW) % 128 == 0, "TMA destination must stay 128-byte aligned");
+    static_assert(!TMEM || ((NW + 3) / 4 * RS * 8 <= 512), "accumulators must fit 512 TMEM columns per lane quarter");
+    static_assert(kTotal <= 227 * 1024, "shared memory");
+};
+
+// accumulator rows of one warp: shared memory (float4 per lane and array) or tensor memory (8 columns per lane)
+template <bool TMEM> struct V3Acc;
+
+template <> struct V3Acc<false>
+{
+    float *ws, *ps;     // this lane's first row
+    __device__ __forceinline__ void load(int r, uint32_t (&v)[8]) const
+    {
+        const uint4 a = *reinterpret_cast<const uint4 *>(ws + r * kTileW);
+        const uint4 b = *reinterpret_cast<const uint4 *>(ps + r * kTileW);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ __forceinline__ void wait_load(uint32_t (&)[8]) const {}
+    __device__ __forceinline__ void store(int r, const uint32_t (&v)[8]) const
+    {
+        *reinterpret_cast<uint4 *>(ws + r * kTileW) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4 *>(ps + r * kTileW) = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+    __device__ __forceinline__ void wait_store() const {}
+};
+
+template <> struct V3Acc<true>
+{
+    uint32_t taddr;     // lane quarter of this warp (bits 31..16) + first column of its strip
+    __device__ __forceinline__ void load(int r, uint32_t (&v)[8]) const
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr + (uint32_t)r * 8u));
+    }
+    // the registers are tied to the wait so that no consumer is scheduled above it
+    __device__ __forceinline__ void wait_load(uint32_t (&v)[8]) const
+    {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+    }
+    __device__ __forceinline__ void store(int r, const uint32_t (&v)[8]) const
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     :: "r"(taddr + (uint32_t)r * 8u), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                     : "memory");
+    }
+    __device__ __forceinline__ void wait_store() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+
+constexpr int kOrgNone = -1;
+constexpr uint32_t kVBias = 0x4B000000u;     // bits of 2^23
+
+// One group of NG horizontally adjacent displacements (dy, dx0 .. dx0+NG-1) over `rows` output rows of this warp's strip.
+//   OBS  : (12 + dx0) & 3, the byte offset of the compare window inside its first word
+//   ORG  : slot of the origin displacement inside the group, or kOrgNone
+// A struct so that the row step can be a function template of its unrolled slot K (every index into hist / P is a
+// compile-time constant; everything is force-inlined and the arrays live in registers).
+template <int NH, int NG, int OBS, int ORG, class ACC>
+struct V3Group
+{
+    static constexpr int N      = 2 * NH + 1;
+    static constexpr int PW     = kTilePW / 4;       // tile pitch in words
+    static constexpr int FIRSTB = 4 - NH;            // the source stream starts 4 pixels left of the lane's first pixel:
+    static constexpr int LASTB  = 7 + NH;            // the four windows cover its bytes FIRSTB .. LASTB
+    static constexpr int NWA    = LASTB / 4 + 1;     // source words (3 for every patch size <= 9)
+    static constexpr int LASTC  = LASTB + NG - 1;    // last compare-stream byte any displacement of the group touches
+    static constexpr int NAL    = LASTC / 4 + 1;     // compare-stream words
+    static constexpr int NRAW   = NAL + 1;           // raw words that cover them at any byte offset
+    static_assert(NWA == 3, "patch size");
+
+    uint32_t V[NG][4];
+    uint32_t hist[N][NG][4];
+    uint32_t P[N][2];                                // compare-stream words 1 and 2 of the last rows: the averaged pixels
+    const uint32_t *arow, *brow, *orow;
+    const ACC &acc;
+    uint32_t lut_lane_addr;
+    float wscale, wbias;
+    double origin_tune;
+
+    __device__ __forceinline__ V3Group(const uint32_t *cur, const uint32_t *cmp, const ACC &acc_, uint32_t lut_lane_addr_, float wscale_,
+                                       float wbias_, double origin_tune_, int seg_y0, int lane, int dy, int dx0)
+        : acc(acc_), lut_lane_addr(lut_lane_addr_), wscale(wscale_), wbias(wbias_), origin_tune(origin_tune_)
+    {
+        const int s   = 12 + dx0;                    // tile byte (relative to 4 * lane) of compare-stream byte 0
+        const int wb0 = s >> 2;
+#pragma unroll
+        for (int g = 0; g < NG; g++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                V[g][i] = kVBias;
+#pragma unroll
+                for (int k = 0; k < N; k++) hist[k][g][i] = 0;
+            }
+#pragma unroll
+        for (int k = 0; k < N; k++) P[k][0] = P[k][1] = 0;
+        arow = cur + (seg_y0 - NH + kHalo) * PW + lane + 3;
+        brow = cmp + (seg_y0 - NH + kHalo + dy) * PW + lane + wb0;
+        orow = cur + (seg_y0 + kHalo) * PW + lane + kHaloX / 4;
+    }
+
+    static __device__ __forceinline__ bool is_origin(int g) { return ORG >= 0 && g == ORG; }
+
+    // one row step in unrolled slot K; OUT: the row NH above completes and is averaged into accumulator row r
+    template <int K, bool OUT>
+    __device__ __forceinline__ void step(int r)
+    {
+        uint32_t a[NWA], raw[NRAW], bg0[NAL];
+#pragma unroll
+        for (int j = 0; j < NWA; j++) a[j] = arow[j];
+#pragma unroll
+        for (int j = 0; j < NRAW; j++) raw[j] = brow[j];
+        arow += PW;
+        brow += PW;
+        uint32_t accv[8];
+        if (OUT) acc.load(r, accv);
+        // compare stream aligned for displacement 0 of the group
+#pragma unroll
+        for (int j = 0; j < NAL; j++) bg0[j] = OBS == 0 ? raw[j] : __funnelshift_r(raw[j], raw[j + 1], 8 * OBS);
+#pragma unroll
+        for (int g = 0; g < NG; g++)
+        {
+            if (ORG != kOrgNone && is_origin(g)) continue;
+            uint32_t D[NWA];
+#pragma unroll
+            for (int w = 0; w < NWA; w++)
+            {
+                uint32_t bw;
+                if (g == 0) bw = bg0[w];
+                else
+                {
+                    const int sh = (OBS + g) & 3, q = (OBS + g) >> 2;       // compile-time after unrolling
+                    const int j1 = w + q + 1 < NRAW ? w + q + 1 : NRAW - 1;
+                    bw = sh ? __funnelshift_r(raw[w + q], raw[j1], 8 * sh) : raw[w + q];
+                }
+                D[w] = __vabsdiffu4(a[w], bw);
+            }
+            if constexpr (NH == 3)
+            {
+                // patch 7: the windows are bytes 1+i .. 7+i of the D stream = word 1 (bytes 4..7, shared) plus exactly
+                // three more bytes.  Byte 0 of the stream belongs to no window: cleared, it is the zero that pads those
+                // three bytes (gathered by PRMT from words 0 and 2) to a word, so every window is IDP4A(X, X, T1).
+                const uint32_t T1 = __dp4a(D[1], D[1], 0u);
+                const uint32_t Z  = D[0] & 0xFFFFFF00u;
+                uint32_t X[4];
+                X[0] = Z;                                   // bytes 1, 2, 3
+                X[1] = __byte_perm(Z, D[2], 0x0432);        // bytes 2, 3, 8
+                X[2] = __byte_perm(Z, D[2], 0x0543);        // bytes 3, 8, 9
+                X[3] = __byte_perm(Z, D[2], 0x0654);        // bytes 8, 9, 10
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    const uint32_t hs = __dp4a(X[i], X[i], T1);
+                    V[g][i] = V[g][i] + hs - hist[K][g][i];
+                    hist[K][g][i] = hs;
+                }
+            }
+            else
+            {
+            // patch-row sums over bytes FIRSTB+i .. FIRSTB+i+N-1 of the D stream: whole words by IDP4A(D, D), partial
+            // words by IDP4A(D & mask, D); the first whole word is shared by the four windows
+            uint32_t T[NWA];
+#pragma unroll
+            for (int w = 0; w < NWA; w++) T[w] = __dp4a(D[w], D[w], 0u);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                const int b0 = FIRSTB + i, b1 = FIRSTB + i + N - 1;
+                uint32_t hs = 0;
+                bool started = false;
+#pragma unroll
+                for (int w = 0; w < NWA; w++)
+                {
+                    const int lo = b0 > 4 * w ? b0 : 4 * w, hi = b1 < 4 * w + 3 ? b1 : 4 * w + 3;
+                    if (lo == 4 * w && hi == 4 * w + 3 && !started) { hs = T[w]; started = true; }
+                }
+                bool used_full = false;
+#pragma unroll
+                for (int w = 0; w < NWA; w++)
+                {
+                    const int lo = b0 > 4 * w ? b0 : 4 * w, hi = b1 < 4 * w + 3 ? b1 : 4 * w + 3;
+                    if (lo > hi) continue;
+                    if (lo == 4 * w && hi == 4 * w + 3)
+                    {
+                        if (started && !used_full) { used_full = true; continue; }   // already in hs
+                        hs = __dp4a(D[w], D[w], hs);
+                    }
+                    else
+                    {
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++)
+                            if (4 * w + bb >= lo && 4 * w + bb <= hi) m |= 0xFFu << (8 * bb);
+                        hs = __dp4a(D[w] & m, D[w], hs);
+                    }
+                }
+                V[g][i] = V[g][i] + hs - hist[K][g][i];
+                hist[K][g][i] = hs;
+            }
+            }
+        }
+        if (OUT)
+        {
+            constexpr int KP = (K + N - NH) % N;          // the compare row of the output row was loaded NH steps ago
+            const uint32_t p0 = P[KP][0], p1 = P[KP][1];
+            float pixv[NG + 3];
+#pragma unroll
+            for (int j = 0; j < NG + 3; j++)
+                pixv[j] = __fsub_rn(byte_as_biased_float(j < 4 ? p0 : p1, j & 3), 8388608.0f);
+            acc.wait_load(accv);                          // issued at the top of the step: the patch-row sums covered its latency
+            float wgt[NG][4];
+#pragma unroll
+            for (int g = 0; g < NG; g++)
+            {
+                if (ORG != kOrgNone && is_origin(g)) continue;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    float t, u;
+                    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(__uint_as_float(V[g][i])), "f"(wscale), "f"(wbias));
+                    asm("add.rz.f32 %0, %1, 0f47800000;" : "=f"(u) : "f"(t));   // 65536 + floor(128 t)
+                    const uint32_t addr = (__float_as_uint(u) << 7) + lut_lane_addr;
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(wgt[g][i]) : "r"(addr));
+                }
+            }
+            float ws[4], ps[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { ws[i] = __uint_as_float(accv[i]); ps[i] = __uint_as_float(accv[4 + i]); }
+#pragma unroll
+            for (int g = 0; g < NG; g++)
+            {
+                if (ORG != kOrgNone && is_origin(g))
+                {
+                    const uint32_t cw = orow[r * PW];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) add_origin(ws[i], ps[i], origin_tune, (int)((cw >> (8 * i)) & 0xffu));
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                    {
+                        ws[i] = __fadd_rn(ws[i], wgt[g][i]);
+                        ps[i] = __fadd_rn(ps[i], __fmul_rn(wgt[g][i], pixv[g + i]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { accv[i] = __float_as_uint(ws[i]); accv[4 + i] = __float_as_uint(ps[i]); }
+            acc.store(r, accv);
+        }
+        P[K][0] = bg0[1];
+        P[K][1] = bg0[2];
+    }
+
+    template <int... Ks>
+    __device__ __forceinline__ void warm_up(std::integer_sequence<int, Ks...>)
+    {
+        (step<Ks, false>(0), ...);
+    }
+    template <int... Ms>
+    __device__ __forceinline__ void rows_from(int r0, int rows, std::integer_sequence<int, Ms...>)
+    {
+        ((r0 + Ms < rows ? step<(2 * NH + Ms) % N, true>(r0 + Ms) : (void)0), ...);
+    }
+    template <int... Ms>
+    __device__ __forceinline__ void batch(int r0, std::integer_sequence<int, Ms...>)
+    {
+        (step<(2 * NH + Ms) % N, true>(r0 + Ms), ...);
+    }
+
+    // EXACT: `rows` is a multiple of N -- batches of N rows without a per-row test (and without the register moves the
+    // merge points of those tests cost)
+    template <bool EXACT>
+    __device__ __forceinline__ void run(int rows)
+    {
+        // warm-up: the first 2*NH rows only build patch-row sums (slots 0 .. 2NH-1);
+        // steady state: output row r completes at row step r + 2NH, slot (r + 2NH) % N
+        warm_up(std::make_integer_sequence<int, 2 * NH>{});
+        if (EXACT)
+        {
+#pragma unroll 1
+            for (int r0 = 0; r0 < rows; r0 += N) batch(r0, std::make_integer_sequence<int, N>{});
+        }
+        else
+        {
+#pragma unroll 1
+            for (int r0 = 0; r0 < rows; r0 += N) rows_from(r0, rows, std::make_integer_sequence<int, N>{});
+        }
+        acc.wait_store();
+    }
+};
+
+template <int NH, int NG, int OBS, int ORG, bool EXACT, class ACC>
+__device__ __forceinline__ void v3_group(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp, const ACC &acc,
+                                         uint32_t lut_lane_addr, float wscale, float wbias, double origin_tune,
+                                         int seg_y0, int rows, int lane, int dy, int dx0)
+{
+    V3Group<NH, NG, OBS, ORG, ACC> g(cur, cmp, acc, lut_lane_addr, wscale, wbias, origin_tune, seg_y0, lane, dy, dx0);
+    g.template run<EXACT>(rows);
+}
+
+// Group shapes a displacement row can be cut into (three displacements per group, the remainder last), keyed by
+// {displacements, (12 + dx0) & 3, origin slot}.  Every range 3 .. 15 decomposes into these eleven (v3_group_known()).
+#define V3_GROUP_SHAPES(X) \
+    X(3, 0, kOrgNone) X(3, 1, kOrgNone) X(3, 2, kOrgNone) X(3, 3, kOrgNone) \
+    X(3, 3, 1) X(3, 2, 2) X(3, 0, 0) \
+    X(2, 1, kOrgNone) X(2, 0, kOrgNone) X(1, 3, kOrgNone) X(1, 2, kOrgNone)
+
+__host__ __device__ inline bool v3_group_known(int ng, int ob, int org)
+{
+#define X(NG_, OB_, ORG_) if (ng == NG_ && ob == OB_ && org == ORG_) return true;
+    V3_GROUP_SHAPES(X)
+#undef X
+    return false;
+}
+
+template <int NH, int NW, int RS, bool TMEM, int NBUF>
+__global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_constant__ FusedParams fp)
+{
+    constexpr int kThreads = NW * 32;
+    using L = V3Layout<NW, RS, TMEM, NBUF>;
+    int pl = 0;
+    while (pl + 1 < fp.nplanes && (int)blockIdx.x >= fp.first_tile[pl + 1]) pl++;
+    const KernelParams &p = fp.k[pl];
+    const CUtensorMap *maps = fp.maps[pl];
+    const int tile = (int)blockIdx.x - fp.first_tile[pl];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *cur  = smem + L::kOffCur;
+    float *lut    = reinterpret_cast<float *>(smem + L::kOffLut);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);           // [0] current tile, [1 + b] compare buffer b
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (1 + NBUF));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = (tile % fp.tiles_x[pl]) * kTileW, Y0 = (tile / fp.tiles_x[pl]) * L::kTH;
+    const int gx = X0 + kBorder - kHaloX, gy = Y0 + kBorder - kHalo;
+
+    if (tid == 0)
+    {
+        for (int b = 0; b < 1 + NBUF; b++) mbar_init(bar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (TMEM && warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TMEM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (TMEM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0)
+    {
+        mbar_expect_tx(bar, L::kTileBytes);
+        for (int l = 0; l < L::kLoads; l++) tma_load_2d(cur + l * L::kBoxRows * kTilePW, &maps[0], gx, gy + l * L::kBoxRows, bar);
+        // frame 0 is compared with itself: the compare buffers are free, fill them with the following frames now
+        for (int b = 0; b < NBUF && 1 + b < p.nf; b++)
+        {
+            mbar_expect_tx(bar + 1 + b, L::kTileBytes);
+            for (int l = 0; l < L::kLoads; l++)
+                tma_load_2d(smem + L::kOffCmp + b * L::kTileBytes + l * L::kBoxRows * kTilePW, &maps[1 + b], gx, gy + l * L::kBoxRows, bar + 1 + b);
+        }
+    }
+    for (int i = tid; i < kLutEntries * 32; i += kThreads)
+    {
+        const int e = i >> 5;
+        lut[i] = e < HBCU_NLMEANS_EXPSIZE ? p.exptable[e] : 0.f;
+    }
+
+    const int seg_y0 = warp * RS;
+    int rows = p.h - (Y0 + seg_y0);                                     // rows of this warp's strip inside the plane
+    rows = rows < 0 ? 0 : (rows > RS ? RS : rows);
+    V3Acc<TMEM> acc;
+    if constexpr (TMEM)
+    {
+        const uint32_t base = *tmem_base_slot;
+        acc.taddr = base + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * RS * 8);   // lane 32 * (warp % 4) in bits 31..16
+        uint32_t z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int r = 0; r < RS; r++) acc.store(r, z);
+        acc.wait_store();
+    }
+    else
+    {
+        float *acc_ws = reinterpret_cast<float *>(smem + L::kOffWs);
+        float *acc_ps = reinterpret_cast<float *>(smem + L::kOffPs);
+        for (int i = tid; i < L::kTH * kTileW; i += kThreads)
+        {
+            acc_ws[i] = 0.f;
+            acc_ps[i] = 0.f;
+        }
+        acc.ws = acc_ws + seg_y0 * kTileW + lane * 4;
+        acc.ps = acc_ps + seg_y0 * kTileW + lane * 4;
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const float wscale = p.wfact * 0.0078125f;                         // wfact / 128, exact
+    const float wbias  = -8388608.0f * wscale;                         // exact (power-of-two scaling)
+    // shared address of this lane's copy of table entry 0, pre-biased by -(0x47800000 << 7)
+    const uint32_t lut_lane_addr = smem_u32(lut) + (uint32_t)lane * 4u - (0x47800000u << 7);
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur);
+    for (int f = 0; f < p.nf; f++)
+    {
+        const uint32_t *bw = cw;
+        const int buf = (f - 1) % NBUF;
+        if (f > 0)
+        {
+            mbar_wait(bar + 1 + buf, (uint32_t)(((f - 1) / NBUF) & 1));
+            bw = reinterpret_cast<const uint32_t *>(smem + L::kOffCmp + buf * L::kTileBytes);
+        }
+        if (rows > 0)
+        {
+            constexpr bool kExact = RS % (2 * NH + 1) == 0;             // then partial strips run to their end (rows beyond the plane are never stored)
+            const int nrows = kExact ? RS : rows;
+            for (int dy = -p.r_half; dy <= p.r_half; dy++)
+            {
+                for (int dx0 = -p.r_half; dx0 <= p.r_half; dx0 += kGroup)
+                {
+                    const int ng  = min(kGroup, p.r_half - dx0 + 1);
+                    const int org = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : kOrgNone;
+                    const int ob  = (12 + dx0) & 3;
+#define X(NG_, OB_, ORG_)                                                                                                   \
+                    if (ng == NG_ && ob == OB_ && org == ORG_)                                                              \
+                        v3_group<NH, NG_, OB_, ORG_, kExact>(cw, bw, acc, lut_lane_addr, wscale, wbias, p.origin_tune, seg_y0, nrows, lane, dy, dx0); \
+                    else
+                    V3_GROUP_SHAPES(X)
+#undef X
+                    { /* unreachable: the launcher checked v3_group_known() for every group of this range */ }
+                }
+            }
+        }
+        // the buffer just read takes frame f + NBUF (uniform condition: every warp reaches the barrier)
+        if (f > 0 && f + NBUF < p.nf)
+        {
+            __syncthreads();
+            if (tid == 0)
+            {
+                fence_proxy_async();
+                mbar_expect_tx(bar + 1 + buf, L::kTileBytes);
+                for (int l = 0; l < L::kLoads; l++)
+                    tma_load_2d(smem + L::kOffCmp + buf * L::kTileBytes + l * L::kBoxRows * kTilePW, &maps[f + NBUF], gx, gy + l * L::kBoxRows, bar + 1 + buf);
+            }
+        }
+    }
+
+    const int x = lane * 4;
+    uint8_t *dst = reinterpret_cast<uint8_t *>(p.dst);
+    for (int r = 0; r < rows; r++)
+    {
+        const int oy = seg_y0 + r;
+        const int y = Y0 + oy;
+        uint32_t accv[8];
+        acc.load(r, accv);
+        acc.wait_load(accv);
+        const uint32_t cwd = cw[(oy + kHalo) * (kTilePW / 4) + lane + kHaloX / 4];
+        uint8_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            o[i] = finish_pixel<uint8_t>(__uint_as_float(accv[i]), __uint_as_float(accv[4 + i]), (uint8_t)((cwd >> (8 * i)) & 0xffu));
+        uint8_t *drow = dst + (size_t)y * p.dpitch + X0 + x;
+        if (X0 + x + 3 < p.w)
+            *reinterpret_cast<uchar4 *>(drow) = make_uchar4(o[0], o[1], o[2], o[3]);
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (X0 + x + i < p.w) drow[i] = o[i];
+        }
+    }
+    if (TMEM)
+    {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+        {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tmem_base_slot) : "memory");
+        }
+    }
+}

@@ -237,6 +237,9 @@ void hb_shim_set_device_release(void (*release)(void *storage));
 void hb_shim_set_device_retain(void (*retain)(void *storage));
 /* statistics used by the tests (leak check: HB_BUFFER_DEBUG analogue, fifo.c:137-278) */
 long hb_shim_buffers_alive(void);
+/* decoder-style buffers (streaming benchmarks): see hb_runtime.c */
+void        *hb_shim_buffer_set_release(hb_buffer_t *b, hb_shim_free_fn release, hb_shim_free_fn *previous);
+hb_buffer_t *hb_shim_frame_header_dup(const hb_buffer_t *master);
 
 void hb_buffer_list_append(hb_buffer_list_t *list, hb_buffer_t *buf);
 void hb_buffer_list_prepend(hb_buffer_list_t *list, hb_buffer_t *buf);

@@ -1,29 +1,60 @@
 /* hb_bench.c -- streaming benchmark driver over the libhb filter interface.
  *
- * Measures a filter the way libhb runs it (filter_loop, work.c:2527-2600): a
- * stream of host hb_buffer_t frames goes through work(), outputs are consumed
- * in order, EOF flushes.  The same driver times the CUDA objects and -- linked
- * into oracle/_ref/libhbref.so -- the reference's own CPU objects, so both arms
- * of bench.py run the identical host protocol.
+ * Measures a filter, or a chain of filters in libhb's order, the way libhb runs
+ * them (filter_loop, work.c:2527-2600): a stream of host hb_buffer_t frames goes
+ * through work(), outputs are consumed in order, EOF flushes.  The same driver
+ * times the CUDA objects and -- linked into oracle/_ref/libhbref.so -- the
+ * reference's own CPU objects, so both arms of bench.py run the identical host
+ * protocol.
  *
- * Input buffers are created (and filled) before the clock starts: in libhb the
- * decoder writes straight into the hb_buffer_t, so that copy is not part of
- * the filter.  Everything after -- host->device, kernels, device->host into a
- * fresh output hb_buffer_t, buffer release -- is inside the timed region.
+ * Input frames are decoder-style buffers: a bounded ring of frame payloads is
+ * filled once before the clock starts (in libhb the decoder writes straight
+ * into the hb_buffer_t, so that copy is not part of any filter) and every
+ * timed frame is a fresh hb_buffer_t header over the next free payload;
+ * hb_buffer_close() -- wherever in the chain it happens -- hands the payload
+ * back to the ring (hb_shim_buffer_set_release, the way libhb returns wrapped
+ * AVFrame memory to the decoder).  A stream can therefore run for seconds
+ * without one pinned buffer per frame.  Everything after the hand-over --
+ * host->device, kernels, device->host into a fresh output hb_buffer_t, buffer
+ * release -- is inside the timed region.
  */
 #define _GNU_SOURCE
 #include "handbrake/handbrake.h"
 #include "hb_harness.h"
 #include "hb_bench.h"
 
+#include <pthread.h>
 #include <time.h>
+
+#define BENCH_RING_MAX 96
+
+typedef struct
+{
+    hb_buffer_t     *master[BENCH_RING_MAX];   /* owns the payload (header never enters a filter) */
+    void            *base[BENCH_RING_MAX];
+    hb_shim_free_fn  orig_free[BENCH_RING_MAX];
+    int              free_idx[BENCH_RING_MAX]; /* stack of free payloads */
+    int              n, n_free;
+    pthread_mutex_t  lock;
+} bench_ring_t;
 
 struct hb_bench_s
 {
-    hb_filter_object_t *f;
-    int pix_fmt, w, h;
-    int volatile done;
+    int n;
+    hb_filter_object_t **f;
+    int *done;
+    int failed;
+    int pix_fmt, w, h, frame_flags;
+    int volatile done_flag;
+    int64_t next_index;                        /* frames fed so far (timestamps continue across hb_bench_stream calls) */
+    bench_ring_t ring;
+    int64_t ring_misses;
+    hb_bench_stats_t *st;
 };
+
+/* hb_buffer_close() passes only the allocation's base pointer: one bench stream at a time per process owns the ring
+ * (the benchmark processes run one stream at a time; chains share the ring of their stream) */
+static bench_ring_t *g_ring = NULL;
 
 static double now_s(void)
 {
@@ -32,34 +63,85 @@ static double now_s(void)
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
-hb_bench_t *hb_bench_open(hb_filter_object_t *proto, const char *settings, int pix_fmt, int w, int h)
+static void ring_release(void *base)
 {
-    hb_bench_t *b = calloc(1, sizeof(*b));
-    b->f = malloc(sizeof(*b->f));
-    memcpy(b->f, proto, sizeof(*b->f));
-    b->f->settings = settings ? hb_parse_filter_settings(settings) : NULL;
-    b->f->done = &b->done;
-    b->pix_fmt = pix_fmt;
-    b->w = w;
-    b->h = h;
-    hb_filter_init_t init;
-    memset(&init, 0, sizeof(init));
-    init.pix_fmt = pix_fmt;
-    init.geometry.width = w;
-    init.geometry.height = h;
-    init.geometry.par.num = init.geometry.par.den = 1;
-    init.vrate.num = 30000;
-    init.vrate.den = 1001;
-    init.time_base.num = 1;
-    init.time_base.den = 90000;
-    if (b->f->init(b->f, &init) != 0)
+    bench_ring_t *r = g_ring;
+    if (r == NULL) return;
+    pthread_mutex_lock(&r->lock);
+    for (int i = 0; i < r->n; i++)
+        if (r->base[i] == base)
+        {
+            r->free_idx[r->n_free++] = i;
+            break;
+        }
+    pthread_mutex_unlock(&r->lock);
+}
+
+static int ring_fill(hb_bench_t *b, const uint8_t *src, int n_unique, int want)
+{
+    bench_ring_t *r = &b->ring;
+    const size_t fb = hb_harness_frame_bytes(b->pix_fmt, b->w, b->h);
+    /* a whole number of passes over the source frames, so that payload i always holds source frame i % n_unique */
+    if (want > BENCH_RING_MAX) want = BENCH_RING_MAX;
+    want = want / n_unique * n_unique;
+    if (want < n_unique) want = n_unique;
+    while (r->n < want)
     {
-        if (b->f->settings) hb_dict_free(&b->f->settings);
-        free(b->f);
-        free(b);
-        return NULL;
+        const int i = r->n;
+        hb_buffer_t *m = hb_harness_frame_from_packed(b->pix_fmt, b->w, b->h, src + (size_t)(i % n_unique) * fb);
+        if (m == NULL) return -1;
+        r->master[i] = m;
+        r->base[i] = hb_shim_buffer_set_release(m, ring_release, &r->orig_free[i]);
+        r->free_idx[r->n_free++] = i;
+        r->n++;
     }
-    return b;
+    return 0;
+}
+
+static void ring_destroy(hb_bench_t *b)
+{
+    bench_ring_t *r = &b->ring;
+    if (g_ring == r) g_ring = NULL;
+    for (int i = 0; i < r->n; i++)
+    {
+        hb_shim_buffer_set_release(r->master[i], r->orig_free[i], NULL);
+        hb_buffer_close(&r->master[i]);
+    }
+    r->n = r->n_free = 0;
+}
+
+/* next input frame: header over a free payload holding source frame (index % n_unique); when every payload is still
+ * inside the chain (ring smaller than the chain's appetite) a fresh frame is built the slow way and counted */
+static hb_buffer_t *next_input(hb_bench_t *b, const uint8_t *src, int n_unique)
+{
+    bench_ring_t *r = &b->ring;
+    const int want = (int)(b->next_index % n_unique);
+    hb_buffer_t *buf = NULL;
+    pthread_mutex_lock(&r->lock);
+    for (int k = r->n_free - 1; k >= 0; k--)
+        if (r->free_idx[k] % n_unique == want)
+        {
+            const int i = r->free_idx[k];
+            r->free_idx[k] = r->free_idx[--r->n_free];
+            buf = hb_shim_frame_header_dup(r->master[i]);
+            break;
+        }
+    pthread_mutex_unlock(&r->lock);
+    if (buf == NULL)
+    {
+        const size_t fb = hb_harness_frame_bytes(b->pix_fmt, b->w, b->h);
+        buf = hb_harness_frame_from_packed(b->pix_fmt, b->w, b->h, src + (size_t)want * fb);
+        b->ring_misses++;
+    }
+    if (buf == NULL) return NULL;
+    memset(&buf->s, 0, sizeof(buf->s));
+    buf->s.type     = FRAME_BUF;
+    buf->s.start    = b->next_index * 3003;
+    buf->s.stop     = buf->s.start + 3003;
+    buf->s.duration = 3003;
+    buf->s.flags    = (uint16_t)b->frame_flags;
+    b->next_index++;
+    return buf;
 }
 
 static void consume(hb_buffer_t *list, hb_bench_stats_t *st)
@@ -82,73 +164,7 @@ static void consume(hb_buffer_t *list, hb_bench_stats_t *st)
     }
 }
 
-/* feeds n_frames (cycling over n_unique packed source frames) and an EOF; closes the filter */
-int hb_bench_run(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st)
-{
-    memset(st, 0, sizeof(*st));
-    const size_t fb = hb_harness_frame_bytes(b->pix_fmt, b->w, b->h);
-    hb_buffer_t **in = calloc(n_frames, sizeof(*in));
-    for (int i = 0; i < n_frames; i++)
-    {
-        in[i] = hb_harness_frame_from_packed(b->pix_fmt, b->w, b->h, src + (size_t)(i % n_unique) * fb);
-        if (in[i] == NULL)
-        {
-            for (int j = 0; j < i; j++) hb_buffer_close(&in[j]);
-            free(in);
-            return -1;
-        }
-        in[i]->s.start = (int64_t)i * 3003;
-        in[i]->s.stop = in[i]->s.start + 3003;
-        in[i]->s.duration = 3003;
-        in[i]->s.flags = PIC_FLAG_PROGRESSIVE_FRAME;
-    }
-    hb_buffer_t *eof = hb_buffer_eof_init();
-    int rc = 0;
-
-    const double t0 = now_s();
-    for (int i = 0; i <= n_frames && rc == 0; i++)
-    {
-        hb_buffer_t *buf = i < n_frames ? in[i] : eof;
-        hb_buffer_t *out = NULL;
-        if (i < n_frames)
-        {
-            in[i] = NULL;
-            st->bytes_in += fb;
-        }
-        else
-        {
-            eof = NULL;
-        }
-        int status = b->f->work(b->f, &buf, &out);
-        if (buf != NULL) hb_buffer_close(&buf);
-        if (status == HB_FILTER_FAILED) rc = -1;
-        consume(out, st);
-    }
-    st->seconds = now_s() - t0;
-
-    for (int i = 0; i < n_frames; i++) if (in[i]) hb_buffer_close(&in[i]);
-    if (eof) hb_buffer_close(&eof);
-    free(in);
-    b->f->close(b->f);
-    if (b->f->settings) hb_dict_free(&b->f->settings);
-    free(b->f);
-    free(b);
-    return rc;
-}
-
-/* ------------------------------------------------------------------ */
-/* chains: the filters in libhb's order, each fed by the previous one    */
-/* ------------------------------------------------------------------ */
-typedef struct
-{
-    int n;
-    hb_filter_object_t **f;
-    int *done;
-    int failed;
-    hb_bench_stats_t *st;
-} bench_chain_t;
-
-static void chain_feed(bench_chain_t *c, int k, hb_buffer_t *list)
+static void chain_feed(hb_bench_t *c, int k, hb_buffer_t *list)
 {
     if (k >= c->n)
     {
@@ -174,17 +190,28 @@ static void chain_feed(bench_chain_t *c, int k, hb_buffer_t *list)
     }
 }
 
-int hb_bench_run_chain(int n_filters, hb_filter_object_t *const *protos, const char *const *settings,
-                       int pix_fmt, int w, int h, int frame_flags,
-                       const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st)
+static void free_filter(hb_filter_object_t *f)
 {
-    memset(st, 0, sizeof(*st));
-    bench_chain_t c;
-    memset(&c, 0, sizeof(c));
-    c.f = calloc(n_filters, sizeof(*c.f));
-    c.done = calloc(n_filters, sizeof(int));
-    c.st = st;
-    int volatile done_flag = 0;
+    if (f->settings) hb_dict_free(&f->settings);
+    if (f->sub_filter)
+    {
+        if (f->sub_filter->settings) hb_dict_free(&f->sub_filter->settings);
+        free(f->sub_filter);
+    }
+    free(f);
+}
+
+hb_bench_t *hb_bench_open_chain(int n_filters, hb_filter_object_t *const *protos, const char *const *settings,
+                                int pix_fmt, int w, int h, int frame_flags)
+{
+    hb_bench_t *c = calloc(1, sizeof(*c));
+    c->f = calloc(n_filters, sizeof(*c->f));
+    c->done = calloc(n_filters, sizeof(int));
+    c->pix_fmt = pix_fmt;
+    c->w = w;
+    c->h = h;
+    c->frame_flags = frame_flags;
+    pthread_mutex_init(&c->ring.lock, NULL);
     hb_filter_init_t init;
     memset(&init, 0, sizeof(init));
     init.pix_fmt = pix_fmt;
@@ -193,12 +220,14 @@ int hb_bench_run_chain(int n_filters, hb_filter_object_t *const *protos, const c
     init.geometry.par.num = init.geometry.par.den = 1;
     init.vrate.num = 30000;
     init.vrate.den = 1001;
+    init.time_base.num = 1;
+    init.time_base.den = 90000;
     for (int k = 0; k < n_filters; k++)
     {
         hb_filter_object_t *f = malloc(sizeof(*f));
         memcpy(f, protos[k], sizeof(*f));
         f->settings = settings && settings[k] ? hb_parse_filter_settings(settings[k]) : NULL;
-        f->done = &done_flag;
+        f->done = &c->done_flag;
         if (f->sub_filter != NULL)
         {
             hb_filter_object_t *sub = malloc(sizeof(*sub));
@@ -208,49 +237,106 @@ int hb_bench_run_chain(int n_filters, hb_filter_object_t *const *protos, const c
         }
         if (f->init(f, &init) != 0)
         {
-            free(f);
-            free(c.f);
-            free(c.done);
-            return -2;
+            free_filter(f);
+            for (int j = 0; j < c->n; j++)
+            {
+                c->f[j]->close(c->f[j]);
+                free_filter(c->f[j]);
+            }
+            free(c->f);
+            free(c->done);
+            free(c);
+            return NULL;
         }
-        c.f[c.n++] = f;
+        c->f[c->n++] = f;
     }
-    const size_t fb = hb_harness_frame_bytes(pix_fmt, w, h);
-    hb_buffer_t **in = calloc(n_frames, sizeof(*in));
-    for (int i = 0; i < n_frames; i++)
-    {
-        in[i] = hb_harness_frame_from_packed(pix_fmt, w, h, src + (size_t)(i % n_unique) * fb);
-        in[i]->s.start = (int64_t)i * 3003;
-        in[i]->s.stop = in[i]->s.start + 3003;
-        in[i]->s.duration = 3003;
-        in[i]->s.flags = (uint16_t)frame_flags;
-    }
-    hb_buffer_t *eof = hb_buffer_eof_init();
+    return c;
+}
+
+hb_bench_t *hb_bench_open(hb_filter_object_t *proto, const char *settings, int pix_fmt, int w, int h)
+{
+    hb_filter_object_t *protos[1] = { proto };
+    const char *sets[1] = { settings };
+    return hb_bench_open_chain(1, protos, sets, pix_fmt, w, h, PIC_FLAG_PROGRESSIVE_FRAME);
+}
+
+/* feeds n_frames more frames (cycling over n_unique packed source frames; the stream's timestamps continue) and
+ * consumes whatever comes out; `ring` payloads back the inputs (0 = default) */
+int hb_bench_stream(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, int ring, hb_bench_stats_t *st)
+{
+    memset(st, 0, sizeof(*st));
+    if (b == NULL || b->failed) return -1;
+    if (ring_fill(b, src, n_unique, ring > 0 ? ring : 48) != 0) return -1;
+    g_ring = &b->ring;
+    b->st = st;
+    const size_t fb = hb_harness_frame_bytes(b->pix_fmt, b->w, b->h);
+    const int64_t miss0 = b->ring_misses;
     const double t0 = now_s();
-    for (int i = 0; i < n_frames && !c.failed; i++)
+    for (int i = 0; i < n_frames && !b->failed; i++)
     {
-        hb_buffer_t *b = in[i];
-        in[i] = NULL;
+        hb_buffer_t *buf = next_input(b, src, n_unique);
+        if (buf == NULL) { b->failed = 1; break; }
         st->bytes_in += fb;
-        chain_feed(&c, 0, b);
-    }
-    if (!c.failed)
-    {
-        chain_feed(&c, 0, eof);
-        eof = NULL;
+        chain_feed(b, 0, buf);
     }
     st->seconds = now_s() - t0;
-    for (int i = 0; i < n_frames; i++) if (in[i]) hb_buffer_close(&in[i]);
-    if (eof) hb_buffer_close(&eof);
-    free(in);
-    for (int k = 0; k < c.n; k++)
+    st->ring_misses = b->ring_misses - miss0;
+    b->st = NULL;
+    return b->failed ? -1 : 0;
+}
+
+/* EOF through the chain, outputs consumed, filters closed, handle freed */
+int hb_bench_finish(hb_bench_t *b, hb_bench_stats_t *st)
+{
+    hb_bench_stats_t local;
+    if (st == NULL) st = &local;
+    memset(st, 0, sizeof(*st));
+    if (b == NULL) return -1;
+    b->st = st;
+    g_ring = &b->ring;
+    const double t0 = now_s();
+    if (!b->failed) chain_feed(b, 0, hb_buffer_eof_init());
+    st->seconds = now_s() - t0;
+    const int rc = b->failed ? -1 : 0;
+    for (int k = 0; k < b->n; k++)
     {
-        c.f[k]->close(c.f[k]);
-        if (c.f[k]->settings) hb_dict_free(&c.f[k]->settings);
-        if (c.f[k]->sub_filter) { if (c.f[k]->sub_filter->settings) hb_dict_free(&c.f[k]->sub_filter->settings); free(c.f[k]->sub_filter); }
-        free(c.f[k]);
+        b->f[k]->close(b->f[k]);
+        free_filter(b->f[k]);
     }
-    free(c.f);
-    free(c.done);
-    return c.failed ? -1 : 0;
+    ring_destroy(b);
+    pthread_mutex_destroy(&b->ring.lock);
+    free(b->f);
+    free(b->done);
+    free(b);
+    return rc;
+}
+
+static void add_stats(hb_bench_stats_t *a, const hb_bench_stats_t *b)
+{
+    a->seconds += b->seconds;
+    a->frames_out += b->frames_out;
+    a->bytes_in += b->bytes_in;
+    a->bytes_out += b->bytes_out;
+    a->checksum += b->checksum;
+    a->ring_misses += b->ring_misses;
+}
+
+/* one whole stream: n_frames, EOF, close */
+int hb_bench_run(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st)
+{
+    hb_bench_stats_t fin;
+    int rc = hb_bench_stream(b, src, n_unique, n_frames, 0, st);
+    if (hb_bench_finish(b, &fin) != 0) rc = -1;
+    add_stats(st, &fin);
+    return rc;
+}
+
+int hb_bench_run_chain(int n_filters, hb_filter_object_t *const *protos, const char *const *settings,
+                       int pix_fmt, int w, int h, int frame_flags,
+                       const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st)
+{
+    memset(st, 0, sizeof(*st));
+    hb_bench_t *b = hb_bench_open_chain(n_filters, protos, settings, pix_fmt, w, h, frame_flags);
+    if (b == NULL) return -2;
+    return hb_bench_run(b, src, n_unique, n_frames, st);
 }

@@ -253,6 +253,28 @@ hb_buffer_t *hb_buffer_init(int size)
     return b;
 }
 
+/* Decoder-style frame buffers for streaming benchmarks: a header over a payload somebody else keeps (libhb wraps
+ * decoder memory the same way, hbffmpeg.c:182-239 -- closing the hb_buffer_t hands the memory back to its owner
+ * instead of freeing it).  `release` replaces the allocator's free for this payload until reset with NULL. */
+void *hb_shim_buffer_set_release(hb_buffer_t *b, hb_shim_free_fn release, hb_shim_free_fn *previous)
+{
+    if (b == NULL || b->data == NULL) return NULL;
+    alloc_tag_t *tag = (alloc_tag_t *)(b->data - sizeof(alloc_tag_t));
+    if (previous != NULL) *previous = tag->free_fn;
+    tag->free_fn = release;
+    return tag->base;
+}
+
+hb_buffer_t *hb_shim_frame_header_dup(const hb_buffer_t *master)
+{
+    hb_buffer_t *b = calloc(1, sizeof(*b));
+    if (b == NULL) return NULL;
+    *b = *master;
+    b->next = NULL;
+    __atomic_add_fetch(&g_alive, 1, __ATOMIC_SEQ_CST);
+    return b;
+}
+
 hb_buffer_t *hb_buffer_eof_init(void)
 {
     hb_buffer_t *b = hb_buffer_init(0);
