@@ -59,13 +59,19 @@ def build_cuda(force=False, verbose=False):
     obj_dir.mkdir(exist_ok=True)
     csrc = ROOT / "csrc"
     headers = list(csrc.glob("*.h")) + list(csrc.glob("*.cuh")) + [REPO / "include" / "hbcu.h"]
-    objs = []
+    objs, jobs = [], []
     for name in CU_SOURCES:
         src = csrc / name
         obj = obj_dir / (name + ".o")
         if force or _newer(obj, [src] + headers):
-            _run([nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", src, "-o", obj], verbose)
+            jobs.append([nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", src, "-o", obj])
         objs.append(obj)
+    if jobs:
+        # translation units are independent: compile them side by side (nlmeans.cu alone takes minutes)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for f in [pool.submit(_run, j, verbose) for j in jobs]:
+                f.result()
     out = LIB / "libhbcu.so"
     if force or _newer(out, objs):
         _run([nvcc_path(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xlinker", "--exclude-libs=ALL"], verbose)

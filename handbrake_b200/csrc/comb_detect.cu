@@ -532,6 +532,12 @@ int hbcu_comb_detect_create(hbcu_comb_detect_t **out, const hbcu_comb_detect_con
         set_error("comb_detect_create: unsupported geometry %dx%d depth %d", cfg->width, cfg->height, cfg->depth);
         return -1;
     }
+    if ((cfg->mode & 1) != 0 && ((size_t)sizeof(float) << cfg->depth) > 48 * 1024)
+    {
+        // refused here, where the job can still continue without the filter (work.c:1861-1868), not per frame
+        set_error("comb_detect_create: the gamma table of mode %d at depth %d does not fit shared memory (depths up to 13)", cfg->mode, cfg->depth);
+        return -1;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
     {

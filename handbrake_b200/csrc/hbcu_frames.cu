@@ -6,9 +6,10 @@
 // its own stream wait for the frame's `ready` event.  Nothing blocks on the host, the order of work on the GPU is
 // carried by two events per frame:
 //   ready     producer -> readers   (recorded behind the last write)
-//   consumed  readers  -> next life (each reader waits for the previous record before it records its own, so the
-//                                    most recent record stands for all of them; the pool hands a frame out again at
-//                                    once and the next producer's stream waits for `consumed` before writing)
+//   consumed  readers  -> next life (a reader, when done, waits for the previous record and records its own in one
+//                                    locked step, so the most recent record stands for all readers on all host
+//                                    threads; the pool hands a frame out again at once and the next producer's
+//                                    stream waits for `ready` (write after write) and `consumed` before writing)
 // This mirrors how libhb already carries non-host frames (AVFRAME / COREMEDIA storage, handbrake/internal.h:152-153,
 // fifo.c:1016-1034) and its VideoToolbox adapter filters (platform/macosx/adapter_vt.c).
 #include "hbcu_frames.h"
@@ -21,6 +22,7 @@
 namespace {
 
 std::mutex g_frame_lock;
+std::mutex g_reader_lock;       // makes a reader's wait-then-record on `consumed` one step
 hbcu_frame_s *g_frame_free = nullptr;
 long g_frames_alive = 0;          // frames handed out and not yet released (leak check for the tests)
 
@@ -38,6 +40,9 @@ namespace hbcu {
 
 int frame_begin_write(hbcu_frame_s *f, cudaStream_t st)
 {
+    // behind every reader of the previous life AND behind its producer: a frame that was written but never read (its
+    // buffer dropped on an error path) comes back from the pool with the old producer's kernels possibly still queued
+    HBCU_CHECK(cudaStreamWaitEvent(st, f->ready, 0));
     HBCU_CHECK(cudaStreamWaitEvent(st, f->consumed, 0));
     return 0;
 }
@@ -51,12 +56,16 @@ int frame_end_write(hbcu_frame_s *f, cudaStream_t st)
 int frame_begin_read(hbcu_frame_s *f, cudaStream_t st)
 {
     HBCU_CHECK(cudaStreamWaitEvent(st, f->ready, 0));
-    HBCU_CHECK(cudaStreamWaitEvent(st, f->consumed, 0));     // chain behind the previous reader's record
     return 0;
 }
 
 int frame_end_read(hbcu_frame_s *f, cudaStream_t st)
 {
+    // readers chain: wait for the previous reader's record, then record -- atomically, so that two holders of a
+    // shallow-dup'ed frame reading from different host threads cannot both chain behind the same older record
+    // (the next writer waits for the LAST record only, which must imply all the others)
+    std::lock_guard<std::mutex> g(g_reader_lock);
+    HBCU_CHECK(cudaStreamWaitEvent(st, f->consumed, 0));
     HBCU_CHECK(cudaEventRecord(f->consumed, st));
     return 0;
 }

@@ -1500,6 +1500,11 @@ struct hbcu_nlmeans_s
     std::vector<cudaEvent_t> ev_kernel;   // per out slot
     std::vector<cudaEvent_t> ev_d2h;      // per out slot
     std::vector<int64_t>     out_index;
+    // multi-device dealing (hbcu_nlmeans_upload_peer): a frame this handle took from a peer handle's ring / gave to one
+    std::vector<cudaEvent_t> ev_peer_in;  // per ring slot, this device: the peer copy INTO the slot is done
+    std::vector<cudaEvent_t> peer_wait;   // per ring slot: a peer's ev_peer_in still reading this slot (nullptr: none); the next
+                                          // upload into the slot orders itself behind it
+    bool mid_stream;                      // the handle's index 0 is not the stream's first frame (hbcu_nlmeans_set_stream_slice)
     cudaEvent_t ev_mark[2];
     std::vector<cudaEvent_t> ev_pool;     // event pairs around the main kernels (kernel-only timing)
     int pool_used;                        // pairs recorded since mark 0
@@ -1626,6 +1631,14 @@ int launch_v3(FusedParams &fp, cudaStream_t st)
 // 8 warps (its 9-row history does not fit 168 registers).
 struct V3Shape { int nw, rs, tmem; };
 constexpr V3Shape kV3Default = { 12, 21, 1 };
+
+// rows of one TMA box of the v3 tile: V3Layout::kBoxRows restated for a run-time shape (the kernel's expect-tx byte
+// count and the tensor map must agree)
+int v3_box_rows(int nw, int rs)
+{
+    const int rows = nw * rs + 2 * kHalo, loads = rows > 256 ? 2 : 1;
+    return ((rows + loads - 1) / loads + 3) / 4 * 4;
+}
 
 bool v3_shape_ok(int nw, int rs, int tmem, int n_half)
 {
@@ -1862,7 +1875,7 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         kp.use_pre = h->has_pre[pl] ? 1 : 0;
         // nlmeans_plane reads frame[0].image_pre before it prefilters frame 0 (template :612 vs :628): a frame that was
         // never a compare frame of an earlier output contributes its UNFILTERED image as the source patch
-        kp.src_pre = (h->has_pre[pl] && index >= 1 && pp.nframes >= 2) ? kp.pre[0] : kp.planes[0];
+        kp.src_pre = (h->has_pre[pl] && (index >= 1 || h->mid_stream) && pp.nframes >= 2) ? kp.pre[0] : kp.planes[0];
         kp.w = g.w;
         kp.h = g.h;
         kp.bpitch = g.bpitch;
@@ -2103,6 +2116,9 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
     h->ev_upload.assign(h->ring, nullptr);
     h->ev_h2d.assign(h->ring, nullptr);
     h->ev_readers.assign(h->ring * 2, nullptr);
+    h->ev_peer_in.assign(h->ring, nullptr);
+    h->peer_wait.assign(h->ring, nullptr);
+    h->mid_stream = false;
     h->ev_kernel.assign(h->out_slots, nullptr);
     h->ev_d2h.assign(h->out_slots, nullptr);
     h->maps.resize(h->ring * 3);
@@ -2113,6 +2129,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         CK(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_readers[2 * s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_readers[2 * s + 1], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_peer_in[s], cudaEventDisableTiming));
         CK(cudaMalloc(&h->raw_base[s], h->frame_cap));
         for (int pl = 0; pl < 3; pl++)
         {
@@ -2130,7 +2147,7 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
             if (h->v3_nw > 0 &&
                 hbcu::encode_tensor_map_2d(&h->maps3[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,
                                            (uint64_t)h->g[pl].bh, (uint64_t)h->g[pl].bpitch * h->bps, kTilePW,
-                                           h->v3_nw * h->v3_rs + 2 * kHalo) != 0)
+                                           v3_box_rows(h->v3_nw, h->v3_rs)) != 0)
             {
                 hbcu_nlmeans_destroy(h);
                 return -1;
@@ -2209,6 +2226,7 @@ void hbcu_nlmeans_destroy(hbcu_nlmeans_t *h)
     for (auto p : h->out_base) if (p) cudaFree(p);
     for (auto e : h->ev_upload) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_readers) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_peer_in) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_kernel) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_d2h) if (e) cudaEventDestroy(e);
     if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
@@ -2260,6 +2278,11 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
     HBCU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_upload[slot], 0));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[2 * slot], 0));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->ev_readers[2 * slot + 1], 0));
+    if (h->peer_wait[slot] != nullptr)
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_pad, h->peer_wait[slot], 0));     // a peer device still copies the slot's planes
+        h->peer_wait[slot] = nullptr;
+    }
     size_t off[3] = { 0, 0, 0 }, total = 0;
     const bool whole = !from_device && frame_is_contiguous(h, planes, strides, off, &total);
     if (!from_device)
@@ -2358,6 +2381,71 @@ int hbcu_nlmeans_upload(hbcu_nlmeans_t *h, int64_t index, const void *const plan
 int hbcu_nlmeans_upload_device(hbcu_nlmeans_t *h, int64_t index, const void *const dplanes[3], const int strides[3])
 {
     return upload_common(h, index, dplanes, strides, true);
+}
+
+int hbcu_nlmeans_set_stream_slice(hbcu_nlmeans_t *h, int mid_stream)
+{
+    if (h == nullptr) { set_error("nlmeans_set_stream_slice: bad argument"); return -1; }
+    h->mid_stream = mid_stream != 0;
+    return 0;
+}
+
+// Frame `src_index` of `src` (already uploaded there: bordered, prefiltered) becomes frame `dst_index` of `dst`, copied
+// device to device (NVLink peer copy between two GPUs, a plain device copy when both handles share one).  This is the
+// temporal halo of block-cyclic dealing: the first nframes-1 frames of a block are also the look-ahead window of the
+// previous block, which lives on another device -- one H2D per frame, the halo travels GPU to GPU.
+int hbcu_nlmeans_upload_peer(hbcu_nlmeans_t *dst, int64_t dst_index, hbcu_nlmeans_t *src, int64_t src_index)
+{
+    if (dst == nullptr || src == nullptr || dst == src || dst_index < 0 || src_index < 0)
+    {
+        set_error("nlmeans_upload_peer: bad argument");
+        return -1;
+    }
+    if (dst->bps != src->bps || dst->cfg.width != src->cfg.width || dst->cfg.height != src->cfg.height)
+    {
+        set_error("nlmeans_upload_peer: the two handles differ in geometry");
+        return -1;
+    }
+    for (int pl = 0; pl < 3; pl++)
+        if (dst->g[pl].bbytes != src->g[pl].bbytes || dst->has_pre[pl] != src->has_pre[pl])
+        {
+            set_error("nlmeans_upload_peer: the two handles differ in plane %d (layout or prefilter)", pl);
+            return -1;
+        }
+    const int dslot = (int)(dst_index % dst->ring), sslot = (int)(src_index % src->ring);
+    if (src->ring_index[sslot] != src_index)
+    {
+        set_error("nlmeans_upload_peer: frame %lld is not resident on the source handle", (long long)src_index);
+        return -1;
+    }
+    const int ddev = dst->cfg.device, sdev = src->cfg.device;
+    HBCU_CHECK(cudaSetDevice(ddev));
+    if (ddev != sdev)
+    {
+        // direct NVLink path; without peer access the copy is staged by the driver (still correct)
+        const cudaError_t e = cudaDeviceEnablePeerAccess(sdev, 0);
+        if (e != cudaSuccess) cudaGetLastError();       // already enabled, or not supported: cudaMemcpyPeerAsync copes
+    }
+    // the destination slot is free once the kernels reading its previous frame are done (and no peer reads it)
+    HBCU_CHECK(cudaStreamWaitEvent(dst->s_pad, dst->ev_readers[2 * dslot], 0));
+    HBCU_CHECK(cudaStreamWaitEvent(dst->s_pad, dst->ev_readers[2 * dslot + 1], 0));
+    if (dst->peer_wait[dslot] != nullptr)
+    {
+        HBCU_CHECK(cudaStreamWaitEvent(dst->s_pad, dst->peer_wait[dslot], 0));
+        dst->peer_wait[dslot] = nullptr;
+    }
+    HBCU_CHECK(cudaStreamWaitEvent(dst->s_pad, src->ev_upload[sslot], 0));          // source planes complete
+    for (int pl = 0; pl < 3; pl++)
+    {
+        HBCU_CHECK(cudaMemcpyPeerAsync(dst->ring_mem[dslot * 3 + pl], ddev, src->ring_mem[sslot * 3 + pl], sdev, src->g[pl].bbytes, dst->s_pad));
+        if (dst->has_pre[pl])
+            HBCU_CHECK(cudaMemcpyPeerAsync(dst->pre_mem[dslot * 3 + pl], ddev, src->pre_mem[sslot * 3 + pl], sdev, src->g[pl].bbytes, dst->s_pad));
+    }
+    HBCU_CHECK(cudaEventRecord(dst->ev_upload[dslot], dst->s_pad));
+    HBCU_CHECK(cudaEventRecord(dst->ev_peer_in[dslot], dst->s_pad));
+    src->peer_wait[sslot] = dst->ev_peer_in[dslot];
+    dst->ring_index[dslot] = dst_index;
+    return 0;
 }
 
 int hbcu_nlmeans_wait_upload(hbcu_nlmeans_t *h, int64_t index)

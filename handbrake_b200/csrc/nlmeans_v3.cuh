@@ -91,6 +91,41 @@ template <> struct V3Acc<true>
     __device__ __forceinline__ void wait_store() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
 
+// packed fp32 pairs (sm_100 add/mul.f32x2): each half is an IEEE round-to-nearest (or toward-zero) fp32 operation
+__device__ __forceinline__ uint64_t v3_pack2(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void v3_unpack2(uint64_t v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t v3_add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t v3_add2_rz(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// product of two pairs of NON-NEGATIVE floats.  Written as fma(a, b, +0): ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into one FFMA2 even under -fmad=false (seen in the SASS; the reference rounds the product before it adds), and it
+// cannot fold an explicit fma.  a * b + (+0) == rn(a * b) whenever the product is not -0, which weights and pixels never are.
+__device__ __forceinline__ uint64_t v3_mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(0ull));
+    return r;
+}
+// position of pixel i of a lane's four in the accumulator words (pairs (0, 2) and (1, 3))
+__device__ __forceinline__ constexpr int v3_acc_slot(int i) { return (i & 1) * 2 + (i >> 1); }
+
 constexpr int kOrgNone = -1;
 constexpr uint32_t kVBias = 0x4B000000u;     // bits of 2^23
 
@@ -247,29 +282,41 @@ struct V3Group
         {
             constexpr int KP = (K + N - NH) % N;          // the compare row of the output row was loaded NH steps ago
             const uint32_t p0 = P[KP][0], p1 = P[KP][1];
-            float pixv[NG + 3];
+            // pixels 0/2 and 1/3 of the lane's four travel as packed pairs (add/mul.rn.f32x2: two IEEE fp32 operations per
+            // issue slot, same rounding as the scalar instructions); accumulator words are stored in that order:
+            // {ws0, ws2, ws1, ws3, ps0, ps2, ps1, ps3}
+            uint64_t pix2[NG + 1];                        // (compare pixel j, compare pixel j + 2) as floats
 #pragma unroll
-            for (int j = 0; j < NG + 3; j++)
-                pixv[j] = __fsub_rn(byte_as_biased_float(j < 4 ? p0 : p1, j & 3), 8388608.0f);
+            for (int j = 0; j < NG + 1; j++)
+                pix2[j] = v3_add2(v3_pack2(byte_as_biased_float(j < 4 ? p0 : p1, j & 3), byte_as_biased_float(j + 2 < 4 ? p0 : p1, (j + 2) & 3)),
+                                  v3_pack2(-8388608.0f, -8388608.0f));
             acc.wait_load(accv);                          // issued at the top of the step: the patch-row sums covered its latency
-            float wgt[NG][4];
+            uint64_t W[NG][2];                            // weights of pixels (0, 2) and (1, 3)
 #pragma unroll
             for (int g = 0; g < NG; g++)
             {
                 if (ORG != kOrgNone && is_origin(g)) continue;
+                float t[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++)
+                    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t[i]) : "f"(__uint_as_float(V[g][i])), "f"(wscale), "f"(wbias));
+#pragma unroll
+                for (int h = 0; h < 2; h++)
                 {
-                    float t, u;
-                    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(__uint_as_float(V[g][i])), "f"(wscale), "f"(wbias));
-                    asm("add.rz.f32 %0, %1, 0f47800000;" : "=f"(u) : "f"(t));   // 65536 + floor(128 t)
-                    const uint32_t addr = (__float_as_uint(u) << 7) + lut_lane_addr;
-                    asm("ld.shared.f32 %0, [%1];" : "=f"(wgt[g][i]) : "r"(addr));
+                    float u0, u1, w0, w1;
+                    v3_unpack2(v3_add2_rz(v3_pack2(t[h], t[h + 2]), v3_pack2(65536.0f, 65536.0f)), u0, u1);   // 65536 + floor(128 t)
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(w0) : "r"((__float_as_uint(u0) << 7) + lut_lane_addr));
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(w1) : "r"((__float_as_uint(u1) << 7) + lut_lane_addr));
+                    W[g][h] = v3_pack2(w0, w1);
                 }
             }
-            float ws[4], ps[4];
+            uint64_t ws2[2], ps2[2];
 #pragma unroll
-            for (int i = 0; i < 4; i++) { ws[i] = __uint_as_float(accv[i]); ps[i] = __uint_as_float(accv[4 + i]); }
+            for (int h = 0; h < 2; h++)
+            {
+                ws2[h] = v3_pack2(__uint_as_float(accv[2 * h]), __uint_as_float(accv[2 * h + 1]));
+                ps2[h] = v3_pack2(__uint_as_float(accv[4 + 2 * h]), __uint_as_float(accv[4 + 2 * h + 1]));
+            }
 #pragma unroll
             for (int g = 0; g < NG; g++)
             {
@@ -277,20 +324,36 @@ struct V3Group
                 {
                     const uint32_t cw = orow[r * PW];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) add_origin(ws[i], ps[i], origin_tune, (int)((cw >> (8 * i)) & 0xffu));
+                    for (int h = 0; h < 2; h++)
+                    {
+                        float wa, wb, pa, pb;
+                        v3_unpack2(ws2[h], wa, wb);
+                        v3_unpack2(ps2[h], pa, pb);
+                        add_origin(wa, pa, origin_tune, (int)((cw >> (8 * h)) & 0xffu));
+                        add_origin(wb, pb, origin_tune, (int)((cw >> (8 * (h + 2))) & 0xffu));
+                        ws2[h] = v3_pack2(wa, wb);
+                        ps2[h] = v3_pack2(pa, pb);
+                    }
                 }
                 else
                 {
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                    for (int h = 0; h < 2; h++)
                     {
-                        ws[i] = __fadd_rn(ws[i], wgt[g][i]);
-                        ps[i] = __fadd_rn(ps[i], __fmul_rn(wgt[g][i], pixv[g + i]));
+                        ws2[h] = v3_add2(ws2[h], W[g][h]);
+                        ps2[h] = v3_add2(ps2[h], v3_mul2(W[g][h], pix2[g + h]));
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) { accv[i] = __float_as_uint(ws[i]); accv[4 + i] = __float_as_uint(ps[i]); }
+            for (int h = 0; h < 2; h++)
+            {
+                float a, b;
+                v3_unpack2(ws2[h], a, b);
+                accv[2 * h] = __float_as_uint(a); accv[2 * h + 1] = __float_as_uint(b);
+                v3_unpack2(ps2[h], a, b);
+                accv[4 + 2 * h] = __float_as_uint(a); accv[4 + 2 * h + 1] = __float_as_uint(b);
+            }
             acc.store(r, accv);
         }
         P[K][0] = bg0[1];
@@ -500,7 +563,7 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
         uint8_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            o[i] = finish_pixel<uint8_t>(__uint_as_float(accv[i]), __uint_as_float(accv[4 + i]), (uint8_t)((cwd >> (8 * i)) & 0xffu));
+            o[i] = finish_pixel<uint8_t>(__uint_as_float(accv[v3_acc_slot(i)]), __uint_as_float(accv[4 + v3_acc_slot(i)]), (uint8_t)((cwd >> (8 * i)) & 0xffu));
         uint8_t *drow = dst + (size_t)y * p.dpitch + X0 + x;
         if (X0 + x + 3 < p.w)
             *reinterpret_cast<uchar4 *>(drow) = make_uchar4(o[0], o[1], o[2], o[3]);

@@ -300,10 +300,10 @@ static int decide_frame_length(hb_filter_private_t *pv)
 static dt_frame_t *get_frame(hb_filter_private_t *pv)
 {
     dt_frame_t *fr = &pv->frame;
+    if (pv->failed || pv->first == DT_NONE) return NULL;     /* no field was ever queued (a failed first submit) */
     const int n = decide_frame_length(pv);
-    int aff = pv->fld[pv->fld[pv->first].next].affinity;
-
     if (n == 0 || fr->lock) return NULL;
+    int aff = pv->fld[pv->fld[pv->first].next].affinity;
 
     fr->lock++;
     fr->length = n;

@@ -17,6 +17,14 @@
  * order and content do not.  The `threads` setting is accepted and sizes the
  * number of frames kept in flight.  The prefilter modes (nlmeans.c:72-83) run on
  * the GPU too, with the reference's single-worker behaviour.
+ *
+ * Several GPUs (setting `devices=0,1,..` or HBCU_DEVICES): the same one ordered
+ * input stream is dealt block-cyclically -- `block` consecutive frames per device
+ * in turn -- the way mt_frame_filter.c:169-237 deals frames to CPU threads, and
+ * harvested in stream order.  A block's look-ahead window reaches nframes-1
+ * frames into the next block: those frames cross PCIe once (to their owner) and
+ * reach the previous block's device by an NVLink peer copy
+ * (hbcu_nlmeans_upload_peer).  Every device keeps its own contiguous index space.
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
@@ -32,10 +40,14 @@
 #define NLMEANS_EXPSIZE             HBCU_NLMEANS_EXPSIZE
 
 #define NLM_MAX_INFLIGHT 16
+#define NLM_MAX_DEVICES  16
+#define NLM_BLOCK_DEFAULT 8
 
 typedef struct
 {
-    int64_t      index;
+    int64_t      index;   /* position in the stream */
+    int          dev;     /* which of pv->gpu[] owns the frame */
+    int64_t      li;      /* its index in that device's own index space */
     hb_buffer_t *in;      /* input buffer we took ownership of (source of the async upload) */
     hb_buffer_t *out;     /* output buffer, NULL until the frame has been enqueued */
 } nlm_pending_t;
@@ -50,8 +62,13 @@ struct hb_filter_private_s
     int    threads;
     int    max_frames;
 
-    hbcu_nlmeans_t *gpu;
-    int             inflight_max;   /* outputs in flight on the device */
+    int             ndev;                          /* devices the stream is dealt to (1: everything on `device`) */
+    int             devices[NLM_MAX_DEVICES];      /* CUDA ordinals; an ordinal may repeat (two handles on one GPU) */
+    hbcu_nlmeans_t *gpu[NLM_MAX_DEVICES];
+    int64_t         local_next[NLM_MAX_DEVICES];   /* frames handed to each device so far = its next local index */
+    int             dev_inflight[NLM_MAX_DEVICES]; /* outputs enqueued on the device and not yet emitted */
+    int             block;                         /* frames per block of the block-cyclic dealing */
+    int             inflight_max;   /* outputs in flight per device */
     int             ring;
 
     /* frames received but not yet emitted, oldest first: [head, head+count) modulo cap */
@@ -210,6 +227,24 @@ int hb_nlmeans_cuda_build_config(const hb_dict_t *dict, int pix_fmt, int width, 
     return 0;
 }
 
+/* "0,1,2" -> ordinals; returns the count (0: not given / malformed) */
+static int parse_devices(const char *str, int *out, int max)
+{
+    int n = 0;
+    if (str == NULL) return 0;
+    while (*str != '\0' && n < max)
+    {
+        char *end = NULL;
+        const long v = strtol(str, &end, 10);
+        if (end == str || v < 0) return 0;
+        out[n++] = (int)v;
+        str = end;
+        if (*str == ',' || *str == '+') str++;
+        else if (*str != '\0') return 0;
+    }
+    return n;
+}
+
 static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
 {
     hb_filter_private_t *pv = calloc(1, sizeof(*pv));
@@ -229,11 +264,54 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     }
     pv->depth = cfg.depth;
     pv->bps   = pv->depth > 8 ? 2 : 1;
-    /* `threads` CPU workers -> that many output frames in flight on the streams */
+
+    /* the devices the stream is dealt to: setting `devices` (not part of the reference's template: a front end that
+     * validates settings exposes it by appending the key), else HBCU_DEVICES, else the one device */
+    pv->ndev = 0;
+    pv->block = NLM_BLOCK_DEFAULT;
+    if (filter->settings != NULL)
+    {
+        char *devs = NULL;
+        if (hb_dict_extract_string(&devs, filter->settings, "devices"))
+        {
+            pv->ndev = parse_devices(devs, pv->devices, NLM_MAX_DEVICES);
+            free(devs);
+            if (pv->ndev == 0)
+            {
+                hb_error("nlmeans(cuda): bad `devices` setting");
+                goto fail;
+            }
+        }
+        hb_dict_extract_int(&pv->block, filter->settings, "block");
+    }
+    if (pv->ndev == 0) pv->ndev = parse_devices(getenv("HBCU_DEVICES"), pv->devices, NLM_MAX_DEVICES);
+    if (pv->ndev == 0)
+    {
+        pv->ndev = 1;
+        pv->devices[0] = cfg.device;
+    }
+    if (getenv("HBCU_BLOCK") != NULL && pv->block == NLM_BLOCK_DEFAULT) pv->block = atoi(getenv("HBCU_BLOCK"));
+    /* a block's look-ahead window must end inside the NEXT block */
+    if (pv->block < pv->max_frames - 1) pv->block = pv->max_frames - 1;
+    if (pv->block < 1) pv->block = 1;
+
+    pv->device_out = hbcu_init_wants_device_output(init);
+    if (pv->ndev > 1 && pv->device_out)
+    {
+        hb_error("nlmeans(cuda): device-resident output needs a single device (devices=%d given)", pv->ndev);
+        goto fail;
+    }
+
+    /* `threads` CPU workers -> that many output frames in flight on the streams (per device) */
     pv->inflight_max = pv->threads < 1 ? 4 : pv->threads;
+    if (pv->ndev > 1 && pv->inflight_max < pv->block + 2) pv->inflight_max = pv->block + 2;    /* a whole block and the start of the next */
     if (pv->inflight_max > NLM_MAX_INFLIGHT) pv->inflight_max = NLM_MAX_INFLIGHT;
-    pv->ring = pv->max_frames + pv->inflight_max + 1;
-    pv->cap  = pv->ring + 2;
+    /* Local indices of the outputs in flight on one device are consecutive except for the halo frames between two of
+     * its blocks (they produce no output there): the span of `inflight_max` outputs, in local indices */
+    const int halo  = pv->ndev > 1 ? pv->max_frames - 1 : 0;
+    const int span  = pv->inflight_max + halo * ((pv->inflight_max + pv->block - 1) / pv->block + 1);
+    pv->ring = pv->max_frames + span + 1;
+    pv->cap  = pv->ndev * (pv->inflight_max + halo) + pv->max_frames + 2;
     pv->pending = calloc(pv->cap, sizeof(*pv->pending));
     if (pv->pending == NULL)
     {
@@ -241,22 +319,31 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
         goto fail;
     }
 
-    cfg.ring_frames    = pv->ring;
-    cfg.out_slots      = pv->inflight_max;
-    if (hbcu_nlmeans_create(&pv->gpu, &cfg) != 0)
+    cfg.ring_frames = pv->ring;
+    cfg.out_slots   = span;
+    for (int d = 0; d < pv->ndev; d++)
     {
-        /* no CPU fallback: the job continues without the filter (work.c:1861-1868) */
-        hb_error("nlmeans(cuda): %s", hbcu_last_error());
-        goto fail;
+        cfg.device = pv->devices[d];
+        if (hbcu_nlmeans_create(&pv->gpu[d], &cfg) != 0 ||
+            (d > 0 && hbcu_nlmeans_set_stream_slice(pv->gpu[d], 1) != 0))    /* only gpu[0] ever sees the stream's first frame */
+        {
+            /* no CPU fallback: the job continues without the filter (work.c:1861-1868) */
+            hb_error("nlmeans(cuda): %s", hbcu_last_error());
+            goto fail;
+        }
     }
-    hb_log("NLMeans (CUDA) on device %d, %d frames in flight", cfg.device, pv->inflight_max);
+    if (pv->ndev == 1)
+        hb_log("NLMeans (CUDA) on device %d, %d frames in flight", pv->devices[0], pv->inflight_max);
+    else
+        hb_log("NLMeans (CUDA) dealt over %d devices in blocks of %d frames, %d frames in flight each", pv->ndev, pv->block, pv->inflight_max);
 
-    pv->device     = cfg.device;
-    pv->device_out = hbcu_init_wants_device_output(init);
+    pv->device = pv->devices[0];
     pv->output = *init;
     return 0;
 
 fail:
+    for (int d = 0; d < NLM_MAX_DEVICES; d++)
+        if (pv->gpu[d] != NULL) hbcu_nlmeans_destroy(pv->gpu[d]);
     free(pv->pending);
     free(pv);
     filter->private_data = NULL;
@@ -267,7 +354,12 @@ static void nlmeans_cuda_close(hb_filter_object_t *filter)
 {
     hb_filter_private_t *pv = filter->private_data;
     if (pv == NULL) return;
-    if (pv->gpu != NULL) hbcu_nlmeans_destroy(pv->gpu);   /* synchronises the device first */
+    /* every handle first drains its device; peers only read each other's rings from queued copies, so destroy them
+     * after ALL devices are idle */
+    for (int d = 0; d < pv->ndev; d++)
+        if (pv->gpu[d] != NULL) hbcu_nlmeans_sync(pv->gpu[d]);
+    for (int d = 0; d < pv->ndev; d++)
+        if (pv->gpu[d] != NULL) hbcu_nlmeans_destroy(pv->gpu[d]);
     for (int i = 0; i < pv->count; i++)
     {
         nlm_pending_t *p = pending_at(pv, i);
@@ -279,7 +371,13 @@ static void nlmeans_cuda_close(hb_filter_object_t *filter)
     filter->private_data = NULL;
 }
 
-/* hand frame `index` to the GPU: kernels + download into a fresh output buffer */
+/* block-cyclic owner of stream frame t */
+static int owner_of(const hb_filter_private_t *pv, int64_t t)
+{
+    return pv->ndev == 1 ? 0 : (int)((t / pv->block) % pv->ndev);
+}
+
+/* hand frame `index` to its GPU: kernels + download into a fresh output buffer */
 static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
 {
     hb_buffer_t *out = pv->device_out
@@ -300,8 +398,10 @@ static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
         planes[c]  = out->plane[c].data;
         strides[c] = out->plane[c].stride;
     }
-    const int rc = pv->device_out ? hbcu_nlmeans_filter_frame(pv->gpu, p->index, navail, hbcu_buffer_frame(out))
-                                  : hbcu_nlmeans_filter(pv->gpu, p->index, navail, planes, strides);
+    if (navail > pv->max_frames) navail = pv->max_frames;  /* what the device holds behind p->li: the block's rest + its halo */
+    hbcu_nlmeans_t *gpu = pv->gpu[p->dev];
+    const int rc = pv->device_out ? hbcu_nlmeans_filter_frame(gpu, p->li, navail, hbcu_buffer_frame(out))
+                                  : hbcu_nlmeans_filter(gpu, p->li, navail, planes, strides);
     if (rc != 0)
     {
         hb_error("nlmeans(cuda): %s", hbcu_last_error());
@@ -309,10 +409,12 @@ static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
         return -1;
     }
     p->out = out;
+    pv->dev_inflight[p->dev]++;
     return 0;
 }
 
-/* enqueue every frame whose look-ahead window is complete (or, at EOF, whatever is left) */
+/* enqueue, in stream order, every frame whose look-ahead window is complete (or, at EOF, whatever is left).
+ * Returns 1 when it stopped because the next frame's device has `inflight_max` outputs pending, 0 otherwise, -1 on error */
 static int enqueue_ready(hb_filter_private_t *pv, int flushing)
 {
     while (pv->next_enqueue < pv->next_in)
@@ -321,9 +423,8 @@ static int enqueue_ready(hb_filter_private_t *pv, int flushing)
         const int avail = (int)(pv->next_in - t);
         if (!flushing && avail < pv->max_frames) break;
         nlm_pending_t *oldest = pending_at(pv, 0);
-        const int inflight = (int)(t - oldest->index);       /* enqueued but not yet emitted */
-        if (inflight >= pv->inflight_max) break;
         nlm_pending_t *p = pending_at(pv, (int)(t - oldest->index));
+        if (pv->dev_inflight[p->dev] >= pv->inflight_max) return 1;
         if (enqueue_frame(pv, p, avail) != 0) return -1;
         pv->next_enqueue++;
     }
@@ -337,26 +438,28 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int block_on
     {
         nlm_pending_t *p = pending_at(pv, 0);
         if (p->out == NULL) break;                           /* not enqueued yet */
+        hbcu_nlmeans_t *gpu = pv->gpu[p->dev];
         if (hbcu_buffer_frame(p->out) != NULL)
         {
             /* device output: its consumer orders itself behind the kernel through the frame's events.  A host input
              * buffer may be released once its (asynchronous) upload has left it */
-            if (hbcu_buffer_frame(p->in) == NULL && hbcu_nlmeans_wait_upload(pv->gpu, p->index) != 0) goto gpu_error;
+            if (hbcu_buffer_frame(p->in) == NULL && hbcu_nlmeans_wait_upload(gpu, p->li) != 0) goto gpu_error;
         }
         else if (block_all || block_one)
         {
-            if (hbcu_nlmeans_wait(pv->gpu, p->index) != 0) goto gpu_error;
+            if (hbcu_nlmeans_wait(gpu, p->li) != 0) goto gpu_error;
             block_one = 0;
         }
         else
         {
-            int done = hbcu_nlmeans_poll(pv->gpu, p->index);
+            int done = hbcu_nlmeans_poll(gpu, p->li);
             if (done < 0) goto gpu_error;
             if (done == 0) break;
         }
         hb_buffer_list_append(list, p->out);
         p->out = NULL;
         hb_buffer_close(&p->in);
+        pv->dev_inflight[p->dev]--;
         pv->head = (pv->head + 1) % pv->cap;
         pv->count--;
     }
@@ -365,6 +468,18 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int block_on
 gpu_error:
     hb_error("nlmeans(cuda): %s", hbcu_last_error());
     return -1;
+}
+
+/* enqueue what can be enqueued; while a device's queue is full, wait for the oldest frame in flight and go on */
+static int pump(hb_filter_private_t *pv, hb_buffer_list_t *list, int flushing)
+{
+    for (;;)
+    {
+        const int full = enqueue_ready(pv, flushing);
+        if (full < 0) return -1;
+        if (harvest(pv, list, full, 0) != 0) return -1;
+        if (!full) return 0;
+    }
 }
 
 static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, hb_buffer_t **buf_out)
@@ -379,7 +494,7 @@ static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
         /* flush with the shrinking window (nlmeans.c:599-664), then forward EOF */
         while (pv->count > 0)
         {
-            if (enqueue_ready(pv, 1) != 0 || harvest(pv, &list, 1, 0) != 0)
+            if (pump(pv, &list, 1) != 0 || harvest(pv, &list, 1, 0) != 0)
             {
                 hb_buffer_list_close(&list);
                 return HB_FILTER_FAILED;
@@ -391,7 +506,7 @@ static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
         return HB_FILTER_DONE;
     }
 
-    /* nlmeans_add_frame: the frame goes to the device; we keep the buffer until its
+    /* nlmeans_add_frame: the frame goes to its device; we keep the buffer until its
      * output is emitted because the upload reads it asynchronously */
     const void *planes[3];
     int strides[3];
@@ -406,29 +521,44 @@ static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
         return HB_FILTER_FAILED;
     }
     hbcu_frame_t *fin = hbcu_buffer_frame(in);
-    if ((fin != NULL ? hbcu_nlmeans_upload_frame(pv->gpu, pv->next_in, fin)
-                     : hbcu_nlmeans_upload(pv->gpu, pv->next_in, planes, strides)) != 0)
+    if (fin != NULL && pv->ndev > 1)
+    {
+        hb_error("nlmeans(cuda): device-resident input needs a single device (devices=%d given)", pv->ndev);
+        return HB_FILTER_FAILED;
+    }
+    const int64_t t  = pv->next_in;
+    const int     d  = owner_of(pv, t);
+    const int64_t li = pv->local_next[d];
+    if ((fin != NULL ? hbcu_nlmeans_upload_frame(pv->gpu[d], li, fin)
+                     : hbcu_nlmeans_upload(pv->gpu[d], li, planes, strides)) != 0)
     {
         hb_error("nlmeans(cuda): %s", hbcu_last_error());
         return HB_FILTER_FAILED;
     }
+    pv->local_next[d]++;
+    if (pv->ndev > 1 && t >= pv->block && (t % pv->block) < pv->max_frames - 1)
+    {
+        /* one of the first nframes-1 frames of its block: also the look-ahead of the previous block, on another device */
+        const int q = owner_of(pv, t - pv->block);
+        if (hbcu_nlmeans_upload_peer(pv->gpu[q], pv->local_next[q], pv->gpu[d], li) != 0)
+        {
+            hb_error("nlmeans(cuda): %s", hbcu_last_error());
+            return HB_FILTER_FAILED;
+        }
+        pv->local_next[q]++;
+    }
     nlm_pending_t *p = pending_at(pv, pv->count);
-    p->index = pv->next_in;
+    p->index = t;
+    p->dev   = d;
+    p->li    = li;
     p->in    = in;
     p->out   = NULL;
     pv->count++;
     pv->next_in++;
     *buf_in = NULL;
 
-    if (enqueue_ready(pv, 0) != 0) return HB_FILTER_FAILED;
-    /* keep the device queue bounded: once `inflight_max` outputs are pending, wait for the oldest */
-    const int enq_inflight = (int)(pv->next_enqueue - pending_at(pv, 0)->index);
-    if (harvest(pv, &list, enq_inflight >= pv->inflight_max, 0) != 0)
-    {
-        hb_buffer_list_close(&list);
-        return HB_FILTER_FAILED;
-    }
-    if (enqueue_ready(pv, 0) != 0)
+    /* keep the device queues bounded: while a device has `inflight_max` outputs pending, wait for the oldest */
+    if (pump(pv, &list, 0) != 0)
     {
         hb_buffer_list_close(&list);
         return HB_FILTER_FAILED;

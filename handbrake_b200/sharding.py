@@ -4,6 +4,10 @@ The path partitions by FRAMES: a rank owns contiguous blocks of t
 block-cyclically (block b -> rank b % world), and additionally loads the temporal halo its blocks
 need from their neighbours:
     NLMeans          output t reads inputs t .. t+nframes-1      -> halo_after  = nframes-1, halo_before = 0
+                     (with a prefilter and nframes >= 2: halo_before = 1 -- the stream's FIRST frame alone takes the
+                     unfiltered plane as its patch source (templates/nlmeans_template.c, the frame-0 quirk restated in
+                     csrc/nlmeans.cu run_filter); a block that restarted at index 0 would repeat that quirk on its first
+                     owned frame, so it restarts one frame early and drops that frame's output: nlmeans_halo())
     comb-detect      verdict t reads t-1, t, t+1                 -> halo 1 / 1
     decomb (no EEDI2)                                            -> halo 1 / 1
 There is no data-path collective: a halo frame is simply loaded by both ranks.  The only exchange
@@ -34,6 +38,12 @@ def plan_blocks(n_frames: int, world: int, block: int, halo_before: int = 0, hal
         stop = min(start + block, n_frames)
         out.append(Block(b, b % world, start, stop, max(0, start - halo_before), min(n_frames, stop + halo_after)))
     return out
+
+
+def nlmeans_halo(nframes: int, prefilters=(0, 0, 0)):
+    """(halo_before, halo_after) of a sharded NLMeans block for the widest plane window `nframes`."""
+    before = 1 if nframes >= 2 and any(int(p) != 0 for p in prefilters) else 0
+    return before, max(0, nframes - 1)
 
 
 def run_rank(blocks: List[Block], rank: int, clip_loader: Callable[[int, int], np.ndarray],

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HBCU_ABI_VERSION 4
+#define HBCU_ABI_VERSION 5
 
 /* ------------------------------------------------------------------------- */
 /* runtime                                                                    */
@@ -151,6 +151,17 @@ int  hbcu_nlmeans_filter_device(hbcu_nlmeans_t *h, int64_t index, int navail,
  * filter's input, or a buffer an NCCL send reads): the device-resident hand-off between filters */
 int  hbcu_nlmeans_filter_into(hbcu_nlmeans_t *h, int64_t index, int navail,
                               void *const dplanes[3], const int strides[3]);
+/* Multi-device dealing (the frame-parallel taskset of mt_frame_filter.c:169-237 spread over several GPUs): one handle
+ * per device, each with its OWN contiguous index space; the filter deals blocks of frames to the handles in turn.
+ *   upload_peer      : frame `src_index` of `src` (uploaded there already) becomes frame `dst_index` of `dst`, copied
+ *                      device to device (NVLink peer copy): the temporal halo of a block crosses PCIe once, not twice.
+ *                      Both handles must outlive the copy (destroy them together).
+ *   set_stream_slice : mid_stream != 0 -- the handle's frame 0 is NOT the first frame of the stream, so the
+ *                      start-of-stream rule of the prefilter path (templates/nlmeans_template.c:612 vs :628: the very
+ *                      first frame's source patches come from the unfiltered image) does not apply to it. */
+int  hbcu_nlmeans_upload_peer(hbcu_nlmeans_t *dst, int64_t dst_index, hbcu_nlmeans_t *src, int64_t src_index);
+int  hbcu_nlmeans_set_stream_slice(hbcu_nlmeans_t *h, int mid_stream);
+
 /* device-resident chain: frame `index` arrives in / leaves in an hbcu_frame_t.  Stream-ordered against the frame's
  * producer and readers, never blocks; the output needs no wait/poll -- its consumer orders itself behind it. */
 int  hbcu_nlmeans_upload_frame(hbcu_nlmeans_t *h, int64_t index, hbcu_frame_t *in);

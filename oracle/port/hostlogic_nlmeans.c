@@ -23,6 +23,7 @@ struct hbcu_nlmeans_s
     int ring;
     uint8_t *frames;            /* ring of tightly packed frames */
     int64_t *index;             /* which frame a ring slot holds */
+    int mid_stream;             /* hbcu_nlmeans_set_stream_slice: index 0 is not the stream's first frame */
 };
 
 void oracle_hostlogic_set_error(const char *fmt, ...);
@@ -64,6 +65,23 @@ int oracle_hbcu_nlmeans_upload(hbcu_nlmeans_t *h, int64_t index, const void *con
     return 0;
 }
 
+/* multi-device dealing: the halo frame is taken from the peer handle's ring (the peer copy of the product) */
+int oracle_hbcu_nlmeans_upload_peer(hbcu_nlmeans_t *dst, int64_t dst_index, hbcu_nlmeans_t *src, int64_t src_index)
+{
+    const int sslot = (int)(src_index % src->ring), dslot = (int)(dst_index % dst->ring);
+    if (dst == src || dst->frame_bytes != src->frame_bytes || src->index[sslot] != src_index)
+    {
+        oracle_hostlogic_set_error("upload_peer: frame %lld is not in the source ring", (long long)src_index);
+        return -1;
+    }
+    memcpy(dst->frames + (size_t)dslot * dst->frame_bytes, src->frames + (size_t)sslot * src->frame_bytes, src->frame_bytes);
+    dst->index[dslot] = dst_index;
+    return 0;
+}
+
+int oracle_hbcu_nlmeans_set_stream_slice(hbcu_nlmeans_t *h, int mid_stream) { h->mid_stream = mid_stream != 0; return 0; }
+int oracle_hbcu_nlmeans_sync(hbcu_nlmeans_t *h) { (void)h; return 0; }
+
 int oracle_hbcu_nlmeans_wait_upload(hbcu_nlmeans_t *h, int64_t index) { (void)h; (void)index; return 0; }
 
 int oracle_hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, void *const planes[3], const int strides[3])
@@ -87,7 +105,7 @@ int oracle_hbcu_nlmeans_filter(hbcu_nlmeans_t *h, int64_t index, int navail, voi
         /* the reference's stale source-patch pointer (see nlmeans_port.c): frame 0 of the stream, or no temporal window */
         oracle_nlmeans_plane_with_table(frames, nf, h->w[c], h->h[c], h->cfg.depth, pp->patch_size, pp->range, pp->origin_tune,
                                         pp->bypass, pp->prefilter, pp->weight_fact, pp->diff_max, pp->exptable,
-                                        index == 0 || pp->nframes < 2, tight);
+                                        (index == 0 && !h->mid_stream) || pp->nframes < 2, tight);
         for (int y = 0; y < h->h[c]; y++)
             memcpy((uint8_t *)planes[c] + (size_t)y * strides[c], tight + (size_t)y * h->w[c] * h->bps, (size_t)h->w[c] * h->bps);
         free(tight);

@@ -75,6 +75,49 @@ def test_nlmeans_host_filter_clip_lengths(ref, hostlogic, n):
     same_stream(r, g)
 
 
+MULTI_CASES = [
+    # (extra settings, frames): `devices` lists the handles the ordered stream is dealt to, `block` the frames per turn
+    ("y-strength=6:y-patch-size=3:y-frame-count=2:devices=0,0:block=3", 11),
+    ("y-strength=6:y-patch-size=3:y-frame-count=3:devices=0,0,0:block=2", 13),        # halo of 2 = the whole next block
+    ("y-strength=6:y-patch-size=3:y-frame-count=4:devices=0,0:block=1", 9),           # block raised to nframes - 1
+    ("y-strength=6:y-patch-size=3:y-frame-count=2:devices=0,0,0,0:block=2", 5),       # fewer blocks than devices' turns
+    ("y-strength=6:y-patch-size=3:y-frame-count=3:devices=0,0:block=4", 2),           # shorter than the window: EOF flush only
+    ("y-strength=6:y-patch-size=3:y-frame-count=2:y-prefilter=1:devices=0,0:block=2:threads=1", 8),   # start-of-stream rule on frame 0 only
+    ("y-strength=6:y-patch-size=3:y-frame-count=3:y-prefilter=1032:cb-prefilter=272:devices=0,0,0:block=3:threads=1", 10),
+    ("y-strength=6:y-patch-size=3:y-frame-count=1:devices=0,0:block=2", 7),           # no temporal window: no halo at all
+    ("y-strength=0:cb-strength=5:cb-patch-size=3:devices=0,0:block=2", 6),            # bypassed planes
+]
+
+
+@pytest.mark.parametrize("settings,n", MULTI_CASES)
+def test_nlmeans_multi_device_dealing_equals_reference(ref, hostlogic, settings, n):
+    """one ordered stream dealt block-cyclically to several device handles (mt_frame_filter.c:169-237
+    deals frames to threads the same way), halo by peer copy, harvested in order == the reference's single stream.  The
+    stand-in handles are CPU rings, so this pins the host side: owners, local indices, halo frames, window at block ends,
+    the EOF flush, the start-of-stream rule staying with frame 0."""
+    w, h = 40, 32
+    clip = synth.progressive_clip(FMT[8], w, h, n, seed=90 + n)
+    ref_settings = ":".join(kv for kv in settings.split(":") if not kv.startswith(("devices=", "block=")))
+    r = ref.run("hb_filter_nlmeans", ref_settings, clip, FMT[8], w, h)
+    g = hostlogic.run("hb_filter_nlmeans_cuda", settings, clip, FMT[8], w, h)
+    same_stream(r, g)
+    assert hostlogic.buffers_alive() == 0
+
+
+def test_nlmeans_multi_device_env_and_bad_lists(hostlogic, monkeypatch):
+    w, h = 40, 32
+    clip = synth.progressive_clip(FMT[8], w, h, 7, seed=5)
+    s = "y-strength=6:y-patch-size=3"
+    one = hostlogic.run("hb_filter_nlmeans_cuda", s, clip, FMT[8], w, h)
+    monkeypatch.setenv("HBCU_DEVICES", "0,0,0")
+    monkeypatch.setenv("HBCU_BLOCK", "2")
+    three = hostlogic.run("hb_filter_nlmeans_cuda", s, clip, FMT[8], w, h)
+    assert np.array_equal(one.frames, three.frames) and np.array_equal(one.start, three.start)
+    monkeypatch.delenv("HBCU_DEVICES")
+    bad = hostlogic.run("hb_filter_nlmeans_cuda", s + ":devices=0,x", clip, FMT[8], w, h)
+    assert bad.init_failed
+
+
 def test_nlmeans_host_filter_reproduces_golden_digests(hostlogic):
     golden = json.loads((Path(__file__).parent / "golden" / "nlmeans_golden.json").read_text())
     for name in ("tiny_light_96x64", "tiny_tuned_10bit_64x48"):

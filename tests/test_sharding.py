@@ -38,6 +38,25 @@ def test_sharded_nlmeans_equals_unsharded_single_process():
     assert np.array_equal(got, whole)
 
 
+@pytest.mark.parametrize("prefilter", [1, 2, 1024 + 1])
+def test_sharded_nlmeans_with_prefilter_needs_a_leading_halo(prefilter):
+    """The stream's first frame alone takes the unfiltered plane as patch source: a block that restarts the filter must
+    restart one frame early (nlmeans_halo) or its first owned frame repeats that start-of-stream rule."""
+    port = OraclePort()
+    w, h, n, nf = 48, 32, 9, 2
+    clip = synth.progressive_clip(synth.PIX_FMT_YUV420P, w, h, n, seed=11)
+    params = [dict(strength=8, nframes=nf, prefilter=prefilter)] * 3
+    run = lambda fr: port.nlmeans_clip(fr, w, h, 8, params)
+    whole = run(clip)
+    before, after = sharding.nlmeans_halo(nf, [prefilter] * 3)
+    assert (before, after) == (1, nf - 1)
+    good = _sharded(sharding.plan_blocks(n, 2, 2, halo_before=before, halo_after=after), 2, lambda a, b: clip[a:b], run)
+    assert np.array_equal(good, whole)
+    naive = _sharded(sharding.plan_blocks(n, 2, 2, halo_before=0, halo_after=after), 2, lambda a, b: clip[a:b], run)
+    assert not np.array_equal(naive, whole), "the leading halo is what makes the difference"
+    assert sharding.nlmeans_halo(nf, [0, 0, 0]) == (0, nf - 1) and sharding.nlmeans_halo(1, [1, 1, 1]) == (0, 0)
+
+
 def _sharded(blocks, world, clip_of, run, k=1):
     parts = {}
     for rank in range(world):

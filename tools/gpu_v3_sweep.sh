@@ -5,7 +5,6 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out/v3sweep
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
-for V in "${@:-off 12,12,0 12,21,1 12,18,1 8,28,1}"; do :; done
 SHAPES=${SHAPES:-"off 12,12,0 12,21,1 12,18,1 8,28,1"}
 for V in $SHAPES; do
   tag=$(echo $V | tr ',' '_')
@@ -22,9 +21,11 @@ except Exception as e: print('ERR',e)
 PY
 )" | tee -a $OUT/summary.txt
 done
-for V in ${NCU_SHAPES:-"12,21,1 12,12,0"}; do
+NCU_SHAPES=${NCU_SHAPES:-"12,21,1 12,12,0"}
+for V in $NCU_SHAPES; do
   tag=$(echo $V | tr ',' '_')
   HBCU_NLMEANS_V3=$V timeout 600 ncu --set full --clock-control none --import-source on -k regex:nlmeans_v3 -s 4 -c 1 -o $OUT/ncu_$tag -f python bench.py --steps 1 --warmup 3 --batch 2 --no-cpu-baseline --no-extra --no-copy-only > $OUT/ncu_$tag.log 2>&1
   echo "ncu $V rc=$?" | tee -a $OUT/summary.txt
 done
+if [ -x handbrake_b200/lib/tools/microbench ]; then handbrake_b200/lib/tools/microbench > $OUT/microbench.txt 2>&1; fi
 cat $OUT/summary.txt

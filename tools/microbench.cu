@@ -51,6 +51,49 @@ DEF_OP32(25, "fma.rn.f32 %0, %0, %1, %2; lop3.b32 %0, %0, %1, %2, 0x96;")  // FF
 DEF_OP32(26, "fma.rn.f32 %0, %0, %1, %2; mad.lo.u32 %0, %0, %1, %2;")      // FFMA + IMAD
 DEF_OP32(27, "add.rn.f32 %0, %0, %1; prmt.b32 %0, %0, %1, 0x4321;")        // FADD + PRMT
 
+
+// independent mixes: the first half of the chains runs op A, the second half op B (no dependency between them) --
+// which pairs overlap says which pipe each instruction sits on and whether a packed f32x2 costs one issue slot or two
+#define DEF_MIX32(ID, ASMA, ASMB)                                                             \
+    template <> __device__ __forceinline__ void body<ID>(uint32_t (&r)[NCH], uint32_t k0,     \
+        uint32_t k1, uint64_t (&q)[NCH], float *sm, int lane) {                               \
+        _Pragma("unroll") for (int i = 0; i < NCH / 2; i++) {                                 \
+            asm volatile(ASMA : "+r"(r[i]) : "r"(k0), "r"(k1));                               \
+            asm volatile(ASMB : "+r"(r[i + NCH / 2]) : "r"(k0), "r"(k1)); } }
+#define DEF_MIX64(ID, ASMA, ASMB)                                                             \
+    template <> __device__ __forceinline__ void body<ID>(uint32_t (&r)[NCH], uint32_t k0,     \
+        uint32_t k1, uint64_t (&q)[NCH], float *sm, int lane) {                               \
+        uint64_t kk = ((uint64_t)k1 << 32) | k0;                                              \
+        _Pragma("unroll") for (int i = 0; i < NCH; i++) {                                     \
+            asm volatile(ASMA : "+l"(q[i]) : "l"(kk));                                        \
+            asm volatile(ASMB : "+r"(r[i]) : "r"(k0), "r"(k1)); } }
+#define A_FFMA  "fma.rn.f32 %0, %0, %1, %2;"
+#define A_LOP3  "lop3.b32 %0, %0, %1, %2, 0x96;"
+#define A_DP4A  "dp4a.u32.u32 %0, %0, %1, %2;"
+#define A_VABS  "vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;"
+#define A_IADD3 "{ .reg .b32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }"
+#define A_PRMT  "prmt.b32 %0, %0, %1, 0x4321;"
+#define A_IMAD  "mad.lo.u32 %0, %0, %1, %2;"
+#define A_SHF   "shf.l.wrap.b32 %0, %0, %1, %2;"
+DEF_MIX64(40, "fma.rn.f32x2 %0, %0, %1, %1;", A_LOP3)
+DEF_MIX64(41, "fma.rn.f32x2 %0, %0, %1, %1;", A_FFMA)
+DEF_MIX64(42, "add.rn.f32x2 %0, %0, %1;", A_DP4A)
+DEF_MIX64(43, "add.rn.f32x2 %0, %0, %1;", A_PRMT)
+DEF_MIX32(44, A_DP4A, A_LOP3)
+DEF_MIX32(45, A_DP4A, A_FFMA)
+DEF_MIX32(46, A_VABS, A_DP4A)
+DEF_MIX32(47, A_VABS, A_LOP3)
+DEF_MIX32(48, A_VABS, A_FFMA)
+DEF_MIX32(49, A_IADD3, A_FFMA)
+DEF_MIX32(50, A_IADD3, A_LOP3)
+DEF_MIX32(51, A_IADD3, A_DP4A)
+DEF_MIX32(52, A_PRMT, A_LOP3)
+DEF_MIX32(53, A_IMAD, A_DP4A)
+DEF_MIX32(54, A_SHF, A_LOP3)
+DEF_MIX32(55, A_SHF, A_FFMA)
+DEF_MIX32(56, A_FFMA, A_LOP3)
+DEF_MIX32(57, A_IADD3, A_IADD3)
+
 // shared-memory ops: address chain-free (address from lane), value accumulates
 template <> __device__ __forceinline__ void body<30>(uint32_t (&r)[NCH], uint32_t k0, uint32_t k1, uint64_t (&q)[NCH], float *sm, int lane) {
     #pragma unroll
@@ -141,6 +184,11 @@ int main()
     run<24>("mix FADD+IADD", 2); run<25>("mix FFMA+LOP3", 2); run<26>("mix FFMA+IMAD", 2); run<27>("mix FADD+PRMT", 2);
     run<30>("LDS.32 (+LOP)", 1); run<31>("LDS.128 (+3LOP)", 1); run<32>("LDS.32 LUT replicated", 1);
     run<33>("LDS.32 LUT 128-entry", 1); run<34>("LDS.64+STS.64 RMW", 2);
+    run<40>("ind FFMA2 | LOP3", 2); run<41>("ind FFMA2 | FFMA", 2); run<42>("ind FADD2 | IDP4A", 2); run<43>("ind FADD2 | PRMT", 2);
+    run<44>("ind IDP4A | LOP3", 1); run<45>("ind IDP4A | FFMA", 1); run<46>("ind VABSDIFF4 | IDP4A", 1); run<47>("ind VABSDIFF4 | LOP3", 1);
+    run<48>("ind VABSDIFF4 | FFMA", 1); run<49>("ind IADD3 | FFMA", 1); run<50>("ind IADD3 | LOP3", 1); run<51>("ind IADD3 | IDP4A", 1);
+    run<52>("ind PRMT | LOP3", 1); run<53>("ind IMAD | IDP4A", 1); run<54>("ind SHF | LOP3", 1); run<55>("ind SHF | FFMA", 1);
+    run<56>("ind FFMA | LOP3", 1); run<57>("ind IADD3 | IADD3", 1);
     // occupancy sensitivity of the FP pipe
     run<0>("FADD", 1, 512); run<0>("FADD", 1, 256); run<2>("FFMA", 1, 256); run<5>("FFMA2", 1, 256);
     return 0;
