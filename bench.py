@@ -711,6 +711,25 @@ def run_ours(args, wl, rank, world, local_rank):
     if world > 1 and not args.no_gather:
         gather = gather_arm(ours, dist, wl, host, rank, world, min(B, 64), max(2, min(K, 6)), barrier, max_over_ranks)
 
+    # ---------------- the plugin's own multi-device path: ONE process, ONE ordered stream dealt to all N GPUs in C ----------------
+    # (what a libhb job -- one process, one thread per filter, work.c:2255-2270 -- does with `devices=`; the ranks above
+    # each filter a private stream.)  Rank 0 drives every GPU of the job while the other ranks wait at the barrier.
+    plugin_multi = None
+    if world > 1 and not args.no_plugin_multi:
+        barrier()
+        if rank == 0:
+            devs = [pick_gpu(r_, world) for r_ in range(world)]
+            nfr = world * max(B // 2, int(K * B * 0.25))
+            ms_settings = wl["settings"] + f":threads={args.inflight}:devices={','.join(map(str, devs))}:block={args.block}"
+            rm = ours.stream_arm(["hb_filter_nlmeans_cuda"], [ms_settings], fmt, W, H, synth.PIC_FLAG_PROGRESSIVE_FRAME, host,
+                                 min(Wm * B, 64 * world), nfr, ring=min(256, 48 + 16 * world))
+            plugin_multi = {"value": round(nfr / rm["seconds"], 2), "unit": "frames/s", "seconds": round(rm["seconds"], 3), "frames": nfr,
+                            "devices": devs, "block": args.block, "ring_misses": rm["ring_misses"], "checksum": rm["checksum"],
+                            "what": "one process, one ordered stream of host hb_buffer_t frames through hb_filter_nlmeans_cuda.work() with "
+                                    "devices=<all GPUs>: block-cyclic dealing in C (nlmeans_cuda.c), look-ahead halo by NVLink peer copy "
+                                    "(hbcu_nlmeans_upload_peer), outputs harvested in stream order; H2D + kernels + D2H inside the clock"}
+        barrier()
+
     out = {
         "metric": "4K NLMeans frames/sec" if W == 3840 else "NLMeans frames/sec",
         "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -732,6 +751,8 @@ def run_ours(args, wl, rank, world, local_rank):
         out["copy_only"] = copy_only
     if gather is not None:
         out["gather"] = gather
+    if plugin_multi is not None:
+        out["plugin_multi_device"] = plugin_multi
     if world == 1 and not args.no_cpu_baseline:
         _, out["cpu_baseline"] = cpu_baseline_nlmeans(wl, budget_s=12.0)
     if world == 1 and not args.no_extra:
@@ -790,6 +811,8 @@ def main():
     ap.add_argument("--only-extra", default="", help="substring of the one extra entry to run")
     ap.add_argument("--no-copy-only", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-plugin-multi", action="store_true")
+    ap.add_argument("--block", type=int, default=8, help="frames per device turn of the plugin's multi-device dealing")
     ap.add_argument("--inflight", type=int, default=6, help="frames in flight in the e2e arm (the filter's `threads` setting)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

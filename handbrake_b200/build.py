@@ -1,8 +1,11 @@
 """Builds the native pieces in-tree (no JIT cache: the .so files travel with the repo).
 
   lib/libhbcu.so          CUDA kernels + C-ABI (include/hbcu.h), nvcc, sm_100a only
-  lib/libhbcu_filters.so  libhb-style filter objects in C (gcc) + shim runtime + harness,
-                          linked against libhbcu.so
+  lib/libhbcu_filters.so  the product's host side: the hb_filter_*_cuda objects in C (gcc) and their libhb-facing
+                          helpers, linked against libhbcu.so; everything libhb itself provides (hb_buffer_*, hb_dict_*,
+                          hb_log ...) is an undefined symbol of this library
+  lib/libhbshim.so        TEST SCAFFOLDING: the stand-in for libhb those symbols resolve to outside a HandBrake build
+                          (hb_runtime.c) plus the test harness and the bench driver; never part of an integration
 
 `python -m handbrake_b200.build` or `build_all()`.
 """
@@ -24,7 +27,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
 ]
 CU_SOURCES = ["hbcu_core.cu", "hbcu_frames.cu", "nlmeans.cu", "comb_detect.cu", "decomb.cu", "eedi2.cu", "lapsharp.cu", "unsharp.cu", "hqdn3d.cu", "detelecine.cu"]
-C_SOURCES = ["hb_runtime.c", "hb_harness.c", "hb_bench.c", "hbcu_registry.c", "hbcu_pinned.c", "hbcu_device_frames.c", "nlmeans_cuda.c", "comb_detect_cuda.c", "decomb_cuda.c", "lapsharp_cuda.c", "unsharp_cuda.c", "denoise_cuda.c", "detelecine_cuda.c"]
+SHIM_SOURCES = ["hb_runtime.c", "hb_harness.c", "hb_bench.c"]
+C_SOURCES = ["hbcu_registry.c", "hbcu_pinned.c", "hbcu_device_frames.c", "nlmeans_cuda.c", "comb_detect_cuda.c", "decomb_cuda.c", "lapsharp_cuda.c", "unsharp_cuda.c", "denoise_cuda.c", "detelecine_cuda.c"]
 CFLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wno-unused-function", "-D__LIBHB__", "-pthread"]
 
 
@@ -78,15 +82,27 @@ def build_cuda(force=False, verbose=False):
     return out
 
 
-def build_filters(force=False, verbose=False):
+def build_shim(force=False, verbose=False):
     LIB.mkdir(exist_ok=True)
+    libhb = ROOT / "libhb"
+    srcs = [libhb / s for s in SHIM_SOURCES]
+    headers = list(libhb.glob("**/*.h"))
+    out = LIB / "libhbshim.so"
+    if force or _newer(out, srcs + headers):
+        _run(["gcc"] + CFLAGS + ["-shared", "-o", out] + srcs + ["-I", libhb, "-I", REPO / "include", "-lm", "-lpthread"], verbose)
+    return out
+
+
+def build_filters(force=False, verbose=False):
+    shim = build_shim(force, verbose)
     libhb = ROOT / "libhb"
     srcs = [libhb / s for s in C_SOURCES]
     headers = list(libhb.glob("**/*.h")) + [REPO / "include" / "hbcu.h"]
     out = LIB / "libhbcu_filters.so"
-    if force or _newer(out, srcs + headers + [LIB / "libhbcu.so"]):
+    if force or _newer(out, srcs + headers + [LIB / "libhbcu.so", shim]):
+        # -lhbshim stands where a HandBrake build has libhb itself: the filter objects carry no runtime of their own
         _run(["gcc"] + CFLAGS + ["-shared", "-o", out] + srcs +
-             ["-I", libhb, "-I", REPO / "include", "-L", LIB, "-lhbcu", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"], verbose)
+             ["-I", libhb, "-I", REPO / "include", "-L", LIB, "-lhbcu", "-lhbshim", "-Wl,-rpath,$ORIGIN", "-Wl,-z,defs", "-lm", "-lpthread"], verbose)
     return out
 
 

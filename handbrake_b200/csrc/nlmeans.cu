@@ -1630,7 +1630,7 @@ int launch_v3(FusedParams &fp, cudaStream_t st)
 // v3 shapes built into the library: {warps, rows per warp, accumulators in tensor memory}.  Patch 9 (NH = 4) needs
 // 8 warps (its 9-row history does not fit 168 registers).
 struct V3Shape { int nw, rs, tmem; };
-constexpr V3Shape kV3Default = { 12, 21, 1 };
+constexpr V3Shape kV3Default = { 12, 18, 1 };      // measured on B200 (profiles/r02b_v3_shape_sweep.txt): 12x18 > 12x21 > 8x28 > 12x12 (shared-memory accumulators)
 
 // rows of one TMA box of the v3 tile: V3Layout::kBoxRows restated for a run-time shape (the kernel's expect-tx byte
 // count and the tensor map must agree)
@@ -1644,9 +1644,25 @@ bool v3_shape_ok(int nw, int rs, int tmem, int n_half)
 {
     if (n_half == 4) return nw == 8 && rs == 27 && tmem == 1;
     if (nw == 12 && rs == 12 && tmem == 0) return true;
-    if (nw == 12 && rs == 21 && tmem == 1) return true;
-    if (n_half == 3) return tmem == 1 && ((nw == 12 && rs == 18) || (nw == 8 && rs == 28));
+    if (nw == 12 && rs == 18 && tmem == 1) return true;
+    if (n_half == 3) return tmem == 1 && ((nw == 12 && rs == 21) || (nw == 8 && rs == 28));
     return false;
+}
+
+// the shape a plane with patch half-width n_half runs in, given the handle's shape (whose TMA box its tensor maps
+// were encoded for): patch 9 takes the 8-warp shape with the same tile height as 12 x 18
+bool v3_pick(const hbcu_nlmeans_s *h, int n_half, V3Shape *out)
+{
+    if (h->v3_nw <= 0) return false;
+    V3Shape s = { h->v3_nw, h->v3_rs, h->v3_tmem };
+    if (n_half == 4)
+    {
+        s = V3Shape{ 8, 27, 1 };
+        if (v3_box_rows(s.nw, s.rs) != v3_box_rows(h->v3_nw, h->v3_rs) || s.nw * s.rs != h->v3_nw * h->v3_rs) return false;
+    }
+    if (!v3_shape_ok(s.nw, s.rs, s.tmem, n_half)) return false;
+    *out = s;
+    return true;
 }
 
 int launch_v3_nh(int nw, int rs, int tmem, FusedParams &fp, cudaStream_t st)
@@ -1662,8 +1678,8 @@ int launch_v3_nh(int nw, int rs, int tmem, FusedParams &fp, cudaStream_t st)
         }
 #define V3CASE(NH_, NW_, RS_, TM_, NB_) if (nh == NH_ && nw == NW_ && rs == RS_ && tmem == TM_) return launch_v3<NH_, NW_, RS_, TM_ != 0, NB_>(fp, st)
     V3CASE(1, 12, 12, 0, 1); V3CASE(2, 12, 12, 0, 1); V3CASE(3, 12, 12, 0, 1);
-    V3CASE(1, 12, 21, 1, 2); V3CASE(2, 12, 21, 1, 2); V3CASE(3, 12, 21, 1, 2);
-    V3CASE(3, 12, 18, 1, 2); V3CASE(3, 8, 28, 1, 2);
+    V3CASE(1, 12, 18, 1, 2); V3CASE(2, 12, 18, 1, 2); V3CASE(3, 12, 18, 1, 2);
+    V3CASE(3, 12, 21, 1, 2); V3CASE(3, 8, 28, 1, 2);
     V3CASE(4, 8, 27, 1, 2);
 #undef V3CASE
     return 1;
@@ -1746,9 +1762,10 @@ int launch_plane(hbcu_nlmeans_s *h, const KernelParams &kp, const int *slots, in
             fp.nplanes = 1;
             fp.range_flag = nullptr;
             fp.k[0] = kp;
-            const bool v3 = h->v3_nw > 0 && v3_shape_ok(h->v3_nw, h->v3_rs, h->v3_tmem, kp.n_half);
+            V3Shape vs;
+            const bool v3 = v3_pick(h, kp.n_half, &vs);
             for (int f = 0; f < kp.nf; f++) fp.maps[0][f] = v3 ? h->maps3[slots[f] * 3 + plane] : tp.maps[f];
-            rc = v3 ? launch_v3_nh(h->v3_nw, h->v3_rs, h->v3_tmem, fp, h->s_compute) : launch_fast8_nh(fp, h->s_compute);
+            rc = v3 ? launch_v3_nh(vs.nw, vs.rs, vs.tmem, fp, h->s_compute) : launch_fast8_nh(fp, h->s_compute);
         }
         else
             rc = h->bps == 1 ? launch_tiled_nh<uint8_t, kTH8>(tp, h->s_compute) : launch_tiled_nh<uint16_t, kTH16>(tp, h->s_compute);
@@ -1938,7 +1955,8 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         FusedParams fp;
         fp.nplanes = 0;
         fp.range_flag = nullptr;
-        const bool v3 = h->v3_nw > 0 && v3_shape_ok(h->v3_nw, h->v3_rs, h->v3_tmem, nh8);
+        V3Shape vs;
+        const bool v3 = v3_pick(h, nh8, &vs);
         for (int pl = 0; pl < 3; pl++)
         {
             if (!active[pl]) continue;
@@ -1946,7 +1964,7 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
             for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = (v3 ? h->maps3 : h->maps)[slots[pl][f] * 3 + pl];
             fp.nplanes++;
         }
-        if ((v3 ? launch_v3_nh(h->v3_nw, h->v3_rs, h->v3_tmem, fp, h->s_compute) : launch_fast8_nh(fp, h->s_compute)) != 0)
+        if ((v3 ? launch_v3_nh(vs.nw, vs.rs, vs.tmem, fp, h->s_compute) : launch_fast8_nh(fp, h->s_compute)) != 0)
         { set_error("nlmeans: fused launch failed"); return -1; }
         HBCU_CHECK(cudaGetLastError());
         h->kernel_launches++;

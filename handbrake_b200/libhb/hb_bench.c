@@ -26,7 +26,7 @@
 #include <pthread.h>
 #include <time.h>
 
-#define BENCH_RING_MAX 96
+#define BENCH_RING_MAX 256
 
 typedef struct
 {
