@@ -6,7 +6,7 @@
 
 A *step* is one pass of the NLMeans hot path over one batch of `--batch` synthetic frames per GPU, taken from ONE
 continuous frame stream per GPU (weak scaling: every rank filters its own block of the clip; the stream never
-restarts between steps, so no step pays a pipeline fill or an EOF flush).  With the defaults (K = 20 steps of 512
+restarts between steps, so no step pays a pipeline fill or an EOF flush).  With the defaults (K = 20 steps of 768
 frames) both timed regions last seconds, not milliseconds.
 
   value     frames/s, whole job, inputs already resident in HBM (border + NLMeans kernels, CUDA events on the
@@ -804,7 +804,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k_nlmeans_strong", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=768, help="frames per step per GPU")
     ap.add_argument("--ring", type=int, default=48, help="pinned input payloads the e2e stream cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -141,6 +141,9 @@ int hbcu_frame_alloc(hbcu_frame_t **out, int device, const int row_bytes[3], con
     f->ready = f->consumed = nullptr;
     f->next = nullptr;
     f->refs = 1;
+    f->external = false;
+    f->ext_release = nullptr;
+    f->ext_opaque = nullptr;
     // 256 bytes of zeroed slack behind the last plane: lapsharp and EEDI2 read a little past a plane's end
     if (cudaMalloc(&f->base, off + 256) != cudaSuccess || cudaMemset(f->base, 0, off + 256) != cudaSuccess ||
         cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess ||
@@ -188,12 +191,117 @@ void hbcu_frame_retain(hbcu_frame_t *f)
 void hbcu_frame_release(hbcu_frame_t *f)
 {
     if (f == nullptr) return;
-    // no wait: whoever writes the frame next orders itself behind `consumed`
-    std::lock_guard<std::mutex> g(g_frame_lock);
-    if (--f->refs > 0) return;
-    f->next = g_frame_free;
-    g_frame_free = f;
-    g_frames_alive--;
+    {
+        // no wait: whoever writes the frame next orders itself behind `consumed`
+        std::lock_guard<std::mutex> g(g_frame_lock);
+        if (--f->refs > 0) return;
+        g_frames_alive--;
+        if (!f->external)
+        {
+            f->next = g_frame_free;
+            g_frame_free = f;
+            return;
+        }
+    }
+    // a wrapped frame goes back to its owner, who may overwrite it at once: only after every queued reader is done
+    cudaSetDevice(f->device);
+    cudaEventSynchronize(f->consumed);
+    cudaGetLastError();
+    if (f->ext_release != nullptr) f->ext_release(f->ext_opaque);
+    cudaEventDestroy(f->ready);
+    cudaEventDestroy(f->consumed);
+    delete f;
+}
+
+// The NVDEC / NVENC seam (nvenc_common.c:329-336, hwaccel.c:15-60: hw_pix_fmt = AV_PIX_FMT_CUDA): a frame that already
+// lives in device memory somebody else owns -- what an AVFrame of AV_PIX_FMT_CUDA carries (data[i] = device pointer,
+// linesize[i]) -- becomes an hbcu_frame_t without a copy.
+int hbcu_frame_wrap(hbcu_frame_t **out, int device, void *const dplanes[3], const int row_bytes[3], const int rows[3],
+                    const int strides[3], size_t readable_tail_bytes, void *producer_stream,
+                    hbcu_frame_release_fn release, void *opaque)
+{
+    if (out == nullptr || dplanes == nullptr || row_bytes == nullptr || rows == nullptr || strides == nullptr)
+    {
+        hbcu::set_error("hbcu_frame_wrap: null argument");
+        return -1;
+    }
+    *out = nullptr;
+    for (int p = 0; p < 3; p++)
+    {
+        if (dplanes[p] == nullptr || ((uintptr_t)dplanes[p] % 16) != 0 || row_bytes[p] <= 0 || rows[p] <= 0 ||
+            strides[p] < row_bytes[p] || (strides[p] % 16) != 0)
+        {
+            hbcu::set_error("hbcu_frame_wrap: plane %d: %d bytes x %d rows, stride %d (pointers and strides must be multiples of 16)", p,
+                            row_bytes[p], rows[p], strides[p]);
+            return -1;
+        }
+    }
+    if (readable_tail_bytes < 256)
+    {
+        // the pooled frames carry 256 bytes of slack behind the last plane because the stencil kernels read whole
+        // vectors past a plane's end; a wrapped surface has to promise the same (decoder surfaces do: their height
+        // is aligned up)
+        hbcu::set_error("hbcu_frame_wrap: the allocation must stay readable for 256 bytes past every plane's last row");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    {
+        cudaGetLastError();
+        hbcu::set_error("hbcu_frame_wrap: CUDA device %d not available (%d devices)", device, ndev);
+        return -1;
+    }
+    HBCU_CHECK(cudaSetDevice(device));
+    hbcu_frame_s *f = new (std::nothrow) hbcu_frame_s();
+    if (f == nullptr) { hbcu::set_error("hbcu_frame_wrap: out of memory"); return -1; }
+    f->device = device;
+    f->base = nullptr;
+    f->bytes = 0;
+    for (int p = 0; p < 3; p++)
+    {
+        f->plane[p] = (uint8_t *)dplanes[p];
+        f->row_bytes[p] = row_bytes[p];
+        f->rows[p] = rows[p];
+        f->stride[p] = strides[p];
+    }
+    f->ready = f->consumed = nullptr;
+    f->next = nullptr;
+    f->refs = 1;
+    f->external = true;
+    f->ext_release = release;
+    f->ext_opaque = opaque;
+    if (cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f->consumed, cudaEventDisableTiming) != cudaSuccess ||
+        // the producer (the decoder's stream; NULL = the legacy default stream, i.e. work already synchronised) wrote the
+        // planes: readers order themselves behind this record exactly as behind a filter's
+        cudaEventRecord(f->ready, (cudaStream_t)producer_stream) != cudaSuccess)
+    {
+        hbcu::set_error("hbcu_frame_wrap: %s", cudaGetErrorString(cudaGetLastError()));
+        if (f->ready) cudaEventDestroy(f->ready);
+        if (f->consumed) cudaEventDestroy(f->consumed);
+        delete f;
+        return -1;
+    }
+    {
+        std::lock_guard<std::mutex> g(g_frame_lock);
+        g_frames_alive++;
+    }
+    *out = f;
+    return 0;
+}
+
+// an external consumer (the encoder's stream) reads a device frame: acquire orders `cuda_stream` behind the frame's
+// producer, done marks the reads queued so far on that stream as the frame's latest reader
+int hbcu_frame_acquire(hbcu_frame_t *f, void *cuda_stream)
+{
+    if (f == nullptr) { hbcu::set_error("hbcu_frame_acquire: null frame"); return -1; }
+    return hbcu::frame_begin_read(f, (cudaStream_t)cuda_stream);
+}
+
+int hbcu_frame_done(hbcu_frame_t *f, void *cuda_stream)
+{
+    if (f == nullptr) { hbcu::set_error("hbcu_frame_done: null frame"); return -1; }
+    return hbcu::frame_end_read(f, (cudaStream_t)cuda_stream);
 }
 
 void *hbcu_frame_plane(const hbcu_frame_t *f, int plane) { return f && plane >= 0 && plane < 3 ? f->plane[plane] : nullptr; }

@@ -15,6 +15,10 @@ struct hbcu_frame_s
                                    // so the latest record covers all readers
     int      refs;                 // hb_buffer_t references (hbcu_frame_retain / hbcu_frame_release)
     hbcu_frame_s *next;            // pool link
+    // wrapped frames (hbcu_frame_wrap): memory owned by somebody else (a decoder surface); never pooled
+    bool     external;
+    void   (*ext_release)(void *);
+    void    *ext_opaque;
 };
 
 namespace hbcu {

@@ -702,6 +702,12 @@ __device__ __forceinline__ float byte_as_biased_float(uint32_t w, int k)
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k));
 }
 
+// half k (0/1) of word w as the float 2^23 + value
+__device__ __forceinline__ float half_as_biased_float(uint32_t w, int k)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, k ? 0x7432 : 0x7410));
+}
+
 #include "nlmeans_v3.cuh"
 
 template <int NH, int TH, int NW, bool ORIGIN>
@@ -1174,12 +1180,6 @@ struct Fast16Layout
     static_assert(kTileBytes % 128 == 0, "TMA destination must stay 128-byte aligned");
 };
 
-// half k (0/1) of word w as the float 2^23 + value
-__device__ __forceinline__ float half_as_biased_float(uint32_t w, int k)
-{
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, k ? 0x7432 : 0x7410));
-}
-
 template <int NH, int TH, int NW, bool ORIGIN>
 __device__ __forceinline__ void nlm_group_fast16(const uint2 *__restrict__ cur, const uint2 *__restrict__ cmp,
                                                  float *__restrict__ acc_ws, float *__restrict__ acc_ps,
@@ -1627,6 +1627,29 @@ int launch_v3(FusedParams &fp, cudaStream_t st)
     return 0;
 }
 
+template <int NH, int NW, int RS, bool TMEM, int NBUF>
+int launch_v3w(FusedParams &fp, cudaStream_t st)
+{
+    using L = V3Layout<NW, RS, TMEM, NBUF, 2>;
+    static bool configured = false;
+    if (!configured)
+    {
+        HBCU_CHECK(cudaFuncSetAttribute(nlmeans_v3w_kernel<NH, NW, RS, TMEM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    int total = 0;
+    for (int i = 0; i < fp.nplanes; i++)
+    {
+        fp.first_tile[i] = total;
+        fp.tiles_x[i] = (fp.k[i].w + kTileW - 1) / kTileW;
+        total += fp.tiles_x[i] * ((fp.k[i].h + L::kTH - 1) / L::kTH);
+    }
+    fp.first_tile[fp.nplanes] = total;
+    nlmeans_v3w_kernel<NH, NW, RS, TMEM, NBUF><<<total, NW * 32, L::kTotal, st>>>(fp);
+    hbcu::count_launch();
+    return 0;
+}
+
 // v3 shapes built into the library: {warps, rows per warp, accumulators in tensor memory}.  Patch 9 (NH = 4) needs
 // 8 warps (its 9-row history does not fit 168 registers).
 struct V3Shape { int nw, rs, tmem; };
@@ -1683,6 +1706,27 @@ int launch_v3_nh(int nw, int rs, int tmem, FusedParams &fp, cudaStream_t st)
     V3CASE(4, 8, 27, 1, 2);
 #undef V3CASE
     return 1;
+}
+
+// 16-bit planes: one shape (12 warps x 18 rows, accumulators in tensor memory, one compare buffer: two 74 KB tiles)
+constexpr V3Shape kV3wShape = { 12, 18, 1 };
+
+int launch_v3w_nh(FusedParams &fp, cudaStream_t st)
+{
+    for (int pl = 0; pl < fp.nplanes; pl++)
+        for (int dx0 = -fp.k[pl].r_half; dx0 <= fp.k[pl].r_half; dx0 += kGroup)
+        {
+            const int ng = std::min(kGroup, fp.k[pl].r_half - dx0 + 1);
+            if (!v3_group_known(ng, (12 + dx0) & 3, kOrgNone)) return 1;
+            if (dx0 <= 0 && dx0 + ng > 0 && !v3_group_known(ng, (12 + dx0) & 3, -dx0)) return 1;
+        }
+    switch (fp.k[0].n_half)
+    {
+        case 1: return launch_v3w<1, kV3wShape.nw, kV3wShape.rs, true, 1>(fp, st);
+        case 2: return launch_v3w<2, kV3wShape.nw, kV3wShape.rs, true, 1>(fp, st);
+        case 3: return launch_v3w<3, kV3wShape.nw, kV3wShape.rs, true, 1>(fp, st);
+        default: return 1;
+    }
 }
 
 int launch_fast8_nh(FusedParams &kp, cudaStream_t st)
@@ -1934,10 +1978,23 @@ int run_filter(hbcu_nlmeans_s *h, int64_t index, int navail, int oslot, void *co
         {
             if (!active[pl]) continue;
             fp.k[fp.nplanes] = kps[pl];
-            for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = h->maps[slots[pl][f] * 3 + pl];
+            for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = (h->v3_nw > 0 ? h->maps3 : h->maps)[slots[pl][f] * 3 + pl];
             fp.nplanes++;
         }
-        if (launch_fast16_nh(fp, h->s_compute) != 0) { set_error("nlmeans: fused 16-bit launch failed"); return -1; }
+        int rc16 = h->v3_nw > 0 ? launch_v3w_nh(fp, h->s_compute) : 1;
+        if (rc16 > 0)
+        {
+            // a range the v3 group shapes do not cover (or v3 switched off): the round-1 kernel on its own tensor maps
+            fp.nplanes = 0;
+            for (int pl = 0; pl < 3; pl++)
+            {
+                if (!active[pl]) continue;
+                for (int f = 0; f < kps[pl].nf; f++) fp.maps[fp.nplanes][f] = h->maps[slots[pl][f] * 3 + pl];
+                fp.nplanes++;
+            }
+            rc16 = launch_fast16_nh(fp, h->s_compute);
+        }
+        if (rc16 != 0) { set_error("nlmeans: fused 16-bit launch failed"); return -1; }
         HBCU_CHECK(cudaGetLastError());
         h->kernel_launches++;
         // stand-in for frames with samples above 10 bit: returns immediately unless the border kernel raised the flag
@@ -2062,7 +2119,12 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && v3_shape_ok(a, b, c, 3)) { h->v3_nw = a; h->v3_rs = b; h->v3_tmem = c; }
         else h->v3_nw = 0;
     }
-    if (h->bps != 1) h->v3_nw = 0;
+    if (h->bps != 1)
+    {
+        // 16-bit planes have one v3 shape (nlmeans_v3w_kernel); HBCU_NLMEANS_V3=off still selects the round-1 kernel
+        const bool off = h->v3_nw == 0;
+        h->v3_nw = off ? 0 : kV3wShape.nw; h->v3_rs = kV3wShape.rs; h->v3_tmem = kV3wShape.tmem;
+    }
     h->ring = cfg->ring_frames > 0 ? cfg->ring_frames : 8;
     h->out_slots = cfg->out_slots > 0 ? cfg->out_slots : 4;
     h->d_exptable = nullptr;

@@ -21,14 +21,15 @@
 //     the 2*NH warm-up rows drop from 50 % to 30-33 % of the patch-row-sum work.
 #pragma once
 
-template <int NW, int RS, bool TMEM, int NBUF>
+template <int NW, int RS, bool TMEM, int NBUF, int BPS = 1>
 struct V3Layout
 {
     static constexpr int kTH        = NW * RS;
     static constexpr int kLoads     = kTH + 2 * kHalo > 256 ? 2 : 1;                     // a TMA box has at most 256 rows
     static constexpr int kBoxRows   = ((kTH + 2 * kHalo + kLoads - 1) / kLoads + 3) / 4 * 4;   // 4 rows x 160 B keep every box 128-byte aligned
     static constexpr int kRows      = kBoxRows * kLoads;                                 // >= kTH + 2 * kHalo; surplus rows are loaded, never used
-    static constexpr int kTileBytes = kRows * kTilePW;
+    static constexpr int kRowBytes  = kTilePW * BPS;
+    static constexpr int kTileBytes = kRows * kRowBytes;
     static constexpr int kAccBytes  = TMEM ? 0 : kTH * kTileW * (int)sizeof(float);      // per accumulator array
     static constexpr int kLutBytes  = kLutEntries * 32 * (int)sizeof(float);
     static constexpr int kOffCur    = 0;
@@ -41,7 +42,7 @@ struct V3Layout
     // one CTA per SM by construction (the TMEM variant allocates all 512 columns; a second resident CTA would spin)
     static constexpr int kTotal     = kUsed < 117 * 1024 ? 117 * 1024 : kUsed;
     static_assert(kBoxRows <= 256, "TMA box rows");
-    static_assert((kBoxRows * kTilePW) % 128 == 0, "TMA destination must stay 128-byte aligned");
+    static_assert((kBoxRows * kRowBytes) % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(!TMEM || ((NW + 3) / 4 * RS * 8 <= 512), "accumulators must fit 512 TMEM columns per lane quarter");
     static_assert(kTotal <= 227 * 1024, "shared memory");
 };
@@ -567,6 +568,378 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
         uint8_t *drow = dst + (size_t)y * p.dpitch + X0 + x;
         if (X0 + x + 3 < p.w)
             *reinterpret_cast<uchar4 *>(drow) = make_uchar4(o[0], o[1], o[2], o[3]);
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (X0 + x + i < p.w) drow[i] = o[i];
+        }
+    }
+    if (TMEM)
+    {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+        {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tmem_base_slot) : "memory");
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 16-bit samples (yuv420p10 planes; every sample <= kFast16Max = 1023, checked by the border kernel -- see
+// nlmeans_fast16_kernel for the contract and the integer stand-in that takes over otherwise).
+//
+// Same march as the 8-bit group: a lane owns 4 adjacent pixels and walks down its strip with the vertical running sum V
+// of horizontal patch-row sums in registers.  The squared differences have no packed-integer instruction at this width;
+// they are fp32 integers instead -- every value stays below 2^24, so every add/fma is exact in ANY order, which frees the
+// grouping: the four windows of a row share their middle (27 fp32 operations per displacement and row instead of a
+// 10-long prefix chain plus window differences; packing two displacements into f32x2 pairs was costed and dropped -- the
+// operand pairs cost as many PRMTs as the packed arithmetic saves).  V is a plain integer here
+// (49 x 1023^2 does not fit the 2^23-biased-float trick of the 8-bit kernel): I2FP + FMUL.SAT.
+// The compare pixels of the output row are re-read from shared memory (no 7-row delay line of words in registers).
+template <int NH, int NG, int OB, int ORG, class ACC>
+struct V3Group16
+{
+    static constexpr int N    = 2 * NH + 1;
+    static constexpr int PW   = kTilePW / 2;          // tile pitch in words (two samples each)
+    static constexpr int NA   = 4 + 2 * NH;           // source samples per row
+    static constexpr int NB   = NA + NG - 1;          // compare samples per row
+    static constexpr int OA   = (kHaloX - NH) & 3;    // sample offset of a[0] inside its first quad
+    static constexpr int FB   = (OB - NH) & 3;        // sample offset of b[0] inside its first quad (OB = (12 + dx0) & 3)
+    static constexpr int NWA  = (OA + NA + 1) / 2;    // words covering the source window
+    static constexpr int NWB  = (FB + NB + 1) / 2;
+    static constexpr int OP   = OB & 3;               // the output row's compare pixels start at sample kHaloX + dx0 of the row
+    static constexpr int NWP  = (OP + NG + 3 + 1) / 2;
+    static constexpr float kBias = 8388608.0f;
+    static_assert(NH >= 1 && NH <= 3, "patch-row sums must stay below 2^23");
+
+    int      V[NG][4];
+    uint32_t hist[N][NG][4];                          // patch-row sums as bits of (2^23 + sum): the biases cancel in V
+    const uint32_t *arow, *brow, *prow, *orow;
+    const ACC &acc;
+    uint32_t lut_lane_addr;
+    float wscale;
+    double origin_tune;
+
+    __device__ __forceinline__ V3Group16(const uint32_t *cur, const uint32_t *cmp, const ACC &acc_, uint32_t lut_lane_addr_, float wscale_,
+                                         double origin_tune_, int seg_y0, int lane, int dy, int dx0)
+        : acc(acc_), lut_lane_addr(lut_lane_addr_), wscale(wscale_), origin_tune(origin_tune_)
+    {
+#pragma unroll
+        for (int g = 0; g < NG; g++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                V[g][i] = 0;
+#pragma unroll
+                for (int k = 0; k < N; k++) hist[k][g][i] = kVBias;
+            }
+        const int fa = kHaloX - NH, fb = kHaloX - NH + dx0, fp = kHaloX + dx0;      // first sample of each window, relative to 4 * lane
+        arow = cur + (seg_y0 - NH + kHalo) * PW + 2 * lane + 2 * (fa >> 2);
+        brow = cmp + (seg_y0 - NH + kHalo + dy) * PW + 2 * lane + 2 * (fb >> 2);
+        prow = cmp + (seg_y0 + kHalo + dy) * PW + 2 * lane + 2 * (fp >> 2);
+        orow = cur + (seg_y0 + kHalo) * PW + 2 * lane + kHaloX / 2;
+    }
+
+    static __device__ __forceinline__ bool is_origin(int g) { return ORG >= 0 && g == ORG; }
+
+    template <int K, bool OUT>
+    __device__ __forceinline__ void step(int r)
+    {
+        uint32_t wa[NWA], wb[NWB];
+#pragma unroll
+        for (int j = 0; j < NWA; j++) wa[j] = arow[j];
+#pragma unroll
+        for (int j = 0; j < NWB; j++) wb[j] = brow[j];
+        arow += PW;
+        brow += PW;
+        uint32_t accv[8];
+        if (OUT) acc.load(r, accv);
+        float a[NA], b[NB];
+#pragma unroll
+        for (int j = 0; j < NA; j++) a[j] = half_as_biased_float(wa[(OA + j) >> 1], (OA + j) & 1);
+#pragma unroll
+        for (int j = 0; j < NB; j++) b[j] = half_as_biased_float(wb[(FB + j) >> 1], (FB + j) & 1);
+
+        // hs[i] = sum of d^2 over samples i .. i + 2NH of the row = the common middle M (samples 3 .. 2NH, carrying the
+        // 2^23 bias of the stored sums) + L[i] (samples i .. 2, i <= 2) + R[i - 1] (samples 2NH+1 .. 2NH+i, i >= 1).
+        // Every value is an integer below 2^24: all of it is exact in any order.
+#pragma unroll
+        for (int g = 0; g < NG; g++)
+        {
+            if (ORG != kOrgNone && is_origin(g)) continue;
+            float d[NA];
+#pragma unroll
+            for (int j = 0; j < NA; j++) d[j] = __fsub_rn(a[j], b[j + g]);          // exact: both are 2^23 + sample
+            float M = kBias;
+#pragma unroll
+            for (int j = 3; j <= 2 * NH; j++) M = __fmaf_rn(d[j], d[j], M);
+            float L[3], R[3];
+            L[2] = __fmul_rn(d[2], d[2]);
+            L[1] = __fmaf_rn(d[1], d[1], L[2]);
+            L[0] = __fmaf_rn(d[0], d[0], L[1]);
+            R[0] = __fmul_rn(d[2 * NH + 1], d[2 * NH + 1]);
+            R[1] = __fmaf_rn(d[2 * NH + 2], d[2 * NH + 2], R[0]);
+            R[2] = __fmaf_rn(d[2 * NH + 3], d[2 * NH + 3], R[1]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                float h = M;
+                if (i <= 2) h = __fadd_rn(h, L[i]);
+                if (i >= 1) h = __fadd_rn(h, R[i - 1]);
+                const uint32_t hb = __float_as_uint(h);
+                V[g][i] = V[g][i] + (int)hb - (int)hist[K][g][i];
+                hist[K][g][i] = hb;
+            }
+        }
+        if (OUT)
+        {
+            uint32_t wp[NWP];
+#pragma unroll
+            for (int j = 0; j < NWP; j++) wp[j] = prow[r * PW + j];
+            uint64_t pix2[NG + 1];                        // (compare pixel j, compare pixel j + 2) as floats
+#pragma unroll
+            for (int j = 0; j < NG + 1; j++)
+                pix2[j] = v3_add2(v3_pack2(half_as_biased_float(wp[(OP + j) >> 1], (OP + j) & 1),
+                                           half_as_biased_float(wp[(OP + j + 2) >> 1], (OP + j + 2) & 1)),
+                                  v3_pack2(-kBias, -kBias));
+            acc.wait_load(accv);
+            uint64_t W[NG][2];
+#pragma unroll
+            for (int g = 0; g < NG; g++)
+            {
+                if (ORG != kOrgNone && is_origin(g)) continue;
+                float t[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(t[i]) : "f"(__int2float_rn(V[g][i])), "f"(wscale));
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                {
+                    float u0, u1, w0, w1;
+                    v3_unpack2(v3_add2_rz(v3_pack2(t[h], t[h + 2]), v3_pack2(65536.0f, 65536.0f)), u0, u1);
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(w0) : "r"((__float_as_uint(u0) << 7) + lut_lane_addr));
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(w1) : "r"((__float_as_uint(u1) << 7) + lut_lane_addr));
+                    W[g][h] = v3_pack2(w0, w1);
+                }
+            }
+            uint64_t ws2[2], ps2[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+                ws2[h] = v3_pack2(__uint_as_float(accv[2 * h]), __uint_as_float(accv[2 * h + 1]));
+                ps2[h] = v3_pack2(__uint_as_float(accv[4 + 2 * h]), __uint_as_float(accv[4 + 2 * h + 1]));
+            }
+#pragma unroll
+            for (int g = 0; g < NG; g++)
+            {
+                if (ORG != kOrgNone && is_origin(g))
+                {
+                    const uint32_t c0 = orow[r * PW], c1 = orow[r * PW + 1];
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                    {
+                        float wa_, wb_, pa, pb;
+                        v3_unpack2(ws2[h], wa_, wb_);
+                        v3_unpack2(ps2[h], pa, pb);
+                        add_origin(wa_, pa, origin_tune, (int)((c0 >> (16 * h)) & 0xffffu));      // pixel h
+                        add_origin(wb_, pb, origin_tune, (int)((c1 >> (16 * h)) & 0xffffu));      // pixel h + 2
+                        ws2[h] = v3_pack2(wa_, wb_);
+                        ps2[h] = v3_pack2(pa, pb);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                    {
+                        ws2[h] = v3_add2(ws2[h], W[g][h]);
+                        ps2[h] = v3_add2(ps2[h], v3_mul2(W[g][h], pix2[g + h]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+                float x, y;
+                v3_unpack2(ws2[h], x, y);
+                accv[2 * h] = __float_as_uint(x); accv[2 * h + 1] = __float_as_uint(y);
+                v3_unpack2(ps2[h], x, y);
+                accv[4 + 2 * h] = __float_as_uint(x); accv[4 + 2 * h + 1] = __float_as_uint(y);
+            }
+            acc.store(r, accv);
+        }
+    }
+
+    template <int... Ks>
+    __device__ __forceinline__ void warm_up(std::integer_sequence<int, Ks...>) { (step<Ks, false>(0), ...); }
+    template <int... Ms>
+    __device__ __forceinline__ void rows_from(int r0, int rows, std::integer_sequence<int, Ms...>)
+    {
+        ((r0 + Ms < rows ? step<(2 * NH + Ms) % N, true>(r0 + Ms) : (void)0), ...);
+    }
+    __device__ __forceinline__ void run(int rows)
+    {
+        warm_up(std::make_integer_sequence<int, 2 * NH>{});
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows; r0 += N) rows_from(r0, rows, std::make_integer_sequence<int, N>{});
+        acc.wait_store();
+    }
+};
+
+template <int NH, int NG, int OB, int ORG, class ACC>
+__device__ __forceinline__ void v3_group16(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp, const ACC &acc,
+                                           uint32_t lut_lane_addr, float wscale, double origin_tune,
+                                           int seg_y0, int rows, int lane, int dy, int dx0)
+{
+    V3Group16<NH, NG, OB, ORG, ACC> g(cur, cmp, acc, lut_lane_addr, wscale, origin_tune, seg_y0, lane, dy, dx0);
+    g.run(rows);
+}
+
+template <int NH, int NW, int RS, bool TMEM, int NBUF>
+__global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3w_kernel(const __grid_constant__ FusedParams fp)
+{
+    if (*fp.range_flag != 0u) return;               // samples above 10 bit seen: the integer kernel takes over
+    constexpr int kThreads = NW * 32;
+    using L = V3Layout<NW, RS, TMEM, NBUF, 2>;
+    int pl = 0;
+    while (pl + 1 < fp.nplanes && (int)blockIdx.x >= fp.first_tile[pl + 1]) pl++;
+    const KernelParams &p = fp.k[pl];
+    const CUtensorMap *maps = fp.maps[pl];
+    const int tile = (int)blockIdx.x - fp.first_tile[pl];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *cur  = smem + L::kOffCur;
+    float *lut    = reinterpret_cast<float *>(smem + L::kOffLut);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (1 + NBUF));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = (tile % fp.tiles_x[pl]) * kTileW, Y0 = (tile / fp.tiles_x[pl]) * L::kTH;
+    const int gx = X0 + kBorder - kHaloX, gy = Y0 + kBorder - kHalo;
+
+    if (tid == 0)
+    {
+        for (int b = 0; b < 1 + NBUF; b++) mbar_init(bar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (TMEM && warp == 0)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TMEM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (TMEM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0)
+    {
+        mbar_expect_tx(bar, L::kTileBytes);
+        for (int l = 0; l < L::kLoads; l++) tma_load_2d(cur + l * L::kBoxRows * L::kRowBytes, &maps[0], gx, gy + l * L::kBoxRows, bar);
+        for (int b = 0; b < NBUF && 1 + b < p.nf; b++)
+        {
+            mbar_expect_tx(bar + 1 + b, L::kTileBytes);
+            for (int l = 0; l < L::kLoads; l++)
+                tma_load_2d(smem + L::kOffCmp + b * L::kTileBytes + l * L::kBoxRows * L::kRowBytes, &maps[1 + b], gx, gy + l * L::kBoxRows, bar + 1 + b);
+        }
+    }
+    for (int i = tid; i < kLutEntries * 32; i += kThreads)
+    {
+        const int e = i >> 5;
+        lut[i] = e < HBCU_NLMEANS_EXPSIZE ? p.exptable[e] : 0.f;
+    }
+
+    const int seg_y0 = warp * RS;
+    int rows = p.h - (Y0 + seg_y0);
+    rows = rows < 0 ? 0 : (rows > RS ? RS : rows);
+    V3Acc<TMEM> acc;
+    if constexpr (TMEM)
+    {
+        const uint32_t base = *tmem_base_slot;
+        acc.taddr = base + ((uint32_t)(warp & 3) << 21) + (uint32_t)((warp >> 2) * RS * 8);
+        uint32_t z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int r = 0; r < RS; r++) acc.store(r, z);
+        acc.wait_store();
+    }
+    else
+    {
+        float *acc_ws = reinterpret_cast<float *>(smem + L::kOffWs);
+        float *acc_ps = reinterpret_cast<float *>(smem + L::kOffPs);
+        for (int i = tid; i < L::kTH * kTileW; i += kThreads)
+        {
+            acc_ws[i] = 0.f;
+            acc_ps[i] = 0.f;
+        }
+        acc.ws = acc_ws + seg_y0 * kTileW + lane * 4;
+        acc.ps = acc_ps + seg_y0 * kTileW + lane * 4;
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const float wscale = p.wfact * 0.0078125f;                         // wfact / 128, exact
+    const uint32_t lut_lane_addr = smem_u32(lut) + (uint32_t)lane * 4u - (0x47800000u << 7);
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur);
+    for (int f = 0; f < p.nf; f++)
+    {
+        const uint32_t *bw = cw;
+        const int buf = (f - 1) % NBUF;
+        if (f > 0)
+        {
+            mbar_wait(bar + 1 + buf, (uint32_t)(((f - 1) / NBUF) & 1));
+            bw = reinterpret_cast<const uint32_t *>(smem + L::kOffCmp + buf * L::kTileBytes);
+        }
+        if (rows > 0)
+        {
+            for (int dy = -p.r_half; dy <= p.r_half; dy++)
+            {
+                for (int dx0 = -p.r_half; dx0 <= p.r_half; dx0 += kGroup)
+                {
+                    const int ng  = min(kGroup, p.r_half - dx0 + 1);
+                    const int org = (f == 0 && dy == 0 && dx0 <= 0 && dx0 + ng > 0) ? -dx0 : kOrgNone;
+                    const int ob  = (12 + dx0) & 3;
+#define X(NG_, OB_, ORG_)                                                                                                   \
+                    if (ng == NG_ && ob == OB_ && org == ORG_)                                                              \
+                        v3_group16<NH, NG_, OB_, ORG_>(cw, bw, acc, lut_lane_addr, wscale, p.origin_tune, seg_y0, rows, lane, dy, dx0); \
+                    else
+                    V3_GROUP_SHAPES(X)
+#undef X
+                    { /* unreachable: the launcher checked v3_group_known() for every group of this range */ }
+                }
+            }
+        }
+        if (f > 0 && f + NBUF < p.nf)
+        {
+            __syncthreads();
+            if (tid == 0)
+            {
+                fence_proxy_async();
+                mbar_expect_tx(bar + 1 + buf, L::kTileBytes);
+                for (int l = 0; l < L::kLoads; l++)
+                    tma_load_2d(smem + L::kOffCmp + buf * L::kTileBytes + l * L::kBoxRows * L::kRowBytes, &maps[f + NBUF], gx, gy + l * L::kBoxRows, bar + 1 + buf);
+            }
+        }
+    }
+
+    const int x = lane * 4;
+    uint16_t *dst = reinterpret_cast<uint16_t *>(p.dst);
+    const uint16_t *cur16 = reinterpret_cast<const uint16_t *>(cur);
+    for (int r = 0; r < rows; r++)
+    {
+        const int oy = seg_y0 + r;
+        const int y = Y0 + oy;
+        uint32_t accv[8];
+        acc.load(r, accv);
+        acc.wait_load(accv);
+        uint16_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            o[i] = finish_pixel<uint16_t>(__uint_as_float(accv[v3_acc_slot(i)]), __uint_as_float(accv[4 + v3_acc_slot(i)]),
+                                          cur16[(oy + kHalo) * kTilePW + x + kHaloX + i]);
+        uint16_t *drow = dst + (size_t)y * p.dpitch + X0 + x;
+        if (X0 + x + 3 < p.w)
+            *reinterpret_cast<ushort4 *>(drow) = make_ushort4(o[0], o[1], o[2], o[3]);
         else
         {
 #pragma unroll

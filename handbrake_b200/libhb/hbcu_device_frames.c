@@ -78,6 +78,48 @@ hb_buffer_t *hbcu_device_frame_buffer_init(int pix_fmt, int width, int height, i
     return b;
 }
 
+/* The decoder end of a zero-copy chain: an AVFrame of AV_PIX_FMT_CUDA -- data[i] device pointers,
+ * linesize[i], the frames context's device and stream -- becomes an HBCU_DEVICE hb_buffer_t without a copy
+ * (hwaccel.c:15-60 is where libhb receives such frames; nvenc_common.c:329-336 where the encoder asks for them).
+ * `release(opaque)` is the caller's av_frame_free: it runs when the buffer is closed and the last device reader is done. */
+hb_buffer_t *hbcu_wrap_cuda_frame(int pix_fmt, int width, int height, int device, void *const data[3], const int linesize[3],
+                                  size_t readable_tail_bytes, void *cuda_stream, void (*release)(void *), void *opaque)
+{
+    const AVPixFmtDescriptor *desc = av_pix_fmt_desc_get(pix_fmt);
+    if (desc == NULL || desc->nb_components < 3) return NULL;
+    install_hooks();
+    hb_buffer_t *b = hb_buffer_init(0);
+    if (b == NULL) return NULL;
+    b->f.max_plane = 2;
+    b->s.type      = FRAME_BUF;
+    b->f.width     = width;
+    b->f.height    = height;
+    b->f.fmt       = pix_fmt;
+    const int bps = desc->comp[0].depth > 8 ? 2 : 1;
+    int row_bytes[3], rows[3];
+    for (int p = 0; p < 3; p++)
+    {
+        b->plane[p].stride = linesize[p];
+        b->plane[p].width  = hb_image_width(pix_fmt, width, p);
+        b->plane[p].height = hb_image_height(pix_fmt, height, p);
+        b->plane[p].size   = b->plane[p].stride * b->plane[p].height;
+        b->plane[p].data   = data[p];
+        row_bytes[p] = b->plane[p].width * bps;
+        rows[p]      = b->plane[p].height;
+        b->size     += b->plane[p].size;
+    }
+    hbcu_frame_t *f = NULL;
+    if (hbcu_frame_wrap(&f, device, data, row_bytes, rows, linesize, readable_tail_bytes, cuda_stream, release, opaque) != 0)
+    {
+        hb_error("hbcu: wrapped device frame: %s", hbcu_last_error());
+        hb_buffer_close(&b);
+        return NULL;
+    }
+    b->storage_type = HBCU_DEVICE;
+    b->storage = f;
+    return b;
+}
+
 /* ------------------------------------------------------------------ */
 /* adapter filters                                                       */
 /* ------------------------------------------------------------------ */
@@ -91,6 +133,8 @@ struct hb_filter_private_s
 {
     hbcu_xfer_t *x;
     int          download, device;
+    int          external;      /* HBCU_UPLOAD_EXTERNAL=1 (test hook): behave like a hardware decoder -- the uploaded frame is
+                                 * a surface the adapter owns and goes downstream WRAPPED (hbcu_wrap_cuda_frame) */
     xfer_pending_t pending[XFER_MAX_PENDING];
     int head, count, inflight_max;
     int64_t next_ticket;
@@ -135,6 +179,7 @@ static int xfer_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     pv->device = hbcu_env_device();
     pv->inflight_max = 6;
     pv->input = *init;
+    pv->external = !pv->download && getenv("HBCU_UPLOAD_EXTERNAL") != NULL && atoi(getenv("HBCU_UPLOAD_EXTERNAL")) != 0;
     if (hbcu_xfer_create(&pv->x, pv->device, XFER_MAX_PENDING) != 0)
     {
         hb_error("%s: %s", filter->short_name, hbcu_last_error());
@@ -166,6 +211,39 @@ static void xfer_close(hb_filter_object_t *filter)
     filter->private_data = NULL;
 }
 
+static long g_surfaces_returned = 0;
+long hbcu_test_surfaces_returned(void) { return g_surfaces_returned; }
+
+static void surface_return(void *opaque)
+{
+    hb_buffer_t *surface = opaque;       /* the "decoder" gets its surface back: here it simply frees it */
+    __sync_fetch_and_add(&g_surfaces_returned, 1);
+    hb_buffer_close(&surface);
+}
+
+/* test hook: the uploaded frame plays a decoder-owned surface; what goes downstream is a wrapper around its planes */
+static hb_buffer_t *as_decoder_surface(hb_filter_private_t *pv, hb_buffer_t *surface)
+{
+    void *data[3];
+    int linesize[3];
+    if (hbcu_xfer_wait(pv->x, pv->pending[pv->head].ticket) != 0) return NULL;      /* the "decode" is complete */
+    for (int c = 0; c < 3; c++)
+    {
+        data[c]     = surface->plane[c].data;
+        linesize[c] = surface->plane[c].stride;
+    }
+    hb_buffer_t *w = hbcu_wrap_cuda_frame(surface->f.fmt, surface->f.width, surface->f.height, pv->device, data, linesize,
+                                          256, NULL, surface_return, surface);
+    if (w == NULL) return NULL;
+    w->f.color_prim      = surface->f.color_prim;
+    w->f.color_transfer  = surface->f.color_transfer;
+    w->f.color_matrix    = surface->f.color_matrix;
+    w->f.color_range     = surface->f.color_range;
+    w->f.chroma_location = surface->f.chroma_location;
+    hb_buffer_copy_props(w, surface);
+    return w;
+}
+
 static int xfer_harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int all)
 {
     while (pv->count > 0)
@@ -186,6 +264,7 @@ static int xfer_harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int all
                 if (done == 0) break;
             }
         }
+        if (pv->external && p->ticket >= 0 && (p->out = as_decoder_surface(pv, p->out)) == NULL) return -1;
         hb_buffer_list_append(list, p->out);
         p->out = NULL;
         if (p->in != NULL) hb_buffer_close(&p->in);

@@ -19,6 +19,9 @@ extern hb_filter_object_t hb_filter_hbcu_download;   /* HBCU_DEVICE hb_buffer_t 
 hb_buffer_t  *hbcu_device_frame_buffer_init(int pix_fmt, int width, int height, int device);
 /* the device frame behind a buffer, NULL for host buffers */
 hbcu_frame_t *hbcu_buffer_frame(const hb_buffer_t *b);
+/* an AV_PIX_FMT_CUDA AVFrame's planes (data / linesize / device / stream) as an HBCU_DEVICE buffer, no copy */
+hb_buffer_t  *hbcu_wrap_cuda_frame(int pix_fmt, int width, int height, int device, void *const data[3], const int linesize[3],
+                                   size_t readable_tail_bytes, void *cuda_stream, void (*release)(void *), void *opaque);
 /* does this filter instance hand its output on in HBM?  (init->hw_pix_fmt == AV_PIX_FMT_CUDA, the way libhb marks
  * a hardware-frame pipeline: nvenc_common.c:329-336, hwaccel.c:15-60) */
 int           hbcu_init_wants_device_output(const hb_filter_init_t *init);

@@ -69,6 +69,24 @@ void * hbcu_frame_plane(const hbcu_frame_t *f, int plane);      /* DEVICE pointe
 int    hbcu_frame_stride(const hbcu_frame_t *f, int plane);
 int    hbcu_frame_device(const hbcu_frame_t *f);
 long   hbcu_frames_alive(void);                         /* handed out and not released (leak check) */
+/* The NVDEC / NVENC seam (libhb/nvenc_common.c:329-336 sets hw_pix_fmt = AV_PIX_FMT_CUDA; libhb/hwaccel.c:15-60):
+ * a frame that already lives in device memory SOMEBODY ELSE owns -- what an AVFrame of AV_PIX_FMT_CUDA carries,
+ * data[i] = device pointer, linesize[i] = pitch -- becomes an hbcu_frame_t without a copy.
+ *   dplanes / strides    AVFrame.data / AVFrame.linesize (16-byte aligned, as every decoder surface is)
+ *   readable_tail_bytes  how far past each plane's last row the allocation stays readable (>= 256: the stencil kernels
+ *                        read whole vectors; decoder surfaces are height-aligned and satisfy it)
+ *   producer_stream      the CUstream the planes were written on (AVCUDADeviceContext.stream), or NULL when the
+ *                        writer has already been synchronised: consumers order themselves behind it, nobody blocks
+ *   release(opaque)      called once, after the last hb_buffer_t reference is gone AND every queued device reader has
+ *                        finished (av_frame_free / unmapping the surface goes here)
+ * hbcu_frame_acquire/done let an external consumer (the encoder's stream) read ANY device frame in stream order. */
+typedef void (*hbcu_frame_release_fn)(void *opaque);
+int    hbcu_frame_wrap(hbcu_frame_t **f, int device, void *const dplanes[3], const int row_bytes[3], const int rows[3],
+                       const int strides[3], size_t readable_tail_bytes, void *producer_stream,
+                       hbcu_frame_release_fn release, void *opaque);
+int    hbcu_frame_acquire(hbcu_frame_t *f, void *cuda_stream);
+int    hbcu_frame_done(hbcu_frame_t *f, void *cuda_stream);
+
 void   hbcu_frame_trim(void);                           /* frees the pooled frames */
 /* the two ends of a device-resident chain (the role of libhb's adapter filters,
  * platform/macosx/adapter_vt.c): host frame -> device frame in front of the first CUDA filter,

@@ -20,6 +20,9 @@ struct hbcu_frame_s
     int row_bytes[3], rows[3], strides[3];
     uint8_t *base;
     void *planes[3];
+    hbcu_frame_release_fn ext_release;      /* wrapped frames: somebody else's memory */
+    void *ext_opaque;
+    int external;
 };
 
 static long frames_alive = 0;
@@ -56,9 +59,41 @@ void oracle_hbcu_frame_release(hbcu_frame_t *f)
 {
     if (f == NULL || --f->refs > 0) return;
     frames_alive--;
-    free(f->base);
+    if (f->external)
+    {
+        if (f->ext_release) f->ext_release(f->ext_opaque);
+    }
+    else free(f->base);
     free(f);
 }
+
+int oracle_hbcu_frame_wrap(hbcu_frame_t **out, int device, void *const dplanes[3], const int row_bytes[3], const int rows[3],
+                           const int strides[3], size_t readable_tail_bytes, void *producer_stream,
+                           hbcu_frame_release_fn release, void *opaque)
+{
+    (void)producer_stream;
+    if (readable_tail_bytes < 256)
+    {
+        oracle_hostlogic_set_error("frame_wrap: no readable tail");
+        return -1;
+    }
+    struct hbcu_frame_s *f = calloc(1, sizeof(*f));
+    f->refs = 1;
+    f->device = device;
+    f->external = 1;
+    f->ext_release = release;
+    f->ext_opaque = opaque;
+    for (int p = 0; p < 3; p++)
+    {
+        f->row_bytes[p] = row_bytes[p]; f->rows[p] = rows[p]; f->strides[p] = strides[p];
+        f->planes[p] = dplanes[p];
+    }
+    frames_alive++;
+    *out = f;
+    return 0;
+}
+int oracle_hbcu_frame_acquire(hbcu_frame_t *f, void *s) { (void)f; (void)s; return 0; }
+int oracle_hbcu_frame_done(hbcu_frame_t *f, void *s) { (void)f; (void)s; return 0; }
 void *oracle_hbcu_frame_plane(const hbcu_frame_t *f, int plane) { return f->planes[plane]; }
 int   oracle_hbcu_frame_stride(const hbcu_frame_t *f, int plane) { return f->strides[plane]; }
 int   oracle_hbcu_frame_device(const hbcu_frame_t *f) { return f->device; }
