@@ -431,7 +431,7 @@ def nlm_roofline(wl, workload, ms, ks, frames, clocks_mhz=None):
     r = {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
          "frac": round(achieved / peak, 4) if achieved else None,
          "traffic": int(cap["dram_bytes_total"]) if cap else None, "traffic_source": cap_src,
-         "kernel": ("nlmeans_v3_kernel" if wl["depth"] == 8 else "nlmeans_fast16_kernel") +
+         "kernel": ("nlmeans_v3_kernel" if wl["depth"] == 8 else "nlmeans_v3w_kernel") +
                    " (all tiles of Y, U, V of one frame in one launch)",
          "kernel_ms_per_frame": round(kern_ms, 4), "launch_ms_avg": round(launch_ms, 4), "launches_in_flight": round(in_flight, 2),
          "launches_timed": ks["kernel_calls"], "algorithmic_bytes_per_frame": alg, "peak_source": peak_src,

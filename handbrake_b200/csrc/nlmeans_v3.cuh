@@ -21,7 +21,7 @@
 //     the 2*NH warm-up rows drop from 50 % to 30-33 % of the patch-row-sum work.
 #pragma once
 
-template <int NW, int RS, bool TMEM, int NBUF, int BPS = 1>
+template <int NW, int RS, bool TMEM, int NBUF, int BPS = 1, bool PRE = false>
 struct V3Layout
 {
     static constexpr int kTH        = NW * RS;
@@ -34,7 +34,12 @@ struct V3Layout
     static constexpr int kLutBytes  = kLutEntries * 32 * (int)sizeof(float);
     static constexpr int kOffCur    = 0;
     static constexpr int kOffCmp    = kOffCur + kTileBytes;
-    static constexpr int kOffWs     = kOffCmp + NBUF * kTileBytes;
+    // prefilter variant: the pre-denoised current tile and ONE pre-denoised compare tile (patch distances are taken from
+    // these, pixel values from the plain tiles)
+    static constexpr int kOffPre0   = kOffCmp + NBUF * kTileBytes;
+    static constexpr int kOffCmpPre = kOffPre0 + (PRE ? kTileBytes : 0);
+    static constexpr int kOffWs     = kOffCmpPre + (PRE ? kTileBytes : 0);
+    static_assert(!PRE || NBUF == 1, "the prefilter variant keeps one compare buffer pair");
     static constexpr int kOffPs     = kOffWs + kAccBytes;
     static constexpr int kOffLut    = kOffPs + kAccBytes;
     static constexpr int kOffBar    = kOffLut + kLutBytes;                               // 1 + NBUF mbarriers, TMEM base word
@@ -135,7 +140,7 @@ constexpr uint32_t kVBias = 0x4B000000u;     // bits of 2^23
 //   ORG  : slot of the origin displacement inside the group, or kOrgNone
 // A struct so that the row step can be a function template of its unrolled slot K (every index into hist / P is a
 // compile-time constant; everything is force-inlined and the arrays live in registers).
-template <int NH, int NG, int OBS, int ORG, class ACC>
+template <int NH, int NG, int OBS, int ORG, bool PRE, class ACC>
 struct V3Group
 {
     static constexpr int N      = 2 * NH + 1;
@@ -150,15 +155,17 @@ struct V3Group
 
     uint32_t V[NG][4];
     uint32_t hist[N][NG][4];
-    uint32_t P[N][2];                                // compare-stream words 1 and 2 of the last rows: the averaged pixels
-    const uint32_t *arow, *brow, *orow;
+    uint32_t P[PRE ? 1 : N][2];                      // compare-stream words 1 and 2 of the last rows: the averaged pixels
+    const uint32_t *arow, *brow, *orow, *prow;       // (prefilter variant: re-read from the PLAIN compare tile instead)
     const ACC &acc;
     uint32_t lut_lane_addr;
     float wscale, wbias;
     double origin_tune;
 
-    __device__ __forceinline__ V3Group(const uint32_t *cur, const uint32_t *cmp, const ACC &acc_, uint32_t lut_lane_addr_, float wscale_,
-                                       float wbias_, double origin_tune_, int seg_y0, int lane, int dy, int dx0)
+    // srcp / cmpd: the tiles the patch distances are taken from (source, compare); cmpv: the compare tile whose pixels are
+    // averaged; cur: the plain current tile (origin term).  Without a prefilter srcp == cur and cmpd == cmpv.
+    __device__ __forceinline__ V3Group(const uint32_t *srcp, const uint32_t *cmpd, const uint32_t *cmpv, const uint32_t *cur, const ACC &acc_,
+                                       uint32_t lut_lane_addr_, float wscale_, float wbias_, double origin_tune_, int seg_y0, int lane, int dy, int dx0)
         : acc(acc_), lut_lane_addr(lut_lane_addr_), wscale(wscale_), wbias(wbias_), origin_tune(origin_tune_)
     {
         const int s   = 12 + dx0;                    // tile byte (relative to 4 * lane) of compare-stream byte 0
@@ -173,10 +180,11 @@ struct V3Group
                 for (int k = 0; k < N; k++) hist[k][g][i] = 0;
             }
 #pragma unroll
-        for (int k = 0; k < N; k++) P[k][0] = P[k][1] = 0;
-        arow = cur + (seg_y0 - NH + kHalo) * PW + lane + 3;
-        brow = cmp + (seg_y0 - NH + kHalo + dy) * PW + lane + wb0;
+        for (int k = 0; k < (PRE ? 1 : N); k++) P[k][0] = P[k][1] = 0;
+        arow = srcp + (seg_y0 - NH + kHalo) * PW + lane + 3;
+        brow = cmpd + (seg_y0 - NH + kHalo + dy) * PW + lane + wb0;
         orow = cur + (seg_y0 + kHalo) * PW + lane + kHaloX / 4;
+        prow = cmpv + (seg_y0 + kHalo + dy) * PW + lane + wb0 + 1;
     }
 
     static __device__ __forceinline__ bool is_origin(int g) { return ORG >= 0 && g == ORG; }
@@ -281,8 +289,19 @@ struct V3Group
         }
         if (OUT)
         {
-            constexpr int KP = (K + N - NH) % N;          // the compare row of the output row was loaded NH steps ago
-            const uint32_t p0 = P[KP][0], p1 = P[KP][1];
+            constexpr int KP = PRE ? 0 : (K + N - NH) % N;   // the compare row of the output row was loaded NH steps ago
+            uint32_t p0, p1;
+            if constexpr (PRE)
+            {
+                const uint32_t q0 = prow[r * PW], q1 = prow[r * PW + 1], q2 = prow[r * PW + 2];
+                p0 = OBS == 0 ? q0 : __funnelshift_r(q0, q1, 8 * OBS);
+                p1 = OBS == 0 ? q1 : __funnelshift_r(q1, q2, 8 * OBS);
+            }
+            else
+            {
+                p0 = P[KP][0];
+                p1 = P[KP][1];
+            }
             // pixels 0/2 and 1/3 of the lane's four travel as packed pairs (add/mul.rn.f32x2: two IEEE fp32 operations per
             // issue slot, same rounding as the scalar instructions); accumulator words are stored in that order:
             // {ws0, ws2, ws1, ws3, ps0, ps2, ps1, ps3}
@@ -357,8 +376,11 @@ struct V3Group
             }
             acc.store(r, accv);
         }
-        P[K][0] = bg0[1];
-        P[K][1] = bg0[2];
+        if constexpr (!PRE)
+        {
+            P[K][0] = bg0[1];
+            P[K][1] = bg0[2];
+        }
     }
 
     template <int... Ks>
@@ -399,12 +421,13 @@ struct V3Group
     }
 };
 
-template <int NH, int NG, int OBS, int ORG, bool EXACT, class ACC>
-__device__ __forceinline__ void v3_group(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ cmp, const ACC &acc,
+template <int NH, int NG, int OBS, int ORG, bool EXACT, bool PRE, class ACC>
+__device__ __forceinline__ void v3_group(const uint32_t *__restrict__ srcp, const uint32_t *__restrict__ cmpd, const uint32_t *__restrict__ cmpv,
+                                         const uint32_t *__restrict__ cur, const ACC &acc,
                                          uint32_t lut_lane_addr, float wscale, float wbias, double origin_tune,
                                          int seg_y0, int rows, int lane, int dy, int dx0)
 {
-    V3Group<NH, NG, OBS, ORG, ACC> g(cur, cmp, acc, lut_lane_addr, wscale, wbias, origin_tune, seg_y0, lane, dy, dx0);
+    V3Group<NH, NG, OBS, ORG, PRE, ACC> g(srcp, cmpd, cmpv, cur, acc, lut_lane_addr, wscale, wbias, origin_tune, seg_y0, lane, dy, dx0);
     g.template run<EXACT>(rows);
 }
 
@@ -423,15 +446,16 @@ __host__ __device__ inline bool v3_group_known(int ng, int ob, int org)
     return false;
 }
 
-template <int NH, int NW, int RS, bool TMEM, int NBUF>
+template <int NH, int NW, int RS, bool TMEM, int NBUF, bool PRE = false>
 __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_constant__ FusedParams fp)
 {
     constexpr int kThreads = NW * 32;
-    using L = V3Layout<NW, RS, TMEM, NBUF>;
+    using L = V3Layout<NW, RS, TMEM, NBUF, 1, PRE>;
     int pl = 0;
     while (pl + 1 < fp.nplanes && (int)blockIdx.x >= fp.first_tile[pl + 1]) pl++;
     const KernelParams &p = fp.k[pl];
     const CUtensorMap *maps = fp.maps[pl];
+    const CUtensorMap *maps_pre = fp.maps_pre[pl];       // prefilter variant only
     const int tile = (int)blockIdx.x - fp.first_tile[pl];
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *cur  = smem + L::kOffCur;
@@ -459,14 +483,19 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
     if (TMEM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0)
     {
-        mbar_expect_tx(bar, L::kTileBytes);
+        mbar_expect_tx(bar, L::kTileBytes * (PRE ? 2 : 1));
         for (int l = 0; l < L::kLoads; l++) tma_load_2d(cur + l * L::kBoxRows * kTilePW, &maps[0], gx, gy + l * L::kBoxRows, bar);
+        if (PRE)
+            for (int l = 0; l < L::kLoads; l++) tma_load_2d(smem + L::kOffPre0 + l * L::kBoxRows * kTilePW, &maps_pre[0], gx, gy + l * L::kBoxRows, bar);
         // frame 0 is compared with itself: the compare buffers are free, fill them with the following frames now
         for (int b = 0; b < NBUF && 1 + b < p.nf; b++)
         {
-            mbar_expect_tx(bar + 1 + b, L::kTileBytes);
+            mbar_expect_tx(bar + 1 + b, L::kTileBytes * (PRE ? 2 : 1));
             for (int l = 0; l < L::kLoads; l++)
                 tma_load_2d(smem + L::kOffCmp + b * L::kTileBytes + l * L::kBoxRows * kTilePW, &maps[1 + b], gx, gy + l * L::kBoxRows, bar + 1 + b);
+            if (PRE)
+                for (int l = 0; l < L::kLoads; l++)
+                    tma_load_2d(smem + L::kOffCmpPre + l * L::kBoxRows * kTilePW, &maps_pre[1 + b], gx, gy + l * L::kBoxRows, bar + 1 + b);
         }
     }
     for (int i = tid; i < kLutEntries * 32; i += kThreads)
@@ -507,6 +536,10 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
     // shared address of this lane's copy of table entry 0, pre-biased by -(0x47800000 << 7)
     const uint32_t lut_lane_addr = smem_u32(lut) + (uint32_t)lane * 4u - (0x47800000u << 7);
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur);
+    const uint32_t *pre0w = reinterpret_cast<const uint32_t *>(smem + L::kOffPre0);
+    // the source patches: the pre-denoised current tile -- or the plain one where the reference's pointer is stale
+    // (KernelParams::src_pre, the first frame of a stream)
+    const uint32_t *srcw = (PRE && p.src_pre != p.planes[0]) ? pre0w : cw;
     for (int f = 0; f < p.nf; f++)
     {
         const uint32_t *bw = cw;
@@ -516,6 +549,8 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
             mbar_wait(bar + 1 + buf, (uint32_t)(((f - 1) / NBUF) & 1));
             bw = reinterpret_cast<const uint32_t *>(smem + L::kOffCmp + buf * L::kTileBytes);
         }
+        // the tile the patch distances compare against: the pre-denoised twin of `bw` in the prefilter variant
+        const uint32_t *bd = !PRE ? bw : (f == 0 ? pre0w : reinterpret_cast<const uint32_t *>(smem + L::kOffCmpPre));
         if (rows > 0)
         {
             constexpr bool kExact = RS % (2 * NH + 1) == 0;             // then partial strips run to their end (rows beyond the plane are never stored)
@@ -529,7 +564,7 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
                     const int ob  = (12 + dx0) & 3;
 #define X(NG_, OB_, ORG_)                                                                                                   \
                     if (ng == NG_ && ob == OB_ && org == ORG_)                                                              \
-                        v3_group<NH, NG_, OB_, ORG_, kExact>(cw, bw, acc, lut_lane_addr, wscale, wbias, p.origin_tune, seg_y0, nrows, lane, dy, dx0); \
+                        v3_group<NH, NG_, OB_, ORG_, kExact, PRE>(srcw, bd, bw, cw, acc, lut_lane_addr, wscale, wbias, p.origin_tune, seg_y0, nrows, lane, dy, dx0); \
                     else
                     V3_GROUP_SHAPES(X)
 #undef X
@@ -544,9 +579,12 @@ __global__ void __launch_bounds__(NW * 32, 1) nlmeans_v3_kernel(const __grid_con
             if (tid == 0)
             {
                 fence_proxy_async();
-                mbar_expect_tx(bar + 1 + buf, L::kTileBytes);
+                mbar_expect_tx(bar + 1 + buf, L::kTileBytes * (PRE ? 2 : 1));
                 for (int l = 0; l < L::kLoads; l++)
                     tma_load_2d(smem + L::kOffCmp + buf * L::kTileBytes + l * L::kBoxRows * kTilePW, &maps[f + NBUF], gx, gy + l * L::kBoxRows, bar + 1 + buf);
+                if (PRE)
+                    for (int l = 0; l < L::kLoads; l++)
+                        tma_load_2d(smem + L::kOffCmpPre + l * L::kBoxRows * kTilePW, &maps_pre[f + NBUF], gx, gy + l * L::kBoxRows, bar + 1 + buf);
             }
         }
     }

@@ -102,3 +102,19 @@ def test_product_filter_library_carries_no_libhb_stand_in():
     sh = subprocess.run(["nm", "-D", str(shim)], capture_output=True, text=True).stdout
     assert " T hb_harness_run_chain" in sh and " T hb_bench_stream" in sh and " T hb_buffer_init" in sh
     assert "hbcu_" not in "\n".join(l for l in sh.splitlines() if " U " in l)      # the stand-in knows nothing of the product
+
+
+def test_filter_sources_compile_against_the_real_libhb_headers():
+    """INTEGRATION.md claims the *_cuda.c sources drop into a HandBrake tree unchanged: syntax-only compile against the
+    reference's own handbrake/*.h (tools/check_real_headers.sh; libav/jansson are type-only stubs).  The only names the
+    real tree lacks are the integration patch itself: HBCU_DEVICE and the three fifo.c hooks."""
+    import subprocess
+    ref = Path("/root/reference/libhb")
+    if not (ref / "handbrake" / "internal.h").exists():
+        pytest.skip("no reference tree on this machine")
+    r = subprocess.run(["bash", str(REPO / "tools" / "check_real_headers.sh"), str(ref)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if ": errors=" in l]
+    assert len(lines) >= 10 and all("errors=0 other_warnings=0" in l for l in lines), r.stdout
+    hooks = set(re.findall(r"'(hb_shim_[a-z_]+)'", r.stdout))
+    assert hooks == {"hb_shim_set_frame_allocator", "hb_shim_set_device_release", "hb_shim_set_device_retain"}

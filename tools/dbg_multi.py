@@ -4,16 +4,16 @@ import handbrake_b200
 from handbrake_b200 import synth
 flt = handbrake_b200.filters()
 F = synth.PIX_FMT_YUV420P
-w, h, n = 200, 120, 9
-clip = synth.progressive_clip(F, w, h, n, seed=31)
-for pre in (1, 2, 4, 16, 256):
-  for nf in (2, 3):
-    for blk in (2, 3, 4):
-        s = f"y-strength=6:y-prefilter={pre}:y-frame-count={nf}"
-        one = flt.run("hb_filter_nlmeans_cuda", s, clip, F, w, h)
-        many = flt.run("hb_filter_nlmeans_cuda", s + f":devices=0,0:block={blk}", clip, F, w, h)
-        d = (one.frames != many.frames)
-        per = [int(x.sum()) for x in d]
-        # per plane
-        ysz = w*h
-        print(f"pre={pre} nf={nf} block={blk} differing bytes per frame {per}  luma-only={[int(x[:ysz].sum()) for x in d]}", flush=True)
+w, h = 200, 120
+for n in (7, 9):
+    clip = synth.progressive_clip(F, w, h, n, seed=31)
+    for s, m in (("y-strength=6:y-prefilter=1:y-frame-count=2", "devices=0,0:block=2"), ("y-strength=6:y-frame-count=2", "devices=0,0:block=2"),
+                 ("y-strength=6:y-prefilter=1:y-frame-count=2", "threads=4")):
+        ref = flt.run("hb_filter_nlmeans_cuda", s, clip, F, w, h).frames
+        bad = {}
+        for it in range(40):
+            many = flt.run("hb_filter_nlmeans_cuda", s + ":" + m, clip, F, w, h)
+            d = (ref != many.frames)
+            key = tuple(int(i) for i in np.argwhere(d.any(axis=1)).ravel())
+            bad[key] = bad.get(key, 0) + 1
+        print(f"n={n} {s} + {m}: differing-frame sets over 40 runs: {bad}", flush=True)

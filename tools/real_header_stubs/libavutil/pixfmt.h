@@ -1,0 +1,1 @@
+#include "av_stub.h"
