@@ -15,6 +15,7 @@
 //   * the field stride handed to the metric functions is stride << 1 bytes at 8 bit and stride bytes, used as uint16
 //     elements, above: two picture lines either way (:239, :1049).
 #include "hbcu_common.h"
+#include "hbcu_frames.h"
 #include "../../include/hbcu.h"
 
 #include <cstdlib>
@@ -418,6 +419,43 @@ int hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const plan
         }
     HBCU_CHECK(cudaStreamSynchronize(h->s));
     return 0;
+}
+
+static bool frame_matches(const hbcu_detelecine_t *h, const hbcu_frame_t *f)
+{
+    if (f == nullptr || f->device != h->cfg.device) return false;
+    for (int p = 0; p < 3; p++)
+        if (f->rows[p] != h->pl[p].h || f->row_bytes[p] > h->pl[p].pitch_bytes) return false;
+    return true;
+}
+
+int hbcu_detelecine_upload_frame(hbcu_detelecine_t *h, int picture, hbcu_frame_t *in)
+{
+    if (h == nullptr || bad_picture(h, picture) || !frame_matches(h, in)) { set_error("detelecine_upload_frame: bad argument or frame geometry"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    if (hbcu::frame_begin_read(in, h->s) != 0) return -1;
+    for (int p = 0; p < 3; p++)
+    {
+        // hb_image_copy_plane: the shorter of the two strides per line
+        const int row = in->stride[p] < h->pl[p].pitch_bytes ? in->stride[p] : h->pl[p].pitch_bytes;
+        HBCU_CHECK(cudaMemcpy2DAsync(picture_plane(h, picture, p), h->pl[p].pitch_bytes, in->plane[p], in->stride[p], row, h->pl[p].h,
+                                     cudaMemcpyDeviceToDevice, h->s));
+    }
+    return hbcu::frame_end_read(in, h->s);
+}
+
+int hbcu_detelecine_download_frame(hbcu_detelecine_t *h, int picture, hbcu_frame_t *out)
+{
+    if (h == nullptr || bad_picture(h, picture) || !frame_matches(h, out)) { set_error("detelecine_download_frame: bad argument or frame geometry"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    if (hbcu::frame_begin_write(out, h->s) != 0) return -1;
+    for (int p = 0; p < 3; p++)
+    {
+        const int row = out->stride[p] < h->pl[p].pitch_bytes ? out->stride[p] : h->pl[p].pitch_bytes;
+        HBCU_CHECK(cudaMemcpy2DAsync(out->plane[p], out->stride[p], picture_plane(h, picture, p), h->pl[p].pitch_bytes, row, h->pl[p].h,
+                                     cudaMemcpyDeviceToDevice, h->s));
+    }
+    return hbcu::frame_end_write(out, h->s);      // no host wait: the consumer orders itself behind the frame's `ready`
 }
 
 int hbcu_detelecine_mark(hbcu_detelecine_t *h, int which)

@@ -43,6 +43,7 @@ using hbcu::set_error;
 
 constexpr int kBorder    = 16;    // ((n+2)/2+15)/16*16 for every preset (nlmeans.c:529)
 constexpr int kMaxFrames = 32;    // NLMEANS_FRAMES_MAX
+constexpr int kMaxDevices = 64;   // per-device launch configuration flags (power of two)
 constexpr int kTileW     = 128;
 constexpr int kHalo      = 8;     // vertical halo of the shared-memory tiles (>= n/2 + r/2)
 // Horizontal halo.  Measured on B200 (tools/tma_test.cu): cp.async.bulk.tensor raises
@@ -1525,7 +1526,12 @@ template <typename PIX, int NH, int TH>
 int launch_tiled(const TiledParams &kp, cudaStream_t st)
 {
     using L = TileLayout<PIX, TH>;
-    static bool configured = false;
+    // function attributes live in the device's context: one flag per device (a second GPU would otherwise launch with
+    // the default 48 KB limit -- 'invalid argument'; found by the first run of devices=0,1)
+    static bool configured_on[kMaxDevices] = {};
+    int dev_ = 0;
+    HBCU_CHECK(cudaGetDevice(&dev_));
+    bool &configured = configured_on[dev_ & (kMaxDevices - 1)];
     if (!configured)
     {
         HBCU_CHECK(cudaFuncSetAttribute(nlmeans_tiled_kernel<PIX, NH, TH>,
@@ -1542,7 +1548,12 @@ template <int NH, int TH, int NW, bool DP4A>
 int launch_fast8(FusedParams &fp, cudaStream_t st)
 {
     using L = FastLayout<TH>;
-    static bool configured = false;
+    // function attributes live in the device's context: one flag per device (a second GPU would otherwise launch with
+    // the default 48 KB limit -- 'invalid argument'; found by the first run of devices=0,1)
+    static bool configured_on[kMaxDevices] = {};
+    int dev_ = 0;
+    HBCU_CHECK(cudaGetDevice(&dev_));
+    bool &configured = configured_on[dev_ & (kMaxDevices - 1)];
     if (!configured)
     {
         HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast8_kernel<NH, TH, NW, DP4A>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -1565,7 +1576,12 @@ template <int NH, int TH, int NW>
 int launch_fast16(FusedParams &fp, cudaStream_t st)
 {
     using L = Fast16Layout<TH>;
-    static bool configured = false;
+    // function attributes live in the device's context: one flag per device (a second GPU would otherwise launch with
+    // the default 48 KB limit -- 'invalid argument'; found by the first run of devices=0,1)
+    static bool configured_on[kMaxDevices] = {};
+    int dev_ = 0;
+    HBCU_CHECK(cudaGetDevice(&dev_));
+    bool &configured = configured_on[dev_ & (kMaxDevices - 1)];
     if (!configured)
     {
         HBCU_CHECK(cudaFuncSetAttribute(nlmeans_fast16_kernel<NH, TH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -1610,7 +1626,12 @@ template <int NH, int NW, int RS, bool TMEM, int NBUF>
 int launch_v3(FusedParams &fp, cudaStream_t st)
 {
     using L = V3Layout<NW, RS, TMEM, NBUF>;
-    static bool configured = false;
+    // function attributes live in the device's context: one flag per device (a second GPU would otherwise launch with
+    // the default 48 KB limit -- 'invalid argument'; found by the first run of devices=0,1)
+    static bool configured_on[kMaxDevices] = {};
+    int dev_ = 0;
+    HBCU_CHECK(cudaGetDevice(&dev_));
+    bool &configured = configured_on[dev_ & (kMaxDevices - 1)];
     if (!configured)
     {
         HBCU_CHECK(cudaFuncSetAttribute(nlmeans_v3_kernel<NH, NW, RS, TMEM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -1633,7 +1654,12 @@ template <int NH, int NW, int RS, bool TMEM, int NBUF>
 int launch_v3w(FusedParams &fp, cudaStream_t st)
 {
     using L = V3Layout<NW, RS, TMEM, NBUF, 2>;
-    static bool configured = false;
+    // function attributes live in the device's context: one flag per device (a second GPU would otherwise launch with
+    // the default 48 KB limit -- 'invalid argument'; found by the first run of devices=0,1)
+    static bool configured_on[kMaxDevices] = {};
+    int dev_ = 0;
+    HBCU_CHECK(cudaGetDevice(&dev_));
+    bool &configured = configured_on[dev_ & (kMaxDevices - 1)];
     if (!configured)
     {
         HBCU_CHECK(cudaFuncSetAttribute(nlmeans_v3w_kernel<NH, NW, RS, TMEM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -1658,7 +1684,12 @@ int launch_v3_pre(FusedParams &fp, cudaStream_t st)
 {
     constexpr int NW = 12, RS = 18;
     using L = V3Layout<NW, RS, true, 1, 1, true>;
-    static bool configured = false;
+    // function attributes live in the device's context: one flag per device (a second GPU would otherwise launch with
+    // the default 48 KB limit -- 'invalid argument'; found by the first run of devices=0,1)
+    static bool configured_on[kMaxDevices] = {};
+    int dev_ = 0;
+    HBCU_CHECK(cudaGetDevice(&dev_));
+    bool &configured = configured_on[dev_ & (kMaxDevices - 1)];
     if (!configured)
     {
         HBCU_CHECK(cudaFuncSetAttribute(nlmeans_v3_kernel<NH, NW, RS, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));

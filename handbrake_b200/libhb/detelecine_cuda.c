@@ -13,6 +13,7 @@
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
+#include "hbcu_device_frames.h"
 
 #define DT_PICTURES    10      /* pullup_init_context: nbuffers < 10 -> 10 (:604-607); nothing ever raises it */
 #define DT_MAX_FIELDS  64      /* nodes of the field ring: 9 to start with (:623), one more whenever it is full (:285-296) */
@@ -49,6 +50,7 @@ struct hb_filter_private_s
     int results[4 * DT_MAX_FIELDS];
     int unsynced;               /* an upload from a host buffer may still be in flight */
     int failed;
+    int device, device_out;     /* device_out: woven frames leave as HBCU_DEVICE buffers (hw_pix_fmt == AV_PIX_FMT_CUDA) */
     hb_filter_init_t input, output;
 };
 
@@ -382,13 +384,9 @@ static int detelecine_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *in
     }
     filter->private_data = pv;
     pv->input = *init;
-    if (init->hw_pix_fmt == AV_PIX_FMT_CUDA)
-    {
-        /* pictures arrive in host buffers and leave in host buffers for now: inside a device-resident
-         * chain the filter has to sit before hb_filter_hbcu_upload or after hb_filter_hbcu_download */
-        hb_error("detelecine(cuda): device-resident input is not supported yet");
-        goto fail;
-    }
+    /* inside a device-resident chain (hw_pix_fmt == AV_PIX_FMT_CUDA) pictures arrive in and leave in HBCU_DEVICE buffers;
+     * either kind is accepted per buffer */
+    pv->device_out = hbcu_init_wants_device_output(init);
 
     /* :1025-1047: junk margins of at least one 8-sample column and four line pairs */
     int top = 4, bottom = 4, left = 1, right = 1, plane = 0;
@@ -424,6 +422,7 @@ static int detelecine_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *in
     cfg.chroma_shift_h = desc->log2_chroma_h;
     const char *dev_env = getenv("HBCU_DEVICE");
     cfg.device         = dev_env != NULL ? atoi(dev_env) : 0;
+    pv->device         = cfg.device;
     cfg.pictures       = DT_PICTURES;
     cfg.fields         = DT_MAX_FIELDS;
     cfg.results        = 2 * DT_MAX_FIELDS;
@@ -480,11 +479,6 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
         return HB_FILTER_DONE;
     }
     if (pv->failed) return HB_FILTER_FAILED;
-    if (in->storage_type == HBCU_DEVICE)
-    {
-        hb_error("detelecine(cuda): got a device-resident buffer; see init");
-        return HB_FILTER_FAILED;
-    }
 
     const int picture = get_whole_picture(pv);
     if (picture == DT_NONE)
@@ -494,8 +488,9 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
     }
     const void *planes[3] = { in->plane[0].data, in->plane[1].data, in->plane[2].data };
     const int strides[3] = { in->plane[0].stride, in->plane[1].stride, in->plane[2].stride };
-    GPU(hbcu_detelecine_upload(pv->gpu, picture, planes, strides));
-    pv->unsynced = 1;
+    if (hbcu_buffer_frame(in) != NULL) GPU(hbcu_detelecine_upload_frame(pv->gpu, picture, hbcu_buffer_frame(in)));
+    else                               GPU(hbcu_detelecine_upload(pv->gpu, picture, planes, strides));
+    pv->unsynced = hbcu_buffer_frame(in) == NULL;       /* a device frame's copy is ordered by the frame's own events */
 
     /* field order: the TFF flag, else bottom field first unless the user says otherwise (:1166-1184) */
     int parity = 1;
@@ -550,7 +545,8 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
         return leave(pv, HB_FILTER_FAILED);
     }
 
-    hb_buffer_t *out = hb_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height);
+    hb_buffer_t *out = pv->device_out ? hbcu_device_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height, pv->device)
+                                      : hb_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height);
     if (out == NULL)
     {
         release_frame(pv, frame);
@@ -562,10 +558,23 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
     out->f.color_range     = pv->output.color_range;
     out->f.chroma_location = pv->output.chroma_location;
 
-    void *oplanes[3] = { out->plane[0].data, out->plane[1].data, out->plane[2].data };
-    const int ostrides[3] = { out->plane[0].stride, out->plane[1].stride, out->plane[2].stride };
-    GPU(hbcu_detelecine_download(pv->gpu, frame->picture, oplanes, ostrides));
-    pv->unsynced = 0;
+    if (pv->device_out)
+    {
+        /* stays in HBM: a device copy queued behind the weave, the consumer orders itself behind the frame's event */
+        GPU(hbcu_detelecine_download_frame(pv->gpu, frame->picture, hbcu_buffer_frame(out)));
+        if (pv->unsynced)
+        {
+            GPU(hbcu_detelecine_fetch(pv->gpu, NULL, 0));           /* a HOST input buffer goes back to its owner now */
+            pv->unsynced = 0;
+        }
+    }
+    else
+    {
+        void *oplanes[3] = { out->plane[0].data, out->plane[1].data, out->plane[2].data };
+        const int ostrides[3] = { out->plane[0].stride, out->plane[1].stride, out->plane[2].stride };
+        GPU(hbcu_detelecine_download(pv->gpu, frame->picture, oplanes, ostrides));
+        pv->unsynced = 0;
+    }
     release_frame(pv, frame);
     if (pv->failed)
     {

@@ -438,6 +438,11 @@ int  hbcu_detelecine_fetch(hbcu_detelecine_t *h, int *dst, int nslots);
 int  hbcu_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_picture, int parity);
 /* picture -> host planes (plane height x stride bytes each, as the reference's memcpy of size[p], :1250-1252); waits */
 int  hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3]);
+/* device-resident chain: the picture arrives in / leaves in an hbcu_frame_t -- a device-to-device copy on
+ * the handle's stream, ordered against the frame's producer and readers through its events; nothing waits on the host
+ * (the frame twins of upload / download; detelecine.c:1116-1277 is the work() these serve) */
+int  hbcu_detelecine_upload_frame(hbcu_detelecine_t *h, int picture, hbcu_frame_t *in);
+int  hbcu_detelecine_download_frame(hbcu_detelecine_t *h, int picture, hbcu_frame_t *out);
 /* benchmark hooks as for the other handles */
 int  hbcu_detelecine_mark(hbcu_detelecine_t *h, int which);
 int  hbcu_detelecine_elapsed_ms(hbcu_detelecine_t *h, float *ms);

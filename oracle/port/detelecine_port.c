@@ -206,5 +206,17 @@ int oracle_hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *con
     return 0;
 }
 
+/* device frames: see hostlogic_frames.c */
+const void *const *oracle_hostlogic_frame_planes(const hbcu_frame_t *f);
+const int *oracle_hostlogic_frame_strides(const hbcu_frame_t *f);
+int oracle_hbcu_detelecine_upload_frame(hbcu_detelecine_t *h, int picture, hbcu_frame_t *in)
+{
+    return oracle_hbcu_detelecine_upload(h, picture, oracle_hostlogic_frame_planes(in), oracle_hostlogic_frame_strides(in));
+}
+int oracle_hbcu_detelecine_download_frame(hbcu_detelecine_t *h, int picture, hbcu_frame_t *out)
+{
+    return oracle_hbcu_detelecine_download(h, picture, (void *const *)oracle_hostlogic_frame_planes(out), oracle_hostlogic_frame_strides(out));
+}
+
 int oracle_hbcu_detelecine_mark(hbcu_detelecine_t *h, int which) { (void)h; (void)which; return 0; }
 int oracle_hbcu_detelecine_elapsed_ms(hbcu_detelecine_t *h, float *ms) { (void)h; *ms = 0.f; return 0; }

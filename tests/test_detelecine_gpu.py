@@ -71,3 +71,21 @@ def test_detelecine_too_small_is_refused(cuda_filters):
     clip = synth.progressive_clip(FMT[8], 32, 16, 3)
     g = cuda_filters.run("hb_filter_detelecine_cuda", None, clip, FMT[8], 32, 16)
     assert g.init_failed == 1
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_detelecine_device_resident(ref, cuda_filters, depth):
+    """pullup inside a device-resident chain: device frames in, device frames out (hbcu_detelecine_upload_frame /
+    download_frame), bit-identical to the reference's host chain; nothing leaks"""
+    import ctypes as C
+    from handbrake_b200 import LIBHBCU
+    UP, DOWN = "hb_filter_hbcu_upload", "hb_filter_hbcu_download"
+    w, h = 720, 480
+    clip, flags = synth.telecined_clip(FMT[depth], w, h, 12, seed=8, noise=2)
+    r = ref.run(["hb_filter_detelecine", "hb_filter_lapsharp_mt"], [None, "y-strength=0.3"], clip, FMT[depth], w, h, flags=flags)
+    g = cuda_filters.run([UP, "hb_filter_detelecine_cuda", "hb_filter_lapsharp_cuda", DOWN], [None, None, "y-strength=0.3", None],
+                         clip, FMT[depth], w, h, flags=flags)
+    compare(r, g)
+    core = C.CDLL(str(LIBHBCU))
+    core.hbcu_frames_alive.restype = C.c_long
+    assert core.hbcu_frames_alive() == 0 and cuda_filters.buffers_alive() == 0
