@@ -30,6 +30,44 @@ int hbcu_env_device(void)
     return dev_env != NULL ? atoi(dev_env) : 0;
 }
 
+static int parse_device_list(const char *str, int *out)
+{
+    int n = 0;
+    if (str == NULL) return 0;
+    while (*str != '\0' && n < HBCU_MAX_DEVICES)
+    {
+        char *end = NULL;
+        const long v = strtol(str, &end, 10);
+        if (end == str || v < 0) return -1;
+        out[n++] = (int)v;
+        str = end;
+        if (*str == ',' || *str == '+') str++;
+        else if (*str != '\0') return -1;
+    }
+    return n;
+}
+
+int hbcu_settings_devices(const hb_dict_t *settings, int devices[HBCU_MAX_DEVICES])
+{
+    int n = 0;
+    char *list = NULL;
+    if (settings != NULL && hb_dict_extract_string(&list, settings, "devices"))
+    {
+        n = parse_device_list(list, devices);
+        free(list);
+        if (n <= 0) return -1;
+        return n;
+    }
+    n = parse_device_list(getenv("HBCU_DEVICES"), devices);
+    if (n < 0) return -1;
+    if (n == 0)
+    {
+        devices[0] = hbcu_env_device();
+        n = 1;
+    }
+    return n;
+}
+
 int hbcu_init_wants_device_output(const hb_filter_init_t *init)
 {
     return init != NULL && init->hw_pix_fmt == AV_PIX_FMT_CUDA;

@@ -26,5 +26,10 @@ hb_buffer_t  *hbcu_wrap_cuda_frame(int pix_fmt, int width, int height, int devic
  * a hardware-frame pipeline: nvenc_common.c:329-336, hwaccel.c:15-60) */
 int           hbcu_init_wants_device_output(const hb_filter_init_t *init);
 int           hbcu_env_device(void);
+/* the devices a frame-parallel filter deals its stream to: setting `devices=0,1,..` (not part of the reference's templates:
+ * a front end that validates settings appends the key), else HBCU_DEVICES, else the one device of
+ * HBCU_DEVICE.  Returns the count (>= 1), or -1 for a malformed list.  An ordinal may repeat (two handles on one GPU). */
+#define HBCU_MAX_DEVICES 16
+int           hbcu_settings_devices(const hb_dict_t *settings, int devices[HBCU_MAX_DEVICES]);
 
 #endif

@@ -15,17 +15,19 @@
 #define LAPSHARP_STRENGTH_DEFAULT 0.2
 #define LAPSHARP_KERNEL_DEFAULT   2
 #define LAPSHARP_KERNELS          4
-#define LAPSHARP_MAX_PENDING      16
+#define LAPSHARP_MAX_PENDING      64
 
 typedef struct
 {
     hb_buffer_t *in, *out;
     int64_t      ticket;
+    int          dev;
 } lapsharp_pending_t;
 
 struct hb_filter_private_s
 {
-    hbcu_lapsharp_t *gpu;
+    hbcu_lapsharp_t *gpu[HBCU_MAX_DEVICES];    /* frames are independent: frame t goes to device t % ndev (mt_frame_filter.c:169-237) */
+    int ndev, devices[HBCU_MAX_DEVICES];
     lapsharp_pending_t pending[LAPSHARP_MAX_PENDING];
     int head, count, inflight_max;
     int64_t next_ticket;
@@ -112,20 +114,31 @@ static int lapsharp_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init
     cfg.depth          = desc->comp[0].depth;
     cfg.chroma_shift_w = desc->log2_chroma_w;
     cfg.chroma_shift_h = desc->log2_chroma_h;
-    cfg.device         = hbcu_env_device();
-    pv->device         = cfg.device;
+    pv->ndev = hbcu_settings_devices(filter->settings, pv->devices);
     pv->device_out     = hbcu_init_wants_device_output(init);
-    pv->inflight_max   = 6;
-    cfg.slots          = pv->inflight_max + 2;
-    if (hbcu_lapsharp_create(&pv->gpu, &cfg) != 0)
+    if (pv->ndev < 1 || (pv->ndev > 1 && pv->device_out))
     {
-        hb_error("lapsharp(cuda): %s", hbcu_last_error());
+        hb_error(pv->ndev < 1 ? "lapsharp(cuda): bad `devices` setting" : "lapsharp(cuda): device-resident output needs a single device");
         goto fail;
+    }
+    pv->device         = pv->devices[0];
+    pv->inflight_max   = 6 * pv->ndev < LAPSHARP_MAX_PENDING - 2 ? 6 * pv->ndev : LAPSHARP_MAX_PENDING - 2;
+    cfg.slots          = 6 + 2;
+    for (int d = 0; d < pv->ndev; d++)
+    {
+        cfg.device = pv->devices[d];
+        if (hbcu_lapsharp_create(&pv->gpu[d], &cfg) != 0)
+        {
+            hb_error("lapsharp(cuda): %s", hbcu_last_error());
+            goto fail;
+        }
     }
     pv->output = *init;
     return 0;
 
 fail:
+    for (int d = 0; d < HBCU_MAX_DEVICES; d++)
+        if (pv->gpu[d] != NULL) hbcu_lapsharp_destroy(pv->gpu[d]);
     free(pv);
     filter->private_data = NULL;
     return -1;
@@ -135,7 +148,8 @@ static void lapsharp_cuda_close(hb_filter_object_t *filter)
 {
     hb_filter_private_t *pv = filter->private_data;
     if (pv == NULL) return;
-    if (pv->gpu != NULL) hbcu_lapsharp_destroy(pv->gpu);
+    for (int d = 0; d < pv->ndev; d++)
+        if (pv->gpu[d] != NULL) hbcu_lapsharp_destroy(pv->gpu[d]);
     for (int i = 0; i < pv->count; i++)
     {
         lapsharp_pending_t *p = &pv->pending[(pv->head + i) % LAPSHARP_MAX_PENDING];
@@ -157,11 +171,11 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int all)
         }
         else if (all || pv->count > pv->inflight_max)
         {
-            if (hbcu_lapsharp_wait(pv->gpu, p->ticket) != 0) goto gpu_error;
+            if (hbcu_lapsharp_wait(pv->gpu[p->dev], p->ticket) != 0) goto gpu_error;
         }
         else
         {
-            const int done = hbcu_lapsharp_poll(pv->gpu, p->ticket);
+            const int done = hbcu_lapsharp_poll(pv->gpu[p->dev], p->ticket);
             if (done < 0) goto gpu_error;
             if (done == 0) break;
         }
@@ -221,7 +235,15 @@ static int lapsharp_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, 
         op[c] = out->plane[c].data; os[c] = out->plane[c].stride;
     }
     const int64_t ticket = pv->next_ticket++;
-    if (hbcu_lapsharp_filter_frames(pv->gpu, ticket, fin, ip, is, hbcu_buffer_frame(out), op, os) != 0)
+    const int dev = (int)(ticket % pv->ndev);
+    if (fin != NULL && pv->ndev > 1)
+    {
+        hb_error("lapsharp(cuda): device-resident input needs a single device");
+        hb_buffer_close(&in);
+        hb_buffer_close(&out);
+        return HB_FILTER_FAILED;
+    }
+    if (hbcu_lapsharp_filter_frames(pv->gpu[dev], ticket, fin, ip, is, hbcu_buffer_frame(out), op, os) != 0)
     {
         hb_error("lapsharp(cuda): %s", hbcu_last_error());
         hb_buffer_close(&in);
@@ -232,6 +254,7 @@ static int lapsharp_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, 
     p->in = in;
     p->out = out;
     p->ticket = ticket;
+    p->dev = dev;
     pv->count++;
 
     if (harvest(pv, &list, 0) != 0)

@@ -40,7 +40,7 @@
 #define NLMEANS_EXPSIZE             HBCU_NLMEANS_EXPSIZE
 
 #define NLM_MAX_INFLIGHT 16
-#define NLM_MAX_DEVICES  16
+#define NLM_MAX_DEVICES  HBCU_MAX_DEVICES
 #define NLM_BLOCK_DEFAULT 8
 
 typedef struct
@@ -227,24 +227,6 @@ int hb_nlmeans_cuda_build_config(const hb_dict_t *dict, int pix_fmt, int width, 
     return 0;
 }
 
-/* "0,1,2" -> ordinals; returns the count (0: not given / malformed) */
-static int parse_devices(const char *str, int *out, int max)
-{
-    int n = 0;
-    if (str == NULL) return 0;
-    while (*str != '\0' && n < max)
-    {
-        char *end = NULL;
-        const long v = strtol(str, &end, 10);
-        if (end == str || v < 0) return 0;
-        out[n++] = (int)v;
-        str = end;
-        if (*str == ',' || *str == '+') str++;
-        else if (*str != '\0') return 0;
-    }
-    return n;
-}
-
 static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
 {
     hb_filter_private_t *pv = calloc(1, sizeof(*pv));
@@ -267,28 +249,13 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
 
     /* the devices the stream is dealt to: setting `devices` (not part of the reference's template: a front end that
      * validates settings exposes it by appending the key), else HBCU_DEVICES, else the one device */
-    pv->ndev = 0;
     pv->block = NLM_BLOCK_DEFAULT;
-    if (filter->settings != NULL)
+    if (filter->settings != NULL) hb_dict_extract_int(&pv->block, filter->settings, "block");
+    pv->ndev = hbcu_settings_devices(filter->settings, pv->devices);       /* `devices` setting, HBCU_DEVICES, or the one device */
+    if (pv->ndev < 1)
     {
-        char *devs = NULL;
-        if (hb_dict_extract_string(&devs, filter->settings, "devices"))
-        {
-            pv->ndev = parse_devices(devs, pv->devices, NLM_MAX_DEVICES);
-            free(devs);
-            if (pv->ndev == 0)
-            {
-                hb_error("nlmeans(cuda): bad `devices` setting");
-                goto fail;
-            }
-        }
-        hb_dict_extract_int(&pv->block, filter->settings, "block");
-    }
-    if (pv->ndev == 0) pv->ndev = parse_devices(getenv("HBCU_DEVICES"), pv->devices, NLM_MAX_DEVICES);
-    if (pv->ndev == 0)
-    {
-        pv->ndev = 1;
-        pv->devices[0] = cfg.device;
+        hb_error("nlmeans(cuda): bad `devices` setting");
+        goto fail;
     }
     if (getenv("HBCU_BLOCK") != NULL && pv->block == NLM_BLOCK_DEFAULT) pv->block = atoi(getenv("HBCU_BLOCK"));
     /* a block's look-ahead window must end inside the NEXT block */

@@ -14,17 +14,19 @@
 #define UNSHARP_SIZE_DEFAULT            7
 #define UNSHARP_SIZE_MIN                3
 #define UNSHARP_SIZE_MAX                15
-#define UNSHARP_MAX_PENDING             16
+#define UNSHARP_MAX_PENDING             64
 
 typedef struct
 {
     hb_buffer_t *in, *out;
     int64_t      ticket;
+    int          dev;
 } unsharp_pending_t;
 
 struct hb_filter_private_s
 {
-    hbcu_unsharp_t *gpu;
+    hbcu_unsharp_t *gpu[HBCU_MAX_DEVICES];     /* frames are independent: frame t goes to device t % ndev (mt_frame_filter.c:169-237) */
+    int ndev, devices[HBCU_MAX_DEVICES];
     unsharp_pending_t pending[UNSHARP_MAX_PENDING];
     int head, count, inflight_max;
     int64_t next_ticket;
@@ -127,20 +129,31 @@ static int unsharp_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     cfg.chroma_shift_w = desc->log2_chroma_w;
     cfg.chroma_shift_h = desc->log2_chroma_h;
     cfg.smooth         = pv->smooth;
-    cfg.device         = hbcu_env_device();
-    pv->device         = cfg.device;
+    pv->ndev           = hbcu_settings_devices(filter->settings, pv->devices);
     pv->device_out     = hbcu_init_wants_device_output(init);
-    pv->inflight_max   = 6;
-    cfg.slots          = pv->inflight_max + 2;
-    if (hbcu_unsharp_create(&pv->gpu, &cfg) != 0)
+    if (pv->ndev < 1 || (pv->ndev > 1 && pv->device_out))
     {
-        hb_error("%s(cuda): %s", filter->short_name, hbcu_last_error());
+        hb_error("%s(cuda): %s", filter->short_name, pv->ndev < 1 ? "bad `devices` setting" : "device-resident output needs a single device");
         goto fail;
+    }
+    pv->device         = pv->devices[0];
+    pv->inflight_max   = 6 * pv->ndev < UNSHARP_MAX_PENDING - 2 ? 6 * pv->ndev : UNSHARP_MAX_PENDING - 2;
+    cfg.slots          = 6 + 2;
+    for (int d = 0; d < pv->ndev; d++)
+    {
+        cfg.device = pv->devices[d];
+        if (hbcu_unsharp_create(&pv->gpu[d], &cfg) != 0)
+        {
+            hb_error("%s(cuda): %s", filter->short_name, hbcu_last_error());
+            goto fail;
+        }
     }
     pv->output = *init;
     return 0;
 
 fail:
+    for (int d = 0; d < HBCU_MAX_DEVICES; d++)
+        if (pv->gpu[d] != NULL) hbcu_unsharp_destroy(pv->gpu[d]);
     free(pv);
     filter->private_data = NULL;
     return -1;
@@ -150,7 +163,8 @@ static void unsharp_cuda_close(hb_filter_object_t *filter)
 {
     hb_filter_private_t *pv = filter->private_data;
     if (pv == NULL) return;
-    if (pv->gpu != NULL) hbcu_unsharp_destroy(pv->gpu);      /* waits for the copies in flight */
+    for (int d = 0; d < pv->ndev; d++)
+        if (pv->gpu[d] != NULL) hbcu_unsharp_destroy(pv->gpu[d]);      /* waits for the copies in flight */
     for (int i = 0; i < pv->count; i++)
     {
         unsharp_pending_t *p = &pv->pending[(pv->head + i) % UNSHARP_MAX_PENDING];
@@ -172,11 +186,11 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int all)
         }
         else if (all || pv->count > pv->inflight_max)
         {
-            if (hbcu_unsharp_wait(pv->gpu, p->ticket) != 0) goto gpu_error;
+            if (hbcu_unsharp_wait(pv->gpu[p->dev], p->ticket) != 0) goto gpu_error;
         }
         else
         {
-            const int done = hbcu_unsharp_poll(pv->gpu, p->ticket);
+            const int done = hbcu_unsharp_poll(pv->gpu[p->dev], p->ticket);
             if (done < 0) goto gpu_error;
             if (done == 0) break;
         }
@@ -232,7 +246,15 @@ static int unsharp_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
         op[c] = out->plane[c].data; os[c] = out->plane[c].stride;
     }
     const int64_t ticket = pv->next_ticket++;
-    if (hbcu_unsharp_filter_frames(pv->gpu, ticket, hbcu_buffer_frame(in), ip, is, hbcu_buffer_frame(out), op, os) != 0)
+    const int dev = (int)(ticket % pv->ndev);
+    if (hbcu_buffer_frame(in) != NULL && pv->ndev > 1)
+    {
+        hb_error("%s(cuda): device-resident input needs a single device", filter->short_name);
+        hb_buffer_close(&in);
+        hb_buffer_close(&out);
+        return HB_FILTER_FAILED;
+    }
+    if (hbcu_unsharp_filter_frames(pv->gpu[dev], ticket, hbcu_buffer_frame(in), ip, is, hbcu_buffer_frame(out), op, os) != 0)
     {
         hb_error("%s(cuda): %s", filter->short_name, hbcu_last_error());
         hb_buffer_close(&in);
@@ -243,6 +265,7 @@ static int unsharp_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
     p->in = in;
     p->out = out;
     p->ticket = ticket;
+    p->dev = dev;
     pv->count++;
 
     if (harvest(pv, &list, 0) != 0)

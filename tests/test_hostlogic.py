@@ -373,3 +373,20 @@ def test_wrapped_decoder_surfaces_through_a_device_chain(ref, hostlogic, monkeyp
     same_stream(r, g)
     assert hostlogic.lib.hbcu_test_surfaces_returned() - before == n
     assert hostlogic.buffers_alive() == 0
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0", "0,0,0,0,0"])
+def test_frame_parallel_filters_dealt_over_devices(ref, hostlogic, devices):
+    """the mt_frame clients (lapsharp, unsharp, chroma smooth: frames are independent, mt_frame_filter.c:169-237) with
+    `devices=`: frame t goes to handle t % n, outputs leave in stream order; == the reference"""
+    w, h, n = 96, 64, 17
+    clip = synth.progressive_clip(FMT[8], w, h, n, seed=21)
+    for ref_name, name, settings in (("hb_filter_lapsharp_mt", "hb_filter_lapsharp_cuda", "y-strength=0.3:y-kernel=isolap"),
+                                     ("hb_filter_unsharp_mt", "hb_filter_unsharp_cuda", "y-strength=0.5:y-size=5"),
+                                     ("hb_filter_chroma_smooth_mt", "hb_filter_chroma_smooth_cuda", "cb-strength=0.8:cb-size=5")):
+        r = ref.run(ref_name, settings, clip, FMT[8], w, h)
+        g = hostlogic.run(name, settings + ":devices=" + devices, clip, FMT[8], w, h)
+        same_stream(r, g)
+    bad = hostlogic.run("hb_filter_lapsharp_cuda", "y-strength=0.3:devices=0,,1", clip, FMT[8], w, h)
+    assert bad.init_failed
+    assert hostlogic.buffers_alive() == 0

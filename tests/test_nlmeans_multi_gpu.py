@@ -73,8 +73,22 @@ def test_two_gpus_equal_one(ref, cuda_filters, settings, block):
     one = cuda_filters.run("hb_filter_nlmeans_cuda", settings, clip, FMT8, w, h)
     two = cuda_filters.run("hb_filter_nlmeans_cuda", settings + f":devices=0,1:block={block}", clip, FMT8, w, h)
     same(one, two)
-    r = ref.run("hb_filter_nlmeans", settings + ":threads=2", clip[:10], FMT8, w, h)
-    assert np.array_equal(r.frames[:8], two.frames[:8])        # frames whose window lies inside the first 10
+    r = ref.run("hb_filter_nlmeans", settings + (":threads=1" if "prefilter" in settings else ":threads=2"), clip[:10], FMT8, w, h)
+    assert np.array_equal(r.frames[:6], two.frames[:6])        # frames whose look-ahead window (<= 4 frames) lies inside the first 10
     if device_count() >= 4:
         four = cuda_filters.run("hb_filter_nlmeans_cuda", settings + f":devices=0,1,2,3:block={block}", clip, FMT8, w, h)
         same(one, four)
+
+
+def test_frame_parallel_filters_over_devices(ref, cuda_filters):
+    """lapsharp / unsharp / chroma smooth with `devices=`: round-robin over handles (two on one GPU; two GPUs when visible)"""
+    w, h, n = 640, 360, 19
+    clip = synth.progressive_clip(FMT8, w, h, n, seed=7)
+    lists = ["0,0", "0,0,0"] + (["0,1"] if device_count() >= 2 else []) + (["0,1,2,3"] if device_count() >= 4 else [])
+    for ref_name, name, settings in (("hb_filter_lapsharp_mt", "hb_filter_lapsharp_cuda", "y-strength=0.3:y-kernel=isolap"),
+                                     ("hb_filter_unsharp_mt", "hb_filter_unsharp_cuda", "y-strength=0.5:y-size=5"),
+                                     ("hb_filter_chroma_smooth_mt", "hb_filter_chroma_smooth_cuda", "cb-strength=0.8:cb-size=5")):
+        r = ref.run(ref_name, settings, clip, FMT8, w, h)
+        for devs in lists:
+            same(r, cuda_filters.run(name, settings + ":devices=" + devs, clip, FMT8, w, h))
+    assert cuda_filters.buffers_alive() == 0
