@@ -437,6 +437,7 @@ void         hb_cond_broadcast(hb_cond_t *);
 void         hb_cond_close(hb_cond_t **);
 hb_thread_t *hb_thread_init(const char *name, thread_func_t *fn, void *arg, int priority);
 void         hb_thread_close(hb_thread_t **);
+void         hb_yield(void);                 /* ports.h:189 */
 
 /* sub-filter registry used by mt_frame_filter.c (common.c:5331-5517) */
 hb_filter_object_t *hb_filter_get(int filter_id);

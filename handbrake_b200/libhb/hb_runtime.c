@@ -15,6 +15,7 @@
 #include "handbrake/handbrake.h"
 
 #include <pthread.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <unistd.h>
 
@@ -187,6 +188,8 @@ void hb_thread_close(hb_thread_t **t)
     free(*t);
     *t = NULL;
 }
+
+void hb_yield(void) { sched_yield(); }
 
 /* ------------------------------------------------------------------ */
 /* buffers                                                              */

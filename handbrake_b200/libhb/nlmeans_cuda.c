@@ -24,7 +24,11 @@
  * harvested in stream order.  A block's look-ahead window reaches nframes-1
  * frames into the next block: those frames cross PCIe once (to their owner) and
  * reach the previous block's device by an NVLink peer copy
- * (hbcu_nlmeans_upload_peer).  Every device keeps its own contiguous index space.
+ * (hbcu_nlmeans_upload_peer).  Every device keeps its own contiguous index space,
+ * and -- like the reference's taskset, one thread per worker (nlmeans.c:546-597) --
+ * its own submission thread: work() only queues commands (upload, halo copy,
+ * filter) and the device's thread turns them into CUDA calls, so the stream
+ * submission of G GPUs does not serialise on the filter's one thread.
  */
 #include "handbrake/handbrake.h"
 #include "hbcu.h"
@@ -50,7 +54,34 @@ typedef struct
     int64_t      li;      /* its index in that device's own index space */
     hb_buffer_t *in;      /* input buffer we took ownership of (source of the async upload) */
     hb_buffer_t *out;     /* output buffer, NULL until the frame has been enqueued */
+    volatile int uploaded;   /* multi-device: the owner's thread has issued the upload (a halo copy may read it) */
+    volatile int submitted;  /* multi-device: the owner's thread has issued kernels + download (wait / poll are valid) */
 } nlm_pending_t;
+
+/* commands of a device's submission thread (multi-device only) */
+enum { NLM_CMD_UPLOAD, NLM_CMD_PEER, NLM_CMD_FILTER, NLM_CMD_STOP };
+typedef struct
+{
+    int            kind;
+    int64_t        li;              /* index in this device's index space */
+    nlm_pending_t *p;               /* UPLOAD / FILTER: the frame */
+    int            navail;          /* FILTER */
+    int            src_dev;         /* PEER: halo source */
+    int64_t        src_li;
+    nlm_pending_t *src_p;           /* PEER: wait until its upload has been issued */
+} nlm_cmd_t;
+
+typedef struct
+{
+    struct hb_filter_private_s *pv;
+    int          dev;
+    hb_thread_t *thread;
+    hb_lock_t   *lock;
+    hb_cond_t   *cv;                /* queue not empty */
+    nlm_cmd_t   *q;
+    int          cap, head, count;
+} nlm_worker_t;
+
 
 struct hb_filter_private_s
 {
@@ -68,6 +99,11 @@ struct hb_filter_private_s
     int64_t         local_next[NLM_MAX_DEVICES];   /* frames handed to each device so far = its next local index */
     int             dev_inflight[NLM_MAX_DEVICES]; /* outputs enqueued on the device and not yet emitted */
     int             block;                         /* frames per block of the block-cyclic dealing */
+    nlm_worker_t    worker[NLM_MAX_DEVICES];       /* multi-device: one submission thread per device */
+    hb_lock_t      *done_lock;                     /* guards `submitted` transitions seen by harvest() and `errmsg` */
+    hb_cond_t      *done_cv;
+    volatile int    failed;                        /* a submission thread hit a GPU error */
+    char            errmsg[256];
     int             inflight_max;   /* outputs in flight per device */
     int             ring;
 
@@ -227,6 +263,125 @@ int hb_nlmeans_cuda_build_config(const hb_dict_t *dict, int pix_fmt, int width, 
     return 0;
 }
 
+/* ------------------------------------------------------------------ */
+/* per-device submission threads (multi-device only)                      */
+/* ------------------------------------------------------------------ */
+static void worker_fail(hb_filter_private_t *pv, const char *what)
+{
+    hb_lock(pv->done_lock);
+    if (!pv->failed) snprintf(pv->errmsg, sizeof(pv->errmsg), "%s: %s", what, hbcu_last_error());    /* the error string is per thread */
+    pv->failed = 1;
+    hb_cond_broadcast(pv->done_cv);
+    hb_unlock(pv->done_lock);
+}
+
+static void worker_push(nlm_worker_t *w, const nlm_cmd_t *cmd)
+{
+    hb_lock(w->lock);
+    /* cannot overflow: the queue holds three commands per pending frame and is sized for it */
+    w->q[(w->head + w->count) % w->cap] = *cmd;
+    w->count++;
+    hb_cond_signal(w->cv);
+    hb_unlock(w->lock);
+}
+
+static void worker_main(void *arg)
+{
+    nlm_worker_t *w = arg;
+    hb_filter_private_t *pv = w->pv;
+    hbcu_nlmeans_t *gpu = pv->gpu[w->dev];
+    for (;;)
+    {
+        hb_lock(w->lock);
+        while (w->count == 0) hb_cond_wait(w->cv, w->lock);
+        const nlm_cmd_t c = w->q[w->head];
+        w->head = (w->head + 1) % w->cap;
+        w->count--;
+        hb_unlock(w->lock);
+        if (c.kind == NLM_CMD_STOP) return;
+        switch (c.kind)
+        {
+            case NLM_CMD_UPLOAD:
+            {
+                const void *planes[3];
+                int strides[3];
+                for (int k = 0; k < 3; k++)
+                {
+                    planes[k]  = c.p->in->plane[k].data;
+                    strides[k] = c.p->in->plane[k].stride;
+                }
+                if (!pv->failed && hbcu_nlmeans_upload(gpu, c.li, planes, strides) != 0) worker_fail(pv, "upload");
+                __atomic_store_n(&c.p->uploaded, 1, __ATOMIC_RELEASE);
+                break;
+            }
+            case NLM_CMD_PEER:
+                /* the halo's owner must have ISSUED its upload (its event is what the copy orders itself behind) */
+                while (!__atomic_load_n(&c.src_p->uploaded, __ATOMIC_ACQUIRE) && !pv->failed) hb_yield();
+                if (!pv->failed && hbcu_nlmeans_upload_peer(gpu, c.li, pv->gpu[c.src_dev], c.src_li) != 0) worker_fail(pv, "halo copy");
+                break;
+            case NLM_CMD_FILTER:
+            {
+                void *planes[3];
+                int   strides[3];
+                for (int k = 0; k < 3; k++)
+                {
+                    planes[k]  = c.p->out->plane[k].data;
+                    strides[k] = c.p->out->plane[k].stride;
+                }
+                if (!pv->failed && hbcu_nlmeans_filter(gpu, c.li, c.navail, planes, strides) != 0) worker_fail(pv, "filter");
+                hb_lock(pv->done_lock);
+                c.p->submitted = 1;
+                hb_cond_broadcast(pv->done_cv);
+                hb_unlock(pv->done_lock);
+                break;
+            }
+        }
+    }
+}
+
+static int workers_start(hb_filter_private_t *pv)
+{
+    pv->done_lock = hb_lock_init();
+    pv->done_cv   = hb_cond_init();
+    if (pv->done_lock == NULL || pv->done_cv == NULL) return -1;
+    for (int d = 0; d < pv->ndev; d++)
+    {
+        nlm_worker_t *w = &pv->worker[d];
+        w->pv   = pv;
+        w->dev  = d;
+        w->cap  = 3 * pv->cap + 4;
+        w->q    = calloc(w->cap, sizeof(*w->q));
+        w->lock = hb_lock_init();
+        w->cv   = hb_cond_init();
+        if (w->q == NULL || w->lock == NULL || w->cv == NULL) return -1;
+        w->thread = hb_thread_init("nlmeans-cuda-device", worker_main, w, HB_NORMAL_PRIORITY);
+        if (w->thread == NULL) return -1;
+    }
+    return 0;
+}
+
+static void workers_stop(hb_filter_private_t *pv)
+{
+    for (int d = 0; d < pv->ndev; d++)
+    {
+        nlm_worker_t *w = &pv->worker[d];
+        if (w->thread != NULL)
+        {
+            nlm_cmd_t stop;
+            memset(&stop, 0, sizeof(stop));
+            stop.kind = NLM_CMD_STOP;
+            worker_push(w, &stop);
+            hb_thread_close(&w->thread);         /* joins */
+        }
+        if (w->lock != NULL) hb_lock_close(&w->lock);
+        if (w->cv != NULL) hb_cond_close(&w->cv);
+        free(w->q);
+        w->q = NULL;
+    }
+    if (pv->done_lock != NULL) hb_lock_close(&pv->done_lock);
+    if (pv->done_cv != NULL) hb_cond_close(&pv->done_cv);
+}
+
 static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
 {
     hb_filter_private_t *pv = calloc(1, sizeof(*pv));
@@ -306,9 +461,15 @@ static int nlmeans_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
 
     pv->device = pv->devices[0];
     pv->output = *init;
+    if (pv->ndev > 1 && workers_start(pv) != 0)
+    {
+        hb_error("nlmeans(cuda): could not start the per-device submission threads");
+        goto fail;
+    }
     return 0;
 
 fail:
+    workers_stop(pv);
     for (int d = 0; d < NLM_MAX_DEVICES; d++)
         if (pv->gpu[d] != NULL) hbcu_nlmeans_destroy(pv->gpu[d]);
     free(pv->pending);
@@ -321,6 +482,7 @@ static void nlmeans_cuda_close(hb_filter_object_t *filter)
 {
     hb_filter_private_t *pv = filter->private_data;
     if (pv == NULL) return;
+    workers_stop(pv);                                    /* queued commands are executed, then the threads end */
     /* every handle first drains its device; peers only read each other's rings from queued copies, so destroy them
      * after ALL devices are idle */
     for (int d = 0; d < pv->ndev; d++)
@@ -366,6 +528,20 @@ static int enqueue_frame(hb_filter_private_t *pv, nlm_pending_t *p, int navail)
         strides[c] = out->plane[c].stride;
     }
     if (navail > pv->max_frames) navail = pv->max_frames;  /* what the device holds behind p->li: the block's rest + its halo */
+    if (pv->ndev > 1)
+    {
+        nlm_cmd_t c;
+        memset(&c, 0, sizeof(c));
+        c.kind = NLM_CMD_FILTER;
+        c.li = p->li;
+        c.p = p;
+        c.navail = navail;
+        p->out = out;
+        p->submitted = 0;
+        pv->dev_inflight[p->dev]++;
+        worker_push(&pv->worker[p->dev], &c);
+        return 0;
+    }
     hbcu_nlmeans_t *gpu = pv->gpu[p->dev];
     const int rc = pv->device_out ? hbcu_nlmeans_filter_frame(gpu, p->li, navail, hbcu_buffer_frame(out))
                                   : hbcu_nlmeans_filter(gpu, p->li, navail, planes, strides);
@@ -405,6 +581,20 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int block_on
     {
         nlm_pending_t *p = pending_at(pv, 0);
         if (p->out == NULL) break;                           /* not enqueued yet */
+        if (pv->ndev > 1)
+        {
+            /* the device's thread has to have issued the frame before wait / poll mean anything */
+            int ready;
+            hb_lock(pv->done_lock);
+            while (!(ready = p->submitted) && !pv->failed && (block_one || block_all)) hb_cond_wait(pv->done_cv, pv->done_lock);
+            hb_unlock(pv->done_lock);
+            if (pv->failed)
+            {
+                hb_error("nlmeans(cuda): %s", pv->errmsg);
+                return -1;
+            }
+            if (!ready) break;
+        }
         hbcu_nlmeans_t *gpu = pv->gpu[p->dev];
         if (hbcu_buffer_frame(p->out) != NULL)
         {
@@ -496,30 +686,53 @@ static int nlmeans_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, h
     const int64_t t  = pv->next_in;
     const int     d  = owner_of(pv, t);
     const int64_t li = pv->local_next[d];
-    if ((fin != NULL ? hbcu_nlmeans_upload_frame(pv->gpu[d], li, fin)
-                     : hbcu_nlmeans_upload(pv->gpu[d], li, planes, strides)) != 0)
+    nlm_pending_t *p = pending_at(pv, pv->count);
+    if (pv->failed)
     {
-        hb_error("nlmeans(cuda): %s", hbcu_last_error());
+        hb_error("nlmeans(cuda): %s", pv->errmsg);
         return HB_FILTER_FAILED;
     }
-    pv->local_next[d]++;
-    if (pv->ndev > 1 && t >= pv->block && (t % pv->block) < pv->max_frames - 1)
-    {
-        /* one of the first nframes-1 frames of its block: also the look-ahead of the previous block, on another device */
-        const int q = owner_of(pv, t - pv->block);
-        if (hbcu_nlmeans_upload_peer(pv->gpu[q], pv->local_next[q], pv->gpu[d], li) != 0)
-        {
-            hb_error("nlmeans(cuda): %s", hbcu_last_error());
-            return HB_FILTER_FAILED;
-        }
-        pv->local_next[q]++;
-    }
-    nlm_pending_t *p = pending_at(pv, pv->count);
+    /* the entry is complete before any thread can see it */
     p->index = t;
     p->dev   = d;
     p->li    = li;
     p->in    = in;
     p->out   = NULL;
+    p->uploaded = p->submitted = 0;
+    if (pv->ndev > 1)
+    {
+        /* the owner's thread issues the upload; a frame among the first nframes-1 of its block is also the look-ahead of
+         * the previous block, on another device: that device's thread copies it over NVLink once the upload is issued */
+        nlm_cmd_t c;
+        memset(&c, 0, sizeof(c));
+        c.kind = NLM_CMD_UPLOAD;
+        c.li = li;
+        c.p = p;
+        worker_push(&pv->worker[d], &c);
+        pv->local_next[d]++;
+        if (t >= pv->block && (t % pv->block) < pv->max_frames - 1)
+        {
+            const int q = owner_of(pv, t - pv->block);
+            memset(&c, 0, sizeof(c));
+            c.kind = NLM_CMD_PEER;
+            c.li = pv->local_next[q];
+            c.src_dev = d;
+            c.src_li = li;
+            c.src_p = p;
+            worker_push(&pv->worker[q], &c);
+            pv->local_next[q]++;
+        }
+    }
+    else
+    {
+        if ((fin != NULL ? hbcu_nlmeans_upload_frame(pv->gpu[d], li, fin)
+                         : hbcu_nlmeans_upload(pv->gpu[d], li, planes, strides)) != 0)
+        {
+            hb_error("nlmeans(cuda): %s", hbcu_last_error());
+            return HB_FILTER_FAILED;
+        }
+        pv->local_next[d]++;
+    }
     pv->count++;
     pv->next_in++;
     *buf_in = NULL;

@@ -9,6 +9,10 @@ int main(void)
 {
     struct { hb_filter_object_t *f; const char *s[3]; } jobs[] = {
         { &hb_filter_nlmeans_cuda, { NULL, "y-strength=6:y-frame-count=3:cb-range=5", "y-strength=4:y-prefilter=1032:threads=1" } },
+        /* several device handles: per-device submission threads, block-cyclic dealing, halo copies (round 2) */
+        { &hb_filter_nlmeans_cuda, { "y-strength=6:y-patch-size=3:devices=0,0:block=2", "y-strength=6:y-patch-size=3:y-frame-count=3:devices=0,0,0:block=2",
+                                     "y-strength=4:y-patch-size=3:y-prefilter=1:devices=0,0,0,0:block=3:threads=1" } },
+        { &hb_filter_lapsharp_cuda, { "y-strength=0.4:devices=0,0", "y-strength=0.4:devices=0,0,0", "y-strength=0.4:devices=0,0,0,0,0" } },
         { &hb_filter_comb_detect_cuda, { NULL, "mode=0:spatial-metric=0", "mode=2:spatial-metric=1:filter-mode=1" } },
         { &hb_filter_decomb_cuda, { "mode=7", "mode=31", "mode=55:parity=1" } },
         { &hb_filter_lapsharp_cuda, { NULL, "y-strength=1.1:y-kernel=lap:cb-strength=0.5:cb-kernel=isolog", "y-strength=0" } },
