@@ -63,6 +63,9 @@ WORKLOADS = {
     # diagnostic: every plane bypassed (strength 0) -> the transfer pipeline alone
     "4k_copy_only": dict(width=3840, height=2160, depth=8, settings="y-strength=0", nframes=2,
                          desc="3840x2160 yuv420p 8-bit, NLMeans strength 0 (bypass copy): transfer pipeline diagnostic"),
+    # a prefilter mode (custom settings only, nlmeans.c:72-83): 8-bit planes run the prefilter variant of the v3 kernel
+    "4k_nlmeans_medium_prefilter": dict(width=3840, height=2160, depth=8, settings="y-strength=6:y-prefilter=1", nframes=2,
+                                        desc="3840x2160 yuv420p 8-bit, NLMeans 'medium' with the 3x3 mean prefilter"),
     "4k10_nlmeans_medium": dict(width=3840, height=2160, depth=10, settings="y-strength=6", nframes=2,
                                 desc="3840x2160 yuv420p10 NLMeans 'medium'"),
 }

@@ -22,21 +22,53 @@ namespace {
 
 using hbcu::set_error;
 
-__constant__ int c_kernels[4][25] = {
-    { 0, -1, 0, -1, 5, -1, 0, -1, 0 },                                                    // lap
-    { -1, -4, -1, -4, 25, -4, -1, -4, -1 },                                               // isolap
-    { 0, 0, -1, 0, 0, 0, -1, -2, -1, 0, -1, -2, 21, -2, -1, 0, -1, -2, -1, 0, 0, 0, -1, 0, 0 },        // log
-    { 0, -1, -1, -1, 0, -1, -3, -4, -3, -1, -1, -4, 55, -4, -1, -1, -3, -4, -3, -1, 0, -1, -1, -1, 0 } // isolog
+// the four convolution kernels (lapsharp.c:36-93) as compile-time tables: the kernel id is a template parameter, so every
+// coefficient is an immediate and the zero taps (4 of 9 for lap, 12 of 25 for log) cost nothing
+struct LapTaps { int v[25]; };
+__host__ __device__ constexpr LapTaps lap_taps(int kid)
+{
+    return kid == 0 ? LapTaps{ { 0, -1, 0, -1, 5, -1, 0, -1, 0 } }                                                    // lap
+         : kid == 1 ? LapTaps{ { -1, -4, -1, -4, 25, -4, -1, -4, -1 } }                                               // isolap
+         : kid == 2 ? LapTaps{ { 0, 0, -1, 0, 0, 0, -1, -2, -1, 0, -1, -2, 21, -2, -1, 0, -1, -2, -1, 0, 0, 0, -1, 0, 0 } }       // log
+                    : LapTaps{ { 0, -1, -1, -1, 0, -1, -3, -4, -3, -1, -1, -4, 55, -4, -1, -1, -3, -4, -3, -1, 0, -1, -1, -1, 0 } }; // isolog
+}
+
+struct LapPlane
+{
+    const void *src;
+    void *dst;
+    int width, height, spitch, dpitch, kid, vec;      // vec: rows can be read as aligned 32-bit words
+    double coef, strength;
+};
+struct LapFrame
+{
+    LapPlane pl[3];
+    int max_value;
 };
 
-// one thread = 4 adjacent pixels of one row; the SIZE x (SIZE+3) input window is read once into registers
-template <typename PIX, typename ACC, int SIZE>
-__global__ void __launch_bounds__(256) lapsharp_kernel(const PIX *__restrict__ src, PIX *__restrict__ dst, int width, int height,
-                                                      int spitch, int dpitch, int kid, double coef, double strength, int max_value)
+template <typename PIX, typename ACC>
+__device__ __forceinline__ int lap_finish(int acc, int s0, double coef, double strength, int max_value)
 {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= width || y >= height) return;
+    // the sharpening term exactly as the reference writes it (lapsharp.c:160-176): ACC wrap, double arithmetic,
+    // truncation toward zero, ACC wrap again, clamp
+    ACC pixel = (ACC)acc;
+    const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
+    pixel = (ACC)((int)(ACC)(int)t + s0);
+    int v = pixel;
+    v = v < 0 ? 0 : v;
+    return v > max_value ? max_value : v;
+}
+
+// one thread = 4 adjacent pixels of one row.  Interior groups read each of their SIZE input rows as three (8-bit) or four
+// (16-bit) aligned 32-bit words through the read-only path and pick the SIZE+3 samples out of them.
+template <typename PIX, typename ACC, int KID>
+__device__ __forceinline__ void lap_px4(const LapPlane &p, int max_value, int x0, int y)
+{
+    constexpr int SIZE = KID < 2 ? 3 : 5;
     constexpr int offset_min = -((SIZE - 1) / 2), offset_max = (SIZE + 1) / 2;
+    constexpr LapTaps K = lap_taps(KID);
+    const PIX *src = (const PIX *)p.src;
+    const int width = p.width, height = p.height, spitch = p.spitch;
     const int stride_border = (spitch - width) / 2;
     const PIX *row = src + (size_t)y * spitch;
     int out[4];
@@ -46,32 +78,60 @@ __global__ void __launch_bounds__(256) lapsharp_kernel(const PIX *__restrict__ s
     if (all_interior)
     {
         int acc[4] = { 0, 0, 0, 0 };
+        int s0[4];
 #pragma unroll
         for (int j = offset_min; j < offset_max; j++)
         {
-            const PIX *r = src + (size_t)(y + j) * spitch + x0 + offset_min;
-            int v[SIZE + 3];
+            const PIX *r = src + (size_t)(y + j) * spitch + x0;
+            int v[SIZE + 3];                                   // samples x0 + offset_min .. x0 + offset_max + 2
+            if (p.vec)
+            {
+                if (sizeof(PIX) == 1)
+                {
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(r - 4);     // x0 is a multiple of 4 and >= 4 here
+                    const uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2);
 #pragma unroll
-            for (int t = 0; t < SIZE + 3; t++) v[t] = r[t];
+                    for (int t = 0; t < SIZE + 3; t++)
+                    {
+                        const int b = offset_min + t + 4;
+                        const uint32_t w = b < 4 ? w0 : b < 8 ? w1 : w2;
+                        v[t] = (int)((w >> (8 * (b & 3))) & 0xffu);
+                    }
+                }
+                else
+                {
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(r - 2);
+                    const uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2), w3 = __ldg(rw + 3);
+#pragma unroll
+                    for (int t = 0; t < SIZE + 3; t++)
+                    {
+                        const int b = offset_min + t + 2;      // sample index among the eight loaded
+                        const uint32_t w = b < 2 ? w0 : b < 4 ? w1 : b < 6 ? w2 : w3;
+                        v[t] = (int)((b & 1) ? (w >> 16) : (w & 0xffffu));
+                    }
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int t = 0; t < SIZE + 3; t++) v[t] = r[offset_min + t];
+            }
+            if (j == 0)
+            {
+#pragma unroll
+                for (int i = 0; i < 4; i++) s0[i] = v[i - offset_min];
+            }
 #pragma unroll
             for (int k = 0; k < SIZE; k++)
             {
-                const int c = c_kernels[kid][(j - offset_min) * SIZE + k];
+                const int c = K.v[(j - offset_min) * SIZE + k];
+                if (c == 0) continue;
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[i] += c * v[i + k];
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-            const int s0 = row[x0 + i];
-            ACC pixel = (ACC)acc[i];                                // the reference accumulates in ACC (wraps like it)
-            const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
-            pixel = (ACC)((int)(ACC)(int)t + s0);
-            int v = pixel;
-            v = v < 0 ? 0 : v;
-            out[i] = v > max_value ? max_value : v;
-        }
+        for (int i = 0; i < 4; i++) out[i] = lap_finish<PIX, ACC>(acc[i], s0[i], p.coef, p.strength, max_value);
     }
     else
     {
@@ -91,16 +151,14 @@ __global__ void __launch_bounds__(256) lapsharp_kernel(const PIX *__restrict__ s
             for (int k = offset_min; k < offset_max; k++)
 #pragma unroll
                 for (int j = offset_min; j < offset_max; j++)
-                    acc += c_kernels[kid][(j - offset_min) * SIZE + k - offset_min] * (int)src[(size_t)(y + j) * spitch + (x + k)];
-            ACC pixel = (ACC)acc;
-            const double t = __dmul_rn(__dsub_rn(__dmul_rn((double)pixel, coef), (double)s0), strength);
-            pixel = (ACC)((int)(ACC)(int)t + s0);
-            int v = pixel;
-            v = v < 0 ? 0 : v;
-            out[i] = v > max_value ? max_value : v;
+                {
+                    const int c = K.v[(j - offset_min) * SIZE + k - offset_min];
+                    if (c != 0) acc += c * (int)src[(size_t)(y + j) * spitch + (x + k)];
+                }
+            out[i] = lap_finish<PIX, ACC>(acc, s0, p.coef, p.strength, max_value);
         }
     }
-    PIX *drow = dst + (size_t)y * dpitch;
+    PIX *drow = (PIX *)p.dst + (size_t)y * p.dpitch;
     if (x0 + 3 < width)
     {
         if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(drow + x0) = make_uchar4(out[0], out[1], out[2], out[3]);
@@ -110,6 +168,23 @@ __global__ void __launch_bounds__(256) lapsharp_kernel(const PIX *__restrict__ s
     {
         for (int i = 0; i < 4; i++)
             if (x0 + i < width) drow[x0 + i] = (PIX)out[i];
+    }
+}
+
+// all three planes of a frame in ONE launch (blockIdx.z = plane; the grid is sized for luma, chroma CTAs beyond their plane
+// leave at once): three launches per frame ended in three partial waves
+template <typename PIX, typename ACC>
+__global__ void __launch_bounds__(256) lapsharp_kernel(const __grid_constant__ LapFrame f)
+{
+    const LapPlane &p = f.pl[blockIdx.z];
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= p.width || y >= p.height) return;
+    switch (p.kid)                                   // uniform per CTA
+    {
+        case 0:  lap_px4<PIX, ACC, 0>(p, f.max_value, x0, y); break;
+        case 1:  lap_px4<PIX, ACC, 1>(p, f.max_value, x0, y); break;
+        case 2:  lap_px4<PIX, ACC, 2>(p, f.max_value, x0, y); break;
+        default: lap_px4<PIX, ACC, 3>(p, f.max_value, x0, y); break;
     }
 }
 
@@ -148,17 +223,26 @@ __global__ void mirror_stride16_kernel(uint16_t *d, int width, int height, int s
     for (int ii = threadIdx.x; ii < margin_front; ii += blockDim.x) d[row + stride - 1 - ii] = d[row + stride + ii];
 }
 
-int launch(hbcu_lapsharp_s *h, int pl, const void *src, int spitch_elems, void *dst)
+int launch_frame(hbcu_lapsharp_s *h, const void *const src[3], const int spitch_elems[3], void *const dst[3])
 {
-    const Geom &g = h->g[pl];
-    dim3 blk(32, 8), grid(((g.w + 3) / 4 + 31) / 32, (g.h + 7) / 8);
-    const int kid = h->cfg.kernel[pl];
-    const bool small = kid < 2;                       // lap / isolap are 3x3, log / isolog 5x5
-#define LAP_LAUNCH(PIX, ACC, SIZE) lapsharp_kernel<PIX, ACC, SIZE><<<grid, blk, 0, h->s_compute>>>((const PIX *)src, (PIX *)dst, g.w, g.h, \
-        spitch_elems, g.pitch, kid, kCoef[kid], h->cfg.strength[pl], h->maxv)
-    if (h->bps == 1) { if (small) LAP_LAUNCH(uint8_t, int16_t, 3); else LAP_LAUNCH(uint8_t, int16_t, 5); }
-    else             { if (small) LAP_LAUNCH(uint16_t, int32_t, 3); else LAP_LAUNCH(uint16_t, int32_t, 5); }
-#undef LAP_LAUNCH
+    LapFrame f;
+    f.max_value = h->maxv;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const Geom &g = h->g[pl];
+        LapPlane &p = f.pl[pl];
+        p.src = src[pl];
+        p.dst = dst[pl];
+        p.width = g.w; p.height = g.h; p.spitch = spitch_elems[pl]; p.dpitch = g.pitch;
+        p.kid = h->cfg.kernel[pl];
+        p.coef = kCoef[p.kid];
+        p.strength = h->cfg.strength[pl];
+        p.vec = ((uintptr_t)src[pl] % 4 == 0) && (((size_t)spitch_elems[pl] * h->bps) % 4 == 0);
+    }
+    const Geom &g0 = h->g[0];
+    dim3 blk(32, 8), grid(((g0.w + 3) / 4 + 31) / 32, (g0.h + 7) / 8, 3);
+    if (h->bps == 1) lapsharp_kernel<uint8_t, int16_t><<<grid, blk, 0, h->s_compute>>>(f);
+    else             lapsharp_kernel<uint16_t, int32_t><<<grid, blk, 0, h->s_compute>>>(f);
     hbcu::count_launch();
     HBCU_CHECK(cudaGetLastError());
     return 0;
@@ -306,8 +390,12 @@ int hbcu_lapsharp_filter(hbcu_lapsharp_t *h, int64_t ticket, const void *const i
     HBCU_CHECK(cudaEventRecord(h->ev_up[s], h->s_h2d));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_up[s], 0));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
-    for (int pl = 0; pl < 3; pl++)
-        if (launch(h, pl, h->in_mem[s * 3 + pl], h->g[pl].pitch, h->out_mem[s * 3 + pl]) != 0) return -1;
+    {
+        const void *srcs[3] = { h->in_mem[s * 3 + 0], h->in_mem[s * 3 + 1], h->in_mem[s * 3 + 2] };
+        void *dsts[3] = { h->out_mem[s * 3 + 0], h->out_mem[s * 3 + 1], h->out_mem[s * 3 + 2] };
+        const int sp[3] = { h->g[0].pitch, h->g[1].pitch, h->g[2].pitch };
+        if (launch_frame(h, srcs, sp, dsts) != 0) return -1;
+    }
     HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
     HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_k[s], 0));
     const bool whole_out = same_layout(h, out_planes, out_strides);
@@ -380,11 +468,17 @@ int hbcu_lapsharp_filter_frames(hbcu_lapsharp_t *h, int64_t ticket,
     }
     HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
     if (out_frame && hbcu::frame_begin_write(out_frame, h->s_compute) != 0) return -1;
-    for (int pl = 0; pl < 3; pl++)
     {
-        const void *src = (in_frame && !staged) ? (const void *)in_frame->plane[pl] : (const void *)h->in_mem[s * 3 + pl];
-        void *dst = out_frame ? (void *)out_frame->plane[pl] : (void *)h->out_mem[s * 3 + pl];
-        if (launch(h, pl, src, h->g[pl].pitch, dst) != 0) return -1;
+        const void *srcs[3];
+        void *dsts[3];
+        int sp[3];
+        for (int pl = 0; pl < 3; pl++)
+        {
+            srcs[pl] = (in_frame && !staged) ? (const void *)in_frame->plane[pl] : (const void *)h->in_mem[s * 3 + pl];
+            dsts[pl] = out_frame ? (void *)out_frame->plane[pl] : (void *)h->out_mem[s * 3 + pl];
+            sp[pl] = h->g[pl].pitch;
+        }
+        if (launch_frame(h, srcs, sp, dsts) != 0) return -1;
     }
     HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
     if (in_frame && hbcu::frame_end_read(in_frame, h->s_compute) != 0) return -1;
@@ -417,8 +511,11 @@ int hbcu_lapsharp_filter_device(hbcu_lapsharp_t *h, int64_t ticket, const void *
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     const int s = h->next;
     h->next = (h->next + 1) % h->slots;
-    for (int pl = 0; pl < 3; pl++)
-        if (launch(h, pl, dplanes[pl], strides[pl] / h->bps, h->out_mem[s * 3 + pl]) != 0) return -1;
+    {
+        void *dsts[3] = { h->out_mem[s * 3 + 0], h->out_mem[s * 3 + 1], h->out_mem[s * 3 + 2] };
+        const int sp[3] = { strides[0] / h->bps, strides[1] / h->bps, strides[2] / h->bps };
+        if (launch_frame(h, dplanes, sp, dsts) != 0) return -1;
+    }
     HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
     HBCU_CHECK(cudaEventRecord(h->ev_down[s], h->s_compute));
     h->ticket[s] = ticket;
