@@ -2528,15 +2528,22 @@ static int upload_common(hbcu_nlmeans_t *h, int64_t index, const void *const pla
             if (h->bps == 1) edgeboost_mask_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, g.bpitch, g.w, g.h, h->eb_cls, cp);
             else             edgeboost_mask_kernel<uint16_t><<<grid, blk, 0, h->s_pad>>>((const uint16_t *)srcb, g.bpitch, g.w, g.h, h->eb_cls, cp);
             hbcu::count_launch();
+            // rounds are queued in batches and the host looks at the flag of a batch's LAST round only: once a round changes
+            // nothing the state is the fixed point and every later round leaves it alone, so extra rounds are harmless and
+            // the host waits once per batch instead of once per round
+            constexpr int kRoundsPerWait = 8;
             int cur = 0;
-            for (int round = 0; round < g.w + g.h + 2; round++)
+            for (int round = 0; round < g.w + g.h + 2; round += kRoundsPerWait)
             {
-                HBCU_CHECK(cudaMemsetAsync(h->eb_changed, 0, sizeof(int), h->s_pad));
-                edgeboost_clear_kernel<<<grid, blk, 0, h->s_pad>>>(h->eb_cls, cp, g.w, g.h, h->eb_clr[cur], h->eb_clr[cur ^ 1], h->eb_changed);
-                hbcu::count_launch();
+                for (int k = 0; k < kRoundsPerWait; k++)
+                {
+                    HBCU_CHECK(cudaMemsetAsync(h->eb_changed, 0, sizeof(int), h->s_pad));
+                    edgeboost_clear_kernel<<<grid, blk, 0, h->s_pad>>>(h->eb_cls, cp, g.w, g.h, h->eb_clr[cur], h->eb_clr[cur ^ 1], h->eb_changed);
+                    hbcu::count_launch();
+                    cur ^= 1;
+                }
                 HBCU_CHECK(cudaMemcpyAsync(h->eb_changed_host, h->eb_changed, sizeof(int), cudaMemcpyDeviceToHost, h->s_pad));
                 HBCU_CHECK(cudaStreamSynchronize(h->s_pad));
-                cur ^= 1;
                 if (*h->eb_changed_host == 0) break;
             }
             if (h->bps == 1) edgeboost_apply_kernel<uint8_t><<<grid, blk, 0, h->s_pad>>>(srcb, preb + org, g.bpitch, g.w, g.h, h->eb_cls, h->eb_clr[cur], cp, ft);
