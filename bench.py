@@ -716,24 +716,24 @@ def run_ours(args, wl, rank, world, local_rank):
 
     # ---------------- the plugin's own multi-device path: ONE process, ONE ordered stream dealt to all N GPUs in C ----------------
     # (what a libhb job -- one process, one thread per filter, work.c:2255-2270 -- does with `devices=`; the ranks above
-    # each filter a private stream.)  Rank 0 drives every GPU of the job while the other ranks wait at the barrier.
+    # each filter a private stream.)  A child process of rank 0 drives every GPU of the job while all ranks wait at the
+    # barrier; a child, so that a fault in this side arm can neither hang nor take down the headline line.
     plugin_multi = None
     if world > 1 and not args.no_plugin_multi:
         barrier()
         if rank == 0:
             devs = [pick_gpu(r_, world) for r_ in range(world)]
             nfr = world * max(B // 2, int(K * B * 0.25))
-            ms_settings = wl["settings"] + f":threads={args.inflight}:devices={','.join(map(str, devs))}:block={args.block}"
-            what = ("one process, one ordered stream of host hb_buffer_t frames through hb_filter_nlmeans_cuda.work() with "
-                    "devices=<all GPUs>: block-cyclic dealing in C (nlmeans_cuda.c), look-ahead halo by NVLink peer copy "
-                    "(hbcu_nlmeans_upload_peer), outputs harvested in stream order; H2D + kernels + D2H inside the clock")
-            try:                # a side arm must never take the headline line down with it
-                rm = ours.stream_arm(["hb_filter_nlmeans_cuda"], [ms_settings], fmt, W, H, synth.PIC_FLAG_PROGRESSIVE_FRAME, host,
-                                     min(Wm * B, 64 * world), nfr, ring=min(256, 48 + 16 * world))
-                plugin_multi = {"value": round(nfr / rm["seconds"], 2), "unit": "frames/s", "seconds": round(rm["seconds"], 3), "frames": nfr,
-                                "devices": devs, "block": args.block, "ring_misses": rm["ring_misses"], "checksum": rm["checksum"], "what": what}
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                                                                      "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "HBCU_DEVICE")}
+            cmd = [sys.executable, str(Path(__file__).resolve()), "--plugin-multi-child", ",".join(map(str, devs)), "--workload", args.workload,
+                   "--plugin-frames", str(nfr), "--plugin-warm", str(min(Wm * B, 64 * world)), "--block", str(args.block), "--inflight", str(args.inflight)]
+            try:
+                cp = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+                line = [l for l in cp.stdout.splitlines() if l.startswith("{")]
+                plugin_multi = json.loads(line[-1]) if line else {"error": (cp.stderr or "no output")[-400:], "devices": devs}
             except Exception as e:
-                plugin_multi = {"error": f"{type(e).__name__}: {e}", "devices": devs, "what": what}
+                plugin_multi = {"error": f"{type(e).__name__}: {e}", "devices": devs}
         barrier()
 
     out = {
@@ -803,6 +803,27 @@ def run_reference(args, wl, rank, world):
     }
 
 
+def plugin_multi_child(args, wl):
+    """one process, one ordered stream through hb_filter_nlmeans_cuda.work() with devices=<list> (see run_ours)"""
+    devs = [int(x) for x in args.plugin_multi_child.split(",")]
+    ours = Ours(devs[0])
+    os.environ.pop("HBCU_DEVICE", None)
+    W, H, depth = wl["width"], wl["height"], wl["depth"]
+    fmt = fmt_of(depth)
+    host = np.stack([synth.progressive_frame(fmt, W, H, t) for t in range(4)])
+    settings = wl["settings"] + f":threads={args.inflight}:devices={args.plugin_multi_child}:block={args.block}"
+    rm = ours.stream_arm(["hb_filter_nlmeans_cuda"], [settings], fmt, W, H, synth.PIC_FLAG_PROGRESSIVE_FRAME, host,
+                         args.plugin_warm, args.plugin_frames, ring=min(256, 48 + 16 * len(devs)))
+    fb = synth.frame_bytes(fmt, W, H)
+    print(json.dumps({"value": round(args.plugin_frames / rm["seconds"], 2), "unit": "frames/s", "seconds": round(rm["seconds"], 3),
+                      "frames": args.plugin_frames, "devices": devs, "block": args.block, "ring_misses": rm["ring_misses"], "checksum": rm["checksum"],
+                      "gb_s_per_direction_total": round(args.plugin_frames / rm["seconds"] * fb / 1e9, 1), "pinned_numa": numa_of_pinned(),
+                      "what": "one process, one ordered stream of host hb_buffer_t frames through hb_filter_nlmeans_cuda.work() with "
+                              "devices=<all GPUs>: block-cyclic dealing in C (nlmeans_cuda.c), one submission thread per device, look-ahead "
+                              "halo by NVLink peer copy (hbcu_nlmeans_upload_peer), outputs harvested in stream order; H2D + kernels + D2H "
+                              "inside the clock"}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -818,6 +839,9 @@ def main():
     ap.add_argument("--no-copy-only", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-plugin-multi", action="store_true")
+    ap.add_argument("--plugin-multi-child", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--plugin-frames", type=int, default=2048, help=argparse.SUPPRESS)
+    ap.add_argument("--plugin-warm", type=int, default=256, help=argparse.SUPPRESS)
     ap.add_argument("--block", type=int, default=8, help="frames per device turn of the plugin's multi-device dealing")
     ap.add_argument("--inflight", type=int, default=6, help="frames in flight in the e2e arm (the filter's `threads` setting)")
     args = ap.parse_args()
@@ -827,6 +851,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    if args.plugin_multi_child:
+        plugin_multi_child(args, wl)
+        return
     if args.impl == "reference":
         out = run_reference(args, wl, rank, world)
     else:

@@ -14,4 +14,4 @@ run $CS --tool memcheck python -m pytest tests/test_nlmeans_gpu.py -q -m gpu -x 
 run $CS --tool memcheck python -m pytest tests/test_nlmeans_multi_gpu.py -q -m gpu -x -k "two_handles"
 run $CS --tool memcheck python -m pytest tests/test_wrap_gpu.py tests/test_detelecine_gpu.py -q -m gpu -x -k "wrap or device_resident"
 run $CS --tool racecheck python -m pytest tests/test_nlmeans_gpu.py -q -m gpu -x -k "ragged or test_10bit"
-run $CS --tool initcheck python -m pytest tests/test_nlmeans_multi_gpu.py -q -m gpu -x -k "prefilter or y-strength=3"
+run $CS --tool initcheck python -m pytest tests/test_nlmeans_multi_gpu.py -q -m gpu -x -k "two_handles"
