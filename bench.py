@@ -134,6 +134,9 @@ def bind_bench(lib):
     lib.hb_bench_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(BenchStats)]
     lib.hb_bench_finish.restype = C.c_int
     lib.hb_bench_finish.argtypes = [C.c_void_p, C.POINTER(BenchStats)]
+    if hasattr(lib, "hb_bench_prefill"):
+        lib.hb_bench_prefill.restype = C.c_int
+        lib.hb_bench_prefill.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.hb_shim_set_log_level.argtypes = [C.c_int]
     lib.hb_shim_set_log_level(-1)
     lib.hb_shim_set_zero_buffers(0)     # like libhb's buffer pool: recycled, not zeroed
@@ -408,6 +411,13 @@ class Ours:
         st = BenchStats()
         fb = host.shape[1]
         self.core.hbcu_host_reserve(fb + 4096, ring + 48)
+        if os.environ.get("HBCU_BENCH_WC_INPUT", "0") == "1":
+            # decoder-style inputs in write-combined pinned memory (the CPU only writes them, the GPU only reads them)
+            self.core.hbcu_host_set_write_combined(1)
+            rc = flt.hb_bench_prefill(b, host.ctypes.data, host.shape[0], ring)
+            self.core.hbcu_host_set_write_combined(0)
+            if rc != 0:
+                raise RuntimeError("input ring prefill failed")
         if flt.hb_bench_stream(b, host.ctypes.data, host.shape[0], warm_frames, ring, C.byref(st)) != 0:
             raise RuntimeError("warm-up stream failed: " + self.core.hbcu_last_error().decode())
         barrier()
@@ -806,6 +816,21 @@ def run_reference(args, wl, rank, world):
 def plugin_multi_child(args, wl):
     """one process, one ordered stream through hb_filter_nlmeans_cuda.work() with devices=<list> (see run_ours)"""
     devs = [int(x) for x in args.plugin_multi_child.split(",")]
+    # one process feeds GPUs on both sockets: undo the per-rank NUMA binding inherited from rank 0 and interleave this
+    # process's pages (the pinned frame pool among them) over all nodes
+    policy = "default"
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        nodes = sorted(int(m.group(1)) for m in (re.match(r"node(\d+)$", n) for n in os.listdir("/sys/devices/system/node")) if m)
+        if len(nodes) > 1:
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(sum(1 << n for n in nodes))
+            if libc.syscall(238, 3, C.byref(mask), C.c_ulong(max(nodes) + 2)) == 0:          # set_mempolicy(MPOL_INTERLEAVE)
+                policy = f"interleave over nodes {nodes}"
+            else:
+                policy = f"set_mempolicy failed (errno {C.get_errno()})"
+    except Exception as e:
+        policy = f"default ({type(e).__name__})"
     ours = Ours(devs[0])
     os.environ.pop("HBCU_DEVICE", None)
     W, H, depth = wl["width"], wl["height"], wl["depth"]
@@ -818,6 +843,7 @@ def plugin_multi_child(args, wl):
     print(json.dumps({"value": round(args.plugin_frames / rm["seconds"], 2), "unit": "frames/s", "seconds": round(rm["seconds"], 3),
                       "frames": args.plugin_frames, "devices": devs, "block": args.block, "ring_misses": rm["ring_misses"], "checksum": rm["checksum"],
                       "gb_s_per_direction_total": round(args.plugin_frames / rm["seconds"] * fb / 1e9, 1), "pinned_numa": numa_of_pinned(),
+                      "mempolicy": policy,
                       "what": "one process, one ordered stream of host hb_buffer_t frames through hb_filter_nlmeans_cuda.work() with "
                               "devices=<all GPUs>: block-cyclic dealing in C (nlmeans_cuda.c), one submission thread per device, look-ahead "
                               "halo by NVLink peer copy (hbcu_nlmeans_upload_peer), outputs harvested in stream order; H2D + kernels + D2H "

@@ -86,7 +86,18 @@ struct PinHeader { uint32_t magic; uint32_t cls; PinHeader *next; char pad[64 - 
 static_assert(sizeof(PinHeader) == 64, "header keeps the payload 64-byte aligned");
 constexpr uint32_t kPinMagic = 0x48424355u;   // 'HBCU'
 std::mutex g_pin_lock;
-PinHeader *g_pin_free[32] = { nullptr };
+PinHeader *g_pin_free[2][32] = { { nullptr }, { nullptr } };      // [write-combined][size class]
+constexpr uint32_t kPinWcBit = 0x100u;                            // header cls bit: the block is write-combined memory
+int g_pin_wc = 0;                                                 // hbcu_host_set_write_combined
+}
+
+// Write-combined pinned memory for buffers the CPU only WRITES and the GPU only reads (a decoder's output frames): it is
+// not snooped, so device reads over PCIe leave the host's caches and coherency traffic alone.  CPU reads from it are very
+// slow, so it is a per-allocation choice made by the caller, never the default.
+void hbcu_host_set_write_combined(int on)
+{
+    std::lock_guard<std::mutex> g(g_pin_lock);
+    g_pin_wc = on != 0;
 }
 
 void *hbcu_host_alloc(size_t bytes)
@@ -98,24 +109,26 @@ void *hbcu_host_alloc(size_t bytes)
         hbcu::set_error("hbcu_host_alloc: %zu bytes is too large", bytes);
         return nullptr;
     }
+    int wc;
     {
         std::lock_guard<std::mutex> g(g_pin_lock);
-        if (g_pin_free[cls] != nullptr)
+        wc = g_pin_wc;
+        if (g_pin_free[wc][cls] != nullptr)
         {
-            PinHeader *h = g_pin_free[cls];
-            g_pin_free[cls] = h->next;
+            PinHeader *h = g_pin_free[wc][cls];
+            g_pin_free[wc][cls] = h->next;
             return (void *)(h + 1);
         }
     }
     void *p = nullptr;
-    if (cudaHostAlloc(&p, (size_t)1 << cls, cudaHostAllocPortable) != cudaSuccess)
+    if (cudaHostAlloc(&p, (size_t)1 << cls, cudaHostAllocPortable | (wc ? cudaHostAllocWriteCombined : 0)) != cudaSuccess)
     {
         hbcu::set_error("cudaHostAlloc(%zu) failed: %s", (size_t)1 << cls, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
     PinHeader *h = (PinHeader *)p;
     h->magic = kPinMagic;
-    h->cls = cls;
+    h->cls = cls | (wc ? kPinWcBit : 0u);
     h->next = nullptr;
     return (void *)(h + 1);
 }
@@ -126,8 +139,9 @@ void hbcu_host_free(void *p)
     PinHeader *h = (PinHeader *)p - 1;
     if (h->magic != kPinMagic) return;   // not ours: refuse to touch it
     std::lock_guard<std::mutex> g(g_pin_lock);
-    h->next = g_pin_free[h->cls];
-    g_pin_free[h->cls] = h;
+    const int wc = (h->cls & kPinWcBit) != 0;
+    h->next = g_pin_free[wc][h->cls & 31u];
+    g_pin_free[wc][h->cls & 31u] = h;
 }
 
 int hbcu_host_reserve(size_t bytes, int count)
@@ -157,15 +171,16 @@ int hbcu_host_reserve(size_t bytes, int count)
 void hbcu_host_trim(void)
 {
     std::lock_guard<std::mutex> g(g_pin_lock);
-    for (int c = 0; c < 32; c++)
-    {
-        while (g_pin_free[c] != nullptr)
+    for (int wc = 0; wc < 2; wc++)
+        for (int c = 0; c < 32; c++)
         {
-            PinHeader *h = g_pin_free[c];
-            g_pin_free[c] = h->next;
-            cudaFreeHost(h);
+            while (g_pin_free[wc][c] != nullptr)
+            {
+                PinHeader *h = g_pin_free[wc][c];
+                g_pin_free[wc][c] = h->next;
+                cudaFreeHost(h);
+            }
         }
-    }
 }
 
 uint64_t hbcu_kernel_launches(void) { return hbcu::g_kernel_launches.load(); }

@@ -2306,8 +2306,15 @@ int hbcu_nlmeans_create(hbcu_nlmeans_t **out, const hbcu_nlmeans_config_t *cfg)
         CK(cudaMalloc(&h->raw_base[s], h->frame_cap));
         for (int pl = 0; pl < 3; pl++)
         {
+            // cleared once: the pitch padding right of the bordered picture is never written by the border kernels but
+            // travels with the plane in the multi-device halo copy (initcheck would flag every such byte)
             CK(cudaMalloc(&h->ring_mem[s * 3 + pl], h->g[pl].bbytes));
-            if (h->has_pre[pl]) CK(cudaMalloc(&h->pre_mem[s * 3 + pl], h->g[pl].bbytes));
+            CK(cudaMemset(h->ring_mem[s * 3 + pl], 0, h->g[pl].bbytes));
+            if (h->has_pre[pl])
+            {
+                CK(cudaMalloc(&h->pre_mem[s * 3 + pl], h->g[pl].bbytes));
+                CK(cudaMemset(h->pre_mem[s * 3 + pl], 0, h->g[pl].bbytes));
+            }
             h->raw_mem[s * 3 + pl] = h->raw_base[s] + h->plane_off[pl];
             const int th = h->bps == 1 ? kTH8 : 96;
             if (hbcu::encode_tensor_map_2d(&h->maps[s * 3 + pl], h->bps, h->ring_mem[s * 3 + pl], (uint64_t)h->g[pl].bw,

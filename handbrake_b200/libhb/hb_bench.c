@@ -260,6 +260,13 @@ hb_bench_t *hb_bench_open(hb_filter_object_t *proto, const char *settings, int p
     return hb_bench_open_chain(1, protos, sets, pix_fmt, w, h, PIC_FLAG_PROGRESSIVE_FRAME);
 }
 
+/* fills the input ring without feeding anything (so that the caller can choose the ring's memory type around the call) */
+int hb_bench_prefill(hb_bench_t *b, const uint8_t *src, int n_unique, int ring)
+{
+    if (b == NULL || b->failed) return -1;
+    return ring_fill(b, src, n_unique, ring > 0 ? ring : 48);
+}
+
 /* feeds n_frames more frames (cycling over n_unique packed source frames; the stream's timestamps continue) and
  * consumes whatever comes out; `ring` payloads back the inputs (0 = default) */
 int hb_bench_stream(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, int ring, hb_bench_stats_t *st)

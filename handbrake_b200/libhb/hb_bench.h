@@ -22,6 +22,8 @@ hb_bench_t *hb_bench_open_chain(int n_filters, hb_filter_object_t *const *protos
 /* feed n_frames more frames of a running stream (inputs: decoder-style headers over a ring of `ring` pre-filled
  * payloads, 0 = default), consume the outputs; may be called repeatedly -- timestamps continue */
 int hb_bench_stream(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, int ring, hb_bench_stats_t *st);
+/* fill the ring of input payloads now (before the first hb_bench_stream), e.g. while a different allocator mode is in force */
+int hb_bench_prefill(hb_bench_t *b, const uint8_t *src, int n_unique, int ring);
 /* EOF, flush, close and free */
 int hb_bench_finish(hb_bench_t *b, hb_bench_stats_t *st);
 /* stream + finish */

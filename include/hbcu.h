@@ -46,6 +46,9 @@ int          hbcu_device_count(void);
 void *       hbcu_host_alloc(size_t bytes);
 void         hbcu_host_free(void *p);
 void         hbcu_host_trim(void);
+/* while on, hbcu_host_alloc hands out WRITE-COMBINED pinned memory: for buffers the CPU only writes and the GPU only reads
+ * (a decoder's output frames); never for buffers the CPU reads back (filter outputs) */
+void         hbcu_host_set_write_combined(int on);
 /* pre-populates the pool with `count` blocks able to hold `bytes` each (steady state of a running
  * pipeline, where every frame buffer is a recycled one); returns the number of blocks added */
 int          hbcu_host_reserve(size_t bytes, int count);

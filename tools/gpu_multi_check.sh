@@ -10,4 +10,6 @@ timeout 600 python -m pytest tests/test_nlmeans_multi_gpu.py tests/test_sharding
 echo "pytest rc=$? $(tail -1 $OUT/pytest_multi.log)" | tee $OUT/summary.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err
 echo "bench N=$N rc=$?" | tee -a $OUT/summary.txt
+HBCU_BENCH_WC_INPUT=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 --no-gather --no-plugin-multi > $OUT/bench_n${N}_wc.json 2> $OUT/bench_n${N}_wc.err
+echo "bench N=$N write-combined inputs rc=$?" | tee -a $OUT/summary.txt
 cat $OUT/summary.txt
