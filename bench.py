@@ -822,7 +822,7 @@ def plugin_multi_child(args, wl):
     try:
         os.sched_setaffinity(0, range(os.cpu_count() or 1))
         nodes = sorted(int(m.group(1)) for m in (re.match(r"node(\d+)$", n) for n in os.listdir("/sys/devices/system/node")) if m)
-        if len(nodes) > 1:
+        if len(nodes) > 1 and os.environ.get("HBCU_BENCH_NO_INTERLEAVE", "0") != "1":
             libc = C.CDLL(None, use_errno=True)
             mask = C.c_ulong(sum(1 << n for n in nodes))
             if libc.syscall(238, 3, C.byref(mask), C.c_ulong(max(nodes) + 2)) == 0:          # set_mempolicy(MPOL_INTERLEAVE)

@@ -75,6 +75,57 @@ __device__ __forceinline__ int median_of(const int *order, int n)
     return (n & 1) ? order[n >> 1] : (order[(n - 1) >> 1] + order[n >> 1] + 1) >> 1;
 }
 
+// Branch-free variants for the per-sample filters (the insertion sort above walks a dynamically indexed array --
+// local memory -- with data-dependent loops that diverge per lane).  Candidates sit in FIXED slots; a missing candidate is
+// kNone, which sorts behind every real value, so after the network the n real values are o[0 .. n-1] in ascending order,
+// exactly what eedi2_sort_metrics leaves in order[0 .. n-1] (equal values are indistinguishable).
+constexpr int kNone = 0x3fffffff;      // above every sample and direction value; differences with it cannot overflow
+
+template <int M>
+__device__ __forceinline__ void sort_net(int (&o)[M])
+{
+#pragma unroll
+    for (int i = 0; i < M - 1; i++)
+#pragma unroll
+        for (int j = 0; j + 1 < M - i; j++)
+        {
+            const int lo = min(o[j], o[j + 1]), hi = max(o[j], o[j + 1]);
+            o[j] = lo;
+            o[j + 1] = hi;
+        }
+}
+
+template <int M>
+__device__ __forceinline__ int pick_net(const int (&o)[M], int idx)
+{
+    int r = o[0];
+#pragma unroll
+    for (int i = 1; i < M; i++) r = idx == i ? o[i] : r;
+    return r;
+}
+
+template <int M>
+__device__ __forceinline__ int median_net(const int (&o)[M], int n)
+{
+    const int a = pick_net(o, (n - 1) >> 1), b = pick_net(o, n >> 1);
+    return (n & 1) ? b : (a + b + 1) >> 1;
+}
+
+// count and sum of the first n (sorted) values within `l` of `mid`
+template <int M>
+__device__ __forceinline__ void near_net(const int (&o)[M], int n, int mid, int l, int &count, int &sum)
+{
+    count = 0;
+    sum = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++)
+    {
+        const bool in = i < n && iabs(o[i] - mid) <= l;
+        count += in ? 1 : 0;
+        sum += in ? o[i] : 0;
+    }
+}
+
 // (int)(((float)(sum + mid) / (float)(count + 1)) + 0.5f)
 __device__ __forceinline__ int avg_round(int sum, int mid, int count)
 {
@@ -481,21 +532,17 @@ __device__ __forceinline__ void calc_directions_px(int plane, const PIX *__restr
         if (diffd < mind) { dird = u; mind = diffd; }
         if (diffe < mine) { dire = u; mine = diffe; }
     }
-    int order[5], n = 0;
-    if (dira != -5000) order[n++] = dira;
-    if (dirb != -5000) order[n++] = dirb;
-    if (dirc != -5000) order[n++] = dirc;
-    if (dird != -5000) order[n++] = dird;
-    if (dire != -5000) order[n++] = dire;
+    int order[5] = { dira != -5000 ? dira : kNone, dirb != -5000 ? dirb : kNone, dirc != -5000 ? dirc : kNone,
+                     dird != -5000 ? dird : kNone, dire != -5000 ? dire : kNone };
+    const int n = (dira != -5000) + (dirb != -5000) + (dirc != -5000) + (dird != -5000) + (dire != -5000);
     int out = k.neutral;
     if (n > 1)
     {
-        sort_metrics(order, n);
-        const int mid = median_of(order, n);
+        sort_net(order);
+        const int mid = median_net(order, n);
         const int tlim = max(lim.v[iabs(mid)] >> 2, 2);
-        int sum = 0, count = 0;
-        for (int i = 0; i < n; ++i)
-            if (iabs(order[i] - mid) <= tlim) { ++count; sum += order[i]; }
+        int sum, count;
+        near_net(order, n, mid, tlim, count, sum);
         if (count > 1) out = k.neutral + ((int)__fdiv_rn((float)sum, (float)count)) * (1 << k.shift2);
     }
     dstp[(size_t)y * pitch + x] = (PIX)out;
@@ -551,32 +598,24 @@ __device__ __forceinline__ int dir_map_px(const PIX *__restrict__ mskp, const PI
             const int step = TWOX ? 2 * pitch : pitch;
             const PIX *dp = dc - step, *dn = dc + step;
             const bool up = !TWOX || y > 1, down = !TWOX || y < height - 2;
-            int u = 0, order[9];
-            if (up)
-            {
-                if (dp[x - 1] != k.peak) order[u++] = dp[x - 1];
-                if (dp[x]     != k.peak) order[u++] = dp[x];
-                if (dp[x + 1] != k.peak) order[u++] = dp[x + 1];
-            }
-            if (dc[x - 1] != k.peak) order[u++] = dc[x - 1];
-            if (!EXPAND && dc[x] != k.peak) order[u++] = dc[x];
-            if (dc[x + 1] != k.peak) order[u++] = dc[x + 1];
-            if (down)
-            {
-                if (dn[x - 1] != k.peak) order[u++] = dn[x - 1];
-                if (dn[x]     != k.peak) order[u++] = dn[x];
-                if (dn[x + 1] != k.peak) order[u++] = dn[x + 1];
-            }
+            // nine fixed candidate slots (three rows x three columns); kNone where the reference skips the sample
+            // (a row that does not exist is never read: `take` guards the load)
+            auto cand = [&](bool take, const PIX *row, int i) { const int value = take ? (int)row[i] : k.peak; return value != k.peak ? value : kNone; };
+            int order[9] = { cand(up, dp, x - 1), cand(up, dp, x), cand(up, dp, x + 1),
+                             cand(true, dc, x - 1), cand(!EXPAND, dc, x), cand(true, dc, x + 1),
+                             cand(down, dn, x - 1), cand(down, dn, x), cand(down, dn, x + 1) };
+            int u = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) u += order[i] != kNone;
             if (EXPAND)
             {
                 if (u >= 5)
                 {
-                    sort_metrics(order, u);
-                    const int mid = median_of(order, u);
+                    sort_net(order);
+                    const int mid = median_net(order, u);
                     const int l = lim.v[iabs(mid - k.neutral) >> k.shift2];
-                    int sum = 0, count = 0;
-                    for (int i = 0; i < u; ++i)
-                        if (iabs(order[i] - mid) <= l) { ++count; sum += order[i]; }
+                    int sum, count;
+                    near_net(order, u, mid, l, count, sum);
                     if (count >= 5) v = (int)(PIX)avg_round(sum, mid, count);
                 }
             }
@@ -586,12 +625,11 @@ __device__ __forceinline__ int dir_map_px(const PIX *__restrict__ mskp, const PI
                     v = k.peak;
                 else
                 {
-                    sort_metrics(order, u);
-                    const int mid = median_of(order, u);
+                    sort_net(order);
+                    const int mid = median_net(order, u);
                     const int l = lim.v[iabs(mid - k.neutral) >> k.shift2];
-                    int sum = 0, count = 0;
-                    for (int i = 0; i < u; ++i)
-                        if (iabs(order[i] - mid) <= l) { ++count; sum += order[i]; }
+                    int sum, count;
+                    near_net(order, u, mid, l, count, sum);
                     if (count < 4 || (count < 5 && dc[x] == k.peak)) v = k.peak;
                     else v = (int)(PIX)avg_round(sum, mid, count);
                 }
@@ -722,25 +760,22 @@ __device__ __forceinline__ void mark_directions_2x_px(const PIX *__restrict__ ms
     const PIX *m0 = mskp + (size_t)(y - 1) * pitch, *m1 = m0 + 2 * pitch;
     if (m0[x] != k.peak && m1[x] != k.peak) return;
     const PIX *d0 = dmskp + (size_t)(y - 1) * pitch, *d1 = d0 + 2 * pitch;
-    int v = 0, order[6];
-    if (d0[x - 1] != k.peak) order[v++] = d0[x - 1];
-    if (d0[x]     != k.peak) order[v++] = d0[x];
-    if (d0[x + 1] != k.peak) order[v++] = d0[x + 1];
-    if (d1[x - 1] != k.peak) order[v++] = d1[x - 1];
-    if (d1[x]     != k.peak) order[v++] = d1[x];
-    if (d1[x + 1] != k.peak) order[v++] = d1[x + 1];
+    int order[6] = { d0[x - 1] != k.peak ? (int)d0[x - 1] : kNone, d0[x] != k.peak ? (int)d0[x] : kNone, d0[x + 1] != k.peak ? (int)d0[x + 1] : kNone,
+                     d1[x - 1] != k.peak ? (int)d1[x - 1] : kNone, d1[x] != k.peak ? (int)d1[x] : kNone, d1[x + 1] != k.peak ? (int)d1[x + 1] : kNone };
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) v += order[i] != kNone;
     if (v < 3) return;
-    sort_metrics(order, v);
-    const int mid = median_of(order, v);
+    sort_net(order);
+    const int mid = median_net(order, v);
     const int l = lim.v[iabs(mid - k.neutral) >> k.shift2];
     int u = 0;
     if (iabs((int)d0[x - 1] - (int)d1[x - 1]) <= l || d0[x - 1] == k.peak || d1[x - 1] == k.peak) ++u;
     if (iabs((int)d0[x] - (int)d1[x]) <= l || d0[x] == k.peak || d1[x] == k.peak) ++u;
     if (iabs((int)d0[x + 1] - (int)d1[x - 1]) <= l || d0[x + 1] == k.peak || d1[x + 1] == k.peak) ++u;    // sic (:835)
     if (u < 2) return;
-    int count = 0, sum = 0;
-    for (int i = 0; i < v; ++i)
-        if (iabs(order[i] - mid) <= l) { ++count; sum += order[i]; }
+    int count, sum;
+    near_net(order, v, mid, l, count, sum);
     if (count < v - 2 || count < 2) return;
     dstp[(size_t)y * pitch + x] = (PIX)avg_round(sum, mid, count);
 }
