@@ -481,7 +481,13 @@ def reference_stream(names, settings, fmt, W, H, flags, host, chunk, budget_s, m
         times.append(round(st.seconds, 3))
         if c + 1 >= min_chunks and secs >= budget_s:
             break
-    ref.hb_bench_finish(b, None)
+    # no EOF flush: the reference flushes a partly filled taskset cycle SERIALLY (minutes at 4K / 8K) and the flush is not part
+    # of the sample; the filters are closed with what they buffer, as a cancelled libhb job does
+    if hasattr(ref, "hb_bench_abort"):
+        ref.hb_bench_abort.argtypes = [C.c_void_p]
+        ref.hb_bench_abort(b)
+    else:
+        ref.hb_bench_finish(b, None)
     return dict(fps=frames / secs, seconds=secs, frames=frames, chunks=len(times), chunk=chunk, chunk_seconds=times,
                 ncpu=ref.hb_get_cpu_count())
 

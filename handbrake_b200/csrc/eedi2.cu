@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(256) k_mark_directions_2x(const PIX *__restric
     });
 }
 
-// fill_gaps_2x (:1025-1132): dst already holds a copy of dmsk (k_blit); threads of one gap write identical values
+// fill_gaps_2x (:1025-1132): the copy of dmsk into dst is part of the kernel; every gap sample writes its own position
 template <typename PIX>
 __device__ __forceinline__ void fill_gaps_2x_px(const PIX *__restrict__ mskp, const PIX *__restrict__ dmskp, PIX *__restrict__ dstp,
                                                 int pitch, int width, int height, const K<PIX> &k, int x, int y)
@@ -847,10 +847,11 @@ __device__ __forceinline__ void fill_gaps_2x_px(const PIX *__restrict__ mskp, co
     const int flim = min(fb >> k.shift2, 6);
     if (iabs(forward - back) <= thresh && (v - u - 1 <= flim || tc || bc))
     {
+        // The reference fills the whole gap u+1 .. v-1 from its first sample; every sample of the gap is itself a start
+        // sample that finds the same (u, v, back, forward) and takes the same decision, so each writes just its own
+        // position -- a gather instead of v-u-1 identical scatters per gap.
         const double step = __ddiv_rn((double)(forward - back), (double)(v - u));
-        PIX *drow = dstp + (size_t)y * pitch;
-        for (int j = 0; j < v - u - 1; ++j)
-            drow[u + j + 1] = (PIX)(back + (int)__dadd_rn(__dmul_rn((double)j, step), 0.5));
+        dstp[(size_t)y * pitch + x] = (PIX)(back + (int)__dadd_rn(__dmul_rn((double)(x - u - 1), step), 0.5));
     }
 }
 
@@ -861,8 +862,25 @@ __global__ void __launch_bounds__(256) k_fill_gaps_2x(const PIX *__restrict__ ms
     constexpr int N = Vec<PIX>::N;
     STAGE_LIST(PIX);
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * N;
-    const int y = 2 - field + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;            // index of the processed row
+    const int y = 2 - field + 2 * r;
     const K<PIX> k(depth);
+    // eedi2_bit_blit (:1036) folded in: dst = dmsk over `width`.  A thread copies its vector on its processed row and the
+    // row above it; the first processed row also takes the rows above that pair, the last one the rows below it.  The
+    // barrier inside block_deal orders these stores before the gap samples' own stores.
+    if (x0 < width && y < height - 1)
+    {
+        const int lo = r == 0 ? 0 : y - 1;
+        const int hi = y + 2 >= height - 1 ? height - 1 : y;
+        for (int yy = lo; yy <= hi; yy++)
+        {
+            const PIX *sp = dmskp + (size_t)yy * pitch + x0;
+            PIX *dp = dstp + (size_t)yy * pitch + x0;
+            if (x0 + N <= width) st16(dp, ld16(sp));
+            else
+                for (int i = 0; x0 + i < width; i++) dp[i] = sp[i];
+        }
+    }
     // a gap starts at a sample without direction (peak) that lies on the (line-doubled) edge mask
     uint32_t bits = 0;
     if (y >= height - 1) bits = 0;
@@ -1376,10 +1394,12 @@ int run_plane(Eedi2 *e, int pl, const PIX *cur_plane, int tff, cudaStream_t st)
     LAUNCH((k_mark_directions_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, tmp2p2, tmp2p, pitch, width, height, tff, depth, e->lim)));
     LAUNCH((k_dir_map<PIX, false, true><<<gridv(width, height), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth, e->lim)));
     LAUNCH((k_dir_map<PIX, true, true><<<gridv(width, height), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth, e->lim)));
-    LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(tmp2p, dst2mp, pitch, width, height)));
-    LAUNCH((k_fill_gaps_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth)));
-    LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(dst2mp, tmp2p, pitch, width, height)));
-    LAUNCH((k_fill_gaps_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth)));
+    // fill_gaps_2x twice (:391-392); its eedi2_bit_blit is fused into the kernel (a plane too small to have a processed
+    // row still gets the plain copy)
+    if (rows2 > 0) LAUNCH((k_fill_gaps_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, tmp2p, dst2mp, pitch, width, height, tff, depth)));
+    else           LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(tmp2p, dst2mp, pitch, width, height)));
+    if (rows2 > 0) LAUNCH((k_fill_gaps_2x<PIX><<<gridv(width, rows2), blk, 0, st>>>(msk2p, dst2mp, tmp2p, pitch, width, height, tff, depth)));
+    else           LAUNCH((k_blit<PIX><<<gridrows(width, height), rowblk, 0, st>>>(dst2mp, tmp2p, pitch, width, height)));
 
     // interpolate the missing lines (:1148-1335): first copy one border row, then the two passes
     if (tff == 1) LAUNCH((k_blit<PIX><<<gridrows(width, 1), rowblk, 0, st>>>(dst2p + (size_t)(height - 2) * pitch, dst2p + (size_t)(height - 1) * pitch, pitch, width, 1)));

@@ -318,6 +318,26 @@ int hb_bench_finish(hb_bench_t *b, hb_bench_stats_t *st)
     return rc;
 }
 
+/* ends the stream WITHOUT the EOF flush: filters are closed with whatever they still buffer (what a cancelled libhb job does).
+ * For throughput samples of the CPU reference, whose flush of a partly filled taskset cycle runs serially and can take
+ * minutes at 4K / 8K without being part of any measurement. */
+int hb_bench_abort(hb_bench_t *b)
+{
+    if (b == NULL) return -1;
+    g_ring = &b->ring;
+    for (int k = 0; k < b->n; k++)
+    {
+        b->f[k]->close(b->f[k]);
+        free_filter(b->f[k]);
+    }
+    ring_destroy(b);
+    pthread_mutex_destroy(&b->ring.lock);
+    free(b->f);
+    free(b->done);
+    free(b);
+    return 0;
+}
+
 static void add_stats(hb_bench_stats_t *a, const hb_bench_stats_t *b)
 {
     a->seconds += b->seconds;

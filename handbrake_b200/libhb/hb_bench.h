@@ -26,6 +26,8 @@ int hb_bench_stream(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frame
 int hb_bench_prefill(hb_bench_t *b, const uint8_t *src, int n_unique, int ring);
 /* EOF, flush, close and free */
 int hb_bench_finish(hb_bench_t *b, hb_bench_stats_t *st);
+/* close and free without the EOF flush (buffered frames are dropped) */
+int hb_bench_abort(hb_bench_t *b);
 /* stream + finish */
 int hb_bench_run(hb_bench_t *b, const uint8_t *src, int n_unique, int n_frames, hb_bench_stats_t *st);
 /* a chain of filters in libhb's order (init, stream, EOF, close); frame_flags = s.flags of every input frame */

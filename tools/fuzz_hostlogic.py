@@ -1,12 +1,62 @@
 """Longer randomised comparisons of the product's host-side filter code (oracle/_ref/libhostlogic.so) with the compiled reference
 (oracle/_ref/libhbref.so) than tests/test_hostlogic.py freezes: random settings per filter, random flag / tag streams through chains
 (pictures, timestamps, flags, durations, frame rate), random pulldown streams.  CPU only.
-usage: python tools/fuzz_hostlogic.py settings|chains|pulldown FIRST_SEED LAST_SEED"""
+usage: python tools/fuzz_hostlogic.py settings|chains|pulldown|multi FIRST_SEED LAST_SEED
+  multi: the multi-device dealing of hb_filter_nlmeans_cuda / lapsharp / unsharp (random device lists, block sizes, windows,
+         prefilters, clip lengths incl. shorter than a block or the window) against the reference's single stream"""
 import sys
 from pathlib import Path
 
 REPO = str(Path(__file__).resolve().parent.parent)
 MODE = sys.argv.pop(1)
+if MODE == "multi":
+    sys.path.insert(0, REPO); sys.path.insert(0, REPO + '/tests')
+    import numpy as np
+    from handbrake_b200 import synth
+    from handbrake_b200.hblib import FilterLib
+    ref = FilterLib(REPO + '/oracle/_ref/libhbref.so')
+    hl = FilterLib(REPO + '/oracle/_ref/libhostlogic.so')
+    FMT = {8: synth.PIX_FMT_YUV420P, 10: synth.PIX_FMT_YUV420P10}
+    a, b = int(sys.argv[1]), int(sys.argv[2])
+    bad = 0
+    for seed in range(a, b):
+        rng = np.random.default_rng(seed)
+        depth = 8 if rng.random() < 0.7 else 10
+        fmt = FMT[depth]
+        w, h = 40, 24
+        n = int(rng.integers(1, 30))
+        clip = synth.progressive_clip(fmt, w, h, n, seed=seed)
+        parts = [f"y-strength={rng.choice([3, 6, 10])}", "y-patch-size=3", f"y-range={int(rng.choice([1, 3]))}"]
+        if rng.random() < 0.7: parts.append(f"y-frame-count={int(rng.integers(1, 6))}")
+        if rng.random() < 0.3: parts.append(f"cb-frame-count={int(rng.integers(1, 4))}")
+        pre = rng.random() < 0.3
+        if pre: parts.append(f"y-prefilter={int(rng.choice([1, 2, 16, 257]))}")
+        base = ":".join(parts)
+        ndev = int(rng.integers(2, 7))
+        multi = f"devices={','.join('0' * ndev)}:block={int(rng.integers(1, 9))}:threads={int(rng.integers(1, 6))}"
+        try:
+            r = ref.run("hb_filter_nlmeans", base + ":threads=1", clip, fmt, w, h)
+            g = hl.run("hb_filter_nlmeans_cuda", base + ":" + multi, clip, fmt, w, h)
+            ok = r.frames.shape == g.frames.shape and np.array_equal(r.frames, g.frames) and np.array_equal(r.start, g.start) and g.saw_eof
+        except RuntimeError as e:
+            ok = False
+            print("EXC", e)
+        if not ok:
+            bad += 1
+            print("MISMATCH nlmeans", seed, base, multi, n)
+        clip = synth.progressive_clip(fmt, 88, 50, int(rng.integers(1, 40)), seed=seed, noise=15)
+        for rname, gname, st in (("hb_filter_lapsharp_mt", "hb_filter_lapsharp_cuda", "y-strength=0.4"), ("hb_filter_unsharp_mt", "hb_filter_unsharp_cuda", "y-strength=0.5:y-size=5")):
+            r = ref.run(rname, st, clip, fmt, 88, 50)
+            g = hl.run(gname, st + f":devices={','.join('0' * ndev)}", clip, fmt, 88, 50)
+            if not (np.array_equal(r.frames, g.frames) and np.array_equal(r.start, g.start)):
+                bad += 1
+                print("MISMATCH", gname, seed, ndev)
+        if hl.buffers_alive() != 0:
+            bad += 1
+            print("LEAK", seed, hl.buffers_alive())
+    print("multi seeds", a, b, "bad", bad)
+    sys.exit(1 if bad else 0)
+
 if MODE == "settings":
     sys.path.insert(0, REPO); sys.path.insert(0, REPO + '/tests')
     import numpy as np
