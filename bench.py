@@ -507,7 +507,7 @@ def cpu_baseline_nlmeans(wl, budget_s, host=None):
                          chunk=threads, budget_s=budget_s, min_chunks=3, warm_chunks=0)
     return r, {"value": round(r["fps"], 4), "unit": "frames/s", "cores": threads, "kind": "reference",
                "sample": f"{r['frames']} frames of {wl['desc']}: one continuous stream, {r['chunks']} taskset cycles of {threads} frames "
-                         f"(the filter's own thread heuristic), EOF flush after the clock, {r['seconds']:.1f} s",
+                         f"(the filter's own thread heuristic), no EOF flush, {r['seconds']:.1f} s",
                "host_logical_cpus": r["ncpu"],
                "what": "HandBrake libhb nlmeans.c + nlmeans_x86.c (SSE2) compiled unmodified, gcc -O3 -msse2"}
 

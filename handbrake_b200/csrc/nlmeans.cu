@@ -2617,9 +2617,15 @@ int hbcu_nlmeans_upload_peer(hbcu_nlmeans_t *dst, int64_t dst_index, hbcu_nlmean
     HBCU_CHECK(cudaSetDevice(ddev));
     if (ddev != sdev)
     {
-        // direct NVLink path; without peer access the copy is staged by the driver (still correct)
-        const cudaError_t e = cudaDeviceEnablePeerAccess(sdev, 0);
-        if (e != cudaSuccess) cudaGetLastError();       // already enabled, or not supported: cudaMemcpyPeerAsync copes
+        // direct NVLink path, asked for once per ordered pair of devices; without peer access the copy is staged by the
+        // driver (still correct)
+        static bool asked[kMaxDevices][kMaxDevices] = {};
+        bool &done = asked[ddev & (kMaxDevices - 1)][sdev & (kMaxDevices - 1)];
+        if (!done)
+        {
+            if (cudaDeviceEnablePeerAccess(sdev, 0) != cudaSuccess) cudaGetLastError();   // already enabled, or not supported
+            done = true;
+        }
     }
     // the destination slot is free once the kernels reading its previous frame are done (and no peer reads it)
     HBCU_CHECK(cudaStreamWaitEvent(dst->s_pad, dst->ev_readers[2 * dslot], 0));
