@@ -20,18 +20,26 @@
 #include "hbcu_device_frames.h"
 
 #define PARITY_DEFAULT -1
-#define DECOMB_MAX_PENDING 16
+#define DECOMB_MAX_PENDING 64
+#define DECOMB_BLOCK_DEFAULT 8
 
 typedef struct
 {
     hb_buffer_t *buf;       /* output picture */
     int64_t      ticket;    /* >= 0: the GPU is still writing it; -1: ready (pass-through) */
+    int          dev;       /* which of pv->gpu[] wrote it */
 } decomb_pending_t;
 
 struct hb_filter_private_s
 {
     int device, device_out;        /* device_out: pictures leave as HBCU_DEVICE buffers (hw_pix_fmt == AV_PIX_FMT_CUDA) */
-    hbcu_decomb_t *gpu;
+    /* several GPUs (setting `devices=` / HBCU_DEVICES; not with EEDI2, whose edge mask carries state from field to field):
+     * the ordered stream is dealt block-cyclically -- `block` frames per device in turn (mt_frame_filter.c:169-237 deals
+     * frames to threads the same way); a picture reads prev / cur / next, so the first and the last frame of a block are
+     * uploaded to the neighbouring block's device as well */
+    int ndev, devices[HBCU_MAX_DEVICES], block;
+    hbcu_decomb_t *gpu[HBCU_MAX_DEVICES];
+    unsigned ref_devs[3];          /* devices (bit mask) ref[k] was uploaded to */
     int mode;
     int parity;
 
@@ -127,17 +135,30 @@ static int decomb_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     cfg.depth          = desc->comp[0].depth;
     cfg.chroma_shift_w = desc->log2_chroma_w;
     cfg.chroma_shift_h = desc->log2_chroma_h;
-    cfg.device         = hbcu_env_device();
-    pv->device         = cfg.device;
+    pv->ndev           = hbcu_settings_devices(filter->settings, pv->devices);
+    pv->block          = DECOMB_BLOCK_DEFAULT;
+    if (filter->settings) hb_dict_extract_int(&pv->block, filter->settings, "block");
+    if (pv->block < 1) pv->block = 1;
     pv->device_out     = hbcu_init_wants_device_output(init);
-    pv->inflight_max   = 6;
-    cfg.slots          = 6;
-    cfg.out_slots      = pv->inflight_max + 2;
-    cfg.mode           = pv->mode;
-    if (hbcu_decomb_create(&pv->gpu, &cfg) != 0)
+    if (pv->ndev < 1 || (pv->ndev > 1 && (pv->device_out || (pv->mode & HBCU_DECOMB_EEDI2))))
     {
-        hb_error("decomb(cuda): %s", hbcu_last_error());
+        hb_error("decomb(cuda): %s", pv->ndev < 1 ? "bad `devices` setting"
+                 : "several devices need host output and a mode without EEDI2 (its edge mask carries state between fields)");
         goto fail;
+    }
+    pv->device         = pv->devices[0];
+    pv->inflight_max   = 6 * pv->ndev < DECOMB_MAX_PENDING - 4 ? 6 * pv->ndev : DECOMB_MAX_PENDING - 4;
+    cfg.slots          = pv->ndev > 1 ? pv->block + 6 : 6;
+    cfg.out_slots      = 6 + 2 + 2;
+    cfg.mode           = pv->mode;
+    for (int d = 0; d < pv->ndev; d++)
+    {
+        cfg.device = pv->devices[d];
+        if (hbcu_decomb_create(&pv->gpu[d], &cfg) != 0)
+        {
+            hb_error("decomb(cuda): %s", hbcu_last_error());
+            goto fail;
+        }
     }
     pv->ref_index[0] = pv->ref_index[1] = pv->ref_index[2] = -1;
 
@@ -149,9 +170,17 @@ static int decomb_cuda_init(hb_filter_object_t *filter, hb_filter_init_t *init)
     return 0;
 
 fail:
+    for (int d = 0; d < HBCU_MAX_DEVICES; d++)
+        if (pv->gpu[d] != NULL) hbcu_decomb_destroy(pv->gpu[d]);
     free(pv);
     filter->private_data = NULL;
     return -1;
+}
+
+/* block-cyclic owner of stream frame t */
+static int owner_of(const hb_filter_private_t *pv, int64_t t)
+{
+    return pv->ndev == 1 || t < 0 ? 0 : (int)((t / pv->block) % pv->ndev);
 }
 
 static void decomb_cuda_close(hb_filter_object_t *filter)
@@ -163,7 +192,8 @@ static void decomb_cuda_close(hb_filter_object_t *filter)
         hb_log("decomb: deinterlaced %i | blended %i | unfiltered %i | total %i",
                pv->deinterlaced, pv->blended, pv->unfiltered, pv->frames);
     }
-    if (pv->gpu != NULL) hbcu_decomb_destroy(pv->gpu);      /* waits for in-flight copies */
+    for (int d = 0; d < pv->ndev; d++)
+        if (pv->gpu[d] != NULL) hbcu_decomb_destroy(pv->gpu[d]);      /* waits for in-flight copies */
     for (int i = 0; i < pv->count; i++)
         hb_buffer_close(&pv->pending[(pv->head + i) % DECOMB_MAX_PENDING].buf);
     for (int ii = 0; ii < 3; ii++)
@@ -172,20 +202,23 @@ static void decomb_cuda_close(hb_filter_object_t *filter)
     filter->private_data = NULL;
 }
 
-static void store_ref(hb_filter_private_t *pv, hb_buffer_t *b, int64_t index)
+static void store_ref(hb_filter_private_t *pv, hb_buffer_t *b, int64_t index, unsigned devs)
 {
-    /* the upload of a frame reads its buffer asynchronously: make sure it is over before the
-     * buffer goes back to the pool (normally long done -- the frame entered three calls ago) */
+    /* the upload of a frame reads its buffer asynchronously: make sure it is over (on every device it went to) before
+     * the buffer goes back to the pool (normally long done -- the frame entered three calls ago) */
     if (pv->ref[0] != NULL && pv->ref_index[0] >= 0 && hbcu_buffer_frame(pv->ref[0]) == NULL)
-        hbcu_decomb_wait_upload(pv->gpu, pv->ref_index[0]);
+        for (int d = 0; d < pv->ndev; d++)
+            if (pv->ref_devs[0] & (1u << d)) hbcu_decomb_wait_upload(pv->gpu[d], pv->ref_index[0]);
     hb_buffer_close(&pv->ref[0]);
     for (int k = 0; k < 2; k++)
     {
         pv->ref[k]       = pv->ref[k + 1];
         pv->ref_index[k] = pv->ref_index[k + 1];
+        pv->ref_devs[k]  = pv->ref_devs[k + 1];
     }
     pv->ref[2]       = b;
     pv->ref_index[2] = index;
+    pv->ref_devs[2]  = devs;
 }
 
 /* move finished pictures (oldest first) to the list */
@@ -199,11 +232,11 @@ static int harvest(hb_filter_private_t *pv, hb_buffer_list_t *list, int min_free
             const int must_wait = all || (DECOMB_MAX_PENDING - pv->count) < min_free || pv->count > pv->inflight_max;
             if (must_wait)
             {
-                if (hbcu_decomb_wait(pv->gpu, p->ticket) != 0) goto gpu_error;
+                if (hbcu_decomb_wait(pv->gpu[p->dev], p->ticket) != 0) goto gpu_error;
             }
             else
             {
-                const int done = hbcu_decomb_poll(pv->gpu, p->ticket);
+                const int done = hbcu_decomb_poll(pv->gpu[p->dev], p->ticket);
                 if (done < 0) goto gpu_error;
                 if (done == 0) break;
             }
@@ -220,11 +253,12 @@ gpu_error:
     return -1;
 }
 
-static void push_pending(hb_filter_private_t *pv, hb_buffer_t *buf, int64_t ticket)
+static void push_pending(hb_filter_private_t *pv, hb_buffer_t *buf, int64_t ticket, int dev)
 {
     decomb_pending_t *p = &pv->pending[(pv->head + pv->count) % DECOMB_MAX_PENDING];
     p->buf    = buf;
     p->ticket = ticket;
+    p->dev    = dev;
     pv->count++;
 }
 
@@ -234,7 +268,7 @@ static int process_frame(hb_filter_private_t *pv)
     hb_buffer_t *cur = pv->ref[1];
     if ((pv->mode & HBCU_DECOMB_SELECTIVE) && cur->s.combed == HB_COMB_NONE)
     {
-        push_pending(pv, hb_buffer_shallow_dup(cur), -1);
+        push_pending(pv, hb_buffer_shallow_dup(cur), -1, 0);
         pv->frames++;
         pv->unfiltered++;
         return 0;
@@ -251,6 +285,7 @@ static int process_frame(hb_filter_private_t *pv)
         tff = (pv->parity & 1) ^ 1;
     }
     const int num_frames = (pv->mode & HBCU_DECOMB_BOB) ? 2 : 1;
+    const int dev = owner_of(pv, pv->ref_index[1]);        /* prev and next were uploaded there too */
     hb_buffer_t *made[2] = { NULL, NULL };
     for (int frame = 0; frame < num_frames; frame++)
     {
@@ -286,9 +321,9 @@ static int process_frame(hb_filter_private_t *pv)
         /* `mode` keeps the bob bit: the reference tests `mode == BLEND` / `mode == CUBIC` on it
          * (decomb template :756,:776), so e.g. cubic+bob runs no line filter at all */
         const int rc = pv->device_out
-            ? hbcu_decomb_filter_frame(pv->gpu, ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2], mode, parity, tff,
+            ? hbcu_decomb_filter_frame(pv->gpu[dev], ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2], mode, parity, tff,
                                        hbcu_buffer_frame(buf))
-            : hbcu_decomb_filter(pv->gpu, ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2], mode, parity, tff,
+            : hbcu_decomb_filter(pv->gpu[dev], ticket, pv->ref_index[0], pv->ref_index[1], pv->ref_index[2], mode, parity, tff,
                                  planes, strides);
         if (rc != 0)
         {
@@ -299,7 +334,7 @@ static int process_frame(hb_filter_private_t *pv)
         hb_buffer_copy_props(buf, cur);
         made[frame] = buf;
         /* a device picture needs no wait: its consumer orders itself behind the kernel through the frame's events */
-        push_pending(pv, buf, pv->device_out ? -1 : ticket);
+        push_pending(pv, buf, pv->device_out ? -1 : ticket, dev);
     }
     if (pv->mode & HBCU_DECOMB_BOB)
     {
@@ -326,7 +361,7 @@ static int decomb_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, hb
         if (pv->ref[2] != NULL)
         {
             /* the last frame is its own successor: same pixels, no second upload */
-            store_ref(pv, hb_buffer_shallow_dup(pv->ref[2]), pv->ref_index[2]);
+            store_ref(pv, hb_buffer_shallow_dup(pv->ref[2]), pv->ref_index[2], pv->ref_devs[2]);
             if (harvest(pv, &list, 2, 0) != 0 || process_frame(pv) != 0) failed = 1;
         }
         if (!failed && harvest(pv, &list, 0, 1) != 0) failed = 1;
@@ -344,20 +379,38 @@ static int decomb_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in, hb
         strides[c] = in->plane[c].stride;
     }
     hbcu_frame_t *fin = hbcu_buffer_frame(in);
-    if ((fin != NULL ? hbcu_decomb_upload_frame(pv->gpu, index, fin) : hbcu_decomb_upload(pv->gpu, index, planes, strides)) != 0)
+    if (fin != NULL && pv->ndev > 1)
     {
-        hb_error("decomb(cuda): %s", hbcu_last_error());
+        hb_error("decomb(cuda): device-resident input needs a single device");
         hb_buffer_close(&in);
         return HB_FILTER_FAILED;
     }
+    /* the frame goes to its owner and, as the `next` of the previous block's last frame / the `prev` of the next block's
+     * first frame, to that block's device as well */
+    unsigned devs = 1u << owner_of(pv, index);
+    if (pv->ndev > 1)
+    {
+        if (index % pv->block == 0 && index > 0) devs |= 1u << owner_of(pv, index - 1);
+        if (index % pv->block == pv->block - 1)  devs |= 1u << owner_of(pv, index + 1);
+    }
+    for (int d = 0; d < pv->ndev; d++)
+    {
+        if (!(devs & (1u << d))) continue;
+        if ((fin != NULL ? hbcu_decomb_upload_frame(pv->gpu[d], index, fin) : hbcu_decomb_upload(pv->gpu[d], index, planes, strides)) != 0)
+        {
+            hb_error("decomb(cuda): %s", hbcu_last_error());
+            hb_buffer_close(&in);
+            return HB_FILTER_FAILED;
+        }
+    }
     if (!pv->ready)
     {
-        store_ref(pv, hb_buffer_shallow_dup(in), index);
-        store_ref(pv, in, index);
+        store_ref(pv, hb_buffer_shallow_dup(in), index, devs);
+        store_ref(pv, in, index, devs);
         pv->ready = 1;
         return HB_FILTER_DELAY;
     }
-    store_ref(pv, in, index);
+    store_ref(pv, in, index, devs);
     if (harvest(pv, &list, 2, 0) != 0 || process_frame(pv) != 0 || harvest(pv, &list, 0, 0) != 0)
     {
         hb_buffer_list_close(&list);

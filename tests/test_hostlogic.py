@@ -390,3 +390,21 @@ def test_frame_parallel_filters_dealt_over_devices(ref, hostlogic, devices):
     bad = hostlogic.run("hb_filter_lapsharp_cuda", "y-strength=0.3:devices=0,,1", clip, FMT[8], w, h)
     assert bad.init_failed
     assert hostlogic.buffers_alive() == 0
+
+
+@pytest.mark.parametrize("devices,block", [("0,0", 3), ("0,0,0", 2), ("0,0", 1), ("0,0,0,0", 4)])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_decomb_dealt_over_devices(ref, hostlogic, devices, block, depth):
+    """decomb (yadif / blend / cubic / bob / selective, no EEDI2) with `devices=`: block-cyclic owners, the first and the
+    last frame of a block also uploaded to the neighbouring block's device (prev / next), pictures out in order == the
+    reference; EEDI2 modes refuse several devices at init"""
+    w, h = 96, 64
+    clip, flags, combed = decomb_inputs(depth, w, h, 11, seed=14)
+    for mode, tags in ((7, None), (39, combed), (23, None), (4, None), (2, None), (55, combed)):
+        r = ref.run("hb_filter_decomb", f"mode={mode}", clip, FMT[depth], w, h, flags=flags, combed=tags)
+        g = hostlogic.run("hb_filter_decomb_cuda", f"mode={mode}:devices={devices}:block={block}", clip, FMT[depth], w, h, flags=flags, combed=tags)
+        same_stream(r, g)
+        assert r.vrate == g.vrate
+    g = hostlogic.run("hb_filter_decomb_cuda", f"mode=15:devices={devices}", clip, FMT[depth], w, h, flags=flags)
+    assert g.init_failed
+    assert hostlogic.buffers_alive() == 0

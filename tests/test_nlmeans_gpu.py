@@ -137,6 +137,18 @@ def test_both_ssd_formulations(ref, cuda_filters, monkeypatch, ssd):
         assert_same(r, g)
 
 
+@pytest.mark.parametrize("fmt", [FMT8, FMT10])
+def test_round1_kernels_still_agree(ref, cuda_filters, monkeypatch, fmt):
+    """HBCU_NLMEANS_V3=off selects the round-1 fused kernels (nlmeans_fast8 / fast16), the baseline of the v3 levers in
+    profiles/r02b_v3_shape_sweep.txt: they stay bit-exact"""
+    monkeypatch.setenv("HBCU_NLMEANS_V3", "off")
+    w, h = 330, 210
+    clip = synth.progressive_clip(fmt, w, h, 4, seed=33)
+    for s in ("y-strength=6", "y-strength=10:y-patch-size=5:y-range=5:y-frame-count=3"):
+        r, g = run_both(ref, cuda_filters, s, clip, fmt, w, h)
+        assert_same(r, g)
+
+
 def clip10_extreme(w, h, seed=9):
     """full-range 10-bit noise, flat 0 and flat 1023 frames (worst case for the fp32-exact row sums: d = 1023 everywhere)"""
     n = synth.frame_bytes(FMT10, w, h) // 2

@@ -92,3 +92,17 @@ def test_frame_parallel_filters_over_devices(ref, cuda_filters):
         for devs in lists:
             same(r, cuda_filters.run(name, settings + ":devices=" + devs, clip, FMT8, w, h))
     assert cuda_filters.buffers_alive() == 0
+
+
+def test_decomb_over_devices(ref, cuda_filters):
+    """decomb without EEDI2 dealt over two handles of one GPU (and two GPUs when visible) == the reference"""
+    from test_oracle import decomb_inputs
+    w, h = 352, 288
+    clip, flags, combed = decomb_inputs(8, w, h, 13, seed=6)
+    lists = [("0,0", 3), ("0,0,0", 1)] + ([("0,1", 4)] if device_count() >= 2 else [])
+    for mode, tags in ((7, None), (39, combed), (23, None)):
+        r = ref.run("hb_filter_decomb", f"mode={mode}", clip, FMT8, w, h, flags=flags, combed=tags)
+        for devs, block in lists:
+            g = cuda_filters.run("hb_filter_decomb_cuda", f"mode={mode}:devices={devs}:block={block}", clip, FMT8, w, h, flags=flags, combed=tags)
+            same(r, g)
+    assert cuda_filters.buffers_alive() == 0
