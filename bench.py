@@ -321,7 +321,8 @@ def plane_ptrs(t, dims, bps):
 def ncu_capture(workload, depth):
     """numbers of the committed `ncu --set full` capture of this workload's kernel (never measured live: a run under
     ncu is not a bench value)"""
-    names = {("4k_nlmeans_strong", 8): ["r02_nlmeans_v3_ncu.json", "r01g_nlmeans_fused_ncu.json"]}
+    names = {("4k_nlmeans_strong", 8): ["r02_nlmeans_v3_ncu.json", "r01g_nlmeans_fused_ncu.json"],
+             ("4k10_nlmeans_medium", 10): ["r02_nlmeans_v3w_ncu.json"]}
     for n in names.get((workload, depth), []):
         p = REPO / "profiles" / n
         if p.exists():

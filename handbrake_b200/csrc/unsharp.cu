@@ -45,21 +45,46 @@ template <typename PIX, int S>
 __global__ void __launch_bounds__(kThreads) unsharp_kernel(const UnsharpParams p)
 {
     constexpr int N = 2 * S + 1;
-    constexpr int SW = kTW + 2 * S + 2;           // source tile pitch (elements), +2 keeps rows 4-byte aligned for any S
+    constexpr int EPW = 4 / (int)sizeof(PIX);                     // samples per 32-bit word
+    // source tile: columns X0 - S - lead .. X0 + kTW + S, where lead = (X0 - S) mod EPW aligns the tile's first column to
+    // a word of the (word-aligned) source row; the pitch keeps every tile row word aligned too
+    constexpr int SW = (kTW + 2 * S + (EPW - 1) + EPW - 1) / EPW * EPW + EPW;
     constexpr int SR = kTH + 2 * S;               // source tile rows
-    __shared__ PIX      s_src[SR * SW];
+    __shared__ __align__(16) PIX      s_src[SR * SW];
     __shared__ __align__(16) uint32_t s_h[SR * kTW];
     const PIX *src = (const PIX *)p.src;
     PIX *dst = (PIX *)p.dst;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int tid = threadIdx.x;
-
-    // stage the tile with the edge pixel replicated (x <= 0 -> src[0], x >= w -> src[w-1]; rows likewise)
-    for (int i = tid; i < SR * (kTW + 2 * S); i += kThreads)
+    const int xs = X0 - S;                                        // first staged column (may be negative at the left edge)
+    const int lead = ((xs % EPW) + EPW) % EPW;                    // staged column c sits at s_src[r * SW + lead + c]
+    const bool interior = xs - lead >= 0 && X0 + kTW + S <= p.w && Y0 - S >= 0 && Y0 + kTH + S <= p.h &&
+                          ((uintptr_t)src % 4 == 0) && (((size_t)p.spitch * sizeof(PIX)) % 4 == 0);
+    if (interior)
     {
-        const int r = i / (kTW + 2 * S), c = i - r * (kTW + 2 * S);
-        const int y = min(max(Y0 + r - S, 0), p.h - 1), x = min(max(X0 + c - S, 0), p.w - 1);
-        s_src[r * SW + c] = src[(size_t)y * p.spitch + x];
+        // no clamping anywhere in this tile: aligned 32-bit words straight from the row (read-only path) into the tile
+        constexpr int WPR = (kTW + 2 * S + 2 * (EPW - 1) + EPW - 1) / EPW;       // words per tile row (covers any lead)
+        const int x_word0 = xs - lead;
+        for (int i = tid; i < SR * WPR; i += kThreads)
+        {
+            const int r = i / WPR, wq = i - r * WPR;
+            const int x = x_word0 + wq * EPW;
+            if (x < p.spitch)
+            {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(Y0 + r - S) * p.spitch + x));
+                *reinterpret_cast<uint32_t *>(&s_src[r * SW + wq * EPW]) = v;
+            }
+        }
+    }
+    else
+    {
+        // stage the tile with the edge pixel replicated (x <= 0 -> src[0], x >= w -> src[w-1]; rows likewise)
+        for (int i = tid; i < SR * (kTW + 2 * S); i += kThreads)
+        {
+            const int r = i / (kTW + 2 * S), c = i - r * (kTW + 2 * S);
+            const int y = min(max(Y0 + r - S, 0), p.h - 1), x = min(max(X0 + c - S, 0), p.w - 1);
+            s_src[r * SW + lead + c] = src[(size_t)y * p.spitch + x];
+        }
     }
     __syncthreads();
     // horizontal binomial sums, 4 outputs per item share their 4 + 2S inputs
@@ -68,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) unsharp_kernel(const UnsharpParams p
         const int r = i / (kTW / 4), x4 = (i - r * (kTW / 4)) * 4;
         uint32_t v[4 + 2 * S];
 #pragma unroll
-        for (int k = 0; k < 4 + 2 * S; k++) v[k] = s_src[r * SW + x4 + k];
+        for (int k = 0; k < 4 + 2 * S; k++) v[k] = s_src[r * SW + lead + x4 + k];
         uint32_t a[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int k = 0; k < N; k++)
@@ -80,34 +105,61 @@ __global__ void __launch_bounds__(kThreads) unsharp_kernel(const UnsharpParams p
         *reinterpret_cast<uint4 *>(&s_h[r * kTW + x4]) = make_uint4(a[0], a[1], a[2], a[3]);
     }
     __syncthreads();
-    // vertical sums + the sharpening / smoothing expression, 4 rows per item share their 4 + 2S inputs
+    // vertical sums + the sharpening / smoothing expression: one item = 4 rows x 4 columns (the 4 + 2S rows of horizontal
+    // sums arrive as 128-bit words, the results leave as one vector store per row); 8 x 32 items = one per thread
     constexpr int scalebits = 4 * S;
     constexpr uint32_t halfscale = 1u << (scalebits - 1);
-    for (int i = tid; i < (kTH / 4) * kTW; i += kThreads)
+    for (int i = tid; i < (kTH / 4) * (kTW / 4); i += kThreads)
     {
-        const int y4 = (i / kTW) * 4, x = i - (i / kTW) * kTW;
-        if (X0 + x >= p.w) continue;
-        uint32_t v[4 + 2 * S];
+        const int y4 = (i / (kTW / 4)) * 4, x4 = (i - (i / (kTW / 4)) * (kTW / 4)) * 4;
+        if (X0 + x4 >= p.w || Y0 + y4 >= p.h) continue;
+        uint32_t a[4][4];
 #pragma unroll
-        for (int k = 0; k < 4 + 2 * S; k++) v[k] = s_h[(y4 + k) * kTW + x];
-        uint32_t a[4] = { 0, 0, 0, 0 };
+        for (int j = 0; j < 4; j++)
 #pragma unroll
-        for (int k = 0; k < N; k++)
+            for (int q = 0; q < 4; q++) a[j][q] = 0;
+#pragma unroll
+        for (int k = 0; k < 4 + 2 * S; k++)
         {
-            const uint32_t c = p.coef[k];
+            const uint4 hv = *reinterpret_cast<const uint4 *>(&s_h[(y4 + k) * kTW + x4]);
+            const uint32_t h4[4] = { hv.x, hv.y, hv.z, hv.w };
 #pragma unroll
-            for (int j = 0; j < 4; j++) a[j] += c * v[j + k];
+            for (int j = 0; j < 4; j++)
+            {
+                // row k of the window feeds output row j with coefficient index k - j
+                if (k - j < 0 || k - j >= N) continue;
+                const uint32_t c = p.coef[k - j];
+#pragma unroll
+                for (int q = 0; q < 4; q++) a[j][q] += c * h4[q];
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; j++)
         {
             const int y = Y0 + y4 + j;
             if (y >= p.h) break;
-            const int32_t sv = (int32_t)s_src[(y4 + j + S) * SW + x + S];
-            const int32_t blur = (int32_t)((a[j] + halfscale) >> scalebits);
-            const int32_t delta = (int32_t)((uint32_t)(sv - blur) * (uint32_t)p.amount) >> 16;   // 32-bit product, arithmetic shift
-            const int32_t res = p.smooth ? sv - delta : sv + delta;
-            dst[(size_t)y * p.dpitch + X0 + x] = (PIX)(res > p.maxv ? p.maxv : res < p.minv ? p.minv : res);
+            int out[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int32_t sv = (int32_t)s_src[(y4 + j + S) * SW + lead + x4 + q + S];
+                const int32_t blur = (int32_t)((a[j][q] + halfscale) >> scalebits);
+                const int32_t delta = (int32_t)((uint32_t)(sv - blur) * (uint32_t)p.amount) >> 16;   // 32-bit product, arithmetic shift
+                const int32_t res = p.smooth ? sv - delta : sv + delta;
+                out[q] = res > p.maxv ? p.maxv : res < p.minv ? p.minv : res;
+            }
+            PIX *drow = dst + (size_t)y * p.dpitch + X0 + x4;
+            if (X0 + x4 + 3 < p.w && ((uintptr_t)drow % (4 * sizeof(PIX))) == 0)
+            {
+                if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(drow) = make_uchar4(out[0], out[1], out[2], out[3]);
+                else                  *reinterpret_cast<ushort4 *>(drow) = make_ushort4(out[0], out[1], out[2], out[3]);
+            }
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (X0 + x4 + q < p.w) drow[q] = (PIX)out[q];
+            }
         }
     }
 }
