@@ -52,15 +52,30 @@ __global__ void __launch_bounds__(128) hqdn3d_h_kernel(const PIX *__restrict__ s
     if (row0 >= h) return;
     const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1, lsh = depth == 16 ? 0 : 4;
     int p = 0;
+    // The chain of dependent table lookups is the kernel's critical path; the global loads of the NEXT 32 x 32 tile are
+    // issued before the chain of the current one starts and land in registers while it runs (round 2: the loads used to
+    // sit exposed between two chains -- ~2000 cycles per tile at one warp per 32 rows).
+    uint16_t nxt[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++)
+    {
+        const int y = row0 + r, x = lane;
+        nxt[r] = (y < h && x < w) ? (uint16_t)load16(src + (size_t)y * spitch + x, sh, bias) : 0;
+    }
     for (int x0 = 0; x0 < w; x0 += 32)
     {
-#pragma unroll 8
-        for (int r = 0; r < 32; r++)
-        {
-            const int y = row0 + r, x = x0 + lane;
-            tile[warp][r][lane] = (y < h && x < w) ? (uint16_t)load16(src + (size_t)y * spitch + x, sh, bias) : 0;
-        }
+#pragma unroll
+        for (int r = 0; r < 32; r++) tile[warp][r][lane] = nxt[r];
         __syncwarp();
+        if (x0 + 32 < w)
+        {
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+            {
+                const int y = row0 + r, x = x0 + 32 + lane;
+                nxt[r] = (y < h && x < w) ? (uint16_t)load16(src + (size_t)y * spitch + x, sh, bias) : 0;
+            }
+        }
         if (row < h)
         {
             // the row's 32 samples first (independent loads), then the dependent chain: one table lookup per step
@@ -115,19 +130,28 @@ __global__ void __launch_bounds__(128) hqdn3d_vt_kernel(const PIX *__restrict__ 
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
     const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1, lsh = depth == 16 ? 0 : 4;
-    constexpr int U = 16;                                  // rows fetched ahead of the dependent chain
+    constexpr int U = 16;                                  // rows per batch: the NEXT batch is fetched while this one's chain runs
     int v = 0;
-    for (int y0 = 0; y0 < h; y0 += U)
-    {
-        int cur[U], a[U];
+    int ncur[U], na[U];
+    auto fetch = [&](int y0) {
 #pragma unroll
         for (int k = 0; k < U; k++)
         {
             const int y = min(y0 + k, h - 1);
             const int s = load16(src + (size_t)y * spitch + x, sh, bias);
-            cur[k] = SPATIAL ? (int)hbuf[(size_t)y * w + x] : s;
-            a[k] = first ? s : (int)ant[(size_t)y * w + x];            // denoise.c:175-189: the state starts as the first frame
+            ncur[k] = SPATIAL ? (int)hbuf[(size_t)y * w + x] : s;
+            na[k] = first ? s : (int)ant[(size_t)y * w + x];           // denoise.c:175-189: the state starts as the first frame
         }
+    };
+    fetch(0);
+    for (int y0 = 0; y0 < h; y0 += U)
+    {
+        int cur[U], a[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { cur[k] = ncur[k]; a[k] = na[k]; }
+        // rows y0+U .. y0+2U-1 are not written before this batch's stores (a thread owns its column), so fetching `ant`
+        // ahead of them is safe
+        if (y0 + U < h) fetch(y0 + U);
 #pragma unroll
         for (int k = 0; k < U; k++)
         {
