@@ -167,6 +167,281 @@ __global__ void __launch_bounds__(128) hqdn3d_vt_kernel(const PIX *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Round 2: warp-specialised kernels.  ncu showed the kernels above at 6-14 cycles per instruction: one warp per scheduler
+// executes ~50 instructions per sample (address arithmetic, guards, conversions, stores) in series with its lookup chain.
+// Here the chain warp does nothing but the chain -- samples come from and go back to shared memory as 16-bit values, 8 at
+// a time -- and helper warps of the same CTA move the tiles (16-byte global accesses, conversion, and in the V+T pass the
+// temporal low-pass, which is not recursive within a frame).  A three-deep ring of tiles is handed on with one
+// __syncthreads per step: helper loads tile s, chain works on tile s-1, helper retires tile s-2.
+// Requirements (checked by the launcher, the kernels above remain for everything else): depth < 16 (tables in shared
+// memory, index shift 4), width a multiple of 8, 16-byte aligned planes and pitches.
+constexpr int kTileW = 128, kTilePitch = kTileW * 2 + 16;       // bytes per tile row: 17 x 16 B, conflict free for LDS.128 by row
+
+__device__ __forceinline__ int lut_at(const int16_t *centre, int d)
+{
+    // centre[d >> 4] with the index scaled to bytes in two instructions: (d >> 3) & ~1
+    return *reinterpret_cast<const int16_t *>(reinterpret_cast<const char *>(centre) + ((d >> 3) & ~1));
+}
+
+template <typename PIX>
+__device__ __forceinline__ void widen_store(unsigned char *dst, const PIX *src, int sh, int bias)
+{
+    // 16 (8-bit) or 8 (16-bit) samples -> LOAD()'s 16-bit fixed point (denoise.c:33), stored as 16-byte vectors
+    const uint32_t b2 = (uint32_t)bias * 0x10001u;
+    if (sizeof(PIX) == 1)
+    {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src));
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            o[2 * i]     = __byte_perm(w[i], 0, 0x1404) + b2;        // bytes 0, 1 -> the high bytes of two halves (sh = 8)
+            o[2 * i + 1] = __byte_perm(w[i], 0, 0x3424) + b2;
+        }
+        *reinterpret_cast<uint4 *>(dst)      = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    else
+    {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src));
+        *reinterpret_cast<uint4 *>(dst) = make_uint4((q.x << sh) + b2, (q.y << sh) + b2, (q.z << sh) + b2, (q.w << sh) + b2);
+    }
+}
+
+__device__ __forceinline__ void stage_lut(int16_t *dst, const int16_t *__restrict__ table, int entries)
+{
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(table);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int i = threadIdx.x; i < entries / 8; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+// H pass: CTA = 32 rows; warp 0 = chain (lane = row), warp 1 = helper
+template <typename PIX>
+__global__ void __launch_bounds__(64) hqdn3d_h2_kernel(const PIX *__restrict__ src, int spitch, uint16_t *__restrict__ hbuf,
+                                                      int w, int h, int depth, const int16_t *__restrict__ table, int half)
+{
+    extern __shared__ __align__(16) unsigned char smem2[];
+    int16_t *s_lut = reinterpret_cast<int16_t *>(smem2);
+    unsigned char *tiles = smem2 + (size_t)2 * half * sizeof(int16_t);
+    stage_lut(s_lut, table, 2 * half);
+    __syncthreads();
+    const int16_t *coef = s_lut + half;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row0 = blockIdx.x * 32;
+    const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1;
+    const int ntiles = (w + kTileW - 1) / kTileW;
+    constexpr int SPV = 16 / (int)sizeof(PIX);            // samples per 16-byte global load
+    int p = 0;
+    for (int s = 0; s < ntiles + 2; s++)
+    {
+        if (warp == 1)
+        {
+            if (s < ntiles)
+            {
+                unsigned char *buf = tiles + (size_t)(s % 3) * 32 * kTilePitch;
+                constexpr int LPR = kTileW / SPV;         // lanes per row
+#pragma unroll
+                for (int it = 0; it < 32 * LPR / 32; it++)
+                {
+                    const int r = (it * 32 + lane) / LPR, c = ((it * 32 + lane) % LPR) * SPV;
+                    const int y = row0 + r, x = s * kTileW + c;
+                    // samples outside the plane are zeros: the chain walks over them (results dropped) and must stay inside the table
+                    if (y < h && x < w) widen_store<PIX>(buf + r * kTilePitch + c * 2, src + (size_t)y * spitch + x, sh, bias);
+                    else
+                    {
+                        *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2) = make_uint4(0, 0, 0, 0);
+                        if (sizeof(PIX) == 1) *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2 + 16) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+            }
+            if (s >= 2)
+            {
+                const unsigned char *buf = tiles + (size_t)((s - 2) % 3) * 32 * kTilePitch;
+#pragma unroll
+                for (int it = 0; it < 16; it++)
+                {
+                    const int r = it * 2 + (lane >> 4), c = (lane & 15) * 8;
+                    const int y = row0 + r, x = (s - 2) * kTileW + c;
+                    if (y < h && x < w)
+                        *reinterpret_cast<uint4 *>(hbuf + (size_t)y * w + x) = *reinterpret_cast<const uint4 *>(buf + r * kTilePitch + c * 2);
+                }
+            }
+        }
+        else if (s >= 1 && s <= ntiles)
+        {
+            unsigned char *rowp = tiles + (size_t)((s - 1) % 3) * 32 * kTilePitch + lane * kTilePitch;
+            uint4 q = *reinterpret_cast<const uint4 *>(rowp);
+#pragma unroll 2
+            for (int g = 0; g < kTileW / 8; g++)
+            {
+                const uint4 qn = *reinterpret_cast<const uint4 *>(rowp + (g + 1 < kTileW / 8 ? g + 1 : g) * 16);
+                const uint32_t wv[4] = { q.x, q.y, q.z, q.w };
+                int cur[8], out[8];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { cur[2 * i] = (int)(wv[i] & 0xffffu); cur[2 * i + 1] = (int)(wv[i] >> 16); }
+                int d, l;
+                if (s == 1 && g == 0)
+                {
+                    // first column: lowpass(LOAD(0), LOAD(0)) in row 0, the plain sample elsewhere (denoise.c:140-143 vs :152)
+                    out[0] = (row0 + lane == 0) ? cur[0] + lut_at(coef, 0) : cur[0];
+                }
+                else
+                {
+                    d = p - cur[0];
+                    l = lut_at(coef, d);
+                    out[0] = cur[0] + l;
+                }
+                // out[c] = cur[c] + l_c;  the next index needs only l_c + (cur[c] - cur[c+1]): one add between two lookups
+                d = out[0] - cur[1];
+#pragma unroll
+                for (int c = 1; c < 8; c++)
+                {
+                    l = lut_at(coef, d);
+                    out[c] = cur[c] + l;
+                    // (an opaque add: the compiler otherwise re-associates this into out[c] - cur[c+1], two adds on the chain)
+                    if (c < 7) asm("add.s32 %0, %1, %2;" : "=r"(d) : "r"(l), "r"(cur[c] - cur[c + 1]));
+                }
+                p = out[7];
+                uint4 o;
+                o.x = __byte_perm(out[0], out[1], 0x5410); o.y = __byte_perm(out[2], out[3], 0x5410);
+                o.z = __byte_perm(out[4], out[5], 0x5410); o.w = __byte_perm(out[6], out[7], 0x5410);
+                *reinterpret_cast<uint4 *>(rowp + g * 16) = o;
+                q = qn;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// V + T pass: CTA = 128 columns; warps 0-3 = chains (lane = column), warps 4-7 = helpers.  Tiles are 32 rows deep.
+template <typename PIX>
+__global__ void __launch_bounds__(256) hqdn3d_vt2_kernel(const PIX *__restrict__ src, int spitch, const uint16_t *__restrict__ hbuf,
+                                                        uint16_t *__restrict__ ant, int first, PIX *__restrict__ dst, int dpitch,
+                                                        int w, int h, int depth, const int16_t *__restrict__ stable,
+                                                        const int16_t *__restrict__ ttable, int half)
+{
+    extern __shared__ __align__(16) unsigned char smem2[];
+    int16_t *s_lut = reinterpret_cast<int16_t *>(smem2);
+    unsigned char *tiles = smem2 + (size_t)4 * half * sizeof(int16_t);
+    stage_lut(s_lut, stable, 2 * half);
+    stage_lut(s_lut + 2 * half, ttable, 2 * half);
+    __syncthreads();
+    const int16_t *scoef = s_lut + half, *tcoef = s_lut + 3 * half;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * kTileW;
+    const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1;
+    const int ntiles = (h + 31) / 32;
+    int v = 0;
+    for (int s = 0; s < ntiles + 2; s++)
+    {
+        if (warp >= 4)
+        {
+            const int ht = threadIdx.x - 128;             // 0..127
+            // the retiring tile's `ant` and `src` samples first (their latency overlaps the tile load below)
+            uint4 qa[4], qs[4];
+            const int rt0 = (s - 2) * 32;
+            if (s >= 2)
+            {
+#pragma unroll
+                for (int it = 0; it < 4; it++)
+                {
+                    const int r = it * 8 + (ht >> 4), c = (ht & 15) * 8;
+                    const int y = rt0 + r, x = x0 + c;
+                    qa[it] = make_uint4(0, 0, 0, 0); qs[it] = make_uint4(0, 0, 0, 0);
+                    if (y < h && x < w)
+                    {
+                        if (!first) qa[it] = *reinterpret_cast<const uint4 *>(ant + (size_t)y * w + x);
+                        if (sizeof(PIX) == 1)
+                        {
+                            const uint2 t2 = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)y * spitch + x));
+                            qs[it].x = t2.x; qs[it].y = t2.y;
+                        }
+                        else qs[it] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)y * spitch + x));
+                    }
+                }
+            }
+            if (s < ntiles)
+            {
+                unsigned char *buf = tiles + (size_t)(s % 3) * 32 * kTilePitch;
+#pragma unroll
+                for (int it = 0; it < 4; it++)
+                {
+                    const int r = it * 8 + (ht >> 4), c = (ht & 15) * 8;
+                    const int y = s * 32 + r, x = x0 + c;
+                    *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2) =
+                        (y < h && x < w) ? __ldg(reinterpret_cast<const uint4 *>(hbuf + (size_t)y * w + x)) : make_uint4(0, 0, 0, 0);
+                }
+            }
+            if (s >= 2)
+            {
+                const unsigned char *buf = tiles + (size_t)((s - 2) % 3) * 32 * kTilePitch;
+#pragma unroll
+                for (int it = 0; it < 4; it++)
+                {
+                    const int r = it * 8 + (ht >> 4), c = (ht & 15) * 8;
+                    const int y = rt0 + r, x = x0 + c;
+                    if (!(y < h && x < w)) continue;
+                    const uint4 qv = *reinterpret_cast<const uint4 *>(buf + r * kTilePitch + c * 2);
+                    const uint32_t vw[4] = { qv.x, qv.y, qv.z, qv.w }, aw[4] = { qa[it].x, qa[it].y, qa[it].z, qa[it].w },
+                                   sw[4] = { qs[it].x, qs[it].y, qs[it].z, qs[it].w };
+                    uint32_t tw[4], ow[4];
+                    int t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                    {
+                        const int vv = (int)((i & 1) ? (vw[i >> 1] >> 16) : (vw[i >> 1] & 0xffffu));
+                        int a;
+                        if (first)                         // denoise.c:175-189: the state starts as the first frame
+                        {
+                            const int px = sizeof(PIX) == 1 ? (int)((sw[i >> 2] >> (8 * (i & 3))) & 0xffu)
+                                                            : (int)((i & 1) ? (sw[i >> 1] >> 16) : (sw[i >> 1] & 0xffffu));
+                            a = (px << sh) + bias;
+                        }
+                        else a = (int)((i & 1) ? (aw[i >> 1] >> 16) : (aw[i >> 1] & 0xffffu));
+                        t[i] = vv + lut_at(tcoef, a - vv);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) tw[i] = __byte_perm(t[2 * i], t[2 * i + 1], 0x5410);
+                    *reinterpret_cast<uint4 *>(ant + (size_t)y * w + x) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+                    if (sizeof(PIX) == 1)
+                    {
+#pragma unroll
+                        for (int i = 0; i < 2; i++)
+                            ow[i] = (((unsigned)t[4 * i] >> sh) & 0xffu) | ((((unsigned)t[4 * i + 1] >> sh) & 0xffu) << 8)
+                                  | ((((unsigned)t[4 * i + 2] >> sh) & 0xffu) << 16) | ((((unsigned)t[4 * i + 3] >> sh) & 0xffu) << 24);
+                        *reinterpret_cast<uint2 *>(dst + (size_t)y * dpitch + x) = make_uint2(ow[0], ow[1]);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            ow[i] = (((unsigned)t[2 * i] >> sh) & 0xffffu) | ((((unsigned)t[2 * i + 1] >> sh) & 0xffffu) << 16);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)y * dpitch + x) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                }
+            }
+        }
+        else if (s >= 1 && s <= ntiles)
+        {
+            unsigned char *colp = tiles + (size_t)((s - 1) % 3) * 32 * kTilePitch + (warp * 32 + lane) * 2;
+            const int y0 = (s - 1) * 32;
+            int cur[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) cur[r] = *reinterpret_cast<const uint16_t *>(colp + r * kTilePitch);
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+            {
+                if (y0 + r == 0) v = cur[0];
+                else             v = (cur[r] + lut_at(scoef, v - cur[r])) & 0xffff;      // line_ant[] is uint16_t
+                *reinterpret_cast<uint16_t *>(colp + r * kTilePitch) = (uint16_t)v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 struct Geom { int w, h, pitch; size_t bytes; };
 
 }  // namespace
@@ -199,6 +474,21 @@ int launch_plane_t(hbcu_hqdn3d_s *h, int pl, const void *src, void *dst, cudaStr
     const bool smem = h->cfg.depth < 16;
     const size_t lut1 = smem ? (size_t)2 * h->half * sizeof(int16_t) : 0;
     const int depth = h->cfg.depth;
+    // round-2 kernels: tables in shared memory, vector accesses
+    const bool v2 = smem && h->spatial[pl] && g.w % 8 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)
+                 && ((size_t)g.pitch * h->bps) % 16 == 0 && getenv("HBCU_HQDN3D_V1") == nullptr;
+    if (v2)
+    {
+        const size_t tiles = (size_t)3 * 32 * kTilePitch;
+        hqdn3d_h2_kernel<PIX><<<(g.h + 31) / 32, 64, lut1 + tiles, st>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
+        hbcu::count_launch();
+        hqdn3d_vt2_kernel<PIX><<<(g.w + kTileW - 1) / kTileW, 256, 2 * lut1 + tiles, st>>>((const PIX *)src, g.pitch, h->d_h[pl], h->d_ant[pl], h->first[pl],
+                       (PIX *)dst, g.pitch, g.w, g.h, depth, h->d_coef[2 * pl], h->d_coef[2 * pl + 1], h->half);
+        hbcu::count_launch();
+        h->first[pl] = 0;
+        HBCU_CHECK(cudaGetLastError());
+        return 0;
+    }
     if (h->spatial[pl])
     {
         const int hgrid = (g.h + 127) / 128;
@@ -321,6 +611,15 @@ int hbcu_hqdn3d_create(hbcu_hqdn3d_t **out, const hbcu_hqdn3d_config_t *cfg)
         CK(cudaMalloc(&h->d_coef[i], (size_t)2 * h->half * sizeof(int16_t)));
         CK(cudaMemcpy(h->d_coef[i], cfg->coef[i], (size_t)2 * h->half * sizeof(int16_t), cudaMemcpyHostToDevice));
         h->cfg.coef[i] = nullptr;                           // the caller's tables are not kept
+    }
+    if (cfg->depth < 16)
+    {
+        // per device (a second handle on another GPU needs its own opt-in)
+        const int v2smem = 4 * h->half * (int)sizeof(int16_t) + 3 * 32 * kTilePitch;
+        CK(cudaFuncSetAttribute(hqdn3d_vt2_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2smem));
+        CK(cudaFuncSetAttribute(hqdn3d_vt2_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2smem));
+        CK(cudaFuncSetAttribute(hqdn3d_h2_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2smem));
+        CK(cudaFuncSetAttribute(hqdn3d_h2_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2smem));
     }
     if (cfg->depth < 16)
     {

@@ -61,7 +61,7 @@ __device__ __forceinline__ int lap_finish(int acc, int s0, double coef, double s
 
 // one thread = 4 adjacent pixels of one row.  Interior groups read each of their SIZE input rows as three (8-bit) or four
 // (16-bit) aligned 32-bit words through the read-only path and pick the SIZE+3 samples out of them.
-template <typename PIX, typename ACC, int KID>
+template <typename PIX, typename ACC, int KID, bool VEC>
 __device__ __forceinline__ void lap_px4(const LapPlane &p, int max_value, int x0, int y)
 {
     constexpr int SIZE = KID < 2 ? 3 : 5;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void lap_px4(const LapPlane &p, int max_value, int x0
         {
             const PIX *r = src + (size_t)(y + j) * spitch + x0;
             int v[SIZE + 3];                                   // samples x0 + offset_min .. x0 + offset_max + 2
-            if (p.vec)
+            if (VEC)
             {
                 if (sizeof(PIX) == 1)
                 {
@@ -171,20 +171,162 @@ __device__ __forceinline__ void lap_px4(const LapPlane &p, int max_value, int x0
     }
 }
 
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)        // 4 unsigned bytes . 4 signed bytes + c
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// taps k .. k+3 of kernel row j as four signed bytes (every coefficient of the four kernels fits: |c| <= 55)
+template <int KID>
+__host__ __device__ constexpr int lap_tap_word(int j, int k)
+{
+    constexpr int SIZE = KID < 2 ? 3 : 5;
+    constexpr LapTaps K = lap_taps(KID);
+    unsigned w = 0;
+    for (int t = 0; t < 4; t++)
+        if (k + t < SIZE) w |= (unsigned)(K.v[j * SIZE + k + t] & 0xff) << (8 * t);
+    return (int)w;
+}
+
+// Round 2: one thread = 4 adjacent pixels of R consecutive rows.  A thread-tile that lies wholly inside the filtered
+// region reads each of its R + SIZE - 1 input rows ONCE as aligned 32-bit words (round 1 read SIZE rows per output row)
+// and, at 8 bit, feeds them to the byte dot product: the 4-byte window of an output pixel in one input row is a funnel
+// shift of two loaded words and `dp4a` applies that kernel row's taps in one instruction (9 / 25 multiply-adds per pixel
+// become 3 / 5+).  Accumulating in 32 bits and wrapping to ACC once equals the reference's wrap after every tap
+// (lapsharp.c:150-158: modular arithmetic).  Every other tile goes row by row through lap_px4.
+template <typename PIX, typename ACC, int KID, bool VEC, int R>
+__device__ __forceinline__ void lap_tile(const LapPlane &p, int max_value, int x0, int y0)
+{
+    constexpr int SIZE = KID < 2 ? 3 : 5;
+    constexpr int offset_min = -((SIZE - 1) / 2), offset_max = (SIZE + 1) / 2;
+    constexpr int NR = R + SIZE - 1;
+    constexpr LapTaps K = lap_taps(KID);
+    const int width = p.width, height = p.height, spitch = p.spitch;
+    const int stride_border = (spitch - width) / 2;
+    const bool interior = VEC && y0 >= offset_max && y0 + R - 1 <= height - offset_max
+                       && !(x0 < stride_border + offset_max) && !(x0 + 3 > width + stride_border - offset_max) && (x0 + 3 < width);
+    if (!interior)
+    {
+#pragma unroll 1
+        for (int r = 0; r < R; r++)
+            if (y0 + r < height) lap_px4<PIX, ACC, KID, VEC>(p, max_value, x0, y0 + r);
+        return;
+    }
+    const PIX *src = (const PIX *)p.src + (size_t)(y0 + offset_min) * spitch + x0;
+    int acc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[r][i] = 0;
+    if (sizeof(PIX) == 1)
+    {
+        uint32_t centre[R];
+#pragma unroll
+        for (int q = 0; q < NR; q++)                           // input row y0 + offset_min + q
+        {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)q * spitch - 4);
+            const uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2);
+            uint32_t win[4], fifth[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                const int b = 4 + i + offset_min;              // byte index of the window's first sample in (w0, w1, w2)
+                win[i] = b < 4 ? __funnelshift_r(w0, w1, 8 * b) : b == 4 ? w1 : __funnelshift_r(w1, w2, 8 * (b - 4));
+                const int b5 = b + 4;                          // fifth sample of a 5-tap row
+                fifth[i] = b5 < 8 ? (w1 >> (8 * (b5 - 4))) & 0xffu : (w2 >> (8 * (b5 - 8))) & 0xffu;
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                const int j = q - r;                           // kernel row this input row is for output row r
+                if (j < 0 || j >= SIZE) continue;
+                const int tw = j == 0 ? lap_tap_word<KID>(0, 0) : j == 1 ? lap_tap_word<KID>(1, 0) : j == 2 ? lap_tap_word<KID>(2, 0)
+                             : j == 3 ? lap_tap_word<KID>(SIZE > 3 ? 3 : 0, 0) : lap_tap_word<KID>(SIZE > 4 ? 4 : 0, 0);
+                const int c5 = SIZE == 5 ? K.v[j * SIZE + SIZE - 1] : 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    if (tw != 0) acc[r][i] = dp4a_us(win[i], tw, acc[r][i]);
+                    if (c5 != 0) acc[r][i] += c5 * (int)fifth[i];
+                }
+                if (j == -offset_min) centre[r] = w1;
+            }
+        }
+        uint8_t *drow = (uint8_t *)p.dst + (size_t)y0 * p.dpitch + x0;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+        {
+            int o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                o[i] = lap_finish<PIX, ACC>(acc[r][i], (int)((centre[r] >> (8 * i)) & 0xffu), p.coef, p.strength, max_value);
+            *reinterpret_cast<uchar4 *>(drow + (size_t)r * p.dpitch) = make_uchar4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    else
+    {
+        uint32_t centre[R][2];
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+        {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)q * spitch - 2);
+            const uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2), w3 = __ldg(rw + 3);
+            int v[SIZE + 3];                                   // samples x0 + offset_min .. x0 + offset_max + 2
+#pragma unroll
+            for (int t = 0; t < SIZE + 3; t++)
+            {
+                const int b = offset_min + t + 2;
+                const uint32_t w = b < 2 ? w0 : b < 4 ? w1 : b < 6 ? w2 : w3;
+                v[t] = (int)((b & 1) ? (w >> 16) : (w & 0xffffu));
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                const int j = q - r;
+                if (j < 0 || j >= SIZE) continue;
+#pragma unroll
+                for (int k = 0; k < SIZE; k++)
+                {
+                    const int c = K.v[j * SIZE + k];
+                    if (c == 0) continue;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc[r][i] += c * v[i + k];
+                }
+                if (j == -offset_min) { centre[r][0] = w1; centre[r][1] = w2; }
+            }
+        }
+        uint16_t *drow = (uint16_t *)p.dst + (size_t)y0 * p.dpitch + x0;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+        {
+            int o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                const uint32_t w = centre[r][i >> 1];
+                o[i] = lap_finish<PIX, ACC>(acc[r][i], (int)((i & 1) ? (w >> 16) : (w & 0xffffu)), p.coef, p.strength, max_value);
+            }
+            *reinterpret_cast<ushort4 *>(drow + (size_t)r * p.dpitch) = make_ushort4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 // all three planes of a frame in ONE launch (blockIdx.z = plane; the grid is sized for luma, chroma CTAs beyond their plane
 // leave at once): three launches per frame ended in three partial waves
-template <typename PIX, typename ACC>
-__global__ void __launch_bounds__(256) lapsharp_kernel(const __grid_constant__ LapFrame f)
+template <typename PIX, typename ACC, bool VEC, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) lapsharp_kernel(const __grid_constant__ LapFrame f)
 {
     const LapPlane &p = f.pl[blockIdx.z];
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= p.width || y >= p.height) return;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y0 = (blockIdx.y * blockDim.y + threadIdx.y) * R;
+    if (x0 >= p.width || y0 >= p.height) return;
     switch (p.kid)                                   // uniform per CTA
     {
-        case 0:  lap_px4<PIX, ACC, 0>(p, f.max_value, x0, y); break;
-        case 1:  lap_px4<PIX, ACC, 1>(p, f.max_value, x0, y); break;
-        case 2:  lap_px4<PIX, ACC, 2>(p, f.max_value, x0, y); break;
-        default: lap_px4<PIX, ACC, 3>(p, f.max_value, x0, y); break;
+        case 0:  lap_tile<PIX, ACC, 0, VEC, R>(p, f.max_value, x0, y0); break;
+        case 1:  lap_tile<PIX, ACC, 1, VEC, R>(p, f.max_value, x0, y0); break;
+        case 2:  lap_tile<PIX, ACC, 2, VEC, R>(p, f.max_value, x0, y0); break;
+        default: lap_tile<PIX, ACC, 3, VEC, R>(p, f.max_value, x0, y0); break;
     }
 }
 
@@ -240,9 +382,21 @@ int launch_frame(hbcu_lapsharp_s *h, const void *const src[3], const int spitch_
         p.vec = ((uintptr_t)src[pl] % 4 == 0) && (((size_t)spitch_elems[pl] * h->bps) % 4 == 0);
     }
     const Geom &g0 = h->g[0];
-    dim3 blk(32, 8), grid(((g0.w + 3) / 4 + 31) / 32, (g0.h + 7) / 8, 3);
-    if (h->bps == 1) lapsharp_kernel<uint8_t, int16_t><<<grid, blk, 0, h->s_compute>>>(f);
-    else             lapsharp_kernel<uint16_t, int32_t><<<grid, blk, 0, h->s_compute>>>(f);
+    const bool vec = f.pl[0].vec && f.pl[1].vec && f.pl[2].vec;
+    static const int variant = getenv("HBCU_LAP_VARIANT") ? atoi(getenv("HBCU_LAP_VARIANT")) : 0;
+    const int R = !vec ? 4 : variant == 2 ? 2 : variant == 3 ? 8 : 4;
+    dim3 blk(32, 8), grid(((g0.w + 3) / 4 + 31) / 32, (g0.h + 8 * R - 1) / (8 * R), 3);
+#define LAP(PIX, ACC)                                                                                          \
+    do {                                                                                                       \
+        if (!vec)              lapsharp_kernel<PIX, ACC, false, 4, 2><<<grid, blk, 0, h->s_compute>>>(f);     \
+        else if (variant == 1) lapsharp_kernel<PIX, ACC, true, 4, 4><<<grid, blk, 0, h->s_compute>>>(f);      \
+        else if (variant == 2) lapsharp_kernel<PIX, ACC, true, 2, 4><<<grid, blk, 0, h->s_compute>>>(f);      \
+        else if (variant == 3) lapsharp_kernel<PIX, ACC, true, 8, 2><<<grid, blk, 0, h->s_compute>>>(f);      \
+        else                   lapsharp_kernel<PIX, ACC, true, 4, 2><<<grid, blk, 0, h->s_compute>>>(f);      \
+    } while (0)
+    if (h->bps == 1) LAP(uint8_t, int16_t);
+    else             LAP(uint16_t, int32_t);
+#undef LAP
     hbcu::count_launch();
     HBCU_CHECK(cudaGetLastError());
     return 0;
