@@ -185,13 +185,12 @@ __device__ __forceinline__ int lut_at(const int16_t *centre, int d)
 }
 
 template <typename PIX>
-__device__ __forceinline__ void widen_store(unsigned char *dst, const PIX *src, int sh, int bias)
+__device__ __forceinline__ void widen_store(unsigned char *dst, const uint4 q, bool inside, int sh, int bias)
 {
     // 16 (8-bit) or 8 (16-bit) samples -> LOAD()'s 16-bit fixed point (denoise.c:33), stored as 16-byte vectors
-    const uint32_t b2 = (uint32_t)bias * 0x10001u;
+    const uint32_t b2 = inside ? (uint32_t)bias * 0x10001u : 0u;
     if (sizeof(PIX) == 1)
     {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src));
         const uint32_t w[4] = { q.x, q.y, q.z, q.w };
         uint32_t o[8];
 #pragma unroll
@@ -204,10 +203,7 @@ __device__ __forceinline__ void widen_store(unsigned char *dst, const PIX *src, 
         *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(o[4], o[5], o[6], o[7]);
     }
     else
-    {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src));
         *reinterpret_cast<uint4 *>(dst) = make_uint4((q.x << sh) + b2, (q.y << sh) + b2, (q.z << sh) + b2, (q.w << sh) + b2);
-    }
 }
 
 __device__ __forceinline__ void stage_lut(int16_t *dst, const int16_t *__restrict__ table, int entries)
@@ -217,10 +213,12 @@ __device__ __forceinline__ void stage_lut(int16_t *dst, const int16_t *__restric
     for (int i = threadIdx.x; i < entries / 8; i += blockDim.x) d4[i] = __ldg(s4 + i);
 }
 
-// H pass: CTA = 32 rows; warp 0 = chain (lane = row), warp 1 = helper
+// H pass: CTA = 32 rows; warp 0 = chain (lane = row), warps 1-3 = helpers (one helper alone took longer over a tile than
+// the chain: 6 us per 128 columns against 3)
+constexpr int kHHelpers = 3 * 32;
 template <typename PIX>
-__global__ void __launch_bounds__(64) hqdn3d_h2_kernel(const PIX *__restrict__ src, int spitch, uint16_t *__restrict__ hbuf,
-                                                      int w, int h, int depth, const int16_t *__restrict__ table, int half)
+__global__ void __launch_bounds__(32 + kHHelpers, 1) hqdn3d_h2_kernel(const PIX *__restrict__ src, int spitch, uint16_t *__restrict__ hbuf,
+                                                                   int w, int h, int depth, const int16_t *__restrict__ table, int half)
 {
     extern __shared__ __align__(16) unsigned char smem2[];
     int16_t *s_lut = reinterpret_cast<int16_t *>(smem2);
@@ -236,23 +234,25 @@ __global__ void __launch_bounds__(64) hqdn3d_h2_kernel(const PIX *__restrict__ s
     int p = 0;
     for (int s = 0; s < ntiles + 2; s++)
     {
-        if (warp == 1)
+        if (warp >= 1)
         {
-            if (s < ntiles)
+            const int ht = threadIdx.x - 32;
+            constexpr int LPR = kTileW / SPV;             // chunks per row
+            constexpr int NCH = 32 * LPR, IT = (NCH + kHHelpers - 1) / kHHelpers;
+            uint4 q[IT];
+            unsigned ok = 0;
+            if (s < ntiles)                               // all loads of the tile first, then conversion and stores
             {
-                unsigned char *buf = tiles + (size_t)(s % 3) * 32 * kTilePitch;
-                constexpr int LPR = kTileW / SPV;         // lanes per row
 #pragma unroll
-                for (int it = 0; it < 32 * LPR / 32; it++)
+                for (int it = 0; it < IT; it++)
                 {
-                    const int r = (it * 32 + lane) / LPR, c = ((it * 32 + lane) % LPR) * SPV;
+                    const int idx = it * kHHelpers + ht, r = idx / LPR, c = (idx % LPR) * SPV;
                     const int y = row0 + r, x = s * kTileW + c;
-                    // samples outside the plane are zeros: the chain walks over them (results dropped) and must stay inside the table
-                    if (y < h && x < w) widen_store<PIX>(buf + r * kTilePitch + c * 2, src + (size_t)y * spitch + x, sh, bias);
-                    else
+                    q[it] = make_uint4(0, 0, 0, 0);
+                    if (idx < NCH && y < h && x < w)
                     {
-                        *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2) = make_uint4(0, 0, 0, 0);
-                        if (sizeof(PIX) == 1) *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2 + 16) = make_uint4(0, 0, 0, 0);
+                        q[it] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)y * spitch + x));
+                        ok |= 1u << it;
                     }
                 }
             }
@@ -260,12 +260,24 @@ __global__ void __launch_bounds__(64) hqdn3d_h2_kernel(const PIX *__restrict__ s
             {
                 const unsigned char *buf = tiles + (size_t)((s - 2) % 3) * 32 * kTilePitch;
 #pragma unroll
-                for (int it = 0; it < 16; it++)
+                for (int it = 0; it < (32 * 16 + kHHelpers - 1) / kHHelpers; it++)
                 {
-                    const int r = it * 2 + (lane >> 4), c = (lane & 15) * 8;
+                    const int idx = it * kHHelpers + ht, r = idx >> 4, c = (idx & 15) * 8;
                     const int y = row0 + r, x = (s - 2) * kTileW + c;
-                    if (y < h && x < w)
+                    if (idx < 32 * 16 && y < h && x < w)
                         *reinterpret_cast<uint4 *>(hbuf + (size_t)y * w + x) = *reinterpret_cast<const uint4 *>(buf + r * kTilePitch + c * 2);
+                }
+            }
+            if (s < ntiles)
+            {
+                unsigned char *buf = tiles + (size_t)(s % 3) * 32 * kTilePitch;
+#pragma unroll
+                for (int it = 0; it < IT; it++)
+                {
+                    const int idx = it * kHHelpers + ht, r = idx / LPR, c = (idx % LPR) * SPV;
+                    if (idx >= NCH) continue;
+                    // samples outside the plane are zeros: the chain walks over them (results dropped) and must stay inside the table
+                    widen_store<PIX>(buf + r * kTilePitch + c * 2, q[it], (ok >> it) & 1, sh, bias);
                 }
             }
         }
@@ -315,9 +327,10 @@ __global__ void __launch_bounds__(64) hqdn3d_h2_kernel(const PIX *__restrict__ s
     }
 }
 
-// V + T pass: CTA = 128 columns; warps 0-3 = chains (lane = column), warps 4-7 = helpers.  Tiles are 32 rows deep.
+// V + T pass: CTA = 128 columns; warps 0-3 = chains (lane = column), warps 4-11 = helpers (with four, the helpers' share of a
+// tile -- 32 temporal lookups per thread -- took twice as long as the chain).  Tiles are 32 rows deep.
 template <typename PIX>
-__global__ void __launch_bounds__(256) hqdn3d_vt2_kernel(const PIX *__restrict__ src, int spitch, const uint16_t *__restrict__ hbuf,
+__global__ void __launch_bounds__(384, 1) hqdn3d_vt2_kernel(const PIX *__restrict__ src, int spitch, const uint16_t *__restrict__ hbuf,
                                                         uint16_t *__restrict__ ant, int first, PIX *__restrict__ dst, int dpitch,
                                                         int w, int h, int depth, const int16_t *__restrict__ stable,
                                                         const int16_t *__restrict__ ttable, int half)
@@ -338,16 +351,16 @@ __global__ void __launch_bounds__(256) hqdn3d_vt2_kernel(const PIX *__restrict__
     {
         if (warp >= 4)
         {
-            const int ht = threadIdx.x - 128;             // 0..127
+            const int ht = threadIdx.x - 128;             // 0..255
             // the retiring tile's `ant` and `src` samples first (their latency overlaps the tile load below)
-            uint4 qa[4], qs[4];
+            uint4 qa[2], qs[2];
             const int rt0 = (s - 2) * 32;
             if (s >= 2)
             {
 #pragma unroll
-                for (int it = 0; it < 4; it++)
+                for (int it = 0; it < 2; it++)
                 {
-                    const int r = it * 8 + (ht >> 4), c = (ht & 15) * 8;
+                    const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
                     const int y = rt0 + r, x = x0 + c;
                     qa[it] = make_uint4(0, 0, 0, 0); qs[it] = make_uint4(0, 0, 0, 0);
                     if (y < h && x < w)
@@ -366,9 +379,9 @@ __global__ void __launch_bounds__(256) hqdn3d_vt2_kernel(const PIX *__restrict__
             {
                 unsigned char *buf = tiles + (size_t)(s % 3) * 32 * kTilePitch;
 #pragma unroll
-                for (int it = 0; it < 4; it++)
+                for (int it = 0; it < 2; it++)
                 {
-                    const int r = it * 8 + (ht >> 4), c = (ht & 15) * 8;
+                    const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
                     const int y = s * 32 + r, x = x0 + c;
                     *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2) =
                         (y < h && x < w) ? __ldg(reinterpret_cast<const uint4 *>(hbuf + (size_t)y * w + x)) : make_uint4(0, 0, 0, 0);
@@ -378,9 +391,9 @@ __global__ void __launch_bounds__(256) hqdn3d_vt2_kernel(const PIX *__restrict__
             {
                 const unsigned char *buf = tiles + (size_t)((s - 2) % 3) * 32 * kTilePitch;
 #pragma unroll
-                for (int it = 0; it < 4; it++)
+                for (int it = 0; it < 2; it++)
                 {
-                    const int r = it * 8 + (ht >> 4), c = (ht & 15) * 8;
+                    const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
                     const int y = rt0 + r, x = x0 + c;
                     if (!(y < h && x < w)) continue;
                     const uint4 qv = *reinterpret_cast<const uint4 *>(buf + r * kTilePitch + c * 2);
@@ -480,9 +493,9 @@ int launch_plane_t(hbcu_hqdn3d_s *h, int pl, const void *src, void *dst, cudaStr
     if (v2)
     {
         const size_t tiles = (size_t)3 * 32 * kTilePitch;
-        hqdn3d_h2_kernel<PIX><<<(g.h + 31) / 32, 64, lut1 + tiles, st>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
+        hqdn3d_h2_kernel<PIX><<<(g.h + 31) / 32, 32 + kHHelpers, lut1 + tiles, st>>>((const PIX *)src, g.pitch, h->d_h[pl], g.w, g.h, depth, h->d_coef[2 * pl], h->half);
         hbcu::count_launch();
-        hqdn3d_vt2_kernel<PIX><<<(g.w + kTileW - 1) / kTileW, 256, 2 * lut1 + tiles, st>>>((const PIX *)src, g.pitch, h->d_h[pl], h->d_ant[pl], h->first[pl],
+        hqdn3d_vt2_kernel<PIX><<<(g.w + kTileW - 1) / kTileW, 384, 2 * lut1 + tiles, st>>>((const PIX *)src, g.pitch, h->d_h[pl], h->d_ant[pl], h->first[pl],
                        (PIX *)dst, g.pitch, g.w, g.h, depth, h->d_coef[2 * pl], h->d_coef[2 * pl + 1], h->half);
         hbcu::count_launch();
         h->first[pl] = 0;

@@ -14,7 +14,7 @@ __global__ void chain(const int16_t *table, int *out, long long *cyc, int seed)
     for (int i = threadIdx.x; i < 8192; i += blockDim.x) lut[i] = table[i];
     __syncthreads();
     const char *centre = reinterpret_cast<const char *>(lut + 4096);
-    int d = seed + threadIdx.x, acc = 0;
+    int d = 2 * (seed + (int)threadIdx.x), acc = 0;
     const long long t0 = clock64();
 #pragma unroll 16
     for (int i = 0; i < N; i++)
