@@ -254,38 +254,26 @@ __global__ void __launch_bounds__(128) comb_score_kernel(const uint8_t *__restri
 constexpr int kGuard = 4;
 constexpr int kMaskRows = 16;                  // rows a thread marches down in the mask kernel
 
-// the first gate of the decision (comb_detect_template.c:300-312): both vertical neighbours differ from the sample in the
-// same direction by more than the threshold.  Only samples that pass need the previous / next frame at all.
-template <bool GAMMA>
-__device__ __forceinline__ bool comb_spatial(const CombParams &p, int pu1, int pc, int pd1, float gu1, float gc, float gd1)
+template <typename PIX, bool GAMMA>
+__device__ __forceinline__ int comb_px(const PIX *__restrict__ prev, const PIX *__restrict__ next, const float *__restrict__ lut,
+                                       const CombParams &p, size_t i, int pu2, int pu1, int pc, int pd1, int pd2,
+                                       float gu2, float gu1, float gc, float gd1, float gd2)
 {
     if (GAMMA)
     {
         const float up = __fsub_rn(gc, gu1), down = __fsub_rn(gc, gd1);
-        return (up > p.g_athresh && down > p.g_athresh) || (up < -p.g_athresh && down < -p.g_athresh);
-    }
-    const int up = pc - pu1, down = pc - pd1;
-    return (up > p.athresh && down > p.athresh) || (up < -p.athresh && down < -p.athresh);
-}
-
-// the rest for a sample that passed comb_spatial: motion against the previous / next frame (q* / n*: rows y-1, y, y+1
-// of those frames, as samples or as gamma values), then the spatial metric
-template <bool GAMMA>
-__device__ __forceinline__ int comb_rest(const CombParams &p, int pu2, int pu1, int pc, int pd1, int pd2,
-                                         float gu2, float gu1, float gc, float gd1, float gd2,
-                                         int qu1, int qc, int qd1, int nu1, int nc, int nd1,
-                                         float qgu1, float qgc, float qgd1, float ngu1, float ngc, float ngd1)
-{
-    if (GAMMA)
-    {
+        if (!((up > p.g_athresh && down > p.g_athresh) || (up < -p.g_athresh && down < -p.g_athresh))) return 0;
         int motion = 0;
         if (p.g_mthresh > 0)
         {
-            if (fabsf(__fsub_rn(qgc, gc)) > p.g_mthresh && fabsf(__fsub_rn(gu1, ngu1)) > p.g_mthresh &&
-                fabsf(__fsub_rn(gd1, ngd1)) > p.g_mthresh)
+            const float qc = lut[prev[i]], nc = lut[next[i]];
+            const float qu1 = lut[prev[i - p.pitch]], qd1 = lut[prev[i + p.pitch]];
+            const float nu1 = lut[next[i - p.pitch]], nd1 = lut[next[i + p.pitch]];
+            if (fabsf(__fsub_rn(qc, gc)) > p.g_mthresh && fabsf(__fsub_rn(gu1, nu1)) > p.g_mthresh &&
+                fabsf(__fsub_rn(gd1, nd1)) > p.g_mthresh)
                 motion++;
-            if (fabsf(__fsub_rn(ngc, gc)) > p.g_mthresh && fabsf(__fsub_rn(qgu1, gu1)) > p.g_mthresh &&
-                fabsf(__fsub_rn(qgd1, gd1)) > p.g_mthresh)
+            if (fabsf(__fsub_rn(nc, gc)) > p.g_mthresh && fabsf(__fsub_rn(qu1, gu1)) > p.g_mthresh &&
+                fabsf(__fsub_rn(qd1, gd1)) > p.g_mthresh)
                 motion++;
         }
         else
@@ -295,9 +283,14 @@ __device__ __forceinline__ int comb_rest(const CombParams &p, int pu2, int pu1, 
         const float rhs = __fmul_rn(3.0f, __fadd_rn(gu1, gd1));
         return fabsf(__fsub_rn(lhs, rhs)) > p.g_athresh6;
     }
+    const int up = pc - pu1, down = pc - pd1;
+    if (!((up > p.athresh && down > p.athresh) || (up < -p.athresh && down < -p.athresh))) return 0;
     int motion = 0;
     if (p.mthresh > 0)
     {
+        const int qc = prev[i], nc = next[i];
+        const int qu1 = prev[i - p.pitch], qd1 = prev[i + p.pitch];
+        const int nu1 = next[i - p.pitch], nd1 = next[i + p.pitch];
         if (abs(qc - pc) > p.mthresh && abs(pu1 - nu1) > p.mthresh && abs(pd1 - nd1) > p.mthresh) motion++;
         if (abs(nc - pc) > p.mthresh && abs(qu1 - pu1) > p.mthresh && abs(qd1 - pd1) > p.mthresh) motion++;
     }
@@ -311,10 +304,7 @@ __device__ __forceinline__ int comb_rest(const CombParams &p, int pu2, int pu1, 
 }
 
 // one warp = 32 neighbouring columns marching down kMaskRows rows: every luma sample of the current frame is read
-// once (five-row window in registers).  Previous / next frame: a row of them is fetched -- by the whole warp, 64
-// contiguous bytes, once -- when the first sample of the warp that passed the spatial gate asks for it (rows y-1, y, y+1),
-// and then serves the following output rows too.  Round 1 let every passing lane fetch its own six samples per row
-// (95 instructions per pixel on combed content, 8.3 long-scoreboard stalls per issue: profiles/r02_comb_mask_ncu.json).
+// once (five-row window in registers); previous / next frame only where the spatial test already fired
 template <typename PIX, bool GAMMA>
 __global__ void __launch_bounds__(256) comb_mask_bits_kernel(const PIX *__restrict__ prev, const PIX *__restrict__ cur,
                                                             const PIX *__restrict__ next, uint32_t *__restrict__ bits,
@@ -342,41 +332,15 @@ __global__ void __launch_bounds__(256) comb_mask_bits_kernel(const PIX *__restri
 #pragma unroll
     for (int k = 0; k < kMaskRows + 4; k++)
         g[k] = GAMMA ? s_lut[c[k]] : 0.f;
-    // previous / next frame, rows y0 - 1 + k: samples (integer path) or gamma values
-    int q[kMaskRows + 2], n[kMaskRows + 2];
-    float qg[kMaskRows + 2], ng[kMaskRows + 2];
-    unsigned have = 0;                                        // warp uniform
-    const bool motion_test = GAMMA ? p.g_mthresh > 0 : p.mthresh > 0;
-    const PIX *pcol = prev + xc, *ncol = next + xc;
-#pragma unroll
-    for (int k = 0; k < kMaskRows + 2; k++) { q[k] = n[k] = 0; qg[k] = ng[k] = 0.f; }
 #pragma unroll
     for (int r = 0; r < kMaskRows; r++)
     {
         const int y = y0 + r;
         if (y >= p.h) break;                                  // warp uniform
         int m = 0;
-        const bool gate = colok && y >= 2 && y < p.h - 2 && comb_spatial<GAMMA>(p, c[r + 1], c[r + 2], c[r + 3], g[r + 1], g[r + 2], g[r + 3]);
-        if (__any_sync(0xffffffffu, gate))
-        {
-            if (motion_test)
-            {
-#pragma unroll
-                for (int k = r; k <= r + 2; k++)              // rows y - 1, y, y + 1 (inside the picture: 2 <= y < h - 2)
-                {
-                    if (have & (1u << k)) continue;
-                    const size_t off = (size_t)(y0 - 1 + k) * p.pitch;
-                    const int qv = pcol[off], nv = ncol[off];
-                    if (GAMMA) { qg[k] = s_lut[qv]; ng[k] = s_lut[nv]; }
-                    else       { q[k] = qv; n[k] = nv; }
-                    have |= 1u << k;
-                }
-            }
-            if (gate)
-                m = comb_rest<GAMMA>(p, c[r], c[r + 1], c[r + 2], c[r + 3], c[r + 4], g[r], g[r + 1], g[r + 2], g[r + 3], g[r + 4],
-                                     q[r], q[r + 1], q[r + 2], n[r], n[r + 1], n[r + 2],
-                                     qg[r], qg[r + 1], qg[r + 2], ng[r], ng[r + 1], ng[r + 2]);
-        }
+        if (colok && y >= 2 && y < p.h - 2)
+            m = comb_px<PIX, GAMMA>(prev, next, s_lut, p, (size_t)y * p.pitch + x, c[r], c[r + 1], c[r + 2], c[r + 3], c[r + 4],
+                                    g[r], g[r + 1], g[r + 2], g[r + 3], g[r + 4]);
         const uint32_t word = __ballot_sync(0xffffffffu, m != 0);
         if (lane == 0) bits[(size_t)(y + kGuard) * wpitch + 1 + wx] = word;
     }

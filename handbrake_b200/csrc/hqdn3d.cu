@@ -347,34 +347,45 @@ __global__ void __launch_bounds__(384, 1) hqdn3d_vt2_kernel(const PIX *__restric
     const int sh = 16 - depth, bias = ((1 << sh) - 1) >> 1;
     const int ntiles = (h + 31) / 32;
     int v = 0;
+    // helper registers, one step ahead of their use: the H tile that enters the ring next step, and the `ant` / `src`
+    // samples of the tile that retires next step (every global load has a whole step -- a chain over 32 rows -- to land)
+    const int ht = threadIdx.x - 128;                     // helper thread 0..255
+    uint4 qh[2], qa[2], qs[2];
+    auto fetch_h = [&](int t) {
+#pragma unroll
+        for (int it = 0; it < 2; it++)
+        {
+            const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
+            const int y = t * 32 + r, x = x0 + c;
+            // samples outside the plane are zeros: the chain walks over them (results dropped) and must stay inside the table
+            qh[it] = (y < h && x < w) ? __ldg(reinterpret_cast<const uint4 *>(hbuf + (size_t)y * w + x)) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    auto fetch_retiring = [&](int t) {
+#pragma unroll
+        for (int it = 0; it < 2; it++)
+        {
+            const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
+            const int y = t * 32 + r, x = x0 + c;
+            qa[it] = make_uint4(0, 0, 0, 0); qs[it] = make_uint4(0, 0, 0, 0);
+            if (y < h && x < w)
+            {
+                if (!first) qa[it] = *reinterpret_cast<const uint4 *>(ant + (size_t)y * w + x);
+                if (sizeof(PIX) == 1)
+                {
+                    const uint2 t2 = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)y * spitch + x));
+                    qs[it].x = t2.x; qs[it].y = t2.y;
+                }
+                else qs[it] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)y * spitch + x));
+            }
+        }
+    };
+    if (warp >= 4) fetch_h(0);
     for (int s = 0; s < ntiles + 2; s++)
     {
         if (warp >= 4)
         {
-            const int ht = threadIdx.x - 128;             // 0..255
-            // the retiring tile's `ant` and `src` samples first (their latency overlaps the tile load below)
-            uint4 qa[2], qs[2];
             const int rt0 = (s - 2) * 32;
-            if (s >= 2)
-            {
-#pragma unroll
-                for (int it = 0; it < 2; it++)
-                {
-                    const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
-                    const int y = rt0 + r, x = x0 + c;
-                    qa[it] = make_uint4(0, 0, 0, 0); qs[it] = make_uint4(0, 0, 0, 0);
-                    if (y < h && x < w)
-                    {
-                        if (!first) qa[it] = *reinterpret_cast<const uint4 *>(ant + (size_t)y * w + x);
-                        if (sizeof(PIX) == 1)
-                        {
-                            const uint2 t2 = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)y * spitch + x));
-                            qs[it].x = t2.x; qs[it].y = t2.y;
-                        }
-                        else qs[it] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)y * spitch + x));
-                    }
-                }
-            }
             if (s < ntiles)
             {
                 unsigned char *buf = tiles + (size_t)(s % 3) * 32 * kTilePitch;
@@ -382,11 +393,10 @@ __global__ void __launch_bounds__(384, 1) hqdn3d_vt2_kernel(const PIX *__restric
                 for (int it = 0; it < 2; it++)
                 {
                     const int r = it * 16 + (ht >> 4), c = (ht & 15) * 8;
-                    const int y = s * 32 + r, x = x0 + c;
-                    *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2) =
-                        (y < h && x < w) ? __ldg(reinterpret_cast<const uint4 *>(hbuf + (size_t)y * w + x)) : make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(buf + r * kTilePitch + c * 2) = qh[it];
                 }
             }
+            if (s + 1 < ntiles) fetch_h(s + 1);
             if (s >= 2)
             {
                 const unsigned char *buf = tiles + (size_t)((s - 2) % 3) * 32 * kTilePitch;
@@ -435,6 +445,7 @@ __global__ void __launch_bounds__(384, 1) hqdn3d_vt2_kernel(const PIX *__restric
                     }
                 }
             }
+            if (s >= 1 && s <= ntiles) fetch_retiring(s - 1);      // tile s-1 retires in step s+1 (this thread writes its `ant` then)
         }
         else if (s >= 1 && s <= ntiles)
         {

@@ -396,16 +396,17 @@ int launch_frame(hbcu_lapsharp_s *h, const void *const src[3], const int spitch_
     const Geom &g0 = h->g[0];
     const bool vec = f.pl[0].vec && f.pl[1].vec && f.pl[2].vec;
     // 4 rows per thread at 4 CTAs per SM (64 registers) measured best of {2, 4, 8 rows} x {2..6 CTAs}: 47.7k frames/s against
-    // 42.7k at 2 CTAs per SM (profiles/r02_lapsharp_variants.txt).  HBCU_LAP_VARIANT=7: conversion instructions instead of
-    // the exact_i2d arithmetic (A/B).
+    // 42.7k at 2 CTAs per SM (profiles/r02_lapsharp_variants.txt).  HBCU_LAP_VARIANT=8: the exact_i2d arithmetic instead of
+    // the conversion instructions -- measured SLOWER (43.9k against 46.8k on the same box: the two extra DADD and the xor cost
+    // more issue slots than the quarter-rate I2F.F64 costs pipe time), kept for the A/B only.
     static const int variant = getenv("HBCU_LAP_VARIANT") ? atoi(getenv("HBCU_LAP_VARIANT")) : 0;
     constexpr int R = 4;
     dim3 blk(32, 8), grid(((g0.w + 3) / 4 + 31) / 32, (g0.h + 8 * R - 1) / (8 * R), 3);
 #define LAP(PIX, ACC, MB)                                                                                          \
     do {                                                                                                           \
-        if (!vec)              lapsharp_kernel<PIX, ACC, false, R, 2, true><<<grid, blk, 0, h->s_compute>>>(f);   \
-        else if (variant == 7) lapsharp_kernel<PIX, ACC, true, R, MB, false><<<grid, blk, 0, h->s_compute>>>(f);   \
-        else                   lapsharp_kernel<PIX, ACC, true, R, MB, true><<<grid, blk, 0, h->s_compute>>>(f);    \
+        if (!vec)              lapsharp_kernel<PIX, ACC, false, R, 2, false><<<grid, blk, 0, h->s_compute>>>(f);   \
+        else if (variant == 8) lapsharp_kernel<PIX, ACC, true, R, MB, true><<<grid, blk, 0, h->s_compute>>>(f);    \
+        else                   lapsharp_kernel<PIX, ACC, true, R, MB, false><<<grid, blk, 0, h->s_compute>>>(f);   \
     } while (0)
     if (h->bps == 1) LAP(uint8_t, int16_t, 4);
     else             LAP(uint16_t, int32_t, 3);          // 85 registers: the 16-bit tile spills at 64
