@@ -176,7 +176,9 @@ template <typename PIX> __device__ __forceinline__ void load12(const PIX *__rest
 // yadif for the 4 pixels x0..x0+3 of row y, everything read once into registers (same arithmetic as
 // yadif_px, which stays the reference formulation and handles the groups next to the left/right edge).
 // Requires 4 <= x0 and x0 + 8 <= w.
-template <typename PIX>
+// CUBIC / EEDI: fp.mode & HBCU_DECOMB_CUBIC and fp.eedi != nullptr, known per launch -- as run-time values both sides of every
+// `use_cubic` / `eedi` choice were compiled into the pixel loop as predicated code
+template <typename PIX, bool CUBIC, bool EEDI>
 __device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, int *out)
 {
     const PIX *prev = (const PIX *)fp.prev, *cur = (const PIX *)fp.cur, *next = (const PIX *)fp.next;
@@ -185,14 +187,14 @@ __device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, 
     const PIX *prev2 = par ? prev : cur, *next2 = par ? cur : next;
     const int yp = y ? y - 1 : y + 1, yn = y + 1 < h ? y + 1 : y - 1;
     const bool vertical_edge = (y < 3) || (y > h - 4);
-    const bool cubic = (fp.mode & HBCU_DECOMB_CUBIC) != 0;
-    const int margin = cubic ? 3 : 2;
+    constexpr bool cubic = CUBIC;
+    constexpr int margin = cubic ? 3 : 2;
     const int o = y * pitch + x0, op = yp * pitch + x0, on = yn * pitch + x0;
 
     int P[12], N[12], A[12], D[12];                   // cur rows yp, yn, y-3, y+3 over x0-4 .. x0+7
     load12<PIX>(cur + op - 4, P);
     load12<PIX>(cur + on - 4, N);
-    const bool use_cubic = cubic && !vertical_edge && fp.eedi == nullptr;
+    const bool use_cubic = cubic && !vertical_edge && !EEDI;
     if (use_cubic)
     {
         load12<PIX>(cur + o - 3 * pitch - 4, A);
@@ -212,7 +214,7 @@ __device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, 
         load4<PIX>(prev2 + o + 2 * pitch, f2p);
         load4<PIX>(next2 + o + 2 * pitch, f2n);
     }
-    if (fp.eedi != nullptr) load4<PIX>((const PIX *)fp.eedi + y * fp.epitch + x0, ee);
+    if (EEDI) load4<PIX>((const PIX *)fp.eedi + y * fp.epitch + x0, ee);
 
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -225,7 +227,7 @@ __device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, 
         const int td2 = (abs(np_[i] - c) + abs(nn[i] - e)) >> 1;
         int diff = max(max(td0 >> 1, td1), td2);
         int spatial_pred;
-        if (fp.eedi != nullptr)
+        if (EEDI)
         {
             spatial_pred = ee[i];
         }
@@ -278,7 +280,7 @@ __device__ __forceinline__ void yadif_px4(const FieldParams &fp, int x0, int y, 
 // one thread = 4 adjacent pixels of two consecutive output rows (one kept, one rebuilt): every warp carries the same
 // amount of work.  With one row per thread half of the warps (kept rows) retire at once and the SM runs at half its
 // already register-limited occupancy (ncu, profiles/r01h_decomb_ncu.txt: 12.9 % warps active, long-scoreboard bound).
-template <typename PIX>
+template <typename PIX, bool CUBIC, bool EEDI>
 __device__ __forceinline__ void decomb_row4(const FieldParams &fp, int x0, int y)
 {
     const PIX *cur = (const PIX *)fp.cur;
@@ -288,7 +290,7 @@ __device__ __forceinline__ void decomb_row4(const FieldParams &fp, int x0, int y
     if (filtered && fp.mode != HBCU_DECOMB_BLEND && fp.mode != HBCU_DECOMB_CUBIC && (fp.mode & HBCU_DECOMB_YADIF) &&
         x0 >= 4 && x0 + 8 <= fp.w)
     {
-        yadif_px4<PIX>(fp, x0, y, v);
+        yadif_px4<PIX, CUBIC, EEDI>(fp, x0, y, v);
         if (sizeof(PIX) == 1) *reinterpret_cast<uchar4 *>(dst + x0) = make_uchar4(v[0], v[1], v[2], v[3]);
         else                  *reinterpret_cast<ushort4 *>(dst + x0) = make_ushort4(v[0], v[1], v[2], v[3]);
         return;
@@ -322,14 +324,14 @@ __device__ __forceinline__ void decomb_row4(const FieldParams &fp, int x0, int y
     }
 }
 
-template <typename PIX, int MINB>
+template <typename PIX, int MINB, bool CUBIC, bool EEDI>
 __global__ void __launch_bounds__(256, MINB) decomb_field_kernel(FieldParams fp)
 {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
     if (x0 >= fp.w || y0 >= fp.h) return;
-    decomb_row4<PIX>(fp, x0, y0);
-    if (y0 + 1 < fp.h) decomb_row4<PIX>(fp, x0, y0 + 1);
+    decomb_row4<PIX, CUBIC, EEDI>(fp, x0, y0);
+    if (y0 + 1 < fp.h) decomb_row4<PIX, CUBIC, EEDI>(fp, x0, y0 + 1);
 }
 
 template <typename PIX>
@@ -418,20 +420,18 @@ int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64
         fp.w = g.w; fp.h = g.h; fp.pitch = g.pitch; fp.dpitch = g.pitch; fp.epitch = g.pitch;
         fp.mode = frame_mode; fp.parity = parity; fp.tff = tff; fp.maxv = h->maxv;
         dim3 blk(64, 4), grid(((g.w + 3) / 4 + 63) / 64, ((g.h + 1) / 2 + 3) / 4);   // 4 px x 2 rows per thread
-        // resident CTAs per SM the kernel is compiled for (register cap 128 / 85 / 64); HBCU_DECOMB_OCC is a tuning hook
-        static const int occ = getenv("HBCU_DECOMB_OCC") ? atoi(getenv("HBCU_DECOMB_OCC")) : 3;
-        if (h->bps == 1)
-        {
-            if (occ == 4)      decomb_field_kernel<uint8_t, 4><<<grid, blk, 0, h->s_compute>>>(fp);
-            else if (occ == 3) decomb_field_kernel<uint8_t, 3><<<grid, blk, 0, h->s_compute>>>(fp);
-            else               decomb_field_kernel<uint8_t, 2><<<grid, blk, 0, h->s_compute>>>(fp);
-        }
-        else
-        {
-            if (occ == 4)      decomb_field_kernel<uint16_t, 4><<<grid, blk, 0, h->s_compute>>>(fp);
-            else if (occ == 3) decomb_field_kernel<uint16_t, 3><<<grid, blk, 0, h->s_compute>>>(fp);
-            else               decomb_field_kernel<uint16_t, 2><<<grid, blk, 0, h->s_compute>>>(fp);
-        }
+        // 3 resident CTAs per SM (register cap 85) measured best of 2 / 3 / 4 in round 1
+        const bool cub = (frame_mode & HBCU_DECOMB_CUBIC) != 0, ee = fp.eedi != nullptr;
+#define FIELD(PIX)                                                                                          \
+        do {                                                                                                \
+            if (cub && ee)       decomb_field_kernel<PIX, 3, true, true><<<grid, blk, 0, h->s_compute>>>(fp);    \
+            else if (cub)        decomb_field_kernel<PIX, 3, true, false><<<grid, blk, 0, h->s_compute>>>(fp);   \
+            else if (ee)         decomb_field_kernel<PIX, 3, false, true><<<grid, blk, 0, h->s_compute>>>(fp);   \
+            else                 decomb_field_kernel<PIX, 3, false, false><<<grid, blk, 0, h->s_compute>>>(fp);  \
+        } while (0)
+        if (h->bps == 1) FIELD(uint8_t);
+        else             FIELD(uint16_t);
+#undef FIELD
         hbcu::count_launch();
         HBCU_CHECK(cudaGetLastError());
     }
