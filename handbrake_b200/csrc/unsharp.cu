@@ -184,6 +184,8 @@ struct hbcu_unsharp_s
     std::vector<uint8_t *> in_base, out_base;
     std::vector<int64_t> ticket;
     cudaStream_t s_h2d, s_compute, s_d2h;
+    cudaStream_t s_chroma[2];            // the chroma planes run beside luma (forked from / joined to s_compute): their CTAs fill luma's last wave
+    cudaEvent_t ev_fork, ev_join[2];
     std::vector<cudaEvent_t> ev_up, ev_k, ev_down;
     cudaEvent_t ev_mark[2];
     uint32_t coef[3][2 * kMaxSteps + 1];
@@ -208,7 +210,7 @@ int launch_steps(const UnsharpParams &p, int steps, dim3 grid, cudaStream_t st)
     return 0;
 }
 
-int launch_plane(hbcu_unsharp_s *h, int pl, const void *src, void *dst)
+int launch_plane(hbcu_unsharp_s *h, int pl, const void *src, void *dst, cudaStream_t st)
 {
     const Geom &g = h->g[pl];
     const int amount = h->cfg.amount[pl];
@@ -216,8 +218,8 @@ int launch_plane(hbcu_unsharp_s *h, int pl, const void *src, void *dst)
     {
         // hb_image_copy_plane (unsharp.c:113-117)
         dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
-        if (h->bps == 1) plane_copy_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>((const uint8_t *)src, g.pitch, (uint8_t *)dst, g.pitch, g.w, g.h);
-        else             plane_copy_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.pitch, (uint16_t *)dst, g.pitch, g.w, g.h);
+        if (h->bps == 1) plane_copy_kernel<uint8_t><<<grid, blk, 0, st>>>((const uint8_t *)src, g.pitch, (uint8_t *)dst, g.pitch, g.w, g.h);
+        else             plane_copy_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, g.pitch, (uint16_t *)dst, g.pitch, g.w, g.h);
     }
     else
     {
@@ -230,8 +232,8 @@ int launch_plane(hbcu_unsharp_s *h, int pl, const void *src, void *dst)
         p.minv = (int)(int16_t)(h->cfg.smooth ? maxi / 16 : 0);
         memcpy(p.coef, h->coef[pl], sizeof(p.coef));
         dim3 grid((g.w + kTW - 1) / kTW, (g.h + kTH - 1) / kTH);
-        const int rc = h->bps == 1 ? launch_steps<uint8_t>(p, h->cfg.steps[pl], grid, h->s_compute)
-                                   : launch_steps<uint16_t>(p, h->cfg.steps[pl], grid, h->s_compute);
+        const int rc = h->bps == 1 ? launch_steps<uint8_t>(p, h->cfg.steps[pl], grid, st)
+                                   : launch_steps<uint16_t>(p, h->cfg.steps[pl], grid, st);
         if (rc != 0) { set_error("unsharp: steps %d out of range", h->cfg.steps[pl]); return -1; }
     }
     hbcu::count_launch();
@@ -307,6 +309,8 @@ int hbcu_unsharp_create(hbcu_unsharp_t **out, const hbcu_unsharp_config_t *cfg)
     h->slots = cfg->slots >= 2 ? cfg->slots : 4;
     h->next = 0;
     h->s_h2d = h->s_compute = h->s_d2h = nullptr;
+    h->s_chroma[0] = h->s_chroma[1] = nullptr;
+    h->ev_fork = h->ev_join[0] = h->ev_join[1] = nullptr;
     h->ev_mark[0] = h->ev_mark[1] = nullptr;
     for (int pl = 0; pl < 3; pl++)
     {
@@ -338,6 +342,12 @@ int hbcu_unsharp_create(hbcu_unsharp_t **out, const hbcu_unsharp_config_t *cfg)
     } while (0)
     CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++)
+    {
+        CK(cudaStreamCreateWithFlags(&h->s_chroma[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
     CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     h->in_base.assign(h->slots, nullptr);
     h->out_base.assign(h->slots, nullptr);
@@ -377,6 +387,12 @@ void hbcu_unsharp_destroy(hbcu_unsharp_t *h)
     if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    for (int i = 0; i < 2; i++)
+    {
+        if (h->s_chroma[i]) cudaStreamDestroy(h->s_chroma[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
 }
@@ -411,12 +427,17 @@ int hbcu_unsharp_filter_frames(hbcu_unsharp_t *h, int64_t ticket,
     else if (hbcu::frame_begin_read(in_frame, h->s_compute) != 0) return -1;
     HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_down[s], 0));
     if (out_frame && hbcu::frame_begin_write(out_frame, h->s_compute) != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_fork, h->s_compute));
     for (int pl = 0; pl < 3; pl++)
     {
         const void *src = in_frame ? (const void *)in_frame->plane[pl] : (const void *)(h->in_base[s] + h->plane_off[pl]);
         void *dst = out_frame ? (void *)out_frame->plane[pl] : (void *)(h->out_base[s] + h->plane_off[pl]);
-        if (launch_plane(h, pl, src, dst) != 0) return -1;
+        cudaStream_t st = pl == 0 ? h->s_compute : h->s_chroma[pl - 1];
+        if (pl > 0) HBCU_CHECK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+        if (launch_plane(h, pl, src, dst, st) != 0) return -1;
+        if (pl > 0) HBCU_CHECK(cudaEventRecord(h->ev_join[pl - 1], st));
     }
+    for (int i = 0; i < 2; i++) HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_join[i], 0));
     HBCU_CHECK(cudaEventRecord(h->ev_k[s], h->s_compute));
     if (in_frame && hbcu::frame_end_read(in_frame, h->s_compute) != 0) return -1;
     if (out_frame)

@@ -7,7 +7,7 @@ from test_oracle import HQDN3D_CASES
 
 pytestmark = pytest.mark.gpu
 
-FMT = {8: synth.PIX_FMT_YUV420P, 10: synth.PIX_FMT_YUV420P10}
+FMT = {8: synth.PIX_FMT_YUV420P, 10: synth.PIX_FMT_YUV420P10, 12: synth.PIX_FMT_YUV420P12}
 UP, DOWN = "hb_filter_hbcu_upload", "hb_filter_hbcu_download"
 
 
@@ -21,7 +21,10 @@ def same(r, g):
 
 
 @pytest.mark.parametrize("settings", [c[0] for c in HQDN3D_CASES])
-@pytest.mark.parametrize("depth,w,h", [(8, 333, 211), (10, 330, 210)])
+@pytest.mark.parametrize("depth,w,h", [(8, 333, 211), (10, 330, 210),
+                                       # widths the warp-specialised kernels take (multiples of 8; 328: luma only, chroma 164 stays on
+                                       # the round-1 kernels), heights that end inside a 32-row tile, more than one 128-column tile
+                                       (8, 328, 211), (10, 400, 130), (12, 272, 75)])
 def test_hqdn3d(ref, cuda_filters, settings, depth, w, h):
     """ragged sizes (rows and columns that do not fill the 32-sample tiles), a dozen frames of temporal state,
     temporal-only planes, the default chain of strengths"""
@@ -53,3 +56,13 @@ def test_1080p_and_device_chain(ref, cuda_filters):
     same(r, cuda_filters.run(["hb_filter_denoise_cuda", "hb_filter_lapsharp_cuda"], [sd, sl], clip, FMT[8], w, h))
     same(r, cuda_filters.run([UP, "hb_filter_denoise_cuda", "hb_filter_lapsharp_cuda", DOWN], [None, sd, sl, None], clip, FMT[8], w, h))
     assert cuda_filters.buffers_alive() == 0
+
+
+def test_round1_kernels_still_agree(ref, cuda_filters, monkeypatch):
+    """HBCU_HQDN3D_V1=1 forces the one-warp-does-everything kernels (still used for odd widths and 16-bit depth)"""
+    monkeypatch.setenv("HBCU_HQDN3D_V1", "1")
+    w, h = 384, 130
+    for depth in (8, 10):
+        clip = synth.progressive_clip(FMT[depth], w, h, 6, seed=97)
+        same(ref.run("hb_filter_denoise", HQDN3D_CASES[0][0], clip, FMT[depth], w, h),
+             cuda_filters.run("hb_filter_denoise_cuda", HQDN3D_CASES[0][0], clip, FMT[depth], w, h))
