@@ -363,6 +363,8 @@ struct hbcu_decomb_s
     int next_out;
     hbcu::Eedi2 *eedi;                   // EEDI2 state (mask carry-over) + scratch, one per handle
     cudaStream_t s_h2d, s_compute, s_d2h;
+    cudaStream_t s_chroma[2];            // chroma field kernels run beside luma's (forked from / joined to s_compute)
+    cudaEvent_t ev_fork, ev_join[2];
     cudaEvent_t ev_mark[2];
 };
 
@@ -396,8 +398,11 @@ int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64
         const void *planes[3] = { h->in_mem[slot[1] * 3 + 0], h->in_mem[slot[1] * 3 + 1], h->in_mem[slot[1] * 3 + 2] };
         if (hbcu::eedi2_run(h->eedi, planes, !parity, h->s_compute) != 0) return -1;
     }
+    HBCU_CHECK(cudaEventRecord(h->ev_fork, h->s_compute));
     for (int pl = 0; pl < 3; pl++)
     {
+        cudaStream_t st = pl == 0 ? h->s_compute : h->s_chroma[pl - 1];
+        if (pl > 0) HBCU_CHECK(cudaStreamWaitEvent(st, h->ev_fork, 0));
         const Geom &g = h->g[pl];
         uint8_t *dst = ext_dst ? ext_dst[pl] : h->out_mem[oslot * 3 + pl];     // external planes share the reference stride
         if (frame_mode == 0 || (use_eedi && !(frame_mode & HBCU_DECOMB_YADIF)))
@@ -405,10 +410,11 @@ int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64
             // pass-through (hb_buffer_copy) or "just EEDI2": whole-plane copy (decomb template :855-875, :893-896)
             const uint8_t *src = frame_mode == 0 ? h->in_mem[slot[1] * 3 + pl] : (const uint8_t *)hbcu::eedi2_output(h->eedi, pl);
             dim3 blk(64, 4), grid((g.w + 63) / 64, (g.h + 3) / 4);
-            if (h->bps == 1) copy_rows_kernel<uint8_t><<<grid, blk, 0, h->s_compute>>>(src, g.pitch, dst, g.pitch, g.w, g.h);
-            else copy_rows_kernel<uint16_t><<<grid, blk, 0, h->s_compute>>>((const uint16_t *)src, g.pitch, (uint16_t *)dst, g.pitch, g.w, g.h);
+            if (h->bps == 1) copy_rows_kernel<uint8_t><<<grid, blk, 0, st>>>(src, g.pitch, dst, g.pitch, g.w, g.h);
+            else copy_rows_kernel<uint16_t><<<grid, blk, 0, st>>>((const uint16_t *)src, g.pitch, (uint16_t *)dst, g.pitch, g.w, g.h);
             hbcu::count_launch();
             HBCU_CHECK(cudaGetLastError());
+            if (pl > 0) HBCU_CHECK(cudaEventRecord(h->ev_join[pl - 1], st));
             continue;
         }
         FieldParams fp;
@@ -424,17 +430,19 @@ int run_field(hbcu_decomb_s *h, int64_t ticket, int64_t prev, int64_t cur, int64
         const bool cub = (frame_mode & HBCU_DECOMB_CUBIC) != 0, ee = fp.eedi != nullptr;
 #define FIELD(PIX)                                                                                          \
         do {                                                                                                \
-            if (cub && ee)       decomb_field_kernel<PIX, 3, true, true><<<grid, blk, 0, h->s_compute>>>(fp);    \
-            else if (cub)        decomb_field_kernel<PIX, 3, true, false><<<grid, blk, 0, h->s_compute>>>(fp);   \
-            else if (ee)         decomb_field_kernel<PIX, 3, false, true><<<grid, blk, 0, h->s_compute>>>(fp);   \
-            else                 decomb_field_kernel<PIX, 3, false, false><<<grid, blk, 0, h->s_compute>>>(fp);  \
+            if (cub && ee)       decomb_field_kernel<PIX, 3, true, true><<<grid, blk, 0, st>>>(fp);    \
+            else if (cub)        decomb_field_kernel<PIX, 3, true, false><<<grid, blk, 0, st>>>(fp);   \
+            else if (ee)         decomb_field_kernel<PIX, 3, false, true><<<grid, blk, 0, st>>>(fp);   \
+            else                 decomb_field_kernel<PIX, 3, false, false><<<grid, blk, 0, st>>>(fp);  \
         } while (0)
         if (h->bps == 1) FIELD(uint8_t);
         else             FIELD(uint16_t);
 #undef FIELD
         hbcu::count_launch();
         HBCU_CHECK(cudaGetLastError());
+        if (pl > 0) HBCU_CHECK(cudaEventRecord(h->ev_join[pl - 1], st));
     }
+    for (int i = 0; i < 2; i++) HBCU_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_join[i], 0));
     HBCU_CHECK(cudaEventRecord(h->ev_kernel[oslot], h->s_compute));
     // prev leaves the window once the last field of this frame is done; recording after every field is harmless
     HBCU_CHECK(cudaEventRecord(h->ev_readers[slot[0]], h->s_compute));
@@ -480,6 +488,8 @@ int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
     h->next_out = 0;
     h->eedi = nullptr;
     h->s_h2d = h->s_compute = h->s_d2h = nullptr;
+    h->s_chroma[0] = h->s_chroma[1] = nullptr;
+    h->ev_fork = h->ev_join[0] = h->ev_join[1] = nullptr;
     h->ev_mark[0] = h->ev_mark[1] = nullptr;
     for (int pl = 0; pl < 3; pl++)
     {
@@ -504,6 +514,12 @@ int hbcu_decomb_create(hbcu_decomb_t **out, const hbcu_decomb_config_t *cfg)
     } while (0)
     CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++)
+    {
+        CK(cudaStreamCreateWithFlags(&h->s_chroma[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
     CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     h->in_mem.assign(h->slots * 3, nullptr);
     h->in_base.assign(h->slots, nullptr);
@@ -579,6 +595,12 @@ void hbcu_decomb_destroy(hbcu_decomb_t *h)
     if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    for (int i = 0; i < 2; i++)
+    {
+        if (h->s_chroma[i]) cudaStreamDestroy(h->s_chroma[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
 }
