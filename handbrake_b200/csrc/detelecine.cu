@@ -168,9 +168,12 @@ struct hbcu_detelecine_s
     int metric_w, metric_h, metric_len;
     size_t metric_off_bytes;            // junk offset inside the metric plane (:617)
     uint8_t *d_pictures;
+    uint8_t *d_staging;                 // download_begin: the woven picture is parked here, so the picture itself is free at once
     int *d_metrics;                     // [fields][3][metric_len]: diffs, comb, var
     int *d_results, *h_results;
     cudaStream_t s;
+    cudaStream_t s_d2h;                 // hbcu_detelecine_download_begin: the copy out overlaps the next picture's upload and metrics
+    cudaEvent_t ev_woven, ev_d2h;
     cudaEvent_t ev_mark[2];
 };
 
@@ -222,6 +225,9 @@ int hbcu_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_config
     h->cfg = *cfg;
     h->bps = cfg->depth > 8 ? 2 : 1;
     h->d_pictures = nullptr;
+    h->d_staging = nullptr;
+    h->s_d2h = nullptr;
+    h->ev_woven = h->ev_d2h = nullptr;
     h->d_metrics = h->d_results = h->h_results = nullptr;
     h->s = nullptr;
     h->ev_mark[0] = h->ev_mark[1] = nullptr;
@@ -258,10 +264,15 @@ int hbcu_detelecine_create(hbcu_detelecine_t **out, const hbcu_detelecine_config
         }                                                                         \
     } while (0)
     CK(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_woven, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev_mark[0]));
     CK(cudaEventCreate(&h->ev_mark[1]));
     CK(cudaMalloc(&h->d_pictures, h->picture_bytes * cfg->pictures));
     CK(cudaMemset(h->d_pictures, 0, h->picture_bytes * cfg->pictures));
+    CK(cudaMalloc(&h->d_staging, h->picture_bytes));
+    CK(cudaMemset(h->d_staging, 0, h->picture_bytes));
     CK(cudaMalloc(&h->d_metrics, sizeof(int) * 3 * h->metric_len * cfg->fields));
     CK(cudaMemset(h->d_metrics, 0, sizeof(int) * 3 * h->metric_len * cfg->fields));        // calloc, :224-228
     CK(cudaMalloc(&h->d_results, sizeof(int) * 2 * cfg->results));
@@ -278,12 +289,17 @@ void hbcu_detelecine_destroy(hbcu_detelecine_t *h)
     if (h == nullptr) return;
     cudaSetDevice(h->cfg.device);
     if (h->s) cudaStreamSynchronize(h->s);
+    if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
     if (h->d_pictures) cudaFree(h->d_pictures);
+    if (h->d_staging) cudaFree(h->d_staging);
     if (h->d_metrics) cudaFree(h->d_metrics);
     if (h->d_results) cudaFree(h->d_results);
     if (h->h_results) cudaFreeHost(h->h_results);
     if (h->ev_mark[0]) cudaEventDestroy(h->ev_mark[0]);
     if (h->ev_mark[1]) cudaEventDestroy(h->ev_mark[1]);
+    if (h->ev_woven) cudaEventDestroy(h->ev_woven);
+    if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->s) cudaStreamDestroy(h->s);
     delete h;
 }
@@ -398,26 +414,59 @@ int hbcu_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_pi
     return 0;
 }
 
-int hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3])
+static int download_on(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3], bool staged, const char *who)
 {
-    if (h == nullptr || planes == nullptr || strides == nullptr || bad_picture(h, picture)) { set_error("detelecine_download: bad argument"); return -1; }
+    if (h == nullptr || planes == nullptr || strides == nullptr || bad_picture(h, picture)) { set_error("%s: bad argument", who); return -1; }
     HBCU_CHECK(cudaSetDevice(h->cfg.device));
     bool contiguous = true;
     for (int p = 0; p < 3; p++)
     {
-        if (planes[p] == nullptr || strides[p] <= 0) { set_error("detelecine_download: plane %d missing", p); return -1; }
+        if (planes[p] == nullptr || strides[p] <= 0) { set_error("%s: plane %d missing", who, p); return -1; }
         if (strides[p] != h->pl[p].pitch_bytes || (uint8_t *)planes[p] != (uint8_t *)planes[0] + h->pl[p].off) contiguous = false;
     }
+    cudaStream_t st = h->s;
+    const uint8_t *base = picture_plane(h, picture, 0);
+    if (staged)
+    {
+        // park the picture (the previous copy out of the staging buffer must be through), then copy out on the other stream
+        HBCU_CHECK(cudaStreamWaitEvent(h->s, h->ev_d2h, 0));
+        HBCU_CHECK(cudaMemcpyAsync(h->d_staging, base, h->picture_bytes, cudaMemcpyDeviceToDevice, h->s));
+        HBCU_CHECK(cudaEventRecord(h->ev_woven, h->s));
+        HBCU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_woven, 0));
+        st = h->s_d2h;
+        base = h->d_staging;
+    }
     if (contiguous)
-        HBCU_CHECK(cudaMemcpyAsync(planes[0], picture_plane(h, picture, 0), h->picture_bytes, cudaMemcpyDeviceToHost, h->s));
+        HBCU_CHECK(cudaMemcpyAsync(planes[0], base, h->picture_bytes, cudaMemcpyDeviceToHost, st));
     else
         for (int p = 0; p < 3; p++)
         {
             const int row = strides[p] < h->pl[p].pitch_bytes ? strides[p] : h->pl[p].pitch_bytes;
-            HBCU_CHECK(cudaMemcpy2DAsync(planes[p], strides[p], picture_plane(h, picture, p), h->pl[p].pitch_bytes, row, h->pl[p].h,
-                                         cudaMemcpyDeviceToHost, h->s));
+            HBCU_CHECK(cudaMemcpy2DAsync(planes[p], strides[p], base + h->pl[p].off, h->pl[p].pitch_bytes, row, h->pl[p].h,
+                                         cudaMemcpyDeviceToHost, st));
         }
+    return 0;
+}
+
+int hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3])
+{
+    if (download_on(h, picture, planes, strides, false, "detelecine_download") != 0) return -1;
     HBCU_CHECK(cudaStreamSynchronize(h->s));
+    return 0;
+}
+
+int hbcu_detelecine_download_begin(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3])
+{
+    if (download_on(h, picture, planes, strides, true, "detelecine_download_begin") != 0) return -1;
+    HBCU_CHECK(cudaEventRecord(h->ev_d2h, h->s_d2h));
+    return 0;
+}
+
+int hbcu_detelecine_download_end(hbcu_detelecine_t *h)
+{
+    if (h == nullptr) { set_error("detelecine_download_end: null handle"); return -1; }
+    HBCU_CHECK(cudaSetDevice(h->cfg.device));
+    HBCU_CHECK(cudaEventSynchronize(h->ev_d2h));
     return 0;
 }
 

@@ -49,6 +49,8 @@ struct hb_filter_private_s
     int slot_breaks[DT_MAX_FIELDS], slot_affinity[DT_MAX_FIELDS];
     int results[4 * DT_MAX_FIELDS];
     int unsynced;               /* an upload from a host buffer may still be in flight */
+    hb_buffer_t *pending_out;   /* a woven frame whose copy to the host is still running: it leaves with the NEXT call's output
+                                 * (or ahead of EOF), so its PCIe copy overlaps the next picture's upload and metrics */
     int failed;
     int device, device_out;     /* device_out: woven frames leave as HBCU_DEVICE buffers (hw_pix_fmt == AV_PIX_FMT_CUDA) */
     hb_filter_init_t input, output;
@@ -451,19 +453,42 @@ static void detelecine_cuda_close(hb_filter_object_t *filter)
 {
     hb_filter_private_t *pv = filter->private_data;
     if (pv == NULL) return;
+    if (pv->pending_out != NULL)
+    {
+        if (pv->gpu != NULL) hbcu_detelecine_download_end(pv->gpu);
+        hb_buffer_close(&pv->pending_out);
+    }
     if (pv->gpu != NULL) hbcu_detelecine_destroy(pv->gpu);
     free(pv);
     filter->private_data = NULL;
 }
 
-/* the input buffer goes back to its owner when work() returns: no copy out of it may still be running */
-static int leave(hb_filter_private_t *pv, int status)
+/* the frame parked by the previous call, its copy to the host finished; NULL when there is none */
+static hb_buffer_t *take_pending(hb_filter_private_t *pv)
+{
+    hb_buffer_t *out = pv->pending_out;
+    if (out == NULL) return NULL;
+    pv->pending_out = NULL;
+    if (hbcu_detelecine_download_end(pv->gpu) != 0)
+    {
+        hb_error("detelecine(cuda): %s", hbcu_last_error());
+        pv->failed = 1;
+        hb_buffer_close(&out);
+        return NULL;
+    }
+    return out;
+}
+
+/* the input buffer goes back to its owner when work() returns: no copy out of it may still be running.  A call that has
+ * nothing new to show still hands on the frame the previous call parked. */
+static int leave(hb_filter_private_t *pv, int status, hb_buffer_t **buf_out)
 {
     if (pv->unsynced)
     {
         GPU(hbcu_detelecine_fetch(pv->gpu, NULL, 0));
         pv->unsynced = 0;
     }
+    if (buf_out != NULL && !pv->failed && status == HB_FILTER_OK) *buf_out = take_pending(pv);
     return pv->failed ? HB_FILTER_FAILED : status;
 }
 
@@ -474,7 +499,9 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
 
     if (in->s.flags & HB_BUF_FLAG_EOF)
     {
-        *buf_out = in;
+        hb_buffer_t *last = pv->failed ? NULL : take_pending(pv);
+        if (last != NULL) last->next = in;
+        *buf_out = last != NULL ? last : in;
         *buf_in = NULL;
         return HB_FILTER_DONE;
     }
@@ -506,13 +533,16 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
     dt_frame_t *frame = get_frame(pv);
     if (frame == NULL)
     {
-        if (pv->fakecount == 0) return leave(pv, HB_FILTER_OK);          /* nothing to show for this input */
+        if (pv->fakecount == 0) return leave(pv, HB_FILTER_OK, buf_out);  /* nothing to show for this input */
         pv->fakecount--;                                                   /* the queue is still filling: pass through */
-        const int status = leave(pv, HB_FILTER_OK);
+        const int status = leave(pv, HB_FILTER_OK, NULL);
         if (status == HB_FILTER_OK)
         {
+            hb_buffer_t *before = take_pending(pv);                        /* (none while the queue fills; order kept anyway) */
+            if (pv->failed) return HB_FILTER_FAILED;
             *buf_in = NULL;
-            *buf_out = in;
+            if (before != NULL) before->next = in;
+            *buf_out = before != NULL ? before : in;
         }
         return status;
     }
@@ -522,17 +552,17 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
     {
         release_frame(pv, frame);
         frame = get_frame(pv);
-        if (frame == NULL) return leave(pv, HB_FILTER_OK);
+        if (frame == NULL) return leave(pv, HB_FILTER_OK, buf_out);
         if (frame->length < 2)
         {
             release_frame(pv, frame);
-            if (!(in->s.flags & PIC_FLAG_REPEAT_FIRST_FIELD)) return leave(pv, HB_FILTER_OK);
+            if (!(in->s.flags & PIC_FLAG_REPEAT_FIRST_FIELD)) return leave(pv, HB_FILTER_OK, buf_out);
             frame = get_frame(pv);
-            if (frame == NULL) return leave(pv, HB_FILTER_OK);
+            if (frame == NULL) return leave(pv, HB_FILTER_OK, buf_out);
             if (frame->length < 2)
             {
                 release_frame(pv, frame);
-                return leave(pv, HB_FILTER_OK);
+                return leave(pv, HB_FILTER_OK, buf_out);
             }
         }
     }
@@ -542,7 +572,7 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
         hb_error("detelecine(cuda): no free picture to weave a frame in");
         pv->failed = 1;
         release_frame(pv, frame);
-        return leave(pv, HB_FILTER_FAILED);
+        return leave(pv, HB_FILTER_FAILED, NULL);
     }
 
     hb_buffer_t *out = pv->device_out ? hbcu_device_frame_buffer_init(pv->output.pix_fmt, in->f.width, in->f.height, pv->device)
@@ -550,7 +580,7 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
     if (out == NULL)
     {
         release_frame(pv, frame);
-        return leave(pv, HB_FILTER_FAILED);
+        return leave(pv, HB_FILTER_FAILED, NULL);
     }
     out->f.color_prim      = pv->output.color_prim;
     out->f.color_transfer  = pv->output.color_transfer;
@@ -572,8 +602,26 @@ static int detelecine_cuda_work(hb_filter_object_t *filter, hb_buffer_t **buf_in
     {
         void *oplanes[3] = { out->plane[0].data, out->plane[1].data, out->plane[2].data };
         const int ostrides[3] = { out->plane[0].stride, out->plane[1].stride, out->plane[2].stride };
-        GPU(hbcu_detelecine_download(pv->gpu, frame->picture, oplanes, ostrides));
-        pv->unsynced = 0;
+        /* the previous frame's copy has had a whole call to finish; this one's starts now and is collected by the next call */
+        hb_buffer_t *before = take_pending(pv);
+        GPU(hbcu_detelecine_download_begin(pv->gpu, frame->picture, oplanes, ostrides));
+        if (pv->unsynced)
+        {
+            GPU(hbcu_detelecine_fetch(pv->gpu, NULL, 0));               /* the host input buffer goes back to its owner now */
+            pv->unsynced = 0;
+        }
+        release_frame(pv, frame);
+        if (pv->failed)
+        {
+            hbcu_detelecine_download_end(pv->gpu);
+            hb_buffer_close(&out);
+            if (before != NULL) hb_buffer_close(&before);
+            return HB_FILTER_FAILED;
+        }
+        hb_buffer_copy_props(out, in);
+        pv->pending_out = out;
+        *buf_out = before;
+        return HB_FILTER_OK;
     }
     release_frame(pv, frame);
     if (pv->failed)

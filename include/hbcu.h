@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HBCU_ABI_VERSION 5
+#define HBCU_ABI_VERSION 6
 
 /* ------------------------------------------------------------------------- */
 /* runtime                                                                    */
@@ -402,7 +402,7 @@ int  hbcu_hqdn3d_elapsed_ms(hbcu_hqdn3d_t *h, float *ms);
 /* The field-queue state machine (what to compare with what, how long a frame is, which fields make it) is control
  * flow on a handful of integers; it stays on the host (handbrake_b200/libhb/detelecine_cuda.c) and drives these calls.
  * Pictures and the per-field metric arrays never leave the device.  Everything is queued on the handle's stream; only
- * hbcu_detelecine_fetch() and hbcu_detelecine_download() wait. */
+ * hbcu_detelecine_fetch(), hbcu_detelecine_download() and hbcu_detelecine_download_end() wait. */
 typedef struct hbcu_detelecine_config_s
 {
     int width, height, depth;
@@ -441,6 +441,11 @@ int  hbcu_detelecine_fetch(hbcu_detelecine_t *h, int *dst, int nslots);
 int  hbcu_detelecine_copy_field(hbcu_detelecine_t *h, int dst_picture, int src_picture, int parity);
 /* picture -> host planes (plane height x stride bytes each, as the reference's memcpy of size[p], :1250-1252); waits */
 int  hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3]);
+/* the same without the wait: the copy runs on the handle's download stream behind everything queued so far, so it overlaps
+ * the next picture's upload and metrics; _end waits for the most recent _begin.  The caller keeps the picture untouched
+ * (and its host planes alive) until then.  (detelecine.c:1246-1258 is the copy-out this serves.) */
+int  hbcu_detelecine_download_begin(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3]);
+int  hbcu_detelecine_download_end(hbcu_detelecine_t *h);
 /* device-resident chain: the picture arrives in / leaves in an hbcu_frame_t -- a device-to-device copy on
  * the handle's stream, ordered against the frame's producer and readers through its events; nothing waits on the host
  * (the frame twins of upload / download; detelecine.c:1116-1277 is the work() these serve) */

@@ -206,6 +206,37 @@ int oracle_hbcu_detelecine_download(hbcu_detelecine_t *h, int picture, void *con
     return 0;
 }
 
+/* the deferred copy: _begin parks the picture (as the product's staging buffer does), _end delivers it -- the latest the
+ * product's asynchronous copy can land, so a caller that touched the host planes early would be caught */
+static uint8_t *g_staging;
+static size_t g_staging_bytes;
+static struct { hbcu_detelecine_t *h; void *planes[3]; int strides[3]; int armed; } g_pending_copy;
+int oracle_hbcu_detelecine_download_begin(hbcu_detelecine_t *h, int picture, void *const planes[3], const int strides[3])
+{
+    size_t total = 0, off[3];
+    for (int p = 0; p < 3; p++) { off[p] = total; total += (size_t)h->pitch[p] * h->h[p]; }
+    if (g_staging_bytes < total) { free(g_staging); g_staging = malloc(total); g_staging_bytes = total; }
+    for (int p = 0; p < 3; p++) memcpy(g_staging + off[p], plane_of(h, picture, p), (size_t)h->pitch[p] * h->h[p]);
+    g_pending_copy.h = h;
+    for (int p = 0; p < 3; p++) { g_pending_copy.planes[p] = planes[p]; g_pending_copy.strides[p] = strides[p]; }
+    g_pending_copy.armed = 1;
+    return 0;
+}
+int oracle_hbcu_detelecine_download_end(hbcu_detelecine_t *h)
+{
+    if (!g_pending_copy.armed || g_pending_copy.h != h) return 0;
+    size_t off = 0;
+    for (int p = 0; p < 3; p++)
+    {
+        const int row = g_pending_copy.strides[p] < h->pitch[p] ? g_pending_copy.strides[p] : h->pitch[p];
+        for (int y = 0; y < h->h[p]; y++)
+            memcpy((uint8_t *)g_pending_copy.planes[p] + (size_t)y * g_pending_copy.strides[p], g_staging + off + (size_t)y * h->pitch[p], row);
+        off += (size_t)h->pitch[p] * h->h[p];
+    }
+    g_pending_copy.armed = 0;
+    return 0;
+}
+
 /* device frames: see hostlogic_frames.c */
 const void *const *oracle_hostlogic_frame_planes(const hbcu_frame_t *f);
 const int *oracle_hostlogic_frame_strides(const hbcu_frame_t *f);

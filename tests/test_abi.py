@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) > 40
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.hbcu_abi_version() == 5
+    assert lib.hbcu_abi_version() == 6
 
 
 def test_filter_objects_exported_with_reference_ids():
