@@ -346,6 +346,138 @@ __global__ void __launch_bounds__(256) comb_mask_bits_kernel(const PIX *__restri
     }
 }
 
+// the first gate of the decision (comb_detect_template.c:300-312): both vertical neighbours differ from the sample in the
+// same direction by more than the threshold.  Only samples that pass need the previous / next frame at all.
+template <bool GAMMA>
+__device__ __forceinline__ bool comb_spatial(const CombParams &p, int pu1, int pc, int pd1, float gu1, float gc, float gd1)
+{
+    if (GAMMA)
+    {
+        const float up = __fsub_rn(gc, gu1), down = __fsub_rn(gc, gd1);
+        return (up > p.g_athresh && down > p.g_athresh) || (up < -p.g_athresh && down < -p.g_athresh);
+    }
+    const int up = pc - pu1, down = pc - pd1;
+    return (up > p.athresh && down > p.athresh) || (up < -p.athresh && down < -p.athresh);
+}
+
+// the rest for a sample that passed comb_spatial: motion against the previous / next frame (q* / n*: rows y-1, y, y+1
+// of those frames, as samples or as gamma values), then the spatial metric
+template <bool GAMMA>
+__device__ __forceinline__ int comb_rest(const CombParams &p, int pu2, int pu1, int pc, int pd1, int pd2,
+                                         float gu2, float gu1, float gc, float gd1, float gd2,
+                                         int qu1, int qc, int qd1, int nu1, int nc, int nd1,
+                                         float qgu1, float qgc, float qgd1, float ngu1, float ngc, float ngd1)
+{
+    if (GAMMA)
+    {
+        int motion = 0;
+        if (p.g_mthresh > 0)
+        {
+            if (fabsf(__fsub_rn(qgc, gc)) > p.g_mthresh && fabsf(__fsub_rn(gu1, ngu1)) > p.g_mthresh &&
+                fabsf(__fsub_rn(gd1, ngd1)) > p.g_mthresh)
+                motion++;
+            if (fabsf(__fsub_rn(ngc, gc)) > p.g_mthresh && fabsf(__fsub_rn(qgu1, gu1)) > p.g_mthresh &&
+                fabsf(__fsub_rn(qgd1, gd1)) > p.g_mthresh)
+                motion++;
+        }
+        else
+            motion = 1;
+        if (!(motion || p.force)) return 0;
+        const float lhs = __fadd_rn(__fadd_rn(gu2, __fmul_rn(4.0f, gc)), gd2);     // left to right, no contraction
+        const float rhs = __fmul_rn(3.0f, __fadd_rn(gu1, gd1));
+        return fabsf(__fsub_rn(lhs, rhs)) > p.g_athresh6;
+    }
+    int motion = 0;
+    if (p.mthresh > 0)
+    {
+        if (abs(qc - pc) > p.mthresh && abs(pu1 - nu1) > p.mthresh && abs(pd1 - nd1) > p.mthresh) motion++;
+        if (abs(nc - pc) > p.mthresh && abs(qu1 - pu1) > p.mthresh && abs(qd1 - pd1) > p.mthresh) motion++;
+    }
+    else
+        motion = 1;
+    if (!(motion || p.force)) return 0;
+    if (p.spatial_metric == 0) return (abs(pc - pd2) < p.c32min) && (abs(pc - pd1) > p.c32max);
+    if (p.spatial_metric == 1) return (pu1 - pc) * (pd1 - pc) > p.athresh_sq;
+    if (p.spatial_metric == 2) return abs(pu2 + 4 * pc + pd2 - 3 * (pu1 + pd1)) > p.athresh6;
+    return 0;
+}
+
+// Round 2 variant of the mask kernel, three phases instead of a row loop that stalls on its own loads: (1) the spatial gate of
+// all kMaskRows rows from the column segment in registers; (2) every previous / next-frame sample some gated row of this lane
+// needs (rows y-1, y, y+1: consecutive output rows share two of three) issued back to back as predicated loads, then their
+// gamma lookups; (3) the motion tests and the metric, ballots and stores.  Round 1 let each gated row fetch its own six
+// samples inside the row loop: up to 16 exposed DRAM round trips per lane (8.3 long-scoreboard stalls per issue,
+// profiles/r02_comb_mask_ncu.json) and every sample fetched up to three times.
+template <typename PIX, bool GAMMA>
+__global__ void __launch_bounds__(256) comb_mask_bits2_kernel(const PIX *__restrict__ prev, const PIX *__restrict__ cur,
+                                                             const PIX *__restrict__ next, uint32_t *__restrict__ bits,
+                                                             int wpitch, CombParams p)
+{
+    extern __shared__ float s_lut[];
+    if (GAMMA)
+    {
+        for (int i = threadIdx.x; i < p.lut_size; i += blockDim.x) s_lut[i] = p.gamma_lut[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wx = blockIdx.x * 8 + warp;
+    if (wx * 32 >= p.w) return;                               // whole warp
+    const int x = wx * 32 + lane;
+    const bool colok = x < p.w;
+    const int xc = colok ? x : p.w - 1;
+    const int y0 = blockIdx.y * kMaskRows;
+    int c[kMaskRows + 4];
+    float g[kMaskRows + 4];
+#pragma unroll
+    for (int k = 0; k < kMaskRows + 4; k++)
+        c[k] = cur[(size_t)min(max(y0 - 2 + k, 0), p.h - 1) * p.pitch + xc];
+#pragma unroll
+    for (int k = 0; k < kMaskRows + 4; k++)
+        g[k] = GAMMA ? s_lut[c[k]] : 0.f;
+    unsigned gate = 0;
+#pragma unroll
+    for (int r = 0; r < kMaskRows; r++)
+    {
+        const int y = y0 + r;
+        if (colok && y >= 2 && y < p.h - 2 && comb_spatial<GAMMA>(p, c[r + 1], c[r + 2], c[r + 3], g[r + 1], g[r + 2], g[r + 3])) gate |= 1u << r;
+    }
+    // window row k <-> picture row y0 - 1 + k; output row r reads k = r, r + 1, r + 2 (inside the picture: 2 <= y < h - 2)
+    const bool motion_test = GAMMA ? p.g_mthresh > 0 : p.mthresh > 0;
+    const unsigned need = motion_test ? (gate | (gate << 1) | (gate << 2)) : 0u;
+    int q[kMaskRows + 2], n[kMaskRows + 2];
+    float qg[kMaskRows + 2], ng[kMaskRows + 2];
+    const PIX *pcol = prev + (size_t)(y0 - 1) * p.pitch + xc, *ncol = next + (size_t)(y0 - 1) * p.pitch + xc;
+#pragma unroll
+    for (int k = 0; k < kMaskRows + 2; k++)
+    {
+        q[k] = n[k] = 0;
+        if ((need >> k) & 1u)
+        {
+            q[k] = pcol[(size_t)k * p.pitch];
+            n[k] = ncol[(size_t)k * p.pitch];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaskRows + 2; k++)
+    {
+        qg[k] = ng[k] = 0.f;
+        if (GAMMA && ((need >> k) & 1u)) { qg[k] = s_lut[q[k]]; ng[k] = s_lut[n[k]]; }
+    }
+#pragma unroll
+    for (int r = 0; r < kMaskRows; r++)
+    {
+        const int y = y0 + r;
+        if (y >= p.h) break;                                  // warp uniform
+        int m = 0;
+        if ((gate >> r) & 1u)
+            m = comb_rest<GAMMA>(p, c[r], c[r + 1], c[r + 2], c[r + 3], c[r + 4], g[r], g[r + 1], g[r + 2], g[r + 3], g[r + 4],
+                                 q[r], q[r + 1], q[r + 2], n[r], n[r + 1], n[r + 2],
+                                 qg[r], qg[r + 1], qg[r + 2], ng[r], ng[r + 1], ng[r + 2]);
+        const uint32_t word = __ballot_sync(0xffffffffu, m != 0);
+        if (lane == 0) bits[(size_t)(y + kGuard) * wpitch + 1 + wx] = word;
+    }
+}
+
 struct Nb { uint32_t l, c, r; };      // the words of the left / same / right pixel of every bit position
 __device__ __forceinline__ Nb neighbours(const uint32_t *row, int ci, int ncols)
 {
@@ -724,17 +856,26 @@ int hbcu_comb_detect_run(hbcu_comb_detect_t *h, int64_t prev, int64_t cur, int64
             return -1;
         }
         dim3 mgrid((h->nwords + 7) / 8, (c.height + kMaskRows - 1) / kMaskRows);
+        // three-phase kernel by default (37.8 us against 49.2 us for the 4K 10-bit luma plane, profiles/r02_comb_mask2_ncu.json);
+        // HBCU_COMB_MASK=1 selects the round-1 row-loop kernel (A/B, tests)
+        static const int mask_impl = getenv("HBCU_COMB_MASK") ? atoi(getenv("HBCU_COMB_MASK")) : 2;
+#define MASK(K, PIX, A, B, D)                                                                                               \
+        do {                                                                                                                \
+            if (gamma) K<PIX, true><<<mgrid, 256, lut_bytes, h->s_compute>>>(A, B, D, h->d_bits, h->wpitch, p);           \
+            else       K<PIX, false><<<mgrid, 256, 0, h->s_compute>>>(A, B, D, h->d_bits, h->wpitch, p);                  \
+        } while (0)
         if (h->bps == 1)
         {
-            if (gamma) comb_mask_bits_kernel<uint8_t, true><<<mgrid, 256, lut_bytes, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_bits, h->wpitch, p);
-            else       comb_mask_bits_kernel<uint8_t, false><<<mgrid, 256, 0, h->s_compute>>>(pl[0], pl[1], pl[2], h->d_bits, h->wpitch, p);
+            if (mask_impl == 2) MASK(comb_mask_bits2_kernel, uint8_t, pl[0], pl[1], pl[2]);
+            else                MASK(comb_mask_bits_kernel, uint8_t, pl[0], pl[1], pl[2]);
         }
         else
         {
             const uint16_t *a = (const uint16_t *)pl[0], *b = (const uint16_t *)pl[1], *d = (const uint16_t *)pl[2];
-            if (gamma) comb_mask_bits_kernel<uint16_t, true><<<mgrid, 256, lut_bytes, h->s_compute>>>(a, b, d, h->d_bits, h->wpitch, p);
-            else       comb_mask_bits_kernel<uint16_t, false><<<mgrid, 256, 0, h->s_compute>>>(a, b, d, h->d_bits, h->wpitch, p);
+            if (mask_impl == 2) MASK(comb_mask_bits2_kernel, uint16_t, a, b, d);
+            else                MASK(comb_mask_bits_kernel, uint16_t, a, b, d);
         }
+#undef MASK
         hbcu::count_launch();
         HBCU_CHECK(cudaGetLastError());
         const bool filtered = (c.mode & 2) != 0;

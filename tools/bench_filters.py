@@ -8,6 +8,7 @@ usage: python tools/bench_filters.py [--frames 48] [--cpu-frames 6] [--only NAME
 import argparse
 import ctypes as C
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -235,9 +236,10 @@ def main():
 
     def comb_job():
         depth = 10; fmt = fmt_of(depth)
-        host = np.stack([synth.interlaced_frame(fmt, W, H, t) for t in range(4)])
+        progressive = os.environ.get("HBCU_BENCH_COMB_PROGRESSIVE") == "1"       # content that rarely passes the spatial gate
+        host = np.stack([(synth.progressive_frame(fmt, W, H, t, noise=2) if progressive else synth.interlaced_frame(fmt, W, H, t)) for t in range(4)])
         core.hbcu_host_reserve(synth.frame_bytes(fmt, W, H) + 4096, 3 * n + 24)
-        r = {"workload": "4k10_comb_detect", "desc": "3840x2160 yuv420p10, comb_detect preset default"}
+        r = {"workload": "4k10_comb_detect", "desc": "3840x2160 yuv420p10, comb_detect preset default" + (" (progressive content)" if progressive else " (interlaced content)")}
         # kernel-only: luma planes resident in HBM, verdict per frame
         sys.path.insert(0, str(REPO / "tests"))
         from test_comb_detect_gpu import CombConfig
